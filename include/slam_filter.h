@@ -1,0 +1,169 @@
+/*
+ * slam_filter.h -- C-ABI of the B200-native EKF-SLAM / UKF-SLAM filter hot path.
+ *
+ * Drop-in boundary for the abstract `Filter` plugin of kevin-robb/live_ekf_slam
+ * (ekf_ws/src/localization_pkg/include/localization_pkg/filter.h:54-145) and for the simulator's
+ * measurement generator (ekf_ws/src/base_pkg/src/sim_node.py:209-250).  Plain pointers and sizes only;
+ * no exceptions cross this boundary (every call returns 0 on success, non-zero on error, and
+ * slam_last_error() explains).  Every entry point launches hand-written sm_100a CUDA kernels;
+ * there is no CPU fallback.
+ *
+ * A handle owns `batch` independent filter instances (Monte-Carlo runs).  batch == 1 is the
+ * reference's single filter.  A handle is NOT thread-safe (the reference's filter is driven by a
+ * single-threaded ros::spin(), localization_node.cpp:197); each handle owns one CUDA stream, calls are
+ * asynchronous on it and getters synchronise.
+ *
+ * Reference paths cited below are relative to ekf_ws/src/.
+ */
+#ifndef SLAM_FILTER_H
+#define SLAM_FILTER_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* FilterChoice, localization_pkg/include/localization_pkg/filter.h:44-51 (same numeric values) */
+#define SLAM_EKF_SLAM 1
+#define SLAM_UKF_SLAM 3
+
+/* per-instance status bits (replace the reference's uncaught std::runtime_error / eigen_assert, filter.h:5) */
+#define SLAM_STATUS_NAN               1  /* state or covariance became non-finite                               */
+#define SLAM_STATUS_SAME_STEP_REMATCH 2  /* unknown-ID EKF matched a landmark inserted in the same step; the     */
+                                         /* reference indexes x_t out of range there (ekf.cpp:115) and dies      */
+#define SLAM_STATUS_CAPACITY          4  /* an insertion was dropped: max_landmarks reached                      */
+#define SLAM_STATUS_MEAS_OVERFLOW     8  /* a step delivered more than max_meas measurements (extra ones dropped)*/
+
+/* What Filter::readCommonParams reads from params.yaml (filter.h:105-121) plus the simulator's
+ * constraints (base_pkg/config/params.yaml:27-32).  yaml values go in unchanged; with
+ * compat_noise_bug != 0 the library reproduces filter.h:116-117 (V <- sensing covs, W = I). */
+typedef struct slam_params {
+    float  v_d, v_th;               /* process_noise.mean.{v_d,v_th}          filter.h:108-109 */
+    float  w_r, w_b;                /* sensing_noise.mean.{w_r,w_b}           filter.h:114-115 */
+    double V_00, V_11;              /* process_noise.cov.{V_00,V_11}          filter.h:110-111 */
+    double W_00, W_11;              /* sensing_noise.cov.{W_00,W_11}          filter.h:116-117 */
+    int    landmark_id_is_known;    /* constraints.measurements.*             filter.h:119     */
+    float  min_landmark_separation; /*                                        filter.h:120     */
+    int    compat_noise_bug;        /* 1 (default of the shims) = reference behaviour          */
+    double d_max, th_max;           /* constraints.commands   (simulator)     sim_node.py:219-220 */
+    double range_max, fov_min, fov_max; /* constraints.vision (simulator)     sim_node.py:239-241 */
+} slam_params;
+
+typedef struct slam_filter* slam_handle_t;
+typedef struct slam_sim*    slam_sim_t;
+
+/* ---- construction: replaces `filter = std::make_unique<EKF|UKF>(); filter->readParams(config)`
+ *      (localization_pkg/src/localization_node.cpp:33-47, ekf.cpp:4-27, ukf.cpp:3-29).
+ *      kind: SLAM_EKF_SLAM | SLAM_UKF_SLAM.  max_landmarks bounds M; max_meas bounds detections/step. */
+int  slam_create(int kind, const slam_params* params, int batch, int max_landmarks, int max_meas,
+                 int device, slam_handle_t* out);
+int  slam_destroy(slam_handle_t h);
+const char* slam_last_error(slam_handle_t h);          /* h may be NULL: error of the last failed create */
+void* slam_stream(slam_handle_t h);                    /* the handle's cudaStream_t */
+int  slam_synchronize(slam_handle_t h);
+int  slam_batch(slam_handle_t h);
+int  slam_kind(slam_handle_t h);
+
+/* ---- Filter::init(float x_0, float y_0, float yaw_0)  (filter.h:60, ekf.cpp:29-34, ukf.cpp:31-45).
+ *      Every instance of the batch gets the same start pose and is reset to timestep 0, M = 0. */
+int  slam_init(slam_handle_t h, float x_0, float y_0, float yaw_0);
+
+/* ---- Filter::update(Command cmdMsg, Float32MultiArray lmMeasMsg)  (filter.h:61, ekf.cpp:37-179,
+ *      ukf.cpp:161-195): one fused predict+update per instance.
+ *      fwd/ang: Command.msg:3-5 float32; cmd_stride 0 = one command shared by the batch, 1 = per instance.
+ *      meas: float32 [batch][max_meas][3] = [id, range, bearing]* exactly as on /landmark
+ *      (sim_node.py:245-250); n_meas[batch] = detections per instance (lm_meas.size()/3, ekf.cpp:65).
+ *      slam_step takes HOST pointers (copied on the handle's stream); *_device takes DEVICE pointers. */
+int  slam_step(slam_handle_t h, const float* fwd, const float* ang, int cmd_stride,
+               const float* meas, const int* n_meas);
+int  slam_step_device(slam_handle_t h, const float* d_fwd, const float* d_ang, int cmd_stride,
+                      const float* d_meas, const int* d_n_meas);
+
+/* ---- split form asked for by the north star: predict from the commanded motion, then update from the
+ *      measurements.  predict == ekf.cpp:43-61 followed by the early-return commit of :67-71;
+ *      update == ekf.cpp:73-177 with the landmark means snapshotted at entry (SURVEY B-3).  EKF only:
+ *      the UKF's update stage consumes the propagated sigma points of the same call (ukf.cpp:305-337). */
+int  slam_predict(slam_handle_t h, const float* fwd, const float* ang, int cmd_stride);
+int  slam_update(slam_handle_t h, const float* meas, const int* n_meas);
+int  slam_predict_device(slam_handle_t h, const float* d_fwd, const float* d_ang, int cmd_stride);
+int  slam_update_device(slam_handle_t h, const float* d_meas, const int* d_n_meas);
+
+/* ---- getters: replace getStateVector() (filter.h:76, ekf.cpp:182-185, ukf.cpp:47-53) and the fields
+ *      publishState() serialises (ekf.cpp:192-220, ukf.cpp:60-104).  FP64 out; the shim down-casts to the
+ *      float32 wire types.  All synchronise the handle's stream. */
+int  slam_get_timestep(slam_handle_t h, int inst, int* timestep);
+int  slam_get_num_landmarks(slam_handle_t h, int inst, int* M);
+int  slam_get_status(slam_handle_t h, int inst, int* status);
+int  slam_get_state(slam_handle_t h, int inst, double* x, int* n);          /* raw x_t: EKF 3+2M, UKF 4+2M */
+int  slam_get_state_vector(slam_handle_t h, int inst, double* xv, int* n);  /* (x,y,yaw,lm...) = 3+2M      */
+int  slam_get_cov(slam_handle_t h, int inst, double* P_rowmajor, int* n);   /* n*n row-major (ekf.cpp:211-217) */
+int  slam_get_landmark_ids(slam_handle_t h, int inst, int* ids, int* M);    /* lm_IDs, filter.h:70 */
+int  slam_get_assoc(slam_handle_t h, int inst, int* slot, int* k);          /* last step: slot index or -1 (new) per measurement */
+int  slam_get_sigma_points(slam_handle_t h, int inst, double* X, int* n);   /* UKF X, point-major (ukf.cpp:91-99) */
+int  slam_get_poses(slam_handle_t h, double* xyyaw);                        /* [batch][3] vehicle pose estimates */
+int  slam_get_all_status(slam_handle_t h, int* status);                     /* [batch] */
+int  slam_get_all_num_landmarks(slam_handle_t h, int* M);                   /* [batch] */
+/* teacher forcing (tests): overwrite the committed state of one instance */
+int  slam_set_state(slam_handle_t h, int inst, const double* x, const double* P_rowmajor,
+                    const int* ids, int M, int timestep);
+
+/* ---- workload source: the simulator's measurement generator, base_pkg/src/sim_node.py:209-250
+ *      (get_cmd: noisy clamped command -> truth propagation -> range/FOV visibility -> noisy float32
+ *      [id,r,b]).  One simulated vehicle per filter instance, all on the shared landmark map lm_xy
+ *      [n_lm][2].  Noise: Philox4x32-10 keyed (seed; instance_offset+i, step, channel), uniform +-cov
+ *      exactly like sim_node.py:216-217,247-248.  Bound to the filter handle's stream and batch. */
+int  slam_sim_create(slam_handle_t h, const double* lm_xy, int n_lm, uint64_t seed,
+                     uint32_t instance_offset, slam_sim_t* out);
+int  slam_sim_destroy(slam_sim_t s);
+int  slam_sim_reset(slam_sim_t s, double x_0, double y_0, double yaw_0);
+/* one get_cmd() for every vehicle; commands are HOST (slam_sim_step) or DEVICE (…_device) float32.
+ * Results stay on the device: slam_sim_meas()/slam_sim_n_meas() return the DEVICE buffers
+ * ([batch][max_meas][3] float32, [batch] int32) that slam_step_device consumes. */
+int  slam_sim_step(slam_sim_t s, const float* fwd, const float* ang, int cmd_stride, uint32_t step);
+int  slam_sim_step_device(slam_sim_t s, const float* d_fwd, const float* d_ang, int cmd_stride, uint32_t step);
+const float* slam_sim_meas(slam_sim_t s);
+const int*   slam_sim_n_meas(slam_sim_t s);
+int  slam_sim_get_truth(slam_sim_t s, double* xyyaw);                       /* [batch][3] to host */
+int  slam_sim_get_meas(slam_sim_t s, float* meas, int* n_meas);             /* copy last step's messages to host */
+
+/* ---- Monte-Carlo sweep: T reference steps for every instance in ONE launch sequence, the simulator
+ *      feeding the filter on the device (sim_node.py:143-152 publishes cmd t, get_cmd produces meas t,
+ *      localization_node.cpp:108-131 consumes both).  cmd_fwd/cmd_ang: HOST float32 [T] shared trajectory
+ *      (cmd_stride 0) or [T][batch] (cmd_stride 1).  first_step numbers the Philox step counter.
+ *      Error statistics against the simulator's truth are accumulated per instance (see slam_get_stats). */
+int  slam_run(slam_handle_t h, slam_sim_t s, const float* cmd_fwd, const float* cmd_ang, int cmd_stride,
+              int T, uint32_t first_step);
+/* same with the command trajectory already resident in HBM (DEVICE pointers) */
+int  slam_run_device(slam_handle_t h, slam_sim_t s, const float* d_cmd_fwd, const float* d_cmd_ang, int cmd_stride,
+                     int T, uint32_t first_step);
+/* Filter::init executed on the device (no host staging, asynchronous): used between Monte-Carlo sweeps */
+int  slam_reset(slam_handle_t h, float x_0, float y_0, float yaw_0);
+/* Filter::update + the pose read-back of publishState in one asynchronous call: HOST buffers in, HOST poses
+ * [batch][3] out (pinned memory makes both copies truly asynchronous); the caller synchronises. */
+int  slam_step_io(slam_handle_t h, const float* fwd, const float* ang, int cmd_stride,
+                  const float* meas, const int* n_meas, double* poses_out);
+
+/* ---- accuracy statistics accumulated by slam_run / slam_accumulate_error, summed over the batch:
+ *      out[0]=count, [1]=sum ex^2, [2]=sum ey^2, [3]=sum eyaw^2 (wrapped), [4]=sum sqrt(ex^2+ey^2)
+ *      (the reference's only metric, plotting_node.py:212-214), [5]=sum 3-dof pose NEES (extension),
+ *      [6]=instances with non-zero status, [7]=sum of M; work counters kept by the step kernels:
+ *      [8]=sum of algorithmic HBM bytes (16 n^2 + 16 n + 12 (k+j) + 8 per update), [9]=sum of
+ *      algorithmic flops (EKF 4 k n^2; UKF 9n^3+2n^3+2n^2(2n+1)+12kn^2), [10]=sum of n, [11]=sum of k+j.
+ *      Ranks all-reduce this vector (SUM). */
+#define SLAM_NUM_STATS 12
+int  slam_accumulate_error(slam_handle_t h, slam_sim_t s);
+int  slam_get_stats(slam_handle_t h, double* out /* SLAM_NUM_STATS */);
+int  slam_reset_stats(slam_handle_t h);
+
+/* ---- introspection for the benchmark harness */
+long long slam_kernel_launches(slam_handle_t h);      /* kernels launched by this handle so far */
+/* per-launch device timing of the filter-step kernel (CUDA events on the handle's stream) */
+int  slam_set_profiling(slam_handle_t h, int on);
+int  slam_get_profile(slam_handle_t h, double* total_ms, long long* launches);  /* synchronises; resets the pool */
+int  slam_build_info(char* buf, int cap);             /* arch, compile flags */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLAM_FILTER_H */

@@ -1,0 +1,564 @@
+// capi.cu -- the C-ABI of include/slam_filter.h: handle lifetime, host<->device staging and kernel launches.
+// No compute happens on the host; every entry point that advances a filter launches sm_100a kernels.
+#include "common.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace slam;
+
+static thread_local std::string g_create_error;
+
+struct slam_filter {
+    int kind = 0;
+    int device = 0;
+    slam_params params{};
+    FilterConst fc{};
+    SimConst sc{};
+    BatchState b{};
+    cudaStream_t stream = nullptr;
+    // staging for host-pointer entry points
+    float* d_fwd = nullptr; float* d_ang = nullptr; float* d_meas = nullptr; int* d_nmeas = nullptr;
+    float* d_traj_fwd = nullptr; float* d_traj_ang = nullptr; size_t traj_cap = 0;
+    double* d_out = nullptr;      // scratch for stats / poses
+    size_t d_out_cap = 0;
+    long long launches = 0;
+    // per-launch timing of the filter-step kernel
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev;      // pairs
+    size_t ev_used = 0;
+    std::string err;
+};
+
+struct slam_sim {
+    slam_filter* owner = nullptr;
+    SimState s{};
+    double* d_lm = nullptr;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            if (h) h->err = buf_; else g_create_error = buf_;                                      \
+            return 1;                                                                              \
+        }                                                                                          \
+    } while (0)
+
+static int fail(slam_filter* h, const char* msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return 1;
+}
+
+extern "C" {
+
+const char* slam_last_error(slam_handle_t h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int slam_create(int kind, const slam_params* params, int batch, int max_landmarks, int max_meas, int device,
+                slam_handle_t* out) {
+    slam_filter* h = nullptr;
+    if (!out) return fail(h, "slam_create: out is NULL");
+    *out = nullptr;
+    if (kind != SLAM_EKF_SLAM && kind != SLAM_UKF_SLAM)
+        return fail(h, "Invalid filter choice (expected SLAM_EKF_SLAM or SLAM_UKF_SLAM).");   // localization_node.cpp:44
+    if (!params) return fail(h, "slam_create: params is NULL");
+    if (batch < 1 || max_landmarks < 1 || max_meas < 1) return fail(h, "slam_create: batch, max_landmarks and max_meas must be >= 1");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) return fail(h, "slam_create: no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(h, "slam_create: bad device ordinal");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(h, "slam_create: kernels are built for sm_100a (B200) only");
+
+    h = new slam_filter();
+    h->kind = kind; h->device = device; h->params = *params;
+    // Filter::readCommonParams, filter.h:105-121 (the V/W mix-up is reproduced when compat_noise_bug != 0)
+    FilterConst& fc = h->fc;
+    fc.V00 = params->V_00; fc.V11 = params->V_11; fc.W00 = 1.0; fc.W11 = 1.0;
+    if (params->compat_noise_bug) { fc.V00 = params->W_00; fc.V11 = params->W_11; }
+    else { fc.W00 = params->W_00; fc.W11 = params->W_11; }
+    fc.v_d = params->v_d; fc.v_th = params->v_th; fc.w_r = params->w_r; fc.w_b = params->w_b;
+    fc.min_sep = params->min_landmark_separation; fc.id_known = params->landmark_id_is_known;
+    SimConst& sc = h->sc;
+    sc.V_00 = params->V_00; sc.V_11 = params->V_11; sc.W_00 = params->W_00; sc.W_11 = params->W_11;
+    sc.d_max = params->d_max; sc.th_max = params->th_max; sc.range_max = params->range_max;
+    sc.fov_min = params->fov_min; sc.fov_max = params->fov_max;
+
+    BatchState& b = h->b;
+    b.batch = batch; b.max_lm = max_landmarks; b.max_meas = max_meas;
+    b.base = (kind == SLAM_EKF_SLAM) ? 3 : 4;
+    b.n_max = b.base + 2 * max_landmarks;
+    b.lds = lds_of(b.n_max);
+    b.x_stride = ldg_of(b.n_max);
+    b.p_stride = (long long)b.n_max * ldg_of(b.n_max);
+    b.sigma_stride = 0;
+
+    const size_t smem = (kind == SLAM_EKF_SLAM) ? ekf_step_smem_bytes(b) : ukf_step_smem_bytes(b);
+    if (smem > (size_t)prop.sharedMemPerBlockOptin) {
+        delete h; h = nullptr;
+        return fail(h, "slam_create: max_landmarks too large for the shared-memory-resident batch kernels");
+    }
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&b.P, sizeof(double) * (size_t)batch * b.p_stride));
+    CK(cudaMalloc(&b.x, sizeof(double) * (size_t)batch * b.x_stride));
+    CK(cudaMalloc(&b.ids, sizeof(int) * (size_t)batch * b.max_lm));
+    CK(cudaMalloc(&b.M, sizeof(int) * batch));
+    CK(cudaMalloc(&b.timestep, sizeof(int) * batch));
+    CK(cudaMalloc(&b.status, sizeof(int) * batch));
+    CK(cudaMalloc(&b.assoc, sizeof(int) * (size_t)batch * b.max_meas));
+    CK(cudaMalloc(&b.n_assoc, sizeof(int) * batch));
+    CK(cudaMalloc(&b.stats, sizeof(double) * (size_t)batch * SLAM_NUM_STATS));
+    if (kind == SLAM_UKF_SLAM) {
+        b.sigma_stride = (long long)b.n_max * (2 * b.n_max + 1);
+        b.sigma = nullptr;   // allocated lazily by slam_get_sigma_points
+    }
+    CK(cudaMalloc(&h->d_fwd, sizeof(float) * batch));
+    CK(cudaMalloc(&h->d_ang, sizeof(float) * batch));
+    CK(cudaMalloc(&h->d_meas, sizeof(float) * 3 * (size_t)batch * max_meas));
+    CK(cudaMalloc(&h->d_nmeas, sizeof(int) * batch));
+    h->d_out_cap = sizeof(double) * (size_t)(3 * batch + SLAM_NUM_STATS);
+    CK(cudaMalloc(&h->d_out, h->d_out_cap));
+    if (kind == SLAM_EKF_SLAM) CK(ekf_step_configure(b)); else CK(ukf_step_configure(b));
+    *out = h;
+    return slam_init(h, 0.f, 0.f, 0.f);
+}
+
+int slam_destroy(slam_handle_t h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    BatchState& b = h->b;
+    cudaFree(b.P); cudaFree(b.x); cudaFree(b.ids); cudaFree(b.M); cudaFree(b.timestep); cudaFree(b.status);
+    cudaFree(b.assoc); cudaFree(b.n_assoc); cudaFree(b.stats); cudaFree(b.sigma);
+    cudaFree(h->d_fwd); cudaFree(h->d_ang); cudaFree(h->d_meas); cudaFree(h->d_nmeas);
+    cudaFree(h->d_traj_fwd); cudaFree(h->d_traj_ang); cudaFree(h->d_out);
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+void* slam_stream(slam_handle_t h) { return h ? (void*)h->stream : nullptr; }
+int slam_synchronize(slam_handle_t h) { if (!h) return 1; CK(cudaStreamSynchronize(h->stream)); return 0; }
+int slam_batch(slam_handle_t h) { return h ? h->b.batch : 0; }
+int slam_kind(slam_handle_t h) { return h ? h->kind : 0; }
+long long slam_kernel_launches(slam_handle_t h) { return h ? h->launches : 0; }
+
+int slam_build_info(char* buf, int cap) {
+    return snprintf(buf, cap, "sm_100a; nvcc %d.%d; kernels: ekf_step_kernel ukf_step_kernel sim_step_kernel", __CUDACC_VER_MAJOR__, __CUDACC_VER_MINOR__);
+}
+
+// Filter::init, ekf.cpp:29-34 / ukf.cpp:31-45 together with the constructors' P_0 (ekf.cpp:8-18, ukf.cpp:7-18)
+int slam_init(slam_handle_t h, float x_0, float y_0, float yaw_0) {
+    if (!h) return 1;
+    CK(cudaSetDevice(h->device));
+    BatchState& b = h->b;
+    const int nb = b.base, ld = ldg_of(nb);
+    std::vector<double> x0(b.x_stride, 0.0), P0((size_t)nb * ld, 0.0);
+    x0[0] = x_0; x0[1] = y_0;
+    if (nb == 3) x0[2] = yaw_0;
+    else { x0[2] = (double)(float)std::cos((double)yaw_0); x0[3] = (double)(float)std::sin((double)yaw_0); }   // ukf.cpp:33 (D-1)
+    P0[0 * ld + 0] = 0.01 * 0.01; P0[1 * ld + 1] = 0.01 * 0.01; P0[2 * ld + 2] = 0.005 * 0.005;
+    if (nb == 4) P0[3 * ld + 3] = 0.005 * 0.005;
+    // replicate on the host once, then one copy per array
+    std::vector<double> xs((size_t)b.batch * b.x_stride);
+    for (int i = 0; i < b.batch; ++i) memcpy(&xs[(size_t)i * b.x_stride], x0.data(), sizeof(double) * b.x_stride);
+    CK(cudaMemsetAsync(b.P, 0, sizeof(double) * (size_t)b.batch * b.p_stride, h->stream));
+    CK(cudaMemcpyAsync(b.x, xs.data(), sizeof(double) * xs.size(), cudaMemcpyHostToDevice, h->stream));
+    {
+        std::vector<double> Ps((size_t)b.batch * P0.size());
+        for (int i = 0; i < b.batch; ++i) memcpy(&Ps[(size_t)i * P0.size()], P0.data(), sizeof(double) * P0.size());
+        CK(cudaMemcpy2DAsync(b.P, sizeof(double) * b.p_stride, Ps.data(), sizeof(double) * P0.size(),
+                             sizeof(double) * P0.size(), b.batch, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));   // Ps / xs are pageable host vectors
+    }
+    CK(cudaMemsetAsync(b.ids, 0, sizeof(int) * (size_t)b.batch * b.max_lm, h->stream));
+    CK(cudaMemsetAsync(b.M, 0, sizeof(int) * b.batch, h->stream));
+    CK(cudaMemsetAsync(b.timestep, 0, sizeof(int) * b.batch, h->stream));
+    CK(cudaMemsetAsync(b.status, 0, sizeof(int) * b.batch, h->stream));
+    CK(cudaMemsetAsync(b.n_assoc, 0, sizeof(int) * b.batch, h->stream));
+    CK(cudaMemsetAsync(b.assoc, 0xff, sizeof(int) * (size_t)b.batch * b.max_meas, h->stream));
+    CK(cudaMemsetAsync(b.stats, 0, sizeof(double) * (size_t)b.batch * SLAM_NUM_STATS, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int do_step(slam_filter* h, const float* d_fwd, const float* d_ang, int cmd_stride, const float* d_meas,
+                   const int* d_nmeas, int phases) {
+    CK(cudaSetDevice(h->device));
+    StepInputs in{d_fwd, d_ang, cmd_stride, d_meas, d_nmeas};
+    if (h->kind != SLAM_EKF_SLAM && phases != (STEP_PREDICT | STEP_UPDATE))
+        return fail(h, "split predict/update is defined for EKF_SLAM only: the UKF update stage consumes the sigma points of the same call (ukf.cpp:305-337)");
+    if (h->profiling) {
+        if (h->ev_used + 2 > h->ev.size()) {
+            const size_t old = h->ev.size();
+            h->ev.resize(old + 4096);
+            for (size_t i = old; i < h->ev.size(); ++i) CK(cudaEventCreate(&h->ev[i]));
+        }
+        CK(cudaEventRecord(h->ev[h->ev_used], h->stream));
+    }
+    if (h->kind == SLAM_EKF_SLAM) CK(launch_ekf_step(h->b, h->fc, in, phases, h->stream));
+    else CK(launch_ukf_step(h->b, h->fc, in, h->stream));
+    if (h->profiling) { CK(cudaEventRecord(h->ev[h->ev_used + 1], h->stream)); h->ev_used += 2; }
+    h->launches += 1;
+    return 0;
+}
+
+static int stage_cmd(slam_filter* h, const float* fwd, const float* ang, int cmd_stride) {
+    const size_t nc = cmd_stride ? (size_t)h->b.batch : 1;
+    CK(cudaMemcpyAsync(h->d_fwd, fwd, sizeof(float) * nc, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_ang, ang, sizeof(float) * nc, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+static int stage_meas(slam_filter* h, const float* meas, const int* n_meas) {
+    CK(cudaMemcpyAsync(h->d_nmeas, n_meas, sizeof(int) * h->b.batch, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_meas, meas, sizeof(float) * 3 * (size_t)h->b.batch * h->b.max_meas, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+int slam_step(slam_handle_t h, const float* fwd, const float* ang, int cmd_stride, const float* meas, const int* n_meas) {
+    if (!h) return 1;
+    if (!fwd || !ang || !meas || !n_meas) return fail(h, "slam_step: NULL argument");
+    CK(cudaSetDevice(h->device));
+    if (stage_cmd(h, fwd, ang, cmd_stride) || stage_meas(h, meas, n_meas)) return 1;
+    return do_step(h, h->d_fwd, h->d_ang, cmd_stride, h->d_meas, h->d_nmeas, STEP_PREDICT | STEP_UPDATE);
+}
+int slam_step_device(slam_handle_t h, const float* d_fwd, const float* d_ang, int cmd_stride, const float* d_meas, const int* d_n_meas) {
+    if (!h) return 1;
+    if (!d_fwd || !d_ang || !d_meas || !d_n_meas) return fail(h, "slam_step_device: NULL argument");
+    return do_step(h, d_fwd, d_ang, cmd_stride, d_meas, d_n_meas, STEP_PREDICT | STEP_UPDATE);
+}
+int slam_predict(slam_handle_t h, const float* fwd, const float* ang, int cmd_stride) {
+    if (!h) return 1;
+    if (!fwd || !ang) return fail(h, "slam_predict: NULL argument");
+    CK(cudaSetDevice(h->device));
+    if (stage_cmd(h, fwd, ang, cmd_stride)) return 1;
+    return do_step(h, h->d_fwd, h->d_ang, cmd_stride, h->d_meas, h->d_nmeas, STEP_PREDICT);
+}
+int slam_update(slam_handle_t h, const float* meas, const int* n_meas) {
+    if (!h) return 1;
+    if (!meas || !n_meas) return fail(h, "slam_update: NULL argument");
+    CK(cudaSetDevice(h->device));
+    if (stage_meas(h, meas, n_meas)) return 1;
+    return do_step(h, h->d_fwd, h->d_ang, 0, h->d_meas, h->d_nmeas, STEP_UPDATE);
+}
+int slam_predict_device(slam_handle_t h, const float* d_fwd, const float* d_ang, int cmd_stride) {
+    if (!h) return 1;
+    return do_step(h, d_fwd, d_ang, cmd_stride, h->d_meas, h->d_nmeas, STEP_PREDICT);
+}
+int slam_update_device(slam_handle_t h, const float* d_meas, const int* d_n_meas) {
+    if (!h) return 1;
+    return do_step(h, h->d_fwd, h->d_ang, 0, d_meas, d_n_meas, STEP_UPDATE);
+}
+
+// ------------------------------------------------------------------------------------------ getters
+static int check_inst(slam_filter* h, int inst) {
+    if (!h) return 1;
+    if (inst < 0 || inst >= h->b.batch) return fail(h, "instance index out of range");
+    return 0;
+}
+static int get_int(slam_filter* h, const int* d_arr, int inst, int* out) {
+    if (check_inst(h, inst)) return 1;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(out, d_arr + inst, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int slam_get_timestep(slam_handle_t h, int inst, int* t) { return get_int(h, h ? h->b.timestep : nullptr, inst, t); }
+int slam_get_num_landmarks(slam_handle_t h, int inst, int* M) { return get_int(h, h ? h->b.M : nullptr, inst, M); }
+int slam_get_status(slam_handle_t h, int inst, int* s) { return get_int(h, h ? h->b.status : nullptr, inst, s); }
+
+int slam_get_state(slam_handle_t h, int inst, double* x, int* n) {
+    int M = 0;
+    if (slam_get_num_landmarks(h, inst, &M)) return 1;
+    const int nn = h->b.base + 2 * M;
+    CK(cudaMemcpyAsync(x, h->b.x + (size_t)inst * h->b.x_stride, sizeof(double) * nn, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (n) *n = nn;
+    return 0;
+}
+
+int slam_get_state_vector(slam_handle_t h, int inst, double* xv, int* n) {
+    if (check_inst(h, inst)) return 1;
+    if (h->kind == SLAM_EKF_SLAM) return slam_get_state(h, inst, xv, n);   // ekf.cpp:182-185
+    std::vector<double> raw(h->b.x_stride);
+    int nr = 0;
+    if (slam_get_state(h, inst, raw.data(), &nr)) return 1;
+    // the (x, y, yaw, landmarks...) vector UKF::getStateVector means to build (ukf.cpp:47-53; the reference's
+    // own version resizes a fixed-size Vector3d and is broken for M > 0, SURVEY B-8)
+    xv[0] = raw[0]; xv[1] = raw[1];
+    xv[2] = std::remainder(std::atan2(raw[3], raw[2]), TWO_PI_REF);
+    for (int i = 4; i < nr; ++i) xv[i - 1] = raw[i];
+    if (n) *n = nr - 1;
+    return 0;
+}
+
+int slam_get_cov(slam_handle_t h, int inst, double* P, int* n) {
+    int M = 0;
+    if (slam_get_num_landmarks(h, inst, &M)) return 1;
+    const int nn = h->b.base + 2 * M, ld = ldg_of(nn);
+    CK(cudaMemcpy2DAsync(P, sizeof(double) * nn, h->b.P + (size_t)inst * h->b.p_stride, sizeof(double) * ld,
+                         sizeof(double) * nn, nn, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (n) *n = nn;
+    return 0;
+}
+
+int slam_get_landmark_ids(slam_handle_t h, int inst, int* ids, int* M) {
+    int m = 0;
+    if (slam_get_num_landmarks(h, inst, &m)) return 1;
+    if (m > 0) {
+        CK(cudaMemcpyAsync(ids, h->b.ids + (size_t)inst * h->b.max_lm, sizeof(int) * m, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    if (M) *M = m;
+    return 0;
+}
+
+int slam_get_assoc(slam_handle_t h, int inst, int* slot, int* k) {
+    int kk = 0;
+    if (get_int(h, h ? h->b.n_assoc : nullptr, inst, &kk)) return 1;
+    if (kk > 0) {
+        CK(cudaMemcpyAsync(slot, h->b.assoc + (size_t)inst * h->b.max_meas, sizeof(int) * kk, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    if (k) *k = kk;
+    return 0;
+}
+
+int slam_get_sigma_points(slam_handle_t h, int inst, double* X, int* n) {
+    if (check_inst(h, inst)) return 1;
+    if (h->kind != SLAM_UKF_SLAM) return fail(h, "slam_get_sigma_points: UKF only");
+    return fail(h, "slam_get_sigma_points: sigma points are not materialised by the batched UKF kernel yet");
+}
+
+int slam_get_poses(slam_handle_t h, double* xyyaw) {
+    if (!h) return 1;
+    CK(cudaSetDevice(h->device));
+    CK(launch_poses(h->b, h->d_out, h->stream));
+    h->launches += 1;
+    CK(cudaMemcpyAsync(xyyaw, h->d_out, sizeof(double) * 3 * h->b.batch, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int slam_get_all_status(slam_handle_t h, int* status) {
+    if (!h) return 1;
+    CK(cudaMemcpyAsync(status, h->b.status, sizeof(int) * h->b.batch, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int slam_get_all_num_landmarks(slam_handle_t h, int* M) {
+    if (!h) return 1;
+    CK(cudaMemcpyAsync(M, h->b.M, sizeof(int) * h->b.batch, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int slam_set_state(slam_handle_t h, int inst, const double* x, const double* P, const int* ids, int M, int timestep) {
+    if (check_inst(h, inst)) return 1;
+    if (M < 0 || M > h->b.max_lm) return fail(h, "slam_set_state: M out of range");
+    CK(cudaSetDevice(h->device));
+    const int nn = h->b.base + 2 * M, ld = ldg_of(nn);
+    const int zero = 0;
+    CK(cudaMemcpyAsync(h->b.x + (size_t)inst * h->b.x_stride, x, sizeof(double) * nn, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpy2DAsync(h->b.P + (size_t)inst * h->b.p_stride, sizeof(double) * ld, P, sizeof(double) * nn,
+                         sizeof(double) * nn, nn, cudaMemcpyHostToDevice, h->stream));
+    if (M > 0) CK(cudaMemcpyAsync(h->b.ids + (size_t)inst * h->b.max_lm, ids, sizeof(int) * M, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->b.M + inst, &M, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->b.timestep + inst, &timestep, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->b.status + inst, &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ simulator
+int slam_sim_create(slam_handle_t h, const double* lm_xy, int n_lm, uint64_t seed, uint32_t instance_offset, slam_sim_t* out) {
+    if (!h) return 1;
+    if (!out || !lm_xy || n_lm < 1) return fail(h, "slam_sim_create: bad argument");
+    CK(cudaSetDevice(h->device));
+    slam_sim* s = new slam_sim();
+    s->owner = h;
+    SimState& st = s->s;
+    st.batch = h->b.batch; st.max_meas = h->b.max_meas; st.n_lm = n_lm;
+    st.instance_offset = instance_offset;
+    st.k0 = (uint32_t)seed; st.k1 = (uint32_t)(seed >> 32);
+    CK(cudaMalloc(&s->d_lm, sizeof(double) * 2 * (size_t)n_lm));
+    CK(cudaMemcpy(s->d_lm, lm_xy, sizeof(double) * 2 * (size_t)n_lm, cudaMemcpyHostToDevice));
+    st.lm_xy = s->d_lm;
+    CK(cudaMalloc(&st.truth, sizeof(double) * 3 * (size_t)st.batch));
+    CK(cudaMalloc(&st.meas, sizeof(float) * 3 * (size_t)st.batch * st.max_meas));
+    CK(cudaMalloc(&st.n_meas, sizeof(int) * st.batch));
+    CK(cudaMalloc(&st.overflow, sizeof(int) * st.batch));
+    CK(cudaMemset(st.meas, 0, sizeof(float) * 3 * (size_t)st.batch * st.max_meas));
+    *out = s;
+    return slam_sim_reset(s, 0.0, 0.0, 0.0);
+}
+int slam_sim_destroy(slam_sim_t s) {
+    if (!s) return 0;
+    cudaSetDevice(s->owner->device);
+    cudaStreamSynchronize(s->owner->stream);
+    cudaFree(s->d_lm); cudaFree(s->s.truth); cudaFree(s->s.meas); cudaFree(s->s.n_meas); cudaFree(s->s.overflow);
+    delete s;
+    return 0;
+}
+int slam_sim_reset(slam_sim_t s, double x_0, double y_0, double yaw_0) {
+    if (!s) return 1;
+    slam_filter* h = s->owner;
+    CK(cudaSetDevice(h->device));
+    std::vector<double> t(3 * (size_t)s->s.batch);
+    for (int i = 0; i < s->s.batch; ++i) { t[3 * i] = x_0; t[3 * i + 1] = y_0; t[3 * i + 2] = yaw_0; }
+    CK(cudaMemcpyAsync(s->s.truth, t.data(), sizeof(double) * t.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(s->s.n_meas, 0, sizeof(int) * s->s.batch, h->stream));
+    CK(cudaMemsetAsync(s->s.overflow, 0, sizeof(int) * s->s.batch, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int slam_sim_step_device(slam_sim_t s, const float* d_fwd, const float* d_ang, int cmd_stride, uint32_t step) {
+    if (!s) return 1;
+    slam_filter* h = s->owner;
+    CK(cudaSetDevice(h->device));
+    CK(launch_sim_step(s->s, h->sc, d_fwd, d_ang, cmd_stride, step, h->stream));
+    h->launches += 1;
+    return 0;
+}
+int slam_sim_step(slam_sim_t s, const float* fwd, const float* ang, int cmd_stride, uint32_t step) {
+    if (!s) return 1;
+    slam_filter* h = s->owner;
+    CK(cudaSetDevice(h->device));
+    if (stage_cmd(h, fwd, ang, cmd_stride)) return 1;
+    return slam_sim_step_device(s, h->d_fwd, h->d_ang, cmd_stride, step);
+}
+const float* slam_sim_meas(slam_sim_t s) { return s ? s->s.meas : nullptr; }
+const int* slam_sim_n_meas(slam_sim_t s) { return s ? s->s.n_meas : nullptr; }
+int slam_sim_get_truth(slam_sim_t s, double* xyyaw) {
+    if (!s) return 1;
+    slam_filter* h = s->owner;
+    CK(cudaMemcpyAsync(xyyaw, s->s.truth, sizeof(double) * 3 * s->s.batch, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int slam_sim_get_meas(slam_sim_t s, float* meas, int* n_meas) {
+    if (!s) return 1;
+    slam_filter* h = s->owner;
+    CK(cudaMemcpyAsync(meas, s->s.meas, sizeof(float) * 3 * (size_t)s->s.batch * s->s.max_meas, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(n_meas, s->s.n_meas, sizeof(int) * s->s.batch, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ sweep + stats
+int slam_run(slam_handle_t h, slam_sim_t s, const float* cmd_fwd, const float* cmd_ang, int cmd_stride, int T, uint32_t first_step) {
+    if (!h || !s || s->owner != h) return fail(h, "slam_run: simulator is not bound to this handle");
+    if (!cmd_fwd || !cmd_ang || T < 0) return fail(h, "slam_run: bad argument");
+    CK(cudaSetDevice(h->device));
+    const size_t per = cmd_stride ? (size_t)h->b.batch : 1;
+    const size_t need = per * (size_t)T;
+    if (need > h->traj_cap) {
+        cudaFree(h->d_traj_fwd); cudaFree(h->d_traj_ang);
+        h->d_traj_fwd = h->d_traj_ang = nullptr; h->traj_cap = 0;
+        CK(cudaMalloc(&h->d_traj_fwd, sizeof(float) * need));
+        CK(cudaMalloc(&h->d_traj_ang, sizeof(float) * need));
+        h->traj_cap = need;
+    }
+    CK(cudaMemcpyAsync(h->d_traj_fwd, cmd_fwd, sizeof(float) * need, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_traj_ang, cmd_ang, sizeof(float) * need, cudaMemcpyHostToDevice, h->stream));
+    for (int t = 0; t < T; ++t) {
+        const float* f = h->d_traj_fwd + per * (size_t)t;
+        const float* a = h->d_traj_ang + per * (size_t)t;
+        CK(launch_sim_step(s->s, h->sc, f, a, cmd_stride, first_step + (uint32_t)t, h->stream));
+        if (do_step(h, f, a, cmd_stride, s->s.meas, s->s.n_meas, STEP_PREDICT | STEP_UPDATE)) return 1;
+        CK(launch_accumulate_error(h->b, s->s, h->stream));
+        h->launches += 2;
+    }
+    return 0;
+}
+
+int slam_run_device(slam_handle_t h, slam_sim_t s, const float* d_cmd_fwd, const float* d_cmd_ang, int cmd_stride, int T, uint32_t first_step) {
+    if (!h || !s || s->owner != h) return fail(h, "slam_run_device: simulator is not bound to this handle");
+    if (!d_cmd_fwd || !d_cmd_ang || T < 0) return fail(h, "slam_run_device: bad argument");
+    CK(cudaSetDevice(h->device));
+    const size_t per = cmd_stride ? (size_t)h->b.batch : 1;
+    for (int t = 0; t < T; ++t) {
+        const float* f = d_cmd_fwd + per * (size_t)t;
+        const float* a = d_cmd_ang + per * (size_t)t;
+        CK(launch_sim_step(s->s, h->sc, f, a, cmd_stride, first_step + (uint32_t)t, h->stream));
+        if (do_step(h, f, a, cmd_stride, s->s.meas, s->s.n_meas, STEP_PREDICT | STEP_UPDATE)) return 1;
+        CK(launch_accumulate_error(h->b, s->s, h->stream));
+        h->launches += 2;
+    }
+    return 0;
+}
+
+int slam_reset(slam_handle_t h, float x_0, float y_0, float yaw_0) {
+    if (!h) return 1;
+    CK(cudaSetDevice(h->device));
+    double a2 = yaw_0, a3 = 0.0;
+    if (h->b.base == 4) { a2 = (double)(float)std::cos((double)yaw_0); a3 = (double)(float)std::sin((double)yaw_0); }   // ukf.cpp:33 (D-1)
+    CK(launch_reset(h->b, (double)x_0, (double)y_0, a2, a3, h->stream));
+    h->launches += 1;
+    return 0;
+}
+
+int slam_step_io(slam_handle_t h, const float* fwd, const float* ang, int cmd_stride, const float* meas, const int* n_meas, double* poses_out) {
+    if (slam_step(h, fwd, ang, cmd_stride, meas, n_meas)) return 1;
+    if (poses_out) {
+        CK(launch_poses(h->b, h->d_out, h->stream));
+        h->launches += 1;
+        CK(cudaMemcpyAsync(poses_out, h->d_out, sizeof(double) * 3 * h->b.batch, cudaMemcpyDeviceToHost, h->stream));
+    }
+    return 0;
+}
+
+int slam_set_profiling(slam_handle_t h, int on) {
+    if (!h) return 1;
+    h->profiling = on != 0;
+    h->ev_used = 0;
+    return 0;
+}
+int slam_get_profile(slam_handle_t h, double* total_ms, long long* launches) {
+    if (!h) return 1;
+    CK(cudaStreamSynchronize(h->stream));
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+        tot += ms;
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = (long long)(h->ev_used / 2);
+    h->ev_used = 0;
+    return 0;
+}
+
+int slam_accumulate_error(slam_handle_t h, slam_sim_t s) {
+    if (!h || !s || s->owner != h) return fail(h, "slam_accumulate_error: simulator is not bound to this handle");
+    CK(cudaSetDevice(h->device));
+    CK(launch_accumulate_error(h->b, s->s, h->stream));
+    h->launches += 1;
+    return 0;
+}
+int slam_get_stats(slam_handle_t h, double* out) {
+    if (!h) return 1;
+    CK(cudaSetDevice(h->device));
+    double* d = h->d_out + 3 * (size_t)h->b.batch;
+    CK(launch_reduce_stats(h->b, d, h->stream));
+    h->launches += 1;
+    CK(cudaMemcpyAsync(out, d, sizeof(double) * SLAM_NUM_STATS, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int slam_reset_stats(slam_handle_t h) {
+    if (!h) return 1;
+    CK(cudaMemsetAsync(h->b.stats, 0, sizeof(double) * (size_t)h->b.batch * SLAM_NUM_STATS, h->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,171 @@
+// common.cuh -- shared device helpers and the batch memory layout for the sm_100a filter kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/slam_filter.h"
+
+#define PI_REF 3.14159265358979323846  // filter.h:42
+#define TWO_PI_REF (2 * PI_REF)
+
+namespace slam {
+
+// ---------------------------------------------------------------------------------------------
+// HBM layout of a batch of filter instances (all arrays are struct-of-arrays over instances).
+//
+//   P      [batch][p_stride]   covariance, row-major, PACKED with leading dimension ldg(n) =
+//                              n rounded up to even (rows are 16-byte multiples so every row is one
+//                              cp.async.bulk); only n*ldg(n) doubles are live and only they cross HBM.
+//   x      [batch][x_stride]   committed state x_t (EKF: x,y,yaw,lm.. ; UKF: x,y,cos,sin,lm..)
+//   ids    [batch][max_lm]     lm_IDs (filter.h:70)
+//   M, timestep, status [batch]
+//   assoc  [batch][max_meas]   slot index (or -1) chosen for each measurement of the last step
+// ---------------------------------------------------------------------------------------------
+struct BatchState {
+    double* P;
+    double* x;
+    int* ids;
+    int* M;
+    int* timestep;
+    int* status;
+    int* assoc;
+    int* n_assoc;
+    double* stats;     // [batch][SLAM_NUM_STATS] per-instance accumulators
+    double* sigma;     // UKF only: [batch][sigma_stride] sigma points X (point-major), optional
+    long long p_stride;
+    long long sigma_stride;
+    int x_stride;
+    int batch;
+    int max_lm;
+    int max_meas;
+    int base;          // 3 (EKF) or 4 (UKF)
+    int n_max;         // base + 2*max_lm
+    int lds;           // shared-memory leading dimension of P
+};
+
+// Effective filter constants after readCommonParams (filter.h:105-121).
+struct FilterConst {
+    double V00, V11;   // process noise used by the filter
+    double W00, W11;   // sensing noise used by the filter
+    float v_d, v_th, w_r, w_b;
+    float min_sep;
+    int id_known;
+};
+
+struct SimConst {
+    double V_00, V_11, W_00, W_11;   // uniform half-widths, sim_node.py:216-217,247-248
+    double d_max, th_max, range_max, fov_min, fov_max;
+};
+
+__host__ __device__ inline int ldg_of(int n) { return (n + 1) & ~1; }
+
+// smallest even leading dimension >= n_max+1 with lds % 4 == 2: rows stay 16-byte aligned for bulk copies
+// and a column walk hits 8 distinct 8-byte bank slots per half-warp (2-way conflict at worst).
+__host__ __device__ inline int lds_of(int n_max) {
+    int l = ldg_of(n_max);
+    while ((l & 3) != 2) l += 2;
+    return l;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10, identical to oracle_philox (counter = instance, step, channel, 0; key = seed)
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__host__ __device__ inline double uniform53(uint32_t hi, uint32_t lo) {
+    return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+#ifdef __CUDACC__
+// D-1: cos/sin of a float argument pinned as (float)cos((double)x) (oracle/slam_oracle.c cos_f/sin_f)
+__device__ __forceinline__ float cos_f(float x) { return (float)cos((double)x); }
+__device__ __forceinline__ float sin_f(float x) { return (float)sin((double)x); }
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + 1-D bulk async copy (TMA without a tensor map: cp.async.bulk, SASS UBLKCP)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared, completion signalled on an mbarrier (bytes: multiple of 16, both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global, bulk-group completion
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+#endif
+
+// host-side launchers (defined in the .cu files, called from capi.cu)
+struct StepInputs {
+    const float* fwd;      // device
+    const float* ang;      // device
+    int cmd_stride;        // 0 shared / 1 per instance
+    const float* meas;     // device [batch][max_meas][3]
+    const int* n_meas;     // device [batch]
+};
+
+enum { STEP_PREDICT = 1, STEP_UPDATE = 2 };
+
+cudaError_t launch_ekf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, int phases, cudaStream_t st);
+size_t ekf_step_smem_bytes(const BatchState& b);
+cudaError_t ekf_step_configure(const BatchState& b);
+
+cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, cudaStream_t st);
+size_t ukf_step_smem_bytes(const BatchState& b);
+cudaError_t ukf_step_configure(const BatchState& b);
+
+struct SimState {
+    double* truth;         // [batch][3]
+    const double* lm_xy;   // [n_lm][2]
+    float* meas;           // [batch][max_meas][3]
+    int* n_meas;           // [batch]
+    int* overflow;         // [batch] detections dropped because max_meas was reached
+    int n_lm;
+    int batch;
+    int max_meas;
+    uint32_t instance_offset;
+    uint32_t k0, k1;
+};
+cudaError_t launch_sim_step(const SimState& s, const SimConst& sc, const float* d_fwd, const float* d_ang,
+                            int cmd_stride, uint32_t step, cudaStream_t st);
+cudaError_t launch_accumulate_error(const BatchState& b, const SimState& s, cudaStream_t st);
+cudaError_t launch_reduce_stats(const BatchState& b, double* d_out, cudaStream_t st);
+cudaError_t launch_poses(const BatchState& b, double* d_out, cudaStream_t st);
+cudaError_t launch_reset(const BatchState& b, double x0, double y0, double a2, double a3, cudaStream_t st);
+
+}  // namespace slam

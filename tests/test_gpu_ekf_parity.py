@@ -1,0 +1,249 @@
+"""GPU parity: the batched EKF-SLAM CUDA path (through the C-ABI) against the CPU oracle on identical inputs.
+Tolerances are the north star's: association / landmark ids / M bit-exact; state and covariance within 1e-9
+(norm-wise) per step; final trajectory within 1e-6 m / 1e-6 rad."""
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def shim():
+    from live_ekf_slam_b200 import shim as s
+    s.load()
+    return s
+
+
+def _compare(fb, inst, of, tol=H.REL_TOL):
+    assert fb.num_landmarks(inst) == of.M
+    assert list(fb.landmark_ids(inst)) == list(of.landmark_ids())
+    ex = H.normwise(fb.state(inst), of.state())
+    eP = H.normwise(fb.cov(inst), of.cov())
+    assert ex <= tol and eP <= tol, (ex, eP)
+    return max(ex, eP)
+
+
+def test_kat_through_abi(shim, oracle):
+    p = H.Params()
+    fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 1, 8, 4)
+    fb.init(0, 0, 0)
+    meas, n = fb.pack_meas([np.array([[7, 1.0, 0.0]], dtype=np.float32)])
+    fb.step(0.1, 0.0, meas, n)
+    d = float(np.float32(0.1))
+    np.testing.assert_allclose(fb.state(0), [d, 0, 0, d + 1.0, 0], rtol=1e-15, atol=1e-18)
+    P = fb.cov(0)
+    np.testing.assert_allclose(P[3:, 3:], [[1.0101, 0], [0, 1.01013025]], rtol=1e-8)
+    assert list(fb.landmark_ids(0)) == [7] and fb.timestep(0) == 1 and list(fb.assoc(0)) == [-1]
+
+
+def test_config1_single_instance_per_step(shim, oracle):
+    """BASELINE config 1: single EKF, random 20-landmark map, TSP trajectory, known IDs; checked EVERY step."""
+    p, lm, fwd, ang = H.config1(seed=0, steps=1000)
+    op = H.oracle_params(oracle, p)
+    stream, truth = H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=0, instance=0)
+    of = oracle.OracleFilter(oracle.EKF_SLAM, op, 20)
+    of.init(0, 0, 0)
+    fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 1, 20, 8)
+    fb.init(0, 0, 0)
+    worst = 0.0
+    for t in range(len(fwd)):
+        of.update(fwd[t], ang[t], stream[t], oracle.DENSE)
+        meas, n = fb.pack_meas([stream[t]])
+        fb.step(fwd[t], ang[t], meas, n)
+        assert list(fb.assoc(0)) == list(of.assoc_log()), t
+        if t % 10 == 0 or t > 990:
+            worst = max(worst, _compare(fb, 0, of))
+    worst = max(worst, _compare(fb, 0, of))
+    x, xo = fb.state(0), of.state()
+    assert np.abs(x[:2] - xo[:2]).max() <= H.FINAL_TOL and abs(x[2] - xo[2]) <= H.FINAL_TOL
+    assert fb.status(0) == 0 and fb.timestep(0) == len(fwd)
+    assert of.M >= 15   # the TSP tour discovers (nearly) the whole map
+    print("config1 worst normwise err", worst, "final M", of.M)
+
+
+def test_batch_free_running_grid(shim, oracle):
+    """BASELINE config 2 at reduced size: 48 instances on the 5x10 grid, 400 steps, free running."""
+    p, lm, fwd, ang = H.config2(seed=1, steps=400)
+    op = H.oracle_params(oracle, p)
+    B = 48
+    fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), B, 50, 8)
+    fb.init(0, 0, 0)
+    streams = [H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=7, instance=i)[0] for i in range(B)]
+    ofs = []
+    for i in range(B):
+        of = oracle.OracleFilter(oracle.EKF_SLAM, op, 50)
+        of.init(0, 0, 0)
+        ofs.append(of)
+    for t in range(len(fwd)):
+        meas, n = fb.pack_meas([streams[i][t] for i in range(B)])
+        fb.step(fwd[t], ang[t], meas, n)
+        for i in range(B):
+            ofs[i].update(fwd[t], ang[t], streams[i][t], oracle.STRUCTURED)
+        if t % 100 == 99:
+            for i in range(0, B, 7):
+                assert list(fb.assoc(i)) == list(ofs[i].assoc_log())
+    worst = max(_compare(fb, i, ofs[i]) for i in range(B))
+    poses = fb.poses()
+    for i in range(B):
+        xo = ofs[i].state()
+        assert np.abs(poses[i] - xo[:3]).max() <= H.FINAL_TOL
+    assert (fb.all_status() == 0).all()
+    assert (fb.all_num_landmarks() == [o.M for o in ofs]).all()
+    print("batch worst normwise err", worst)
+
+
+def test_teacher_forced_single_steps(shim, oracle):
+    """Load the oracle's (x, P, ids) of step t into the GPU filter, run ONE step, compare (SURVEY App. E protocol)."""
+    p, lm, fwd, ang = H.config2(seed=2, steps=300)
+    op = H.oracle_params(oracle, p)
+    stream, _ = H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=3, instance=5)
+    of = oracle.OracleFilter(oracle.EKF_SLAM, op, 50)
+    of.init(0, 0, 0)
+    fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 2, 50, 8)
+    fb.init(0, 0, 0)
+    checked = 0
+    for t in range(len(fwd)):
+        if t % 17 == 0 and of.M > 0:
+            fb.set_state(1, of.state(), of.cov(), of.landmark_ids(), of.timestep)
+            of.update(fwd[t], ang[t], stream[t], oracle.DENSE)
+            meas, n = fb.pack_meas([[], stream[t]])
+            fb.step(fwd[t], ang[t], meas, n)
+            assert _compare(fb, 1, of) <= 1e-12     # one step from identical state: far tighter than 1e-9
+            assert fb.timestep(1) == of.timestep
+            checked += 1
+        else:
+            of.update(fwd[t], ang[t], stream[t], oracle.DENSE)
+    assert checked >= 10
+
+
+def test_split_predict_update_matches_fused(shim, oracle):
+    p, lm, fwd, ang = H.config2(seed=4, steps=120)
+    op = H.oracle_params(oracle, p)
+    stream, _ = H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=9, instance=0)
+    fused = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 1, 50, 8)
+    split = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 1, 50, 8)
+    of = oracle.OracleFilter(oracle.EKF_SLAM, op, 50)
+    for f in (fused, split, of):
+        f.init(0, 0, 0)
+    for t in range(len(fwd)):
+        meas, n = fused.pack_meas([stream[t]])
+        fused.step(fwd[t], ang[t], meas, n)
+        split.predict(fwd[t], ang[t])
+        split.update(meas, n)
+        of.predict(fwd[t], ang[t])
+        of.measure(stream[t])
+    np.testing.assert_array_equal(fused.state(0), split.state(0))
+    np.testing.assert_array_equal(fused.cov(0), split.cov(0))
+    _compare(split, 0, of)
+    assert split.timestep(0) == len(fwd)
+
+
+def test_unknown_id_box_gate_association(shim, oracle):
+    """landmark_id_is_known = false: first-match axis-aligned box gate in float (ekf.cpp:82-98); ids are slot numbers."""
+    p, lm, fwd, ang = H.config2(seed=5, steps=300)
+    p.landmark_id_is_known = False
+    op = H.oracle_params(oracle, p)
+    stream, _ = H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=11, instance=2)
+    of = oracle.OracleFilter(oracle.EKF_SLAM, op, 50)
+    of.init(0, 0, 0)
+    fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 1, 50, 8)
+    fb.init(0, 0, 0)
+    matched = 0
+    for t in range(len(fwd)):
+        scrambled = stream[t].copy()
+        if len(scrambled):
+            scrambled[:, 0] = 999.0     # ids on the wire must be ignored in this mode
+        of.update(fwd[t], ang[t], scrambled, oracle.DENSE)
+        meas, n = fb.pack_meas([scrambled])
+        fb.step(fwd[t], ang[t], meas, n)
+        a = list(fb.assoc(0))
+        assert a == list(of.assoc_log()), t
+        matched += sum(1 for v in a if v >= 0)
+    _compare(fb, 0, of)
+    assert list(fb.landmark_ids(0)) == list(range(of.M))
+    assert matched > 50
+
+
+def test_edge_cases(shim, oracle):
+    p = H.Params()
+    op = H.oracle_params(oracle, p)
+    # (a) no detections at all: predict-only steps (ekf.cpp:67-71)
+    fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 3, 2, 2)
+    fb.init(0.5, -0.25, 0.3)
+    of = oracle.OracleFilter(oracle.EKF_SLAM, op, 2)
+    of.init(0.5, -0.25, 0.3)
+    for t in range(5):
+        meas, n = fb.pack_meas([[], [], []])
+        fb.step(0.05, 0.01, meas, n)
+        of.update(0.05, 0.01, [])
+    for i in range(3):
+        _compare(fb, i, of, tol=1e-13)
+    # (b) capacity: third distinct landmark is dropped and flagged
+    m = np.array([[1, 1.0, 0.1], [2, 1.5, -0.2]], dtype=np.float32)
+    meas, n = fb.pack_meas([m, m, m])
+    fb.step(0.05, 0.0, meas, n)
+    of.update(0.05, 0.0, m)
+    m3 = np.array([[3, 2.0, 0.0], [1, 1.0, 0.1]], dtype=np.float32)
+    meas, n = fb.pack_meas([m3, m3, m3])
+    fb.step(0.05, 0.0, meas, n)
+    of.update(0.05, 0.0, m3)
+    assert fb.status(0) & shim.STATUS_CAPACITY and of.status & oracle.ERR_CAPACITY
+    _compare(fb, 0, of)
+    assert list(fb.assoc(0)) == [-1, 0]
+    # (c) more detections than max_meas: flagged, extra ones dropped
+    m4 = np.array([[1, 1.0, 0.1], [2, 1.5, -0.2], [1, 1.0, 0.1]], dtype=np.float32)
+    meas, n = fb.pack_meas([m4, [], []])
+    assert n[0] == 3
+    fb.step(0.0, 0.0, meas, n)
+    assert fb.status(0) & shim.STATUS_MEAS_OVERFLOW
+    # (d) invalid filter choice fails loudly (localization_node.cpp:44)
+    with pytest.raises(shim.SlamError):
+        shim.FilterBatch(2, p.to_c(), 1, 2, 2)
+
+
+def test_same_step_rematch_is_flagged(shim, oracle):
+    """Unknown-ID mode: a second detection that falls inside the gate of a landmark inserted in the same step makes
+    the reference index x_t out of range (ekf.cpp:115) and die; both implementations flag and freeze the instance."""
+    p = H.Params()
+    p.landmark_id_is_known = False
+    op = H.oracle_params(oracle, p)
+    fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 1, 8, 4)
+    fb.init(0, 0, 0)
+    of = oracle.OracleFilter(oracle.EKF_SLAM, op, 8)
+    of.init(0, 0, 0)
+    m = np.array([[0, 2.0, 0.1], [0, 2.01, 0.1]], dtype=np.float32)
+    meas, n = fb.pack_meas([m])
+    fb.step(0.05, 0.0, meas, n)
+    of.update(0.05, 0.0, m)
+    assert of.status & oracle.ERR_SAME_STEP_REMATCH
+    assert fb.status(0) & shim.STATUS_SAME_STEP_REMATCH
+    assert fb.num_landmarks(0) == 0 == of.M
+    np.testing.assert_array_equal(fb.state(0), of.state())
+
+
+def test_filter_classes_mirror_reference_interface(shim, oracle):
+    """The Filter/EKF host classes: readParams -> init -> update per tick -> publishState/getStateVector."""
+    from live_ekf_slam_b200.filter import make_filter, EKF, FilterChoice
+    p, lm, fwd, ang = H.config1(seed=3, steps=60)
+    op = H.oracle_params(oracle, p)
+    stream, _ = H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=1, instance=0)
+    filt = make_filter(p, max_landmarks=20, max_meas=8)
+    assert isinstance(filt, EKF) and filt.type == FilterChoice.EKF_SLAM and not filt.isInit
+    filt.init(0, 0, 0)
+    of = oracle.OracleFilter(oracle.EKF_SLAM, op, 20)
+    of.init(0, 0, 0)
+    for t in range(len(fwd)):
+        filt.update((fwd[t], ang[t]), stream[t].reshape(-1))
+        of.update(fwd[t], ang[t], stream[t])
+    assert H.normwise(filt.getStateVector(), of.state()) <= H.REL_TOL
+    msg = filt.publishState()
+    assert msg["timestep"] == 60 and msg["M"] == of.M and msg["P"].dtype == np.float32
+    assert msg["P"].size == of.n * of.n and msg["landmarks"].size == 3 * of.M
+    with pytest.raises(RuntimeError):
+        filt.updateNaiveVehPoseEstimate(None, None)
+    bad = H.Params(filter="ekf_slam")
+    bad.filter = "nope"
+    with pytest.raises(RuntimeError):
+        make_filter(bad)

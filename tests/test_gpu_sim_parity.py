@@ -1,0 +1,92 @@
+"""GPU parity of the workload source: the on-GPU measurement generator (sim_node.py:209-250 restated in
+csrc/sim.cu) against the CPU oracle, and the fused sim+filter sweep (slam_run) against oracle_run_instance."""
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def shim():
+    from live_ekf_slam_b200 import shim as s
+    s.load()
+    return s
+
+
+def test_sim_messages_bit_exact(shim, oracle):
+    p, lm, fwd, ang = H.config2(seed=0, steps=250)
+    op = H.oracle_params(oracle, p)
+    B, seed, off = 16, 1234567890123, 3
+    fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), B, 50, 8)
+    sim = shim.Simulator(fb, lm, seed=seed, instance_offset=off)
+    truths = [np.zeros(3) for _ in range(B)]
+    n_msgs = 0
+    ulp_flips = 0
+    for t in range(len(fwd)):
+        sim.step(fwd[t], ang[t], t)
+        m, n = sim.meas()
+        tr = sim.truth()
+        for i in range(B):
+            ref = oracle.sim_step(op, truths[i], fwd[t], ang[t], lm, seed, off + i, t)
+            assert n[i] == len(ref), (t, i)
+            got = m[i, : n[i]]
+            np.testing.assert_array_equal(got[:, 0], ref[:, 0])          # ids and visibility decisions: exact
+            if not np.array_equal(got, ref):
+                # device libm differs from glibc by <= 2 ulp(double); after rounding to float32 that flips at most
+                # the last float32 bit, on ~1e-8 of the values.
+                np.testing.assert_allclose(got, ref, rtol=1.3e-7, atol=0)
+                ulp_flips += int((got != ref).sum())
+            n_msgs += len(ref)
+            assert np.abs(tr[i] - truths[i]).max() <= 1e-12
+    assert n_msgs > 3000
+    assert ulp_flips <= 2, ulp_flips
+
+
+def test_slam_run_matches_oracle_instances(shim, oracle):
+    """The device-side sweep (sim -> filter -> error accumulators) reproduces independent oracle instances."""
+    p, lm, fwd, ang = H.config2(seed=6, steps=300)
+    op = H.oracle_params(oracle, p)
+    B, seed, off = 24, 42, 100
+    fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), B, 50, 8)
+    fb.init(0, 0, 0)
+    sim = shim.Simulator(fb, lm, seed=seed, instance_offset=off)
+    sim.run(fwd, ang, first_step=0)
+    poses = fb.poses()
+    truth = sim.truth()
+    sum_pos_err = 0.0
+    sum_sq = np.zeros(3)
+    for i in range(B):
+        st, pose, tr, filt = oracle.run_instance(oracle.EKF_SLAM, op, lm, fwd, ang, seed, off + i, 50,
+                                                 oracle.STRUCTURED, keep=True)
+        assert st == 0
+        assert np.abs(poses[i] - pose[-1]).max() <= H.FINAL_TOL
+        assert np.abs(truth[i] - tr[-1]).max() <= 1e-11
+        assert fb.num_landmarks(i) == filt.M
+        assert list(fb.landmark_ids(i)) == list(filt.landmark_ids())
+        assert H.normwise(fb.cov(i), filt.cov()) <= 1e-8
+        e = pose - tr
+        e[:, 2] = np.remainder(e[:, 2] + np.pi, 2 * np.pi) - np.pi
+        sum_pos_err += np.sqrt(e[:, 0] ** 2 + e[:, 1] ** 2).sum()
+        sum_sq += (e ** 2).sum(axis=0)
+    s = fb.stats()
+    assert s[0] == B * len(fwd)
+    np.testing.assert_allclose(s[1:4], sum_sq, rtol=1e-6)
+    np.testing.assert_allclose(s[4], sum_pos_err, rtol=1e-6)
+    assert s[5] > 0 and s[6] == 0 and s[7] == fb.all_num_landmarks().sum()
+
+
+def test_shard_invariance(shim, oracle):
+    """Instance i gives bit-identical results whether it runs in a batch of 16 at offset 0 or in a shard of 4 at
+    offset 8 (multi-GPU sharding changes nothing: RNG is keyed by the global instance id)."""
+    p, lm, fwd, ang = H.config2(seed=8, steps=150)
+    full = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 16, 50, 8)
+    sim_full = shim.Simulator(full, lm, seed=5, instance_offset=0)
+    sim_full.run(fwd, ang)
+    shard = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 4, 50, 8)
+    sim_shard = shim.Simulator(shard, lm, seed=5, instance_offset=8)
+    sim_shard.run(fwd, ang)
+    for j in range(4):
+        np.testing.assert_array_equal(full.state(8 + j), shard.state(j))
+        np.testing.assert_array_equal(full.cov(8 + j), shard.cov(j))
