@@ -162,6 +162,10 @@ long long slam_kernel_launches(slam_handle_t h);      /* kernels launched by thi
 int  slam_set_profiling(slam_handle_t h, int on);
 int  slam_get_profile(slam_handle_t h, double* total_ms, long long* launches);  /* synchronises; resets the pool */
 int  slam_build_info(char* buf, int cap);             /* arch, compile flags */
+/* tuning / test knobs.  key 0: force the shared-memory landmark capacity of the first pass (0 = automatic;
+ * instances that do not fit are drained by the full-capacity retry pass); key 1: headroom (landmarks) added to
+ * the stale max(M) hint.  Results never depend on either. */
+int  slam_tune(slam_handle_t h, int key, int value);
 
 #ifdef __cplusplus
 }

@@ -28,6 +28,14 @@ struct slam_filter {
     size_t d_out_cap = 0;
     long long launches = 0;
     // per-launch timing of the filter-step kernel
+    // capacity hint: device max(M) read back with a lag of HINT_LAG launches (never waited on in steady state)
+    static constexpr int HINT_RING = 16, HINT_LAG = 8;
+    int* h_hint = nullptr;            // pinned [HINT_RING]
+    cudaEvent_t hint_ev[HINT_RING] = {};
+    long long step_seq = 0;           // filter-step launches since the last init/reset
+    int hint_base = 0;                // max(M) known on the host at step_seq == 0
+    int cap_headroom = 4;             // landmarks of slack on top of the stale max(M)
+    int cap_force = 0;                // > 0: force this capacity for the first pass (tests of the retry path)
     bool profiling = false;
     std::vector<cudaEvent_t> ev;      // pairs
     size_t ev_used = 0;
@@ -110,11 +118,15 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
     CK(cudaMalloc(&b.P, sizeof(double) * (size_t)batch * b.p_stride));
     CK(cudaMalloc(&b.x, sizeof(double) * (size_t)batch * b.x_stride));
     CK(cudaMalloc(&b.ids, sizeof(int) * (size_t)batch * b.max_lm));
-    CK(cudaMalloc(&b.M, sizeof(int) * batch));
-    CK(cudaMalloc(&b.timestep, sizeof(int) * batch));
-    CK(cudaMalloc(&b.status, sizeof(int) * batch));
+    CK(cudaMalloc(&b.meta, sizeof(int4) * batch));
     CK(cudaMalloc(&b.assoc, sizeof(int) * (size_t)batch * b.max_meas));
-    CK(cudaMalloc(&b.n_assoc, sizeof(int) * batch));
+    CK(cudaMalloc(&b.retry_list, sizeof(int) * batch));
+    CK(cudaMalloc(&b.retry_count, sizeof(int)));
+    CK(cudaMalloc(&b.max_M, sizeof(int)));
+    CK(cudaMemset(b.retry_count, 0, sizeof(int)));
+    CK(cudaMemset(b.max_M, 0, sizeof(int)));
+    CK(cudaMallocHost(&h->h_hint, sizeof(int) * slam_filter::HINT_RING));
+    for (int i = 0; i < slam_filter::HINT_RING; ++i) { h->h_hint[i] = 0; CK(cudaEventCreateWithFlags(&h->hint_ev[i], cudaEventDisableTiming)); }
     CK(cudaMalloc(&b.stats, sizeof(double) * (size_t)batch * SLAM_NUM_STATS));
     if (kind == SLAM_UKF_SLAM) {
         b.sigma_stride = (long long)b.n_max * (2 * b.n_max + 1);
@@ -136,8 +148,11 @@ int slam_destroy(slam_handle_t h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     BatchState& b = h->b;
-    cudaFree(b.P); cudaFree(b.x); cudaFree(b.ids); cudaFree(b.M); cudaFree(b.timestep); cudaFree(b.status);
-    cudaFree(b.assoc); cudaFree(b.n_assoc); cudaFree(b.stats); cudaFree(b.sigma);
+    cudaFree(b.P); cudaFree(b.x); cudaFree(b.ids); cudaFree(b.meta);
+    cudaFree(b.assoc); cudaFree(b.stats); cudaFree(b.sigma);
+    cudaFree(b.retry_list); cudaFree(b.retry_count); cudaFree(b.max_M);
+    if (h->h_hint) cudaFreeHost(h->h_hint);
+    for (int i = 0; i < slam_filter::HINT_RING; ++i) if (h->hint_ev[i]) cudaEventDestroy(h->hint_ev[i]);
     cudaFree(h->d_fwd); cudaFree(h->d_ang); cudaFree(h->d_meas); cudaFree(h->d_nmeas);
     cudaFree(h->d_traj_fwd); cudaFree(h->d_traj_ang); cudaFree(h->d_out);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -151,6 +166,14 @@ int slam_synchronize(slam_handle_t h) { if (!h) return 1; CK(cudaStreamSynchroni
 int slam_batch(slam_handle_t h) { return h ? h->b.batch : 0; }
 int slam_kind(slam_handle_t h) { return h ? h->kind : 0; }
 long long slam_kernel_launches(slam_handle_t h) { return h ? h->launches : 0; }
+
+int slam_tune(slam_handle_t h, int key, int value) {
+    if (!h) return 1;
+    if (key == 0) h->cap_force = value;
+    else if (key == 1) h->cap_headroom = value;
+    else return fail(h, "slam_tune: unknown key");
+    return 0;
+}
 
 int slam_build_info(char* buf, int cap) {
     return snprintf(buf, cap, "sm_100a; nvcc %d.%d; kernels: ekf_step_kernel ukf_step_kernel sim_step_kernel", __CUDACC_VER_MAJOR__, __CUDACC_VER_MINOR__);
@@ -181,10 +204,9 @@ int slam_init(slam_handle_t h, float x_0, float y_0, float yaw_0) {
         CK(cudaStreamSynchronize(h->stream));   // Ps / xs are pageable host vectors
     }
     CK(cudaMemsetAsync(b.ids, 0, sizeof(int) * (size_t)b.batch * b.max_lm, h->stream));
-    CK(cudaMemsetAsync(b.M, 0, sizeof(int) * b.batch, h->stream));
-    CK(cudaMemsetAsync(b.timestep, 0, sizeof(int) * b.batch, h->stream));
-    CK(cudaMemsetAsync(b.status, 0, sizeof(int) * b.batch, h->stream));
-    CK(cudaMemsetAsync(b.n_assoc, 0, sizeof(int) * b.batch, h->stream));
+    CK(cudaMemsetAsync(b.meta, 0, sizeof(int4) * b.batch, h->stream));
+    CK(cudaMemsetAsync(b.max_M, 0, sizeof(int), h->stream));
+    h->step_seq = 0; h->hint_base = 0;
     CK(cudaMemsetAsync(b.assoc, 0xff, sizeof(int) * (size_t)b.batch * b.max_meas, h->stream));
     CK(cudaMemsetAsync(b.stats, 0, sizeof(double) * (size_t)b.batch * SLAM_NUM_STATS, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -205,10 +227,25 @@ static int do_step(slam_filter* h, const float* d_fwd, const float* d_ang, int c
         }
         CK(cudaEventRecord(h->ev[h->ev_used], h->stream));
     }
-    if (h->kind == SLAM_EKF_SLAM) CK(launch_ekf_step(h->b, h->fc, in, phases, h->stream));
+    // capacity for this launch: max(M) as it was HINT_LAG launches ago (its copy has long completed, so the wait
+    // below never blocks in steady state but bounds how far the host can run ahead) plus headroom
+    int cap = h->b.max_lm;
+    if (h->cap_force > 0) cap = h->cap_force;
+    else if (h->step_seq >= slam_filter::HINT_LAG) {
+        const int slot = (int)((h->step_seq - slam_filter::HINT_LAG) % slam_filter::HINT_RING);
+        CK(cudaEventSynchronize(h->hint_ev[slot]));
+        cap = h->h_hint[slot] + h->cap_headroom;
+    } else cap = h->hint_base + (int)(h->step_seq + 1) * h->b.max_meas;      // M can grow by at most max_meas per step
+    if (h->kind == SLAM_EKF_SLAM) CK(launch_ekf_step(h->b, h->fc, in, phases, cap, h->stream));
     else CK(launch_ukf_step(h->b, h->fc, in, h->stream));
     if (h->profiling) { CK(cudaEventRecord(h->ev[h->ev_used + 1], h->stream)); h->ev_used += 2; }
-    h->launches += 1;
+    {
+        const int slot = (int)(h->step_seq % slam_filter::HINT_RING);
+        CK(cudaMemcpyAsync(&h->h_hint[slot], h->b.max_M, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(h->hint_ev[slot], h->stream));
+        h->step_seq += 1;
+    }
+    h->launches += (cap < h->b.max_lm) ? 2 : 1;
     return 0;
 }
 
@@ -265,16 +302,25 @@ static int check_inst(slam_filter* h, int inst) {
     if (inst < 0 || inst >= h->b.batch) return fail(h, "instance index out of range");
     return 0;
 }
-static int get_int(slam_filter* h, const int* d_arr, int inst, int* out) {
+enum { META_M = 0, META_STATUS = 1, META_TIMESTEP = 2, META_NASSOC = 3 };
+static int get_meta(slam_filter* h, int field, int inst, int* out) {
     if (check_inst(h, inst)) return 1;
     CK(cudaSetDevice(h->device));
-    CK(cudaMemcpyAsync(out, d_arr + inst, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(out, reinterpret_cast<const int*>(h->b.meta + inst) + field, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
-int slam_get_timestep(slam_handle_t h, int inst, int* t) { return get_int(h, h ? h->b.timestep : nullptr, inst, t); }
-int slam_get_num_landmarks(slam_handle_t h, int inst, int* M) { return get_int(h, h ? h->b.M : nullptr, inst, M); }
-int slam_get_status(slam_handle_t h, int inst, int* s) { return get_int(h, h ? h->b.status : nullptr, inst, s); }
+static int get_meta_all(slam_filter* h, int field, int* out) {
+    if (!h) return 1;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy2DAsync(out, sizeof(int), reinterpret_cast<const int*>(h->b.meta) + field, sizeof(int4), sizeof(int),
+                         h->b.batch, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int slam_get_timestep(slam_handle_t h, int inst, int* t) { return get_meta(h, META_TIMESTEP, inst, t); }
+int slam_get_num_landmarks(slam_handle_t h, int inst, int* M) { return get_meta(h, META_M, inst, M); }
+int slam_get_status(slam_handle_t h, int inst, int* s) { return get_meta(h, META_STATUS, inst, s); }
 
 int slam_get_state(slam_handle_t h, int inst, double* x, int* n) {
     int M = 0;
@@ -325,7 +371,7 @@ int slam_get_landmark_ids(slam_handle_t h, int inst, int* ids, int* M) {
 
 int slam_get_assoc(slam_handle_t h, int inst, int* slot, int* k) {
     int kk = 0;
-    if (get_int(h, h ? h->b.n_assoc : nullptr, inst, &kk)) return 1;
+    if (get_meta(h, META_NASSOC, inst, &kk)) return 1;
     if (kk > 0) {
         CK(cudaMemcpyAsync(slot, h->b.assoc + (size_t)inst * h->b.max_meas, sizeof(int) * kk, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -349,32 +395,27 @@ int slam_get_poses(slam_handle_t h, double* xyyaw) {
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
-int slam_get_all_status(slam_handle_t h, int* status) {
-    if (!h) return 1;
-    CK(cudaMemcpyAsync(status, h->b.status, sizeof(int) * h->b.batch, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    return 0;
-}
-int slam_get_all_num_landmarks(slam_handle_t h, int* M) {
-    if (!h) return 1;
-    CK(cudaMemcpyAsync(M, h->b.M, sizeof(int) * h->b.batch, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    return 0;
-}
+int slam_get_all_status(slam_handle_t h, int* status) { return get_meta_all(h, META_STATUS, status); }
+int slam_get_all_num_landmarks(slam_handle_t h, int* M) { return get_meta_all(h, META_M, M); }
 
 int slam_set_state(slam_handle_t h, int inst, const double* x, const double* P, const int* ids, int M, int timestep) {
     if (check_inst(h, inst)) return 1;
     if (M < 0 || M > h->b.max_lm) return fail(h, "slam_set_state: M out of range");
     CK(cudaSetDevice(h->device));
     const int nn = h->b.base + 2 * M, ld = ldg_of(nn);
-    const int zero = 0;
+    const int4 meta = make_int4(M, 0, timestep, 0);
     CK(cudaMemcpyAsync(h->b.x + (size_t)inst * h->b.x_stride, x, sizeof(double) * nn, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpy2DAsync(h->b.P + (size_t)inst * h->b.p_stride, sizeof(double) * ld, P, sizeof(double) * nn,
                          sizeof(double) * nn, nn, cudaMemcpyHostToDevice, h->stream));
     if (M > 0) CK(cudaMemcpyAsync(h->b.ids + (size_t)inst * h->b.max_lm, ids, sizeof(int) * M, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->b.M + inst, &M, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->b.timestep + inst, &timestep, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->b.status + inst, &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->b.meta + inst, &meta, sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    {   // the capacity hint must not be below the state just loaded
+        int cur = 0;
+        CK(cudaMemcpyAsync(&cur, h->b.max_M, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (M > cur) CK(cudaMemcpyAsync(h->b.max_M, &M, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        h->step_seq = 0; h->hint_base = M > cur ? M : cur;   // next launches size conservatively again
+    }
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -503,6 +544,8 @@ int slam_reset(slam_handle_t h, float x_0, float y_0, float yaw_0) {
     double a2 = yaw_0, a3 = 0.0;
     if (h->b.base == 4) { a2 = (double)(float)std::cos((double)yaw_0); a3 = (double)(float)std::sin((double)yaw_0); }   // ukf.cpp:33 (D-1)
     CK(launch_reset(h->b, (double)x_0, (double)y_0, a2, a3, h->stream));
+    CK(cudaMemsetAsync(h->b.max_M, 0, sizeof(int), h->stream));
+    h->step_seq = 0; h->hint_base = 0;
     h->launches += 1;
     return 0;
 }

@@ -19,18 +19,18 @@ namespace slam {
 //                              cp.async.bulk); only n*ldg(n) doubles are live and only they cross HBM.
 //   x      [batch][x_stride]   committed state x_t (EKF: x,y,yaw,lm.. ; UKF: x,y,cos,sin,lm..)
 //   ids    [batch][max_lm]     lm_IDs (filter.h:70)
-//   M, timestep, status [batch]
+//   meta   [batch] int4 {M, status, timestep, n_assoc}
 //   assoc  [batch][max_meas]   slot index (or -1) chosen for each measurement of the last step
 // ---------------------------------------------------------------------------------------------
 struct BatchState {
     double* P;
     double* x;
     int* ids;
-    int* M;
-    int* timestep;
-    int* status;
+    int4* meta;        // [batch] {M, status, timestep, n_assoc}: one 16-byte load per instance at kernel entry
     int* assoc;
-    int* n_assoc;
+    int* retry_list;   // [batch] instances deferred by a capacity-limited launch
+    int* retry_count;  // [1]
+    int* max_M;        // [1] running max of M over the batch (capacity hint for the next launches)
     double* stats;     // [batch][SLAM_NUM_STATS] per-instance accumulators
     double* sigma;     // UKF only: [batch][sigma_stride] sigma points X (point-major), optional
     long long p_stride;
@@ -141,7 +141,7 @@ struct StepInputs {
 
 enum { STEP_PREDICT = 1, STEP_UPDATE = 2 };
 
-cudaError_t launch_ekf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, int phases, cudaStream_t st);
+cudaError_t launch_ekf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, int phases, int cap_hint, cudaStream_t st);
 size_t ekf_step_smem_bytes(const BatchState& b);
 cudaError_t ekf_step_configure(const BatchState& b);
 

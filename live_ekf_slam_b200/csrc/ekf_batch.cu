@@ -15,8 +15,17 @@
 
 namespace slam {
 
-constexpr int EKF_THREADS = 256;
-constexpr int EKF_WARPS = EKF_THREADS / 32;
+// Launch geometry.  Shared memory is sized for the landmark capacity of THIS launch (cap_lm <= max_lm), chosen
+// by the host from a slightly stale device-side max(M) plus headroom, so that early in a run -- while the map
+// is still small -- many more CTAs fit per SM.  An instance whose M + detections could exceed cap_lm is
+// deferred untouched to a retry list that a second, full-capacity launch drains (correctness never depends
+// on the hint).
+struct EkfLaunch {
+    int cap_lm;        // landmark capacity of this launch's shared-memory tile
+    int n_cap;         // 3 + 2*cap_lm
+    int lds;           // shared-memory leading dimension for n_cap
+    int from_list;     // 0: instance = blockIdx.x ; 1: instances come from b.retry_list (persistent loop)
+};
 
 struct EkfSmem {
     double* P;      // n_max x lds
@@ -33,18 +42,18 @@ struct EkfSmem {
     uint64_t* bar;
 };
 
-__host__ __device__ inline size_t ekf_smem_carve(const BatchState& b, unsigned char* base, EkfSmem* s) {
+__host__ __device__ inline size_t ekf_smem_carve(const BatchState& b, const EkfLaunch& L, unsigned char* base, EkfSmem* s) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
-    const int nmp = ldg_of(b.n_max);
-    size_t oP = take(sizeof(double) * (size_t)b.n_max * b.lds);
+    const int nmp = ldg_of(L.n_cap);
+    size_t oP = take(sizeof(double) * (size_t)L.n_cap * L.lds);
     size_t ox = take(sizeof(double) * nmp);
     size_t oxs = take(sizeof(double) * nmp);
-    size_t oHP = take(sizeof(double) * 2 * b.lds);
+    size_t oHP = take(sizeof(double) * 2 * L.lds);
     size_t oPH = take(sizeof(double) * 2 * nmp);
     size_t oK = take(sizeof(double) * 2 * nmp);
     size_t osc = take(sizeof(double) * 32);
-    size_t oids = take(sizeof(int) * (b.max_lm + 1));
+    size_t oids = take(sizeof(int) * (L.cap_lm + 1));
     size_t omeas = take(sizeof(float) * 3 * b.max_meas);
     size_t oassoc = take(sizeof(int) * b.max_meas);
     size_t oi = take(sizeof(int) * 8);
@@ -61,27 +70,35 @@ __host__ __device__ inline size_t ekf_smem_carve(const BatchState& b, unsigned c
 // scalar slots in sc[]
 enum { SC_H = 0 /*10*/, SC_NU = 10 /*2*/, SC_XD = 12, SC_YD = 13, SC_CB = 14, SC_SB = 15 };
 
-__global__ void __launch_bounds__(EKF_THREADS, 2)
-ekf_step_kernel(BatchState b, FilterConst fc, StepInputs in, int phases) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    EkfSmem s;
-    ekf_smem_carve(b, smem_raw, &s);
+// One reference EKF::update for instance `inst`.  Returns true when the mbarrier phase `parity` was consumed.
+template <int THREADS>
+__device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterConst& fc, const StepInputs& in,
+                                             const int phases, const EkfLaunch& L, const EkfSmem& s, const int inst,
+                                             const uint32_t parity) {
+    constexpr int WARPS = THREADS / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int inst = blockIdx.x;
-    const int lds = b.lds;
+    const int lds = L.lds;
 
-    const int status_in = b.status[inst];
-    if (status_in & SLAM_STATUS_SAME_STEP_REMATCH) return;   // the reference process is dead past this point
-    int M = b.M[inst];
+    const int4 meta_in = b.meta[inst];
+    int nm = 0;
+    if (phases & STEP_UPDATE) nm = in.n_meas[inst];
+    const int status_in = meta_in.y;
+    if (status_in & SLAM_STATUS_SAME_STEP_REMATCH) return false;   // the reference process is dead past this point
+    int M = meta_in.x;
     const int M_start = M;
     int n = 3 + 2 * M;
     int status = status_in;
+    if (nm > b.max_meas) { nm = b.max_meas; status |= SLAM_STATUS_MEAS_OVERFLOW; }
+    if (M + nm > L.cap_lm && L.cap_lm < b.max_lm) {
+        // this launch's tile may be too small for the insertions of this step: defer, untouched
+        if (tid == 0) b.retry_list[atomicAdd(b.retry_count, 1)] = inst;
+        return false;
+    }
     double* gP = b.P + (size_t)inst * b.p_stride;
     double* gx = b.x + (size_t)inst * b.x_stride;
 
     // ---- stage P: one bulk copy per live row, all completing on one mbarrier
-    if (tid == 0) { mbar_init(s.bar, 1); fence_mbar_init(); s.iscr[0] = INT_MAX; s.iscr[1] = INT_MAX; s.iscr[2] = 0; }
-    __syncthreads();
+    if (tid == 0) { s.iscr[0] = INT_MAX; s.iscr[1] = INT_MAX; s.iscr[2] = 0; }
     {
         const int ldg = ldg_of(n);
         if (warp == 0) {
@@ -92,14 +109,9 @@ ekf_step_kernel(BatchState b, FilterConst fc, StepInputs in, int phases) {
         }
     }
     // ---- meanwhile: state, ids, messages
-    for (int i = tid; i < n; i += EKF_THREADS) { const double v = gx[i]; s.x[i] = v; s.xs[i] = v; }
-    for (int i = tid; i < M; i += EKF_THREADS) s.ids[i] = b.ids[(size_t)inst * b.max_lm + i];
-    int nm = 0;
-    if (phases & STEP_UPDATE) {
-        nm = in.n_meas[inst];
-        if (nm > b.max_meas) { nm = b.max_meas; status |= SLAM_STATUS_MEAS_OVERFLOW; }
-        for (int i = tid; i < 3 * nm; i += EKF_THREADS) s.meas[i] = in.meas[(size_t)inst * b.max_meas * 3 + i];
-    }
+    for (int i = tid; i < n; i += THREADS) { const double v = gx[i]; s.x[i] = v; s.xs[i] = v; }
+    for (int i = tid; i < M; i += THREADS) s.ids[i] = b.ids[(size_t)inst * b.max_lm + i];
+    for (int i = tid; i < 3 * nm; i += THREADS) s.meas[i] = in.meas[(size_t)inst * b.max_meas * 3 + i];
     __syncthreads();
 
     // ---- PREDICT, ekf.cpp:43-61
@@ -118,17 +130,17 @@ ekf_step_kernel(BatchState b, FilterConst fc, StepInputs in, int phases) {
             s.x[2] = remainder(s.xs[2] + (double)d_th + (double)fc.v_th, TWO_PI_REF);   // :59
         }
     }
-    mbar_wait(s.bar, 0);
+    mbar_wait(s.bar, parity);
     if (phases & STEP_PREDICT) {
         // T = F_x P : rows 0,1 pick up row 2
-        for (int j = tid; j < n; j += EKF_THREADS) {
+        for (int j = tid; j < n; j += THREADS) {
             const double p2 = s.P[2 * lds + j];
             s.P[j] = s.P[j] + fa * p2;
             s.P[lds + j] = s.P[lds + j] + fb * p2;
         }
         __syncthreads();
         // P' = T F_x^T : cols 0,1 pick up col 2 ; + (F_v V) F_v^T on the vehicle block
-        for (int i = tid; i < n; i += EKF_THREADS) {
+        for (int i = tid; i < n; i += THREADS) {
             const double t2 = s.P[i * lds + 2];
             double p0 = s.P[i * lds + 0] + t2 * fa;
             double p1 = s.P[i * lds + 1] + t2 * fb;
@@ -159,14 +171,14 @@ ekf_step_kernel(BatchState b, FilterConst fc, StepInputs in, int phases) {
             }
             __syncthreads();
             const double xd = s.sc[SC_XD], yd = s.sc[SC_YD];
-            for (int j = tid; j < M; j += EKF_THREADS) {
+            for (int j = tid; j < M; j += THREADS) {
                 const float x_diff = (float)fabs(xd - s.x[3 + 2 * j]);     // :91
                 const float y_diff = (float)fabs(yd - s.x[4 + 2 * j]);     // :92
                 if (x_diff < fc.min_sep && y_diff < fc.min_sep) { cand = j; break; }   // first match per thread
             }
         } else {
             id = (int)s.meas[3 * l];                                       // :101
-            for (int j = tid; j < M; j += EKF_THREADS)
+            for (int j = tid; j < M; j += THREADS)
                 if (s.ids[j] == id) { cand = j; break; }
         }
         cand = __reduce_min_sync(0xffffffffu, cand);
@@ -204,8 +216,8 @@ ekf_step_kernel(BatchState b, FilterConst fc, StepInputs in, int phases) {
             for (int q = 0; q < 10; ++q) H[q] = s.sc[SC_H + q];
             const int hc3 = i, hc4 = i + 1;
             // -- phase A: H P (2 x n) on the low half of the CTA, P H^T (n x 2) on the high half
-            if (tid < EKF_THREADS / 2) {
-                for (int j = tid; j < ldg_of(n); j += EKF_THREADS / 2) {
+            if (tid < THREADS / 2) {
+                for (int j = tid; j < ldg_of(n); j += THREADS / 2) {
                     double h0 = 0.0, h1 = 0.0;
                     if (j < n) {
                         const double p0 = s.P[j], p1 = s.P[lds + j], p2 = s.P[2 * lds + j];
@@ -216,7 +228,7 @@ ekf_step_kernel(BatchState b, FilterConst fc, StepInputs in, int phases) {
                     s.HP[j] = h0; s.HP[lds + j] = h1;
                 }
             } else {
-                for (int q = tid - EKF_THREADS / 2; q < n; q += EKF_THREADS / 2) {
+                for (int q = tid - THREADS / 2; q < n; q += THREADS / 2) {
                     const double* row = s.P + (size_t)q * lds;
                     const double p0 = row[0], p1 = row[1], p2 = row[2], p3 = row[hc3], p4 = row[hc4];
                     double a0 = p0 * H[0]; a0 += p1 * H[1]; a0 += p2 * H[2]; a0 += p3 * H[3]; a0 += p4 * H[4];
@@ -249,7 +261,7 @@ ekf_step_kernel(BatchState b, FilterConst fc, StepInputs in, int phases) {
                     y1 = b1c1 - l10 * b0c1; i11 = y1 / u11; i01 = (b0c1 - a01 * i11) / a00;
                 }
                 const double nu0 = s.sc[SC_NU], nu1 = s.sc[SC_NU + 1];
-                for (int q = tid; q < n; q += EKF_THREADS) {
+                for (int q = tid; q < n; q += THREADS) {
                     const double ph0 = s.PH[2 * q], ph1 = s.PH[2 * q + 1];
                     const double k0 = ph0 * i00 + ph1 * i10;
                     const double k1 = ph0 * i01 + ph1 * i11;
@@ -262,21 +274,38 @@ ekf_step_kernel(BatchState b, FilterConst fc, StepInputs in, int phases) {
             __syncthreads();
             // -- phase C: P -= K (H P), :140 as a rank-2 update over the packed row width
             {
+                // warp w owns rows w, w+8, ...; a lane owns one double2 column pair per 32-pair chunk and keeps
+                // its two (H P) pairs in registers for the whole sweep; 4 rows in flight per iteration.
                 const int hp = ldg_of(n) >> 1;               // double2 per row
-                const int total = n * hp;
-                const int di = EKF_THREADS / hp, dj = EKF_THREADS % hp;
-                int ri = tid / hp, rj = tid % hp;
-                for (int e = tid; e < total; e += EKF_THREADS) {
-                    const double2 k = *reinterpret_cast<const double2*>(s.K + 2 * ri);
-                    const double2 h0 = *reinterpret_cast<const double2*>(s.HP + 2 * rj);
-                    const double2 h1 = *reinterpret_cast<const double2*>(s.HP + lds + 2 * rj);
-                    double2* pp = reinterpret_cast<double2*>(s.P + (size_t)ri * lds + 2 * rj);
-                    double2 p = *pp;
-                    p.x = p.x - (k.x * h0.x + k.y * h1.x);
-                    p.y = p.y - (k.x * h0.y + k.y * h1.y);
-                    *pp = p;
-                    ri += di; rj += dj;
-                    if (rj >= hp) { rj -= hp; ri += 1; }
+                for (int c0 = 0; c0 < hp; c0 += 32) {
+                    const int jp = c0 + lane;
+                    if (jp < hp) {
+                        const double2 h0 = *reinterpret_cast<const double2*>(s.HP + 2 * jp);
+                        const double2 h1 = *reinterpret_cast<const double2*>(s.HP + lds + 2 * jp);
+                        double* col = s.P + 2 * jp;
+                        int row = warp;
+                        for (; row + 3 * WARPS < n; row += 4 * WARPS) {
+                            double2 k[4], p[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                k[u] = *reinterpret_cast<const double2*>(s.K + 2 * (row + u * WARPS));
+                                p[u] = *reinterpret_cast<const double2*>(col + (size_t)(row + u * WARPS) * lds);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                p[u].x = p[u].x - (k[u].x * h0.x + k[u].y * h1.x);
+                                p[u].y = p[u].y - (k[u].x * h0.y + k[u].y * h1.y);
+                                *reinterpret_cast<double2*>(col + (size_t)(row + u * WARPS) * lds) = p[u];
+                            }
+                        }
+                        for (; row < n; row += WARPS) {
+                            const double2 k = *reinterpret_cast<const double2*>(s.K + 2 * row);
+                            double2 p = *reinterpret_cast<const double2*>(col + (size_t)row * lds);
+                            p.x = p.x - (k.x * h0.x + k.y * h1.x);
+                            p.y = p.y - (k.x * h0.y + k.y * h1.y);
+                            *reinterpret_cast<double2*>(col + (size_t)row * lds) = p;
+                        }
+                    }
                 }
             }
             __syncthreads();
@@ -291,7 +320,7 @@ ekf_step_kernel(BatchState b, FilterConst fc, StepInputs in, int phases) {
             const double cb = s.sc[SC_CB], sb = s.sc[SC_SB];
             const double g02 = -(double)r * sb, g12 = (double)r * cb;      // G_x(0,2), G_x(1,2), :162,165
             // rows n, n+1 over old columns; columns n, n+1 over old rows
-            for (int j = tid; j < n; j += EKF_THREADS) {
+            for (int j = tid; j < n; j += THREADS) {
                 const double p0 = s.P[j], p1 = s.P[lds + j], p2 = s.P[2 * lds + j];
                 double t0 = 1.0 * p0; t0 += 0.0 * p1; t0 += g02 * p2;
                 double t1 = 0.0 * p0; t1 += 1.0 * p1; t1 += g12 * p2;
@@ -335,24 +364,23 @@ ekf_step_kernel(BatchState b, FilterConst fc, StepInputs in, int phases) {
     // ---- commit, :176-177
     if (dead) {
         // frozen at the last committed state: nothing but the status word changes
-        if (tid == 0) { b.status[inst] = status; b.n_assoc[inst] = 0; }
-        return;
+        if (tid == 0) b.meta[inst] = make_int4(meta_in.x, status, meta_in.z, 0);
+        return true;
     }
-    for (int i = tid; i < n; i += EKF_THREADS) {
+    for (int i = tid; i < n; i += THREADS) {
         const double v = s.x[i];
         gx[i] = v;
         if (!isfinite(v) || !isfinite(s.P[(size_t)i * lds + i])) s.iscr[2] = 1;
     }
-    for (int i = tid + M_start; i < M; i += EKF_THREADS) b.ids[(size_t)inst * b.max_lm + i] = s.ids[i];
-    for (int i = tid; i < nm; i += EKF_THREADS) b.assoc[(size_t)inst * b.max_meas + i] = s.assoc[i];
+    for (int i = tid + M_start; i < M; i += THREADS) b.ids[(size_t)inst * b.max_lm + i] = s.ids[i];
+    for (int i = tid; i < nm; i += THREADS) b.assoc[(size_t)inst * b.max_meas + i] = s.assoc[i];
     fence_proxy_async();     // generic-proxy writes of P must be visible to the bulk-copy engine
     __syncthreads();
     if (tid == 0) {
         if (s.iscr[2]) status |= SLAM_STATUS_NAN;
-        b.M[inst] = M;
-        b.status[inst] = status;
-        if (phases & STEP_UPDATE) b.n_assoc[inst] = nm;
-        if (phases & STEP_PREDICT) b.timestep[inst] += 1;                  // :39
+        b.meta[inst] = make_int4(M, status, meta_in.z + ((phases & STEP_PREDICT) ? 1 : 0),   // timestep, :39
+                                 (phases & STEP_UPDATE) ? nm : meta_in.w);
+        if (M > M_start) atomicMax(b.max_M, M);
         // algorithmic work of this update, using the live n at the end of the step
         double* st = b.stats + (size_t)inst * SLAM_NUM_STATS;
         const double nd = (double)n;
@@ -368,6 +396,28 @@ ekf_step_kernel(BatchState b, FilterConst fc, StepInputs in, int phases) {
         bulk_commit();
         bulk_wait_all();
     }
+    return true;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS >= 256) ? 2 : 6)
+ekf_step_kernel(BatchState b, FilterConst fc, StepInputs in, int phases, EkfLaunch L) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EkfSmem s;
+    ekf_smem_carve(b, L, smem_raw, &s);
+    if (threadIdx.x == 0) { mbar_init(s.bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    if (!L.from_list) {
+        ekf_instance<THREADS>(b, fc, in, phases, L, s, (int)blockIdx.x, 0u);
+        return;
+    }
+    // retry pass: a persistent grid drains the list of instances the capacity-limited launch deferred
+    const int count = *b.retry_count;
+    uint32_t parity = 0;
+    for (int q = blockIdx.x; q < count; q += gridDim.x) {
+        if (ekf_instance<THREADS>(b, fc, in, phases, L, s, b.retry_list[q], parity)) parity ^= 1u;
+        __syncthreads();
+    }
 }
 
 // Filter::init on the device (ekf.cpp:8-18,29-34 / ukf.cpp:7-18,31-45): one thread per instance writes x_0 and the
@@ -382,7 +432,7 @@ __global__ void reset_kernel(BatchState b, double x0, double y0, double a2, doub
     for (int r = 0; r < nb; ++r) for (int c = 0; c < ld; ++c) P[r * ld + c] = 0.0;
     P[0] = 0.01 * 0.01; P[ld + 1] = 0.01 * 0.01; P[2 * ld + 2] = 0.005 * 0.005;
     if (nb == 4) P[3 * ld + 3] = 0.005 * 0.005;
-    b.M[i] = 0; b.timestep[i] = 0; b.status[i] = 0; b.n_assoc[i] = 0;
+    b.meta[i] = make_int4(0, 0, 0, 0);
     double* st = b.stats + (size_t)i * SLAM_NUM_STATS;
     for (int k = 0; k < SLAM_NUM_STATS; ++k) st[k] = 0.0;
 }
@@ -392,14 +442,43 @@ cudaError_t launch_reset(const BatchState& b, double x0, double y0, double a2, d
     return cudaGetLastError();
 }
 
-size_t ekf_step_smem_bytes(const BatchState& b) { return ekf_smem_carve(b, nullptr, nullptr); }
-
-cudaError_t ekf_step_configure(const BatchState& b) {
-    return cudaFuncSetAttribute(ekf_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ekf_step_smem_bytes(b));
+static EkfLaunch make_launch(const BatchState& b, int cap_lm, int from_list) {
+    EkfLaunch L;
+    L.cap_lm = cap_lm < b.max_lm ? cap_lm : b.max_lm;
+    if (L.cap_lm < 1) L.cap_lm = 1;
+    L.n_cap = 3 + 2 * L.cap_lm;
+    L.lds = lds_of(L.n_cap);
+    L.from_list = from_list;
+    return L;
 }
 
-cudaError_t launch_ekf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, int phases, cudaStream_t st) {
-    ekf_step_kernel<<<b.batch, EKF_THREADS, ekf_step_smem_bytes(b), st>>>(b, fc, in, phases);
+size_t ekf_step_smem_bytes(const BatchState& b) { return ekf_smem_carve(b, make_launch(b, b.max_lm, 0), nullptr, nullptr); }
+
+cudaError_t ekf_step_configure(const BatchState& b) {
+    const int bytes = (int)ekf_step_smem_bytes(b);
+    cudaError_t e = cudaFuncSetAttribute(ekf_step_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(ekf_step_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+// cap_hint: landmark capacity to size this launch for (<= 0 or >= max_lm: full capacity, no retry pass).
+cudaError_t launch_ekf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, int phases, int cap_hint,
+                            cudaStream_t st) {
+    const bool limited = cap_hint > 0 && cap_hint < b.max_lm;
+    const EkfLaunch L = make_launch(b, limited ? cap_hint : b.max_lm, 0);
+    const size_t smem = ekf_smem_carve(b, L, nullptr, nullptr);
+    if (limited) {
+        cudaError_t e = cudaMemsetAsync(b.retry_count, 0, sizeof(int), st);
+        if (e != cudaSuccess) return e;
+    }
+    // small tiles: 128-thread CTAs (the O(n^2) sweep is short and more CTAs fit per SM)
+    if (L.n_cap <= 67) ekf_step_kernel<128><<<b.batch, 128, smem, st>>>(b, fc, in, phases, L);
+    else ekf_step_kernel<256><<<b.batch, 256, smem, st>>>(b, fc, in, phases, L);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || !limited) return e;
+    const EkfLaunch R = make_launch(b, b.max_lm, 1);
+    const int grid = b.batch < 296 ? b.batch : 296;
+    ekf_step_kernel<256><<<grid, 256, ekf_smem_carve(b, R, nullptr, nullptr), st>>>(b, fc, in, phases, R);
     return cudaGetLastError();
 }
 

@@ -72,7 +72,7 @@ __global__ void accumulate_error_kernel(BatchState b, SimState s) {
     if (i >= b.batch) return;
     const double* x = b.x + (size_t)i * b.x_stride;
     const double* P = b.P + (size_t)i * b.p_stride;
-    const int n = b.base + 2 * b.M[i];
+    const int n = b.base + 2 * b.meta[i].x;
     const int ld = ldg_of(n);
     const double* tr = s.truth + 3 * (size_t)i;
     double yaw, C[3][3];
@@ -128,8 +128,9 @@ __global__ void reduce_stats_kernel(BatchState b, double* out) {
         const double* st = b.stats + (size_t)i * SLAM_NUM_STATS;
         for (int k = 0; k < 6; ++k) acc[k] += st[k];
         for (int k = 8; k < SLAM_NUM_STATS; ++k) acc[k] += st[k];
-        acc[6] += (b.status[i] != 0) ? 1.0 : 0.0;
-        acc[7] += (double)b.M[i];
+        const int4 m = b.meta[i];
+        acc[6] += (m.y != 0) ? 1.0 : 0.0;
+        acc[7] += (double)m.x;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int k = 0; k < SLAM_NUM_STATS; ++k) {

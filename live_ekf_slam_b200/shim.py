@@ -31,7 +31,7 @@ ABI_SYMBOLS = (
     "slam_sim_meas", "slam_sim_n_meas", "slam_sim_get_truth", "slam_sim_get_meas",
     "slam_run", "slam_run_device", "slam_reset", "slam_step_io", "slam_set_profiling", "slam_get_profile",
     "slam_accumulate_error", "slam_get_stats", "slam_reset_stats",
-    "slam_kernel_launches", "slam_build_info",
+    "slam_kernel_launches", "slam_build_info", "slam_tune",
 )
 
 _lib = None
@@ -97,6 +97,7 @@ def load(path: str | None = None):
     L.slam_kernel_launches.argtypes = [vp]
     L.slam_kernel_launches.restype = C.c_longlong
     L.slam_build_info.argtypes = [C.c_char_p, C.c_int]
+    L.slam_tune.argtypes = [vp, C.c_int, C.c_int]
     if path is None:
         _lib = L
     return L
@@ -282,6 +283,9 @@ class FilterBatch:
     def step_io(self, fwd, ang, cmd_stride: int, meas, n_meas, poses_out):
         """slam_step_io with caller-owned (ideally pinned) host buffers; asynchronous."""
         self._ck(self._L.slam_step_io(self._h, _ptr(fwd), _ptr(ang), cmd_stride, _ptr(meas), _ptr(n_meas), _ptr(poses_out)))
+
+    def tune(self, key: int, value: int):
+        self._ck(self._L.slam_tune(self._h, key, value))
 
     def set_profiling(self, on: bool):
         self._ck(self._L.slam_set_profiling(self._h, int(on)))

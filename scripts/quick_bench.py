@@ -16,10 +16,11 @@ def main():
     p, lm, fwd, ang = H.config2(seed=0, steps=T)
     fb = shim.FilterBatch(kind, p.to_c(), B, 50, 8)
     sim = shim.Simulator(fb, lm, seed=1)
-    for rep in range(3):
+    reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+    for rep in range(reps):
         fb.reset(0, 0, 0)
         sim.reset()
-        fb.set_profiling(rep == 2)
+        fb.set_profiling(rep == reps - 1)
         fb.synchronize()
         t0 = time.time()
         sim.run(fwd, ang)
@@ -27,7 +28,7 @@ def main():
         dt = time.time() - t0
         s = fb.stats()
         line = f"rep {rep}: {dt*1e3:.1f} ms  {B*T/dt/1e6:.2f} M updates/s  alg GB/s {s[8]/dt/1e9:.0f}  mean n {s[10]/s[0]:.1f} mean k {s[11]/s[0]:.2f} pos err {s[4]/s[0]:.3f} bad {s[6]}"
-        if rep == 2:
+        if rep == reps - 1:
             ms, n = fb.profile()
             line += f" | step kernel {ms:.1f} ms over {n} launches -> alg GB/s {s[8]/ms/1e6:.0f}"
         print(line, flush=True)

@@ -247,3 +247,30 @@ def test_filter_classes_mirror_reference_interface(shim, oracle):
     bad.filter = "nope"
     with pytest.raises(RuntimeError):
         make_filter(bad)
+
+
+@pytest.mark.parametrize("cap", [1, 6, 20])
+def test_capacity_limited_launch_and_retry_pass(shim, oracle, cap):
+    """The first pass is sized for `cap` landmarks; instances that might outgrow it are deferred untouched to the
+    full-capacity retry pass.  Results must not depend on the split."""
+    p, lm, fwd, ang = H.config2(seed=12, steps=220)
+    op = H.oracle_params(oracle, p)
+    B = 12
+    fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), B, 50, 8)
+    fb.tune(0, cap)
+    fb.init(0, 0, 0)
+    streams = [H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=21, instance=i)[0] for i in range(B)]
+    ofs = []
+    for i in range(B):
+        of = oracle.OracleFilter(oracle.EKF_SLAM, op, 50)
+        of.init(0, 0, 0)
+        ofs.append(of)
+    for t in range(len(fwd)):
+        meas, n = fb.pack_meas([streams[i][t] for i in range(B)])
+        fb.step(fwd[t], ang[t], meas, n)
+        for i in range(B):
+            ofs[i].update(fwd[t], ang[t], streams[i][t], oracle.STRUCTURED)
+    for i in range(B):
+        _compare(fb, i, ofs[i])
+        assert fb.timestep(i) == len(fwd)
+    assert max(o.M for o in ofs) > 6
