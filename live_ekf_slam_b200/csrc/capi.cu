@@ -108,6 +108,7 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
     b.x_stride = ldg_of(b.n_max);
     b.p_stride = (long long)b.n_max * ldg_of(b.n_max);
     b.sigma_stride = 0;
+    b.fixed_ld = (kind == SLAM_UKF_SLAM) ? ldg_of(b.n_max) : 0;
 
     const size_t smem = (kind == SLAM_EKF_SLAM) ? ekf_step_smem_bytes(b) : ukf_step_smem_bytes(b);
     if (smem > (size_t)prop.sharedMemPerBlockOptin) {
@@ -184,7 +185,7 @@ int slam_init(slam_handle_t h, float x_0, float y_0, float yaw_0) {
     if (!h) return 1;
     CK(cudaSetDevice(h->device));
     BatchState& b = h->b;
-    const int nb = b.base, ld = ldg_of(nb);
+    const int nb = b.base, ld = ldp_of(b.fixed_ld, nb);
     std::vector<double> x0(b.x_stride, 0.0), P0((size_t)nb * ld, 0.0);
     x0[0] = x_0; x0[1] = y_0;
     if (nb == 3) x0[2] = yaw_0;
@@ -350,7 +351,7 @@ int slam_get_state_vector(slam_handle_t h, int inst, double* xv, int* n) {
 int slam_get_cov(slam_handle_t h, int inst, double* P, int* n) {
     int M = 0;
     if (slam_get_num_landmarks(h, inst, &M)) return 1;
-    const int nn = h->b.base + 2 * M, ld = ldg_of(nn);
+    const int nn = h->b.base + 2 * M, ld = ldp_of(h->b.fixed_ld, nn);
     CK(cudaMemcpy2DAsync(P, sizeof(double) * nn, h->b.P + (size_t)inst * h->b.p_stride, sizeof(double) * ld,
                          sizeof(double) * nn, nn, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -402,7 +403,7 @@ int slam_set_state(slam_handle_t h, int inst, const double* x, const double* P, 
     if (check_inst(h, inst)) return 1;
     if (M < 0 || M > h->b.max_lm) return fail(h, "slam_set_state: M out of range");
     CK(cudaSetDevice(h->device));
-    const int nn = h->b.base + 2 * M, ld = ldg_of(nn);
+    const int nn = h->b.base + 2 * M, ld = ldp_of(h->b.fixed_ld, nn);
     const int4 meta = make_int4(M, 0, timestep, 0);
     CK(cudaMemcpyAsync(h->b.x + (size_t)inst * h->b.x_stride, x, sizeof(double) * nn, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpy2DAsync(h->b.P + (size_t)inst * h->b.p_stride, sizeof(double) * ld, P, sizeof(double) * nn,

@@ -42,6 +42,7 @@ struct BatchState {
     int base;          // 3 (EKF) or 4 (UKF)
     int n_max;         // base + 2*max_lm
     int lds;           // shared-memory leading dimension of P
+    int fixed_ld;      // 0: P packed with ldg(n) (EKF, streamed every step); else fixed global leading dimension (UKF)
 };
 
 // Effective filter constants after readCommonParams (filter.h:105-121).
@@ -59,6 +60,7 @@ struct SimConst {
 };
 
 __host__ __device__ inline int ldg_of(int n) { return (n + 1) & ~1; }
+__host__ __device__ inline int ldp_of(const int fixed_ld, int n) { return fixed_ld ? fixed_ld : ((n + 1) & ~1); }
 
 // smallest even leading dimension >= n_max+1 with lds % 4 == 2: rows stay 16-byte aligned for bulk copies
 // and a column walk hits 8 distinct 8-byte bank slots per half-warp (2-way conflict at worst).

@@ -427,7 +427,7 @@ __global__ void reset_kernel(BatchState b, double x0, double y0, double a2, doub
     if (i >= b.batch) return;
     double* x = b.x + (size_t)i * b.x_stride;
     double* P = b.P + (size_t)i * b.p_stride;
-    const int nb = b.base, ld = ldg_of(nb);
+    const int nb = b.base, ld = ldp_of(b.fixed_ld, nb);
     x[0] = x0; x[1] = y0; x[2] = a2; if (nb == 4) x[3] = a3;
     for (int r = 0; r < nb; ++r) for (int c = 0; c < ld; ++c) P[r * ld + c] = 0.0;
     P[0] = 0.01 * 0.01; P[ld + 1] = 0.01 * 0.01; P[2 * ld + 2] = 0.005 * 0.005;

@@ -73,7 +73,7 @@ __global__ void accumulate_error_kernel(BatchState b, SimState s) {
     const double* x = b.x + (size_t)i * b.x_stride;
     const double* P = b.P + (size_t)i * b.p_stride;
     const int n = b.base + 2 * b.meta[i].x;
-    const int ld = ldg_of(n);
+    const int ld = ldp_of(b.fixed_ld, n);
     const double* tr = s.truth + 3 * (size_t)i;
     double yaw, C[3][3];
     if (b.base == 3) {

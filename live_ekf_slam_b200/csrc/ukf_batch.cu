@@ -1,7 +1,681 @@
-// ukf_batch.cu -- batched UKF-SLAM step (placeholder until the kernel lands; fails loudly).
+// ukf_batch.cu -- batched UKF-SLAM step for sm_100a: one CTA per filter instance.
+//
+// Restates UKF::update, ekf_ws/src/localization_pkg/src/ukf.cpp:161-371 (nearestSPD :106-123, motionModel :125-135,
+// sensingModel :137-159, predictionStage :197-241, updateStage :243-291, landmarkUpdate :293-349,
+// landmarkInsertion :351-371) with the reference's float/double roundings.
+//
+// What the reference does with dense n x (2n+1) sigma-point matrices is evaluated here from the symmetric
+// eigendecomposition  Y = scale * sym(P) = Z D Z^T  alone (Z kept transposed in shared memory):
+//   * sqrt(nearestSPD) = S = Z sqrt(D+) Z^T is never formed: only rows 0..3 of S (vehicle rows of the sigma
+//     points), the two rows of the landmark being updated, and products S*v are needed             -> O(n^2)
+//   * the motion model only changes rows 0..3, so for landmark rows a,b >= 4
+//       P_pred[a][b] = 2w (S S^T)[a][b] + (sum w) e_a e_b,   S S^T = Y + sum_{clipped k} (1e-8 - d_k) z_k z_k^T
+//     and the vehicle/landmark cross block is  w * S (Xp_i - Xp_{i+n}) + e_b * sum_i w_i dv_i        -> O(n^2)
+//   * cross covariance of a landmark update: C[a] = f_a * sum_i w_i dz_i + w * S (dz_i - dz_{i+n})   -> O(n^2)
+// so the step is dominated by the eigendecomposition (Householder tridiagonalisation + implicit QL, 9 n^3 nominal):
+// the UKF batch is FP64-compute bound, not HBM bound.  P stays in global memory (L2) with a fixed
+// leading dimension; only Z lives in shared memory, which lets two CTAs share an SM.
 #include "common.cuh"
+
+#include <climits>
+
 namespace slam {
-size_t ukf_step_smem_bytes(const BatchState&) { return 0; }
-cudaError_t ukf_step_configure(const BatchState&) { return cudaSuccess; }
-cudaError_t launch_ukf_step(const BatchState&, const FilterConst&, const StepInputs&, cudaStream_t) { return cudaErrorNotSupported; }
+
+constexpr int UKF_THREADS = 256;
+constexpr int UKF_WARPS = UKF_THREADS / 32;
+
+struct UkfSmem {
+    double* A;      // n_max x lds : Y, then Q, then Z^T
+    double* x;      // prior x_t
+    double* xp;     // running x_pred
+    double* d;      // eigenvalues -> sqrt(max(d,1e-8))
+    double* e;      // off-diagonal / scratch
+    double* Xp;     // [4][ns_max] propagated vehicle rows of the sigma points
+    double* S4;     // [4][nmp] rows 0..3 of S ; later z0|z1 [ns_max] each
+    double* K;      // [nmp][2]
+    double* pool;   // 8*nmp doubles of phase-local scratch
+    double* red;    // 64 doubles reduction scratch
+    double* corr;   // clipped-eigenvalue corrections (1e-8 - d_k), aligned with clip[]
+    int* clip;      // indices of clipped eigenvalues
+    int* ids;
+    float* meas;
+    int* assoc;
+    int* iscr;
+};
+
+__host__ __device__ inline size_t ukf_smem_carve(const BatchState& b, unsigned char* base, UkfSmem* s) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
+    const int nmp = ldg_of(b.n_max), nsm = 2 * b.n_max + 2;
+    size_t oA = take(sizeof(double) * (size_t)b.n_max * b.lds);
+    size_t ox = take(sizeof(double) * nmp), oxp = take(sizeof(double) * nmp);
+    size_t od = take(sizeof(double) * nmp), oe = take(sizeof(double) * nmp);
+    size_t oXp = take(sizeof(double) * 4 * nsm);
+    size_t oS4 = take(sizeof(double) * (4 * nmp > 2 * nsm ? 4 * nmp : 2 * nsm));
+    size_t oK = take(sizeof(double) * 2 * nmp);
+    size_t opool = take(sizeof(double) * 8 * nmp);
+    size_t ored = take(sizeof(double) * 64);
+    size_t ocorr = take(sizeof(double) * nmp);
+    size_t oclip = take(sizeof(int) * nmp);
+    size_t oids = take(sizeof(int) * (b.max_lm + 1));
+    size_t omeas = take(sizeof(float) * 3 * b.max_meas);
+    size_t oassoc = take(sizeof(int) * b.max_meas);
+    size_t oi = take(sizeof(int) * 8);
+    if (s) {
+        s->A = (double*)(base + oA); s->x = (double*)(base + ox); s->xp = (double*)(base + oxp);
+        s->d = (double*)(base + od); s->e = (double*)(base + oe); s->Xp = (double*)(base + oXp);
+        s->S4 = (double*)(base + oS4); s->K = (double*)(base + oK); s->pool = (double*)(base + opool);
+        s->red = (double*)(base + ored); s->corr = (double*)(base + ocorr); s->clip = (int*)(base + oclip);
+        s->ids = (int*)(base + oids); s->meas = (float*)(base + omeas); s->assoc = (int*)(base + oassoc);
+        s->iscr = (int*)(base + oi);
+    }
+    return off;
 }
+
+// sum NV per-thread values over the CTA; every thread receives the totals.  Two barriers.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double t = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) red[k * UKF_WARPS + warp] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < UKF_WARPS; ++w) t += red[k * UKF_WARPS + w];
+        v[k] = t;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float yaw_of(double c, double s) { return (float)remainder(atan2(s, c), TWO_PI_REF); }
+
+// ---------------------------------------------------------------------------------------------------------
+// Symmetric eigendecomposition of the n x n matrix in A (full storage, leading dimension lds), in place:
+// on exit d[0..n) holds the eigenvalues (unsorted) and A holds Z^T (row k = eigenvector k).
+// Householder tridiagonalisation (LAPACK dsytd2 'L' organisation, one thread per column of the trailing block),
+// explicit Q (dorg2r organisation), in-place transpose, implicit QL with the rotation sequence of each sweep
+// generated by one thread and applied by one thread per row.  Scratch: v, p, w, tau (n each), cs (2n).
+// ---------------------------------------------------------------------------------------------------------
+__device__ void eigh_smem(double* A, const int lds, const int n, double* d, double* e, double* scratch, double* red) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* v = scratch;            // [n]
+    double* p = scratch + n;        // [n]
+    double* w = scratch + 2 * n;    // [n]
+    double* tau = scratch + 3 * n;  // [n]
+    double* csc = scratch + 4 * n;  // [n]
+    double* css = scratch + 5 * n;  // [n]
+
+    // ---- reduction to tridiagonal form: A = Q T Q^T
+    for (int k = 0; k < n - 1; ++k) {
+        const int m0 = k + 1;                      // first row/col of the trailing block
+        if (warp == 0) {
+            double ss = 0.0;
+            for (int i = k + 2 + lane; i < n; i += 32) { const double a = A[(size_t)i * lds + k]; ss += a * a; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            if (lane == 0) {
+                const double alpha = A[(size_t)m0 * lds + k];
+                double tk = 0.0, scal = 0.0, beta = alpha;
+                if (ss != 0.0) {
+                    beta = -copysign(sqrt(alpha * alpha + ss), alpha);
+                    tk = (beta - alpha) / beta;
+                    scal = 1.0 / (alpha - beta);
+                }
+                tau[k] = tk; e[k] = beta; d[k] = A[(size_t)k * lds + k];
+                red[0] = tk; red[1] = scal;
+            }
+        }
+        __syncthreads();
+        const double tk = red[0], scal = red[1];
+        if (tk != 0.0) {                            // uniform
+            for (int i = m0 + tid; i < n; i += UKF_THREADS) {
+                const double vi = (i == m0) ? 1.0 : A[(size_t)i * lds + k] * scal;
+                v[i] = vi;
+                A[(size_t)i * lds + k] = vi;        // keep the reflector in column k
+            }
+            __syncthreads();
+            // p = tau * A22 * v  (column c of the symmetric block, conflict-free), and p^T v
+            double pv[1] = {0.0};
+            for (int c = m0 + tid; c < n; c += UKF_THREADS) {
+                double acc = 0.0;
+                for (int i = m0; i < n; ++i) acc += A[(size_t)i * lds + c] * v[i];
+                acc *= tk;
+                p[c] = acc;
+                pv[0] += acc * v[c];
+            }
+            block_sum<1>(pv, red + 8);
+            const double a2 = -0.5 * tk * pv[0];
+            for (int c = m0 + tid; c < n; c += UKF_THREADS) w[c] = p[c] + a2 * v[c];
+            __syncthreads();
+            // A22 -= v w^T + w v^T   (both triangles kept; the two products are added symmetrically)
+            for (int c = m0 + tid; c < n; c += UKF_THREADS) {
+                const double vc = v[c], wc = w[c];
+                for (int i = m0; i < n; ++i) {
+                    const double t1 = __dmul_rn(v[i], wc), t2 = __dmul_rn(w[i], vc);
+                    A[(size_t)i * lds + c] -= __dadd_rn(t1, t2);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { d[n - 1] = A[(size_t)(n - 1) * lds + (n - 1)]; e[n - 1] = 0.0; }
+    __syncthreads();
+
+    // ---- explicit Q in place.  Shift the reflectors one column to the right (reflector k -> column k+1),
+    //      first row/column of Q = unit vector, then dorg2r on the (n-1) x (n-1) trailing block.
+    for (int i = tid; i < n; i += UKF_THREADS) {          // one thread per row, high column to low: no hazard
+        for (int k = i - 2; k >= 0; --k) A[(size_t)i * lds + k + 1] = A[(size_t)i * lds + k];
+        A[(size_t)i * lds + 0] = (i == 0) ? 1.0 : 0.0;
+        if (i > 0) A[i] = 0.0;                            // row 0
+    }
+    __syncthreads();
+    // B = A[1:,1:] ; reflector j (tau[j]) sits in B column j below the diagonal; last column = unit vector
+    if (n >= 2) {
+        for (int i = tid; i < n - 1; i += UKF_THREADS)
+            A[(size_t)(1 + i) * lds + (n - 1)] = (i == n - 2) ? 1.0 : 0.0;
+        __syncthreads();
+    }
+    for (int j = n - 3; j >= 0; --j) {
+        const double tj = tau[j];
+        const int r0 = 1 + j;                              // row/col of B[j][j] in A
+        // apply H_j to B[j:, j+1:] from the left: column c owned by one thread
+        for (int c = r0 + 1 + tid; c < n; c += UKF_THREADS) {
+            double t = 0.0;                                // v^T B[:,c] with v[j] = 1 and B[j][c] = 0 on entry
+            for (int i = r0 + 1; i < n; ++i) t += A[(size_t)i * lds + r0] * A[(size_t)i * lds + c];
+            t *= tj;
+            A[(size_t)r0 * lds + c] = -t;
+            for (int i = r0 + 1; i < n; ++i) A[(size_t)i * lds + c] -= A[(size_t)i * lds + r0] * t;
+        }
+        __syncthreads();
+        for (int i = r0 + tid; i < n; i += UKF_THREADS)
+            A[(size_t)i * lds + r0] = (i == r0) ? 1.0 - tj : -tj * A[(size_t)i * lds + r0];
+        for (int i = 1 + tid; i < r0; i += UKF_THREADS) A[(size_t)i * lds + r0] = 0.0;
+        __syncthreads();
+    }
+    if (n == 2) { /* Q = I already */ }
+
+    // ---- transpose in place: A <- Q^T so that a QL rotation touches two ROWS (conflict-free per-row threads)
+    for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
+        const int i = idx / n, j = idx - i * n;
+        if (j > i) {
+            const double a = A[(size_t)i * lds + j], bb = A[(size_t)j * lds + i];
+            A[(size_t)i * lds + j] = bb; A[(size_t)j * lds + i] = a;
+        }
+    }
+    __syncthreads();
+
+    // ---- implicit QL on (d, e), e[k] couples k and k+1 (EISPACK tql2 organisation)
+    int* ctl = reinterpret_cast<int*>(red + 32);           // [0]=l-range start, [1]=m, [2]=done flag
+    double f = 0.0, tst1 = 0.0;                            // live in thread 0 only
+    const double eps = 2.220446049250313e-16;
+    for (int l = 0; l < n; ++l) {
+        int iter = 0;
+        while (true) {
+            if (tid == 0) {
+                if (iter == 0) { const double t = fabs(d[l]) + fabs(e[l]); if (t > tst1) tst1 = t; }
+                int m = l;
+                while (m < n - 1) { if (fabs(e[m]) <= eps * tst1) break; ++m; }
+                if (m == l || iter >= 60) { d[l] += f; e[l] = 0.0; ctl[2] = 1; }
+                else {
+                    ctl[2] = 0; ctl[1] = m;
+                    double g = d[l];
+                    double pp = (d[l + 1] - g) / (2.0 * e[l]);
+                    double r = sqrt(pp * pp + 1.0);
+                    if (pp < 0) r = -r;
+                    d[l] = e[l] / (pp + r);
+                    d[l + 1] = e[l] * (pp + r);
+                    const double dl1 = d[l + 1];
+                    double h = g - d[l];
+                    for (int i = l + 2; i < n; ++i) d[i] -= h;
+                    f += h;
+                    pp = d[m];
+                    double c = 1.0, c2 = c, c3 = c, s = 0.0, s2 = 0.0;
+                    const double el1 = e[l + 1];
+                    for (int i = m - 1; i >= l; --i) {
+                        c3 = c2; c2 = c; s2 = s;
+                        g = c * e[i];
+                        h = c * pp;
+                        r = sqrt(pp * pp + e[i] * e[i]);
+                        e[i + 1] = s * r;
+                        const double rinv = 1.0 / r;
+                        s = e[i] * rinv;
+                        c = pp * rinv;
+                        pp = c * d[i] - s * g;
+                        d[i + 1] = h + s * (c * g + s * d[i]);
+                        csc[i] = c; css[i] = s;
+                    }
+                    pp = -s * s2 * c3 * el1 * e[l] / dl1;
+                    e[l] = s * pp;
+                    d[l] = c * pp;
+                }
+            }
+            __syncthreads();
+            if (ctl[2]) break;
+            const int m = ctl[1];
+            // apply the sweep's rotations to Z^T: thread r owns component r of every eigenvector
+            for (int r = tid; r < n; r += UKF_THREADS) {
+                double fz = A[(size_t)m * lds + r];
+                for (int i = m - 1; i >= l; --i) {
+                    const double zi = A[(size_t)i * lds + r];
+                    const double c = csc[i], s = css[i];
+                    A[(size_t)(i + 1) * lds + r] = s * zi + c * fz;
+                    fz = c * zi - s * fz;
+                }
+                A[(size_t)l * lds + r] = fz;
+            }
+            ++iter;
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+}
+
+// rows r0.. of S = Z sqrt(D+) Z^T:  out[q][c] = sum_k Zt[k][rows[q]] * sq[k] * Zt[k][c]   (thread per column c)
+template <int NR>
+__device__ __forceinline__ void s_rows(const double* Zt, const int lds, const int n, const double* sq,
+                                       const int (&rows)[NR], double* out, const int ldo) {
+    for (int c = threadIdx.x; c < n; c += UKF_THREADS) {
+        double acc[NR];
+#pragma unroll
+        for (int q = 0; q < NR; ++q) acc[q] = 0.0;
+        for (int k = 0; k < n; ++k) {
+            const double* zr = Zt + (size_t)k * lds;
+            const double zc = zr[c] * sq[k];
+#pragma unroll
+            for (int q = 0; q < NR; ++q) acc[q] += zr[rows[q]] * zc;
+        }
+#pragma unroll
+        for (int q = 0; q < NR; ++q) out[q * ldo + c] = acc[q];
+    }
+}
+
+// out[q][b] = (S vin[q])_b for NV vectors:  t[q][k] = sq[k] * sum_i Zt[k][i] vin[q][i]  (warp per k), then
+// out[q][b] = sum_k Zt[k][b] t[q][k]  (thread per b).  t is scratch [NV][ldv].  One barrier inside, one after.
+template <int NV>
+__device__ __forceinline__ void s_times(const double* Zt, const int lds, const int n, const double* sq,
+                                        const double* vin, double* t, double* out, const int ldv) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = warp; k < n; k += UKF_WARPS) {
+        const double* zr = Zt + (size_t)k * lds;
+        double acc[NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) acc[q] = 0.0;
+        for (int i = lane; i < n; i += 32) {
+            const double z = zr[i];
+#pragma unroll
+            for (int q = 0; q < NV; ++q) acc[q] += z * vin[q * ldv + i];
+        }
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            double a = acc[q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) t[q * ldv + k] = a * sq[k];
+        }
+    }
+    __syncthreads();
+    for (int bcol = threadIdx.x; bcol < n; bcol += UKF_THREADS) {
+        double acc[NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) acc[q] = 0.0;
+        for (int k = 0; k < n; ++k) {
+            const double z = Zt[(size_t)k * lds + bcol];
+#pragma unroll
+            for (int q = 0; q < NV; ++q) acc[q] += z * t[q * ldv + k];
+        }
+#pragma unroll
+        for (int q = 0; q < NV; ++q) out[q * ldv + bcol] = acc[q];
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(UKF_THREADS, 2)
+ukf_step_kernel(BatchState b, FilterConst fc, StepInputs in) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    UkfSmem s;
+    ukf_smem_carve(b, smem_raw, &s);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int inst = blockIdx.x;
+    const int lds = b.lds;
+    const int ldp = b.fixed_ld;                    // global leading dimension of P (fixed for the UKF)
+    const int nmp = ldg_of(b.n_max), nsm = 2 * b.n_max + 2;
+
+    const int4 meta_in = b.meta[inst];
+    int nm = in.n_meas[inst];
+    int status = meta_in.y;
+    int M = meta_in.x;
+    const int M_start = M;
+    const int n = 4 + 2 * M;                       // ukf.cpp:167 (state size of this step's sigma points)
+    const int ns = 2 * n + 1;
+    if (nm > b.max_meas) { nm = b.max_meas; status |= SLAM_STATUS_MEAS_OVERFLOW; }
+    double* gP = b.P + (size_t)inst * b.p_stride;
+    double* gx = b.x + (size_t)inst * b.x_stride;
+
+    for (int i = tid; i < n; i += UKF_THREADS) { const double v = gx[i]; s.x[i] = v; }
+    for (int i = tid; i < M; i += UKF_THREADS) s.ids[i] = b.ids[(size_t)inst * b.max_lm + i];
+    for (int i = tid; i < 3 * nm; i += UKF_THREADS) s.meas[i] = in.meas[(size_t)inst * b.max_meas * 3 + i];
+    if (tid == 0) { s.iscr[0] = INT_MAX; s.iscr[1] = INT_MAX; s.iscr[2] = 0; }
+    // P -> A (row loads are coalesced)
+    for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
+        const int i = idx / n, j = idx - i * n;
+        s.A[(size_t)i * lds + j] = gP[(size_t)i * ldp + j];
+    }
+    __syncthreads();
+
+    // weights and scale are float-valued (ukf.cpp:35,114,175)
+    const float W0f = 0.2f;                                                // filter.h:207
+    const double W0 = (double)W0f;
+    const double wgt = (double)((1 - W0f) / (2 * n));                      // :175
+    const double scale = (double)((2 * M + 4) / (1 - W0f));                // :114
+    const double sw = W0 + (double)(2 * n) * wgt;                          // sum of the 2n+1 weights (not 1)
+    const float u_d = in.fwd[in.cmd_stride ? inst : 0], u_th = in.ang[in.cmd_stride ? inst : 0];
+    const float yaw_prior = yaw_of(s.x[2], s.x[3]);                        // :182 and :139 (prior x_t)
+    const double cy = (double)cos_f(yaw_prior), sy = (double)sin_f(yaw_prior);
+    const double Qd[4] = {fc.V00 * cy, fc.V00 * sy, fc.V11 * cy, fc.V11 * sy};   // :183-186
+
+    // ---- nearestSPD input: Y = 0.5 (P + P^T) * scale (:112-114); and P_LL <- 2 w Y (landmark block of P_pred
+    //      before the clipped-eigenvalue correction)
+    for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
+        const int i = idx / n, j = idx - i * n;
+        if (j >= i) {
+            const double y = (0.5 * (s.A[(size_t)i * lds + j] + s.A[(size_t)j * lds + i])) * scale;
+            s.A[(size_t)i * lds + j] = y; s.A[(size_t)j * lds + i] = y;
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
+        const int i = idx / n, j = idx - i * n;
+        if (i >= 4 && j >= 4) gP[(size_t)i * ldp + j] = (2.0 * wgt) * s.A[(size_t)i * lds + j];
+    }
+    __syncthreads();
+
+    // ---- eigendecomposition (:116-118) -> s.d eigenvalues, s.A = Z^T
+    eigh_smem(s.A, lds, n, s.d, s.e, s.pool, s.red);
+
+    // ---- clip (:120) and sqrt; list of clipped eigenpairs
+    if (tid == 0) {
+        int nc = 0;
+        for (int k = 0; k < n; ++k) {
+            double dk = s.d[k];
+            if (dk < 0.00000001) { s.clip[nc] = k; s.corr[nc] = 0.00000001 - dk; ++nc; dk = 0.00000001; }
+            s.d[k] = sqrt(dk);
+        }
+        s.iscr[3] = nc;
+    }
+    __syncthreads();
+    const double* Zt = s.A;
+    const double* sq = s.d;
+    const int nclip = s.iscr[3];
+
+    // ---- sigma points, vehicle rows (:214-226): rows 0..3 of S, motion model per sigma point
+    {
+        const int rows4[4] = {0, 1, 2, 3};
+        s_rows<4>(Zt, lds, n, sq, rows4, s.S4, nmp);
+    }
+    __syncthreads();
+    for (int i = tid; i < ns; i += UKF_THREADS) {
+        double X[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const double xr = s.x[r];
+            X[r] = (i == 0) ? xr : (i <= n ? xr + s.S4[r * nmp + (i - 1)] : xr - s.S4[r * nmp + (i - 1 - n)]);
+        }
+        const float yaw = yaw_of(X[2], X[3]);                              // :128
+        const float ud = u_d + fc.v_d;
+        s.Xp[0 * nsm + i] = X[0] + (double)(ud * cos_f(yaw));              // :129 float product
+        s.Xp[1 * nsm + i] = X[1] + (double)(ud * sin_f(yaw));              // :130
+        const float fsum = yaw + u_th + fc.v_th;
+        const float new_yaw = (float)remainder((double)fsum, TWO_PI_REF);  // :131
+        s.Xp[2 * nsm + i] = (double)cos_f(new_yaw);                        // :132
+        s.Xp[3 * nsm + i] = (double)sin_f(new_yaw);                        // :133
+    }
+    __syncthreads();
+    // ---- mean (:228-232): vehicle rows by reduction, landmark rows analytically (sum w) * x
+    {
+        double acc[4] = {0, 0, 0, 0};
+        for (int i = tid; i < ns; i += UKF_THREADS) {
+            const double wi = (i == 0) ? W0 : wgt;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] += wi * s.Xp[r * nsm + i];
+        }
+        block_sum<4>(acc, s.red);
+        if (tid < 4) s.xp[tid] = acc[tid];
+        for (int r = 4 + tid; r < n; r += UKF_THREADS) s.xp[r] = sw * s.x[r];
+    }
+    __syncthreads();
+    // ---- covariance (:235-240)
+    //  vehicle block: sum_i w_i dv_i dv_i^T + Q ; mv[a] = sum_i w_i dv_i[a]
+    double mv[4];
+    {
+        double acc[14] = {0};
+        for (int i = tid; i < ns; i += UKF_THREADS) {
+            const double wi = (i == 0) ? W0 : wgt;
+            double dv[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) dv[r] = s.Xp[r * nsm + i] - s.xp[r];
+            int q = 0;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = a; c < 4; ++c) acc[q++] += (wi * dv[a]) * dv[c];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) acc[10 + a] += wi * dv[a];
+        }
+        block_sum<14>(acc, s.red);
+        if (tid == 0) {
+            int q = 0;
+            for (int a = 0; a < 4; ++a)
+                for (int c = a; c < 4; ++c) {
+                    const double val = acc[q++] + ((a == c) ? Qd[a] : 0.0);
+                    gP[(size_t)a * ldp + c] = val; gP[(size_t)c * ldp + a] = val;
+                }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) mv[a] = acc[10 + a];
+    }
+    //  cross block: P[a][b] = w (S g_a)_b + e_b mv[a],  g_a[i] = Xp[a][1+i] - Xp[a][1+n+i],  e_b = x[b] - xp[b]
+    {
+        double* g = s.pool;                 // [4][nmp]
+        double* t = s.pool + 4 * nmp;       // [4][nmp]
+        for (int i = tid; i < n; i += UKF_THREADS)
+#pragma unroll
+            for (int a = 0; a < 4; ++a) g[a * nmp + i] = s.Xp[a * nsm + 1 + i] - s.Xp[a * nsm + 1 + n + i];
+        __syncthreads();
+        s_times<4>(Zt, lds, n, sq, g, t, g, nmp);       // g <- S g (out may alias vin: vin is dead after phase 1)
+        for (int bcol = 4 + tid; bcol < n; bcol += UKF_THREADS) {
+            const double eb = s.x[bcol] - s.xp[bcol];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const double val = wgt * g[a * nmp + bcol] + eb * mv[a];
+                gP[(size_t)a * ldp + bcol] = val;
+                gP[(size_t)bcol * ldp + a] = val;
+            }
+        }
+    }
+    //  landmark block: += 2w sum_{clipped k} (1e-8 - d_k) z_k z_k^T + (sum w) e_a e_b
+    for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
+        const int a = idx / n, c = idx - a * n;
+        if (a >= 4 && c >= 4) {
+            double add = sw * (s.x[a] - s.xp[a]) * (s.x[c] - s.xp[c]);
+            for (int q = 0; q < nclip; ++q) {
+                const double* zr = Zt + (size_t)s.clip[q] * lds;
+                add += (2.0 * wgt) * s.corr[q] * zr[a] * zr[c];
+            }
+            gP[(size_t)a * ldp + c] += add;
+        }
+    }
+    __syncthreads();
+
+    // ---- update stage (:243-291): updates first (in message order), insertions afterwards
+    int n_upd = 0;
+    double* z0 = s.S4;                       // [nsm]  (S4 is dead)
+    double* z1 = s.S4 + nsm;                 // [nsm]
+    for (int l = 0; l < nm; ++l) {
+        const int id = (int)s.meas[3 * l];                                  // :258
+        const float r = s.meas[3 * l + 1], bb = s.meas[3 * l + 2];
+        int* match = &s.iscr[l & 1];
+        int cand = INT_MAX;
+        for (int j = tid; j < M_start; j += UKF_THREADS) if (s.ids[j] == id) { cand = j; break; }   // :264-269
+        cand = __reduce_min_sync(0xffffffffu, cand);
+        if (lane == 0 && cand != INT_MAX) atomicMin(match, cand);
+        __syncthreads();
+        const int slot = *match;
+        if (tid == 0) { s.iscr[(l + 1) & 1] = INT_MAX; s.assoc[l] = (slot == INT_MAX) ? -1 : slot; }
+        if (slot == INT_MAX) { __syncthreads(); continue; }                 // new landmark: handled after the loop (:272-274)
+        ++n_upd;
+        // -------- landmarkUpdate (:293-349)
+        const int li = slot * 2 + 4;                                        // :298
+        double* SL = s.pool;                 // [2][nmp] rows li, li+1 of S
+        {
+            const int rows2[2] = {li, li + 1};
+            s_rows<2>(Zt, lds, n, sq, rows2, SL, nmp);
+        }
+        __syncthreads();
+        for (int i = tid; i < ns; i += UKF_THREADS) {                       // sensingModel per sigma point (:305-308)
+            double lx = s.x[li], ly = s.x[li + 1];
+            if (i >= 1 && i <= n) { lx += SL[i - 1]; ly += SL[nmp + i - 1]; }
+            else if (i > n) { lx -= SL[i - 1 - n]; ly -= SL[nmp + i - 1 - n]; }
+            const double dx = lx - s.Xp[0 * nsm + i], dy = ly - s.Xp[1 * nsm + i];
+            z0[i] = sqrt(dx * dx + dy * dy) + (double)fc.w_r;               // :144
+            z1[i] = remainder(atan2(dy, dx) - (double)yaw_prior + (double)fc.w_b, TWO_PI_REF);   // :145,156
+        }
+        __syncthreads();
+        double zest0;
+        {
+            double acc[1] = {0.0};
+            for (int i = tid; i < ns; i += UKF_THREADS) acc[0] += ((i == 0) ? W0 : wgt) * z0[i];   // :312-314
+            block_sum<1>(acc, s.red);
+            zest0 = acc[0];
+        }
+        // dz in place; S2, sum_i w_i dz_i, and the vehicle rows of C
+        double S2[2][2], sdz[2], Cv[4][2];
+        {
+            double acc[13] = {0};
+            for (int i = tid; i < ns; i += UKF_THREADS) {
+                const double wi = (i == 0) ? W0 : wgt;
+                const double d0 = z0[i] - zest0;
+                const double d1 = remainder(z1[i] - 0.0, TWO_PI_REF);       // z_est(1) is never accumulated (:310-314,321)
+                z0[i] = d0; z1[i] = d1;
+                acc[0] += (wi * d0) * d0; acc[1] += (wi * d0) * d1; acc[2] += (wi * d1) * d1;
+                acc[3] += wi * d0; acc[4] += wi * d1;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const double wd = wi * (s.Xp[a * nsm + i] - s.xp[a]);
+                    acc[5 + 2 * a] += wd * d0; acc[6 + 2 * a] += wd * d1;
+                }
+            }
+            block_sum<13>(acc, s.red);
+            S2[0][0] = acc[0] + fc.W00; S2[0][1] = acc[1]; S2[1][0] = acc[1]; S2[1][1] = acc[2] + fc.W11;   // :326
+            sdz[0] = acc[3]; sdz[1] = acc[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { Cv[a][0] = acc[5 + 2 * a]; Cv[a][1] = acc[6 + 2 * a]; }
+        }
+        // landmark rows of C: f_a * sdz + w * S (dz_i - dz_{i+n})
+        double* hv = s.pool + 2 * nmp;       // [2][nmp]
+        double* tv = s.pool + 4 * nmp;       // [2][nmp]
+        for (int i = tid; i < n; i += UKF_THREADS) {
+            hv[i] = z0[1 + i] - z0[1 + n + i];
+            hv[nmp + i] = z1[1 + i] - z1[1 + n + i];
+        }
+        __syncthreads();
+        s_times<2>(Zt, lds, n, sq, hv, tv, hv, nmp);
+        // K = C S2^-1 (:339, partial-pivot LU like Eigen's dynamic inverse), x_pred += K innovation (:342-345)
+        double i00, i01, i10, i11;
+        {
+            const bool swp = fabs(S2[1][0]) > fabs(S2[0][0]);
+            const double a00 = swp ? S2[1][0] : S2[0][0], a01 = swp ? S2[1][1] : S2[0][1];
+            const double a10 = swp ? S2[0][0] : S2[1][0], a11 = swp ? S2[0][1] : S2[1][1];
+            const double l10 = a10 / a00, u11 = a11 - l10 * a01;
+            const double b0c0 = swp ? 0.0 : 1.0, b1c0 = swp ? 1.0 : 0.0, b0c1 = swp ? 1.0 : 0.0, b1c1 = swp ? 0.0 : 1.0;
+            double y1 = b1c0 - l10 * b0c0; i10 = y1 / u11; i00 = (b0c0 - a01 * i10) / a00;
+            y1 = b1c1 - l10 * b0c1; i11 = y1 / u11; i01 = (b0c1 - a01 * i11) / a00;
+        }
+        const double in0 = (double)r - zest0;
+        const double in1 = remainder((double)bb - 0.0, TWO_PI_REF);         // :344
+        for (int a = tid; a < n; a += UKF_THREADS) {
+            double c0, c1;
+            if (a < 4) { c0 = Cv[a][0]; c1 = Cv[a][1]; }
+            else {
+                const double fa = s.x[a] - s.xp[a];
+                c0 = fa * sdz[0] + wgt * hv[a];
+                c1 = fa * sdz[1] + wgt * hv[nmp + a];
+            }
+            const double k0 = c0 * i00 + c1 * i10, k1 = c0 * i01 + c1 * i11;
+            s.K[2 * a] = k0; s.K[2 * a + 1] = k1;
+            s.xp[a] = s.xp[a] + (k0 * in0 + k1 * in1);
+        }
+        __syncthreads();
+        // P_pred -= (K S2) K^T (:348) on the L2-resident covariance
+        for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
+            const int i = idx / n, j = idx - i * n;
+            const double ki0 = s.K[2 * i], ki1 = s.K[2 * i + 1];
+            const double ks0 = ki0 * S2[0][0] + ki1 * S2[1][0], ks1 = ki0 * S2[0][1] + ki1 * S2[1][1];
+            gP[(size_t)i * ldp + j] -= ks0 * s.K[2 * j] + ks1 * s.K[2 * j + 1];
+        }
+        __syncthreads();
+    }
+    // -------- landmarkInsertion for the unmatched measurements, in message order (:278-287,351-371)
+    for (int l = 0; l < nm; ++l) {
+        if (s.assoc[l] != -1) continue;
+        if (M >= b.max_lm) { status |= SLAM_STATUS_CAPACITY; continue; }
+        const int nn = 4 + 2 * M;
+        const float r = s.meas[3 * l + 1], bb = s.meas[3 * l + 2];
+        if (tid == 0) {
+            const float yaw = yaw_of(s.xp[2], s.xp[3]);                     // :356
+            const float yb = yaw + bb;
+            s.xp[nn] = s.xp[0] + (double)(r * cos_f(yb));                   // :358
+            s.xp[nn + 1] = s.xp[1] + (double)(r * sin_f(yb));               // :359
+            s.ids[M] = (int)s.meas[3 * l];                                  // :361
+        }
+        for (int i = tid; i < nn + 2; i += UKF_THREADS) {                   // :365-368, W block and zero cross terms
+            gP[(size_t)i * ldp + nn] = (i == nn) ? fc.W00 : 0.0;
+            gP[(size_t)i * ldp + nn + 1] = (i == nn + 1) ? fc.W11 : 0.0;
+            gP[(size_t)nn * ldp + i] = (i == nn) ? fc.W00 : 0.0;
+            gP[(size_t)(nn + 1) * ldp + i] = (i == nn + 1) ? fc.W11 : 0.0;
+        }
+        M += 1;
+        __syncthreads();
+    }
+
+    // ---- commit (:289-290)
+    const int n_out = 4 + 2 * M;
+    for (int i = tid; i < n_out; i += UKF_THREADS) {
+        const double v = s.xp[i];
+        gx[i] = v;
+        if (!isfinite(v)) s.iscr[2] = 1;
+    }
+    for (int i = tid + M_start; i < M; i += UKF_THREADS) b.ids[(size_t)inst * b.max_lm + i] = s.ids[i];
+    for (int i = tid; i < nm; i += UKF_THREADS) b.assoc[(size_t)inst * b.max_meas + i] = s.assoc[i];
+    __syncthreads();
+    if (tid == 0) {
+        if (s.iscr[2]) status |= SLAM_STATUS_NAN;
+        b.meta[inst] = make_int4(M, status, meta_in.z + 1, nm);             // timestep, :164
+        if (M > M_start) atomicMax(b.max_M, M);
+        double* st = b.stats + (size_t)inst * SLAM_NUM_STATS;
+        const double nd = (double)n;
+        st[8] += 16.0 * nd * nd + 16.0 * nd + 12.0 * nm + 8.0;
+        st[9] += 9.0 * nd * nd * nd + 2.0 * nd * nd * nd + 2.0 * nd * nd * (2.0 * nd + 1.0) + 12.0 * n_upd * nd * nd;
+        st[10] += nd;
+        st[11] += (double)nm;
+    }
+}
+
+size_t ukf_step_smem_bytes(const BatchState& b) { return ukf_smem_carve(b, nullptr, nullptr); }
+
+cudaError_t ukf_step_configure(const BatchState& b) {
+    return cudaFuncSetAttribute(ukf_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b));
+}
+
+cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, cudaStream_t st) {
+    ukf_step_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, fc, in);
+    return cudaGetLastError();
+}
+
+}  // namespace slam

@@ -1,0 +1,163 @@
+"""GPU parity: the batched UKF-SLAM CUDA path (through the C-ABI) against the CPU oracle on identical inputs.
+Tolerances: landmark ids / M / association bit-exact; state and covariance within 1e-9 norm-wise per step
+(|delta| <= 1e-9 * max(1, max|.|), SURVEY.md 7 hard part 2); final pose within 1e-6 m / 1e-6 rad."""
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def shim():
+    from live_ekf_slam_b200 import shim as s
+    s.load()
+    return s
+
+
+def _compare(fb, inst, of, tol=H.REL_TOL):
+    assert fb.num_landmarks(inst) == of.M
+    assert list(fb.landmark_ids(inst)) == list(of.landmark_ids())
+    ex = H.normwise(fb.state(inst), of.state())
+    eP = H.normwise(fb.cov(inst), of.cov())
+    assert ex <= tol and eP <= tol, (ex, eP)
+    return max(ex, eP)
+
+
+def test_ukf_kats_through_abi(shim, oracle):
+    p = H.Params(filter="ukf_slam")
+    fb = shim.FilterBatch(shim.UKF_SLAM, p.to_c(), 1, 8, 4)
+    fb.init(1.0, 2.0, 0.0)
+    meas, n = fb.pack_meas([[]])
+    fb.step(0.0, 0.0, meas, n)
+    x = fb.state(0)
+    sw = float(np.float32(0.2)) + 8 * float(np.float32(0.1))       # KAT-3: weights do not sum to 1
+    assert abs(x[0] - sw * 1.0) < 1e-12 and abs(x[1] - sw * 2.0) < 1e-12
+    P = fb.cov(0)
+    assert abs(P[0, 0] - (1e-4 + 0.01)) < 1e-9 and abs(P[1, 1] - 1e-4) < 1e-9   # first-step Q = diag(.01,0,.01,0)
+    assert fb.timestep(0) == 1
+
+
+def test_ukf_single_instance_per_step(shim, oracle):
+    """UKF-SLAM on the 5x10 grid, every step compared with the oracle (free running, 500 steps)."""
+    p, lm, fwd, ang = H.config2(seed=0, steps=500, filt="ukf_slam")
+    op = H.oracle_params(oracle, p)
+    stream, _ = H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=0, instance=0)
+    of = oracle.OracleFilter(oracle.UKF_SLAM, op, 50)
+    of.init(0, 0, 0)
+    fb = shim.FilterBatch(shim.UKF_SLAM, p.to_c(), 1, 50, 8)
+    fb.init(0, 0, 0)
+    worst = 0.0
+    for t in range(len(fwd)):
+        of.update(fwd[t], ang[t], stream[t], oracle.DENSE)
+        meas, n = fb.pack_meas([stream[t]])
+        fb.step(fwd[t], ang[t], meas, n)
+        assert list(fb.assoc(0)) == list(of.assoc_log()), t
+        if t % 5 == 0 or t > 490:
+            worst = max(worst, _compare(fb, 0, of))
+    xv = fb.state_vector(0)
+    xo = of.state()
+    yaw_o = np.arctan2(xo[3], xo[2])
+    assert np.abs(xv[:2] - xo[:2]).max() <= H.FINAL_TOL and abs(xv[2] - yaw_o) <= H.FINAL_TOL
+    assert fb.status(0) == 0 and fb.timestep(0) == len(fwd) and of.M >= 20
+    print("ukf single worst normwise err", worst, "final M", of.M)
+
+
+def test_ukf_batch_free_running(shim, oracle):
+    p, lm, fwd, ang = H.config2(seed=3, steps=250, filt="ukf_slam")
+    op = H.oracle_params(oracle, p)
+    B = 12
+    fb = shim.FilterBatch(shim.UKF_SLAM, p.to_c(), B, 50, 8)
+    fb.init(0, 0, 0)
+    streams = [H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=5, instance=i)[0] for i in range(B)]
+    ofs = []
+    for i in range(B):
+        of = oracle.OracleFilter(oracle.UKF_SLAM, op, 50)
+        of.init(0, 0, 0)
+        ofs.append(of)
+    for t in range(len(fwd)):
+        meas, n = fb.pack_meas([streams[i][t] for i in range(B)])
+        fb.step(fwd[t], ang[t], meas, n)
+        for i in range(B):
+            ofs[i].update(fwd[t], ang[t], streams[i][t], oracle.STRUCTURED)
+    worst = max(_compare(fb, i, ofs[i]) for i in range(B))
+    poses = fb.poses()
+    for i in range(B):
+        xo = ofs[i].state()
+        assert np.abs(poses[i, :2] - xo[:2]).max() <= H.FINAL_TOL
+        assert abs(poses[i, 2] - np.arctan2(xo[3], xo[2])) <= H.FINAL_TOL
+    assert (fb.all_status() == 0).all()
+    print("ukf batch worst normwise err", worst)
+
+
+def test_ukf_teacher_forced_single_steps(shim, oracle):
+    p, lm, fwd, ang = H.config2(seed=2, steps=260, filt="ukf_slam")
+    op = H.oracle_params(oracle, p)
+    stream, _ = H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=3, instance=5)
+    of = oracle.OracleFilter(oracle.UKF_SLAM, op, 50)
+    of.init(0, 0, 0)
+    fb = shim.FilterBatch(shim.UKF_SLAM, p.to_c(), 2, 50, 8)
+    fb.init(0, 0, 0)
+    checked, worst = 0, 0.0
+    for t in range(len(fwd)):
+        if t % 13 == 0 and of.M > 0:
+            fb.set_state(1, of.state(), of.cov(), of.landmark_ids(), of.timestep)
+            of.update(fwd[t], ang[t], stream[t], oracle.DENSE)
+            meas, n = fb.pack_meas([[], stream[t]])
+            fb.step(fwd[t], ang[t], meas, n)
+            worst = max(worst, _compare(fb, 1, of))
+            checked += 1
+        else:
+            of.update(fwd[t], ang[t], stream[t], oracle.DENSE)
+    assert checked >= 10
+    print("ukf teacher-forced worst", worst)
+
+
+def test_ukf_edge_cases(shim, oracle):
+    p = H.Params(filter="ukf_slam")
+    op = H.oracle_params(oracle, p)
+    fb = shim.FilterBatch(shim.UKF_SLAM, p.to_c(), 2, 2, 3)
+    fb.init(0.5, -0.25, 0.3)
+    of = oracle.OracleFilter(oracle.UKF_SLAM, op, 2)
+    of.init(0.5, -0.25, 0.3)
+    for _ in range(4):                                  # predict-only steps
+        meas, n = fb.pack_meas([[], []])
+        fb.step(0.05, 0.01, meas, n)
+        of.update(0.05, 0.01, [])
+    _compare(fb, 0, of)
+    m = np.array([[1, 1.0, 0.1], [2, 1.5, -0.2], [3, 2.0, 0.0]], dtype=np.float32)   # third insertion exceeds capacity
+    meas, n = fb.pack_meas([m, m])
+    fb.step(0.05, 0.0, meas, n)
+    of.update(0.05, 0.0, m)
+    assert fb.status(0) & shim.STATUS_CAPACITY and of.status & oracle.ERR_CAPACITY
+    _compare(fb, 1, of)
+    m2 = np.array([[2, 1.4, -0.25], [1, 0.9, 0.12]], dtype=np.float32)               # two updates, message order
+    meas, n = fb.pack_meas([m2, m2])
+    fb.step(0.05, 0.0, meas, n)
+    of.update(0.05, 0.0, m2)
+    _compare(fb, 0, of)
+    assert list(fb.assoc(0)) == [1, 0]
+    with pytest.raises(shim.SlamError):                 # split predict/update is EKF-only (ukf.cpp:305-337)
+        fb.predict(0.1, 0.0)
+
+
+def test_ukf_filter_class(shim, oracle):
+    from live_ekf_slam_b200.filter import make_filter, UKF
+    p, lm, fwd, ang = H.config2(seed=3, steps=40, filt="ukf_slam")
+    op = H.oracle_params(oracle, p)
+    stream, _ = H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=1, instance=0)
+    filt = make_filter(p, max_landmarks=50, max_meas=8)
+    assert isinstance(filt, UKF)
+    filt.init(0, 0, 0)
+    of = oracle.OracleFilter(oracle.UKF_SLAM, op, 50)
+    of.init(0, 0, 0)
+    for t in range(len(fwd)):
+        filt.update((fwd[t], ang[t]), stream[t].reshape(-1))
+        of.update(fwd[t], ang[t], stream[t])
+    xo = of.state()
+    sv = filt.getStateVector()                            # (x, y, yaw, landmarks...) -- the vector ukf.cpp:47-53 means to build
+    assert sv.size == 3 + 2 * of.M
+    assert H.normwise(sv[3:], xo[4:]) <= H.REL_TOL and abs(sv[2] - np.arctan2(xo[3], xo[2])) <= 1e-9
+    msg = filt.publishState()
+    assert msg["P"].size == of.n * of.n and msg["M"] == of.M
