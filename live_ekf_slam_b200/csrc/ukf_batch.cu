@@ -34,7 +34,7 @@ struct UkfSmem {
     double* S4;     // [4][nmp] rows 0..3 of S ; later z0|z1 [ns_max] each
     double* K;      // [nmp][2]
     double* pool;   // 8*nmp doubles of phase-local scratch
-    double* red;    // 64 doubles reduction scratch
+    double* red;    // 160 doubles reduction scratch
     double* corr;   // clipped-eigenvalue corrections (1e-8 - d_k), aligned with clip[]
     int* clip;      // indices of clipped eigenvalues
     int* ids;
@@ -54,7 +54,7 @@ __host__ __device__ inline size_t ukf_smem_carve(const BatchState& b, unsigned c
     size_t oS4 = take(sizeof(double) * (4 * nmp > 2 * nsm ? 4 * nmp : 2 * nsm));
     size_t oK = take(sizeof(double) * 2 * nmp);
     size_t opool = take(sizeof(double) * 8 * nmp);
-    size_t ored = take(sizeof(double) * 64);
+    size_t ored = take(sizeof(double) * 160);   // block_sum<14> needs 14*8; QL control words live at +140
     size_t ocorr = take(sizeof(double) * nmp);
     size_t oclip = take(sizeof(int) * nmp);
     size_t oids = take(sizeof(int) * (b.max_lm + 1));
@@ -212,7 +212,7 @@ __device__ void eigh_smem(double* A, const int lds, const int n, double* d, doub
     __syncthreads();
 
     // ---- implicit QL on (d, e), e[k] couples k and k+1 (EISPACK tql2 organisation)
-    int* ctl = reinterpret_cast<int*>(red + 32);           // [0]=l-range start, [1]=m, [2]=done flag
+    int* ctl = reinterpret_cast<int*>(red + 140);          // [0]=l-range start, [1]=m, [2]=done flag
     double f = 0.0, tst1 = 0.0;                            // live in thread 0 only
     const double eps = 2.220446049250313e-16;
     for (int l = 0; l < n; ++l) {
