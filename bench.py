@@ -152,20 +152,18 @@ def run_ours(args):
     import torch.distributed as dist
     from live_ekf_slam_b200 import shim
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from live_ekf_slam_b200 import parallel
+    rank, local, world = parallel.world_info()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    parallel.init_distributed("nccl", torch.device("cuda", local))
     shim.load()
     B, T, K, W = args.instances, args.filter_steps, args.steps, args.warmup
     kind = shim.EKF_SLAM if args.filter == "ekf" else shim.UKF_SLAM
     p, lm, fwd, ang = build_workload("ekf_slam" if args.filter == "ekf" else "ukf_slam", T)
     fb = shim.FilterBatch(kind, p.to_c(), B, 50, args.max_meas, device=local)
-    sim = shim.Simulator(fb, lm, seed=args.seed, instance_offset=rank * B)   # RNG keyed by the GLOBAL instance id
+    sim = shim.Simulator(fb, lm, seed=args.seed, instance_offset=parallel.weak_offset(B, rank))   # RNG keyed by the GLOBAL instance id
     stream = torch.cuda.ExternalStream(fb.stream, device=torch.device("cuda", local))
     d_fwd = torch.from_numpy(fwd).cuda()
     d_ang = torch.from_numpy(ang).cuda()
@@ -206,10 +204,7 @@ def run_ours(args):
     value = world * B * T * K / (ms * 1e-3)
 
     # ---- accuracy statistics of the last sweep, summed over ranks (the only collective on this path)
-    stats = torch.from_numpy(fb.stats()).cuda()
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-    st = stats.cpu().numpy()
+    st = parallel.allreduce_stats(fb.stats(), torch.device("cuda", local))   # NCCL over NVLink when world > 1
 
     # ---- roofline of the dominant kernel: per-launch CUDA events on the launching stream, separate sweep
     fb.set_profiling(True)
@@ -288,15 +283,11 @@ def run_ours(args):
                "sample": f"{cores * per} instances x {T} steps ({cores} threads x {per}), dense-faithful oracle, {s:.1f} s"}
 
     if rank == 0:
-        cnt = max(st[0], 1.0)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "config": workload_config(args, B), "clocks": clk, "e2e": e2e,
                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-               "accuracy": {"rmse_x": float(np.sqrt(st[1] / cnt)), "rmse_y": float(np.sqrt(st[2] / cnt)),
-                            "rmse_yaw": float(np.sqrt(st[3] / cnt)), "mean_pos_err_m": float(st[4] / cnt),
-                            "mean_nees3": float(st[5] / cnt), "bad_instances": int(st[6]),
-                            "mean_final_landmarks": float(st[7] / (world * B))}}
+               "accuracy": parallel.derive_accuracy(st, world * B)}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -315,7 +306,7 @@ def main():
     ap.add_argument("--max-meas", type=int, default=8)
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--e2e-sweeps", type=int, default=2)
-    ap.add_argument("--ref-instances-per-core", type=int, default=2)
+    ap.add_argument("--ref-instances-per-core", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--traffic-bytes", type=float, default=None,

@@ -116,6 +116,21 @@ def _ptr(a):
     raise TypeError(type(a))
 
 
+def pack_meas(batch: int, max_meas: int, per_instance) -> tuple[np.ndarray, np.ndarray]:
+    """list (one per instance) of [k,3] float32 [id, r, b] arrays -> the ABI's [batch][max_meas][3] buffer + counts.
+    Counts are NOT clamped: a count above max_meas makes the kernels flag SLAM_STATUS_MEAS_OVERFLOW."""
+    if len(per_instance) != batch:
+        raise ValueError("one measurement list per instance expected")
+    meas = np.zeros((batch, max_meas, 3), dtype=np.float32)
+    n = np.zeros(batch, dtype=np.int32)
+    for i, m in enumerate(per_instance):
+        m = np.asarray(m, dtype=np.float32).reshape(-1, 3)
+        k = min(len(m), max_meas)
+        meas[i, :k] = m[:k]
+        n[i] = len(m)
+    return meas, n
+
+
 class SlamError(RuntimeError):
     """The C++ reference throws std::runtime_error (filter.h:5, localization_node.cpp:44); the ABI returns a
     status and the shim re-raises."""
@@ -178,14 +193,7 @@ class FilterBatch:
 
     def pack_meas(self, per_instance) -> tuple[np.ndarray, np.ndarray]:
         """list (one per instance) of [k,3] float32 arrays -> the [batch][max_meas][3] buffer + counts."""
-        meas = np.zeros((self.batch, self.max_meas, 3), dtype=np.float32)
-        n = np.zeros(self.batch, dtype=np.int32)
-        for i, m in enumerate(per_instance):
-            m = np.asarray(m, dtype=np.float32).reshape(-1, 3)
-            k = min(len(m), self.max_meas)
-            meas[i, :k] = m[:k]
-            n[i] = len(m)
-        return meas, n
+        return pack_meas(self.batch, self.max_meas, per_instance)
 
     def step(self, fwd, ang, meas: np.ndarray, n_meas: np.ndarray):
         """Filter::update for every instance, host buffers."""

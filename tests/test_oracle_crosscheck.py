@@ -1,0 +1,158 @@
+"""The C oracle against the independently written NumPy restatement (one mis-transcription must not
+silently define truth), plus internal consistency of the oracle's evaluation modes."""
+import numpy as np
+import pytest
+
+from oracle import oracle_np
+from tests import helpers as H
+
+
+def _run_pair(oracle, kind, NP, steps, seed, known=True):
+    p, lm, fwd, ang = H.config2(seed=seed, steps=steps)
+    p.landmark_id_is_known = known
+    op = H.oracle_params(oracle, p)
+    pd = dict(oracle.DEFAULTS)
+    pd["landmark_id_is_known"] = int(known)
+    fc = oracle.OracleFilter(kind, op, 50)
+    fn = NP(pd)
+    fc.init(0, 0, 0)
+    fn.init(0, 0, 0)
+    stream, _ = H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=seed + 1, instance=0)
+    worst = 0.0
+    for t in range(steps):
+        fc.update(fwd[t], ang[t], stream[t], oracle.DENSE)
+        fn.update(fwd[t], ang[t], stream[t])
+        assert list(fc.assoc_log()) == fn.assoc, t
+        worst = max(worst, H.normwise(fc.state(), fn.x_t), H.normwise(fc.cov(), fn.P_t))
+    assert fc.M == fn.M and list(fc.landmark_ids()) == fn.lm_IDs
+    return worst, fc
+
+
+def test_ekf_c_vs_numpy(oracle):
+    worst, f = _run_pair(oracle, oracle.EKF_SLAM, oracle_np.EKFNP, 250, seed=0)
+    assert worst <= 1e-12 and f.M >= 8
+
+
+def test_ekf_unknown_ids_c_vs_numpy(oracle):
+    worst, f = _run_pair(oracle, oracle.EKF_SLAM, oracle_np.EKFNP, 250, seed=1, known=False)
+    assert worst <= 1e-12
+    assert list(f.landmark_ids()) == list(range(f.M))      # ids are slot numbers in this mode (ekf.cpp:84,150)
+
+
+def test_ukf_c_vs_numpy(oracle):
+    worst, f = _run_pair(oracle, oracle.UKF_SLAM, oracle_np.UKFNP, 120, seed=2)
+    assert worst <= 1e-11 and f.M >= 4
+
+
+def test_ekf_dense_equals_structured_bitwise(oracle):
+    """Structured mode only skips terms that are exactly zero in the reference's dense products."""
+    p, lm, fwd, ang = H.config2(seed=3, steps=300)
+    for known in (True, False):
+        p.landmark_id_is_known = known
+        op = H.oracle_params(oracle, p)
+        a = oracle.OracleFilter(oracle.EKF_SLAM, op, 50)
+        b = oracle.OracleFilter(oracle.EKF_SLAM, op, 50)
+        a.init(0, 0, 0)
+        b.init(0, 0, 0)
+        stream, _ = H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=4, instance=1)
+        for t in range(len(fwd)):
+            a.update(fwd[t], ang[t], stream[t], oracle.DENSE)
+            b.update(fwd[t], ang[t], stream[t], oracle.STRUCTURED)
+        assert (a.state() == b.state()).all() and (a.cov() == b.cov()).all()
+
+
+def test_ukf_single_vs_double_decomposition(oracle):
+    """sqrt(Q D+ Q^T) through a second decomposition (literal, D-3) vs Q sqrt(D+) Q^T (~1e-12)."""
+    p, lm, fwd, ang = H.config2(seed=5, steps=150)
+    op = H.oracle_params(oracle, p)
+    a = oracle.OracleFilter(oracle.UKF_SLAM, op, 50)
+    b = oracle.OracleFilter(oracle.UKF_SLAM, op, 50)
+    a.init(0, 0, 0)
+    b.init(0, 0, 0)
+    stream, _ = H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=6, instance=0)
+    for t in range(len(fwd)):
+        a.update(fwd[t], ang[t], stream[t], oracle.DENSE)
+        b.update(fwd[t], ang[t], stream[t], oracle.STRUCTURED)
+    assert H.normwise(a.state(), b.state()) <= 1e-10 and H.normwise(a.cov(), b.cov()) <= 1e-10
+
+
+def test_split_predict_measure_equals_fused(oracle):
+    p, lm, fwd, ang = H.config2(seed=7, steps=200)
+    op = H.oracle_params(oracle, p)
+    a = oracle.OracleFilter(oracle.EKF_SLAM, op, 50)
+    b = oracle.OracleFilter(oracle.EKF_SLAM, op, 50)
+    a.init(0, 0, 0)
+    b.init(0, 0, 0)
+    stream, _ = H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=8, instance=0)
+    for t in range(len(fwd)):
+        a.update(fwd[t], ang[t], stream[t], oracle.DENSE)
+        b.predict(fwd[t], ang[t], oracle.DENSE)
+        b.measure(stream[t], oracle.DENSE)
+    assert (a.state() == b.state()).all() and (a.cov() == b.cov()).all() and a.timestep == b.timestep
+
+
+def test_same_step_rematch_raises_in_both(oracle):
+    p = H.Params()
+    p.landmark_id_is_known = False
+    op = H.oracle_params(oracle, p)
+    f = oracle.OracleFilter(oracle.EKF_SLAM, op, 8)
+    f.init(0, 0, 0)
+    m = np.array([[0, 2.0, 0.1], [0, 2.01, 0.1]], dtype=np.float32)
+    f.update(0.05, 0.0, m)
+    assert f.status & oracle.ERR_SAME_STEP_REMATCH and f.M == 0
+    pd = dict(oracle.DEFAULTS)
+    pd["landmark_id_is_known"] = 0
+    g = oracle_np.EKFNP(pd)
+    g.init(0, 0, 0)
+    with pytest.raises((RuntimeError, IndexError)):
+        g.update(0.05, 0.0, m)
+
+
+def test_sim_c_vs_numpy(oracle):
+    """sim_node.py:209-250: the C generator against the NumPy one given the same Philox uniforms."""
+    p, lm, fwd, ang = H.config2(seed=9, steps=200)
+    op = H.oracle_params(oracle, p)
+    pd = p.as_dict()
+    truth_c = np.zeros(3)
+    truth_n = [0.0, 0.0, 0.0]
+    seed, inst, total = 77, 5, 0
+    for t in range(len(fwd)):
+        mc = oracle.sim_step(op, truth_c, fwd[t], ang[t], lm, seed, inst, t)
+        rn = oracle.philox(inst, t, 0, 0, seed & 0xffffffff, seed >> 32)
+        u_cmd = (oracle.uniform(rn[0], rn[1]), oracle.uniform(rn[2], rn[3]))
+        u_lm = {}
+        for ident in range(len(lm)):
+            r4 = oracle.philox(inst, t, 1 + ident, 0, seed & 0xffffffff, seed >> 32)
+            u_lm[ident] = (oracle.uniform(r4[0], r4[1]), oracle.uniform(r4[2], r4[3]))
+        truth_n, mn = oracle_np.sim_step_np(pd, truth_n, fwd[t], ang[t], lm, u_cmd, u_lm)
+        np.testing.assert_array_equal(mc, mn)
+        assert np.abs(np.asarray(truth_n) - truth_c).max() == 0.0
+        total += len(mc)
+    assert total > 150
+    # visibility constraints hold on every message (params.yaml:30-32)
+    assert (mc[:, 1] <= p.range_max + p.W_00 + 1e-6).all() if len(mc) else True
+
+
+def test_trig_pinning_deviation_rate(oracle):
+    """D-1: cosf/sinf of a float are pinned as (float)cos((double)x).  Measure how often that differs from this
+    host's libm cosf/sinf (the reference's actual overload) and how far a UKF run moves when libm is used."""
+    xs = np.random.default_rng(0).uniform(-np.pi, np.pi, 200000).astype(np.float32)
+    pinned = np.cos(xs.astype(np.float64)).astype(np.float32)
+    libm = np.cos(xs)                                    # numpy float32 cos -> libm/SVML float path
+    rate = float((pinned != libm).mean())
+    assert rate < 0.2                                    # a few percent at most: last-bit differences only
+    assert np.abs(pinned.astype(np.float64) - libm.astype(np.float64)).max() <= 1.3e-7
+    p, lm, fwd, ang = H.config2(seed=10, steps=100)
+    op = H.oracle_params(oracle, p)
+    stream, _ = H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=1, instance=0)
+    out = []
+    for mode in (0, 1):
+        oracle.set_trig_mode(mode)
+        f = oracle.OracleFilter(oracle.UKF_SLAM, op, 50)
+        f.init(0, 0, 0)
+        for t in range(len(fwd)):
+            f.update(fwd[t], ang[t], stream[t], oracle.STRUCTURED)
+        out.append((f.state(), f.cov()))
+    oracle.set_trig_mode(0)
+    dev = max(H.normwise(out[0][0], out[1][0]), H.normwise(out[0][1], out[1][1]))
+    assert dev < 1e-4                                    # documented in DESIGN.md: float-ulp sized, far above 1e-9
