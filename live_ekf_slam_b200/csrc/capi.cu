@@ -27,6 +27,10 @@ struct slam_filter {
     double* d_out = nullptr;      // scratch for stats / poses
     size_t d_out_cap = 0;
     long long launches = 0;
+    // single large-map instance (P in HBM, deferred rank-2k DMMA update): csrc/ekf_large.cu
+    bool large = false;
+    LargeState lg{};
+    int* h_nmeas_pin = nullptr;       // pinned scratch for the host-side measurement count
     // per-launch timing of the filter-step kernel
     // capacity hint: device max(M) read back with a lag of HINT_LAG launches (never waited on in steady state)
     static constexpr int HINT_RING = 16, HINT_LAG = 8;
@@ -112,8 +116,14 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
 
     const size_t smem = (kind == SLAM_EKF_SLAM) ? ekf_step_smem_bytes(b) : ukf_step_smem_bytes(b);
     if (smem > (size_t)prop.sharedMemPerBlockOptin) {
-        delete h; h = nullptr;
-        return fail(h, "slam_create: max_landmarks too large for the shared-memory-resident batch kernels");
+        if (kind == SLAM_EKF_SLAM && batch == 1 && max_meas <= 256) {
+            h->large = true;                       // P stays in HBM: large-map path
+            b.fixed_ld = ldg_of(b.n_max);
+        } else {
+            delete h; h = nullptr;
+            return fail(h, "slam_create: max_landmarks too large for the shared-memory-resident batch kernels "
+                           "(the HBM-resident large-map path needs kind = EKF_SLAM, batch = 1, max_meas <= 256)");
+        }
     }
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaMalloc(&b.P, sizeof(double) * (size_t)batch * b.p_stride));
@@ -139,7 +149,19 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
     CK(cudaMalloc(&h->d_nmeas, sizeof(int) * batch));
     h->d_out_cap = sizeof(double) * (size_t)(3 * batch + SLAM_NUM_STATS);
     CK(cudaMalloc(&h->d_out, h->d_out_cap));
-    if (kind == SLAM_EKF_SLAM) CK(ekf_step_configure(b)); else CK(ukf_step_configure(b));
+    if (h->large) {
+        LargeState& g = h->lg;
+        g.P = b.P; g.x = b.x; g.ids = b.ids; g.meta = b.meta; g.assoc = b.assoc; g.stats = b.stats;
+        g.ld = b.fixed_ld; g.n_max = b.n_max; g.max_lm = b.max_lm; g.max_meas = b.max_meas;
+        CK(cudaMalloc(&g.xp, sizeof(double) * b.x_stride));
+        CK(cudaMalloc(&g.U, sizeof(double) * (size_t)b.max_meas * b.n_max * 2));
+        CK(cudaMalloc(&g.G, sizeof(double) * (size_t)b.max_meas * 2 * g.ld));
+        CK(cudaMalloc(&g.ctl, sizeof(int) * 4 * b.max_meas));
+        CK(cudaMalloc(&g.cur, sizeof(int) * 4));
+        CK(cudaMalloc(&g.sc, sizeof(double) * 16));
+        CK(cudaMemset(g.cur, 0, sizeof(int) * 4));
+        CK(cudaMallocHost(&h->h_nmeas_pin, sizeof(int)));
+    } else if (kind == SLAM_EKF_SLAM) CK(ekf_step_configure(b)); else CK(ukf_step_configure(b));
     *out = h;
     return slam_init(h, 0.f, 0.f, 0.f);
 }
@@ -152,6 +174,8 @@ int slam_destroy(slam_handle_t h) {
     cudaFree(b.P); cudaFree(b.x); cudaFree(b.ids); cudaFree(b.meta);
     cudaFree(b.assoc); cudaFree(b.stats); cudaFree(b.sigma);
     cudaFree(b.retry_list); cudaFree(b.retry_count); cudaFree(b.max_M);
+    if (h->large) { cudaFree(h->lg.xp); cudaFree(h->lg.U); cudaFree(h->lg.G); cudaFree(h->lg.ctl); cudaFree(h->lg.cur); cudaFree(h->lg.sc); }
+    if (h->h_nmeas_pin) cudaFreeHost(h->h_nmeas_pin);
     if (h->h_hint) cudaFreeHost(h->h_hint);
     for (int i = 0; i < slam_filter::HINT_RING; ++i) if (h->hint_ev[i]) cudaEventDestroy(h->hint_ev[i]);
     cudaFree(h->d_fwd); cudaFree(h->d_ang); cudaFree(h->d_meas); cudaFree(h->d_nmeas);
@@ -217,6 +241,25 @@ int slam_init(slam_handle_t h, float x_0, float y_0, float yaw_0) {
 static int do_step(slam_filter* h, const float* d_fwd, const float* d_ang, int cmd_stride, const float* d_meas,
                    const int* d_nmeas, int phases) {
     CK(cudaSetDevice(h->device));
+    if (h->large) {
+        if (phases != (STEP_PREDICT | STEP_UPDATE)) return fail(h, "split predict/update is not available on the large-map path");
+        // the per-measurement kernels are launched from the host: the detection count must be known here
+        CK(cudaMemcpyAsync(h->h_nmeas_pin, d_nmeas, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        int nm = *h->h_nmeas_pin;
+        if (nm > h->b.max_meas) nm = h->b.max_meas;
+        if (h->profiling) {
+            if (h->ev_used + 2 > h->ev.size()) {
+                const size_t old = h->ev.size();
+                h->ev.resize(old + 4096);
+                for (size_t i = old; i < h->ev.size(); ++i) CK(cudaEventCreate(&h->ev[i]));
+            }
+            CK(cudaEventRecord(h->ev[h->ev_used], h->stream));
+        }
+        CK(launch_ekf_large_step(h->lg, h->fc, d_fwd, d_ang, d_meas, nm, h->b.n_max, h->stream, &h->launches));
+        if (h->profiling) { CK(cudaEventRecord(h->ev[h->ev_used + 1], h->stream)); h->ev_used += 2; }
+        return 0;
+    }
     StepInputs in{d_fwd, d_ang, cmd_stride, d_meas, d_nmeas};
     if (h->kind != SLAM_EKF_SLAM && phases != (STEP_PREDICT | STEP_UPDATE))
         return fail(h, "split predict/update is defined for EKF_SLAM only: the UKF update stage consumes the sigma points of the same call (ukf.cpp:305-337)");

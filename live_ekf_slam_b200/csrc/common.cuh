@@ -151,6 +151,25 @@ cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const St
 size_t ukf_step_smem_bytes(const BatchState& b);
 cudaError_t ukf_step_configure(const BatchState& b);
 
+// single large-map EKF instance (csrc/ekf_large.cu): P stays in HBM with a fixed leading dimension
+struct LargeState {
+    double* P;        // [n_max][ld]
+    double* x;        // committed x_t
+    double* xp;       // running x_pred
+    double* U;        // [max_meas][n_max][2]   -K_q of the step's updates
+    double* G;        // [max_meas][2][ld]      G_q = H_q P_{q-1}
+    int* ids;         // lm_IDs
+    int4* meta;       // {M, status, timestep, n_assoc}
+    int* assoc;       // [max_meas]
+    int* ctl;         // per measurement: [4l+0]=slot, [4l+1]=updates before, [4l+2]=M before, [4l+3]=kind (0 skip, 1 update, 2 insert)
+    int* cur;         // [0]=updates so far, [1]=M so far, [2]=status, [3]=M at step start
+    double* sc;       // scalars of the current measurement: H[10], nu[2], cb, sb, r, b
+    double* stats;
+    int ld, n_max, max_lm, max_meas;
+};
+cudaError_t launch_ekf_large_step(const LargeState& L, const FilterConst& fc, const float* d_fwd, const float* d_ang,
+                                  const float* d_meas, int n_meas, int n_upper, cudaStream_t st, long long* launches);
+
 struct SimState {
     double* truth;         // [batch][3]
     const double* lm_xy;   // [n_lm][2]

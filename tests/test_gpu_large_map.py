@@ -1,0 +1,76 @@
+"""GPU parity of the large-map EKF path (BASELINE config 4 at reduced scale): P resident in HBM, the step's landmark
+updates deferred and applied as one rank-2k DMMA contraction, unknown-ID box-gate association."""
+import numpy as np
+import pytest
+
+from live_ekf_slam_b200 import workload as wl
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def shim():
+    from live_ekf_slam_b200 import shim as s
+    s.load()
+    return s
+
+
+def dense_workload(n_lm, bound, steps, seed, known):
+    p = H.Params(filter="ekf_slam")
+    p.landmark_id_is_known = known
+    p.map_bound = bound
+    rng = np.random.default_rng(seed)
+    lm = wl.random_map_fast(n_lm, bound, 0.3, rng)      # generation min-sep 0.3
+    fwd, ang = wl.tsp_trajectory(lm, p, rng, steps)
+    return p, lm, fwd, ang
+
+
+@pytest.mark.parametrize("known", [False, True])
+def test_large_map_per_step_parity(shim, oracle, known):
+    p, lm, fwd, ang = dense_workload(140, 3.2, 120, seed=3, known=known)
+    op = H.oracle_params(oracle, p)
+    stream, _ = H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=17, instance=0)
+    kmax = max(len(m) for m in stream)
+    assert kmax >= 20, kmax                               # dense enough that a step is a genuine rank-2k update
+    of = oracle.OracleFilter(oracle.EKF_SLAM, op, 140)
+    of.init(0, 0, 0)
+    fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 1, 140, 128)     # 283 states: does not fit on chip -> HBM path
+    fb.init(0, 0, 0)
+    worst, updates = 0.0, 0
+    for t in range(len(fwd)):
+        m = stream[t].copy()
+        if not known and len(m):
+            m[:, 0] = -5.0                               # ids must be ignored in unknown-ID mode
+        of.update(fwd[t], ang[t], m, oracle.STRUCTURED)
+        meas, n = fb.pack_meas([m])
+        fb.step(fwd[t], ang[t], meas, n)
+        a = list(fb.assoc(0))
+        assert a == list(of.assoc_log()), t              # association decisions bit-exact
+        updates += sum(1 for v in a if v >= 0)
+        if t % 10 == 0 or t == len(fwd) - 1:
+            assert fb.num_landmarks(0) == of.M
+            assert list(fb.landmark_ids(0)) == list(of.landmark_ids())
+            ex, eP = H.normwise(fb.state(0), of.state()), H.normwise(fb.cov(0), of.cov())
+            assert ex <= H.REL_TOL and eP <= H.REL_TOL, (t, ex, eP)
+            worst = max(worst, ex, eP)
+    assert of.status == 0 and fb.status(0) == 0 and fb.timestep(0) == len(fwd)
+    assert of.M >= 60 and updates > 1500
+    x, xo = fb.state(0), of.state()
+    assert np.abs(x[:3] - xo[:3]).max() <= H.FINAL_TOL
+    print("large-map worst normwise err", worst, "M", of.M, "updates", updates, "kmax", kmax)
+
+
+def test_large_map_with_gpu_simulator(shim, oracle):
+    """slam_run on the large-map path: on-GPU simulator -> filter, against an oracle instance."""
+    p, lm, fwd, ang = dense_workload(120, 3.0, 60, seed=5, known=False)
+    op = H.oracle_params(oracle, p)
+    fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 1, 120, 128)
+    fb.init(0, 0, 0)
+    sim = shim.Simulator(fb, lm, seed=9, instance_offset=4)
+    sim.run(fwd, ang)
+    st, pose, truth, filt = oracle.run_instance(oracle.EKF_SLAM, op, lm, fwd, ang, 9, 4, 120, oracle.STRUCTURED, keep=True)
+    assert st == 0 and fb.status(0) == 0
+    assert fb.num_landmarks(0) == filt.M
+    assert np.abs(fb.poses()[0] - pose[-1]).max() <= H.FINAL_TOL
+    assert H.normwise(fb.cov(0), filt.cov()) <= 1e-8
