@@ -157,9 +157,9 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
         CK(cudaMalloc(&g.U, sizeof(double) * (size_t)b.max_meas * b.n_max * 2));
         CK(cudaMalloc(&g.G, sizeof(double) * (size_t)b.max_meas * 2 * g.ld));
         CK(cudaMalloc(&g.ctl, sizeof(int) * 4 * b.max_meas));
-        CK(cudaMalloc(&g.cur, sizeof(int) * 4));
+        CK(cudaMalloc(&g.cur, sizeof(int) * 16));      // [0..3] step bookkeeping, [8] grid-barrier counter
         CK(cudaMalloc(&g.sc, sizeof(double) * 16));
-        CK(cudaMemset(g.cur, 0, sizeof(int) * 4));
+        CK(cudaMemset(g.cur, 0, sizeof(int) * 16));
         CK(cudaMallocHost(&h->h_nmeas_pin, sizeof(int)));
     } else if (kind == SLAM_EKF_SLAM) CK(ekf_step_configure(b)); else CK(ukf_step_configure(b));
     *out = h;

@@ -37,7 +37,7 @@ __global__ void lm_predict_rows(LargeState L, FilterConst fc, const float* fwd, 
         if (j == 2) xv = remainder(L.x[2] + (double)d_th + (double)fc.v_th, TWO_PI_REF);
         L.xp[j] = xv;
     }
-    if (j == 0) { L.cur[0] = 0; L.cur[1] = M; L.cur[2] = L.meta[0].y; L.cur[3] = M; }
+    if (j == 0) { L.cur[0] = 0; L.cur[1] = M; L.cur[2] = L.meta[0].y; L.cur[3] = M; }   // also valid when the step has no detections
 }
 // P' = T F_x^T (cols 0,1 pick up col 2) + (F_v V) F_v^T
 __global__ void lm_predict_cols(LargeState L, FilterConst fc, const float* fwd) {
@@ -57,236 +57,245 @@ __global__ void lm_predict_cols(LargeState L, FilterConst fc, const float* fwd) 
     if (i == 2) row[2] = t2 + fc.V11;
 }
 
-// ---- association + bookkeeping of measurement l (ekf.cpp:79-109), one CTA of 1024 threads
-__global__ void __launch_bounds__(1024) lm_assoc(LargeState L, FilterConst fc, const float* meas, int l) {
-    __shared__ int s_min;
-    __shared__ double s_det[2];
-    const int tid = threadIdx.x;
-    const int M = L.cur[1], m = L.cur[0], M_start = L.cur[3];
-    const float r = meas[3 * l + 1], bb = meas[3 * l + 2];
-    if (tid == 0) {
-        s_min = INT_MAX;
-        if (!fc.id_known) {
-            double sa, ca;
-            sincos(L.xp[2] + (double)bb, &sa, &ca);
-            s_det[0] = (double)(float)(L.xp[0] + (double)r * ca);   // :87
-            s_det[1] = (double)(float)(L.xp[1] + (double)r * sa);   // :88
-        }
-    }
-    __syncthreads();
-    int cand = INT_MAX;
-    if (!fc.id_known) {
-        const double xd = s_det[0], yd = s_det[1];
-        for (int j = tid; j < M; j += blockDim.x) {
-            const float x_diff = (float)fabs(xd - L.xp[3 + 2 * j]);
-            const float y_diff = (float)fabs(yd - L.xp[4 + 2 * j]);
-            if (x_diff < fc.min_sep && y_diff < fc.min_sep) { cand = j; break; }
-        }
-    } else {
-        const int id = (int)meas[3 * l];
-        for (int j = tid; j < M; j += blockDim.x) if (L.ids[j] == id) { cand = j; break; }
-    }
-    cand = __reduce_min_sync(0xffffffffu, cand);
-    if ((tid & 31) == 0 && cand != INT_MAX) atomicMin(&s_min, cand);
-    __syncthreads();
-    if (tid == 0) {
-        const int slot = s_min;
-        int kind = 0;
-        int status = L.cur[2];
-        if (status & SLAM_STATUS_SAME_STEP_REMATCH) kind = 0;          // dead for the rest of the step
-        else if (slot != INT_MAX) {
-            if (slot >= M_start) { status |= SLAM_STATUS_SAME_STEP_REMATCH; kind = 0; }   // ekf.cpp:115 would throw
-            else kind = 1;
-        } else {
-            if (M >= L.max_lm) { status |= SLAM_STATUS_CAPACITY; kind = 0; }
-            else kind = 2;
-        }
-        L.assoc[l] = (slot == INT_MAX) ? -1 : slot;
-        L.ctl[4 * l + 0] = slot; L.ctl[4 * l + 1] = m; L.ctl[4 * l + 2] = M; L.ctl[4 * l + 3] = kind;
-        L.cur[2] = status;
-        if (kind == 1) {
-            // scalars of the update (:115-131): landmark from the stale x_t, vehicle from the running x_pred
-            const int i = slot * 2 + 3;
-            const double dx = L.x[i] - L.xp[0], dy = L.x[i + 1] - L.xp[1];
-            const float dist = (float)sqrt(dx * dx + dy * dy);
-            const double dd = (double)dist, d2 = (double)(dist * dist);
-            double* H = L.sc;
-            H[0] = -(dx) / dd; H[1] = -(dy) / dd; H[2] = 0.0; H[3] = dx / dd; H[4] = dy / dd;
-            H[5] = dy / d2; H[6] = -(dx) / d2; H[7] = -1.0; H[8] = -(dy) / d2; H[9] = dx / d2;
-            const float ang = (float)remainder(atan2(dy, dx) - L.xp[2], TWO_PI_REF);
-            L.sc[10] = (double)(r - dist - fc.w_r);
-            L.sc[11] = (double)(bb - ang - fc.w_b);
-            L.cur[0] = m + 1;
-        } else if (kind == 2) {
-            double sb, cb;
-            sincos(L.xp[2] + (double)bb, &sb, &cb);
-            L.sc[12] = cb; L.sc[13] = sb; L.sc[14] = (double)r; L.sc[15] = (double)bb;
-            L.ids[M] = fc.id_known ? (int)meas[3 * l] : M;              // :84,150
-            L.cur[1] = M + 1;
-        }
-    }
-}
-
-// ---- measurement l, all slices: either the deferred update (writes G_m, U_m, x_pred) or the insertion
+// ---- the sequential part of the step: ONE persistent kernel walks the measurements (ekf.cpp:73-174); the CTAs own
+// slices of the state and meet at a software grid barrier twice per measurement (after the association vote and
+// after x_pred / U / G of the measurement are published).  All CTAs are co-resident (cooperative launch).
 constexpr int LM_THREADS = 128;
 constexpr int LM_QMAX = 256;     // max updates per step held in the coefficient tables
 
-__global__ void __launch_bounds__(LM_THREADS) lm_measure(LargeState L, FilterConst fc, int l) {
+__device__ __forceinline__ void grid_sync(unsigned* counter, const unsigned nblocks, unsigned& gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const unsigned target = (++gen) * nblocks;
+        unsigned v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while (v < target);
+    } else ++gen;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(LM_THREADS) lm_front(LargeState L, FilterConst fc, const float* meas, const int n_meas) {
     __shared__ double s_cq[LM_QMAX][4];   // (H K_q)   [r][s]
     __shared__ double s_eq[LM_QMAX][4];   // (G_q H^T) [s][r]
-    __shared__ double s_H[10];
+    __shared__ double s_sc[16];           // H[10], nu[2], cb, sb / x_detected, y_detected
     __shared__ double s_Sinv[4];
-    __shared__ double s_T3[2][3];
-    const int kind = L.ctl[4 * l + 3];
-    if (kind == 0) return;
+    __shared__ int s_min;
     const int tid = threadIdx.x;
-    const int m = L.ctl[4 * l + 1], M = L.ctl[4 * l + 2];
-    const int n = 3 + 2 * M, ld = L.ld;
-    const int idx = blockIdx.x * LM_THREADS + tid;        // this thread's row i and column j
+    const int ld = L.ld;
+    const int idx = blockIdx.x * LM_THREADS + tid;        // this thread's row i, column j and landmark-pair slot
     const size_t ustride = (size_t)L.n_max * 2, gstride = (size_t)2 * ld;
+    unsigned* bar = reinterpret_cast<unsigned*>(L.cur + 8);
+    int* slots = L.ctl;                                   // [max_meas], preset to INT_MAX by the host
+    unsigned gen = 0;
+    // replicated bookkeeping: every thread of every CTA tracks the same (m, M, status)
+    const int M_start = L.cur[3];
+    int m = 0, M = M_start, status = L.cur[2];
 
-    if (kind == 1) {
-        const int slot = L.ctl[4 * l + 0];
-        const int hc[5] = {0, 1, 2, slot * 2 + 3, slot * 2 + 4};
-        if (tid < 10) s_H[tid] = L.sc[tid];
-        __syncthreads();
-        double H[10];
-#pragma unroll
-        for (int q = 0; q < 10; ++q) H[q] = s_H[q];
-        // coefficient tables for the earlier updates of this step
-        for (int q = tid; q < m; q += LM_THREADS) {
-            const double* Uq = L.U + q * ustride;          // holds -K_q
-            const double* Gq = L.G + q * gstride;
-            double c00 = 0, c01 = 0, c10 = 0, c11 = 0, e00 = 0, e01 = 0, e10 = 0, e11 = 0;
-#pragma unroll
-            for (int c = 0; c < 5; ++c) {
-                const double k0 = -Uq[2 * hc[c]], k1 = -Uq[2 * hc[c] + 1];
-                c00 += H[c] * k0; c01 += H[c] * k1; c10 += H[5 + c] * k0; c11 += H[5 + c] * k1;
-                const double g0 = Gq[hc[c]], g1 = Gq[ld + hc[c]];
-                e00 += g0 * H[c]; e01 += g0 * H[5 + c]; e10 += g1 * H[c]; e11 += g1 * H[5 + c];
+    for (int l = 0; l < n_meas; ++l) {
+        const float r = meas[3 * l + 1], bb = meas[3 * l + 2];
+        // -------- association vote (:79-109): first match in ascending slot order = global min
+        if (tid == 0) {
+            s_min = INT_MAX;
+            if (!fc.id_known) {
+                double sa, ca;
+                sincos(__ldcg(L.xp + 2) + (double)bb, &sa, &ca);
+                s_sc[12] = (double)(float)(__ldcg(L.xp + 0) + (double)r * ca);   // float x_detected, :87
+                s_sc[13] = (double)(float)(__ldcg(L.xp + 1) + (double)r * sa);   // float y_detected, :88
             }
-            s_cq[q][0] = c00; s_cq[q][1] = c01; s_cq[q][2] = c10; s_cq[q][3] = c11;
-            s_eq[q][0] = e00; s_eq[q][1] = e01; s_eq[q][2] = e10; s_eq[q][3] = e11;
         }
         __syncthreads();
-        // S = (H P_m)[.,hc] H^T + W, evaluated redundantly by every CTA (:133), then S^-1 (partial-pivot LU, :135)
-        if (tid == 0) {
-            double S[2][2] = {{0, 0}, {0, 0}};
-            for (int cc = 0; cc < 5; ++cc) {
-                double g0 = 0, g1 = 0;
+        int cand = INT_MAX;
+        if (idx < M) {
+            if (!fc.id_known) {
+                const float x_diff = (float)fabs(s_sc[12] - __ldcg(L.xp + 3 + 2 * idx));   // :91
+                const float y_diff = (float)fabs(s_sc[13] - __ldcg(L.xp + 4 + 2 * idx));   // :92
+                if (x_diff < fc.min_sep && y_diff < fc.min_sep) cand = idx;
+            } else if (__ldcg(L.ids + idx) == (int)meas[3 * l]) cand = idx;               // :101-108
+        }
+        cand = __reduce_min_sync(0xffffffffu, cand);
+        if ((tid & 31) == 0 && cand != INT_MAX) atomicMin(&s_min, cand);
+        __syncthreads();
+        if (tid == 0 && s_min != INT_MAX) atomicMin(&slots[l], s_min);
+        grid_sync(bar, gridDim.x, gen);
+        int slot = __ldcg(slots + l);
+        if (slot == 0x7f7f7f7f) slot = INT_MAX;
+        int kind = 0;
+        if (status & SLAM_STATUS_SAME_STEP_REMATCH) kind = 0;                  // dead for the rest of the step
+        else if (slot != INT_MAX) {
+            if (slot >= M_start) status |= SLAM_STATUS_SAME_STEP_REMATCH;       // ekf.cpp:115 would throw here
+            else kind = 1;
+        } else {
+            if (M >= L.max_lm) status |= SLAM_STATUS_CAPACITY;
+            else kind = 2;
+        }
+        if (blockIdx.x == 0 && tid == 0) L.assoc[l] = (slot == INT_MAX) ? -1 : slot;
+        const int n = 3 + 2 * M;
+
+        if (kind == 1) {
+            // -------- deferred landmark update (:110-140)
+            const int hc[5] = {0, 1, 2, slot * 2 + 3, slot * 2 + 4};
+            if (tid == 0) {
+                // landmark from the stale x_t, vehicle from the running x_pred (:115-131)
+                const int i = slot * 2 + 3;
+                const double xv0 = __ldcg(L.xp + 0), xv1 = __ldcg(L.xp + 1), xv2 = __ldcg(L.xp + 2);
+                const double dx = L.x[i] - xv0, dy = L.x[i + 1] - xv1;
+                const float dist = (float)sqrt(dx * dx + dy * dy);
+                const double dd = (double)dist, d2 = (double)(dist * dist);
+                s_sc[0] = -(dx) / dd; s_sc[1] = -(dy) / dd; s_sc[2] = 0.0; s_sc[3] = dx / dd; s_sc[4] = dy / dd;
+                s_sc[5] = dy / d2; s_sc[6] = -(dx) / d2; s_sc[7] = -1.0; s_sc[8] = -(dy) / d2; s_sc[9] = dx / d2;
+                const float ang = (float)remainder(atan2(dy, dx) - xv2, TWO_PI_REF);
+                s_sc[10] = (double)(r - dist - fc.w_r);
+                s_sc[11] = (double)(bb - ang - fc.w_b);
+            }
+            __syncthreads();
+            double H[10];
+#pragma unroll
+            for (int q = 0; q < 10; ++q) H[q] = s_sc[q];
+            // coefficient tables for the earlier updates of this step
+            for (int q = tid; q < m; q += LM_THREADS) {
+                const double* Uq = L.U + q * ustride;          // holds -K_q
+                const double* Gq = L.G + q * gstride;
+                double c00 = 0, c01 = 0, c10 = 0, c11 = 0, e00 = 0, e01 = 0, e10 = 0, e11 = 0;
+#pragma unroll
                 for (int c = 0; c < 5; ++c) {
-                    const double p = L.P[(size_t)hc[c] * ld + hc[cc]];
-                    g0 += H[c] * p; g1 += H[5 + c] * p;
+                    const double k0 = -__ldcg(Uq + 2 * hc[c]), k1 = -__ldcg(Uq + 2 * hc[c] + 1);
+                    c00 += H[c] * k0; c01 += H[c] * k1; c10 += H[5 + c] * k0; c11 += H[5 + c] * k1;
+                    const double g0 = __ldcg(Gq + hc[c]), g1 = __ldcg(Gq + ld + hc[c]);
+                    e00 += g0 * H[c]; e01 += g0 * H[5 + c]; e10 += g1 * H[c]; e11 += g1 * H[5 + c];
                 }
+                s_cq[q][0] = c00; s_cq[q][1] = c01; s_cq[q][2] = c10; s_cq[q][3] = c11;
+                s_eq[q][0] = e00; s_eq[q][1] = e01; s_eq[q][2] = e10; s_eq[q][3] = e11;
+            }
+            __syncthreads();
+            // S = (H P_m)[.,hc] H^T + W (:133), evaluated redundantly per CTA; S^-1 by partial-pivot LU (:135)
+            if (tid < 32) {
+                // lane c' < 5 reconstructs column hc[c'] of H P_m
+                double g0 = 0, g1 = 0;
+                if (tid < 5) {
+                    for (int c = 0; c < 5; ++c) {
+                        const double pv = __ldcg(L.P + (size_t)hc[c] * ld + hc[tid]);
+                        g0 += H[c] * pv; g1 += H[5 + c] * pv;
+                    }
+                    for (int q = 0; q < m; ++q) {
+                        const double* Gq = L.G + q * gstride;
+                        const double a0 = __ldcg(Gq + hc[tid]), a1 = __ldcg(Gq + ld + hc[tid]);
+                        g0 -= s_cq[q][0] * a0 + s_cq[q][1] * a1;
+                        g1 -= s_cq[q][2] * a0 + s_cq[q][3] * a1;
+                    }
+                }
+                double S00 = 0, S01 = 0, S10 = 0, S11 = 0;
+                for (int cc = 0; cc < 5; ++cc) {
+                    const double a = __shfl_sync(0xffffffffu, g0, cc), bq = __shfl_sync(0xffffffffu, g1, cc);
+                    S00 += a * H[cc]; S01 += a * H[5 + cc]; S10 += bq * H[cc]; S11 += bq * H[5 + cc];
+                }
+                if (tid == 0) {
+                    S00 += fc.W00; S11 += fc.W11;
+                    const bool sw = fabs(S10) > fabs(S00);
+                    const double a00 = sw ? S10 : S00, a01 = sw ? S11 : S01, a10 = sw ? S00 : S10, a11 = sw ? S01 : S11;
+                    const double l10 = a10 / a00, u11 = a11 - l10 * a01;
+                    const double b0c0 = sw ? 0.0 : 1.0, b1c0 = sw ? 1.0 : 0.0, b0c1 = sw ? 1.0 : 0.0, b1c1 = sw ? 0.0 : 1.0;
+                    double y1 = b1c0 - l10 * b0c0;
+                    const double i10 = y1 / u11, i00 = (b0c0 - a01 * i10) / a00;
+                    y1 = b1c1 - l10 * b0c1;
+                    const double i11 = y1 / u11, i01 = (b0c1 - a01 * i11) / a00;
+                    s_Sinv[0] = i00; s_Sinv[1] = i01; s_Sinv[2] = i10; s_Sinv[3] = i11;
+                }
+            }
+            __syncthreads();
+            if (idx < n) {
+                double g0 = 0, g1 = 0;                         // column idx of G_m = H P_m
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    const double pv = __ldcg(L.P + (size_t)hc[c] * ld + idx);
+                    g0 += H[c] * pv; g1 += H[5 + c] * pv;
+                }
+                const double* row = L.P + (size_t)idx * ld;    // row idx of P_m H^T
+                double a0 = 0, a1 = 0;
+#pragma unroll
+                for (int c = 0; c < 5; ++c) { const double pv = __ldcg(row + hc[c]); a0 += pv * H[c]; a1 += pv * H[5 + c]; }
                 for (int q = 0; q < m; ++q) {
                     const double* Gq = L.G + q * gstride;
-                    const double a0 = Gq[hc[cc]], a1 = Gq[ld + hc[cc]];
-                    g0 -= s_cq[q][0] * a0 + s_cq[q][1] * a1;
-                    g1 -= s_cq[q][2] * a0 + s_cq[q][3] * a1;
+                    const double ga = __ldcg(Gq + idx), gb = __ldcg(Gq + ld + idx);
+                    g0 -= s_cq[q][0] * ga + s_cq[q][1] * gb;
+                    g1 -= s_cq[q][2] * ga + s_cq[q][3] * gb;
+                    const double2 u = __ldcg(reinterpret_cast<const double2*>(L.U + q * ustride + 2 * (size_t)idx));   // -K_q[i]
+                    a0 += u.x * s_eq[q][0] + u.y * s_eq[q][2];
+                    a1 += u.x * s_eq[q][1] + u.y * s_eq[q][3];
                 }
-                S[0][0] += g0 * H[cc]; S[0][1] += g0 * H[5 + cc]; S[1][0] += g1 * H[cc]; S[1][1] += g1 * H[5 + cc];
+                double* Gm = L.G + m * gstride;
+                Gm[idx] = g0; Gm[ld + idx] = g1;
+                const double k0 = a0 * s_Sinv[0] + a1 * s_Sinv[2];
+                const double k1 = a0 * s_Sinv[1] + a1 * s_Sinv[3];
+                *reinterpret_cast<double2*>(L.U + m * ustride + 2 * (size_t)idx) = make_double2(-k0, -k1);
+                double xv = __ldcg(L.xp + idx) + (k0 * s_sc[10] + k1 * s_sc[11]);   // :138
+                if (idx == 2) xv = remainder(xv, TWO_PI_REF);                       // :139
+                L.xp[idx] = xv;
             }
-            S[0][0] += fc.W00; S[1][1] += fc.W11;
-            const bool sw = fabs(S[1][0]) > fabs(S[0][0]);
-            const double a00 = sw ? S[1][0] : S[0][0], a01 = sw ? S[1][1] : S[0][1];
-            const double a10 = sw ? S[0][0] : S[1][0], a11 = sw ? S[0][1] : S[1][1];
-            const double l10 = a10 / a00, u11 = a11 - l10 * a01;
-            const double b0c0 = sw ? 0.0 : 1.0, b1c0 = sw ? 1.0 : 0.0, b0c1 = sw ? 1.0 : 0.0, b1c1 = sw ? 0.0 : 1.0;
-            double y1 = b1c0 - l10 * b0c0;
-            const double i10 = y1 / u11, i00 = (b0c0 - a01 * i10) / a00;
-            y1 = b1c1 - l10 * b0c1;
-            const double i11 = y1 / u11, i01 = (b0c1 - a01 * i11) / a00;
-            s_Sinv[0] = i00; s_Sinv[1] = i01; s_Sinv[2] = i10; s_Sinv[3] = i11;
-        }
-        __syncthreads();
-        if (idx < n) {
-            // column j = idx of G_m = H P_m
-            double g0 = 0, g1 = 0;
+            m += 1;
+        } else if (kind == 2) {
+            // -------- insertion (:141-173): rows/cols nn, nn+1 materialised into P_0 from the reconstructed P_m
+            const int nn = n;
+            double sb, cb;
+            sincos(__ldcg(L.xp + 2) + (double)bb, &sb, &cb);
+            const double rr_ = (double)r;
+            const double g02 = -rr_ * sb, g12 = rr_ * cb;
+            if (blockIdx.x == 0 && tid == 0) {
+                double Pv[3][3];
+                for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) {
+                    double pv = __ldcg(L.P + (size_t)a * ld + c);
+                    for (int q = 0; q < m; ++q) {
+                        const double* Uq = L.U + q * ustride; const double* Gq = L.G + q * gstride;
+                        pv += __ldcg(Uq + 2 * a) * __ldcg(Gq + c) + __ldcg(Uq + 2 * a + 1) * __ldcg(Gq + ld + c);
+                    }
+                    Pv[a][c] = pv;
+                }
+                const double gx[2][3] = {{1.0, 0.0, g02}, {0.0, 1.0, g12}};
+                const double gz[2][2] = {{cb, -rr_ * sb}, {sb, rr_ * cb}};
+                const double Wm[2][2] = {{fc.W00, 0.0}, {0.0, fc.W11}};
+                double T3[2][3];
+                for (int rr = 0; rr < 2; ++rr) for (int k = 0; k < 3; ++k) {
+                    double t = gx[rr][0] * Pv[0][k]; t += gx[rr][1] * Pv[1][k]; t += gx[rr][2] * Pv[2][k];
+                    T3[rr][k] = t;
+                }
+                for (int rr = 0; rr < 2; ++rr) for (int c2 = 0; c2 < 2; ++c2) {
+                    const double t20 = gz[rr][0] * Wm[0][0] + gz[rr][1] * Wm[1][0], t21 = gz[rr][0] * Wm[0][1] + gz[rr][1] * Wm[1][1];
+                    double t = T3[rr][0] * gx[c2][0]; t += T3[rr][1] * gx[c2][1]; t += T3[rr][2] * gx[c2][2];
+                    t += t20 * gz[c2][0]; t += t21 * gz[c2][1];
+                    L.P[(size_t)(nn + rr) * ld + nn + c2] = t;
+                }
+                L.xp[nn] = __ldcg(L.xp + 0) + rr_ * cb;        // :147
+                L.xp[nn + 1] = __ldcg(L.xp + 1) + rr_ * sb;    // :148
+                L.ids[M] = fc.id_known ? (int)meas[3 * l] : M; // :84,150
+            }
+            if (idx < nn) {
+                double pr[3], pc[3];                           // P_m rows 0..2 at column idx / columns 0..2 at row idx
 #pragma unroll
-            for (int c = 0; c < 5; ++c) {
-                const double p = L.P[(size_t)hc[c] * ld + idx];
-                g0 += H[c] * p; g1 += H[5 + c] * p;
-            }
-            // row i = idx of P_m H^T
-            const double* row = L.P + (size_t)idx * ld;
-            double a0 = 0, a1 = 0;
-#pragma unroll
-            for (int c = 0; c < 5; ++c) { const double p = row[hc[c]]; a0 += p * H[c]; a1 += p * H[5 + c]; }
-            for (int q = 0; q < m; ++q) {
-                const double* Gq = L.G + q * gstride;
-                const double ga = Gq[idx], gb = Gq[ld + idx];
-                g0 -= s_cq[q][0] * ga + s_cq[q][1] * gb;
-                g1 -= s_cq[q][2] * ga + s_cq[q][3] * gb;
-                const double2 u = *reinterpret_cast<const double2*>(L.U + q * ustride + 2 * (size_t)idx);   // -K_q[i]
-                a0 += u.x * s_eq[q][0] + u.y * s_eq[q][2];
-                a1 += u.x * s_eq[q][1] + u.y * s_eq[q][3];
-            }
-            double* Gm = L.G + m * gstride;
-            Gm[idx] = g0; Gm[ld + idx] = g1;
-            const double k0 = a0 * s_Sinv[0] + a1 * s_Sinv[2];
-            const double k1 = a0 * s_Sinv[1] + a1 * s_Sinv[3];
-            *reinterpret_cast<double2*>(L.U + m * ustride + 2 * (size_t)idx) = make_double2(-k0, -k1);
-            double xv = L.xp[idx] + (k0 * L.sc[10] + k1 * L.sc[11]);       // :138
-            if (idx == 2) xv = remainder(xv, TWO_PI_REF);                   // :139
-            L.xp[idx] = xv;
-        }
-    } else {
-        // ---------------- insertion (:141-173): rows/cols nn, nn+1 materialised into P_0
-        const int nn = n;                                   // first new index (M is the count before insertion)
-        const double cb = L.sc[12], sb = L.sc[13], r = L.sc[14];
-        const double g02 = -r * sb, g12 = r * cb;
-        if (blockIdx.x == 0 && tid == 0) {
-            // 2x2 block and the new means need P_m[0..2][0..2]
-            double Pv[3][3];
-            for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) {
-                double p = L.P[(size_t)a * ld + c];
+                for (int k = 0; k < 3; ++k) { pr[k] = __ldcg(L.P + (size_t)k * ld + idx); pc[k] = __ldcg(L.P + (size_t)idx * ld + k); }
                 for (int q = 0; q < m; ++q) {
                     const double* Uq = L.U + q * ustride; const double* Gq = L.G + q * gstride;
-                    p += Uq[2 * a] * Gq[c] + Uq[2 * a + 1] * Gq[ld + c];
-                }
-                Pv[a][c] = p;
-            }
-            const double gx[2][3] = {{1.0, 0.0, g02}, {0.0, 1.0, g12}};
-            const double gz[2][2] = {{cb, -r * sb}, {sb, r * cb}};
-            const double Wm[2][2] = {{fc.W00, 0.0}, {0.0, fc.W11}};
-            for (int rr = 0; rr < 2; ++rr) for (int k = 0; k < 3; ++k) {
-                double t = gx[rr][0] * Pv[0][k]; t += gx[rr][1] * Pv[1][k]; t += gx[rr][2] * Pv[2][k];
-                s_T3[rr][k] = t;
-            }
-            for (int rr = 0; rr < 2; ++rr) for (int c2 = 0; c2 < 2; ++c2) {
-                const double t20 = gz[rr][0] * Wm[0][0] + gz[rr][1] * Wm[1][0], t21 = gz[rr][0] * Wm[0][1] + gz[rr][1] * Wm[1][1];
-                double t = s_T3[rr][0] * gx[c2][0]; t += s_T3[rr][1] * gx[c2][1]; t += s_T3[rr][2] * gx[c2][2];
-                t += t20 * gz[c2][0]; t += t21 * gz[c2][1];
-                L.P[(size_t)(nn + rr) * ld + nn + c2] = t;
-            }
-            L.xp[nn] = L.xp[0] + r * cb;                    // :147
-            L.xp[nn + 1] = L.xp[1] + r * sb;                // :148
-        }
-        if (idx < nn) {
-            // P_m rows 0..2 at column idx, and P_m columns 0..2 at row idx
-            double pr[3], pc[3];
+                    const double ga = __ldcg(Gq + idx), gb = __ldcg(Gq + ld + idx);
+                    const double ui0 = __ldcg(Uq + 2 * (size_t)idx), ui1 = __ldcg(Uq + 2 * (size_t)idx + 1);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { pr[k] = L.P[(size_t)k * ld + idx]; pc[k] = L.P[(size_t)idx * ld + k]; }
-            for (int q = 0; q < m; ++q) {
-                const double* Uq = L.U + q * ustride; const double* Gq = L.G + q * gstride;
-                const double ga = Gq[idx], gb = Gq[ld + idx];
-                const double ui0 = Uq[2 * (size_t)idx], ui1 = Uq[2 * (size_t)idx + 1];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    pr[k] += Uq[2 * k] * ga + Uq[2 * k + 1] * gb;
-                    pc[k] += ui0 * Gq[k] + ui1 * Gq[ld + k];
+                    for (int k = 0; k < 3; ++k) {
+                        pr[k] += __ldcg(Uq + 2 * k) * ga + __ldcg(Uq + 2 * k + 1) * gb;
+                        pc[k] += ui0 * __ldcg(Gq + k) + ui1 * __ldcg(Gq + ld + k);
+                    }
                 }
+                double t0 = 1.0 * pr[0]; t0 += 0.0 * pr[1]; t0 += g02 * pr[2];
+                double t1 = 0.0 * pr[0]; t1 += 1.0 * pr[1]; t1 += g12 * pr[2];
+                L.P[(size_t)nn * ld + idx] = t0;
+                L.P[(size_t)(nn + 1) * ld + idx] = t1;
+                double c0 = pc[0] * 1.0; c0 += pc[1] * 0.0; c0 += pc[2] * g02;
+                double c1 = pc[0] * 0.0; c1 += pc[1] * 1.0; c1 += pc[2] * g12;
+                L.P[(size_t)idx * ld + nn] = c0;
+                L.P[(size_t)idx * ld + nn + 1] = c1;
             }
-            double t0 = 1.0 * pr[0]; t0 += 0.0 * pr[1]; t0 += g02 * pr[2];
-            double t1 = 0.0 * pr[0]; t1 += 1.0 * pr[1]; t1 += g12 * pr[2];
-            L.P[(size_t)nn * ld + idx] = t0;
-            L.P[(size_t)(nn + 1) * ld + idx] = t1;
-            double c0 = pc[0] * 1.0; c0 += pc[1] * 0.0; c0 += pc[2] * g02;
-            double c1 = pc[0] * 0.0; c1 += pc[1] * 1.0; c1 += pc[2] * g12;
-            L.P[(size_t)idx * ld + nn] = c0;
-            L.P[(size_t)idx * ld + nn + 1] = c1;
+            M += 1;
         }
+        grid_sync(bar, gridDim.x, gen);
     }
+    if (blockIdx.x == 0 && tid == 0) { L.cur[0] = m; L.cur[1] = M; L.cur[2] = status; }
 }
 
 // ---- closing contraction  P <- P + U G  on the FP64 tensor cores.  U: [q][i][2] = -K_q[i], G: [q][2][ld].
@@ -382,32 +391,35 @@ __global__ void lm_commit(LargeState L, int n_meas) {
     }
 }
 
-// One reference EKF::update for the large-map instance.  n_meas is known on the host (the per-measurement kernels
-// are launched from a host loop); meas is a DEVICE pointer to [n_meas][3] float32.
+// One reference EKF::update for the large-map instance.  n_meas is known on the host; meas is a DEVICE pointer to
+// [n_meas][3] float32.
 cudaError_t launch_ekf_large_step(const LargeState& L, const FilterConst& fc, const float* d_fwd, const float* d_ang,
                                   const float* d_meas, int n_meas, int n_upper, cudaStream_t st, long long* launches) {
     const int tb = 256;
     const int gb = (n_upper + tb - 1) / tb;
     cudaError_t e;
-    // U and G are zero-extended for landmarks inserted later in the step: clear what the step can touch
     const int kcap = n_meas < L.max_meas ? n_meas : L.max_meas;
+    if (kcap > LM_QMAX) return cudaErrorInvalidValue;
     if (kcap > 0) {
+        // U and G are zero-extended for landmarks inserted later in the step: clear what the step can touch;
+        // association slots start at INT_MAX (0x7f7f7f7f is large enough and memset-able); barrier counter at 0
         e = cudaMemsetAsync(L.U, 0, sizeof(double) * (size_t)kcap * L.n_max * 2, st); if (e != cudaSuccess) return e;
         e = cudaMemsetAsync(L.G, 0, sizeof(double) * (size_t)kcap * 2 * L.ld, st); if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(L.ctl, 0x7f, sizeof(int) * (size_t)L.max_meas, st); if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(L.cur + 8, 0, sizeof(int), st); if (e != cudaSuccess) return e;
     }
     lm_predict_rows<<<gb, tb, 0, st>>>(L, fc, d_fwd, d_ang);
     lm_predict_cols<<<gb, tb, 0, st>>>(L, fc, d_fwd);
     *launches += 2;
-    const int gm = (n_upper + LM_THREADS - 1) / LM_THREADS;
-    for (int l = 0; l < kcap; ++l) {
-        lm_assoc<<<1, 1024, 0, st>>>(L, fc, d_meas, l);
-        lm_measure<<<gm, LM_THREADS, 0, st>>>(L, fc, l);
-        *launches += 2;
-    }
     if (kcap > 0) {
+        const int gm = (n_upper + LM_THREADS - 1) / LM_THREADS;     // <= 148 co-resident CTAs for n <= 18944
+        LargeState Lc = L; FilterConst fcc = fc; const float* mp = d_meas; int nm = kcap;
+        void* args[] = {&Lc, &fcc, &mp, &nm};
+        e = cudaLaunchCooperativeKernel((const void*)lm_front, dim3(gm), dim3(LM_THREADS), args, 0, st);
+        if (e != cudaSuccess) return e;
         const int gt = (n_upper + GT - 1) / GT;
         lm_gemm<<<dim3(gt, gt), 128, 0, st>>>(L);
-        *launches += 1;
+        *launches += 2;
     }
     lm_commit<<<gb, tb, 0, st>>>(L, n_meas);
     *launches += 1;
