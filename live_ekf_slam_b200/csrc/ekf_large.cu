@@ -60,7 +60,9 @@ __global__ void lm_predict_cols(LargeState L, FilterConst fc, const float* fwd) 
 // ---- the sequential part of the step: ONE persistent kernel walks the measurements (ekf.cpp:73-174); the CTAs own
 // slices of the state and meet at a software grid barrier twice per measurement (after the association vote and
 // after x_pred / U / G of the measurement are published).  All CTAs are co-resident (cooperative launch).
-constexpr int LM_THREADS = 128;
+constexpr int LM_THREADS = 256;
+constexpr int LM_WARPS = LM_THREADS / 32;
+constexpr int LM_SPAN = 32;      // state indices owned by a CTA per pass (one per lane); the warps split the q range
 constexpr int LM_QMAX = 256;     // max updates per step held in the coefficient tables
 
 __device__ __forceinline__ void grid_sync(unsigned* counter, const unsigned nblocks, unsigned& gen) {
@@ -80,10 +82,11 @@ __global__ void __launch_bounds__(LM_THREADS) lm_front(LargeState L, FilterConst
     __shared__ double s_eq[LM_QMAX][4];   // (G_q H^T) [s][r]
     __shared__ double s_sc[16];           // H[10], nu[2], cb, sb / x_detected, y_detected
     __shared__ double s_Sinv[4];
+    __shared__ double s_part[4][LM_WARPS][LM_SPAN];       // per-warp partial sums of the low-rank corrections
     __shared__ int s_min;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ld = L.ld;
-    const int idx = blockIdx.x * LM_THREADS + tid;        // this thread's row i, column j and landmark-pair slot
+    const int jlm = blockIdx.x * LM_THREADS + tid;        // landmark slot this thread votes for
     const size_t ustride = (size_t)L.n_max * 2, gstride = (size_t)2 * ld;
     unsigned* bar = reinterpret_cast<unsigned*>(L.cur + 8);
     int* slots = L.ctl;                                   // [max_meas], preset to INT_MAX by the host
@@ -106,12 +109,12 @@ __global__ void __launch_bounds__(LM_THREADS) lm_front(LargeState L, FilterConst
         }
         __syncthreads();
         int cand = INT_MAX;
-        if (idx < M) {
+        for (int j = jlm; j < M; j += gridDim.x * LM_THREADS) {
             if (!fc.id_known) {
-                const float x_diff = (float)fabs(s_sc[12] - __ldcg(L.xp + 3 + 2 * idx));   // :91
-                const float y_diff = (float)fabs(s_sc[13] - __ldcg(L.xp + 4 + 2 * idx));   // :92
-                if (x_diff < fc.min_sep && y_diff < fc.min_sep) cand = idx;
-            } else if (__ldcg(L.ids + idx) == (int)meas[3 * l]) cand = idx;               // :101-108
+                const float x_diff = (float)fabs(s_sc[12] - __ldcg(L.xp + 3 + 2 * j));     // :91
+                const float y_diff = (float)fabs(s_sc[13] - __ldcg(L.xp + 4 + 2 * j));     // :92
+                if (x_diff < fc.min_sep && y_diff < fc.min_sep) { cand = j; break; }
+            } else if (__ldcg(L.ids + j) == (int)meas[3 * l]) { cand = j; break; }         // :101-108
         }
         cand = __reduce_min_sync(0xffffffffu, cand);
         if ((tid & 31) == 0 && cand != INT_MAX) atomicMin(&s_min, cand);
@@ -169,27 +172,40 @@ __global__ void __launch_bounds__(LM_THREADS) lm_front(LargeState L, FilterConst
             }
             __syncthreads();
             // S = (H P_m)[.,hc] H^T + W (:133), evaluated redundantly per CTA; S^-1 by partial-pivot LU (:135)
-            if (tid < 32) {
-                // lane c' < 5 reconstructs column hc[c'] of H P_m
-                double g0 = 0, g1 = 0;
-                if (tid < 5) {
-                    for (int c = 0; c < 5; ++c) {
-                        const double pv = __ldcg(L.P + (size_t)hc[c] * ld + hc[tid]);
-                        g0 += H[c] * pv; g1 += H[5 + c] * pv;
-                    }
-                    for (int q = 0; q < m; ++q) {
-                        const double* Gq = L.G + q * gstride;
-                        const double a0 = __ldcg(Gq + hc[tid]), a1 = __ldcg(Gq + ld + hc[tid]);
-                        g0 -= s_cq[q][0] * a0 + s_cq[q][1] * a1;
-                        g1 -= s_cq[q][2] * a0 + s_cq[q][3] * a1;
+            if (warp == 0) {
+                // columns hc[0..4] of H P_m: lanes split the q range, lane cc < 5 adds the P_0 part of column hc[cc]
+                double g0[5], g1[5];
+#pragma unroll
+                for (int cc = 0; cc < 5; ++cc) { g0[cc] = 0.0; g1[cc] = 0.0; }
+                for (int q = lane; q < m; q += 32) {
+                    const double* Gq = L.G + q * gstride;
+#pragma unroll
+                    for (int cc = 0; cc < 5; ++cc) {
+                        const double a0 = __ldcg(Gq + hc[cc]), a1 = __ldcg(Gq + ld + hc[cc]);
+                        g0[cc] -= s_cq[q][0] * a0 + s_cq[q][1] * a1;
+                        g1[cc] -= s_cq[q][2] * a0 + s_cq[q][3] * a1;
                     }
                 }
-                double S00 = 0, S01 = 0, S10 = 0, S11 = 0;
+#pragma unroll
                 for (int cc = 0; cc < 5; ++cc) {
-                    const double a = __shfl_sync(0xffffffffu, g0, cc), bq = __shfl_sync(0xffffffffu, g1, cc);
-                    S00 += a * H[cc]; S01 += a * H[5 + cc]; S10 += bq * H[cc]; S11 += bq * H[5 + cc];
+                    if (lane == cc) {
+                        for (int c = 0; c < 5; ++c) {
+                            const double pv = __ldcg(L.P + (size_t)hc[c] * ld + hc[cc]);
+                            g0[cc] += H[c] * pv; g1[cc] += H[5 + c] * pv;
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        g0[cc] += __shfl_xor_sync(0xffffffffu, g0[cc], o);
+                        g1[cc] += __shfl_xor_sync(0xffffffffu, g1[cc], o);
+                    }
                 }
-                if (tid == 0) {
+                if (lane == 0) {
+                    double S00 = 0, S01 = 0, S10 = 0, S11 = 0;
+#pragma unroll
+                    for (int cc = 0; cc < 5; ++cc) {
+                        S00 += g0[cc] * H[cc]; S01 += g0[cc] * H[5 + cc]; S10 += g1[cc] * H[cc]; S11 += g1[cc] * H[5 + cc];
+                    }
                     S00 += fc.W00; S11 += fc.W11;
                     const bool sw = fabs(S10) > fabs(S00);
                     const double a00 = sw ? S10 : S00, a01 = sw ? S11 : S01, a10 = sw ? S00 : S10, a11 = sw ? S01 : S11;
@@ -203,34 +219,49 @@ __global__ void __launch_bounds__(LM_THREADS) lm_front(LargeState L, FilterConst
                 }
             }
             __syncthreads();
-            if (idx < n) {
-                double g0 = 0, g1 = 0;                         // column idx of G_m = H P_m
+            for (int base = blockIdx.x * LM_SPAN; base < n; base += gridDim.x * LM_SPAN) {
+                const int idx = base + lane;                   // this lane's row i and column j
+                double g0 = 0, g1 = 0, a0 = 0, a1 = 0;
+                if (idx < n) {
+                    if (warp == 0) {
 #pragma unroll
-                for (int c = 0; c < 5; ++c) {
-                    const double pv = __ldcg(L.P + (size_t)hc[c] * ld + idx);
-                    g0 += H[c] * pv; g1 += H[5 + c] * pv;
-                }
-                const double* row = L.P + (size_t)idx * ld;    // row idx of P_m H^T
-                double a0 = 0, a1 = 0;
+                        for (int c = 0; c < 5; ++c) {          // column idx of H P_0
+                            const double pv = __ldcg(L.P + (size_t)hc[c] * ld + idx);
+                            g0 += H[c] * pv; g1 += H[5 + c] * pv;
+                        }
+                    } else if (warp == 1) {
+                        const double* row = L.P + (size_t)idx * ld;    // row idx of P_0 H^T
 #pragma unroll
-                for (int c = 0; c < 5; ++c) { const double pv = __ldcg(row + hc[c]); a0 += pv * H[c]; a1 += pv * H[5 + c]; }
-                for (int q = 0; q < m; ++q) {
-                    const double* Gq = L.G + q * gstride;
-                    const double ga = __ldcg(Gq + idx), gb = __ldcg(Gq + ld + idx);
-                    g0 -= s_cq[q][0] * ga + s_cq[q][1] * gb;
-                    g1 -= s_cq[q][2] * ga + s_cq[q][3] * gb;
-                    const double2 u = __ldcg(reinterpret_cast<const double2*>(L.U + q * ustride + 2 * (size_t)idx));   // -K_q[i]
-                    a0 += u.x * s_eq[q][0] + u.y * s_eq[q][2];
-                    a1 += u.x * s_eq[q][1] + u.y * s_eq[q][3];
+                        for (int c = 0; c < 5; ++c) { const double pv = __ldcg(row + hc[c]); a0 += pv * H[c]; a1 += pv * H[5 + c]; }
+                    }
+                    for (int q = warp; q < m; q += LM_WARPS) {  // low-rank corrections, q range split over the warps
+                        const double* Gq = L.G + q * gstride;
+                        const double ga = __ldcg(Gq + idx), gb = __ldcg(Gq + ld + idx);
+                        g0 -= s_cq[q][0] * ga + s_cq[q][1] * gb;
+                        g1 -= s_cq[q][2] * ga + s_cq[q][3] * gb;
+                        const double2 u = __ldcg(reinterpret_cast<const double2*>(L.U + q * ustride + 2 * (size_t)idx));   // -K_q[i]
+                        a0 += u.x * s_eq[q][0] + u.y * s_eq[q][2];
+                        a1 += u.x * s_eq[q][1] + u.y * s_eq[q][3];
+                    }
                 }
-                double* Gm = L.G + m * gstride;
-                Gm[idx] = g0; Gm[ld + idx] = g1;
-                const double k0 = a0 * s_Sinv[0] + a1 * s_Sinv[2];
-                const double k1 = a0 * s_Sinv[1] + a1 * s_Sinv[3];
-                *reinterpret_cast<double2*>(L.U + m * ustride + 2 * (size_t)idx) = make_double2(-k0, -k1);
-                double xv = __ldcg(L.xp + idx) + (k0 * s_sc[10] + k1 * s_sc[11]);   // :138
-                if (idx == 2) xv = remainder(xv, TWO_PI_REF);                       // :139
-                L.xp[idx] = xv;
+                s_part[0][warp][lane] = g0; s_part[1][warp][lane] = g1; s_part[2][warp][lane] = a0; s_part[3][warp][lane] = a1;
+                __syncthreads();
+                if (warp == 0 && idx < n) {
+                    g0 = 0; g1 = 0; a0 = 0; a1 = 0;
+#pragma unroll
+                    for (int w = 0; w < LM_WARPS; ++w) {
+                        g0 += s_part[0][w][lane]; g1 += s_part[1][w][lane]; a0 += s_part[2][w][lane]; a1 += s_part[3][w][lane];
+                    }
+                    double* Gm = L.G + m * gstride;
+                    Gm[idx] = g0; Gm[ld + idx] = g1;
+                    const double k0 = a0 * s_Sinv[0] + a1 * s_Sinv[2];
+                    const double k1 = a0 * s_Sinv[1] + a1 * s_Sinv[3];
+                    *reinterpret_cast<double2*>(L.U + m * ustride + 2 * (size_t)idx) = make_double2(-k0, -k1);
+                    double xv = __ldcg(L.xp + idx) + (k0 * s_sc[10] + k1 * s_sc[11]);   // :138
+                    if (idx == 2) xv = remainder(xv, TWO_PI_REF);                       // :139
+                    L.xp[idx] = xv;
+                }
+                __syncthreads();
             }
             m += 1;
         } else if (kind == 2) {
@@ -268,7 +299,7 @@ __global__ void __launch_bounds__(LM_THREADS) lm_front(LargeState L, FilterConst
                 L.xp[nn + 1] = __ldcg(L.xp + 1) + rr_ * sb;    // :148
                 L.ids[M] = fc.id_known ? (int)meas[3 * l] : M; // :84,150
             }
-            if (idx < nn) {
+            for (int idx = blockIdx.x * LM_THREADS + tid; idx < nn; idx += gridDim.x * LM_THREADS) {
                 double pr[3], pc[3];                           // P_m rows 0..2 at column idx / columns 0..2 at row idx
 #pragma unroll
                 for (int k = 0; k < 3; ++k) { pr[k] = __ldcg(L.P + (size_t)k * ld + idx); pc[k] = __ldcg(L.P + (size_t)idx * ld + k); }
@@ -412,7 +443,8 @@ cudaError_t launch_ekf_large_step(const LargeState& L, const FilterConst& fc, co
     lm_predict_cols<<<gb, tb, 0, st>>>(L, fc, d_fwd);
     *launches += 2;
     if (kcap > 0) {
-        const int gm = (n_upper + LM_THREADS - 1) / LM_THREADS;     // <= 148 co-resident CTAs for n <= 18944
+        int gm = (n_upper + LM_SPAN - 1) / LM_SPAN;                // one CTA per 32 state indices, all co-resident
+        if (gm > 148) gm = 148;
         LargeState Lc = L; FilterConst fcc = fc; const float* mp = d_meas; int nm = kcap;
         void* args[] = {&Lc, &fcc, &mp, &nm};
         e = cudaLaunchCooperativeKernel((const void*)lm_front, dim3(gm), dim3(LM_THREADS), args, 0, st);
