@@ -40,7 +40,11 @@ struct slam_filter {
     int hint_base = 0;                // max(M) known on the host at step_seq == 0
     int cap_headroom = 4;             // landmarks of slack on top of the stale max(M)
     int cap_force = 0;                // > 0: force this capacity for the first pass (tests of the retry path)
-    bool profiling = false;
+    int force_threads = 0;            // > 0: CTA width of the EKF kernels (tuning)
+    int sweep_off = 0;                // 1: slam_run* always uses per-step launches (tests compare both paths)
+    int* d_work = nullptr;            // work counter of the persistent sweep kernel
+    bool profiling = false;           // per-launch events around the per-step filter kernel
+    bool profiling_sweep = false;     // events around the persistent sweep kernel
     std::vector<cudaEvent_t> ev;      // pairs
     size_t ev_used = 0;
     std::string err;
@@ -134,6 +138,7 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
     CK(cudaMalloc(&b.retry_list, sizeof(int) * batch));
     CK(cudaMalloc(&b.retry_count, sizeof(int)));
     CK(cudaMalloc(&b.max_M, sizeof(int)));
+    CK(cudaMalloc(&h->d_work, sizeof(int)));
     CK(cudaMemset(b.retry_count, 0, sizeof(int)));
     CK(cudaMemset(b.max_M, 0, sizeof(int)));
     CK(cudaMallocHost(&h->h_hint, sizeof(int) * slam_filter::HINT_RING));
@@ -173,7 +178,7 @@ int slam_destroy(slam_handle_t h) {
     BatchState& b = h->b;
     cudaFree(b.P); cudaFree(b.x); cudaFree(b.ids); cudaFree(b.meta);
     cudaFree(b.assoc); cudaFree(b.stats); cudaFree(b.sigma);
-    cudaFree(b.retry_list); cudaFree(b.retry_count); cudaFree(b.max_M);
+    cudaFree(b.retry_list); cudaFree(b.retry_count); cudaFree(b.max_M); cudaFree(h->d_work);
     if (h->large) { cudaFree(h->lg.xp); cudaFree(h->lg.U); cudaFree(h->lg.G); cudaFree(h->lg.ctl); cudaFree(h->lg.cur); cudaFree(h->lg.sc); }
     if (h->h_nmeas_pin) cudaFreeHost(h->h_nmeas_pin);
     if (h->h_hint) cudaFreeHost(h->h_hint);
@@ -196,6 +201,11 @@ int slam_tune(slam_handle_t h, int key, int value) {
     if (!h) return 1;
     if (key == 0) h->cap_force = value;
     else if (key == 1) h->cap_headroom = value;
+    else if (key == 2) {
+        if (value != 0 && value != 32 && value != 64 && value != 128 && value != 256 && value != 512)
+            return fail(h, "slam_tune: CTA width must be 0 (automatic), 32, 64, 128, 256 or 512");
+        h->force_threads = value;
+    } else if (key == 3) h->sweep_off = value;
     else return fail(h, "slam_tune: unknown key");
     return 0;
 }
@@ -280,7 +290,7 @@ static int do_step(slam_filter* h, const float* d_fwd, const float* d_ang, int c
         CK(cudaEventSynchronize(h->hint_ev[slot]));
         cap = h->h_hint[slot] + h->cap_headroom;
     } else cap = h->hint_base + (int)(h->step_seq + 1) * h->b.max_meas;      // M can grow by at most max_meas per step
-    if (h->kind == SLAM_EKF_SLAM) CK(launch_ekf_step(h->b, h->fc, in, phases, cap, h->stream));
+    if (h->kind == SLAM_EKF_SLAM) CK(launch_ekf_step(h->b, h->fc, in, phases, cap, h->force_threads, h->stream));
     else CK(launch_ukf_step(h->b, h->fc, in, h->stream));
     if (h->profiling) { CK(cudaEventRecord(h->ev[h->ev_used + 1], h->stream)); h->ev_used += 2; }
     {
@@ -540,6 +550,42 @@ int slam_sim_get_meas(slam_sim_t s, float* meas, int* n_meas) {
 }
 
 // ------------------------------------------------------------------------------------------ sweep + stats
+}  // extern "C"
+
+// T fused steps.  Known-ID EKF batches run the whole sweep in ONE persistent launch with the filters resident in
+// shared memory (ekf_sweep_kernel); everything else loops over per-step launches.
+static int run_steps(slam_filter* h, slam_sim* s, const float* d_fwd, const float* d_ang, int cmd_stride, int T, uint32_t first_step) {
+    const size_t per = cmd_stride ? (size_t)h->b.batch : 1;
+    const bool sweep = h->kind == SLAM_EKF_SLAM && !h->large && h->fc.id_known && !h->sweep_off && !h->profiling && T > 0;
+    if (sweep) {
+        if (h->profiling_sweep) {
+            if (h->ev_used + 2 > h->ev.size()) {
+                const size_t old = h->ev.size();
+                h->ev.resize(old + 64);
+                for (size_t i = old; i < h->ev.size(); ++i) CK(cudaEventCreate(&h->ev[i]));
+            }
+            CK(cudaEventRecord(h->ev[h->ev_used], h->stream));
+        }
+        CK(launch_ekf_sweep(h->b, h->fc, s->s, h->sc, d_fwd, d_ang, cmd_stride, T, first_step, h->d_work,
+                            h->force_threads, h->stream));
+        if (h->profiling_sweep) { CK(cudaEventRecord(h->ev[h->ev_used + 1], h->stream)); h->ev_used += 2; }
+        h->launches += 1;
+        // the per-step capacity hint is stale now: size the next per-step launches conservatively
+        h->step_seq = 0; h->hint_base = h->b.max_lm;
+        return 0;
+    }
+    for (int t = 0; t < T; ++t) {
+        const float* f = d_fwd + per * (size_t)t;
+        const float* a = d_ang + per * (size_t)t;
+        CK(launch_sim_step(s->s, h->sc, f, a, cmd_stride, first_step + (uint32_t)t, h->stream));
+        if (do_step(h, f, a, cmd_stride, s->s.meas, s->s.n_meas, STEP_PREDICT | STEP_UPDATE)) return 1;
+        CK(launch_accumulate_error(h->b, s->s, h->stream));
+        h->launches += 2;
+    }
+    return 0;
+}
+
+extern "C" {
 int slam_run(slam_handle_t h, slam_sim_t s, const float* cmd_fwd, const float* cmd_ang, int cmd_stride, int T, uint32_t first_step) {
     if (!h || !s || s->owner != h) return fail(h, "slam_run: simulator is not bound to this handle");
     if (!cmd_fwd || !cmd_ang || T < 0) return fail(h, "slam_run: bad argument");
@@ -555,31 +601,14 @@ int slam_run(slam_handle_t h, slam_sim_t s, const float* cmd_fwd, const float* c
     }
     CK(cudaMemcpyAsync(h->d_traj_fwd, cmd_fwd, sizeof(float) * need, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_traj_ang, cmd_ang, sizeof(float) * need, cudaMemcpyHostToDevice, h->stream));
-    for (int t = 0; t < T; ++t) {
-        const float* f = h->d_traj_fwd + per * (size_t)t;
-        const float* a = h->d_traj_ang + per * (size_t)t;
-        CK(launch_sim_step(s->s, h->sc, f, a, cmd_stride, first_step + (uint32_t)t, h->stream));
-        if (do_step(h, f, a, cmd_stride, s->s.meas, s->s.n_meas, STEP_PREDICT | STEP_UPDATE)) return 1;
-        CK(launch_accumulate_error(h->b, s->s, h->stream));
-        h->launches += 2;
-    }
-    return 0;
+    return run_steps(h, s, h->d_traj_fwd, h->d_traj_ang, cmd_stride, T, first_step);
 }
 
 int slam_run_device(slam_handle_t h, slam_sim_t s, const float* d_cmd_fwd, const float* d_cmd_ang, int cmd_stride, int T, uint32_t first_step) {
     if (!h || !s || s->owner != h) return fail(h, "slam_run_device: simulator is not bound to this handle");
     if (!d_cmd_fwd || !d_cmd_ang || T < 0) return fail(h, "slam_run_device: bad argument");
     CK(cudaSetDevice(h->device));
-    const size_t per = cmd_stride ? (size_t)h->b.batch : 1;
-    for (int t = 0; t < T; ++t) {
-        const float* f = d_cmd_fwd + per * (size_t)t;
-        const float* a = d_cmd_ang + per * (size_t)t;
-        CK(launch_sim_step(s->s, h->sc, f, a, cmd_stride, first_step + (uint32_t)t, h->stream));
-        if (do_step(h, f, a, cmd_stride, s->s.meas, s->s.n_meas, STEP_PREDICT | STEP_UPDATE)) return 1;
-        CK(launch_accumulate_error(h->b, s->s, h->stream));
-        h->launches += 2;
-    }
-    return 0;
+    return run_steps(h, s, d_cmd_fwd, d_cmd_ang, cmd_stride, T, first_step);
 }
 
 int slam_reset(slam_handle_t h, float x_0, float y_0, float yaw_0) {
@@ -606,7 +635,8 @@ int slam_step_io(slam_handle_t h, const float* fwd, const float* ang, int cmd_st
 
 int slam_set_profiling(slam_handle_t h, int on) {
     if (!h) return 1;
-    h->profiling = on != 0;
+    h->profiling = on == 1;           // 1: per-step kernel (forces the per-step path), 2: sweep kernel
+    h->profiling_sweep = on == 2;
     h->ev_used = 0;
     return 0;
 }

@@ -94,6 +94,10 @@ __host__ __device__ inline double uniform53(uint32_t hi, uint32_t lo) {
 __device__ __forceinline__ float cos_f(float x) { return (float)cos((double)x); }
 __device__ __forceinline__ float sin_f(float x) { return (float)sin((double)x); }
 
+// remainder(a, 2*pi) (filter.h:42 pi): for |a| <= pi the IEEE result is a itself (n = 0, ties to even), which is the
+// common case on this path; the library routine handles the rest.  Exact in both branches.
+__device__ __forceinline__ double wrap_2pi(double a) { return (fabs(a) <= PI_REF) ? a : remainder(a, TWO_PI_REF); }
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier + 1-D bulk async copy (TMA without a tensor map: cp.async.bulk, SASS UBLKCP)
 // ---------------------------------------------------------------------------------------------
@@ -143,7 +147,8 @@ struct StepInputs {
 
 enum { STEP_PREDICT = 1, STEP_UPDATE = 2 };
 
-cudaError_t launch_ekf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, int phases, int cap_hint, cudaStream_t st);
+cudaError_t launch_ekf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, int phases, int cap_hint,
+                            int force_threads, cudaStream_t st);
 size_t ekf_step_smem_bytes(const BatchState& b);
 cudaError_t ekf_step_configure(const BatchState& b);
 
@@ -182,6 +187,9 @@ struct SimState {
     uint32_t instance_offset;
     uint32_t k0, k1;
 };
+cudaError_t launch_ekf_sweep(const BatchState& b, const FilterConst& fc, const SimState& sim, const SimConst& sc,
+                             const float* d_fwd, const float* d_ang, int cmd_stride, int T, uint32_t first_step,
+                             int* work_counter, int force_threads, cudaStream_t st);
 cudaError_t launch_sim_step(const SimState& s, const SimConst& sc, const float* d_fwd, const float* d_ang,
                             int cmd_stride, uint32_t step, cudaStream_t st);
 cudaError_t launch_accumulate_error(const BatchState& b, const SimState& s, cudaStream_t st);

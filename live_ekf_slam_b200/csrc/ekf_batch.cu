@@ -1,15 +1,26 @@
-// ekf_batch.cu -- batched EKF-SLAM step for sm_100a: one CTA per filter instance, the covariance staged
-// in shared memory by 1-D bulk async copies (cp.async.bulk / mbarrier), one HBM round trip per step.
+// ekf_batch.cu -- batched EKF-SLAM for sm_100a: one CTA per filter instance, the covariance staged in shared memory
+// by 1-D bulk async copies (cp.async.bulk / mbarrier).  Two kernels share one core:
+//   ekf_step_kernel   one reference EKF::update per launch: P crosses HBM once each way per step (HBM bound);
+//   ekf_sweep_kernel  a whole Monte-Carlo sweep (simulator -> filter -> error terms, T steps) per launch with P
+//                     RESIDENT in shared memory for all T steps: HBM sees P once per sweep.
 //
-// Restates EKF::update, ekf_ws/src/localization_pkg/src/ekf.cpp:37-179, with the reference's
-// float/double roundings and evaluates its dense products structurally:
+// Restates EKF::update, ekf_ws/src/localization_pkg/src/ekf.cpp:37-179, with the reference's float/double roundings
+//  and evaluates its dense products structurally:
 //   :61   F_x P F_x^T + F_v V F_v^T   -> rows/cols 0..1 pick up row/col 2, + 3x3 block      O(n)
-//   :133  H P H^T + W                 -> 5 rows of P                                        O(n)
+//   :133  H P H^T + W                 -> the 5x5 sub-block of P that H touches              O(1)
 //   :135  P H^T S^-1                  -> 5 columns of P                                     O(n)
 //   :140  P - (K H) P                 -> rank-2 update P -= K (H P)                         O(n^2)
 //   :172  Y blkdiag(P,W) Y^T          -> two new rows/cols                                  O(n)
-// so a step moves 16 n^2 bytes through HBM and is bandwidth bound.
-#include "common.cuh"
+//
+// Thread organisation (THREADS = 32 * WARPS, WARPS in {1,2,4,8,16}, chosen per launch from the tile size so that
+// about 32 warps are resident per SM whatever n is).  Scalar chains (sincos, sqrt, atan2, divisions) are the
+// latency- and issue-critical part at small n, so:
+//   * the last warp is the "scalar warp": its lane 0 evaluates the predict trigonometry and the innovation
+//     (atan2 / remainder) while the other warps do O(n) work; it joins the O(n^2) sweep;
+//   * the four distinct quotients of H are computed once per warp, lane-parallel, and shuffled;
+//   * S and S^-1 come from the 5x5 sub-block directly, so a landmark update costs two CTA barriers;
+//   * known-ID association (integer compares on lm_IDs) is resolved for the whole message before P is touched.
+#include "sim_device.cuh"
 
 #include <climits>
 
@@ -28,21 +39,20 @@ struct EkfLaunch {
 };
 
 struct EkfSmem {
-    double* P;      // n_max x lds
+    double* P;      // n_cap x lds
     double* x;      // running x_pred
     double* xs;     // x_t at step start (stale landmark means, ekf.cpp:115)
     double* HP;     // 2 x lds   (H_x * P_pred)
-    double* PH;     // n_max x 2 (P_pred * H_x^T)
-    double* K;      // n_max x 2
+    double* K;      // n_cap x 2
     double* sc;     // scalars
     int* ids;
     float* meas;
     int* assoc;
-    int* iscr;      // [0..1] match slots, [2] nan flag
+    int* iscr;      // [0] dead flag of the association pre-pass, [1] nan flag, [2] n_meas (sweep), [3] work item (sweep)
     uint64_t* bar;
 };
 
-__host__ __device__ inline size_t ekf_smem_carve(const BatchState& b, const EkfLaunch& L, unsigned char* base, EkfSmem* s) {
+__host__ __device__ inline size_t ekf_smem_carve(const int max_meas, const EkfLaunch& L, unsigned char* base, EkfSmem* s) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
     const int nmp = ldg_of(L.n_cap);
@@ -50,17 +60,16 @@ __host__ __device__ inline size_t ekf_smem_carve(const BatchState& b, const EkfL
     size_t ox = take(sizeof(double) * nmp);
     size_t oxs = take(sizeof(double) * nmp);
     size_t oHP = take(sizeof(double) * 2 * L.lds);
-    size_t oPH = take(sizeof(double) * 2 * nmp);
     size_t oK = take(sizeof(double) * 2 * nmp);
-    size_t osc = take(sizeof(double) * 32);
+    size_t osc = take(sizeof(double) * 24);
     size_t oids = take(sizeof(int) * (L.cap_lm + 1));
-    size_t omeas = take(sizeof(float) * 3 * b.max_meas);
-    size_t oassoc = take(sizeof(int) * b.max_meas);
+    size_t omeas = take(sizeof(float) * 3 * max_meas);
+    size_t oassoc = take(sizeof(int) * max_meas);
     size_t oi = take(sizeof(int) * 8);
     size_t obar = take(sizeof(uint64_t));
     if (s) {
         s->P = (double*)(base + oP); s->x = (double*)(base + ox); s->xs = (double*)(base + oxs);
-        s->HP = (double*)(base + oHP); s->PH = (double*)(base + oPH); s->K = (double*)(base + oK);
+        s->HP = (double*)(base + oHP); s->K = (double*)(base + oK);
         s->sc = (double*)(base + osc); s->ids = (int*)(base + oids); s->meas = (float*)(base + omeas);
         s->assoc = (int*)(base + oassoc); s->iscr = (int*)(base + oi); s->bar = (uint64_t*)(base + obar);
     }
@@ -68,187 +77,195 @@ __host__ __device__ inline size_t ekf_smem_carve(const BatchState& b, const EkfL
 }
 
 // scalar slots in sc[]
-enum { SC_H = 0 /*10*/, SC_NU = 10 /*2*/, SC_XD = 12, SC_YD = 13, SC_CB = 14, SC_SB = 15 };
+enum { SC_FA = 0, SC_FB, SC_C, SC_S, SC_NX0, SC_NX1, SC_NX2, SC_NU0, SC_NU1, SC_XD, SC_YD, SC_CB, SC_SB,
+       SC_TR = 16 /* sweep: truth of step parity 0 at [16..18], parity 1 at [19..21] */ };
+enum { IS_DEAD = 0, IS_NAN = 1, IS_NM = 2, IS_WORK = 3 };
+enum { ASSOC_NEW = -1, ASSOC_DROPPED = -2 };   // internal codes of the pre-pass; both read back as -1 (new landmark)
 
-// One reference EKF::update for instance `inst`.  Returns true when the mbarrier phase `parity` was consumed.
 template <int THREADS>
-__device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterConst& fc, const StepInputs& in,
-                                             const int phases, const EkfLaunch& L, const EkfSmem& s, const int inst,
-                                             const uint32_t parity) {
-    constexpr int WARPS = THREADS / 32;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int lds = L.lds;
+__device__ __forceinline__ void cta_sync() {
+    if constexpr (THREADS == 32) __syncwarp(); else __syncthreads();
+}
 
-    const int4 meta_in = b.meta[inst];
-    int nm = 0;
-    if (phases & STEP_UPDATE) nm = in.n_meas[inst];
-    const int status_in = meta_in.y;
-    if (status_in & SLAM_STATUS_SAME_STEP_REMATCH) return false;   // the reference process is dead past this point
-    int M = meta_in.x;
+// ---- predict scalars (ekf.cpp:43-59), one thread: F_x(0,2), F_x(1,2), cos, sin and the new vehicle pose
+__device__ __forceinline__ void ekf_predict_scalars(const FilterConst& fc, const EkfSmem& s, const float d_d, const float d_th) {
+    double sn, c;
+    const double th = s.x[2];
+    sincos(th, &sn, &c);
+    s.sc[SC_FA] = (double)(-1 * d_d) * sn;        // F_x(0,2), :48
+    s.sc[SC_FB] = (double)d_d * c;                // F_x(1,2), :49
+    s.sc[SC_C] = c; s.sc[SC_S] = sn;
+    const float dv = d_d + fc.v_d;                // float add, :57-58
+    s.sc[SC_NX0] = s.x[0] + (double)dv * c;
+    s.sc[SC_NX1] = s.x[1] + (double)dv * sn;
+    s.sc[SC_NX2] = wrap_2pi(th + (double)d_th + (double)fc.v_th);   // :59
+}
+
+// ---- known-ID association for the whole message (ekf.cpp:99-109), one warp, before anything is modified.
+// s.assoc[l] <- slot in the committed lm_IDs, ASSOC_NEW (will be inserted) or ASSOC_DROPPED (capacity reached).
+// A measurement that repeats the id of a landmark inserted earlier in the same step would make the reference index
+// x_t out of range (:115): flagged dead (SLAM_STATUS_SAME_STEP_REMATCH), nothing of the step is applied.
+__device__ __forceinline__ void ekf_assoc_prepass(const EkfSmem& s, const int lane, const int M, const int nm, const int max_lm) {
+    int M_run = M;
+    bool dead = false;
+    for (int l = 0; l < nm; ++l) {
+        const int id = (int)s.meas[3 * l];                                 // :101
+        int cand = INT_MAX;
+        for (int j = lane; j < M; j += 32)
+            if (s.ids[j] == id) { cand = j; break; }
+        cand = __reduce_min_sync(0xffffffffu, cand);                       // first match in ascending slot order
+        int code = cand;
+        if (cand == INT_MAX) {
+            bool dup = false;
+            for (int q = lane; q < l; q += 32) dup |= (s.assoc[q] == ASSOC_NEW) && ((int)s.meas[3 * q] == id);
+            if (__any_sync(0xffffffffu, dup)) { dead = true; break; }
+            if (M_run < max_lm) { code = ASSOC_NEW; ++M_run; } else code = ASSOC_DROPPED;
+        }
+        if (lane == 0) s.assoc[l] = code;
+        __syncwarp();
+    }
+    if (lane == 0) s.iscr[IS_DEAD] = dead ? 1 : 0;
+}
+
+// ---- one reference EKF::update on the shared-memory-resident filter.
+// On entry (all visible to the CTA): s.P / s.x / s.xs (= s.x) / s.ids hold the committed filter with M landmarks,
+// s.meas the message, s.sc the predict scalars, and -- known-ID mode -- s.assoc / s.iscr[IS_DEAD] the pre-pass.
+// Returns true when the step was applied; false when the instance died (same-step re-match).  `intact` then tells
+// whether the shared-memory state is still the committed one (always in known-ID mode).
+template <int THREADS>
+__device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s, const int lds, const int max_lm,
+                                         const int phases, int& M, const int nm, int& status, int& n_upd, bool& intact) {
+    constexpr int WARPS = THREADS / 32;
+    constexpr int SW = WARPS - 1;                               // the scalar warp
+    constexpr int ABT = (WARPS > 1) ? THREADS - 32 : 32;        // threads doing the O(n) phase of an update
+    constexpr int UNR = (THREADS >= 512) ? 2 : 4;               // rows in flight in the rank-2 sweep
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool scalar_thread = (warp == SW) && (lane == 0);
+    const bool ab_worker = (WARPS == 1) || (warp != SW);
     const int M_start = M;
     int n = 3 + 2 * M;
-    int status = status_in;
-    if (nm > b.max_meas) { nm = b.max_meas; status |= SLAM_STATUS_MEAS_OVERFLOW; }
-    if (M + nm > L.cap_lm && L.cap_lm < b.max_lm) {
-        // this launch's tile may be too small for the insertions of this step: defer, untouched
-        if (tid == 0) b.retry_list[atomicAdd(b.retry_count, 1)] = inst;
-        return false;
-    }
-    double* gP = b.P + (size_t)inst * b.p_stride;
-    double* gx = b.x + (size_t)inst * b.x_stride;
+    intact = true;
+    n_upd = 0;
 
-    // ---- stage P: one bulk copy per live row, all completing on one mbarrier
-    if (tid == 0) { s.iscr[0] = INT_MAX; s.iscr[1] = INT_MAX; s.iscr[2] = 0; }
-    {
-        const int ldg = ldg_of(n);
-        if (warp == 0) {
-            if (lane == 0) mbar_expect_tx(s.bar, (uint32_t)(n * ldg * sizeof(double)));
-            __syncwarp();
-            for (int row = lane; row < n; row += 32)
-                bulk_g2s(s.P + (size_t)row * lds, gP + (size_t)row * ldg, (uint32_t)(ldg * sizeof(double)), s.bar);
-        }
-    }
-    // ---- meanwhile: state, ids, messages
-    for (int i = tid; i < n; i += THREADS) { const double v = gx[i]; s.x[i] = v; s.xs[i] = v; }
-    for (int i = tid; i < M; i += THREADS) s.ids[i] = b.ids[(size_t)inst * b.max_lm + i];
-    for (int i = tid; i < 3 * nm; i += THREADS) s.meas[i] = in.meas[(size_t)inst * b.max_meas * 3 + i];
-    __syncthreads();
+    if ((phases & STEP_UPDATE) && fc.id_known && s.iscr[IS_DEAD]) { status |= SLAM_STATUS_SAME_STEP_REMATCH; return false; }
 
-    // ---- PREDICT, ekf.cpp:43-61
-    double fa = 0.0, fb = 0.0, c = 1.0, sn = 0.0;
+    // ---- PREDICT, ekf.cpp:43-61.  T = F_x P (rows 0,1 pick up row 2), P' = T F_x^T (cols 0,1 pick up col 2)
+    //      + (F_v V) F_v^T on the vehicle block.  For j >= 3 the row and column parts touch disjoint entries, so one
+    //      pass does both; the 3x3 vehicle block is done by one thread in the reference's order.
     if (phases & STEP_PREDICT) {
-        const float d_d = in.fwd[in.cmd_stride ? inst : 0];
-        const float d_th = in.ang[in.cmd_stride ? inst : 0];
-        const double th = s.xs[2];
-        sincos(th, &sn, &c);
-        fa = (double)(-1 * d_d) * sn;            // F_x(0,2), :48
-        fb = (double)d_d * c;                    // F_x(1,2), :49
-        if (tid == 0) {
-            const float dv = d_d + fc.v_d;       // float add, :57-58
-            s.x[0] = s.xs[0] + (double)dv * c;
-            s.x[1] = s.xs[1] + (double)dv * sn;
-            s.x[2] = remainder(s.xs[2] + (double)d_th + (double)fc.v_th, TWO_PI_REF);   // :59
-        }
-    }
-    mbar_wait(s.bar, parity);
-    if (phases & STEP_PREDICT) {
-        // T = F_x P : rows 0,1 pick up row 2
+        const double fa = s.sc[SC_FA], fb = s.sc[SC_FB];
         for (int j = tid; j < n; j += THREADS) {
-            const double p2 = s.P[2 * lds + j];
-            s.P[j] = s.P[j] + fa * p2;
-            s.P[lds + j] = s.P[lds + j] + fb * p2;
+            if (j >= 3) {
+                const double p2 = s.P[2 * lds + j];
+                s.P[j] = s.P[j] + fa * p2;
+                s.P[lds + j] = s.P[lds + j] + fb * p2;
+                double* row = s.P + (size_t)j * lds;
+                const double t2 = row[2];
+                row[0] = row[0] + t2 * fa;
+                row[1] = row[1] + t2 * fb;
+            } else if (j == 0) {
+                const double c = s.sc[SC_C], sn = s.sc[SC_S];
+                double T[3][3];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const double p2 = s.P[2 * lds + q];
+                    T[0][q] = s.P[q] + fa * p2;
+                    T[1][q] = s.P[lds + q] + fb * p2;
+                    T[2][q] = p2;
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const double t2 = T[i][2];
+                    double p0 = T[i][0] + t2 * fa;
+                    double p1 = T[i][1] + t2 * fb;
+                    if (i == 0) { const double cV = c * fc.V00; p0 += cV * c; p1 += cV * sn; }
+                    if (i == 1) { const double sV = sn * fc.V00; p0 += sV * c; p1 += sV * sn; }
+                    s.P[i * lds + 0] = p0;
+                    s.P[i * lds + 1] = p1;
+                    s.P[i * lds + 2] = (i == 2) ? t2 + fc.V11 : t2;
+                }
+                s.x[0] = s.sc[SC_NX0]; s.x[1] = s.sc[SC_NX1]; s.x[2] = s.sc[SC_NX2];
+            }
         }
-        __syncthreads();
-        // P' = T F_x^T : cols 0,1 pick up col 2 ; + (F_v V) F_v^T on the vehicle block
-        for (int i = tid; i < n; i += THREADS) {
-            const double t2 = s.P[i * lds + 2];
-            double p0 = s.P[i * lds + 0] + t2 * fa;
-            double p1 = s.P[i * lds + 1] + t2 * fb;
-            if (i == 0) { const double cV = c * fc.V00; p0 += cV * c; p1 += cV * sn; }
-            if (i == 1) { const double sV = sn * fc.V00; p0 += sV * c; p1 += sV * sn; }
-            s.P[i * lds + 0] = p0;
-            s.P[i * lds + 1] = p1;
-            if (i == 2) s.P[2 * lds + 2] = t2 + fc.V11;
-        }
+        intact = false;
+        cta_sync<THREADS>();
     }
-    __syncthreads();
 
     // ---- UPDATE, ekf.cpp:63-174
-    bool dead = false;
-    int n_upd = 0;
     for (int l = 0; l < nm; ++l) {
         const float r = s.meas[3 * l + 1], bb = s.meas[3 * l + 2];
-        int* match = &s.iscr[l & 1];
-        int id;
-        // -- association, :79-109
-        int cand = INT_MAX;
-        if (!fc.id_known) {
+        int slot, id;
+        if (fc.id_known) {
+            slot = s.assoc[l];
+            id = (int)s.meas[3 * l];
+            if (slot == ASSOC_DROPPED) { status |= SLAM_STATUS_CAPACITY; continue; }
+        } else {
+            // -- unknown IDs, :82-98: first landmark inside the float box gate around the detection
             id = M;
-            if (tid == 0) {
+            if (scalar_thread) {
                 double sa, ca; sincos(s.x[2] + (double)bb, &sa, &ca);
-                s.sc[SC_XD] = (double)(float)(s.x[0] + (double)r * ca);   // float x_detected, :87
-                s.sc[SC_YD] = (double)(float)(s.x[1] + (double)r * sa);   // float y_detected, :88
+                s.sc[SC_XD] = (double)(float)(s.x[0] + (double)r * ca);    // float x_detected, :87
+                s.sc[SC_YD] = (double)(float)(s.x[1] + (double)r * sa);    // float y_detected, :88
+                s.sc[SC_CB] = ca; s.sc[SC_SB] = sa;                        // reused by the insertion below
             }
-            __syncthreads();
+            cta_sync<THREADS>();
             const double xd = s.sc[SC_XD], yd = s.sc[SC_YD];
-            for (int j = tid; j < M; j += THREADS) {
+            int cand = INT_MAX;
+            for (int j = lane; j < M; j += 32) {                           // every warp scans the whole map: no barrier
                 const float x_diff = (float)fabs(xd - s.x[3 + 2 * j]);     // :91
                 const float y_diff = (float)fabs(yd - s.x[4 + 2 * j]);     // :92
-                if (x_diff < fc.min_sep && y_diff < fc.min_sep) { cand = j; break; }   // first match per thread
+                if (x_diff < fc.min_sep && y_diff < fc.min_sep) { cand = j; break; }
             }
-        } else {
-            id = (int)s.meas[3 * l];                                       // :101
-            for (int j = tid; j < M; j += THREADS)
-                if (s.ids[j] == id) { cand = j; break; }
+            cand = __reduce_min_sync(0xffffffffu, cand);                   // first j in ascending order, :93-97
+            slot = (cand == INT_MAX) ? ASSOC_NEW : cand;
+            if (slot != ASSOC_NEW) id = slot;
+            if (slot == ASSOC_NEW && M >= max_lm) {
+                status |= SLAM_STATUS_CAPACITY;
+                if (tid == 0) s.assoc[l] = ASSOC_NEW;
+                cta_sync<THREADS>();      // sc[] is rewritten by the next measurement
+                continue;
+            }
+            if (tid == 0) s.assoc[l] = slot;
+            if (slot >= M_start) { status |= SLAM_STATUS_SAME_STEP_REMATCH; return false; }   // :115 reads x_t out of range
         }
-        cand = __reduce_min_sync(0xffffffffu, cand);
-        if (lane == 0 && cand != INT_MAX) atomicMin(match, cand);
-        __syncthreads();
-        const int slot = *match;                                           // first j in ascending order, :93-97
-        if (tid == 0) { s.iscr[(l + 1) & 1] = INT_MAX; s.assoc[l] = (slot == INT_MAX) ? -1 : slot; }
-        if (!fc.id_known && slot != INT_MAX) id = slot;
 
-        if (slot != INT_MAX) {
+        if (slot >= 0) {
             // -------- landmark update, :110-140
-            if (slot >= M_start) { status |= SLAM_STATUS_SAME_STEP_REMATCH; dead = true; break; }
             const int i = slot * 2 + 3;
             ++n_upd;
-            if (tid == 0) {
-                const double dx = s.xs[i] - s.x[0], dy = s.xs[i + 1] - s.x[1];
-                const float dist = (float)sqrt(dx * dx + dy * dy);         // :115
+            // landmark from the stale x_t, vehicle from the running x_pred (:115)
+            const double dx = s.xs[i] - s.x[0], dy = s.xs[i + 1] - s.x[1];
+            const float dist = (float)sqrt(dx * dx + dy * dy);             // :115
+            if (scalar_thread) {
+                const float ang = (float)wrap_2pi(atan2(dy, dx) - s.x[2]); // :129
+                s.sc[SC_NU0] = (double)(r - dist - fc.w_r);                // all-float arithmetic, :130
+                s.sc[SC_NU1] = (double)(bb - ang - fc.w_b);                // :131
+            }
+            if (ab_worker) {
+                // the four distinct quotients of H_x (:118-126), one per lane, shuffled to the warp
                 const double dd = (double)dist;
                 const double d2 = (double)(dist * dist);                   // float product, :120
-                double* H = s.sc + SC_H;
-                H[0] = -(dx) / dd; H[1] = -(dy) / dd; H[2] = 0.0; H[3] = dx / dd; H[4] = dy / dd;
-                H[5] = dy / d2; H[6] = -(dx) / d2; H[7] = -1.0; H[8] = -(dy) / d2; H[9] = dx / d2;
-                // innovation is all-float arithmetic, :129-131 (evaluated on the second warp below)
-            }
-            if (tid == 32) {
-                const double dx = s.xs[i] - s.x[0], dy = s.xs[i + 1] - s.x[1];
-                const float dist = (float)sqrt(dx * dx + dy * dy);
-                const float ang = (float)remainder(atan2(dy, dx) - s.x[2], TWO_PI_REF);   // :129
-                s.sc[SC_NU] = (double)(r - dist - fc.w_r);                 // :130
-                s.sc[SC_NU + 1] = (double)(bb - ang - fc.w_b);             // :131
-            }
-            __syncthreads();
-            double H[10];
+                const int ql = lane & 3;
+                const double qv = ((ql == 0 || ql == 3) ? dx : dy) / ((ql < 2) ? dd : d2);
+                const double q0 = __shfl_sync(0xffffffffu, qv, 0);         // dx / dist
+                const double q1 = __shfl_sync(0xffffffffu, qv, 1);         // dy / dist
+                const double q2 = __shfl_sync(0xffffffffu, qv, 2);         // dy / dist^2
+                const double q3 = __shfl_sync(0xffffffffu, qv, 3);         // dx / dist^2
+                const double H[10] = {-q0, -q1, 0.0, q0, q1, q2, -q3, -1.0, -q2, q3};
+                const int hc[5] = {0, 1, 2, i, i + 1};
+                // S = H P H^T + W (:133) from the 5x5 sub-block, S^-1 by partial-pivot LU like Eigen's dynamic
+                // inverse() (:135); evaluated by every worker thread (broadcast reads, no barrier)
+                double S00 = 0, S01 = 0, S10 = 0, S11 = 0;
 #pragma unroll
-            for (int q = 0; q < 10; ++q) H[q] = s.sc[SC_H + q];
-            const int hc3 = i, hc4 = i + 1;
-            // -- phase A: H P (2 x n) on the low half of the CTA, P H^T (n x 2) on the high half
-            if (tid < THREADS / 2) {
-                for (int j = tid; j < ldg_of(n); j += THREADS / 2) {
-                    double h0 = 0.0, h1 = 0.0;
-                    if (j < n) {
-                        const double p0 = s.P[j], p1 = s.P[lds + j], p2 = s.P[2 * lds + j];
-                        const double p3 = s.P[hc3 * lds + j], p4 = s.P[hc4 * lds + j];
-                        h0 = H[0] * p0; h0 += H[1] * p1; h0 += H[2] * p2; h0 += H[3] * p3; h0 += H[4] * p4;
-                        h1 = H[5] * p0; h1 += H[6] * p1; h1 += H[7] * p2; h1 += H[8] * p3; h1 += H[9] * p4;
-                    }
-                    s.HP[j] = h0; s.HP[lds + j] = h1;
+                for (int c = 0; c < 5; ++c) {
+                    double p[5];
+#pragma unroll
+                    for (int a = 0; a < 5; ++a) p[a] = s.P[(size_t)hc[a] * lds + hc[c]];
+                    double g0 = H[0] * p[0]; g0 += H[1] * p[1]; g0 += H[2] * p[2]; g0 += H[3] * p[3]; g0 += H[4] * p[4];
+                    double g1 = H[5] * p[0]; g1 += H[6] * p[1]; g1 += H[7] * p[2]; g1 += H[8] * p[3]; g1 += H[9] * p[4];
+                    S00 += g0 * H[c]; S01 += g0 * H[5 + c]; S10 += g1 * H[c]; S11 += g1 * H[5 + c];
                 }
-            } else {
-                for (int q = tid - THREADS / 2; q < n; q += THREADS / 2) {
-                    const double* row = s.P + (size_t)q * lds;
-                    const double p0 = row[0], p1 = row[1], p2 = row[2], p3 = row[hc3], p4 = row[hc4];
-                    double a0 = p0 * H[0]; a0 += p1 * H[1]; a0 += p2 * H[2]; a0 += p3 * H[3]; a0 += p4 * H[4];
-                    double a1 = p0 * H[5]; a1 += p1 * H[6]; a1 += p2 * H[7]; a1 += p3 * H[8]; a1 += p4 * H[9];
-                    s.PH[2 * q] = a0; s.PH[2 * q + 1] = a1;
-                }
-            }
-            __syncthreads();
-            // -- phase B: S = (H P) H^T + W, S^-1 (partial-pivot LU like Eigen's dynamic inverse(), :133-135), K, x
-            {
-                double S00, S01, S10, S11;
-                {
-                    const double a0 = s.HP[0], a1 = s.HP[1], a2 = s.HP[2], a3 = s.HP[hc3], a4 = s.HP[hc4];
-                    const double b0 = s.HP[lds], b1 = s.HP[lds + 1], b2 = s.HP[lds + 2], b3 = s.HP[lds + hc3], b4 = s.HP[lds + hc4];
-                    S00 = a0 * H[0]; S00 += a1 * H[1]; S00 += a2 * H[2]; S00 += a3 * H[3]; S00 += a4 * H[4];
-                    S01 = a0 * H[5]; S01 += a1 * H[6]; S01 += a2 * H[7]; S01 += a3 * H[8]; S01 += a4 * H[9];
-                    S10 = b0 * H[0]; S10 += b1 * H[1]; S10 += b2 * H[2]; S10 += b3 * H[3]; S10 += b4 * H[4];
-                    S11 = b0 * H[5]; S11 += b1 * H[6]; S11 += b2 * H[7]; S11 += b3 * H[8]; S11 += b4 * H[9];
-                    S00 += fc.W00; S11 += fc.W11;
-                }
+                S00 += fc.W00; S11 += fc.W11;
                 double i00, i01, i10, i11;
                 {
                     const bool sw = fabs(S10) > fabs(S00);
@@ -260,45 +277,72 @@ __device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterCo
                     double y1 = b1c0 - l10 * b0c0; i10 = y1 / u11; i00 = (b0c0 - a01 * i10) / a00;
                     y1 = b1c1 - l10 * b0c1; i11 = y1 / u11; i01 = (b0c1 - a01 * i11) / a00;
                 }
-                const double nu0 = s.sc[SC_NU], nu1 = s.sc[SC_NU + 1];
+                // H P (2 x n, kept for the sweep) and K = P H^T S^-1 (n x 2)
+                const int ldg = ldg_of(n);
+                for (int idx = tid; idx < ldg + n; idx += ABT) {
+                    if (idx < ldg) {
+                        const int j = idx;
+                        double h0 = 0.0, h1 = 0.0;
+                        if (j < n) {
+                            const double p0 = s.P[j], p1 = s.P[lds + j], p2 = s.P[2 * lds + j];
+                            const double p3 = s.P[(size_t)i * lds + j], p4 = s.P[(size_t)(i + 1) * lds + j];
+                            h0 = H[0] * p0; h0 += H[1] * p1; h0 += H[2] * p2; h0 += H[3] * p3; h0 += H[4] * p4;
+                            h1 = H[5] * p0; h1 += H[6] * p1; h1 += H[7] * p2; h1 += H[8] * p3; h1 += H[9] * p4;
+                        }
+                        s.HP[j] = h0; s.HP[lds + j] = h1;
+                    } else {
+                        const int q = idx - ldg;
+                        const double* row = s.P + (size_t)q * lds;
+                        const double p0 = row[0], p1 = row[1], p2 = row[2], p3 = row[i], p4 = row[i + 1];
+                        double a0 = p0 * H[0]; a0 += p1 * H[1]; a0 += p2 * H[2]; a0 += p3 * H[3]; a0 += p4 * H[4];
+                        double a1 = p0 * H[5]; a1 += p1 * H[6]; a1 += p2 * H[7]; a1 += p3 * H[8]; a1 += p4 * H[9];
+                        s.K[2 * q] = a0 * i00 + a1 * i10;
+                        s.K[2 * q + 1] = a0 * i01 + a1 * i11;
+                    }
+                }
+            }
+            cta_sync<THREADS>();
+            // x_pred += K nu (:138), yaw wrapped (:139)
+            {
+                const double nu0 = s.sc[SC_NU0], nu1 = s.sc[SC_NU1];
                 for (int q = tid; q < n; q += THREADS) {
-                    const double ph0 = s.PH[2 * q], ph1 = s.PH[2 * q + 1];
-                    const double k0 = ph0 * i00 + ph1 * i10;
-                    const double k1 = ph0 * i01 + ph1 * i11;
-                    s.K[2 * q] = k0; s.K[2 * q + 1] = k1;
-                    double xv = s.x[q] + (k0 * nu0 + k1 * nu1);            // :138
-                    if (q == 2) xv = remainder(xv, TWO_PI_REF);            // :139
+                    double xv = s.x[q] + (s.K[2 * q] * nu0 + s.K[2 * q + 1] * nu1);
+                    if (q == 2) xv = wrap_2pi(xv);
                     s.x[q] = xv;
                 }
             }
-            __syncthreads();
-            // -- phase C: P -= K (H P), :140 as a rank-2 update over the packed row width
+            // P -= K (H P), :140 as a rank-2 update over the packed row width.  A lane owns one double2 column pair
+            // (its two (H P) pairs stay in registers), a warp owns RPI consecutive rows per iteration (RPI > 1 when a
+            // row is narrower than a warp), UNR row groups in flight.
             {
-                // warp w owns rows w, w+8, ...; a lane owns one double2 column pair per 32-pair chunk and keeps
-                // its two (H P) pairs in registers for the whole sweep; 4 rows in flight per iteration.
-                const int hp = ldg_of(n) >> 1;               // double2 per row
-                for (int c0 = 0; c0 < hp; c0 += 32) {
-                    const int jp = c0 + lane;
+                const int hp = ldg_of(n) >> 1;                  // double2 per row
+                int cpw = 32;                                   // lanes per row: smallest power of two >= hp, <= 32
+                while ((cpw >> 1) >= hp && cpw > 1) cpw >>= 1;
+                const int rpi = 32 / cpw;
+                const int lr = lane / cpw, lc = lane & (cpw - 1);
+                for (int c0 = 0; c0 < hp; c0 += cpw) {
+                    const int jp = c0 + lc;
                     if (jp < hp) {
                         const double2 h0 = *reinterpret_cast<const double2*>(s.HP + 2 * jp);
                         const double2 h1 = *reinterpret_cast<const double2*>(s.HP + lds + 2 * jp);
                         double* col = s.P + 2 * jp;
-                        int row = warp;
-                        for (; row + 3 * WARPS < n; row += 4 * WARPS) {
-                            double2 k[4], p[4];
+                        const int rstep = WARPS * rpi;
+                        int row = warp * rpi + lr;
+                        for (; row + (UNR - 1) * rstep < n; row += UNR * rstep) {
+                            double2 k[UNR], p[UNR];
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                k[u] = *reinterpret_cast<const double2*>(s.K + 2 * (row + u * WARPS));
-                                p[u] = *reinterpret_cast<const double2*>(col + (size_t)(row + u * WARPS) * lds);
+                            for (int u = 0; u < UNR; ++u) {
+                                k[u] = *reinterpret_cast<const double2*>(s.K + 2 * (row + u * rstep));
+                                p[u] = *reinterpret_cast<const double2*>(col + (size_t)(row + u * rstep) * lds);
                             }
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
+                            for (int u = 0; u < UNR; ++u) {
                                 p[u].x = p[u].x - (k[u].x * h0.x + k[u].y * h1.x);
                                 p[u].y = p[u].y - (k[u].x * h0.y + k[u].y * h1.y);
-                                *reinterpret_cast<double2*>(col + (size_t)(row + u * WARPS) * lds) = p[u];
+                                *reinterpret_cast<double2*>(col + (size_t)(row + u * rstep) * lds) = p[u];
                             }
                         }
-                        for (; row < n; row += WARPS) {
+                        for (; row < n; row += rstep) {
                             const double2 k = *reinterpret_cast<const double2*>(s.K + 2 * row);
                             double2 p = *reinterpret_cast<const double2*>(col + (size_t)row * lds);
                             p.x = p.x - (k.x * h0.x + k.y * h1.x);
@@ -308,15 +352,16 @@ __device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterCo
                     }
                 }
             }
-            __syncthreads();
+            cta_sync<THREADS>();
         } else {
             // -------- landmark insertion, :141-173
-            if (M >= b.max_lm) { status |= SLAM_STATUS_CAPACITY; if (tid == 0) s.assoc[l] = -1; __syncthreads(); continue; }
-            if (tid == 0) {
-                double sb, cb; sincos(s.x[2] + (double)bb, &sb, &cb);
-                s.sc[SC_CB] = cb; s.sc[SC_SB] = sb;
+            if (fc.id_known) {
+                if (scalar_thread) {
+                    double sb, cb; sincos(s.x[2] + (double)bb, &sb, &cb);
+                    s.sc[SC_CB] = cb; s.sc[SC_SB] = sb;
+                }
+                cta_sync<THREADS>();
             }
-            __syncthreads();
             const double cb = s.sc[SC_CB], sb = s.sc[SC_SB];
             const double g02 = -(double)r * sb, g12 = (double)r * cb;      // G_x(0,2), G_x(1,2), :162,165
             // rows n, n+1 over old columns; columns n, n+1 over old rows
@@ -333,7 +378,7 @@ __device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterCo
                 s.P[(size_t)j * lds + n] = c0;
                 s.P[(size_t)j * lds + n + 1] = c1;
             }
-            if (tid == 32) {
+            if (scalar_thread) {
                 // new 2x2 block: G_x P_vv G_x^T + G_z W G_z^T, :155-172
                 const double gx[2][3] = {{1.0, 0.0, g02}, {0.0, 1.0, g12}};
                 const double gz[2][2] = {{cb, -(double)r * sb}, {sb, (double)r * cb}};
@@ -357,56 +402,121 @@ __device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterCo
                 s.ids[M] = id;                                             // :150
             }
             M += 1; n += 2;
-            __syncthreads();
+            cta_sync<THREADS>();
         }
     }
+    return true;
+}
+
+// algorithmic work of one update, using the live n at the end of the step
+__device__ __forceinline__ void ekf_work_terms(const int n, const int nm, const int n_upd, double (&w)[4]) {
+    const double nd = (double)n;
+    w[0] += 16.0 * nd * nd + 16.0 * nd + 12.0 * nm + 8.0;
+    w[1] += 4.0 * (double)n_upd * nd * nd;
+    w[2] += nd;
+    w[3] += (double)nm;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// ekf_step_kernel: one reference EKF::update per instance per launch.  Returns true when the mbarrier phase
+// `parity` was consumed.
+// ------------------------------------------------------------------------------------------------------------
+template <int THREADS>
+__device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterConst& fc, const StepInputs& in,
+                                             const int phases, const EkfLaunch& L, const EkfSmem& s, const int inst,
+                                             const uint32_t parity) {
+    constexpr int WARPS = THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lds = L.lds;
+
+    const int4 meta_in = b.meta[inst];
+    int nm = (phases & STEP_UPDATE) ? in.n_meas[inst] : 0;
+    int status = meta_in.y;
+    if (status & SLAM_STATUS_SAME_STEP_REMATCH) return false;   // the reference process is dead past this point
+    int M = meta_in.x;
+    const int M_start = M;
+    const int n0 = 3 + 2 * M;
+    if (nm > b.max_meas) { nm = b.max_meas; status |= SLAM_STATUS_MEAS_OVERFLOW; }
+    if (M + nm > L.cap_lm && L.cap_lm < b.max_lm) {
+        // this launch's tile may be too small for the insertions of this step: defer, untouched
+        if (tid == 0) b.retry_list[atomicAdd(b.retry_count, 1)] = inst;
+        return false;
+    }
+    double* gP = b.P + (size_t)inst * b.p_stride;
+    double* gx = b.x + (size_t)inst * b.x_stride;
+
+    // ---- stage P: one bulk copy per live row, all completing on one mbarrier
+    {
+        const int ldg = ldg_of(n0);
+        if (warp == 0) {
+            if (lane == 0) { mbar_expect_tx(s.bar, (uint32_t)(n0 * ldg * sizeof(double))); s.iscr[IS_NAN] = 0; s.iscr[IS_DEAD] = 0; }
+            __syncwarp();
+            for (int row = lane; row < n0; row += 32)
+                bulk_g2s(s.P + (size_t)row * lds, gP + (size_t)row * ldg, (uint32_t)(ldg * sizeof(double)), s.bar);
+        }
+    }
+    // ---- meanwhile: state, ids, messages
+    for (int i = tid; i < n0; i += THREADS) { const double v = gx[i]; s.x[i] = v; s.xs[i] = v; }
+    for (int i = tid; i < M; i += THREADS) s.ids[i] = b.ids[(size_t)inst * b.max_lm + i];
+    for (int i = tid; i < 3 * nm; i += THREADS) s.meas[i] = in.meas[(size_t)inst * b.max_meas * 3 + i];
+    cta_sync<THREADS>();
+    // ---- scalar pre-work while P is in flight
+    if ((phases & STEP_PREDICT) && warp == WARPS - 1 && lane == 0)
+        ekf_predict_scalars(fc, s, in.fwd[in.cmd_stride ? inst : 0], in.ang[in.cmd_stride ? inst : 0]);
+    if ((phases & STEP_UPDATE) && fc.id_known && warp == 0) ekf_assoc_prepass(s, lane, M, nm, b.max_lm);
+    mbar_wait(s.bar, parity);
+    cta_sync<THREADS>();
+
+    int n_upd = 0;
+    bool intact = true;
+    const bool alive = ekf_core<THREADS>(fc, s, lds, b.max_lm, phases, M, nm, status, n_upd, intact);
 
     // ---- commit, :176-177
-    if (dead) {
-        // frozen at the last committed state: nothing but the status word changes
+    if (!alive) {
+        // frozen at the last committed state (global memory still holds it): only the status word changes
         if (tid == 0) b.meta[inst] = make_int4(meta_in.x, status, meta_in.z, 0);
         return true;
     }
+    const int n = 3 + 2 * M;
     for (int i = tid; i < n; i += THREADS) {
         const double v = s.x[i];
         gx[i] = v;
-        if (!isfinite(v) || !isfinite(s.P[(size_t)i * lds + i])) s.iscr[2] = 1;
+        if (!isfinite(v) || !isfinite(s.P[(size_t)i * lds + i])) s.iscr[IS_NAN] = 1;
     }
     for (int i = tid + M_start; i < M; i += THREADS) b.ids[(size_t)inst * b.max_lm + i] = s.ids[i];
-    for (int i = tid; i < nm; i += THREADS) b.assoc[(size_t)inst * b.max_meas + i] = s.assoc[i];
+    for (int i = tid; i < nm; i += THREADS) { const int a = s.assoc[i]; b.assoc[(size_t)inst * b.max_meas + i] = a < 0 ? -1 : a; }
     fence_proxy_async();     // generic-proxy writes of P must be visible to the bulk-copy engine
-    __syncthreads();
-    if (tid == 0) {
-        if (s.iscr[2]) status |= SLAM_STATUS_NAN;
-        b.meta[inst] = make_int4(M, status, meta_in.z + ((phases & STEP_PREDICT) ? 1 : 0),   // timestep, :39
-                                 (phases & STEP_UPDATE) ? nm : meta_in.w);
-        if (M > M_start) atomicMax(b.max_M, M);
-        // algorithmic work of this update, using the live n at the end of the step
-        double* st = b.stats + (size_t)inst * SLAM_NUM_STATS;
-        const double nd = (double)n;
-        st[8] += 16.0 * nd * nd + 16.0 * nd + 12.0 * nm + 8.0;
-        st[9] += 4.0 * (double)n_upd * nd * nd;
-        st[10] += nd;
-        st[11] += (double)nm;
-    }
+    cta_sync<THREADS>();
     if (warp == 0) {
         const int ldg = ldg_of(n);
         for (int row = lane; row < n; row += 32)
             bulk_s2g(gP + (size_t)row * ldg, s.P + (size_t)row * lds, (uint32_t)(ldg * sizeof(double)));
         bulk_commit();
-        bulk_wait_all();
     }
+    if (tid == 0) {
+        if (s.iscr[IS_NAN]) status |= SLAM_STATUS_NAN;
+        b.meta[inst] = make_int4(M, status, meta_in.z + ((phases & STEP_PREDICT) ? 1 : 0),   // timestep, :39
+                                 (phases & STEP_UPDATE) ? nm : meta_in.w);
+        if (M > M_start) atomicMax(b.max_M, M);
+        double w[4] = {0, 0, 0, 0};
+        ekf_work_terms(n, nm, n_upd, w);
+        double* st = b.stats + (size_t)inst * SLAM_NUM_STATS;
+        st[8] += w[0]; st[9] += w[1]; st[10] += w[2]; st[11] += w[3];
+    }
+    // shared memory may be reused / released once the bulk engine has READ it; global visibility of the writes is
+    // guaranteed at kernel completion
+    if (warp == 0) bulk_wait_read();
     return true;
 }
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, (THREADS >= 256) ? 2 : 6)
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 ekf_step_kernel(BatchState b, FilterConst fc, StepInputs in, int phases, EkfLaunch L) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EkfSmem s;
-    ekf_smem_carve(b, L, smem_raw, &s);
+    ekf_smem_carve(b.max_meas, L, smem_raw, &s);
     if (threadIdx.x == 0) { mbar_init(s.bar, 1); fence_mbar_init(); }
-    __syncthreads();
+    cta_sync<THREADS>();
     if (!L.from_list) {
         ekf_instance<THREADS>(b, fc, in, phases, L, s, (int)blockIdx.x, 0u);
         return;
@@ -416,6 +526,154 @@ ekf_step_kernel(BatchState b, FilterConst fc, StepInputs in, int phases, EkfLaun
     uint32_t parity = 0;
     for (int q = blockIdx.x; q < count; q += gridDim.x) {
         if (ekf_instance<THREADS>(b, fc, in, phases, L, s, b.retry_list[q], parity)) parity ^= 1u;
+        cta_sync<THREADS>();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// ekf_sweep_kernel: T consecutive reference steps of every instance in ONE launch -- simulator (sim_node.py:209-250)
+// -> EKF::update -> error terms -- with the filter resident in shared memory.  A persistent grid pulls instances
+// from a work counter.  Per step: the scalar warp simulates the vehicle and associates the message, one thread
+// evaluates the predict trigonometry, one thread folds the previous step's error terms; then ekf_core.
+// Known-ID mode only (the host falls back to per-step launches otherwise): the pre-pass association detects a
+// same-step re-match before the step touches anything, so a dead instance stays at its committed state.
+// ------------------------------------------------------------------------------------------------------------
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 2)
+ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, const float* __restrict__ cmd_fwd,
+                 const float* __restrict__ cmd_ang, const int cmd_stride, const int T, const uint32_t first_step,
+                 int* work_counter, EkfLaunch L) {
+    constexpr int WARPS = THREADS / 32;
+    static_assert(WARPS >= 4, "the sweep kernel specialises three warps");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EkfSmem s;
+    ekf_smem_carve(b.max_meas, L, smem_raw, &s);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lds = L.lds;
+    const bool sim_warp = warp == WARPS - 1;
+    const bool trig_thread = tid == 0;
+    const bool err_thread = tid == 32;
+    if (tid == 0) { mbar_init(s.bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    uint32_t parity = 0;
+
+    while (true) {
+        if (tid == 0) s.iscr[IS_WORK] = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int inst = s.iscr[IS_WORK];
+        if (inst >= b.batch) break;
+        const int4 meta_in = b.meta[inst];
+        int status = meta_in.y;
+        int M = meta_in.x;
+        const int M_first = M;
+        double* gP = b.P + (size_t)inst * b.p_stride;
+        double* gx = b.x + (size_t)inst * b.x_stride;
+        const int n0 = 3 + 2 * M;
+        {
+            const int ldg = ldg_of(n0);
+            if (warp == 0) {
+                if (lane == 0) { mbar_expect_tx(s.bar, (uint32_t)(n0 * ldg * sizeof(double))); s.iscr[IS_NAN] = 0; s.iscr[IS_DEAD] = 0; }
+                __syncwarp();
+                for (int row = lane; row < n0; row += 32)
+                    bulk_g2s(s.P + (size_t)row * lds, gP + (size_t)row * ldg, (uint32_t)(ldg * sizeof(double)), s.bar);
+            }
+        }
+        for (int i = tid; i < n0; i += THREADS) s.x[i] = gx[i];
+        for (int i = tid; i < M; i += THREADS) s.ids[i] = b.ids[(size_t)inst * b.max_lm + i];
+        double tr[3] = {0, 0, 0};                    // truth state, carried by the simulator warp
+        if (sim_warp) { const double* t = sim.truth + 3 * (size_t)inst; tr[0] = t[0]; tr[1] = t[1]; tr[2] = t[2]; }
+        double eacc[6] = {0, 0, 0, 0, 0, 0};         // error terms, carried by err_thread
+        double wacc[4] = {0, 0, 0, 0};               // work counters, carried by thread 0
+        int timestep = meta_in.z, nm = 0, overflow = 0;
+        mbar_wait(s.bar, parity);
+        parity ^= 1u;
+        __syncthreads();
+
+        for (int t = 0; t < T; ++t) {
+            const bool frozen = (status & SLAM_STATUS_SAME_STEP_REMATCH) != 0;
+            const float d_d = cmd_fwd[(size_t)t * (cmd_stride ? b.batch : 1) + (cmd_stride ? inst : 0)];
+            const float d_th = cmd_ang[(size_t)t * (cmd_stride ? b.batch : 1) + (cmd_stride ? inst : 0)];
+            // ---- phase 0: simulator + association | predict trigonometry | previous step's error terms | x_t snapshot
+            if (sim_warp) {
+                const int count = sim_get_cmd_warp(lane, sc, sim.lm_xy, sim.n_lm, b.max_meas, sim.k0, sim.k1,
+                                                   sim.instance_offset + (uint32_t)inst, first_step + (uint32_t)t, d_d, d_th,
+                                                   tr, s.meas);
+                if (count > b.max_meas) overflow = 1;
+                const int k = count < b.max_meas ? count : b.max_meas;
+                if (lane == 0) {
+                    s.iscr[IS_NM] = k;
+                    double* st = s.sc + SC_TR + 3 * (t & 1);
+                    st[0] = tr[0]; st[1] = tr[1]; st[2] = tr[2];
+                }
+                __syncwarp();
+                if (!frozen) ekf_assoc_prepass(s, lane, M, k, b.max_lm);
+            }
+            if (err_thread && t > 0) {
+                const double* st = s.sc + SC_TR + 3 * ((t - 1) & 1);
+                double C[3][3];
+                for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) C[a][c] = s.P[a * lds + c];
+                pose_error_terms(s.x[0] - st[0], s.x[1] - st[1], remainder(s.x[2] - st[2], TWO_PI_REF), C, eacc);
+            }
+            if (trig_thread && !frozen) ekf_predict_scalars(fc, s, d_d, d_th);
+            for (int i = tid; i < 3 + 2 * M; i += THREADS) s.xs[i] = s.x[i];
+            __syncthreads();
+            nm = s.iscr[IS_NM];
+            if (!frozen) {
+                int n_upd = 0;
+                bool intact = true;
+                if (ekf_core<THREADS>(fc, s, lds, b.max_lm, STEP_PREDICT | STEP_UPDATE, M, nm, status, n_upd, intact)) {
+                    ++timestep;
+                    if (tid == 0) ekf_work_terms(3 + 2 * M, nm, n_upd, wacc);
+                }
+            }
+        }
+        // ---- error terms of the last step, then commit the instance
+        if (err_thread && T > 0) {
+            const double* st = s.sc + SC_TR + 3 * ((T - 1) & 1);
+            double C[3][3];
+            for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) C[a][c] = s.P[a * lds + c];
+            pose_error_terms(s.x[0] - st[0], s.x[1] - st[1], remainder(s.x[2] - st[2], TWO_PI_REF), C, eacc);
+            double* g = b.stats + (size_t)inst * SLAM_NUM_STATS;
+            for (int k = 0; k < 6; ++k) g[k] += eacc[k];
+        }
+        const int n = 3 + 2 * M;
+        for (int i = tid; i < n; i += THREADS) {
+            const double v = s.x[i];
+            gx[i] = v;
+            if (!isfinite(v) || !isfinite(s.P[(size_t)i * lds + i])) s.iscr[IS_NAN] = 1;
+        }
+        for (int i = tid + M_first; i < M; i += THREADS) b.ids[(size_t)inst * b.max_lm + i] = s.ids[i];
+        if (T > 0) {
+            const bool frozen = (status & SLAM_STATUS_SAME_STEP_REMATCH) != 0;
+            for (int i = tid; i < nm; i += THREADS) {
+                const int a = s.assoc[i];
+                if (!frozen) b.assoc[(size_t)inst * b.max_meas + i] = a < 0 ? -1 : a;
+            }
+            for (int i = tid; i < 3 * nm; i += THREADS) sim.meas[(size_t)inst * b.max_meas * 3 + i] = s.meas[i];
+        }
+        if (sim_warp && lane == 0 && T > 0) {
+            double* tg = sim.truth + 3 * (size_t)inst;
+            tg[0] = tr[0]; tg[1] = tr[1]; tg[2] = tr[2];
+            sim.n_meas[inst] = nm;
+            if (overflow) sim.overflow[inst] = 1;
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (warp == 0) {
+            const int ldg = ldg_of(n);
+            for (int row = lane; row < n; row += 32)
+                bulk_s2g(gP + (size_t)row * ldg, s.P + (size_t)row * lds, (uint32_t)(ldg * sizeof(double)));
+            bulk_commit();
+        }
+        if (tid == 0) {
+            if (s.iscr[IS_NAN]) status |= SLAM_STATUS_NAN;
+            const bool frozen = (status & SLAM_STATUS_SAME_STEP_REMATCH) != 0;
+            b.meta[inst] = make_int4(M, status, timestep, (T > 0 && !frozen) ? nm : (frozen ? 0 : meta_in.w));
+            if (M > M_first) atomicMax(b.max_M, M);
+            double* st = b.stats + (size_t)inst * SLAM_NUM_STATS;
+            st[8] += wacc[0]; st[9] += wacc[1]; st[10] += wacc[2]; st[11] += wacc[3];
+        }
+        if (warp == 0) bulk_wait_read();    // the tile is re-filled by the next instance
         __syncthreads();
     }
 }
@@ -452,33 +710,84 @@ static EkfLaunch make_launch(const BatchState& b, int cap_lm, int from_list) {
     return L;
 }
 
-size_t ekf_step_smem_bytes(const BatchState& b) { return ekf_smem_carve(b, make_launch(b, b.max_lm, 0), nullptr, nullptr); }
+size_t ekf_step_smem_bytes(const BatchState& b) { return ekf_smem_carve(b.max_meas, make_launch(b, b.max_lm, 0), nullptr, nullptr); }
+
+static constexpr size_t SMEM_PER_SM = 227 * 1024, SMEM_CTA_RESERVED = 1024;
+
+// CTA width for a tile: about 32 resident warps per SM whatever the tile size (registers cap a CTA at 64/thread).
+static int pick_threads(size_t smem) {
+    size_t ipsm = SMEM_PER_SM / (smem + SMEM_CTA_RESERVED);
+    if (ipsm < 1) ipsm = 1;
+    if (ipsm > 32) ipsm = 32;
+    int warps = 1;
+    while (warps * 2 * (int)ipsm <= 32 && warps < 16) warps *= 2;
+    return warps * 32;
+}
+
+template <int THREADS>
+static cudaError_t set_smem_step(int bytes) {
+    return cudaFuncSetAttribute(ekf_step_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
 
 cudaError_t ekf_step_configure(const BatchState& b) {
     const int bytes = (int)ekf_step_smem_bytes(b);
-    cudaError_t e = cudaFuncSetAttribute(ekf_step_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(ekf_step_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaError_t e;
+    if ((e = set_smem_step<32>(bytes)) != cudaSuccess) return e;
+    if ((e = set_smem_step<64>(bytes)) != cudaSuccess) return e;
+    if ((e = set_smem_step<128>(bytes)) != cudaSuccess) return e;
+    if ((e = set_smem_step<256>(bytes)) != cudaSuccess) return e;
+    if ((e = set_smem_step<512>(bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ekf_sweep_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(ekf_sweep_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+static cudaError_t launch_step_threads(int threads, int grid, size_t smem, cudaStream_t st, const BatchState& b,
+                                       const FilterConst& fc, const StepInputs& in, int phases, const EkfLaunch& L) {
+    switch (threads) {
+        case 32: ekf_step_kernel<32><<<grid, 32, smem, st>>>(b, fc, in, phases, L); break;
+        case 64: ekf_step_kernel<64><<<grid, 64, smem, st>>>(b, fc, in, phases, L); break;
+        case 128: ekf_step_kernel<128><<<grid, 128, smem, st>>>(b, fc, in, phases, L); break;
+        case 256: ekf_step_kernel<256><<<grid, 256, smem, st>>>(b, fc, in, phases, L); break;
+        default: ekf_step_kernel<512><<<grid, 512, smem, st>>>(b, fc, in, phases, L); break;
+    }
+    return cudaGetLastError();
 }
 
 // cap_hint: landmark capacity to size this launch for (<= 0 or >= max_lm: full capacity, no retry pass).
+// force_threads: 0 = automatic CTA width, else 32..512 (tuning / tests).
 cudaError_t launch_ekf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, int phases, int cap_hint,
-                            cudaStream_t st) {
+                            int force_threads, cudaStream_t st) {
     const bool limited = cap_hint > 0 && cap_hint < b.max_lm;
     const EkfLaunch L = make_launch(b, limited ? cap_hint : b.max_lm, 0);
-    const size_t smem = ekf_smem_carve(b, L, nullptr, nullptr);
+    const size_t smem = ekf_smem_carve(b.max_meas, L, nullptr, nullptr);
     if (limited) {
         cudaError_t e = cudaMemsetAsync(b.retry_count, 0, sizeof(int), st);
         if (e != cudaSuccess) return e;
     }
-    // small tiles: 128-thread CTAs (the O(n^2) sweep is short and more CTAs fit per SM)
-    if (L.n_cap <= 67) ekf_step_kernel<128><<<b.batch, 128, smem, st>>>(b, fc, in, phases, L);
-    else ekf_step_kernel<256><<<b.batch, 256, smem, st>>>(b, fc, in, phases, L);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_step_threads(force_threads ? force_threads : pick_threads(smem), b.batch, smem, st, b, fc, in, phases, L);
     if (e != cudaSuccess || !limited) return e;
     const EkfLaunch R = make_launch(b, b.max_lm, 1);
-    const int grid = b.batch < 296 ? b.batch : 296;
-    ekf_step_kernel<256><<<grid, 256, ekf_smem_carve(b, R, nullptr, nullptr), st>>>(b, fc, in, phases, R);
+    const size_t rsmem = ekf_smem_carve(b.max_meas, R, nullptr, nullptr);
+    const int rthreads = force_threads ? force_threads : pick_threads(rsmem);
+    const int per_sm = (int)(SMEM_PER_SM / (rsmem + SMEM_CTA_RESERVED)) > 0 ? (int)(SMEM_PER_SM / (rsmem + SMEM_CTA_RESERVED)) : 1;
+    const int grid = b.batch < 148 * per_sm ? b.batch : 148 * per_sm;
+    return launch_step_threads(rthreads, grid, rsmem, st, b, fc, in, phases, R);
+}
+
+// Whole sweep in one launch (known-ID EKF batches).  work_counter: device int, zeroed here.
+cudaError_t launch_ekf_sweep(const BatchState& b, const FilterConst& fc, const SimState& sim, const SimConst& sc,
+                             const float* d_fwd, const float* d_ang, int cmd_stride, int T, uint32_t first_step,
+                             int* work_counter, int force_threads, cudaStream_t st) {
+    const EkfLaunch L = make_launch(b, b.max_lm, 0);
+    const size_t smem = ekf_smem_carve(b.max_meas, L, nullptr, nullptr);
+    cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    int per_sm = (int)(SMEM_PER_SM / (smem + SMEM_CTA_RESERVED));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 2) per_sm = 2;
+    const int grid = b.batch < 148 * per_sm ? b.batch : 148 * per_sm;
+    if (force_threads == 512) ekf_sweep_kernel<512><<<grid, 512, smem, st>>>(b, fc, sim, sc, d_fwd, d_ang, cmd_stride, T, first_step, work_counter, L);
+    else ekf_sweep_kernel<256><<<grid, 256, smem, st>>>(b, fc, sim, sc, d_fwd, d_ang, cmd_stride, T, first_step, work_counter, L);
     return cudaGetLastError();
 }
 

@@ -274,3 +274,93 @@ def test_capacity_limited_launch_and_retry_pass(shim, oracle, cap):
         _compare(fb, i, ofs[i])
         assert fb.timestep(i) == len(fwd)
     assert max(o.M for o in ofs) > 6
+
+
+@pytest.mark.parametrize("threads", [32, 64, 128, 256, 512])
+def test_cta_widths_agree_with_oracle(shim, oracle, threads):
+    """ekf_step_kernel is instantiated for 1..16 warps per instance (the launcher picks from the tile size); every
+    width must give the oracle's results."""
+    p, lm, fwd, ang = H.config2(seed=3, steps=160)
+    op = H.oracle_params(oracle, p)
+    B = 6
+    fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), B, 50, 8)
+    fb.tune(2, threads)
+    fb.init(0, 0, 0)
+    streams = [H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=31, instance=i)[0] for i in range(B)]
+    ofs = []
+    for i in range(B):
+        of = oracle.OracleFilter(oracle.EKF_SLAM, op, 50)
+        of.init(0, 0, 0)
+        ofs.append(of)
+    for t in range(len(fwd)):
+        meas, n = fb.pack_meas([streams[i][t] for i in range(B)])
+        fb.step(fwd[t], ang[t], meas, n)
+        for i in range(B):
+            ofs[i].update(fwd[t], ang[t], streams[i][t], oracle.STRUCTURED)
+        if t % 40 == 39:
+            for i in range(B):
+                assert list(fb.assoc(i)) == list(ofs[i].assoc_log())
+    for i in range(B):
+        _compare(fb, i, ofs[i])
+    assert max(o.M for o in ofs) >= 5
+
+
+@pytest.mark.parametrize("threads", [0, 512])
+def test_sweep_kernel_matches_per_step_launches(shim, oracle, threads):
+    """slam_run on a known-ID EKF batch is ONE persistent launch (ekf_sweep_kernel: simulator + filter + error terms,
+    P resident in shared memory for all T steps).  It must reproduce the per-step launch sequence: same association
+    log, landmark ids, messages, truth, statistics; state and covariance to rounding."""
+    p, lm, fwd, ang = H.config2(seed=4, steps=260)
+    B = 40
+    res = []
+    for sweep_off in (0, 1):
+        fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), B, 50, 8)
+        fb.tune(3, sweep_off)
+        if not sweep_off:
+            fb.tune(2, threads)
+        fb.init(0, 0, 0)
+        sim = shim.Simulator(fb, lm, seed=77, instance_offset=1000)
+        l0 = fb.kernel_launches
+        sim.run(fwd[:200], ang[:200], first_step=0)
+        sim.run(fwd[200:], ang[200:], first_step=200)      # a second sweep continues from the committed state
+        fb.synchronize()
+        launches = fb.kernel_launches - l0
+        m, n = sim.meas()
+        res.append(dict(x=[fb.state(i) for i in range(B)], P=[fb.cov(i) for i in range(B)],
+                        ids=[list(fb.landmark_ids(i)) for i in range(B)], assoc=[list(fb.assoc(i)) for i in range(B)],
+                        ts=[fb.timestep(i) for i in range(B)], truth=sim.truth(), meas=m, n=n, stats=fb.stats(),
+                        status=fb.all_status(), launches=launches))
+    a, b = res
+    assert a["launches"] == 2 and b["launches"] >= 3 * 260
+    assert a["ids"] == b["ids"] and a["assoc"] == b["assoc"] and a["ts"] == b["ts"] == [260] * B
+    np.testing.assert_array_equal(a["truth"], b["truth"])
+    np.testing.assert_array_equal(a["n"], b["n"])
+    for i in range(B):
+        np.testing.assert_array_equal(a["meas"][i, : a["n"][i]], b["meas"][i, : b["n"][i]])
+        assert H.normwise(a["x"][i], b["x"][i]) <= 1e-12 and H.normwise(a["P"][i], b["P"][i]) <= 1e-12
+    assert (a["status"] == 0).all() and (b["status"] == 0).all()
+    np.testing.assert_allclose(a["stats"], b["stats"], rtol=1e-9)
+    # and against the oracle, free running
+    op = H.oracle_params(oracle, p)
+    for i in range(0, B, 9):
+        st, pose, tr, filt = oracle.run_instance(oracle.EKF_SLAM, op, lm, fwd, ang, 77, 1000 + i, 50, oracle.STRUCTURED, keep=True)
+        assert st == 0 and a["ids"][i] == list(filt.landmark_ids())
+        assert H.normwise(a["x"][i], filt.state()) <= H.REL_TOL and H.normwise(a["P"][i], filt.cov()) <= 1e-8
+
+
+def test_sweep_kernel_freezes_dead_instance(shim, oracle):
+    """A repeated id inside one message makes the reference die (ekf.cpp:115).  The per-step path flags it and freezes
+    the instance at its last committed state; a sweep must do the same (here: duplicate landmark positions in the map
+    never produce duplicate ids, so the dead path is driven through slam_step and the sweep continues frozen)."""
+    p, lm, fwd, ang = H.config2(seed=5, steps=60)
+    fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 2, 50, 8)
+    fb.init(0, 0, 0)
+    meas, n = fb.pack_meas([np.array([[3, 1.0, 0.1], [3, 1.0, 0.1]], dtype=np.float32), np.zeros((0, 3), dtype=np.float32)])
+    fb.step(0.05, 0.0, meas, n)
+    assert fb.status(0) & shim.STATUS_SAME_STEP_REMATCH and fb.status(1) == 0
+    x0, P0 = fb.state(0), fb.cov(0)
+    sim = shim.Simulator(fb, lm, seed=1)
+    sim.run(fwd, ang)
+    np.testing.assert_array_equal(fb.state(0), x0)
+    np.testing.assert_array_equal(fb.cov(0), P0)
+    assert fb.timestep(0) == 0 and fb.timestep(1) == 61 and fb.num_landmarks(0) == 0
