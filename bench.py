@@ -164,6 +164,10 @@ def run_ours(args):
     p, lm, fwd, ang = build_workload("ekf_slam" if args.filter == "ekf" else "ukf_slam", T)
     fb = shim.FilterBatch(kind, p.to_c(), B, 50, args.max_meas, device=local)
     sim = shim.Simulator(fb, lm, seed=args.seed, instance_offset=parallel.weak_offset(B, rank))   # RNG keyed by the GLOBAL instance id
+    if args.no_sweep:
+        fb.tune(3, 1)
+    if args.cta_threads:
+        fb.tune(2, args.cta_threads)
     stream = torch.cuda.ExternalStream(fb.stream, device=torch.device("cuda", local))
     d_fwd = torch.from_numpy(fwd).cuda()
     d_ang = torch.from_numpy(ang).cuda()
@@ -215,7 +219,7 @@ def run_ours(args):
     sweep()
     k_ms, k_n = fb.profile()
     fb.set_profiling(0)
-    fb.tune(3, 0)
+    fb.tune(3, 1 if args.no_sweep else 0)
     loc = fb.stats()
     step_roof = {"bound": "hbm", "kernel": kname, "achieved": loc[8] / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0,
                  "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": args.traffic_bytes,
@@ -331,6 +335,8 @@ def main():
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--e2e-sweeps", type=int, default=2)
     ap.add_argument("--ref-instances-per-core", type=int, default=16)
+    ap.add_argument("--no-sweep", action="store_true", help="per-step launches on the value path (to profile ekf_step_kernel)")
+    ap.add_argument("--cta-threads", type=int, default=0, help="force the CTA width of the EKF kernels (tuning)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-traffic-bytes", type=float, default=None,

@@ -94,9 +94,19 @@ __host__ __device__ inline double uniform53(uint32_t hi, uint32_t lo) {
 __device__ __forceinline__ float cos_f(float x) { return (float)cos((double)x); }
 __device__ __forceinline__ float sin_f(float x) { return (float)sin((double)x); }
 
-// remainder(a, 2*pi) (filter.h:42 pi): for |a| <= pi the IEEE result is a itself (n = 0, ties to even), which is the
-// common case on this path; the library routine handles the rest.  Exact in both branches.
-__device__ __forceinline__ double wrap_2pi(double a) { return (fabs(a) <= PI_REF) ? a : remainder(a, TWO_PI_REF); }
+// remainder(a, 2*pi) (filter.h:42 pi), exact.  |a| <= pi: the IEEE result is a itself (n = 0, ties to even) -- the
+// common case on the filter path.  Otherwise n' = rint(a / 2pi) and r = fma(-n', 2pi, a): whenever |r| is clearly
+// below pi, n' is the integer nearest to a / 2pi, so a - n' 2pi IS the IEEE remainder, which is representable, and the
+// fma (exact product, one rounding) returns it exactly.  Anything near the +-pi boundary goes to the library routine.
+__device__ __forceinline__ double wrap_2pi(double a) {
+    if (fabs(a) <= PI_REF) return a;
+    if (fabs(a) < 1.0e6) {
+        const double n = rint(a * (1.0 / TWO_PI_REF));
+        const double r = fma(-n, TWO_PI_REF, a);
+        if (fabs(r) < 3.1415) return r;
+    }
+    return remainder(a, TWO_PI_REF);
+}
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier + 1-D bulk async copy (TMA without a tensor map: cp.async.bulk, SASS UBLKCP)

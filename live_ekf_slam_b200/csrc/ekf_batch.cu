@@ -15,11 +15,12 @@
 // Thread organisation (THREADS = 32 * WARPS, WARPS in {1,2,4,8,16}, chosen per launch from the tile size so that
 // about 32 warps are resident per SM whatever n is).  Scalar chains (sincos, sqrt, atan2, divisions) are the
 // latency- and issue-critical part at small n, so:
-//   * the last warp is the "scalar warp": its lane 0 evaluates the predict trigonometry and the innovation
-//     (atan2 / remainder) while the other warps do O(n) work; it joins the O(n^2) sweep;
-//   * the four distinct quotients of H are computed once per warp, lane-parallel, and shuffled;
-//   * S and S^-1 come from the 5x5 sub-block directly, so a landmark update costs two CTA barriers;
-//   * known-ID association (integer compares on lm_IDs) is resolved for the whole message before P is touched.
+//   * warp 0 evaluates the H / S / S^-1 chain of a landmark update ONCE (lane-parallel divisions, S from the 5x5
+//     sub-block of P that H touches) while lane 0 of the last warp evaluates the innovation (atan2 / remainder) and,
+//     at step start, the predict trigonometry; the other warps wait at the barrier and cost no issue slots;
+//   * known-ID association (integer compares on lm_IDs) is resolved for the whole message before P is touched;
+//   * in the sweep kernel a dedicated producer warp runs the simulator one step ahead of the filter warps and folds
+//     the error terms one step behind them (named barriers, double-buffered messages).
 #include "sim_device.cuh"
 
 #include <climits>
@@ -78,13 +79,23 @@ __host__ __device__ inline size_t ekf_smem_carve(const int max_meas, const EkfLa
 
 // scalar slots in sc[]
 enum { SC_FA = 0, SC_FB, SC_C, SC_S, SC_NX0, SC_NX1, SC_NX2, SC_NU0, SC_NU1, SC_XD, SC_YD, SC_CB, SC_SB,
-       SC_TR = 16 /* sweep: truth of step parity 0 at [16..18], parity 1 at [19..21] */ };
-enum { IS_DEAD = 0, IS_NAN = 1, IS_NM = 2, IS_WORK = 3 };
+       SC_Q0 = 13 /* 4 quotients of H */, SC_I00 = 17 /* S^-1, 4 */, SC_END = 21 };
+enum { IS_DEAD = 0, IS_NAN = 1, IS_WORK = 2 };
 enum { ASSOC_NEW = -1, ASSOC_DROPPED = -2 };   // internal codes of the pre-pass; both read back as -1 (new landmark)
 
-template <int THREADS>
-__device__ __forceinline__ void cta_sync() {
-    if constexpr (THREADS == 32) __syncwarp(); else __syncthreads();
+// barrier among the NT threads that run the filter core
+template <int NT>
+struct CtaSync {            // the whole CTA runs the core (ekf_step_kernel)
+    static __device__ __forceinline__ void sync() { if constexpr (NT == 32) __syncwarp(); else __syncthreads(); }
+};
+template <int NT, int ID>
+struct NamedSync {          // a subset of the CTA's warps runs the core (ekf_sweep_kernel consumers)
+    static __device__ __forceinline__ void sync() { asm volatile("bar.sync %0, %1;" ::"r"(ID), "r"(NT) : "memory"); }
+};
+__device__ __forceinline__ void named_sync(const int id, const int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(const int id, const int count) {
+    __threadfence_block();
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
 // ---- predict scalars (ekf.cpp:43-59), one thread: F_x(0,2), F_x(1,2), cos, sin and the new vehicle pose
@@ -127,24 +138,21 @@ __device__ __forceinline__ void ekf_assoc_prepass(const EkfSmem& s, const int la
     if (lane == 0) s.iscr[IS_DEAD] = dead ? 1 : 0;
 }
 
-// ---- one reference EKF::update on the shared-memory-resident filter.
-// On entry (all visible to the CTA): s.P / s.x / s.xs (= s.x) / s.ids hold the committed filter with M landmarks,
-// s.meas the message, s.sc the predict scalars, and -- known-ID mode -- s.assoc / s.iscr[IS_DEAD] the pre-pass.
-// Returns true when the step was applied; false when the instance died (same-step re-match).  `intact` then tells
-// whether the shared-memory state is still the committed one (always in known-ID mode).
-template <int THREADS>
+// ---- one reference EKF::update on the shared-memory-resident filter, executed by NT threads (threadIdx.x < NT)
+// that synchronise through Sync.  On entry (all visible): s.P / s.x / s.xs (= s.x) / s.ids hold the committed filter
+// with M landmarks, s.meas the message, s.sc the predict scalars, and -- known-ID mode -- s.assoc / s.iscr[IS_DEAD]
+// the pre-pass.  Returns true when the step was applied; false when the instance died (same-step re-match): in
+// known-ID mode nothing has been modified then, in unknown-ID mode the shared-memory state must be discarded.
+template <int NT, class Sync>
 __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s, const int lds, const int max_lm,
-                                         const int phases, int& M, const int nm, int& status, int& n_upd, bool& intact) {
-    constexpr int WARPS = THREADS / 32;
-    constexpr int SW = WARPS - 1;                               // the scalar warp
-    constexpr int ABT = (WARPS > 1) ? THREADS - 32 : 32;        // threads doing the O(n) phase of an update
-    constexpr int UNR = (THREADS >= 512) ? 2 : 4;               // rows in flight in the rank-2 sweep
+                                         const int phases, int& M, const int nm, int& status, int& n_upd) {
+    constexpr int WARPS = NT / 32;
+    constexpr int NUW = WARPS - 1;                              // lane 0 of this warp owns the atan2 / sincos chains
+    constexpr int UNR = (NT >= 512) ? 2 : 4;                    // row groups in flight in the rank-2 sweep
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool scalar_thread = (warp == SW) && (lane == 0);
-    const bool ab_worker = (WARPS == 1) || (warp != SW);
+    const bool nu_thread = (warp == NUW) && (lane == 0);
     const int M_start = M;
     int n = 3 + 2 * M;
-    intact = true;
     n_upd = 0;
 
     if ((phases & STEP_UPDATE) && fc.id_known && s.iscr[IS_DEAD]) { status |= SLAM_STATUS_SAME_STEP_REMATCH; return false; }
@@ -154,7 +162,7 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
     //      pass does both; the 3x3 vehicle block is done by one thread in the reference's order.
     if (phases & STEP_PREDICT) {
         const double fa = s.sc[SC_FA], fb = s.sc[SC_FB];
-        for (int j = tid; j < n; j += THREADS) {
+        for (int j = tid; j < n; j += NT) {
             if (j >= 3) {
                 const double p2 = s.P[2 * lds + j];
                 s.P[j] = s.P[j] + fa * p2;
@@ -187,8 +195,7 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
                 s.x[0] = s.sc[SC_NX0]; s.x[1] = s.sc[SC_NX1]; s.x[2] = s.sc[SC_NX2];
             }
         }
-        intact = false;
-        cta_sync<THREADS>();
+        Sync::sync();
     }
 
     // ---- UPDATE, ekf.cpp:63-174
@@ -202,13 +209,13 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
         } else {
             // -- unknown IDs, :82-98: first landmark inside the float box gate around the detection
             id = M;
-            if (scalar_thread) {
+            if (nu_thread) {
                 double sa, ca; sincos(s.x[2] + (double)bb, &sa, &ca);
                 s.sc[SC_XD] = (double)(float)(s.x[0] + (double)r * ca);    // float x_detected, :87
                 s.sc[SC_YD] = (double)(float)(s.x[1] + (double)r * sa);    // float y_detected, :88
                 s.sc[SC_CB] = ca; s.sc[SC_SB] = sa;                        // reused by the insertion below
             }
-            cta_sync<THREADS>();
+            Sync::sync();
             const double xd = s.sc[SC_XD], yd = s.sc[SC_YD];
             int cand = INT_MAX;
             for (int j = lane; j < M; j += 32) {                           // every warp scans the whole map: no barrier
@@ -222,7 +229,7 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
             if (slot == ASSOC_NEW && M >= max_lm) {
                 status |= SLAM_STATUS_CAPACITY;
                 if (tid == 0) s.assoc[l] = ASSOC_NEW;
-                cta_sync<THREADS>();      // sc[] is rewritten by the next measurement
+                Sync::sync();             // sc[] is rewritten by the next measurement
                 continue;
             }
             if (tid == 0) s.assoc[l] = slot;
@@ -233,53 +240,66 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
             // -------- landmark update, :110-140
             const int i = slot * 2 + 3;
             ++n_upd;
-            // landmark from the stale x_t, vehicle from the running x_pred (:115)
-            const double dx = s.xs[i] - s.x[0], dy = s.xs[i + 1] - s.x[1];
-            const float dist = (float)sqrt(dx * dx + dy * dy);             // :115
-            if (scalar_thread) {
-                const float ang = (float)wrap_2pi(atan2(dy, dx) - s.x[2]); // :129
-                s.sc[SC_NU0] = (double)(r - dist - fc.w_r);                // all-float arithmetic, :130
-                s.sc[SC_NU1] = (double)(bb - ang - fc.w_b);                // :131
-            }
-            if (ab_worker) {
-                // the four distinct quotients of H_x (:118-126), one per lane, shuffled to the warp
-                const double dd = (double)dist;
-                const double d2 = (double)(dist * dist);                   // float product, :120
-                const int ql = lane & 3;
-                const double qv = ((ql == 0 || ql == 3) ? dx : dy) / ((ql < 2) ? dd : d2);
-                const double q0 = __shfl_sync(0xffffffffu, qv, 0);         // dx / dist
-                const double q1 = __shfl_sync(0xffffffffu, qv, 1);         // dy / dist
-                const double q2 = __shfl_sync(0xffffffffu, qv, 2);         // dy / dist^2
-                const double q3 = __shfl_sync(0xffffffffu, qv, 3);         // dx / dist^2
-                const double H[10] = {-q0, -q1, 0.0, q0, q1, q2, -q3, -1.0, -q2, q3};
-                const int hc[5] = {0, 1, 2, i, i + 1};
-                // S = H P H^T + W (:133) from the 5x5 sub-block, S^-1 by partial-pivot LU like Eigen's dynamic
-                // inverse() (:135); evaluated by every worker thread (broadcast reads, no barrier)
-                double S00 = 0, S01 = 0, S10 = 0, S11 = 0;
-#pragma unroll
-                for (int c = 0; c < 5; ++c) {
-                    double p[5];
-#pragma unroll
-                    for (int a = 0; a < 5; ++a) p[a] = s.P[(size_t)hc[a] * lds + hc[c]];
-                    double g0 = H[0] * p[0]; g0 += H[1] * p[1]; g0 += H[2] * p[2]; g0 += H[3] * p[3]; g0 += H[4] * p[4];
-                    double g1 = H[5] * p[0]; g1 += H[6] * p[1]; g1 += H[7] * p[2]; g1 += H[8] * p[3]; g1 += H[9] * p[4];
-                    S00 += g0 * H[c]; S01 += g0 * H[5 + c]; S10 += g1 * H[c]; S11 += g1 * H[5 + c];
+            // -- scalar phase: warp 0 -> H (4 distinct quotients), S, S^-1 ; nu thread -> innovation
+            if (warp == 0 || nu_thread) {
+                // landmark from the stale x_t, vehicle from the running x_pred (:115)
+                const double dx = s.xs[i] - s.x[0], dy = s.xs[i + 1] - s.x[1];
+                const float dist = (float)sqrt(dx * dx + dy * dy);         // :115
+                if (nu_thread) {
+                    const float ang = (float)wrap_2pi(atan2(dy, dx) - s.x[2]);   // :129
+                    s.sc[SC_NU0] = (double)(r - dist - fc.w_r);            // all-float arithmetic, :130
+                    s.sc[SC_NU1] = (double)(bb - ang - fc.w_b);            // :131
                 }
-                S00 += fc.W00; S11 += fc.W11;
-                double i00, i01, i10, i11;
-                {
+                if (warp == 0) {
+                    // the four distinct quotients of H_x (:118-126), one per lane, shuffled to the warp
+                    const double dd = (double)dist;
+                    const double d2 = (double)(dist * dist);               // float product, :120
+                    const int ql = lane & 3;
+                    const double qv = ((ql == 0 || ql == 3) ? dx : dy) / ((ql < 2) ? dd : d2);
+                    const double q0 = __shfl_sync(0xffffffffu, qv, 0);     // dx / dist
+                    const double q1 = __shfl_sync(0xffffffffu, qv, 1);     // dy / dist
+                    const double q2 = __shfl_sync(0xffffffffu, qv, 2);     // dy / dist^2
+                    const double q3 = __shfl_sync(0xffffffffu, qv, 3);     // dx / dist^2
+                    const double H[10] = {-q0, -q1, 0.0, q0, q1, q2, -q3, -1.0, -q2, q3};
+                    // S = H P H^T + W (:133) from the 5x5 sub-block of P that H touches: lane c < 5 forms column
+                    // hc[c] of H P, the 2x2 sums are reduced over the 5 lanes in ascending c order
+                    const int hcl = (lane < 3) ? lane : i + (lane - 3);    // hc[lane] for lane < 5
+                    double g0 = 0.0, g1 = 0.0;
+                    if (lane < 5) {
+                        const double p0 = s.P[hcl], p1 = s.P[lds + hcl], p2 = s.P[2 * lds + hcl];
+                        const double p3 = s.P[(size_t)i * lds + hcl], p4 = s.P[(size_t)(i + 1) * lds + hcl];
+                        g0 = H[0] * p0; g0 += H[1] * p1; g0 += H[2] * p2; g0 += H[3] * p3; g0 += H[4] * p4;
+                        g1 = H[5] * p0; g1 += H[6] * p1; g1 += H[7] * p2; g1 += H[8] * p3; g1 += H[9] * p4;
+                    }
+                    double S00 = 0, S01 = 0, S10 = 0, S11 = 0;
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) {
+                        const double a0 = __shfl_sync(0xffffffffu, g0, c), a1 = __shfl_sync(0xffffffffu, g1, c);
+                        S00 += a0 * H[c]; S01 += a0 * H[5 + c]; S10 += a1 * H[c]; S11 += a1 * H[5 + c];
+                    }
+                    S00 += fc.W00; S11 += fc.W11;
+                    // S^-1 by partial-pivot LU like Eigen's dynamic inverse() (:135); the two columns of the inverse
+                    // are solved on two lanes (three dependent divisions instead of five)
                     const bool sw = fabs(S10) > fabs(S00);
                     const double a00 = sw ? S10 : S00, a01 = sw ? S11 : S01, a10 = sw ? S00 : S10, a11 = sw ? S01 : S11;
                     const double l10 = a10 / a00, u11 = a11 - l10 * a01;
-                    // columns of the permuted identity
-                    const double b0c0 = sw ? 0.0 : 1.0, b1c0 = sw ? 1.0 : 0.0;
-                    const double b0c1 = sw ? 1.0 : 0.0, b1c1 = sw ? 0.0 : 1.0;
-                    double y1 = b1c0 - l10 * b0c0; i10 = y1 / u11; i00 = (b0c0 - a01 * i10) / a00;
-                    y1 = b1c1 - l10 * b0c1; i11 = y1 / u11; i01 = (b0c1 - a01 * i11) / a00;
+                    const bool col1 = (lane & 1) != 0;
+                    // column `col` of the permuted identity: (b0, b1)
+                    const double b0 = (sw != col1) ? 0.0 : 1.0, b1 = (sw != col1) ? 1.0 : 0.0;
+                    const double y1 = b1 - l10 * b0;
+                    const double i1c = y1 / u11;                           // S^-1(1, col)
+                    const double i0c = (b0 - a01 * i1c) / a00;             // S^-1(0, col)
+                    if (lane < 2) { s.sc[SC_I00 + lane] = i0c; s.sc[SC_I00 + 2 + lane] = i1c; }   // i00 i01 i10 i11
+                    if (lane == 0) { s.sc[SC_Q0] = q0; s.sc[SC_Q0 + 1] = q1; s.sc[SC_Q0 + 2] = q2; s.sc[SC_Q0 + 3] = q3; }
                 }
-                // H P (2 x n, kept for the sweep) and K = P H^T S^-1 (n x 2)
+            }
+            Sync::sync();
+            // -- O(n) phase: H P (2 x n, kept for the sweep) and K = P H^T S^-1 (n x 2)
+            {
+                const double q0 = s.sc[SC_Q0], q1 = s.sc[SC_Q0 + 1], q2 = s.sc[SC_Q0 + 2], q3 = s.sc[SC_Q0 + 3];
+                const double H[10] = {-q0, -q1, 0.0, q0, q1, q2, -q3, -1.0, -q2, q3};
                 const int ldg = ldg_of(n);
-                for (int idx = tid; idx < ldg + n; idx += ABT) {
+                for (int idx = tid; idx < ldg + n; idx += NT) {
                     if (idx < ldg) {
                         const int j = idx;
                         double h0 = 0.0, h1 = 0.0;
@@ -292,6 +312,7 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
                         s.HP[j] = h0; s.HP[lds + j] = h1;
                     } else {
                         const int q = idx - ldg;
+                        const double i00 = s.sc[SC_I00], i01 = s.sc[SC_I00 + 1], i10 = s.sc[SC_I00 + 2], i11 = s.sc[SC_I00 + 3];
                         const double* row = s.P + (size_t)q * lds;
                         const double p0 = row[0], p1 = row[1], p2 = row[2], p3 = row[i], p4 = row[i + 1];
                         double a0 = p0 * H[0]; a0 += p1 * H[1]; a0 += p2 * H[2]; a0 += p3 * H[3]; a0 += p4 * H[4];
@@ -301,25 +322,25 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
                     }
                 }
             }
-            cta_sync<THREADS>();
-            // x_pred += K nu (:138), yaw wrapped (:139)
+            Sync::sync();
+            // -- x_pred += K nu (:138), yaw wrapped (:139)
             {
                 const double nu0 = s.sc[SC_NU0], nu1 = s.sc[SC_NU1];
-                for (int q = tid; q < n; q += THREADS) {
+                for (int q = tid; q < n; q += NT) {
                     double xv = s.x[q] + (s.K[2 * q] * nu0 + s.K[2 * q + 1] * nu1);
                     if (q == 2) xv = wrap_2pi(xv);
                     s.x[q] = xv;
                 }
             }
-            // P -= K (H P), :140 as a rank-2 update over the packed row width.  A lane owns one double2 column pair
-            // (its two (H P) pairs stay in registers), a warp owns RPI consecutive rows per iteration (RPI > 1 when a
-            // row is narrower than a warp), UNR row groups in flight.
+            // -- P -= K (H P), :140 as a rank-2 update over the packed row width.  A lane owns one double2 column pair
+            //    (its two (H P) pairs stay in registers), a warp owns RPI consecutive rows per iteration (RPI > 1 when
+            //    a row is narrower than a warp), UNR row groups in flight.
             {
                 const int hp = ldg_of(n) >> 1;                  // double2 per row
-                int cpw = 32;                                   // lanes per row: smallest power of two >= hp, <= 32
-                while ((cpw >> 1) >= hp && cpw > 1) cpw >>= 1;
-                const int rpi = 32 / cpw;
-                const int lr = lane / cpw, lc = lane & (cpw - 1);
+                int cpw = 32, cps = 5;                          // lanes per row: smallest power of two >= hp, <= 32
+                while (cpw > 1 && (cpw >> 1) >= hp) { cpw >>= 1; --cps; }
+                const int rpi = 32 >> cps;
+                const int lr = lane >> cps, lc = lane & (cpw - 1);
                 for (int c0 = 0; c0 < hp; c0 += cpw) {
                     const int jp = c0 + lc;
                     if (jp < hp) {
@@ -352,20 +373,20 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
                     }
                 }
             }
-            cta_sync<THREADS>();
+            Sync::sync();
         } else {
             // -------- landmark insertion, :141-173
             if (fc.id_known) {
-                if (scalar_thread) {
+                if (nu_thread) {
                     double sb, cb; sincos(s.x[2] + (double)bb, &sb, &cb);
                     s.sc[SC_CB] = cb; s.sc[SC_SB] = sb;
                 }
-                cta_sync<THREADS>();
+                Sync::sync();
             }
             const double cb = s.sc[SC_CB], sb = s.sc[SC_SB];
             const double g02 = -(double)r * sb, g12 = (double)r * cb;      // G_x(0,2), G_x(1,2), :162,165
             // rows n, n+1 over old columns; columns n, n+1 over old rows
-            for (int j = tid; j < n; j += THREADS) {
+            for (int j = tid; j < n; j += NT) {
                 const double p0 = s.P[j], p1 = s.P[lds + j], p2 = s.P[2 * lds + j];
                 double t0 = 1.0 * p0; t0 += 0.0 * p1; t0 += g02 * p2;
                 double t1 = 0.0 * p0; t1 += 1.0 * p1; t1 += g12 * p2;
@@ -378,7 +399,7 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
                 s.P[(size_t)j * lds + n] = c0;
                 s.P[(size_t)j * lds + n + 1] = c1;
             }
-            if (scalar_thread) {
+            if (nu_thread) {
                 // new 2x2 block: G_x P_vv G_x^T + G_z W G_z^T, :155-172
                 const double gx[2][3] = {{1.0, 0.0, g02}, {0.0, 1.0, g12}};
                 const double gz[2][2] = {{cb, -(double)r * sb}, {sb, (double)r * cb}};
@@ -402,7 +423,7 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
                 s.ids[M] = id;                                             // :150
             }
             M += 1; n += 2;
-            cta_sync<THREADS>();
+            Sync::sync();
         }
     }
     return true;
@@ -459,17 +480,16 @@ __device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterCo
     for (int i = tid; i < n0; i += THREADS) { const double v = gx[i]; s.x[i] = v; s.xs[i] = v; }
     for (int i = tid; i < M; i += THREADS) s.ids[i] = b.ids[(size_t)inst * b.max_lm + i];
     for (int i = tid; i < 3 * nm; i += THREADS) s.meas[i] = in.meas[(size_t)inst * b.max_meas * 3 + i];
-    cta_sync<THREADS>();
+    CtaSync<THREADS>::sync();
     // ---- scalar pre-work while P is in flight
     if ((phases & STEP_PREDICT) && warp == WARPS - 1 && lane == 0)
         ekf_predict_scalars(fc, s, in.fwd[in.cmd_stride ? inst : 0], in.ang[in.cmd_stride ? inst : 0]);
     if ((phases & STEP_UPDATE) && fc.id_known && warp == 0) ekf_assoc_prepass(s, lane, M, nm, b.max_lm);
     mbar_wait(s.bar, parity);
-    cta_sync<THREADS>();
+    CtaSync<THREADS>::sync();
 
     int n_upd = 0;
-    bool intact = true;
-    const bool alive = ekf_core<THREADS>(fc, s, lds, b.max_lm, phases, M, nm, status, n_upd, intact);
+    const bool alive = ekf_core<THREADS, CtaSync<THREADS>>(fc, s, lds, b.max_lm, phases, M, nm, status, n_upd);
 
     // ---- commit, :176-177
     if (!alive) {
@@ -486,7 +506,7 @@ __device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterCo
     for (int i = tid + M_start; i < M; i += THREADS) b.ids[(size_t)inst * b.max_lm + i] = s.ids[i];
     for (int i = tid; i < nm; i += THREADS) { const int a = s.assoc[i]; b.assoc[(size_t)inst * b.max_meas + i] = a < 0 ? -1 : a; }
     fence_proxy_async();     // generic-proxy writes of P must be visible to the bulk-copy engine
-    cta_sync<THREADS>();
+    CtaSync<THREADS>::sync();
     if (warp == 0) {
         const int ldg = ldg_of(n);
         for (int row = lane; row < n; row += 32)
@@ -516,7 +536,7 @@ ekf_step_kernel(BatchState b, FilterConst fc, StepInputs in, int phases, EkfLaun
     EkfSmem s;
     ekf_smem_carve(b.max_meas, L, smem_raw, &s);
     if (threadIdx.x == 0) { mbar_init(s.bar, 1); fence_mbar_init(); }
-    cta_sync<THREADS>();
+    CtaSync<THREADS>::sync();
     if (!L.from_list) {
         ekf_instance<THREADS>(b, fc, in, phases, L, s, (int)blockIdx.x, 0u);
         return;
@@ -526,33 +546,51 @@ ekf_step_kernel(BatchState b, FilterConst fc, StepInputs in, int phases, EkfLaun
     uint32_t parity = 0;
     for (int q = blockIdx.x; q < count; q += gridDim.x) {
         if (ekf_instance<THREADS>(b, fc, in, phases, L, s, b.retry_list[q], parity)) parity ^= 1u;
-        cta_sync<THREADS>();
+        CtaSync<THREADS>::sync();
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // ekf_sweep_kernel: T consecutive reference steps of every instance in ONE launch -- simulator (sim_node.py:209-250)
 // -> EKF::update -> error terms -- with the filter resident in shared memory.  A persistent grid pulls instances
-// from a work counter.  Per step: the scalar warp simulates the vehicle and associates the message, one thread
-// evaluates the predict trigonometry, one thread folds the previous step's error terms; then ekf_core.
+// from a work counter.  CW consumer warps run the filter; one producer warp runs the simulator AHEAD of them
+// (messages double-buffered) and folds the error terms of the step they just finished (pose snapshot), so neither is
+// on the filter's critical path.  Named barriers: FULL[p] producer -> consumers "message of a step with parity p is
+// ready", DONE[p] consumers -> producer "step finished, snapshot[p] valid, message buffer p free".
 // Known-ID mode only (the host falls back to per-step launches otherwise): the pre-pass association detects a
 // same-step re-match before the step touches anything, so a dead instance stays at its committed state.
 // ------------------------------------------------------------------------------------------------------------
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 2)
+enum { BAR_CONS = 1, BAR_FULL0 = 2, BAR_FULL1 = 3, BAR_DONE0 = 4, BAR_DONE1 = 5 };
+
+struct SweepSmem {
+    float* meas[2];     // [max_meas][3] message of step parity p
+    int* nm;            // [2] detections of step parity p (clamped to max_meas)
+    double* snap;       // [2][12] pose (3) + pose covariance (9) after the step of parity p
+};
+
+__host__ __device__ inline size_t sweep_smem_carve(const int max_meas, unsigned char* base, size_t off, SweepSmem* w) {
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
+    size_t o0 = take(sizeof(float) * 3 * max_meas), o1 = take(sizeof(float) * 3 * max_meas);
+    size_t on = take(sizeof(int) * 4), os = take(sizeof(double) * 24);
+    if (w) { w->meas[0] = (float*)(base + o0); w->meas[1] = (float*)(base + o1); w->nm = (int*)(base + on); w->snap = (double*)(base + os); }
+    return off;
+}
+
+template <int CW>      // consumer warps; the CTA has CW + 1 warps
+__global__ void __launch_bounds__(32 * (CW + 1), 2)
 ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, const float* __restrict__ cmd_fwd,
                  const float* __restrict__ cmd_ang, const int cmd_stride, const int T, const uint32_t first_step,
                  int* work_counter, EkfLaunch L) {
-    constexpr int WARPS = THREADS / 32;
-    static_assert(WARPS >= 4, "the sweep kernel specialises three warps");
+    constexpr int NT = 32 * CW;                 // filter threads
+    constexpr int THREADS = NT + 32;
+    using Sync = NamedSync<NT, BAR_CONS>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EkfSmem s;
-    ekf_smem_carve(b.max_meas, L, smem_raw, &s);
+    SweepSmem w;
+    sweep_smem_carve(b.max_meas, smem_raw, ekf_smem_carve(b.max_meas, L, smem_raw, &s), &w);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lds = L.lds;
-    const bool sim_warp = warp == WARPS - 1;
-    const bool trig_thread = tid == 0;
-    const bool err_thread = tid == 32;
+    const bool producer = warp == CW;
     if (tid == 0) { mbar_init(s.bar, 1); fence_mbar_init(); }
     __syncthreads();
     uint32_t parity = 0;
@@ -563,117 +601,127 @@ ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, const 
         const int inst = s.iscr[IS_WORK];
         if (inst >= b.batch) break;
         const int4 meta_in = b.meta[inst];
-        int status = meta_in.y;
-        int M = meta_in.x;
-        const int M_first = M;
-        double* gP = b.P + (size_t)inst * b.p_stride;
-        double* gx = b.x + (size_t)inst * b.x_stride;
-        const int n0 = 3 + 2 * M;
-        {
-            const int ldg = ldg_of(n0);
-            if (warp == 0) {
-                if (lane == 0) { mbar_expect_tx(s.bar, (uint32_t)(n0 * ldg * sizeof(double))); s.iscr[IS_NAN] = 0; s.iscr[IS_DEAD] = 0; }
-                __syncwarp();
-                for (int row = lane; row < n0; row += 32)
-                    bulk_g2s(s.P + (size_t)row * lds, gP + (size_t)row * ldg, (uint32_t)(ldg * sizeof(double)), s.bar);
-            }
-        }
-        for (int i = tid; i < n0; i += THREADS) s.x[i] = gx[i];
-        for (int i = tid; i < M; i += THREADS) s.ids[i] = b.ids[(size_t)inst * b.max_lm + i];
-        double tr[3] = {0, 0, 0};                    // truth state, carried by the simulator warp
-        if (sim_warp) { const double* t = sim.truth + 3 * (size_t)inst; tr[0] = t[0]; tr[1] = t[1]; tr[2] = t[2]; }
-        double eacc[6] = {0, 0, 0, 0, 0, 0};         // error terms, carried by err_thread
-        double wacc[4] = {0, 0, 0, 0};               // work counters, carried by thread 0
-        int timestep = meta_in.z, nm = 0, overflow = 0;
-        mbar_wait(s.bar, parity);
-        parity ^= 1u;
-        __syncthreads();
+        const size_t cstep = cmd_stride ? (size_t)b.batch : 1, coff = cmd_stride ? (size_t)inst : 0;
 
-        for (int t = 0; t < T; ++t) {
-            const bool frozen = (status & SLAM_STATUS_SAME_STEP_REMATCH) != 0;
-            const float d_d = cmd_fwd[(size_t)t * (cmd_stride ? b.batch : 1) + (cmd_stride ? inst : 0)];
-            const float d_th = cmd_ang[(size_t)t * (cmd_stride ? b.batch : 1) + (cmd_stride ? inst : 0)];
-            // ---- phase 0: simulator + association | predict trigonometry | previous step's error terms | x_t snapshot
-            if (sim_warp) {
-                const int count = sim_get_cmd_warp(lane, sc, sim.lm_xy, sim.n_lm, b.max_meas, sim.k0, sim.k1,
-                                                   sim.instance_offset + (uint32_t)inst, first_step + (uint32_t)t, d_d, d_th,
-                                                   tr, s.meas);
-                if (count > b.max_meas) overflow = 1;
-                const int k = count < b.max_meas ? count : b.max_meas;
+        if (producer) {
+            // ================= producer warp: simulator ahead, error terms behind =================
+            double tr[3];
+            { const double* t = sim.truth + 3 * (size_t)inst; tr[0] = t[0]; tr[1] = t[1]; tr[2] = t[2]; }
+            double trp[2][3] = {{0, 0, 0}, {0, 0, 0}};   // truth of the step with parity p
+            double eacc[6] = {0, 0, 0, 0, 0, 0};
+            int overflow = 0, nm_last = 0;
+            for (int t = 0; t <= T; ++t) {
+                if (t < T) {
+                    const int p = t & 1;
+                    const int count = sim_get_cmd_warp(lane, sc, sim.lm_xy, sim.n_lm, b.max_meas, sim.k0, sim.k1,
+                                                       sim.instance_offset + (uint32_t)inst, first_step + (uint32_t)t,
+                                                       cmd_fwd[(size_t)t * cstep + coff], cmd_ang[(size_t)t * cstep + coff],
+                                                       tr, w.meas[p]);
+                    if (count > b.max_meas) overflow = 1;
+                    nm_last = count < b.max_meas ? count : b.max_meas;
+                    if (lane == 0) w.nm[p] = nm_last;
+                    trp[p][0] = tr[0]; trp[p][1] = tr[1]; trp[p][2] = tr[2];
+                    named_arrive(BAR_FULL0 + p, THREADS);
+                }
+                if (t >= 1) {
+                    const int q = (t - 1) & 1;
+                    named_sync(BAR_DONE0 + q, THREADS);          // step t-1 finished: snapshot[q] valid
+                    if (lane == 0) {
+                        const double* sn = w.snap + 12 * q;
+                        double C[3][3];
+                        for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) C[a][c] = sn[3 + 3 * a + c];
+                        pose_error_terms(sn[0] - trp[q][0], sn[1] - trp[q][1], wrap_2pi(sn[2] - trp[q][2]), C, eacc);
+                    }
+                }
+            }
+            if (T > 0) {
                 if (lane == 0) {
-                    s.iscr[IS_NM] = k;
-                    double* st = s.sc + SC_TR + 3 * (t & 1);
-                    st[0] = tr[0]; st[1] = tr[1]; st[2] = tr[2];
+                    double* g = b.stats + (size_t)inst * SLAM_NUM_STATS;
+                    for (int k = 0; k < 6; ++k) g[k] += eacc[k];
+                    double* tg = sim.truth + 3 * (size_t)inst;
+                    tg[0] = tr[0]; tg[1] = tr[1]; tg[2] = tr[2];
+                    sim.n_meas[inst] = nm_last;
+                    if (overflow) sim.overflow[inst] = 1;
                 }
-                __syncwarp();
-                if (!frozen) ekf_assoc_prepass(s, lane, M, k, b.max_lm);
+                const float* last = w.meas[(T - 1) & 1];
+                for (int i = lane; i < 3 * nm_last; i += 32) sim.meas[(size_t)inst * b.max_meas * 3 + i] = last[i];
             }
-            if (err_thread && t > 0) {
-                const double* st = s.sc + SC_TR + 3 * ((t - 1) & 1);
-                double C[3][3];
-                for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) C[a][c] = s.P[a * lds + c];
-                pose_error_terms(s.x[0] - st[0], s.x[1] - st[1], remainder(s.x[2] - st[2], TWO_PI_REF), C, eacc);
-            }
-            if (trig_thread && !frozen) ekf_predict_scalars(fc, s, d_d, d_th);
-            for (int i = tid; i < 3 + 2 * M; i += THREADS) s.xs[i] = s.x[i];
-            __syncthreads();
-            nm = s.iscr[IS_NM];
-            if (!frozen) {
-                int n_upd = 0;
-                bool intact = true;
-                if (ekf_core<THREADS>(fc, s, lds, b.max_lm, STEP_PREDICT | STEP_UPDATE, M, nm, status, n_upd, intact)) {
-                    ++timestep;
-                    if (tid == 0) ekf_work_terms(3 + 2 * M, nm, n_upd, wacc);
+        } else {
+            // ================= consumer warps: the filter =================
+            int status = meta_in.y;
+            int M = meta_in.x;
+            const int M_first = M;
+            double* gP = b.P + (size_t)inst * b.p_stride;
+            double* gx = b.x + (size_t)inst * b.x_stride;
+            const int n0 = 3 + 2 * M;
+            {
+                const int ldg = ldg_of(n0);
+                if (warp == 0) {
+                    if (lane == 0) { mbar_expect_tx(s.bar, (uint32_t)(n0 * ldg * sizeof(double))); s.iscr[IS_NAN] = 0; s.iscr[IS_DEAD] = 0; }
+                    __syncwarp();
+                    for (int row = lane; row < n0; row += 32)
+                        bulk_g2s(s.P + (size_t)row * lds, gP + (size_t)row * ldg, (uint32_t)(ldg * sizeof(double)), s.bar);
                 }
             }
-        }
-        // ---- error terms of the last step, then commit the instance
-        if (err_thread && T > 0) {
-            const double* st = s.sc + SC_TR + 3 * ((T - 1) & 1);
-            double C[3][3];
-            for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) C[a][c] = s.P[a * lds + c];
-            pose_error_terms(s.x[0] - st[0], s.x[1] - st[1], remainder(s.x[2] - st[2], TWO_PI_REF), C, eacc);
-            double* g = b.stats + (size_t)inst * SLAM_NUM_STATS;
-            for (int k = 0; k < 6; ++k) g[k] += eacc[k];
-        }
-        const int n = 3 + 2 * M;
-        for (int i = tid; i < n; i += THREADS) {
-            const double v = s.x[i];
-            gx[i] = v;
-            if (!isfinite(v) || !isfinite(s.P[(size_t)i * lds + i])) s.iscr[IS_NAN] = 1;
-        }
-        for (int i = tid + M_first; i < M; i += THREADS) b.ids[(size_t)inst * b.max_lm + i] = s.ids[i];
-        if (T > 0) {
-            const bool frozen = (status & SLAM_STATUS_SAME_STEP_REMATCH) != 0;
-            for (int i = tid; i < nm; i += THREADS) {
-                const int a = s.assoc[i];
-                if (!frozen) b.assoc[(size_t)inst * b.max_meas + i] = a < 0 ? -1 : a;
+            for (int i = tid; i < n0; i += NT) s.x[i] = gx[i];
+            for (int i = tid; i < M; i += NT) s.ids[i] = b.ids[(size_t)inst * b.max_lm + i];
+            double wacc[4] = {0, 0, 0, 0};               // work counters, carried by thread 0
+            int timestep = meta_in.z, nm = 0;
+            mbar_wait(s.bar, parity);
+            Sync::sync();
+
+            for (int t = 0; t < T; ++t) {
+                const int p = t & 1;
+                const bool frozen = (status & SLAM_STATUS_SAME_STEP_REMATCH) != 0;
+                named_sync(BAR_FULL0 + p, THREADS);              // message of step t is in w.meas[p]
+                nm = w.nm[p];
+                if (!frozen) {
+                    s.meas = w.meas[p];
+                    // ---- phase 0: association (warp 0) | predict trigonometry (last warp) | x_t snapshot
+                    if (warp == 0) ekf_assoc_prepass(s, lane, M, nm, b.max_lm);
+                    if (warp == CW - 1 && lane == 0)
+                        ekf_predict_scalars(fc, s, cmd_fwd[(size_t)t * cstep + coff], cmd_ang[(size_t)t * cstep + coff]);
+                    for (int i = tid; i < 3 + 2 * M; i += NT) s.xs[i] = s.x[i];
+                    Sync::sync();
+                    int n_upd = 0;
+                    if (ekf_core<NT, Sync>(fc, s, lds, b.max_lm, STEP_PREDICT | STEP_UPDATE, M, nm, status, n_upd)) {
+                        ++timestep;
+                        if (tid == 0) ekf_work_terms(3 + 2 * M, nm, n_upd, wacc);
+                    }
+                }
+                // pose snapshot for the error terms (the producer folds it while the next step runs)
+                if (tid < 12) w.snap[12 * p + tid] = (tid < 3) ? s.x[tid] : s.P[((tid - 3) / 3) * lds + (tid - 3) % 3];
+                named_arrive(BAR_DONE0 + p, THREADS);
             }
-            for (int i = tid; i < 3 * nm; i += THREADS) sim.meas[(size_t)inst * b.max_meas * 3 + i] = s.meas[i];
-        }
-        if (sim_warp && lane == 0 && T > 0) {
-            double* tg = sim.truth + 3 * (size_t)inst;
-            tg[0] = tr[0]; tg[1] = tr[1]; tg[2] = tr[2];
-            sim.n_meas[inst] = nm;
-            if (overflow) sim.overflow[inst] = 1;
-        }
-        fence_proxy_async();
-        __syncthreads();
-        if (warp == 0) {
-            const int ldg = ldg_of(n);
-            for (int row = lane; row < n; row += 32)
-                bulk_s2g(gP + (size_t)row * ldg, s.P + (size_t)row * lds, (uint32_t)(ldg * sizeof(double)));
-            bulk_commit();
-        }
-        if (tid == 0) {
-            if (s.iscr[IS_NAN]) status |= SLAM_STATUS_NAN;
+            // ---- commit the instance
             const bool frozen = (status & SLAM_STATUS_SAME_STEP_REMATCH) != 0;
-            b.meta[inst] = make_int4(M, status, timestep, (T > 0 && !frozen) ? nm : (frozen ? 0 : meta_in.w));
-            if (M > M_first) atomicMax(b.max_M, M);
-            double* st = b.stats + (size_t)inst * SLAM_NUM_STATS;
-            st[8] += wacc[0]; st[9] += wacc[1]; st[10] += wacc[2]; st[11] += wacc[3];
+            const int n = 3 + 2 * M;
+            for (int i = tid; i < n; i += NT) {
+                const double v = s.x[i];
+                gx[i] = v;
+                if (!isfinite(v) || !isfinite(s.P[(size_t)i * lds + i])) s.iscr[IS_NAN] = 1;
+            }
+            for (int i = tid + M_first; i < M; i += NT) b.ids[(size_t)inst * b.max_lm + i] = s.ids[i];
+            if (T > 0 && !frozen)
+                for (int i = tid; i < nm; i += NT) { const int a = s.assoc[i]; b.assoc[(size_t)inst * b.max_meas + i] = a < 0 ? -1 : a; }
+            fence_proxy_async();
+            Sync::sync();
+            if (warp == 0) {
+                const int ldg = ldg_of(n);
+                for (int row = lane; row < n; row += 32)
+                    bulk_s2g(gP + (size_t)row * ldg, s.P + (size_t)row * lds, (uint32_t)(ldg * sizeof(double)));
+                bulk_commit();
+            }
+            if (tid == 0) {
+                if (s.iscr[IS_NAN]) status |= SLAM_STATUS_NAN;
+                b.meta[inst] = make_int4(M, status, timestep, (T > 0 && !frozen) ? nm : (frozen ? 0 : meta_in.w));
+                if (M > M_first) atomicMax(b.max_M, M);
+                double* st = b.stats + (size_t)inst * SLAM_NUM_STATS;
+                st[8] += wacc[0]; st[9] += wacc[1]; st[10] += wacc[2]; st[11] += wacc[3];
+            }
+            if (warp == 0) bulk_wait_read();    // the tile is re-filled by the next instance
         }
-        if (warp == 0) bulk_wait_read();    // the tile is re-filled by the next instance
+        parity ^= 1u;
         __syncthreads();
     }
 }
@@ -737,8 +785,10 @@ cudaError_t ekf_step_configure(const BatchState& b) {
     if ((e = set_smem_step<128>(bytes)) != cudaSuccess) return e;
     if ((e = set_smem_step<256>(bytes)) != cudaSuccess) return e;
     if ((e = set_smem_step<512>(bytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ekf_sweep_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(ekf_sweep_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    const int sbytes = (int)sweep_smem_carve(b.max_meas, nullptr, (size_t)bytes, nullptr);
+    if ((e = cudaFuncSetAttribute(ekf_sweep_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sbytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ekf_sweep_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sbytes)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(ekf_sweep_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, sbytes);
 }
 
 static cudaError_t launch_step_threads(int threads, int grid, size_t smem, cudaStream_t st, const BatchState& b,
@@ -779,15 +829,17 @@ cudaError_t launch_ekf_sweep(const BatchState& b, const FilterConst& fc, const S
                              const float* d_fwd, const float* d_ang, int cmd_stride, int T, uint32_t first_step,
                              int* work_counter, int force_threads, cudaStream_t st) {
     const EkfLaunch L = make_launch(b, b.max_lm, 0);
-    const size_t smem = ekf_smem_carve(b.max_meas, L, nullptr, nullptr);
+    const size_t smem = sweep_smem_carve(b.max_meas, nullptr, ekf_smem_carve(b.max_meas, L, nullptr, nullptr), nullptr);
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     int per_sm = (int)(SMEM_PER_SM / (smem + SMEM_CTA_RESERVED));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 2) per_sm = 2;
     const int grid = b.batch < 148 * per_sm ? b.batch : 148 * per_sm;
-    if (force_threads == 512) ekf_sweep_kernel<512><<<grid, 512, smem, st>>>(b, fc, sim, sc, d_fwd, d_ang, cmd_stride, T, first_step, work_counter, L);
-    else ekf_sweep_kernel<256><<<grid, 256, smem, st>>>(b, fc, sim, sc, d_fwd, d_ang, cmd_stride, T, first_step, work_counter, L);
+    // force_threads selects the number of filter warps (128 -> 4, 512 -> 12, else 8); one more warp runs the simulator
+    if (force_threads == 128) ekf_sweep_kernel<4><<<grid, 160, smem, st>>>(b, fc, sim, sc, d_fwd, d_ang, cmd_stride, T, first_step, work_counter, L);
+    else if (force_threads == 512) ekf_sweep_kernel<12><<<grid, 416, smem, st>>>(b, fc, sim, sc, d_fwd, d_ang, cmd_stride, T, first_step, work_counter, L);
+    else ekf_sweep_kernel<8><<<grid, 288, smem, st>>>(b, fc, sim, sc, d_fwd, d_ang, cmd_stride, T, first_step, work_counter, L);
     return cudaGetLastError();
 }
 

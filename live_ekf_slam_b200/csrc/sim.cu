@@ -64,7 +64,7 @@ __global__ void accumulate_error_kernel(BatchState b, SimState s) {
             C[a][c] = t;
         }
     }
-    const double ex = x[0] - tr[0], ey = x[1] - tr[1], eyaw = remainder(yaw - tr[2], TWO_PI_REF);
+    const double ex = x[0] - tr[0], ey = x[1] - tr[1], eyaw = wrap_2pi(yaw - tr[2]);
     double acc[6] = {0, 0, 0, 0, 0, 0};
     pose_error_terms(ex, ey, eyaw, C, acc);
     double* st = b.stats + (size_t)i * SLAM_NUM_STATS;

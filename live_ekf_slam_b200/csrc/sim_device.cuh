@@ -34,7 +34,7 @@ __device__ __forceinline__ int sim_get_cmd_warp(const int lane, const SimConst& 
             const double dx = lm_xy[2 * id] - tx, dy = lm_xy[2 * id + 1] - ty;
             r = sqrt(dx * dx + dy * dy);                                    // :235
             if (!(r > sc.range_max)) {                                      // :239 (the bearing only matters in range)
-                beta = remainder(atan2(dy, dx) - tyaw, TWO_PI_REF);         // :236-237
+                beta = wrap_2pi(atan2(dy, dx) - tyaw);                   // :236-237
                 vis = beta > sc.fov_min && beta < sc.fov_max;               // :240-241
             }
         }
