@@ -42,6 +42,8 @@ struct slam_filter {
     int cap_force = 0;                // > 0: force this capacity for the first pass (tests of the retry path)
     int force_threads = 0;            // > 0: CTA width of the EKF kernels (tuning)
     int sweep_off = 0;                // 1: slam_run* always uses per-step launches (tests compare both paths)
+    int step_mode = 0;                // EKF per-step kernel: 0/1 shared-memory-resident (default), 2 row-streaming (known IDs)
+    bool stream_ok = false;           // ekf_stream_kernel usable for this handle
     int* d_work = nullptr;            // work counter of the persistent sweep kernel
     bool profiling = false;           // per-launch events around the per-step filter kernel
     bool profiling_sweep = false;     // events around the persistent sweep kernel
@@ -116,7 +118,7 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
     b.x_stride = ldg_of(b.n_max);
     b.p_stride = (long long)b.n_max * ldg_of(b.n_max);
     b.sigma_stride = 0;
-    b.fixed_ld = (kind == SLAM_UKF_SLAM) ? ldg_of(b.n_max) : 0;
+    b.fixed_ld = ldg_of(b.n_max);      // rows of P keep a fixed stride in HBM; only the live n x ldg(n) part is ever moved
 
     const size_t smem = (kind == SLAM_EKF_SLAM) ? ekf_step_smem_bytes(b) : ukf_step_smem_bytes(b);
     if (smem > (size_t)prop.sharedMemPerBlockOptin) {
@@ -166,7 +168,11 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
         CK(cudaMalloc(&g.sc, sizeof(double) * 16));
         CK(cudaMemset(g.cur, 0, sizeof(int) * 16));
         CK(cudaMallocHost(&h->h_nmeas_pin, sizeof(int)));
-    } else if (kind == SLAM_EKF_SLAM) CK(ekf_step_configure(b)); else CK(ukf_step_configure(b));
+    } else if (kind == SLAM_EKF_SLAM) {
+        CK(ekf_step_configure(b));
+        h->stream_ok = fc.id_known && ekf_stream_supported(b);
+        if (h->stream_ok) CK(ekf_stream_configure(b));
+    } else CK(ukf_step_configure(b));
     *out = h;
     return slam_init(h, 0.f, 0.f, 0.f);
 }
@@ -206,6 +212,10 @@ int slam_tune(slam_handle_t h, int key, int value) {
             return fail(h, "slam_tune: CTA width must be 0 (automatic), 32, 64, 128, 256 or 512");
         h->force_threads = value;
     } else if (key == 3) h->sweep_off = value;
+    else if (key == 4) {
+        if (value == 2 && !h->stream_ok) return fail(h, "slam_tune: the HBM-streaming EKF kernel needs known landmark IDs and 3 + 2*max_landmarks <= 126");
+        h->step_mode = value;
+    }
     else return fail(h, "slam_tune: unknown key");
     return 0;
 }
@@ -290,7 +300,10 @@ static int do_step(slam_filter* h, const float* d_fwd, const float* d_ang, int c
         CK(cudaEventSynchronize(h->hint_ev[slot]));
         cap = h->h_hint[slot] + h->cap_headroom;
     } else cap = h->hint_base + (int)(h->step_seq + 1) * h->b.max_meas;      // M can grow by at most max_meas per step
-    if (h->kind == SLAM_EKF_SLAM) CK(launch_ekf_step(h->b, h->fc, in, phases, cap, h->force_threads, h->stream));
+    if (h->kind == SLAM_EKF_SLAM) {
+        if (h->stream_ok && h->step_mode == 2) CK(launch_ekf_stream_step(h->b, h->fc, in, phases, cap, h->stream));
+        else CK(launch_ekf_step(h->b, h->fc, in, phases, cap, h->force_threads, h->stream));
+    }
     else CK(launch_ukf_step(h->b, h->fc, in, h->stream));
     if (h->profiling) { CK(cudaEventRecord(h->ev[h->ev_used + 1], h->stream)); h->ev_used += 2; }
     {

@@ -14,9 +14,10 @@ namespace slam {
 // ---------------------------------------------------------------------------------------------
 // HBM layout of a batch of filter instances (all arrays are struct-of-arrays over instances).
 //
-//   P      [batch][p_stride]   covariance, row-major, PACKED with leading dimension ldg(n) =
-//                              n rounded up to even (rows are 16-byte multiples so every row is one
-//                              cp.async.bulk); only n*ldg(n) doubles are live and only they cross HBM.
+//   P      [batch][p_stride]   covariance, row-major with the fixed leading dimension ldg(n_max); the live
+//                              part of a row is its first ldg(n) = n rounded up to even doubles (a 16-byte
+//                              multiple: one cp.async.bulk / whole double2 loads), so only n*ldg(n) doubles
+//                              cross HBM per step.
 //   x      [batch][x_stride]   committed state x_t (EKF: x,y,yaw,lm.. ; UKF: x,y,cos,sin,lm..)
 //   ids    [batch][max_lm]     lm_IDs (filter.h:70)
 //   meta   [batch] int4 {M, status, timestep, n_assoc}
@@ -42,7 +43,7 @@ struct BatchState {
     int base;          // 3 (EKF) or 4 (UKF)
     int n_max;         // base + 2*max_lm
     int lds;           // shared-memory leading dimension of P
-    int fixed_ld;      // 0: P packed with ldg(n) (EKF, streamed every step); else fixed global leading dimension (UKF)
+    int fixed_ld;      // global leading dimension of P (ldg(n_max)); a live row is its first ldg(n) doubles
 };
 
 // Effective filter constants after readCommonParams (filter.h:105-121).
@@ -161,6 +162,12 @@ cudaError_t launch_ekf_step(const BatchState& b, const FilterConst& fc, const St
                             int force_threads, cudaStream_t st);
 size_t ekf_step_smem_bytes(const BatchState& b);
 cudaError_t ekf_step_configure(const BatchState& b);
+
+// HBM-streaming EKF step (known IDs; csrc/ekf_stream.cu)
+bool ekf_stream_supported(const BatchState& b);
+cudaError_t ekf_stream_configure(const BatchState& b);
+cudaError_t launch_ekf_stream_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, int phases, int cap_hint,
+                                   cudaStream_t st);
 
 cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, cudaStream_t st);
 size_t ukf_step_smem_bytes(const BatchState& b);

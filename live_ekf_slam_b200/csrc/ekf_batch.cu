@@ -37,6 +37,9 @@ struct EkfLaunch {
     int n_cap;         // 3 + 2*cap_lm
     int lds;           // shared-memory leading dimension for n_cap
     int from_list;     // 0: instance = blockIdx.x ; 1: instances come from b.retry_list (persistent loop)
+    int off[16];       // shared-memory byte offsets (laid out on the host: the kernels add constant-bank offsets)
+    int smem_bytes;    // step kernel's dynamic shared memory
+    int sweep_bytes;   // sweep kernel's (step layout + message double buffer + pose snapshots)
 };
 
 struct EkfSmem {
@@ -53,28 +56,36 @@ struct EkfSmem {
     uint64_t* bar;
 };
 
-__host__ __device__ inline size_t ekf_smem_carve(const int max_meas, const EkfLaunch& L, unsigned char* base, EkfSmem* s) {
+enum { EO_P = 0, EO_X, EO_XS, EO_HP, EO_K, EO_SC, EO_IDS, EO_MEAS, EO_ASSOC, EO_ISCR, EO_BAR, EO_WM0, EO_WM1, EO_WNM, EO_WSNAP };
+
+static void ekf_smem_layout(const int max_meas, EkfLaunch& L) {
     size_t off = 0;
-    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return (int)o; };
     const int nmp = ldg_of(L.n_cap);
-    size_t oP = take(sizeof(double) * (size_t)L.n_cap * L.lds);
-    size_t ox = take(sizeof(double) * nmp);
-    size_t oxs = take(sizeof(double) * nmp);
-    size_t oHP = take(sizeof(double) * 2 * L.lds);
-    size_t oK = take(sizeof(double) * 2 * nmp);
-    size_t osc = take(sizeof(double) * 24);
-    size_t oids = take(sizeof(int) * (L.cap_lm + 1));
-    size_t omeas = take(sizeof(float) * 3 * max_meas);
-    size_t oassoc = take(sizeof(int) * max_meas);
-    size_t oi = take(sizeof(int) * 8);
-    size_t obar = take(sizeof(uint64_t));
-    if (s) {
-        s->P = (double*)(base + oP); s->x = (double*)(base + ox); s->xs = (double*)(base + oxs);
-        s->HP = (double*)(base + oHP); s->K = (double*)(base + oK);
-        s->sc = (double*)(base + osc); s->ids = (int*)(base + oids); s->meas = (float*)(base + omeas);
-        s->assoc = (int*)(base + oassoc); s->iscr = (int*)(base + oi); s->bar = (uint64_t*)(base + obar);
-    }
-    return off;
+    L.off[EO_P] = take(sizeof(double) * (size_t)L.n_cap * L.lds);
+    L.off[EO_X] = take(sizeof(double) * nmp);
+    L.off[EO_XS] = take(sizeof(double) * nmp);
+    L.off[EO_HP] = take(sizeof(double) * 2 * L.lds);
+    L.off[EO_K] = take(sizeof(double) * 2 * nmp);
+    L.off[EO_SC] = take(sizeof(double) * 24);
+    L.off[EO_IDS] = take(sizeof(int) * (L.cap_lm + 1));
+    L.off[EO_MEAS] = take(sizeof(float) * 3 * max_meas);
+    L.off[EO_ASSOC] = take(sizeof(int) * max_meas);
+    L.off[EO_ISCR] = take(sizeof(int) * 8);
+    L.off[EO_BAR] = take(sizeof(uint64_t));
+    L.smem_bytes = (int)off;
+    L.off[EO_WM0] = take(sizeof(float) * 3 * max_meas);
+    L.off[EO_WM1] = take(sizeof(float) * 3 * max_meas);
+    L.off[EO_WNM] = take(sizeof(int) * 4);
+    L.off[EO_WSNAP] = take(sizeof(double) * 24);
+    L.sweep_bytes = (int)off;
+}
+
+__device__ __forceinline__ void ekf_smem_bind(const EkfLaunch& L, unsigned char* base, EkfSmem& s) {
+    s.P = (double*)(base + L.off[EO_P]); s.x = (double*)(base + L.off[EO_X]); s.xs = (double*)(base + L.off[EO_XS]);
+    s.HP = (double*)(base + L.off[EO_HP]); s.K = (double*)(base + L.off[EO_K]); s.sc = (double*)(base + L.off[EO_SC]);
+    s.ids = (int*)(base + L.off[EO_IDS]); s.meas = (float*)(base + L.off[EO_MEAS]); s.assoc = (int*)(base + L.off[EO_ASSOC]);
+    s.iscr = (int*)(base + L.off[EO_ISCR]); s.bar = (uint64_t*)(base + L.off[EO_BAR]);
 }
 
 // scalar slots in sc[]
@@ -473,7 +484,7 @@ __device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterCo
             if (lane == 0) { mbar_expect_tx(s.bar, (uint32_t)(n0 * ldg * sizeof(double))); s.iscr[IS_NAN] = 0; s.iscr[IS_DEAD] = 0; }
             __syncwarp();
             for (int row = lane; row < n0; row += 32)
-                bulk_g2s(s.P + (size_t)row * lds, gP + (size_t)row * ldg, (uint32_t)(ldg * sizeof(double)), s.bar);
+                bulk_g2s(s.P + (size_t)row * lds, gP + (size_t)row * b.fixed_ld, (uint32_t)(ldg * sizeof(double)), s.bar);
         }
     }
     // ---- meanwhile: state, ids, messages
@@ -485,7 +496,7 @@ __device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterCo
     if ((phases & STEP_PREDICT) && warp == WARPS - 1 && lane == 0)
         ekf_predict_scalars(fc, s, in.fwd[in.cmd_stride ? inst : 0], in.ang[in.cmd_stride ? inst : 0]);
     if ((phases & STEP_UPDATE) && fc.id_known && warp == 0) ekf_assoc_prepass(s, lane, M, nm, b.max_lm);
-    mbar_wait(s.bar, parity);
+    if (warp == 0) mbar_wait(s.bar, parity);     // one warp polls the mbarrier; the others park at the CTA barrier
     CtaSync<THREADS>::sync();
 
     int n_upd = 0;
@@ -510,7 +521,7 @@ __device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterCo
     if (warp == 0) {
         const int ldg = ldg_of(n);
         for (int row = lane; row < n; row += 32)
-            bulk_s2g(gP + (size_t)row * ldg, s.P + (size_t)row * lds, (uint32_t)(ldg * sizeof(double)));
+            bulk_s2g(gP + (size_t)row * b.fixed_ld, s.P + (size_t)row * lds, (uint32_t)(ldg * sizeof(double)));
         bulk_commit();
     }
     if (tid == 0) {
@@ -534,7 +545,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 ekf_step_kernel(BatchState b, FilterConst fc, StepInputs in, int phases, EkfLaunch L) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EkfSmem s;
-    ekf_smem_carve(b.max_meas, L, smem_raw, &s);
+    ekf_smem_bind(L, smem_raw, s);
     if (threadIdx.x == 0) { mbar_init(s.bar, 1); fence_mbar_init(); }
     CtaSync<THREADS>::sync();
     if (!L.from_list) {
@@ -568,12 +579,9 @@ struct SweepSmem {
     double* snap;       // [2][12] pose (3) + pose covariance (9) after the step of parity p
 };
 
-__host__ __device__ inline size_t sweep_smem_carve(const int max_meas, unsigned char* base, size_t off, SweepSmem* w) {
-    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
-    size_t o0 = take(sizeof(float) * 3 * max_meas), o1 = take(sizeof(float) * 3 * max_meas);
-    size_t on = take(sizeof(int) * 4), os = take(sizeof(double) * 24);
-    if (w) { w->meas[0] = (float*)(base + o0); w->meas[1] = (float*)(base + o1); w->nm = (int*)(base + on); w->snap = (double*)(base + os); }
-    return off;
+__device__ __forceinline__ void sweep_smem_bind(const EkfLaunch& L, unsigned char* base, SweepSmem& w) {
+    w.meas[0] = (float*)(base + L.off[EO_WM0]); w.meas[1] = (float*)(base + L.off[EO_WM1]);
+    w.nm = (int*)(base + L.off[EO_WNM]); w.snap = (double*)(base + L.off[EO_WSNAP]);
 }
 
 template <int CW>      // consumer warps; the CTA has CW + 1 warps
@@ -587,7 +595,8 @@ ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, const 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EkfSmem s;
     SweepSmem w;
-    sweep_smem_carve(b.max_meas, smem_raw, ekf_smem_carve(b.max_meas, L, smem_raw, &s), &w);
+    ekf_smem_bind(L, smem_raw, s);
+    sweep_smem_bind(L, smem_raw, w);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lds = L.lds;
     const bool producer = warp == CW;
@@ -660,14 +669,14 @@ ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, const 
                     if (lane == 0) { mbar_expect_tx(s.bar, (uint32_t)(n0 * ldg * sizeof(double))); s.iscr[IS_NAN] = 0; s.iscr[IS_DEAD] = 0; }
                     __syncwarp();
                     for (int row = lane; row < n0; row += 32)
-                        bulk_g2s(s.P + (size_t)row * lds, gP + (size_t)row * ldg, (uint32_t)(ldg * sizeof(double)), s.bar);
+                        bulk_g2s(s.P + (size_t)row * lds, gP + (size_t)row * b.fixed_ld, (uint32_t)(ldg * sizeof(double)), s.bar);
                 }
             }
             for (int i = tid; i < n0; i += NT) s.x[i] = gx[i];
             for (int i = tid; i < M; i += NT) s.ids[i] = b.ids[(size_t)inst * b.max_lm + i];
             double wacc[4] = {0, 0, 0, 0};               // work counters, carried by thread 0
             int timestep = meta_in.z, nm = 0;
-            mbar_wait(s.bar, parity);
+            if (warp == 0) mbar_wait(s.bar, parity);
             Sync::sync();
 
             for (int t = 0; t < T; ++t) {
@@ -709,7 +718,7 @@ ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, const 
             if (warp == 0) {
                 const int ldg = ldg_of(n);
                 for (int row = lane; row < n; row += 32)
-                    bulk_s2g(gP + (size_t)row * ldg, s.P + (size_t)row * lds, (uint32_t)(ldg * sizeof(double)));
+                    bulk_s2g(gP + (size_t)row * b.fixed_ld, s.P + (size_t)row * lds, (uint32_t)(ldg * sizeof(double)));
                 bulk_commit();
             }
             if (tid == 0) {
@@ -755,10 +764,11 @@ static EkfLaunch make_launch(const BatchState& b, int cap_lm, int from_list) {
     L.n_cap = 3 + 2 * L.cap_lm;
     L.lds = lds_of(L.n_cap);
     L.from_list = from_list;
+    ekf_smem_layout(b.max_meas, L);
     return L;
 }
 
-size_t ekf_step_smem_bytes(const BatchState& b) { return ekf_smem_carve(b.max_meas, make_launch(b, b.max_lm, 0), nullptr, nullptr); }
+size_t ekf_step_smem_bytes(const BatchState& b) { return (size_t)make_launch(b, b.max_lm, 0).smem_bytes; }
 
 static constexpr size_t SMEM_PER_SM = 227 * 1024, SMEM_CTA_RESERVED = 1024;
 
@@ -785,7 +795,7 @@ cudaError_t ekf_step_configure(const BatchState& b) {
     if ((e = set_smem_step<128>(bytes)) != cudaSuccess) return e;
     if ((e = set_smem_step<256>(bytes)) != cudaSuccess) return e;
     if ((e = set_smem_step<512>(bytes)) != cudaSuccess) return e;
-    const int sbytes = (int)sweep_smem_carve(b.max_meas, nullptr, (size_t)bytes, nullptr);
+    const int sbytes = make_launch(b, b.max_lm, 0).sweep_bytes;
     if ((e = cudaFuncSetAttribute(ekf_sweep_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sbytes)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ekf_sweep_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sbytes)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(ekf_sweep_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, sbytes);
@@ -809,7 +819,7 @@ cudaError_t launch_ekf_step(const BatchState& b, const FilterConst& fc, const St
                             int force_threads, cudaStream_t st) {
     const bool limited = cap_hint > 0 && cap_hint < b.max_lm;
     const EkfLaunch L = make_launch(b, limited ? cap_hint : b.max_lm, 0);
-    const size_t smem = ekf_smem_carve(b.max_meas, L, nullptr, nullptr);
+    const size_t smem = (size_t)L.smem_bytes;
     if (limited) {
         cudaError_t e = cudaMemsetAsync(b.retry_count, 0, sizeof(int), st);
         if (e != cudaSuccess) return e;
@@ -817,7 +827,7 @@ cudaError_t launch_ekf_step(const BatchState& b, const FilterConst& fc, const St
     cudaError_t e = launch_step_threads(force_threads ? force_threads : pick_threads(smem), b.batch, smem, st, b, fc, in, phases, L);
     if (e != cudaSuccess || !limited) return e;
     const EkfLaunch R = make_launch(b, b.max_lm, 1);
-    const size_t rsmem = ekf_smem_carve(b.max_meas, R, nullptr, nullptr);
+    const size_t rsmem = (size_t)R.smem_bytes;
     const int rthreads = force_threads ? force_threads : pick_threads(rsmem);
     const int per_sm = (int)(SMEM_PER_SM / (rsmem + SMEM_CTA_RESERVED)) > 0 ? (int)(SMEM_PER_SM / (rsmem + SMEM_CTA_RESERVED)) : 1;
     const int grid = b.batch < 148 * per_sm ? b.batch : 148 * per_sm;
@@ -829,7 +839,7 @@ cudaError_t launch_ekf_sweep(const BatchState& b, const FilterConst& fc, const S
                              const float* d_fwd, const float* d_ang, int cmd_stride, int T, uint32_t first_step,
                              int* work_counter, int force_threads, cudaStream_t st) {
     const EkfLaunch L = make_launch(b, b.max_lm, 0);
-    const size_t smem = sweep_smem_carve(b.max_meas, nullptr, ekf_smem_carve(b.max_meas, L, nullptr, nullptr), nullptr);
+    const size_t smem = (size_t)L.sweep_bytes;
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     int per_sm = (int)(SMEM_PER_SM / (smem + SMEM_CTA_RESERVED));

@@ -63,12 +63,16 @@ def test_config1_single_instance_per_step(shim, oracle):
     print("config1 worst normwise err", worst, "final M", of.M)
 
 
-def test_batch_free_running_grid(shim, oracle):
-    """BASELINE config 2 at reduced size: 48 instances on the 5x10 grid, 400 steps, free running."""
+@pytest.mark.parametrize("step_mode", [1, 2])
+def test_batch_free_running_grid(shim, oracle, step_mode):
+    """BASELINE config 2 at reduced size: 48 instances on the 5x10 grid, 400 steps, free running.
+    step_mode 1 = shared-memory-resident ekf_step_kernel, 2 = HBM-streaming ekf_stream_kernel (the default for
+    known landmark IDs)."""
     p, lm, fwd, ang = H.config2(seed=1, steps=400)
     op = H.oracle_params(oracle, p)
     B = 48
     fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), B, 50, 8)
+    fb.tune(4, step_mode)
     fb.init(0, 0, 0)
     streams = [H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=7, instance=i)[0] for i in range(B)]
     ofs = []
@@ -94,7 +98,8 @@ def test_batch_free_running_grid(shim, oracle):
     print("batch worst normwise err", worst)
 
 
-def test_teacher_forced_single_steps(shim, oracle):
+@pytest.mark.parametrize("step_mode", [1, 2])
+def test_teacher_forced_single_steps(shim, oracle, step_mode):
     """Load the oracle's (x, P, ids) of step t into the GPU filter, run ONE step, compare (SURVEY App. E protocol)."""
     p, lm, fwd, ang = H.config2(seed=2, steps=300)
     op = H.oracle_params(oracle, p)
@@ -102,6 +107,7 @@ def test_teacher_forced_single_steps(shim, oracle):
     of = oracle.OracleFilter(oracle.EKF_SLAM, op, 50)
     of.init(0, 0, 0)
     fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 2, 50, 8)
+    fb.tune(4, step_mode)
     fb.init(0, 0, 0)
     checked = 0
     for t in range(len(fwd)):
@@ -118,13 +124,16 @@ def test_teacher_forced_single_steps(shim, oracle):
     assert checked >= 10
 
 
-def test_split_predict_update_matches_fused(shim, oracle):
+@pytest.mark.parametrize("step_mode", [1, 2])
+def test_split_predict_update_matches_fused(shim, oracle, step_mode):
     p, lm, fwd, ang = H.config2(seed=4, steps=120)
     op = H.oracle_params(oracle, p)
     stream, _ = H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=9, instance=0)
     fused = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 1, 50, 8)
     split = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 1, 50, 8)
     of = oracle.OracleFilter(oracle.EKF_SLAM, op, 50)
+    fused.tune(4, step_mode)
+    split.tune(4, step_mode)
     for f in (fused, split, of):
         f.init(0, 0, 0)
     for t in range(len(fwd)):
@@ -166,11 +175,13 @@ def test_unknown_id_box_gate_association(shim, oracle):
     assert matched > 50
 
 
-def test_edge_cases(shim, oracle):
+@pytest.mark.parametrize("step_mode", [1, 2])
+def test_edge_cases(shim, oracle, step_mode):
     p = H.Params()
     op = H.oracle_params(oracle, p)
     # (a) no detections at all: predict-only steps (ekf.cpp:67-71)
     fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 3, 2, 2)
+    fb.tune(4, step_mode)
     fb.init(0.5, -0.25, 0.3)
     of = oracle.OracleFilter(oracle.EKF_SLAM, op, 2)
     of.init(0.5, -0.25, 0.3)
@@ -249,8 +260,9 @@ def test_filter_classes_mirror_reference_interface(shim, oracle):
         make_filter(bad)
 
 
+@pytest.mark.parametrize("step_mode", [1, 2])
 @pytest.mark.parametrize("cap", [1, 6, 20])
-def test_capacity_limited_launch_and_retry_pass(shim, oracle, cap):
+def test_capacity_limited_launch_and_retry_pass(shim, oracle, cap, step_mode):
     """The first pass is sized for `cap` landmarks; instances that might outgrow it are deferred untouched to the
     full-capacity retry pass.  Results must not depend on the split."""
     p, lm, fwd, ang = H.config2(seed=12, steps=220)
@@ -258,6 +270,7 @@ def test_capacity_limited_launch_and_retry_pass(shim, oracle, cap):
     B = 12
     fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), B, 50, 8)
     fb.tune(0, cap)
+    fb.tune(4, step_mode)
     fb.init(0, 0, 0)
     streams = [H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=21, instance=i)[0] for i in range(B)]
     ofs = []
@@ -284,6 +297,7 @@ def test_cta_widths_agree_with_oracle(shim, oracle, threads):
     op = H.oracle_params(oracle, p)
     B = 6
     fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), B, 50, 8)
+    fb.tune(4, 1)          # the shared-memory-resident kernel (known IDs default to the streaming kernel)
     fb.tune(2, threads)
     fb.init(0, 0, 0)
     streams = [H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=31, instance=i)[0] for i in range(B)]
