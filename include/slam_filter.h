@@ -144,6 +144,15 @@ int  slam_reset(slam_handle_t h, float x_0, float y_0, float yaw_0);
 int  slam_step_io(slam_handle_t h, const float* fwd, const float* ang, int cmd_stride,
                   const float* meas, const int* n_meas, double* poses_out);
 
+/* T x slam_step_io for a whole recorded run in ONE asynchronous call (the reference's results-only mode replays a
+ * precomputed trajectory the same way: base_pkg/launch/filter_demo_results_only.launch, sim_node.py:143-152).
+ * HOST buffers (pinned memory makes the copies overlap the kernels): cmd_fwd/cmd_ang [T] (cmd_stride 0) or
+ * [T][batch]; meas [T][batch][max_meas][3]; n_meas [T][batch]; poses_out [T][batch][3] (may be NULL).  Chunks of the
+ * run are uploaded, filtered and downloaded in a three-stage pipeline; known-ID EKF batches keep each filter resident
+ * in shared memory for a whole chunk.  The caller synchronises (slam_synchronize) before reading poses_out. */
+int  slam_run_io(slam_handle_t h, const float* cmd_fwd, const float* cmd_ang, int cmd_stride,
+                 const float* meas, const int* n_meas, double* poses_out, int T);
+
 /* ---- accuracy statistics accumulated by slam_run / slam_accumulate_error, summed over the batch:
  *      out[0]=count, [1]=sum ex^2, [2]=sum ey^2, [3]=sum eyaw^2 (wrapped), [4]=sum sqrt(ex^2+ey^2)
  *      (the reference's only metric, plotting_node.py:212-214), [5]=sum 3-dof pose NEES (extension),
@@ -164,7 +173,9 @@ int  slam_get_profile(slam_handle_t h, double* total_ms, long long* launches);  
 int  slam_build_info(char* buf, int cap);             /* arch, compile flags */
 /* tuning / test knobs.  key 0: force the shared-memory landmark capacity of the first pass (0 = automatic;
  * instances that do not fit are drained by the full-capacity retry pass); key 1: headroom (landmarks) added to
- * the stale max(M) hint.  Results never depend on either. */
+ * the stale max(M) hint of the per-step launches; key 2: CTA width of the EKF kernels (0 = automatic); key 3: 1 =
+ * slam_run* uses per-step launches instead of the persistent sweep kernel; key 5: steps per sweep-kernel launch;
+ * key 6: headroom of the sweep kernel's tile.  Results never depend on any of them. */
 int  slam_tune(slam_handle_t h, int key, int value);
 
 #ifdef __cplusplus

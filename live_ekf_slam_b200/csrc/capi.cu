@@ -42,9 +42,17 @@ struct slam_filter {
     int cap_force = 0;                // > 0: force this capacity for the first pass (tests of the retry path)
     int force_threads = 0;            // > 0: CTA width of the EKF kernels (tuning)
     int sweep_off = 0;                // 1: slam_run* always uses per-step launches (tests compare both paths)
-    int step_mode = 0;                // EKF per-step kernel: 0/1 shared-memory-resident (default), 2 row-streaming (known IDs)
-    bool stream_ok = false;           // ekf_stream_kernel usable for this handle
-    int* d_work = nullptr;            // work counter of the persistent sweep kernel
+    int sweep_chunk = 32;             // steps per launch of the persistent sweep kernel
+    int sweep_headroom = 8;           // landmarks of slack on top of the stale max(M) when sizing a chunk's tile
+    int* d_work = nullptr;            // [2] work counters of the sweep kernel (tile-sized launch, full-capacity launch)
+    int* d_progress = nullptr;        // [batch] run-relative steps completed (chunk gate of the sweep kernel)
+    int* h_run_hint = nullptr;        // pinned [HINT_RING]: max(M) after each chunk of the current run
+    cudaEvent_t run_ev[HINT_RING] = {};
+    // trajectory replay through host buffers (slam_run_io): two copy streams, double-buffered device chunks
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    float* d_rmeas[2] = {nullptr, nullptr}; int* d_rn[2] = {nullptr, nullptr}; double* d_rposes[2] = {nullptr, nullptr};
+    int r_chunk_cap = 0;              // steps the replay buffers hold
+    cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
     bool profiling = false;           // per-launch events around the per-step filter kernel
     bool profiling_sweep = false;     // events around the persistent sweep kernel
     std::vector<cudaEvent_t> ev;      // pairs
@@ -118,7 +126,8 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
     b.x_stride = ldg_of(b.n_max);
     b.p_stride = (long long)b.n_max * ldg_of(b.n_max);
     b.sigma_stride = 0;
-    b.fixed_ld = ldg_of(b.n_max);      // rows of P keep a fixed stride in HBM; only the live n x ldg(n) part is ever moved
+    b.fixed_ld = ldg_of(b.n_max);      // row-major layouts (UKF, large map): rows of P keep a fixed stride in HBM
+    b.ps2g = 0;
 
     const size_t smem = (kind == SLAM_EKF_SLAM) ? ekf_step_smem_bytes(b) : ukf_step_smem_bytes(b);
     if (smem > (size_t)prop.sharedMemPerBlockOptin) {
@@ -131,7 +140,19 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
                            "(the HBM-resident large-map path needs kind = EKF_SLAM, batch = 1, max_meas <= 256)");
         }
     }
+    if (kind == SLAM_EKF_SLAM && !h->large) {
+        // batched EKF: packed symmetric covariance, two planes of A_max (A_max + 1) doubles (common.cuh: bpl_idx)
+        b.ps2g = bpl_plane_doubles(2 + b.max_lm);
+        b.p_stride = 2LL * b.ps2g;
+    }
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming));
+    }
     CK(cudaMalloc(&b.P, sizeof(double) * (size_t)batch * b.p_stride));
     CK(cudaMalloc(&b.x, sizeof(double) * (size_t)batch * b.x_stride));
     CK(cudaMalloc(&b.ids, sizeof(int) * (size_t)batch * b.max_lm));
@@ -140,7 +161,11 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
     CK(cudaMalloc(&b.retry_list, sizeof(int) * batch));
     CK(cudaMalloc(&b.retry_count, sizeof(int)));
     CK(cudaMalloc(&b.max_M, sizeof(int)));
-    CK(cudaMalloc(&h->d_work, sizeof(int)));
+    CK(cudaMalloc(&h->d_work, 2 * sizeof(int)));
+    CK(cudaMalloc(&h->d_progress, sizeof(int) * batch));
+    CK(cudaMemset(h->d_progress, 0, sizeof(int) * batch));
+    CK(cudaMallocHost(&h->h_run_hint, sizeof(int) * slam_filter::HINT_RING));
+    for (int i = 0; i < slam_filter::HINT_RING; ++i) CK(cudaEventCreateWithFlags(&h->run_ev[i], cudaEventDisableTiming));
     CK(cudaMemset(b.retry_count, 0, sizeof(int)));
     CK(cudaMemset(b.max_M, 0, sizeof(int)));
     CK(cudaMallocHost(&h->h_hint, sizeof(int) * slam_filter::HINT_RING));
@@ -170,8 +195,6 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
         CK(cudaMallocHost(&h->h_nmeas_pin, sizeof(int)));
     } else if (kind == SLAM_EKF_SLAM) {
         CK(ekf_step_configure(b));
-        h->stream_ok = fc.id_known && ekf_stream_supported(b);
-        if (h->stream_ok) CK(ekf_stream_configure(b));
     } else CK(ukf_step_configure(b));
     *out = h;
     return slam_init(h, 0.f, 0.f, 0.f);
@@ -184,7 +207,17 @@ int slam_destroy(slam_handle_t h) {
     BatchState& b = h->b;
     cudaFree(b.P); cudaFree(b.x); cudaFree(b.ids); cudaFree(b.meta);
     cudaFree(b.assoc); cudaFree(b.stats); cudaFree(b.sigma);
-    cudaFree(b.retry_list); cudaFree(b.retry_count); cudaFree(b.max_M); cudaFree(h->d_work);
+    cudaFree(b.retry_list); cudaFree(b.retry_count); cudaFree(b.max_M); cudaFree(h->d_work); cudaFree(h->d_progress);
+    if (h->h_run_hint) cudaFreeHost(h->h_run_hint);
+    for (int i = 0; i < slam_filter::HINT_RING; ++i) if (h->run_ev[i]) cudaEventDestroy(h->run_ev[i]);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(h->d_rmeas[i]); cudaFree(h->d_rn[i]); cudaFree(h->d_rposes[i]);
+        if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+        if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
+        if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
+    }
+    if (h->s_h2d) { cudaStreamSynchronize(h->s_h2d); cudaStreamDestroy(h->s_h2d); }
+    if (h->s_d2h) { cudaStreamSynchronize(h->s_d2h); cudaStreamDestroy(h->s_d2h); }
     if (h->large) { cudaFree(h->lg.xp); cudaFree(h->lg.U); cudaFree(h->lg.G); cudaFree(h->lg.ctl); cudaFree(h->lg.cur); cudaFree(h->lg.sc); }
     if (h->h_nmeas_pin) cudaFreeHost(h->h_nmeas_pin);
     if (h->h_hint) cudaFreeHost(h->h_hint);
@@ -212,10 +245,8 @@ int slam_tune(slam_handle_t h, int key, int value) {
             return fail(h, "slam_tune: CTA width must be 0 (automatic), 32, 64, 128, 256 or 512");
         h->force_threads = value;
     } else if (key == 3) h->sweep_off = value;
-    else if (key == 4) {
-        if (value == 2 && !h->stream_ok) return fail(h, "slam_tune: the HBM-streaming EKF kernel needs known landmark IDs and 3 + 2*max_landmarks <= 126");
-        h->step_mode = value;
-    }
+    else if (key == 5) { if (value < 1) return fail(h, "slam_tune: the sweep chunk must be >= 1 step"); h->sweep_chunk = value; }
+    else if (key == 6) h->sweep_headroom = value < 0 ? 0 : value;
     else return fail(h, "slam_tune: unknown key");
     return 0;
 }
@@ -229,31 +260,16 @@ int slam_init(slam_handle_t h, float x_0, float y_0, float yaw_0) {
     if (!h) return 1;
     CK(cudaSetDevice(h->device));
     BatchState& b = h->b;
-    const int nb = b.base, ld = ldp_of(b.fixed_ld, nb);
-    std::vector<double> x0(b.x_stride, 0.0), P0((size_t)nb * ld, 0.0);
-    x0[0] = x_0; x0[1] = y_0;
-    if (nb == 3) x0[2] = yaw_0;
-    else { x0[2] = (double)(float)std::cos((double)yaw_0); x0[3] = (double)(float)std::sin((double)yaw_0); }   // ukf.cpp:33 (D-1)
-    P0[0 * ld + 0] = 0.01 * 0.01; P0[1 * ld + 1] = 0.01 * 0.01; P0[2 * ld + 2] = 0.005 * 0.005;
-    if (nb == 4) P0[3 * ld + 3] = 0.005 * 0.005;
-    // replicate on the host once, then one copy per array
-    std::vector<double> xs((size_t)b.batch * b.x_stride);
-    for (int i = 0; i < b.batch; ++i) memcpy(&xs[(size_t)i * b.x_stride], x0.data(), sizeof(double) * b.x_stride);
+    double a2 = yaw_0, a3 = 0.0;
+    if (b.base == 4) { a2 = (double)(float)std::cos((double)yaw_0); a3 = (double)(float)std::sin((double)yaw_0); }   // ukf.cpp:33 (D-1)
     CK(cudaMemsetAsync(b.P, 0, sizeof(double) * (size_t)b.batch * b.p_stride, h->stream));
-    CK(cudaMemcpyAsync(b.x, xs.data(), sizeof(double) * xs.size(), cudaMemcpyHostToDevice, h->stream));
-    {
-        std::vector<double> Ps((size_t)b.batch * P0.size());
-        for (int i = 0; i < b.batch; ++i) memcpy(&Ps[(size_t)i * P0.size()], P0.data(), sizeof(double) * P0.size());
-        CK(cudaMemcpy2DAsync(b.P, sizeof(double) * b.p_stride, Ps.data(), sizeof(double) * P0.size(),
-                             sizeof(double) * P0.size(), b.batch, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaStreamSynchronize(h->stream));   // Ps / xs are pageable host vectors
-    }
+    CK(cudaMemsetAsync(b.x, 0, sizeof(double) * (size_t)b.batch * b.x_stride, h->stream));
+    CK(launch_reset(b, (double)x_0, (double)y_0, a2, a3, h->stream));      // x_0, P_0, meta, stats on the device
+    h->launches += 1;
     CK(cudaMemsetAsync(b.ids, 0, sizeof(int) * (size_t)b.batch * b.max_lm, h->stream));
-    CK(cudaMemsetAsync(b.meta, 0, sizeof(int4) * b.batch, h->stream));
     CK(cudaMemsetAsync(b.max_M, 0, sizeof(int), h->stream));
     h->step_seq = 0; h->hint_base = 0;
     CK(cudaMemsetAsync(b.assoc, 0xff, sizeof(int) * (size_t)b.batch * b.max_meas, h->stream));
-    CK(cudaMemsetAsync(b.stats, 0, sizeof(double) * (size_t)b.batch * SLAM_NUM_STATS, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -301,8 +317,7 @@ static int do_step(slam_filter* h, const float* d_fwd, const float* d_ang, int c
         cap = h->h_hint[slot] + h->cap_headroom;
     } else cap = h->hint_base + (int)(h->step_seq + 1) * h->b.max_meas;      // M can grow by at most max_meas per step
     if (h->kind == SLAM_EKF_SLAM) {
-        if (h->stream_ok && h->step_mode == 2) CK(launch_ekf_stream_step(h->b, h->fc, in, phases, cap, h->stream));
-        else CK(launch_ekf_step(h->b, h->fc, in, phases, cap, h->force_threads, h->stream));
+        CK(launch_ekf_step(h->b, h->fc, in, phases, cap, h->force_threads, h->stream));
     }
     else CK(launch_ukf_step(h->b, h->fc, in, h->stream));
     if (h->profiling) { CK(cudaEventRecord(h->ev[h->ev_used + 1], h->stream)); h->ev_used += 2; }
@@ -418,6 +433,19 @@ int slam_get_cov(slam_handle_t h, int inst, double* P, int* n) {
     int M = 0;
     if (slam_get_num_landmarks(h, inst, &M)) return 1;
     const int nn = h->b.base + 2 * M, ld = ldp_of(h->b.fixed_ld, nn);
+    if (h->b.ps2g) {
+        // packed symmetric storage -> the full row-major matrix publishState serialises (ekf.cpp:211-217)
+        const int live = bpl_plane_doubles(2 + M), ps2 = h->b.ps2g;
+        std::vector<double> pk(2 * (size_t)live);
+        const double* g = h->b.P + (size_t)inst * h->b.p_stride;
+        CK(cudaMemcpyAsync(pk.data(), g, sizeof(double) * live, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(pk.data() + live, g + ps2, sizeof(double) * live, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int r = 0; r < nn; ++r)
+            for (int c = 0; c < nn; ++c) P[(size_t)r * nn + c] = pk[bpl_sym(r + 1, c + 1, live)];
+        if (n) *n = nn;
+        return 0;
+    }
     CK(cudaMemcpy2DAsync(P, sizeof(double) * nn, h->b.P + (size_t)inst * h->b.p_stride, sizeof(double) * ld,
                          sizeof(double) * nn, nn, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -472,6 +500,17 @@ int slam_set_state(slam_handle_t h, int inst, const double* x, const double* P, 
     const int nn = h->b.base + 2 * M, ld = ldp_of(h->b.fixed_ld, nn);
     const int4 meta = make_int4(M, 0, timestep, 0);
     CK(cudaMemcpyAsync(h->b.x + (size_t)inst * h->b.x_stride, x, sizeof(double) * nn, cudaMemcpyHostToDevice, h->stream));
+    std::vector<double> pk;
+    if (h->b.ps2g) {
+        // pack the lower triangle (the kernels keep P symmetric; the upper triangle of the input is ignored)
+        const int live = bpl_plane_doubles(2 + M), ps2 = h->b.ps2g;
+        pk.assign(2 * (size_t)live, 0.0);
+        for (int r = 0; r < nn; ++r)
+            for (int c = 0; c <= r; ++c) pk[bpl_idx(r + 1, c + 1, live)] = P[(size_t)r * nn + c];
+        double* g = h->b.P + (size_t)inst * h->b.p_stride;
+        CK(cudaMemcpyAsync(g, pk.data(), sizeof(double) * live, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(g + ps2, pk.data() + live, sizeof(double) * live, cudaMemcpyHostToDevice, h->stream));
+    } else
     CK(cudaMemcpy2DAsync(h->b.P + (size_t)inst * h->b.p_stride, sizeof(double) * ld, P, sizeof(double) * nn,
                          sizeof(double) * nn, nn, cudaMemcpyHostToDevice, h->stream));
     if (M > 0) CK(cudaMemcpyAsync(h->b.ids + (size_t)inst * h->b.max_lm, ids, sizeof(int) * M, cudaMemcpyHostToDevice, h->stream));
@@ -565,24 +604,75 @@ int slam_sim_get_meas(slam_sim_t s, float* meas, int* n_meas) {
 // ------------------------------------------------------------------------------------------ sweep + stats
 }  // extern "C"
 
-// T fused steps.  Known-ID EKF batches run the whole sweep in ONE persistent launch with the filters resident in
-// shared memory (ekf_sweep_kernel); everything else loops over per-step launches.
+// ---- chunked persistent sweep (known-ID EKF batches): the T steps of a run are cut into chunks of sweep_chunk
+// steps; each chunk is ONE launch of ekf_sweep_kernel with the shared-memory tile sized for the landmarks the batch
+// holds now (device max(M), read back with a lag of two chunks, plus headroom), followed by a full-capacity launch
+// that picks up the instances the first one had to leave untouched (normally none: it exits at once).
+static bool sweep_capable(const slam_filter* h) {
+    return h->kind == SLAM_EKF_SLAM && !h->large && h->fc.id_known && !h->sweep_off && !h->profiling;
+}
+struct SweepRun {            // host bookkeeping of one run's capacity hints
+    int base_hint = 0;       // max(M) at run start (synchronous read)
+    int chunk = 0;           // chunks launched so far
+};
+static int sweep_begin(slam_filter* h, SweepRun& run) {
+    CK(cudaMemsetAsync(h->d_progress, 0, sizeof(int) * h->b.batch, h->stream));
+    CK(cudaMemcpyAsync(&h->h_run_hint[0], h->b.max_M, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    run.base_hint = h->h_run_hint[0];
+    run.chunk = 0;
+    return 0;
+}
+static int sweep_chunk_launch(slam_filter* h, SweepRun& run, const SimState& sim, SweepArgs a, bool replay) {
+    constexpr int LAG = 2;
+    int hint = run.base_hint;
+    if (run.chunk >= LAG) {
+        const int slot = (run.chunk - LAG) % slam_filter::HINT_RING;
+        CK(cudaEventSynchronize(h->run_ev[slot]));      // completed long ago in steady state; bounds the host's lead
+        hint = h->h_run_hint[slot];
+    }
+    int cap = hint + h->sweep_headroom;
+    if (h->cap_force > 0) cap = h->cap_force;
+    if (cap > h->b.max_lm) cap = h->b.max_lm;
+    if (h->profiling_sweep) {
+        if (h->ev_used + 2 > h->ev.size()) {
+            const size_t old = h->ev.size();
+            h->ev.resize(old + 256);
+            for (size_t i = old; i < h->ev.size(); ++i) CK(cudaEventCreate(&h->ev[i]));
+        }
+        CK(cudaEventRecord(h->ev[h->ev_used], h->stream));
+    }
+    a.progress = h->d_progress;
+    a.work_counter = h->d_work;
+    CK(launch_ekf_sweep(h->b, h->fc, sim, h->sc, a, replay, cap, h->force_threads, h->stream));
+    h->launches += 1;
+    if (cap < h->b.max_lm) {
+        a.work_counter = h->d_work + 1;
+        CK(launch_ekf_sweep(h->b, h->fc, sim, h->sc, a, replay, h->b.max_lm, h->force_threads, h->stream));
+        h->launches += 1;
+    }
+    if (h->profiling_sweep) { CK(cudaEventRecord(h->ev[h->ev_used + 1], h->stream)); h->ev_used += 2; }
+    const int slot = run.chunk % slam_filter::HINT_RING;
+    CK(cudaMemcpyAsync(&h->h_run_hint[slot], h->b.max_M, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(h->run_ev[slot], h->stream));
+    run.chunk += 1;
+    return 0;
+}
+
+// T fused steps.  Known-ID EKF batches run on the chunked persistent sweep kernel with the filters resident in
+// shared memory; everything else loops over per-step launches.
 static int run_steps(slam_filter* h, slam_sim* s, const float* d_fwd, const float* d_ang, int cmd_stride, int T, uint32_t first_step) {
     const size_t per = cmd_stride ? (size_t)h->b.batch : 1;
-    const bool sweep = h->kind == SLAM_EKF_SLAM && !h->large && h->fc.id_known && !h->sweep_off && !h->profiling && T > 0;
-    if (sweep) {
-        if (h->profiling_sweep) {
-            if (h->ev_used + 2 > h->ev.size()) {
-                const size_t old = h->ev.size();
-                h->ev.resize(old + 64);
-                for (size_t i = old; i < h->ev.size(); ++i) CK(cudaEventCreate(&h->ev[i]));
-            }
-            CK(cudaEventRecord(h->ev[h->ev_used], h->stream));
+    if (sweep_capable(h) && T > 0) {
+        SweepRun run;
+        if (sweep_begin(h, run)) return 1;
+        for (int t0 = 0; t0 < T; t0 += h->sweep_chunk) {
+            SweepArgs a{};
+            a.cmd_fwd = d_fwd + per * (size_t)t0; a.cmd_ang = d_ang + per * (size_t)t0; a.cmd_stride = cmd_stride;
+            a.T = (T - t0 < h->sweep_chunk) ? T - t0 : h->sweep_chunk;
+            a.first_step = first_step + (uint32_t)t0; a.t0 = t0;
+            if (sweep_chunk_launch(h, run, s->s, a, false)) return 1;
         }
-        CK(launch_ekf_sweep(h->b, h->fc, s->s, h->sc, d_fwd, d_ang, cmd_stride, T, first_step, h->d_work,
-                            h->force_threads, h->stream));
-        if (h->profiling_sweep) { CK(cudaEventRecord(h->ev[h->ev_used + 1], h->stream)); h->ev_used += 2; }
-        h->launches += 1;
         // the per-step capacity hint is stale now: size the next per-step launches conservatively
         h->step_seq = 0; h->hint_base = h->b.max_lm;
         return 0;
@@ -598,13 +688,7 @@ static int run_steps(slam_filter* h, slam_sim* s, const float* d_fwd, const floa
     return 0;
 }
 
-extern "C" {
-int slam_run(slam_handle_t h, slam_sim_t s, const float* cmd_fwd, const float* cmd_ang, int cmd_stride, int T, uint32_t first_step) {
-    if (!h || !s || s->owner != h) return fail(h, "slam_run: simulator is not bound to this handle");
-    if (!cmd_fwd || !cmd_ang || T < 0) return fail(h, "slam_run: bad argument");
-    CK(cudaSetDevice(h->device));
-    const size_t per = cmd_stride ? (size_t)h->b.batch : 1;
-    const size_t need = per * (size_t)T;
+static int ensure_traj(slam_filter* h, size_t need) {
     if (need > h->traj_cap) {
         cudaFree(h->d_traj_fwd); cudaFree(h->d_traj_ang);
         h->d_traj_fwd = h->d_traj_ang = nullptr; h->traj_cap = 0;
@@ -612,6 +696,17 @@ int slam_run(slam_handle_t h, slam_sim_t s, const float* cmd_fwd, const float* c
         CK(cudaMalloc(&h->d_traj_ang, sizeof(float) * need));
         h->traj_cap = need;
     }
+    return 0;
+}
+
+extern "C" {
+int slam_run(slam_handle_t h, slam_sim_t s, const float* cmd_fwd, const float* cmd_ang, int cmd_stride, int T, uint32_t first_step) {
+    if (!h || !s || s->owner != h) return fail(h, "slam_run: simulator is not bound to this handle");
+    if (!cmd_fwd || !cmd_ang || T < 0) return fail(h, "slam_run: bad argument");
+    CK(cudaSetDevice(h->device));
+    const size_t per = cmd_stride ? (size_t)h->b.batch : 1;
+    const size_t need = per * (size_t)T;
+    if (ensure_traj(h, need)) return 1;
     CK(cudaMemcpyAsync(h->d_traj_fwd, cmd_fwd, sizeof(float) * need, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_traj_ang, cmd_ang, sizeof(float) * need, cudaMemcpyHostToDevice, h->stream));
     return run_steps(h, s, h->d_traj_fwd, h->d_traj_ang, cmd_stride, T, first_step);
@@ -643,6 +738,76 @@ int slam_step_io(slam_handle_t h, const float* fwd, const float* ang, int cmd_st
         h->launches += 1;
         CK(cudaMemcpyAsync(poses_out, h->d_out, sizeof(double) * 3 * h->b.batch, cudaMemcpyDeviceToHost, h->stream));
     }
+    return 0;
+}
+
+// T x (Filter::update + the pose read-back of publishState) for a whole recorded run, HOST buffers in and out.
+// The trajectory is cut into chunks; chunk c+1 is uploaded (copy stream) while chunk c runs (known-ID EKF batches:
+// ekf_sweep_kernel in replay mode with the filters resident in shared memory; otherwise per-step launches) and the
+// poses of chunk c-1 are downloaded (second copy stream).  Asynchronous: slam_synchronize() waits for everything,
+// including the last download.
+int slam_run_io(slam_handle_t h, const float* cmd_fwd, const float* cmd_ang, int cmd_stride, const float* meas,
+                const int* n_meas, double* poses_out, int T) {
+    if (!h) return 1;
+    if (!cmd_fwd || !cmd_ang || !meas || !n_meas || T < 0) return fail(h, "slam_run_io: bad argument");
+    if (h->large) return fail(h, "slam_run_io: not available on the large-map path (use slam_step)");
+    CK(cudaSetDevice(h->device));
+    const BatchState& b = h->b;
+    const size_t per = cmd_stride ? (size_t)b.batch : 1;
+    const size_t m_step = (size_t)b.batch * b.max_meas * 3, n_step = (size_t)b.batch, p_step = (size_t)b.batch * 3;
+    const int C = h->sweep_chunk;
+    if (h->r_chunk_cap < C) {
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(h->d_rmeas[i]); cudaFree(h->d_rn[i]); cudaFree(h->d_rposes[i]);
+            h->d_rmeas[i] = nullptr; h->d_rn[i] = nullptr; h->d_rposes[i] = nullptr;
+        }
+        h->r_chunk_cap = 0;
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaMalloc(&h->d_rmeas[i], sizeof(float) * m_step * C));
+            CK(cudaMalloc(&h->d_rn[i], sizeof(int) * n_step * C));
+            CK(cudaMalloc(&h->d_rposes[i], sizeof(double) * p_step * C));
+        }
+        h->r_chunk_cap = C;
+    }
+    if (ensure_traj(h, per * (size_t)(T > 0 ? T : 1))) return 1;
+    CK(cudaMemcpyAsync(h->d_traj_fwd, cmd_fwd, sizeof(float) * per * T, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_traj_ang, cmd_ang, sizeof(float) * per * T, cudaMemcpyHostToDevice, h->stream));
+    const bool sweep = sweep_capable(h);
+    SweepRun run;
+    if (sweep && T > 0 && sweep_begin(h, run)) return 1;
+    SimState nosim{};
+    int c = 0;
+    for (int t0 = 0; t0 < T; t0 += C, ++c) {
+        const int slot = c & 1, Tc = (T - t0 < C) ? T - t0 : C;
+        // upload chunk c once the kernels that read this slot two chunks ago are done
+        CK(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[slot], 0));
+        CK(cudaMemcpyAsync(h->d_rmeas[slot], meas + m_step * t0, sizeof(float) * m_step * Tc, cudaMemcpyHostToDevice, h->s_h2d));
+        CK(cudaMemcpyAsync(h->d_rn[slot], n_meas + n_step * t0, sizeof(int) * n_step * Tc, cudaMemcpyHostToDevice, h->s_h2d));
+        CK(cudaEventRecord(h->ev_h2d[slot], h->s_h2d));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_h2d[slot], 0));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_d2h[slot], 0));        // the pose buffer of this slot has been drained
+        if (sweep) {
+            SweepArgs a{};
+            a.cmd_fwd = h->d_traj_fwd + per * (size_t)t0; a.cmd_ang = h->d_traj_ang + per * (size_t)t0; a.cmd_stride = cmd_stride;
+            a.T = Tc; a.first_step = 0; a.t0 = t0;
+            a.r_meas = h->d_rmeas[slot]; a.r_nmeas = h->d_rn[slot]; a.r_poses = poses_out ? h->d_rposes[slot] : nullptr;
+            if (sweep_chunk_launch(h, run, nosim, a, true)) return 1;
+        } else {
+            for (int t = 0; t < Tc; ++t) {
+                if (do_step(h, h->d_traj_fwd + per * (size_t)(t0 + t), h->d_traj_ang + per * (size_t)(t0 + t), cmd_stride,
+                            h->d_rmeas[slot] + m_step * t, h->d_rn[slot] + n_step * t, STEP_PREDICT | STEP_UPDATE)) return 1;
+                if (poses_out) { CK(launch_poses(h->b, h->d_rposes[slot] + p_step * t, h->stream)); h->launches += 1; }
+            }
+        }
+        CK(cudaEventRecord(h->ev_comp[slot], h->stream));
+        if (poses_out) {
+            CK(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[slot], 0));
+            CK(cudaMemcpyAsync(poses_out + p_step * t0, h->d_rposes[slot], sizeof(double) * p_step * Tc, cudaMemcpyDeviceToHost, h->s_d2h));
+            CK(cudaEventRecord(h->ev_d2h[slot], h->s_d2h));
+        }
+    }
+    if (poses_out) for (int i = 0; i < 2; ++i) CK(cudaStreamWaitEvent(h->stream, h->ev_d2h[i], 0));
+    if (sweep) { h->step_seq = 0; h->hint_base = h->b.max_lm; }
     return 0;
 }
 

@@ -14,10 +14,9 @@ namespace slam {
 // ---------------------------------------------------------------------------------------------
 // HBM layout of a batch of filter instances (all arrays are struct-of-arrays over instances).
 //
-//   P      [batch][p_stride]   covariance, row-major with the fixed leading dimension ldg(n_max); the live
-//                              part of a row is its first ldg(n) = n rounded up to even doubles (a 16-byte
-//                              multiple: one cp.async.bulk / whole double2 loads), so only n*ldg(n) doubles
-//                              cross HBM per step.
+//   P      [batch][p_stride]   covariance.  UKF / large-map EKF: row-major, fixed leading dimension ldg(n_max).
+//                              Batched EKF: PACKED SYMMETRIC (see bpl_idx below): only the lower triangle exists,
+//                              so ~8 n^2 bytes cross HBM per step and direction-pair instead of 16 n^2.
 //   x      [batch][x_stride]   committed state x_t (EKF: x,y,yaw,lm.. ; UKF: x,y,cos,sin,lm..)
 //   ids    [batch][max_lm]     lm_IDs (filter.h:70)
 //   meta   [batch] int4 {M, status, timestep, n_assoc}
@@ -44,6 +43,7 @@ struct BatchState {
     int n_max;         // base + 2*max_lm
     int lds;           // shared-memory leading dimension of P
     int fixed_ld;      // global leading dimension of P (ldg(n_max)); a live row is its first ldg(n) doubles
+    int ps2g;          // EKF batch kernels: plane stride (doubles) of the packed symmetric layout in HBM, 0 = row-major
 };
 
 // Effective filter constants after readCommonParams (filter.h:105-121).
@@ -70,6 +70,20 @@ __host__ __device__ inline int lds_of(int n_max) {
     while ((l & 3) != 2) l += 2;
     return l;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Packed symmetric covariance of the batched EKF kernels (shared memory AND HBM).
+// Indices are PADDED by one (r' = r + 1): row/column 0 is a permanent zero phantom, so that the vehicle is rows
+// 1..3 and landmark s is rows 4+2s, 5+2s = block row 2+s -- inserting a landmark appends exactly one block row.
+// Only the lower triangle (r' >= c') is stored, as rows of even length in two planes: plane (r' & 1) holds row r' at
+// offset a(a+1), a = r' >> 1, with 2(a+1) entries (columns 0 .. 2a+1; the entry (2a, 2a+1) is never read).  A 2x2
+// block (a, b) is therefore one double2 in each plane at the same offset a(a+1) + 2b: the rank-2 update works on
+// whole blocks with conflict-free 16-byte accesses, a row is contiguous for the O(n) gathers, and a live plane is
+// ONE contiguous run of A(A+1) doubles (A = 2 + M block rows) = one bulk copy.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline int bpl_plane_doubles(int A) { return A * (A + 1); }
+__host__ __device__ inline int bpl_idx(int r, int c, int ps2) { return (r & 1) * ps2 + (r >> 1) * ((r >> 1) + 1) + c; }   // r >= c
+__host__ __device__ inline int bpl_sym(int r, int c, int ps2) { return r >= c ? bpl_idx(r, c, ps2) : bpl_idx(c, r, ps2); }
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10, identical to oracle_philox (counter = instance, step, channel, 0; key = seed)
@@ -163,12 +177,6 @@ cudaError_t launch_ekf_step(const BatchState& b, const FilterConst& fc, const St
 size_t ekf_step_smem_bytes(const BatchState& b);
 cudaError_t ekf_step_configure(const BatchState& b);
 
-// HBM-streaming EKF step (known IDs; csrc/ekf_stream.cu)
-bool ekf_stream_supported(const BatchState& b);
-cudaError_t ekf_stream_configure(const BatchState& b);
-cudaError_t launch_ekf_stream_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, int phases, int cap_hint,
-                                   cudaStream_t st);
-
 cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, cudaStream_t st);
 size_t ukf_step_smem_bytes(const BatchState& b);
 cudaError_t ukf_step_configure(const BatchState& b);
@@ -204,9 +212,25 @@ struct SimState {
     uint32_t instance_offset;
     uint32_t k0, k1;
 };
+// One chunk of a Monte-Carlo sweep / trajectory replay (csrc/ekf_batch.cu: ekf_sweep_kernel).
+struct SweepArgs {
+    const float* cmd_fwd;  // device, [T] (cmd_stride 0) or [T][batch], already offset to the chunk
+    const float* cmd_ang;
+    int cmd_stride;
+    int T;                 // steps of this chunk
+    uint32_t first_step;   // Philox step counter of the chunk's first step
+    int t0;                // run-relative index of the chunk's first step: only instances with progress == t0 run
+    int* progress;         // [batch] run-relative steps completed
+    int* work_counter;     // zeroed by the launcher
+    // replay mode: the messages come from HBM (uploaded host buffers) instead of the simulator, poses go out
+    const float* r_meas;   // [T][batch][max_meas][3]
+    const int* r_nmeas;    // [T][batch]
+    double* r_poses;       // [T][batch][3] (may be null)
+};
+// cap_lm: landmark capacity of the shared-memory tile of this launch; an instance that would outgrow it is left
+// untouched (progress unchanged) for a later launch with a larger tile.  Returns the number of kernels launched.
 cudaError_t launch_ekf_sweep(const BatchState& b, const FilterConst& fc, const SimState& sim, const SimConst& sc,
-                             const float* d_fwd, const float* d_ang, int cmd_stride, int T, uint32_t first_step,
-                             int* work_counter, int force_threads, cudaStream_t st);
+                             const SweepArgs& a, bool replay, int cap_lm, int force_threads, cudaStream_t st);
 cudaError_t launch_sim_step(const SimState& s, const SimConst& sc, const float* d_fwd, const float* d_ang,
                             int cmd_stride, uint32_t step, cudaStream_t st);
 cudaError_t launch_accumulate_error(const BatchState& b, const SimState& s, cudaStream_t st);

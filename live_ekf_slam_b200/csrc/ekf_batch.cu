@@ -1,26 +1,27 @@
 // ekf_batch.cu -- batched EKF-SLAM for sm_100a: one CTA per filter instance, the covariance staged in shared memory
 // by 1-D bulk async copies (cp.async.bulk / mbarrier).  Two kernels share one core:
 //   ekf_step_kernel   one reference EKF::update per launch: P crosses HBM once each way per step (HBM bound);
-//   ekf_sweep_kernel  a whole Monte-Carlo sweep (simulator -> filter -> error terms, T steps) per launch with P
-//                     RESIDENT in shared memory for all T steps: HBM sees P once per sweep.
+//   ekf_sweep_kernel  a chunk of a Monte-Carlo sweep (simulator -> filter -> error terms) or of a trajectory replay
+//                     (uploaded messages -> filter -> poses), T steps per launch with P RESIDENT in shared memory.
 //
 // Restates EKF::update, ekf_ws/src/localization_pkg/src/ekf.cpp:37-179, with the reference's float/double roundings
-//  and evaluates its dense products structurally:
-//   :61   F_x P F_x^T + F_v V F_v^T   -> rows/cols 0..1 pick up row/col 2, + 3x3 block      O(n)
-//   :133  H P H^T + W                 -> the 5x5 sub-block of P that H touches              O(1)
-//   :135  P H^T S^-1                  -> 5 columns of P                                     O(n)
-//   :140  P - (K H) P                 -> rank-2 update P -= K (H P)                         O(n^2)
-//   :172  Y blkdiag(P,W) Y^T          -> two new rows/cols                                  O(n)
+//  and evaluates its dense products structurally on the PACKED SYMMETRIC covariance
+// (common.cuh: bpl_idx; P = P^T up to rounding in the reference -- its asymmetry stays at 1e-15 |P|, SURVEY App. E --
+// so only the lower triangle is kept: half the shared memory, half the HBM bytes, half the rank-2 flops):
+//   :61   F_x P F_x^T + F_v V F_v^T   -> column entries (j,0),(j,1) pick up (j,2), + 3x3 block   O(n)
+//   :133  H P H^T + W                 -> the 5x5 sub-block of P that H touches                   O(1)
+//   :135  P H^T S^-1                  -> (H P)^T S^-1: the same five rows of P as H P            O(n)
+//   :140  P - (K H) P                 -> rank-2 update of the lower triangle, 2x2 blocks         O(n^2 / 2)
+//   :172  Y blkdiag(P,W) Y^T          -> one new block row                                      O(n)
 //
-// Thread organisation (THREADS = 32 * WARPS, WARPS in {1,2,4,8,16}, chosen per launch from the tile size so that
-// about 32 warps are resident per SM whatever n is).  Scalar chains (sincos, sqrt, atan2, divisions) are the
-// latency- and issue-critical part at small n, so:
-//   * warp 0 evaluates the H / S / S^-1 chain of a landmark update ONCE (lane-parallel divisions, S from the 5x5
-//     sub-block of P that H touches) while lane 0 of the last warp evaluates the innovation (atan2 / remainder) and,
-//     at step start, the predict trigonometry; the other warps wait at the barrier and cost no issue slots;
+// Thread organisation (NT = 32 * WARPS filter threads, WARPS in {1,2,4,8,16} chosen per launch from the tile size so
+// that as many instances as possible are resident per SM: the step is a chain of scalar latencies -- sqrt, divisions,
+// atan2, sincos -- and instance-level parallelism is what hides it):
+//   * warp 0 evaluates the H / S / S^-1 chain of a landmark update ONCE (lane-parallel divisions) while lane 0 of the
+//     last warp evaluates the innovation (atan2 / remainder) and, at step start, the predict trigonometry;
 //   * known-ID association (integer compares on lm_IDs) is resolved for the whole message before P is touched;
-//   * in the sweep kernel a dedicated producer warp runs the simulator one step ahead of the filter warps and folds
-//     the error terms one step behind them (named barriers, double-buffered messages).
+//   * in the sweep kernel a dedicated producer warp runs the simulator (or fetches the uploaded messages) one step
+//     ahead of the filter warps and folds the error terms (or writes the poses) one step behind them.
 #include "sim_device.cuh"
 
 #include <climits>
@@ -28,14 +29,13 @@
 namespace slam {
 
 // Launch geometry.  Shared memory is sized for the landmark capacity of THIS launch (cap_lm <= max_lm), chosen
-// by the host from a slightly stale device-side max(M) plus headroom, so that early in a run -- while the map
-// is still small -- many more CTAs fit per SM.  An instance whose M + detections could exceed cap_lm is
-// deferred untouched to a retry list that a second, full-capacity launch drains (correctness never depends
-// on the hint).
+// by the host from a slightly stale device-side max(M) plus headroom, so that while the map is still small many
+// more CTAs fit per SM.  An instance that could outgrow the tile is left untouched for a full-capacity launch
+// (step kernel: retry list; sweep kernel: progress gate), so results never depend on the hint.
 struct EkfLaunch {
     int cap_lm;        // landmark capacity of this launch's shared-memory tile
     int n_cap;         // 3 + 2*cap_lm
-    int lds;           // shared-memory leading dimension for n_cap
+    int ps2;           // shared-memory plane stride (doubles) of the packed covariance
     int from_list;     // 0: instance = blockIdx.x ; 1: instances come from b.retry_list (persistent loop)
     int off[16];       // shared-memory byte offsets (laid out on the host: the kernels add constant-bank offsets)
     int smem_bytes;    // step kernel's dynamic shared memory
@@ -43,30 +43,32 @@ struct EkfLaunch {
 };
 
 struct EkfSmem {
-    double* P;      // n_cap x lds
-    double* x;      // running x_pred
+    double* P;      // packed symmetric covariance, two planes of ps2 doubles
+    double* x;      // running x_pred (unpadded)
     double* xs;     // x_t at step start (stale landmark means, ekf.cpp:115)
-    double* HP;     // 2 x lds   (H_x * P_pred)
-    double* K;      // n_cap x 2
+    double* H0;     // row 0 of H_x P_pred, padded index (H0[0] = 0)
+    double* H1;     // row 1
+    double* K;      // K as double2 per padded row (K[0] = 0)
     double* sc;     // scalars
     int* ids;
     float* meas;
     int* assoc;
-    int* iscr;      // [0] dead flag of the association pre-pass, [1] nan flag, [2] n_meas (sweep), [3] work item (sweep)
+    int* iscr;      // [0] dead flag of the association pre-pass, [1] nan flag, [2] work item, [3] tile overflow flag
     uint64_t* bar;
 };
 
-enum { EO_P = 0, EO_X, EO_XS, EO_HP, EO_K, EO_SC, EO_IDS, EO_MEAS, EO_ASSOC, EO_ISCR, EO_BAR, EO_WM0, EO_WM1, EO_WNM, EO_WSNAP };
+enum { EO_P = 0, EO_X, EO_XS, EO_H0, EO_H1, EO_K, EO_SC, EO_IDS, EO_MEAS, EO_ASSOC, EO_ISCR, EO_BAR, EO_WM0, EO_WM1, EO_WNM, EO_WSNAP };
 
 static void ekf_smem_layout(const int max_meas, EkfLaunch& L) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return (int)o; };
-    const int nmp = ldg_of(L.n_cap);
-    L.off[EO_P] = take(sizeof(double) * (size_t)L.n_cap * L.lds);
-    L.off[EO_X] = take(sizeof(double) * nmp);
-    L.off[EO_XS] = take(sizeof(double) * nmp);
-    L.off[EO_HP] = take(sizeof(double) * 2 * L.lds);
-    L.off[EO_K] = take(sizeof(double) * 2 * nmp);
+    const int np = L.n_cap + 1;                 // padded state size (even)
+    L.off[EO_P] = take(sizeof(double) * 2 * (size_t)L.ps2);
+    L.off[EO_X] = take(sizeof(double) * np);
+    L.off[EO_XS] = take(sizeof(double) * np);
+    L.off[EO_H0] = take(sizeof(double) * np);
+    L.off[EO_H1] = take(sizeof(double) * np);
+    L.off[EO_K] = take(sizeof(double) * 2 * np);
     L.off[EO_SC] = take(sizeof(double) * 24);
     L.off[EO_IDS] = take(sizeof(int) * (L.cap_lm + 1));
     L.off[EO_MEAS] = take(sizeof(float) * 3 * max_meas);
@@ -83,7 +85,8 @@ static void ekf_smem_layout(const int max_meas, EkfLaunch& L) {
 
 __device__ __forceinline__ void ekf_smem_bind(const EkfLaunch& L, unsigned char* base, EkfSmem& s) {
     s.P = (double*)(base + L.off[EO_P]); s.x = (double*)(base + L.off[EO_X]); s.xs = (double*)(base + L.off[EO_XS]);
-    s.HP = (double*)(base + L.off[EO_HP]); s.K = (double*)(base + L.off[EO_K]); s.sc = (double*)(base + L.off[EO_SC]);
+    s.H0 = (double*)(base + L.off[EO_H0]); s.H1 = (double*)(base + L.off[EO_H1]); s.K = (double*)(base + L.off[EO_K]);
+    s.sc = (double*)(base + L.off[EO_SC]);
     s.ids = (int*)(base + L.off[EO_IDS]); s.meas = (float*)(base + L.off[EO_MEAS]); s.assoc = (int*)(base + L.off[EO_ASSOC]);
     s.iscr = (int*)(base + L.off[EO_ISCR]); s.bar = (uint64_t*)(base + L.off[EO_BAR]);
 }
@@ -91,7 +94,7 @@ __device__ __forceinline__ void ekf_smem_bind(const EkfLaunch& L, unsigned char*
 // scalar slots in sc[]
 enum { SC_FA = 0, SC_FB, SC_C, SC_S, SC_NX0, SC_NX1, SC_NX2, SC_NU0, SC_NU1, SC_XD, SC_YD, SC_CB, SC_SB,
        SC_Q0 = 13 /* 4 quotients of H */, SC_I00 = 17 /* S^-1, 4 */, SC_END = 21 };
-enum { IS_DEAD = 0, IS_NAN = 1, IS_WORK = 2 };
+enum { IS_DEAD = 0, IS_NAN = 1, IS_WORK = 2, IS_OVER = 3 };
 enum { ASSOC_NEW = -1, ASSOC_DROPPED = -2 };   // internal codes of the pre-pass; both read back as -1 (new landmark)
 
 // barrier among the NT threads that run the filter core
@@ -101,7 +104,9 @@ struct CtaSync {            // the whole CTA runs the core (ekf_step_kernel)
 };
 template <int NT, int ID>
 struct NamedSync {          // a subset of the CTA's warps runs the core (ekf_sweep_kernel consumers)
-    static __device__ __forceinline__ void sync() { asm volatile("bar.sync %0, %1;" ::"r"(ID), "r"(NT) : "memory"); }
+    static __device__ __forceinline__ void sync() {
+        if constexpr (NT == 32) __syncwarp(); else asm volatile("bar.sync %0, %1;" ::"r"(ID), "r"(NT) : "memory");
+    }
 };
 __device__ __forceinline__ void named_sync(const int id, const int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_arrive(const int id, const int count) {
@@ -124,10 +129,12 @@ __device__ __forceinline__ void ekf_predict_scalars(const FilterConst& fc, const
 }
 
 // ---- known-ID association for the whole message (ekf.cpp:99-109), one warp, before anything is modified.
-// s.assoc[l] <- slot in the committed lm_IDs, ASSOC_NEW (will be inserted) or ASSOC_DROPPED (capacity reached).
+// s.assoc[l] <- slot in the committed lm_IDs, ASSOC_NEW (will be inserted) or ASSOC_DROPPED (max_lm reached).
 // A measurement that repeats the id of a landmark inserted earlier in the same step would make the reference index
 // x_t out of range (:115): flagged dead (SLAM_STATUS_SAME_STEP_REMATCH), nothing of the step is applied.
-__device__ __forceinline__ void ekf_assoc_prepass(const EkfSmem& s, const int lane, const int M, const int nm, const int max_lm) {
+// s.iscr[IS_OVER] <- 1 when the insertions of this message would not fit a tile of tile_lm landmarks.
+__device__ __forceinline__ void ekf_assoc_prepass(const EkfSmem& s, const int lane, const int M, const int nm, const int max_lm,
+                                                  const int tile_lm) {
     int M_run = M;
     bool dead = false;
     for (int l = 0; l < nm; ++l) {
@@ -146,7 +153,7 @@ __device__ __forceinline__ void ekf_assoc_prepass(const EkfSmem& s, const int la
         if (lane == 0) s.assoc[l] = code;
         __syncwarp();
     }
-    if (lane == 0) s.iscr[IS_DEAD] = dead ? 1 : 0;
+    if (lane == 0) { s.iscr[IS_DEAD] = dead ? 1 : 0; s.iscr[IS_OVER] = (M_run > tile_lm) ? 1 : 0; }
 }
 
 // ---- one reference EKF::update on the shared-memory-resident filter, executed by NT threads (threadIdx.x < NT)
@@ -155,41 +162,43 @@ __device__ __forceinline__ void ekf_assoc_prepass(const EkfSmem& s, const int la
 // the pre-pass.  Returns true when the step was applied; false when the instance died (same-step re-match): in
 // known-ID mode nothing has been modified then, in unknown-ID mode the shared-memory state must be discarded.
 template <int NT, class Sync>
-__device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s, const int lds, const int max_lm,
+__device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s, const int ps2, const int max_lm,
                                          const int phases, int& M, const int nm, int& status, int& n_upd) {
     constexpr int WARPS = NT / 32;
     constexpr int NUW = WARPS - 1;                              // lane 0 of this warp owns the atan2 / sincos chains
-    constexpr int UNR = (NT >= 512) ? 2 : 4;                    // row groups in flight in the rank-2 sweep
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool nu_thread = (warp == NUW) && (lane == 0);
     const int M_start = M;
-    int n = 3 + 2 * M;
     n_upd = 0;
 
     if ((phases & STEP_UPDATE) && fc.id_known && s.iscr[IS_DEAD]) { status |= SLAM_STATUS_SAME_STEP_REMATCH; return false; }
 
     // ---- PREDICT, ekf.cpp:43-61.  T = F_x P (rows 0,1 pick up row 2), P' = T F_x^T (cols 0,1 pick up col 2)
-    //      + (F_v V) F_v^T on the vehicle block.  For j >= 3 the row and column parts touch disjoint entries, so one
-    //      pass does both; the 3x3 vehicle block is done by one thread in the reference's order.
+    //      + (F_v V) F_v^T on the vehicle block.  In the lower triangle only the column form exists for j >= 3:
+    //      (j,0) += (j,2) fa, (j,1) += (j,2) fb; the 3x3 vehicle block is done by one thread in the reference's order.
     if (phases & STEP_PREDICT) {
         const double fa = s.sc[SC_FA], fb = s.sc[SC_FB];
-        for (int j = tid; j < n; j += NT) {
-            if (j >= 3) {
-                const double p2 = s.P[2 * lds + j];
-                s.P[j] = s.P[j] + fa * p2;
-                s.P[lds + j] = s.P[lds + j] + fb * p2;
-                double* row = s.P + (size_t)j * lds;
-                const double t2 = row[2];
-                row[0] = row[0] + t2 * fa;
-                row[1] = row[1] + t2 * fb;
+        const int np = 4 + 2 * M;
+        for (int j = tid; j < np; j += NT) {
+            if (j >= 4) {
+                double* rb = s.P + bpl_idx(j, 0, ps2);          // padded row j: [0, (j,x), (j,y), (j,yaw), ...]
+                double2 b0 = *reinterpret_cast<double2*>(rb), b1 = *reinterpret_cast<double2*>(rb + 2);
+                const double t2 = b1.y;
+                b0.y = b0.y + t2 * fa;
+                b1.x = b1.x + t2 * fb;
+                *reinterpret_cast<double2*>(rb) = b0; *reinterpret_cast<double2*>(rb + 2) = b1;
             } else if (j == 0) {
                 const double c = s.sc[SC_C], sn = s.sc[SC_S];
-                double T[3][3];
+                double Pv[3][3], T[3][3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int q = 0; q <= a; ++q) { const double v = s.P[bpl_idx(a + 1, q + 1, ps2)]; Pv[a][q] = v; Pv[q][a] = v; }
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
-                    const double p2 = s.P[2 * lds + q];
-                    T[0][q] = s.P[q] + fa * p2;
-                    T[1][q] = s.P[lds + q] + fb * p2;
+                    const double p2 = Pv[2][q];
+                    T[0][q] = Pv[0][q] + fa * p2;
+                    T[1][q] = Pv[1][q] + fb * p2;
                     T[2][q] = p2;
                 }
 #pragma unroll
@@ -199,9 +208,9 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
                     double p1 = T[i][1] + t2 * fb;
                     if (i == 0) { const double cV = c * fc.V00; p0 += cV * c; p1 += cV * sn; }
                     if (i == 1) { const double sV = sn * fc.V00; p0 += sV * c; p1 += sV * sn; }
-                    s.P[i * lds + 0] = p0;
-                    s.P[i * lds + 1] = p1;
-                    s.P[i * lds + 2] = (i == 2) ? t2 + fc.V11 : t2;
+                    s.P[bpl_idx(i + 1, 1, ps2)] = p0;
+                    if (i >= 1) s.P[bpl_idx(i + 1, 2, ps2)] = p1;
+                    if (i == 2) s.P[bpl_idx(3, 3, ps2)] = t2 + fc.V11;
                 }
                 s.x[0] = s.sc[SC_NX0]; s.x[1] = s.sc[SC_NX1]; s.x[2] = s.sc[SC_NX2];
             }
@@ -212,6 +221,7 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
     // ---- UPDATE, ekf.cpp:63-174
     for (int l = 0; l < nm; ++l) {
         const float r = s.meas[3 * l + 1], bb = s.meas[3 * l + 2];
+        const int n = 3 + 2 * M;
         int slot, id;
         if (fc.id_known) {
             slot = s.assoc[l];
@@ -249,7 +259,8 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
 
         if (slot >= 0) {
             // -------- landmark update, :110-140
-            const int i = slot * 2 + 3;
+            const int i = slot * 2 + 3;          // unpadded state index of the landmark
+            const int ip = i + 1;                // padded
             ++n_upd;
             // -- scalar phase: warp 0 -> H (4 distinct quotients), S, S^-1 ; nu thread -> innovation
             if (warp == 0 || nu_thread) {
@@ -274,11 +285,11 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
                     const double H[10] = {-q0, -q1, 0.0, q0, q1, q2, -q3, -1.0, -q2, q3};
                     // S = H P H^T + W (:133) from the 5x5 sub-block of P that H touches: lane c < 5 forms column
                     // hc[c] of H P, the 2x2 sums are reduced over the 5 lanes in ascending c order
-                    const int hcl = (lane < 3) ? lane : i + (lane - 3);    // hc[lane] for lane < 5
+                    const int hcl = (lane < 3) ? lane + 1 : ip + (lane - 3);    // padded hc[lane] for lane < 5
                     double g0 = 0.0, g1 = 0.0;
                     if (lane < 5) {
-                        const double p0 = s.P[hcl], p1 = s.P[lds + hcl], p2 = s.P[2 * lds + hcl];
-                        const double p3 = s.P[(size_t)i * lds + hcl], p4 = s.P[(size_t)(i + 1) * lds + hcl];
+                        const double p0 = s.P[bpl_sym(1, hcl, ps2)], p1 = s.P[bpl_sym(2, hcl, ps2)], p2 = s.P[bpl_sym(3, hcl, ps2)];
+                        const double p3 = s.P[bpl_sym(ip, hcl, ps2)], p4 = s.P[bpl_sym(ip + 1, hcl, ps2)];
                         g0 = H[0] * p0; g0 += H[1] * p1; g0 += H[2] * p2; g0 += H[3] * p3; g0 += H[4] * p4;
                         g1 = H[5] * p0; g1 += H[6] * p1; g1 += H[7] * p2; g1 += H[8] * p3; g1 += H[9] * p4;
                     }
@@ -305,32 +316,23 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
                 }
             }
             Sync::sync();
-            // -- O(n) phase: H P (2 x n, kept for the sweep) and K = P H^T S^-1 (n x 2)
+            // -- O(n) phase: H P (2 x n, kept for the sweep) and K = P H^T S^-1 = (H P)^T S^-1 (n x 2)
             {
                 const double q0 = s.sc[SC_Q0], q1 = s.sc[SC_Q0 + 1], q2 = s.sc[SC_Q0 + 2], q3 = s.sc[SC_Q0 + 3];
                 const double H[10] = {-q0, -q1, 0.0, q0, q1, q2, -q3, -1.0, -q2, q3};
-                const int ldg = ldg_of(n);
-                for (int idx = tid; idx < ldg + n; idx += NT) {
-                    if (idx < ldg) {
-                        const int j = idx;
-                        double h0 = 0.0, h1 = 0.0;
-                        if (j < n) {
-                            const double p0 = s.P[j], p1 = s.P[lds + j], p2 = s.P[2 * lds + j];
-                            const double p3 = s.P[(size_t)i * lds + j], p4 = s.P[(size_t)(i + 1) * lds + j];
-                            h0 = H[0] * p0; h0 += H[1] * p1; h0 += H[2] * p2; h0 += H[3] * p3; h0 += H[4] * p4;
-                            h1 = H[5] * p0; h1 += H[6] * p1; h1 += H[7] * p2; h1 += H[8] * p3; h1 += H[9] * p4;
-                        }
-                        s.HP[j] = h0; s.HP[lds + j] = h1;
-                    } else {
-                        const int q = idx - ldg;
-                        const double i00 = s.sc[SC_I00], i01 = s.sc[SC_I00 + 1], i10 = s.sc[SC_I00 + 2], i11 = s.sc[SC_I00 + 3];
-                        const double* row = s.P + (size_t)q * lds;
-                        const double p0 = row[0], p1 = row[1], p2 = row[2], p3 = row[i], p4 = row[i + 1];
-                        double a0 = p0 * H[0]; a0 += p1 * H[1]; a0 += p2 * H[2]; a0 += p3 * H[3]; a0 += p4 * H[4];
-                        double a1 = p0 * H[5]; a1 += p1 * H[6]; a1 += p2 * H[7]; a1 += p3 * H[8]; a1 += p4 * H[9];
-                        s.K[2 * q] = a0 * i00 + a1 * i10;
-                        s.K[2 * q + 1] = a0 * i01 + a1 * i11;
+                const double i00 = s.sc[SC_I00], i01 = s.sc[SC_I00 + 1], i10 = s.sc[SC_I00 + 2], i11 = s.sc[SC_I00 + 3];
+                const int np = n + 1;
+                for (int j = tid; j < np; j += NT) {
+                    double h0 = 0.0, h1 = 0.0;
+                    if (j >= 1) {
+                        const double p0 = s.P[bpl_sym(1, j, ps2)], p1 = s.P[bpl_sym(2, j, ps2)], p2 = s.P[bpl_sym(3, j, ps2)];
+                        const double p3 = s.P[bpl_sym(ip, j, ps2)], p4 = s.P[bpl_sym(ip + 1, j, ps2)];
+                        h0 = H[0] * p0; h0 += H[1] * p1; h0 += H[2] * p2; h0 += H[3] * p3; h0 += H[4] * p4;
+                        h1 = H[5] * p0; h1 += H[6] * p1; h1 += H[7] * p2; h1 += H[8] * p3; h1 += H[9] * p4;
                     }
+                    s.H0[j] = h0; s.H1[j] = h1;
+                    s.K[2 * j] = h0 * i00 + h1 * i10;
+                    s.K[2 * j + 1] = h0 * i01 + h1 * i11;
                 }
             }
             Sync::sync();
@@ -338,55 +340,48 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
             {
                 const double nu0 = s.sc[SC_NU0], nu1 = s.sc[SC_NU1];
                 for (int q = tid; q < n; q += NT) {
-                    double xv = s.x[q] + (s.K[2 * q] * nu0 + s.K[2 * q + 1] * nu1);
+                    double xv = s.x[q] + (s.K[2 * q + 2] * nu0 + s.K[2 * q + 3] * nu1);
                     if (q == 2) xv = wrap_2pi(xv);
                     s.x[q] = xv;
                 }
             }
-            // -- P -= K (H P), :140 as a rank-2 update over the packed row width.  A lane owns one double2 column pair
-            //    (its two (H P) pairs stay in registers), a warp owns RPI consecutive rows per iteration (RPI > 1 when
-            //    a row is narrower than a warp), UNR row groups in flight.
+            // -- P -= K (H P), :140, on the lower triangle in 2x2 blocks.  Block rows are paired (A-1-q, q) into
+            //    combined rows of constant length A+1 so that a flat index walks the triangle with one division at
+            //    entry; consecutive threads touch consecutive 16-byte words of each plane.
             {
-                const int hp = ldg_of(n) >> 1;                  // double2 per row
-                int cpw = 32, cps = 5;                          // lanes per row: smallest power of two >= hp, <= 32
-                while (cpw > 1 && (cpw >> 1) >= hp) { cpw >>= 1; --cps; }
-                const int rpi = 32 >> cps;
-                const int lr = lane >> cps, lc = lane & (cpw - 1);
-                for (int c0 = 0; c0 < hp; c0 += cpw) {
-                    const int jp = c0 + lc;
-                    if (jp < hp) {
-                        const double2 h0 = *reinterpret_cast<const double2*>(s.HP + 2 * jp);
-                        const double2 h1 = *reinterpret_cast<const double2*>(s.HP + lds + 2 * jp);
-                        double* col = s.P + 2 * jp;
-                        const int rstep = WARPS * rpi;
-                        int row = warp * rpi + lr;
-                        for (; row + (UNR - 1) * rstep < n; row += UNR * rstep) {
-                            double2 k[UNR], p[UNR];
-#pragma unroll
-                            for (int u = 0; u < UNR; ++u) {
-                                k[u] = *reinterpret_cast<const double2*>(s.K + 2 * (row + u * rstep));
-                                p[u] = *reinterpret_cast<const double2*>(col + (size_t)(row + u * rstep) * lds);
-                            }
-#pragma unroll
-                            for (int u = 0; u < UNR; ++u) {
-                                p[u].x = p[u].x - (k[u].x * h0.x + k[u].y * h1.x);
-                                p[u].y = p[u].y - (k[u].x * h0.y + k[u].y * h1.y);
-                                *reinterpret_cast<double2*>(col + (size_t)(row + u * rstep) * lds) = p[u];
-                            }
-                        }
-                        for (; row < n; row += rstep) {
-                            const double2 k = *reinterpret_cast<const double2*>(s.K + 2 * row);
-                            double2 p = *reinterpret_cast<const double2*>(col + (size_t)row * lds);
-                            p.x = p.x - (k.x * h0.x + k.y * h1.x);
-                            p.y = p.y - (k.x * h0.y + k.y * h1.y);
-                            *reinterpret_cast<double2*>(col + (size_t)row * lds) = p;
-                        }
+                const int A = 2 + M;                            // live block rows
+                const int Lc = A + 1;                           // combined row length (blocks)
+                const int Q = (A + 1) >> 1;                     // combined rows
+                int q = tid / Lc, p = tid - q * Lc;
+                const int dq = NT / Lc, dp = NT - dq * Lc;
+                const double2* K2 = reinterpret_cast<const double2*>(s.K);
+                const double2* H02 = reinterpret_cast<const double2*>(s.H0);
+                const double2* H12 = reinterpret_cast<const double2*>(s.H1);
+                double2* P0 = reinterpret_cast<double2*>(s.P);
+                double2* P1 = reinterpret_cast<double2*>(s.P + ps2);
+                while (q < Q) {
+                    const int split = A - q;
+                    const bool first = p < split;
+                    const int a = first ? (A - 1 - q) : q;
+                    const int bc = first ? p : p - split;
+                    if (first || (A - 1 - q != q)) {             // the self-paired middle block row is walked once
+                        const int tb = ((a * (a + 1)) >> 1) + bc;
+                        const double2 klo = K2[2 * a], khi = K2[2 * a + 1];
+                        const double2 h0 = H02[bc], h1 = H12[bc];
+                        double2 p0 = P0[tb], p1 = P1[tb];
+                        p0.x = p0.x - (klo.x * h0.x + klo.y * h1.x);
+                        p0.y = p0.y - (klo.x * h0.y + klo.y * h1.y);
+                        p1.x = p1.x - (khi.x * h0.x + khi.y * h1.x);
+                        p1.y = p1.y - (khi.x * h0.y + khi.y * h1.y);
+                        P0[tb] = p0; P1[tb] = p1;
                     }
+                    p += dp; q += dq;
+                    if (p >= Lc) { p -= Lc; ++q; }
                 }
             }
             Sync::sync();
         } else {
-            // -------- landmark insertion, :141-173
+            // -------- landmark insertion, :141-173: one new block row (padded rows np, np+1)
             if (fc.id_known) {
                 if (nu_thread) {
                     double sb, cb; sincos(s.x[2] + (double)bb, &sb, &cb);
@@ -396,19 +391,17 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
             }
             const double cb = s.sc[SC_CB], sb = s.sc[SC_SB];
             const double g02 = -(double)r * sb, g12 = (double)r * cb;      // G_x(0,2), G_x(1,2), :162,165
-            // rows n, n+1 over old columns; columns n, n+1 over old rows
-            for (int j = tid; j < n; j += NT) {
-                const double p0 = s.P[j], p1 = s.P[lds + j], p2 = s.P[2 * lds + j];
-                double t0 = 1.0 * p0; t0 += 0.0 * p1; t0 += g02 * p2;
-                double t1 = 0.0 * p0; t1 += 1.0 * p1; t1 += g12 * p2;
-                s.P[(size_t)n * lds + j] = t0;
-                s.P[(size_t)(n + 1) * lds + j] = t1;
-                const double* row = s.P + (size_t)j * lds;
-                const double q0 = row[0], q1 = row[1], q2 = row[2];
-                double c0 = q0 * 1.0; c0 += q1 * 0.0; c0 += q2 * g02;
-                double c1 = q0 * 0.0; c1 += q1 * 1.0; c1 += q2 * g12;
-                s.P[(size_t)j * lds + n] = c0;
-                s.P[(size_t)j * lds + n + 1] = c1;
+            const int np = n + 1;
+            double* r0 = s.P + bpl_idx(np, 0, ps2);
+            double* r1 = s.P + bpl_idx(np + 1, 0, ps2);
+            for (int j = tid; j < np; j += NT) {
+                double t0 = 0.0, t1 = 0.0;                                 // phantom column 0 stays zero
+                if (j >= 1) {
+                    const double p0 = s.P[bpl_sym(1, j, ps2)], p1 = s.P[bpl_sym(2, j, ps2)], p2 = s.P[bpl_sym(3, j, ps2)];
+                    t0 = 1.0 * p0; t0 += 0.0 * p1; t0 += g02 * p2;
+                    t1 = 0.0 * p0; t1 += 1.0 * p1; t1 += g12 * p2;
+                }
+                r0[j] = t0; r1[j] = t1;
             }
             if (nu_thread) {
                 // new 2x2 block: G_x P_vv G_x^T + G_z W G_z^T, :155-172
@@ -418,7 +411,8 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
                 double T3[2][3], T2[2][2];
                 for (int rr = 0; rr < 2; ++rr) {
                     for (int k = 0; k < 3; ++k) {
-                        double t = gx[rr][0] * s.P[k]; t += gx[rr][1] * s.P[lds + k]; t += gx[rr][2] * s.P[2 * lds + k];
+                        double t = gx[rr][0] * s.P[bpl_sym(1, k + 1, ps2)]; t += gx[rr][1] * s.P[bpl_sym(2, k + 1, ps2)];
+                        t += gx[rr][2] * s.P[bpl_sym(3, k + 1, ps2)];
                         T3[rr][k] = t;
                     }
                     for (int c2 = 0; c2 < 2; ++c2) T2[rr][c2] = gz[rr][0] * Wm[0][c2] + gz[rr][1] * Wm[1][c2];
@@ -427,13 +421,13 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
                     for (int c2 = 0; c2 < 2; ++c2) {
                         double t = T3[rr][0] * gx[c2][0]; t += T3[rr][1] * gx[c2][1]; t += T3[rr][2] * gx[c2][2];
                         t += T2[rr][0] * gz[c2][0]; t += T2[rr][1] * gz[c2][1];
-                        s.P[(size_t)(n + rr) * lds + n + c2] = t;
+                        (rr ? r1 : r0)[np + c2] = t;
                     }
                 s.x[n] = s.x[0] + (double)r * cb;                          // :147
                 s.x[n + 1] = s.x[1] + (double)r * sb;                      // :148
                 s.ids[M] = id;                                             // :150
             }
-            M += 1; n += 2;
+            M += 1;
             Sync::sync();
         }
     }
@@ -449,6 +443,20 @@ __device__ __forceinline__ void ekf_work_terms(const int n, const int nm, const 
     w[3] += (double)nm;
 }
 
+// stage the packed covariance of an instance with M landmarks: one bulk copy per plane, both on one mbarrier
+__device__ __forceinline__ void ekf_load_P(const BatchState& b, const EkfSmem& s, const int ps2, const double* gP, const int M) {
+    const uint32_t bytes = (uint32_t)(bpl_plane_doubles(2 + M) * sizeof(double));
+    mbar_expect_tx(s.bar, 2 * bytes);
+    bulk_g2s(s.P, gP, bytes, s.bar);
+    bulk_g2s(s.P + ps2, gP + b.ps2g, bytes, s.bar);
+}
+__device__ __forceinline__ void ekf_store_P(const BatchState& b, const EkfSmem& s, const int ps2, double* gP, const int M) {
+    const uint32_t bytes = (uint32_t)(bpl_plane_doubles(2 + M) * sizeof(double));
+    bulk_s2g(gP, s.P, bytes);
+    bulk_s2g(gP + b.ps2g, s.P + ps2, bytes);
+    bulk_commit();
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // ekf_step_kernel: one reference EKF::update per instance per launch.  Returns true when the mbarrier phase
 // `parity` was consumed.
@@ -459,7 +467,7 @@ __device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterCo
                                              const uint32_t parity) {
     constexpr int WARPS = THREADS / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int lds = L.lds;
+    const int ps2 = L.ps2;
 
     const int4 meta_in = b.meta[inst];
     int nm = (phases & STEP_UPDATE) ? in.n_meas[inst] : 0;
@@ -477,16 +485,8 @@ __device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterCo
     double* gP = b.P + (size_t)inst * b.p_stride;
     double* gx = b.x + (size_t)inst * b.x_stride;
 
-    // ---- stage P: one bulk copy per live row, all completing on one mbarrier
-    {
-        const int ldg = ldg_of(n0);
-        if (warp == 0) {
-            if (lane == 0) { mbar_expect_tx(s.bar, (uint32_t)(n0 * ldg * sizeof(double))); s.iscr[IS_NAN] = 0; s.iscr[IS_DEAD] = 0; }
-            __syncwarp();
-            for (int row = lane; row < n0; row += 32)
-                bulk_g2s(s.P + (size_t)row * lds, gP + (size_t)row * b.fixed_ld, (uint32_t)(ldg * sizeof(double)), s.bar);
-        }
-    }
+    // ---- stage P: one bulk copy per plane
+    if (tid == 0) { s.iscr[IS_NAN] = 0; s.iscr[IS_DEAD] = 0; ekf_load_P(b, s, ps2, gP, M); }
     // ---- meanwhile: state, ids, messages
     for (int i = tid; i < n0; i += THREADS) { const double v = gx[i]; s.x[i] = v; s.xs[i] = v; }
     for (int i = tid; i < M; i += THREADS) s.ids[i] = b.ids[(size_t)inst * b.max_lm + i];
@@ -495,12 +495,12 @@ __device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterCo
     // ---- scalar pre-work while P is in flight
     if ((phases & STEP_PREDICT) && warp == WARPS - 1 && lane == 0)
         ekf_predict_scalars(fc, s, in.fwd[in.cmd_stride ? inst : 0], in.ang[in.cmd_stride ? inst : 0]);
-    if ((phases & STEP_UPDATE) && fc.id_known && warp == 0) ekf_assoc_prepass(s, lane, M, nm, b.max_lm);
+    if ((phases & STEP_UPDATE) && fc.id_known && warp == 0) ekf_assoc_prepass(s, lane, M, nm, b.max_lm, b.max_lm);
     if (warp == 0) mbar_wait(s.bar, parity);     // one warp polls the mbarrier; the others park at the CTA barrier
     CtaSync<THREADS>::sync();
 
     int n_upd = 0;
-    const bool alive = ekf_core<THREADS, CtaSync<THREADS>>(fc, s, lds, b.max_lm, phases, M, nm, status, n_upd);
+    const bool alive = ekf_core<THREADS, CtaSync<THREADS>>(fc, s, ps2, b.max_lm, phases, M, nm, status, n_upd);
 
     // ---- commit, :176-177
     if (!alive) {
@@ -512,19 +512,14 @@ __device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterCo
     for (int i = tid; i < n; i += THREADS) {
         const double v = s.x[i];
         gx[i] = v;
-        if (!isfinite(v) || !isfinite(s.P[(size_t)i * lds + i])) s.iscr[IS_NAN] = 1;
+        if (!isfinite(v) || !isfinite(s.P[bpl_idx(i + 1, i + 1, ps2)])) s.iscr[IS_NAN] = 1;
     }
     for (int i = tid + M_start; i < M; i += THREADS) b.ids[(size_t)inst * b.max_lm + i] = s.ids[i];
     for (int i = tid; i < nm; i += THREADS) { const int a = s.assoc[i]; b.assoc[(size_t)inst * b.max_meas + i] = a < 0 ? -1 : a; }
     fence_proxy_async();     // generic-proxy writes of P must be visible to the bulk-copy engine
     CtaSync<THREADS>::sync();
-    if (warp == 0) {
-        const int ldg = ldg_of(n);
-        for (int row = lane; row < n; row += 32)
-            bulk_s2g(gP + (size_t)row * b.fixed_ld, s.P + (size_t)row * lds, (uint32_t)(ldg * sizeof(double)));
-        bulk_commit();
-    }
     if (tid == 0) {
+        ekf_store_P(b, s, ps2, gP, M);
         if (s.iscr[IS_NAN]) status |= SLAM_STATUS_NAN;
         b.meta[inst] = make_int4(M, status, meta_in.z + ((phases & STEP_PREDICT) ? 1 : 0),   // timestep, :39
                                  (phases & STEP_UPDATE) ? nm : meta_in.w);
@@ -533,15 +528,19 @@ __device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterCo
         ekf_work_terms(n, nm, n_upd, w);
         double* st = b.stats + (size_t)inst * SLAM_NUM_STATS;
         st[8] += w[0]; st[9] += w[1]; st[10] += w[2]; st[11] += w[3];
+        // shared memory may be reused / released once the bulk engine has READ it; global visibility of the writes
+        // is guaranteed at kernel completion
+        bulk_wait_read();
     }
-    // shared memory may be reused / released once the bulk engine has READ it; global visibility of the writes is
-    // guaranteed at kernel completion
-    if (warp == 0) bulk_wait_read();
     return true;
 }
 
+// resident CTAs the register allocation must allow: about 768 threads per SM (<= 80 registers per thread)
+constexpr int step_min_blocks(int threads) { return threads >= 512 ? 1 : 768 / threads; }
+constexpr int sweep_min_blocks(int cw) { return cw == 1 ? 12 : cw == 2 ? 8 : cw == 4 ? 4 : 2; }
+
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
+__global__ void __launch_bounds__(THREADS, step_min_blocks(THREADS))
 ekf_step_kernel(BatchState b, FilterConst fc, StepInputs in, int phases, EkfLaunch L) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EkfSmem s;
@@ -562,12 +561,17 @@ ekf_step_kernel(BatchState b, FilterConst fc, StepInputs in, int phases, EkfLaun
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// ekf_sweep_kernel: T consecutive reference steps of every instance in ONE launch -- simulator (sim_node.py:209-250)
-// -> EKF::update -> error terms -- with the filter resident in shared memory.  A persistent grid pulls instances
-// from a work counter.  CW consumer warps run the filter; one producer warp runs the simulator AHEAD of them
-// (messages double-buffered) and folds the error terms of the step they just finished (pose snapshot), so neither is
-// on the filter's critical path.  Named barriers: FULL[p] producer -> consumers "message of a step with parity p is
-// ready", DONE[p] consumers -> producer "step finished, snapshot[p] valid, message buffer p free".
+// ekf_sweep_kernel: a chunk of T consecutive reference steps of every instance in ONE launch with the filter
+// resident in shared memory.  A persistent grid pulls instances from a work counter.  CW consumer warps run the
+// filter; one producer warp runs AHEAD of them (messages double-buffered) and trails them by one step with the
+// per-step outputs, so neither is on the filter's critical path:
+//   REPLAY = false  Monte-Carlo sweep: simulator (sim_node.py:209-250) -> EKF::update -> error terms;
+//   REPLAY = true   trajectory replay: uploaded [id,r,b] messages -> EKF::update -> pose estimates (publishState).
+// Named barriers: FULL[p] producer -> consumers "message of a step with parity p is ready", DONE[p] consumers ->
+// producer "step finished, snapshot[p] valid, message buffer p free".
+// Chunking: only instances whose progress counter equals a.t0 run; an instance whose insertions would outgrow this
+// launch's tile ABORTS the chunk untouched (nothing committed, progress unchanged) and is picked up by the next
+// launch of the same chunk, which uses a larger tile.
 // Known-ID mode only (the host falls back to per-step launches otherwise): the pre-pass association detects a
 // same-step re-match before the step touches anything, so a dead instance stays at its committed state.
 // ------------------------------------------------------------------------------------------------------------
@@ -575,7 +579,7 @@ enum { BAR_CONS = 1, BAR_FULL0 = 2, BAR_FULL1 = 3, BAR_DONE0 = 4, BAR_DONE1 = 5 
 
 struct SweepSmem {
     float* meas[2];     // [max_meas][3] message of step parity p
-    int* nm;            // [2] detections of step parity p (clamped to max_meas)
+    int* nm;            // [0..1] detections of step parity p, [2] abort flag
     double* snap;       // [2][12] pose (3) + pose covariance (9) after the step of parity p
 };
 
@@ -584,11 +588,9 @@ __device__ __forceinline__ void sweep_smem_bind(const EkfLaunch& L, unsigned cha
     w.nm = (int*)(base + L.off[EO_WNM]); w.snap = (double*)(base + L.off[EO_WSNAP]);
 }
 
-template <int CW>      // consumer warps; the CTA has CW + 1 warps
-__global__ void __launch_bounds__(32 * (CW + 1), 2)
-ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, const float* __restrict__ cmd_fwd,
-                 const float* __restrict__ cmd_ang, const int cmd_stride, const int T, const uint32_t first_step,
-                 int* work_counter, EkfLaunch L) {
+template <int CW, bool REPLAY>      // consumer warps; the CTA has CW + 1 warps
+__global__ void __launch_bounds__(32 * (CW + 1), sweep_min_blocks(CW))
+ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, SweepArgs a, EkfLaunch L) {
     constexpr int NT = 32 * CW;                 // filter threads
     constexpr int THREADS = NT + 32;
     using Sync = NamedSync<NT, BAR_CONS>;
@@ -598,52 +600,67 @@ ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, const 
     ekf_smem_bind(L, smem_raw, s);
     sweep_smem_bind(L, smem_raw, w);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int lds = L.lds;
+    const int ps2 = L.ps2;
+    const int T = a.T;
     const bool producer = warp == CW;
     if (tid == 0) { mbar_init(s.bar, 1); fence_mbar_init(); }
     __syncthreads();
     uint32_t parity = 0;
 
     while (true) {
-        if (tid == 0) s.iscr[IS_WORK] = atomicAdd(work_counter, 1);
+        if (tid == 0) { s.iscr[IS_WORK] = atomicAdd(a.work_counter, 1); w.nm[2] = 0; }
         __syncthreads();
         const int inst = s.iscr[IS_WORK];
         if (inst >= b.batch) break;
         const int4 meta_in = b.meta[inst];
-        const size_t cstep = cmd_stride ? (size_t)b.batch : 1, coff = cmd_stride ? (size_t)inst : 0;
+        if (a.progress[inst] != a.t0 || meta_in.x > L.cap_lm) { __syncthreads(); continue; }   // not this chunk / cannot fit
+        const size_t cstep = a.cmd_stride ? (size_t)b.batch : 1, coff = a.cmd_stride ? (size_t)inst : 0;
+        bool aborted = false;
 
         if (producer) {
-            // ================= producer warp: simulator ahead, error terms behind =================
-            double tr[3];
-            { const double* t = sim.truth + 3 * (size_t)inst; tr[0] = t[0]; tr[1] = t[1]; tr[2] = t[2]; }
+            // ================= producer warp: messages ahead, per-step outputs behind =================
+            double tr[3] = {0, 0, 0};
+            if (!REPLAY) { const double* t = sim.truth + 3 * (size_t)inst; tr[0] = t[0]; tr[1] = t[1]; tr[2] = t[2]; }
             double trp[2][3] = {{0, 0, 0}, {0, 0, 0}};   // truth of the step with parity p
             double eacc[6] = {0, 0, 0, 0, 0, 0};
             int overflow = 0, nm_last = 0;
             for (int t = 0; t <= T; ++t) {
                 if (t < T) {
                     const int p = t & 1;
-                    const int count = sim_get_cmd_warp(lane, sc, sim.lm_xy, sim.n_lm, b.max_meas, sim.k0, sim.k1,
-                                                       sim.instance_offset + (uint32_t)inst, first_step + (uint32_t)t,
-                                                       cmd_fwd[(size_t)t * cstep + coff], cmd_ang[(size_t)t * cstep + coff],
-                                                       tr, w.meas[p]);
-                    if (count > b.max_meas) overflow = 1;
-                    nm_last = count < b.max_meas ? count : b.max_meas;
-                    if (lane == 0) w.nm[p] = nm_last;
-                    trp[p][0] = tr[0]; trp[p][1] = tr[1]; trp[p][2] = tr[2];
+                    if (REPLAY) {
+                        const size_t row = (size_t)t * b.batch + inst;
+                        const int count = a.r_nmeas[row];
+                        nm_last = count < b.max_meas ? count : b.max_meas;
+                        const float* src = a.r_meas + row * (size_t)b.max_meas * 3;
+                        for (int i = lane; i < 3 * nm_last; i += 32) w.meas[p][i] = src[i];
+                        if (lane == 0) w.nm[p] = count;         // raw count: the consumers flag the overflow
+                    } else {
+                        const int count = sim_get_cmd_warp(lane, sc, sim.lm_xy, sim.n_lm, b.max_meas, sim.k0, sim.k1,
+                                                           sim.instance_offset + (uint32_t)inst, a.first_step + (uint32_t)t,
+                                                           a.cmd_fwd[(size_t)t * cstep + coff], a.cmd_ang[(size_t)t * cstep + coff],
+                                                           tr, w.meas[p]);
+                        if (count > b.max_meas) overflow = 1;
+                        nm_last = count < b.max_meas ? count : b.max_meas;
+                        if (lane == 0) w.nm[p] = nm_last;
+                        trp[p][0] = tr[0]; trp[p][1] = tr[1]; trp[p][2] = tr[2];
+                    }
                     named_arrive(BAR_FULL0 + p, THREADS);
                 }
                 if (t >= 1) {
                     const int q = (t - 1) & 1;
                     named_sync(BAR_DONE0 + q, THREADS);          // step t-1 finished: snapshot[q] valid
-                    if (lane == 0) {
-                        const double* sn = w.snap + 12 * q;
+                    if (w.nm[2]) { aborted = true; break; }
+                    const double* sn = w.snap + 12 * q;
+                    if (REPLAY) {
+                        if (a.r_poses != nullptr && lane < 3) a.r_poses[((size_t)(t - 1) * b.batch + inst) * 3 + lane] = sn[lane];
+                    } else if (lane == 0) {
                         double C[3][3];
-                        for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) C[a][c] = sn[3 + 3 * a + c];
+                        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) C[r][c] = sn[3 + 3 * r + c];
                         pose_error_terms(sn[0] - trp[q][0], sn[1] - trp[q][1], wrap_2pi(sn[2] - trp[q][2]), C, eacc);
                     }
                 }
             }
-            if (T > 0) {
+            if (!REPLAY && T > 0 && !aborted) {
                 if (lane == 0) {
                     double* g = b.stats + (size_t)inst * SLAM_NUM_STATS;
                     for (int k = 0; k < 6; ++k) g[k] += eacc[k];
@@ -663,15 +680,7 @@ ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, const 
             double* gP = b.P + (size_t)inst * b.p_stride;
             double* gx = b.x + (size_t)inst * b.x_stride;
             const int n0 = 3 + 2 * M;
-            {
-                const int ldg = ldg_of(n0);
-                if (warp == 0) {
-                    if (lane == 0) { mbar_expect_tx(s.bar, (uint32_t)(n0 * ldg * sizeof(double))); s.iscr[IS_NAN] = 0; s.iscr[IS_DEAD] = 0; }
-                    __syncwarp();
-                    for (int row = lane; row < n0; row += 32)
-                        bulk_g2s(s.P + (size_t)row * lds, gP + (size_t)row * b.fixed_ld, (uint32_t)(ldg * sizeof(double)), s.bar);
-                }
-            }
+            if (tid == 0) { s.iscr[IS_NAN] = 0; s.iscr[IS_DEAD] = 0; s.iscr[IS_OVER] = 0; ekf_load_P(b, s, ps2, gP, M); }
             for (int i = tid; i < n0; i += NT) s.x[i] = gx[i];
             for (int i = tid; i < M; i += NT) s.ids[i] = b.ids[(size_t)inst * b.max_lm + i];
             double wacc[4] = {0, 0, 0, 0};               // work counters, carried by thread 0
@@ -684,51 +693,58 @@ ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, const 
                 const bool frozen = (status & SLAM_STATUS_SAME_STEP_REMATCH) != 0;
                 named_sync(BAR_FULL0 + p, THREADS);              // message of step t is in w.meas[p]
                 nm = w.nm[p];
+                if (nm > b.max_meas) { nm = b.max_meas; status |= SLAM_STATUS_MEAS_OVERFLOW; }
                 if (!frozen) {
                     s.meas = w.meas[p];
                     // ---- phase 0: association (warp 0) | predict trigonometry (last warp) | x_t snapshot
-                    if (warp == 0) ekf_assoc_prepass(s, lane, M, nm, b.max_lm);
+                    if (warp == 0) ekf_assoc_prepass(s, lane, M, nm, b.max_lm, L.cap_lm);
                     if (warp == CW - 1 && lane == 0)
-                        ekf_predict_scalars(fc, s, cmd_fwd[(size_t)t * cstep + coff], cmd_ang[(size_t)t * cstep + coff]);
+                        ekf_predict_scalars(fc, s, a.cmd_fwd[(size_t)t * cstep + coff], a.cmd_ang[(size_t)t * cstep + coff]);
                     for (int i = tid; i < 3 + 2 * M; i += NT) s.xs[i] = s.x[i];
                     Sync::sync();
+                    if (s.iscr[IS_OVER]) {
+                        // the tile of this launch cannot take the insertions of this step: abort the chunk untouched
+                        aborted = true;
+                        if (tid == 0) w.nm[2] = 1;
+                        named_arrive(BAR_DONE0 + p, THREADS);
+                        if (t + 1 < T) named_sync(BAR_FULL0 + ((t + 1) & 1), THREADS);   // drain the message already under way
+                        break;
+                    }
                     int n_upd = 0;
-                    if (ekf_core<NT, Sync>(fc, s, lds, b.max_lm, STEP_PREDICT | STEP_UPDATE, M, nm, status, n_upd)) {
+                    if (ekf_core<NT, Sync>(fc, s, ps2, b.max_lm, STEP_PREDICT | STEP_UPDATE, M, nm, status, n_upd)) {
                         ++timestep;
                         if (tid == 0) ekf_work_terms(3 + 2 * M, nm, n_upd, wacc);
                     }
                 }
-                // pose snapshot for the error terms (the producer folds it while the next step runs)
-                if (tid < 12) w.snap[12 * p + tid] = (tid < 3) ? s.x[tid] : s.P[((tid - 3) / 3) * lds + (tid - 3) % 3];
+                // pose snapshot for the per-step outputs (the producer consumes it while the next step runs)
+                if (tid < 12) w.snap[12 * p + tid] = (tid < 3) ? s.x[tid] : s.P[bpl_sym((tid - 3) / 3 + 1, (tid - 3) % 3 + 1, ps2)];
                 named_arrive(BAR_DONE0 + p, THREADS);
             }
-            // ---- commit the instance
-            const bool frozen = (status & SLAM_STATUS_SAME_STEP_REMATCH) != 0;
-            const int n = 3 + 2 * M;
-            for (int i = tid; i < n; i += NT) {
-                const double v = s.x[i];
-                gx[i] = v;
-                if (!isfinite(v) || !isfinite(s.P[(size_t)i * lds + i])) s.iscr[IS_NAN] = 1;
+            if (!aborted) {
+                // ---- commit the instance
+                const bool frozen = (status & SLAM_STATUS_SAME_STEP_REMATCH) != 0;
+                const int n = 3 + 2 * M;
+                for (int i = tid; i < n; i += NT) {
+                    const double v = s.x[i];
+                    gx[i] = v;
+                    if (!isfinite(v) || !isfinite(s.P[bpl_idx(i + 1, i + 1, ps2)])) s.iscr[IS_NAN] = 1;
+                }
+                for (int i = tid + M_first; i < M; i += NT) b.ids[(size_t)inst * b.max_lm + i] = s.ids[i];
+                if (T > 0 && !frozen)
+                    for (int i = tid; i < nm; i += NT) { const int c = s.assoc[i]; b.assoc[(size_t)inst * b.max_meas + i] = c < 0 ? -1 : c; }
+                fence_proxy_async();
+                Sync::sync();
+                if (tid == 0) {
+                    ekf_store_P(b, s, ps2, gP, M);
+                    if (s.iscr[IS_NAN]) status |= SLAM_STATUS_NAN;
+                    b.meta[inst] = make_int4(M, status, timestep, (T > 0 && !frozen) ? nm : (frozen ? 0 : meta_in.w));
+                    if (M > M_first) atomicMax(b.max_M, M);
+                    double* st = b.stats + (size_t)inst * SLAM_NUM_STATS;
+                    st[8] += wacc[0]; st[9] += wacc[1]; st[10] += wacc[2]; st[11] += wacc[3];
+                    a.progress[inst] = a.t0 + T;
+                    bulk_wait_read();    // the tile is re-filled by the next instance
+                }
             }
-            for (int i = tid + M_first; i < M; i += NT) b.ids[(size_t)inst * b.max_lm + i] = s.ids[i];
-            if (T > 0 && !frozen)
-                for (int i = tid; i < nm; i += NT) { const int a = s.assoc[i]; b.assoc[(size_t)inst * b.max_meas + i] = a < 0 ? -1 : a; }
-            fence_proxy_async();
-            Sync::sync();
-            if (warp == 0) {
-                const int ldg = ldg_of(n);
-                for (int row = lane; row < n; row += 32)
-                    bulk_s2g(gP + (size_t)row * b.fixed_ld, s.P + (size_t)row * lds, (uint32_t)(ldg * sizeof(double)));
-                bulk_commit();
-            }
-            if (tid == 0) {
-                if (s.iscr[IS_NAN]) status |= SLAM_STATUS_NAN;
-                b.meta[inst] = make_int4(M, status, timestep, (T > 0 && !frozen) ? nm : (frozen ? 0 : meta_in.w));
-                if (M > M_first) atomicMax(b.max_M, M);
-                double* st = b.stats + (size_t)inst * SLAM_NUM_STATS;
-                st[8] += wacc[0]; st[9] += wacc[1]; st[10] += wacc[2]; st[11] += wacc[3];
-            }
-            if (warp == 0) bulk_wait_read();    // the tile is re-filled by the next instance
         }
         parity ^= 1u;
         __syncthreads();
@@ -742,11 +758,19 @@ __global__ void reset_kernel(BatchState b, double x0, double y0, double a2, doub
     if (i >= b.batch) return;
     double* x = b.x + (size_t)i * b.x_stride;
     double* P = b.P + (size_t)i * b.p_stride;
-    const int nb = b.base, ld = ldp_of(b.fixed_ld, nb);
+    const int nb = b.base;
     x[0] = x0; x[1] = y0; x[2] = a2; if (nb == 4) x[3] = a3;
-    for (int r = 0; r < nb; ++r) for (int c = 0; c < ld; ++c) P[r * ld + c] = 0.0;
-    P[0] = 0.01 * 0.01; P[ld + 1] = 0.01 * 0.01; P[2 * ld + 2] = 0.005 * 0.005;
-    if (nb == 4) P[3 * ld + 3] = 0.005 * 0.005;
+    if (b.ps2g) {
+        // packed symmetric layout: block rows 0..1 of both planes, diagonal (1,1), (2,2), (3,3) (padded indices)
+        const int live = bpl_plane_doubles(2);
+        for (int c = 0; c < live; ++c) { P[c] = 0.0; P[b.ps2g + c] = 0.0; }
+        P[bpl_idx(1, 1, b.ps2g)] = 0.01 * 0.01; P[bpl_idx(2, 2, b.ps2g)] = 0.01 * 0.01; P[bpl_idx(3, 3, b.ps2g)] = 0.005 * 0.005;
+    } else {
+        const int ld = ldp_of(b.fixed_ld, nb);
+        for (int r = 0; r < nb; ++r) for (int c = 0; c < ld; ++c) P[r * ld + c] = 0.0;
+        P[0] = 0.01 * 0.01; P[ld + 1] = 0.01 * 0.01; P[2 * ld + 2] = 0.005 * 0.005;
+        if (nb == 4) P[3 * ld + 3] = 0.005 * 0.005;
+    }
     b.meta[i] = make_int4(0, 0, 0, 0);
     double* st = b.stats + (size_t)i * SLAM_NUM_STATS;
     for (int k = 0; k < SLAM_NUM_STATS; ++k) st[k] = 0.0;
@@ -762,43 +786,65 @@ static EkfLaunch make_launch(const BatchState& b, int cap_lm, int from_list) {
     L.cap_lm = cap_lm < b.max_lm ? cap_lm : b.max_lm;
     if (L.cap_lm < 1) L.cap_lm = 1;
     L.n_cap = 3 + 2 * L.cap_lm;
-    L.lds = lds_of(L.n_cap);
+    L.ps2 = bpl_plane_doubles(2 + L.cap_lm);
     L.from_list = from_list;
     ekf_smem_layout(b.max_meas, L);
     return L;
 }
 
-size_t ekf_step_smem_bytes(const BatchState& b) { return (size_t)make_launch(b, b.max_lm, 0).smem_bytes; }
+size_t ekf_step_smem_bytes(const BatchState& b) { return (size_t)make_launch(b, b.max_lm, 0).sweep_bytes; }
 
 static constexpr size_t SMEM_PER_SM = 227 * 1024, SMEM_CTA_RESERVED = 1024;
 
-// CTA width for a tile: about 32 resident warps per SM whatever the tile size (registers cap a CTA at 64/thread).
-static int pick_threads(size_t smem) {
-    size_t ipsm = SMEM_PER_SM / (smem + SMEM_CTA_RESERVED);
-    if (ipsm < 1) ipsm = 1;
-    if (ipsm > 32) ipsm = 32;
-    int warps = 1;
-    while (warps * 2 * (int)ipsm <= 32 && warps < 16) warps *= 2;
-    return warps * 32;
+template <int THREADS>
+static int step_occupancy(size_t smem) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ekf_step_kernel<THREADS>, THREADS, smem) != cudaSuccess) nb = 0;
+    return nb;
+}
+
+// CTA width for a tile: the width that keeps the most instances resident per SM (shared memory, registers and the
+// 2048-thread limit decide); among equals the wider CTA (more lanes on each instance's O(n^2) sweep).
+static int pick_threads(size_t smem, int* per_sm_out) {
+    const int widths[5] = {32, 64, 128, 256, 512};
+    const int occ[5] = {step_occupancy<32>(smem), step_occupancy<64>(smem), step_occupancy<128>(smem),
+                        step_occupancy<256>(smem), step_occupancy<512>(smem)};
+    int best = 2;
+    for (int k = 0; k < 5; ++k) {
+        // at least ~24 warps per SM are needed before more instances stop paying; then prefer wider CTAs
+        const long cur = (long)occ[k] * 1000 + widths[k], bst = (long)occ[best] * 1000 + widths[best];
+        const int warps_k = occ[k] * widths[k] / 32;
+        if (occ[k] > 0 && (occ[best] == 0 || (warps_k >= 8 && cur > bst))) best = k;
+    }
+    if (per_sm_out) *per_sm_out = occ[best] > 0 ? occ[best] : 1;
+    return widths[best];
 }
 
 template <int THREADS>
 static cudaError_t set_smem_step(int bytes) {
     return cudaFuncSetAttribute(ekf_step_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
+template <int CW>
+static cudaError_t set_smem_sweep(int bytes) {
+    cudaError_t e = cudaFuncSetAttribute(ekf_sweep_kernel<CW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(ekf_sweep_kernel<CW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
 
 cudaError_t ekf_step_configure(const BatchState& b) {
-    const int bytes = (int)ekf_step_smem_bytes(b);
+    const EkfLaunch L = make_launch(b, b.max_lm, 0);
+    const int bytes = L.smem_bytes;
     cudaError_t e;
     if ((e = set_smem_step<32>(bytes)) != cudaSuccess) return e;
     if ((e = set_smem_step<64>(bytes)) != cudaSuccess) return e;
     if ((e = set_smem_step<128>(bytes)) != cudaSuccess) return e;
     if ((e = set_smem_step<256>(bytes)) != cudaSuccess) return e;
     if ((e = set_smem_step<512>(bytes)) != cudaSuccess) return e;
-    const int sbytes = make_launch(b, b.max_lm, 0).sweep_bytes;
-    if ((e = cudaFuncSetAttribute(ekf_sweep_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sbytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ekf_sweep_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sbytes)) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(ekf_sweep_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, sbytes);
+    const int sbytes = L.sweep_bytes;
+    if ((e = set_smem_sweep<1>(sbytes)) != cudaSuccess) return e;
+    if ((e = set_smem_sweep<2>(sbytes)) != cudaSuccess) return e;
+    if ((e = set_smem_sweep<4>(sbytes)) != cudaSuccess) return e;
+    return set_smem_sweep<8>(sbytes);
 }
 
 static cudaError_t launch_step_threads(int threads, int grid, size_t smem, cudaStream_t st, const BatchState& b,
@@ -824,33 +870,60 @@ cudaError_t launch_ekf_step(const BatchState& b, const FilterConst& fc, const St
         cudaError_t e = cudaMemsetAsync(b.retry_count, 0, sizeof(int), st);
         if (e != cudaSuccess) return e;
     }
-    cudaError_t e = launch_step_threads(force_threads ? force_threads : pick_threads(smem), b.batch, smem, st, b, fc, in, phases, L);
+    cudaError_t e = launch_step_threads(force_threads ? force_threads : pick_threads(smem, nullptr), b.batch, smem, st, b, fc, in, phases, L);
     if (e != cudaSuccess || !limited) return e;
     const EkfLaunch R = make_launch(b, b.max_lm, 1);
     const size_t rsmem = (size_t)R.smem_bytes;
-    const int rthreads = force_threads ? force_threads : pick_threads(rsmem);
-    const int per_sm = (int)(SMEM_PER_SM / (rsmem + SMEM_CTA_RESERVED)) > 0 ? (int)(SMEM_PER_SM / (rsmem + SMEM_CTA_RESERVED)) : 1;
+    int per_sm = 1;
+    int rthreads = pick_threads(rsmem, &per_sm);
+    if (force_threads) { rthreads = force_threads; per_sm = (int)(SMEM_PER_SM / (rsmem + SMEM_CTA_RESERVED)) > 0 ? (int)(SMEM_PER_SM / (rsmem + SMEM_CTA_RESERVED)) : 1; }
     const int grid = b.batch < 148 * per_sm ? b.batch : 148 * per_sm;
     return launch_step_threads(rthreads, grid, rsmem, st, b, fc, in, phases, R);
 }
 
-// Whole sweep in one launch (known-ID EKF batches).  work_counter: device int, zeroed here.
-cudaError_t launch_ekf_sweep(const BatchState& b, const FilterConst& fc, const SimState& sim, const SimConst& sc,
-                             const float* d_fwd, const float* d_ang, int cmd_stride, int T, uint32_t first_step,
-                             int* work_counter, int force_threads, cudaStream_t st) {
-    const EkfLaunch L = make_launch(b, b.max_lm, 0);
+template <int CW, bool REPLAY>
+static int sweep_occupancy(size_t smem) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ekf_sweep_kernel<CW, REPLAY>, 32 * (CW + 1), smem) != cudaSuccess) nb = 0;
+    return nb;
+}
+
+template <int CW, bool REPLAY>
+static void sweep_go(int grid, size_t smem, cudaStream_t st, const BatchState& b, const FilterConst& fc, const SimState& sim,
+                     const SimConst& sc, const SweepArgs& a, const EkfLaunch& L) {
+    ekf_sweep_kernel<CW, REPLAY><<<grid, 32 * (CW + 1), smem, st>>>(b, fc, sim, sc, a, L);
+}
+
+template <bool REPLAY>
+static cudaError_t launch_sweep_t(const BatchState& b, const FilterConst& fc, const SimState& sim, const SimConst& sc,
+                                  const SweepArgs& a, int cap_lm, int force_threads, cudaStream_t st) {
+    const EkfLaunch L = make_launch(b, cap_lm, 0);
     const size_t smem = (size_t)L.sweep_bytes;
-    cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
+    cudaError_t e = cudaMemsetAsync(a.work_counter, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
-    int per_sm = (int)(SMEM_PER_SM / (smem + SMEM_CTA_RESERVED));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 2) per_sm = 2;
+    // filter warps per instance: the count that keeps the most instances resident per SM; among equals the widest
+    const int cws[4] = {1, 2, 4, 8};
+    const int occ[4] = {sweep_occupancy<1, REPLAY>(smem), sweep_occupancy<2, REPLAY>(smem), sweep_occupancy<4, REPLAY>(smem),
+                        sweep_occupancy<8, REPLAY>(smem)};
+    int best = 0;
+    for (int k = 1; k < 4; ++k) if (occ[k] >= occ[best]) best = k;
+    if (force_threads == 32) best = 0; else if (force_threads == 64) best = 1; else if (force_threads == 128) best = 2;
+    else if (force_threads >= 256) best = 3;
+    const int per_sm = occ[best] > 0 ? occ[best] : 1;
     const int grid = b.batch < 148 * per_sm ? b.batch : 148 * per_sm;
-    // force_threads selects the number of filter warps (128 -> 4, 512 -> 12, else 8); one more warp runs the simulator
-    if (force_threads == 128) ekf_sweep_kernel<4><<<grid, 160, smem, st>>>(b, fc, sim, sc, d_fwd, d_ang, cmd_stride, T, first_step, work_counter, L);
-    else if (force_threads == 512) ekf_sweep_kernel<12><<<grid, 416, smem, st>>>(b, fc, sim, sc, d_fwd, d_ang, cmd_stride, T, first_step, work_counter, L);
-    else ekf_sweep_kernel<8><<<grid, 288, smem, st>>>(b, fc, sim, sc, d_fwd, d_ang, cmd_stride, T, first_step, work_counter, L);
+    switch (cws[best]) {
+        case 1: sweep_go<1, REPLAY>(grid, smem, st, b, fc, sim, sc, a, L); break;
+        case 2: sweep_go<2, REPLAY>(grid, smem, st, b, fc, sim, sc, a, L); break;
+        case 4: sweep_go<4, REPLAY>(grid, smem, st, b, fc, sim, sc, a, L); break;
+        default: sweep_go<8, REPLAY>(grid, smem, st, b, fc, sim, sc, a, L); break;
+    }
     return cudaGetLastError();
+}
+
+cudaError_t launch_ekf_sweep(const BatchState& b, const FilterConst& fc, const SimState& sim, const SimConst& sc,
+                             const SweepArgs& a, bool replay, int cap_lm, int force_threads, cudaStream_t st) {
+    return replay ? launch_sweep_t<true>(b, fc, sim, sc, a, cap_lm, force_threads, st)
+                  : launch_sweep_t<false>(b, fc, sim, sc, a, cap_lm, force_threads, st);
 }
 
 }  // namespace slam

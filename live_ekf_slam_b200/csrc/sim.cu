@@ -48,7 +48,8 @@ __global__ void accumulate_error_kernel(BatchState b, SimState s) {
     double yaw, C[3][3];
     if (b.base == 3) {
         yaw = x[2];
-        for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) C[a][c] = P[a * ld + c];
+        for (int a = 0; a < 3; ++a)
+            for (int c = 0; c < 3; ++c) C[a][c] = b.ps2g ? P[bpl_sym(a + 1, c + 1, b.ps2g)] : P[a * ld + c];
     } else {
         // UKF keeps (cos, sin): yaw = atan2(s, c) with Jacobian [-s, c]/(c^2+s^2)
         const double cc = x[2], ss = x[3], q = cc * cc + ss * ss;

@@ -29,7 +29,7 @@ ABI_SYMBOLS = (
     "slam_get_poses", "slam_get_all_status", "slam_get_all_num_landmarks", "slam_set_state",
     "slam_sim_create", "slam_sim_destroy", "slam_sim_reset", "slam_sim_step", "slam_sim_step_device",
     "slam_sim_meas", "slam_sim_n_meas", "slam_sim_get_truth", "slam_sim_get_meas",
-    "slam_run", "slam_run_device", "slam_reset", "slam_step_io", "slam_set_profiling", "slam_get_profile",
+    "slam_run", "slam_run_device", "slam_reset", "slam_step_io", "slam_run_io", "slam_set_profiling", "slam_get_profile",
     "slam_accumulate_error", "slam_get_stats", "slam_reset_stats",
     "slam_kernel_launches", "slam_build_info", "slam_tune",
 )
@@ -89,6 +89,7 @@ def load(path: str | None = None):
     L.slam_run_device.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_uint32]
     L.slam_reset.argtypes = [vp, C.c_float, C.c_float, C.c_float]
     L.slam_step_io.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp]
+    L.slam_run_io.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int]
     L.slam_set_profiling.argtypes = [vp, C.c_int]
     L.slam_get_profile.argtypes = [vp, dp, C.POINTER(C.c_longlong)]
     L.slam_accumulate_error.argtypes = [vp, vp]
@@ -291,6 +292,11 @@ class FilterBatch:
     def step_io(self, fwd, ang, cmd_stride: int, meas, n_meas, poses_out):
         """slam_step_io with caller-owned (ideally pinned) host buffers; asynchronous."""
         self._ck(self._L.slam_step_io(self._h, _ptr(fwd), _ptr(ang), cmd_stride, _ptr(meas), _ptr(n_meas), _ptr(poses_out)))
+
+    def run_io(self, fwd, ang, cmd_stride: int, meas, n_meas, poses_out, T: int):
+        """slam_run_io: a whole recorded run through HOST buffers (numpy arrays, pinned torch tensors or raw
+        addresses); asynchronous -- synchronize() before reading poses_out."""
+        self._ck(self._L.slam_run_io(self._h, _ptr(fwd), _ptr(ang), cmd_stride, _ptr(meas), _ptr(n_meas), _ptr(poses_out), T))
 
     def tune(self, key: int, value: int):
         self._ck(self._L.slam_tune(self._h, key, value))

@@ -63,16 +63,12 @@ def test_config1_single_instance_per_step(shim, oracle):
     print("config1 worst normwise err", worst, "final M", of.M)
 
 
-@pytest.mark.parametrize("step_mode", [1, 2])
-def test_batch_free_running_grid(shim, oracle, step_mode):
-    """BASELINE config 2 at reduced size: 48 instances on the 5x10 grid, 400 steps, free running.
-    step_mode 1 = shared-memory-resident ekf_step_kernel, 2 = HBM-streaming ekf_stream_kernel (the default for
-    known landmark IDs)."""
+def test_batch_free_running_grid(shim, oracle):
+    """BASELINE config 2 at reduced size: 48 instances on the 5x10 grid, 400 steps, free running."""
     p, lm, fwd, ang = H.config2(seed=1, steps=400)
     op = H.oracle_params(oracle, p)
     B = 48
     fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), B, 50, 8)
-    fb.tune(4, step_mode)
     fb.init(0, 0, 0)
     streams = [H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=7, instance=i)[0] for i in range(B)]
     ofs = []
@@ -98,8 +94,7 @@ def test_batch_free_running_grid(shim, oracle, step_mode):
     print("batch worst normwise err", worst)
 
 
-@pytest.mark.parametrize("step_mode", [1, 2])
-def test_teacher_forced_single_steps(shim, oracle, step_mode):
+def test_teacher_forced_single_steps(shim, oracle):
     """Load the oracle's (x, P, ids) of step t into the GPU filter, run ONE step, compare (SURVEY App. E protocol)."""
     p, lm, fwd, ang = H.config2(seed=2, steps=300)
     op = H.oracle_params(oracle, p)
@@ -107,7 +102,6 @@ def test_teacher_forced_single_steps(shim, oracle, step_mode):
     of = oracle.OracleFilter(oracle.EKF_SLAM, op, 50)
     of.init(0, 0, 0)
     fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 2, 50, 8)
-    fb.tune(4, step_mode)
     fb.init(0, 0, 0)
     checked = 0
     for t in range(len(fwd)):
@@ -124,16 +118,13 @@ def test_teacher_forced_single_steps(shim, oracle, step_mode):
     assert checked >= 10
 
 
-@pytest.mark.parametrize("step_mode", [1, 2])
-def test_split_predict_update_matches_fused(shim, oracle, step_mode):
+def test_split_predict_update_matches_fused(shim, oracle):
     p, lm, fwd, ang = H.config2(seed=4, steps=120)
     op = H.oracle_params(oracle, p)
     stream, _ = H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=9, instance=0)
     fused = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 1, 50, 8)
     split = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 1, 50, 8)
     of = oracle.OracleFilter(oracle.EKF_SLAM, op, 50)
-    fused.tune(4, step_mode)
-    split.tune(4, step_mode)
     for f in (fused, split, of):
         f.init(0, 0, 0)
     for t in range(len(fwd)):
@@ -175,13 +166,11 @@ def test_unknown_id_box_gate_association(shim, oracle):
     assert matched > 50
 
 
-@pytest.mark.parametrize("step_mode", [1, 2])
-def test_edge_cases(shim, oracle, step_mode):
+def test_edge_cases(shim, oracle):
     p = H.Params()
     op = H.oracle_params(oracle, p)
     # (a) no detections at all: predict-only steps (ekf.cpp:67-71)
     fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 3, 2, 2)
-    fb.tune(4, step_mode)
     fb.init(0.5, -0.25, 0.3)
     of = oracle.OracleFilter(oracle.EKF_SLAM, op, 2)
     of.init(0.5, -0.25, 0.3)
@@ -260,9 +249,8 @@ def test_filter_classes_mirror_reference_interface(shim, oracle):
         make_filter(bad)
 
 
-@pytest.mark.parametrize("step_mode", [1, 2])
 @pytest.mark.parametrize("cap", [1, 6, 20])
-def test_capacity_limited_launch_and_retry_pass(shim, oracle, cap, step_mode):
+def test_capacity_limited_launch_and_retry_pass(shim, oracle, cap):
     """The first pass is sized for `cap` landmarks; instances that might outgrow it are deferred untouched to the
     full-capacity retry pass.  Results must not depend on the split."""
     p, lm, fwd, ang = H.config2(seed=12, steps=220)
@@ -270,7 +258,6 @@ def test_capacity_limited_launch_and_retry_pass(shim, oracle, cap, step_mode):
     B = 12
     fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), B, 50, 8)
     fb.tune(0, cap)
-    fb.tune(4, step_mode)
     fb.init(0, 0, 0)
     streams = [H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=21, instance=i)[0] for i in range(B)]
     ofs = []
@@ -297,7 +284,6 @@ def test_cta_widths_agree_with_oracle(shim, oracle, threads):
     op = H.oracle_params(oracle, p)
     B = 6
     fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), B, 50, 8)
-    fb.tune(4, 1)          # the shared-memory-resident kernel (known IDs default to the streaming kernel)
     fb.tune(2, threads)
     fb.init(0, 0, 0)
     streams = [H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=31, instance=i)[0] for i in range(B)]
@@ -319,11 +305,13 @@ def test_cta_widths_agree_with_oracle(shim, oracle, threads):
     assert max(o.M for o in ofs) >= 5
 
 
-@pytest.mark.parametrize("threads", [0, 512])
-def test_sweep_kernel_matches_per_step_launches(shim, oracle, threads):
-    """slam_run on a known-ID EKF batch is ONE persistent launch (ekf_sweep_kernel: simulator + filter + error terms,
-    P resident in shared memory for all T steps).  It must reproduce the per-step launch sequence: same association
-    log, landmark ids, messages, truth, statistics; state and covariance to rounding."""
+@pytest.mark.parametrize("threads,chunk,cap", [(0, 32, 0), (512, 1000, 0), (32, 7, 0), (64, 50, 3), (128, 16, 12)])
+def test_sweep_kernel_matches_per_step_launches(shim, oracle, threads, chunk, cap):
+    """slam_run on a known-ID EKF batch runs on the persistent ekf_sweep_kernel (simulator + filter + error terms, P
+    resident in shared memory for a chunk of steps per launch, tile sized from the landmarks held so far).  Whatever
+    the chunk length, the CTA width and the tile capacity (cap > 0 forces small tiles: instances that outgrow them
+    abort the chunk untouched and are redone by the full-capacity launch), it must reproduce the per-step launch
+    sequence: same association log, landmark ids, messages, truth, statistics; state and covariance to rounding."""
     p, lm, fwd, ang = H.config2(seed=4, steps=260)
     B = 40
     res = []
@@ -332,6 +320,8 @@ def test_sweep_kernel_matches_per_step_launches(shim, oracle, threads):
         fb.tune(3, sweep_off)
         if not sweep_off:
             fb.tune(2, threads)
+            fb.tune(5, chunk)
+            fb.tune(0, cap)
         fb.init(0, 0, 0)
         sim = shim.Simulator(fb, lm, seed=77, instance_offset=1000)
         l0 = fb.kernel_launches
@@ -345,7 +335,8 @@ def test_sweep_kernel_matches_per_step_launches(shim, oracle, threads):
                         ts=[fb.timestep(i) for i in range(B)], truth=sim.truth(), meas=m, n=n, stats=fb.stats(),
                         status=fb.all_status(), launches=launches))
     a, b = res
-    assert a["launches"] == 2 and b["launches"] >= 3 * 260
+    n_chunks = -(-200 // chunk) + -(-60 // chunk)
+    assert n_chunks <= a["launches"] <= 2 * n_chunks and b["launches"] >= 3 * 260
     assert a["ids"] == b["ids"] and a["assoc"] == b["assoc"] and a["ts"] == b["ts"] == [260] * B
     np.testing.assert_array_equal(a["truth"], b["truth"])
     np.testing.assert_array_equal(a["n"], b["n"])
@@ -378,3 +369,69 @@ def test_sweep_kernel_freezes_dead_instance(shim, oracle):
     np.testing.assert_array_equal(fb.state(0), x0)
     np.testing.assert_array_equal(fb.cov(0), P0)
     assert fb.timestep(0) == 0 and fb.timestep(1) == 61 and fb.num_landmarks(0) == 0
+
+
+@pytest.mark.parametrize("chunk,cap,poses", [(32, 0, True), (9, 4, True), (1000, 0, False)])
+def test_run_io_replays_recorded_messages(shim, oracle, chunk, cap, poses):
+    """slam_run_io: a whole recorded run through HOST buffers (chunks uploaded / filtered by the replay mode of
+    ekf_sweep_kernel / poses downloaded, pipelined).  Must equal T calls of slam_step + the pose read-back."""
+    p, lm, fwd, ang = H.config2(seed=6, steps=150)
+    op = H.oracle_params(oracle, p)
+    B, T, mm = 10, len(fwd), 8
+    streams = [H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=5, instance=i)[0] for i in range(B)]
+    meas = np.zeros((T, B, mm, 3), dtype=np.float32)
+    nm = np.zeros((T, B), dtype=np.int32)
+    ref = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), B, 50, mm)
+    ref.init(0, 0, 0)
+    ref_poses = np.zeros((T, B, 3))
+    for t in range(T):
+        meas[t], nm[t] = ref.pack_meas([streams[i][t] for i in range(B)])
+        ref.step(fwd[t], ang[t], meas[t], nm[t])
+        ref_poses[t] = ref.poses()
+    fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), B, 50, mm)
+    fb.tune(5, chunk)
+    fb.tune(0, cap)
+    fb.init(0, 0, 0)
+    out = np.full((T, B, 3), np.nan) if poses else None
+    half = 70
+    fb.run_io(fwd[:half], ang[:half], 0, meas[:half], nm[:half], out[:half] if poses else None, half)
+    fb.run_io(fwd[half:], ang[half:], 0, meas[half:], nm[half:], out[half:] if poses else None, T - half)
+    fb.synchronize()
+    if poses:
+        assert np.abs(out - ref_poses).max() <= 1e-12
+    for i in range(B):
+        assert list(fb.landmark_ids(i)) == list(ref.landmark_ids(i)) and list(fb.assoc(i)) == list(ref.assoc(i))
+        assert fb.timestep(i) == T
+        assert H.normwise(fb.state(i), ref.state(i)) <= 1e-12 and H.normwise(fb.cov(i), ref.cov(i)) <= 1e-12
+    of = oracle.OracleFilter(oracle.EKF_SLAM, op, 50)
+    of.init(0, 0, 0)
+    for t in range(T):
+        of.update(fwd[t], ang[t], streams[3][t], oracle.STRUCTURED)
+    _compare(fb, 3, of)
+
+
+def test_run_io_generic_path_unknown_ids(shim, oracle):
+    """slam_run_io for a filter the sweep kernel does not cover (unknown-ID association): chunked uploads feeding
+    per-step launches."""
+    p, lm, fwd, ang = H.config2(seed=8, steps=90)
+    p.landmark_id_is_known = False
+    op = H.oracle_params(oracle, p)
+    B, T, mm = 3, len(fwd), 8
+    streams = [H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=2, instance=i)[0] for i in range(B)]
+    fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), B, 50, mm)
+    fb.tune(5, 25)
+    fb.init(0, 0, 0)
+    meas = np.zeros((T, B, mm, 3), dtype=np.float32)
+    nm = np.zeros((T, B), dtype=np.int32)
+    for t in range(T):
+        meas[t], nm[t] = fb.pack_meas([streams[i][t] for i in range(B)])
+    out = np.zeros((T, B, 3))
+    fb.run_io(fwd, ang, 0, meas, nm, out, T)
+    fb.synchronize()
+    for i in range(B):
+        of = oracle.OracleFilter(oracle.EKF_SLAM, op, 50)
+        of.init(0, 0, 0)
+        for t in range(T):
+            of.update(fwd[t], ang[t], streams[i][t], oracle.STRUCTURED)
+        _compare(fb, i, of)
+        assert np.abs(out[-1, i] - of.state()[:3]).max() <= H.FINAL_TOL
