@@ -30,6 +30,7 @@ struct slam_filter {
     // single large-map instance (P in HBM, deferred rank-2k DMMA update): csrc/ekf_large.cu
     bool large = false;
     LargeState lg{};
+    UkfScratch uk{};                  // HBM scratch between the three launches of a UKF step
     int* h_nmeas_pin = nullptr;       // pinned scratch for the host-side measurement count
     // per-launch timing of the filter-step kernel
     // capacity hint: device max(M) read back with a lag of HINT_LAG launches (never waited on in steady state)
@@ -174,6 +175,16 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
     if (kind == SLAM_UKF_SLAM) {
         b.sigma_stride = (long long)b.n_max * (2 * b.n_max + 1);
         b.sigma = nullptr;   // allocated lazily by slam_get_sigma_points
+        UkfScratch& u = h->uk;
+        u.n_max = b.n_max;
+        u.rot_cap = 2LL * b.n_max * b.n_max;        // ~0.85 n^2 rotations are typical
+        u.swp_cap = 6 * b.n_max;                    // ~1.7 n sweeps are typical
+        CK(cudaMalloc(&u.Zg, sizeof(double) * (size_t)batch * b.n_max * b.n_max));
+        CK(cudaMalloc(&u.dg, sizeof(double) * (size_t)batch * b.n_max));
+        CK(cudaMalloc(&u.eg, sizeof(double) * (size_t)batch * b.n_max));
+        CK(cudaMalloc(&u.rot, sizeof(double2) * (size_t)batch * u.rot_cap));
+        CK(cudaMalloc(&u.swp, sizeof(int2) * (size_t)batch * u.swp_cap));
+        CK(cudaMalloc(&u.nswp, sizeof(int) * batch));
     }
     CK(cudaMalloc(&h->d_fwd, sizeof(float) * batch));
     CK(cudaMalloc(&h->d_ang, sizeof(float) * batch));
@@ -207,6 +218,7 @@ int slam_destroy(slam_handle_t h) {
     BatchState& b = h->b;
     cudaFree(b.P); cudaFree(b.x); cudaFree(b.ids); cudaFree(b.meta);
     cudaFree(b.assoc); cudaFree(b.stats); cudaFree(b.sigma);
+    cudaFree(h->uk.Zg); cudaFree(h->uk.dg); cudaFree(h->uk.eg); cudaFree(h->uk.rot); cudaFree(h->uk.swp); cudaFree(h->uk.nswp);
     cudaFree(b.retry_list); cudaFree(b.retry_count); cudaFree(b.max_M); cudaFree(h->d_work); cudaFree(h->d_progress);
     if (h->h_run_hint) cudaFreeHost(h->h_run_hint);
     for (int i = 0; i < slam_filter::HINT_RING; ++i) if (h->run_ev[i]) cudaEventDestroy(h->run_ev[i]);
@@ -319,7 +331,7 @@ static int do_step(slam_filter* h, const float* d_fwd, const float* d_ang, int c
     if (h->kind == SLAM_EKF_SLAM) {
         CK(launch_ekf_step(h->b, h->fc, in, phases, cap, h->force_threads, h->stream));
     }
-    else CK(launch_ukf_step(h->b, h->fc, in, h->stream));
+    else { CK(launch_ukf_step(h->b, h->fc, in, h->uk, h->stream)); h->launches += 2; }
     if (h->profiling) { CK(cudaEventRecord(h->ev[h->ev_used + 1], h->stream)); h->ev_used += 2; }
     {
         const int slot = (int)(h->step_seq % slam_filter::HINT_RING);

@@ -177,7 +177,19 @@ cudaError_t launch_ekf_step(const BatchState& b, const FilterConst& fc, const St
 size_t ekf_step_smem_bytes(const BatchState& b);
 cudaError_t ekf_step_configure(const BatchState& b);
 
-cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, cudaStream_t st);
+// HBM scratch between the three launches of a UKF step (csrc/ukf_batch.cu)
+struct UkfScratch {
+    double* Zg;         // [batch][n_max * n_max]  Q^T of the tridiagonalisation (compact, leading dimension n)
+    double* dg;         // [n_max][batch]  diagonal of T -> eigenvalues
+    double* eg;         // [n_max][batch]  off-diagonal of T
+    double2* rot;       // [batch][rot_cap]  (c, s) of every QL plane rotation, in generation order
+    int2* swp;          // [batch][swp_cap]  (l, m) range of every QL sweep
+    int* nswp;          // [batch]  number of sweeps logged; -1: log overflow (the back kernel redoes the QL itself)
+    long long rot_cap;
+    int swp_cap;
+    int n_max;
+};
+cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, const UkfScratch& u, cudaStream_t st);
 size_t ukf_step_smem_bytes(const BatchState& b);
 cudaError_t ukf_step_configure(const BatchState& b);
 

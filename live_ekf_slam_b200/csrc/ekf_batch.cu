@@ -300,18 +300,14 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
                         S00 += a0 * H[c]; S01 += a0 * H[5 + c]; S10 += a1 * H[c]; S11 += a1 * H[5 + c];
                     }
                     S00 += fc.W00; S11 += fc.W11;
-                    // S^-1 by partial-pivot LU like Eigen's dynamic inverse() (:135); the two columns of the inverse
-                    // are solved on two lanes (three dependent divisions instead of five)
-                    const bool sw = fabs(S10) > fabs(S00);
-                    const double a00 = sw ? S10 : S00, a01 = sw ? S11 : S01, a10 = sw ? S00 : S10, a11 = sw ? S01 : S11;
-                    const double l10 = a10 / a00, u11 = a11 - l10 * a01;
-                    const bool col1 = (lane & 1) != 0;
-                    // column `col` of the permuted identity: (b0, b1)
-                    const double b0 = (sw != col1) ? 0.0 : 1.0, b1 = (sw != col1) ? 1.0 : 0.0;
-                    const double y1 = b1 - l10 * b0;
-                    const double i1c = y1 / u11;                           // S^-1(1, col)
-                    const double i0c = (b0 - a01 * i1c) / a00;             // S^-1(0, col)
-                    if (lane < 2) { s.sc[SC_I00 + lane] = i0c; s.sc[SC_I00 + 2 + lane] = i1c; }   // i00 i01 i10 i11
+                    // S^-1 (:135).  Eigen's dynamic inverse() is a partial-pivot LU (three dependent divisions); S = H P H^T
+                    // + W is a well-conditioned 2x2, so the adjugate form -- ONE division on the critical path of every
+                    // landmark update -- agrees with it to a few ulp (the oracle keeps the LU)
+                    const double idet = 1.0 / (S00 * S11 - S01 * S10);
+                    if (lane == 0) {
+                        s.sc[SC_I00] = S11 * idet; s.sc[SC_I00 + 1] = -S01 * idet;
+                        s.sc[SC_I00 + 2] = -S10 * idet; s.sc[SC_I00 + 3] = S00 * idet;
+                    }
                     if (lane == 0) { s.sc[SC_Q0] = q0; s.sc[SC_Q0 + 1] = q1; s.sc[SC_Q0 + 2] = q2; s.sc[SC_Q0 + 3] = q3; }
                 }
             }

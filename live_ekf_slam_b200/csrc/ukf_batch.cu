@@ -15,6 +15,14 @@
 // so the step is dominated by the eigendecomposition (Householder tridiagonalisation + implicit QL, 9 n^3 nominal):
 // the UKF batch is FP64-compute bound, not HBM bound.  P stays in global memory (L2) with a fixed
 // leading dimension; only Z lives in shared memory, which lets two CTAs share an SM.
+//
+// A step is THREE launches, split where the parallelism changes shape:
+//   ukf_front_kernel  CTA per instance: Y, Householder tridiagonalisation, explicit Q^T  -> HBM scratch (d, e, Q^T)
+//   ukf_ql_kernel     THREAD per instance: implicit QL on (d, e) -- a serial chain of ~0.85 n^2 plane rotations, each a
+//                     dependent rsqrt; one lane per filter runs thousands of these chains side by side instead of
+//                     stalling a whole CTA on one thread -- eigenvalues + rotation log -> HBM scratch
+//   ukf_back_kernel   CTA per instance: replays the rotation log on Q^T (thread per eigenvector component), then the
+//                     sigma-point algebra, landmark updates and insertions.
 #include "common.cuh"
 
 #include <climits>
@@ -97,24 +105,28 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* red) {
 __device__ __forceinline__ float yaw_of(double c, double s) { return (float)remainder(atan2(s, c), TWO_PI_REF); }
 
 // ---------------------------------------------------------------------------------------------------------
-// Symmetric eigendecomposition of the n x n matrix in A (full storage, leading dimension lds), in place:
-// on exit d[0..n) holds the eigenvalues (unsorted) and A holds Z^T (row k = eigenvector k).
-// Householder tridiagonalisation (LAPACK dsytd2 'L' organisation, one thread per column of the trailing block),
-// explicit Q (dorg2r organisation), in-place transpose, implicit QL with the rotation sequence of each sweep
-// generated by one thread and applied by one thread per row.  Scratch: v, p, w, tau (n each), cs (2n).
+// Symmetric eigendecomposition of the n x n matrix in A (full storage, leading dimension lds), in two parts.
+//
+// tridiag_q: Householder tridiagonalisation (LAPACK dsytd2 'L' organisation) and the explicit orthogonal factor
+// (dorg2r organisation), then an in-place transpose: on exit d / e hold the tridiagonal matrix (e[k] couples k and
+// k+1) and A holds Q^T.  Threads are mapped 2-D on the trailing block: consecutive lanes own consecutive columns
+// (conflict-free shared-memory rows), G = 256 / columns row groups split the long inner loops, partial sums meet in
+// `part` ([8][n]).  Scratch: v, p, w, tau (n each).
+//
+// ql_serial: implicit QL on (d, e) (EISPACK tql2 organisation) with each sweep's rotations generated by one thread
+// and applied to A = Z^T by one thread per column.  Only the fall-back of the back kernel (rotation log overflow).
 // ---------------------------------------------------------------------------------------------------------
-__device__ void eigh_smem(double* A, const int lds, const int n, double* d, double* e, double* scratch, double* red) {
+__device__ void tridiag_q(double* A, const int lds, const int n, double* d, double* e, double* scratch, double* part, double* red) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* v = scratch;            // [n]
     double* p = scratch + n;        // [n]
     double* w = scratch + 2 * n;    // [n]
     double* tau = scratch + 3 * n;  // [n]
-    double* csc = scratch + 4 * n;  // [n]
-    double* css = scratch + 5 * n;  // [n]
 
     // ---- reduction to tridiagonal form: A = Q T Q^T
     for (int k = 0; k < n - 1; ++k) {
         const int m0 = k + 1;                      // first row/col of the trailing block
+        const int m = n - m0;                      // its size
         if (warp == 0) {
             double ss = 0.0;
             for (int i = k + 2 + lane; i < n; i += 32) { const double a = A[(size_t)i * lds + k]; ss += a * a; }
@@ -141,23 +153,56 @@ __device__ void eigh_smem(double* A, const int lds, const int n, double* d, doub
                 A[(size_t)i * lds + k] = vi;        // keep the reflector in column k
             }
             __syncthreads();
+            // 2-D mapping: thread -> (column c, row group g); rows of group g: m0 + g*rb .. (exclusive end clipped)
+            int G = UKF_THREADS / m; if (G > 8) G = 8; if (G < 1) G = 1;
+            const int g = tid / m, cl = tid - g * m;
+            const int rb = (m + G - 1) / G;
+            const bool act = g < G;
+            const int c = m0 + cl;
+            const int r_lo = m0 + g * rb, r_hi = (r_lo + rb < n) ? r_lo + rb : n;
             // p = tau * A22 * v  (column c of the symmetric block, conflict-free), and p^T v
+            if (m > UKF_THREADS) {                  // (never for n_max <= 256) one group, strided columns
+                for (int cc = m0 + tid; cc < n; cc += UKF_THREADS) {
+                    double acc = 0.0;
+                    for (int i = m0; i < n; ++i) acc += A[(size_t)i * lds + cc] * v[i];
+                    part[cc] = acc;
+                }
+            } else if (act) {
+                double a0 = 0.0, a1 = 0.0;
+                int i = r_lo;
+                for (; i + 1 < r_hi; i += 2) {
+                    a0 += A[(size_t)i * lds + c] * v[i];
+                    a1 += A[(size_t)(i + 1) * lds + c] * v[i + 1];
+                }
+                if (i < r_hi) a0 += A[(size_t)i * lds + c] * v[i];
+                part[g * n + c] = a0 + a1;
+            }
+            __syncthreads();
             double pv[1] = {0.0};
-            for (int c = m0 + tid; c < n; c += UKF_THREADS) {
+            const int Gs = (m > UKF_THREADS) ? 1 : G;
+            for (int cc = m0 + tid; cc < n; cc += UKF_THREADS) {
                 double acc = 0.0;
-                for (int i = m0; i < n; ++i) acc += A[(size_t)i * lds + c] * v[i];
+                for (int q = 0; q < Gs; ++q) acc += part[q * n + cc];
                 acc *= tk;
-                p[c] = acc;
-                pv[0] += acc * v[c];
+                p[cc] = acc;
+                pv[0] += acc * v[cc];
             }
             block_sum<1>(pv, red + 8);
             const double a2 = -0.5 * tk * pv[0];
-            for (int c = m0 + tid; c < n; c += UKF_THREADS) w[c] = p[c] + a2 * v[c];
+            for (int cc = m0 + tid; cc < n; cc += UKF_THREADS) w[cc] = p[cc] + a2 * v[cc];
             __syncthreads();
             // A22 -= v w^T + w v^T   (both triangles kept; the two products are added symmetrically)
-            for (int c = m0 + tid; c < n; c += UKF_THREADS) {
+            if (m > UKF_THREADS) {
+                for (int cc = m0 + tid; cc < n; cc += UKF_THREADS) {
+                    const double vc = v[cc], wc = w[cc];
+                    for (int i = m0; i < n; ++i) {
+                        const double t1 = __dmul_rn(v[i], wc), t2 = __dmul_rn(w[i], vc);
+                        A[(size_t)i * lds + cc] -= __dadd_rn(t1, t2);
+                    }
+                }
+            } else if (act) {
                 const double vc = v[c], wc = w[c];
-                for (int i = m0; i < n; ++i) {
+                for (int i = r_lo; i < r_hi; ++i) {
                     const double t1 = __dmul_rn(v[i], wc), t2 = __dmul_rn(w[i], vc);
                     A[(size_t)i * lds + c] -= __dadd_rn(t1, t2);
                 }
@@ -185,13 +230,31 @@ __device__ void eigh_smem(double* A, const int lds, const int n, double* d, doub
     for (int j = n - 3; j >= 0; --j) {
         const double tj = tau[j];
         const int r0 = 1 + j;                              // row/col of B[j][j] in A
-        // apply H_j to B[j:, j+1:] from the left: column c owned by one thread
-        for (int c = r0 + 1 + tid; c < n; c += UKF_THREADS) {
-            double t = 0.0;                                // v^T B[:,c] with v[j] = 1 and B[j][c] = 0 on entry
-            for (int i = r0 + 1; i < n; ++i) t += A[(size_t)i * lds + r0] * A[(size_t)i * lds + c];
+        const int m = n - (r0 + 1);                        // columns r0+1 .. n-1 (and rows)
+        // apply H_j to B[j:, j+1:] from the left: t[c] = tau * v^T B[:,c] (v[j] = 1, B[j][c] = 0 on entry)
+        int G = UKF_THREADS / m; if (G > 8) G = 8; if (G < 1) G = 1;
+        const int g = tid / m, cl = tid - g * m;
+        const int rb = (m + G - 1) / G;
+        const bool act = g < G;
+        const int c = r0 + 1 + cl;
+        const int r_lo = r0 + 1 + g * rb, r_hi = (r_lo + rb < n) ? r_lo + rb : n;
+        if (act) {
+            double a0 = 0.0, a1 = 0.0;
+            int i = r_lo;
+            for (; i + 1 < r_hi; i += 2) {
+                a0 += A[(size_t)i * lds + r0] * A[(size_t)i * lds + c];
+                a1 += A[(size_t)(i + 1) * lds + r0] * A[(size_t)(i + 1) * lds + c];
+            }
+            if (i < r_hi) a0 += A[(size_t)i * lds + r0] * A[(size_t)i * lds + c];
+            part[g * n + c] = a0 + a1;
+        }
+        __syncthreads();
+        if (act) {
+            double t = 0.0;
+            for (int q = 0; q < G; ++q) t += part[q * n + c];
             t *= tj;
-            A[(size_t)r0 * lds + c] = -t;
-            for (int i = r0 + 1; i < n; ++i) A[(size_t)i * lds + c] -= A[(size_t)i * lds + r0] * t;
+            if (g == 0) A[(size_t)r0 * lds + c] = -t;
+            for (int i = r_lo; i < r_hi; ++i) A[(size_t)i * lds + c] -= A[(size_t)i * lds + r0] * t;
         }
         __syncthreads();
         for (int i = r0 + tid; i < n; i += UKF_THREADS)
@@ -199,7 +262,6 @@ __device__ void eigh_smem(double* A, const int lds, const int n, double* d, doub
         for (int i = 1 + tid; i < r0; i += UKF_THREADS) A[(size_t)i * lds + r0] = 0.0;
         __syncthreads();
     }
-    if (n == 2) { /* Q = I already */ }
 
     // ---- transpose in place: A <- Q^T so that a QL rotation touches two ROWS (conflict-free per-row threads)
     for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
@@ -210,8 +272,12 @@ __device__ void eigh_smem(double* A, const int lds, const int n, double* d, doub
         }
     }
     __syncthreads();
+}
 
-    // ---- implicit QL on (d, e), e[k] couples k and k+1 (EISPACK tql2 organisation)
+__device__ void ql_serial(double* A, const int lds, const int n, double* d, double* e, double* scratch, double* red) {
+    const int tid = threadIdx.x;
+    double* csc = scratch;          // [n]
+    double* css = scratch + n;      // [n]
     int* ctl = reinterpret_cast<int*>(red + 140);          // [0]=l-range start, [1]=m, [2]=done flag
     double f = 0.0, tst1 = 0.0;                            // live in thread 0 only
     const double eps = 2.220446049250313e-16;
@@ -242,9 +308,9 @@ __device__ void eigh_smem(double* A, const int lds, const int n, double* d, doub
                         c3 = c2; c2 = c; s2 = s;
                         g = c * e[i];
                         h = c * pp;
-                        r = sqrt(pp * pp + e[i] * e[i]);
+                        const double rinv = rsqrt(pp * pp + e[i] * e[i]);
+                        r = (pp * pp + e[i] * e[i]) * rinv;
                         e[i + 1] = s * r;
-                        const double rinv = 1.0 / r;
                         s = e[i] * rinv;
                         c = pp * rinv;
                         pp = c * d[i] - s * g;
@@ -275,6 +341,121 @@ __device__ void eigh_smem(double* A, const int lds, const int n, double* d, doub
         }
         __syncthreads();
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ukf_ql_kernel: implicit QL (EISPACK tql2 organisation, the same recurrences as ql_serial) on the tridiagonal
+// matrices of ALL instances at once, one THREAD per instance.  (d, e) live in shared memory as [k][lane]; every
+// plane rotation (c, s) is appended to the instance's log in HBM together with the (l, m) range of its sweep, for the
+// back kernel to replay on Q^T.  On success the eigenvalues overwrite dg and nswp = number of sweeps; if a log would
+// overflow, nswp = -1 and dg / eg stay untouched (the back kernel then runs ql_serial itself).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int QL_LANES = 32;
+
+__global__ void __launch_bounds__(QL_LANES)
+ukf_ql_kernel(UkfScratch u, const int4* __restrict__ meta, const int batch) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const int inst = blockIdx.x * QL_LANES + lane;
+    if (inst >= batch) return;
+    if (meta[inst].y & SLAM_STATUS_SAME_STEP_REMATCH) return;
+    const int n = 4 + 2 * meta[inst].x;
+    double* sd = reinterpret_cast<double*>(smem_raw);           // [n_max][32]
+    double* se = sd + (size_t)u.n_max * QL_LANES;               // [n_max][32]
+#define D_(k) sd[(k) * QL_LANES + lane]
+#define E_(k) se[(k) * QL_LANES + lane]
+    for (int k = 0; k < n; ++k) { D_(k) = u.dg[(size_t)k * batch + inst]; E_(k) = u.eg[(size_t)k * batch + inst]; }
+    double2* rot = u.rot + (size_t)inst * u.rot_cap;
+    int2* swp = u.swp + (size_t)inst * u.swp_cap;
+    long long nrot = 0;
+    int nsw = 0;
+    bool over = false;
+    double f = 0.0, tst1 = 0.0;
+    const double eps = 2.220446049250313e-16;
+    for (int l = 0; l < n && !over; ++l) {
+        int iter = 0;
+        while (true) {
+            if (iter == 0) { const double t = fabs(D_(l)) + fabs(E_(l)); if (t > tst1) tst1 = t; }
+            int m = l;
+            while (m < n - 1) { if (fabs(E_(m)) <= eps * tst1) break; ++m; }
+            if (m == l || iter >= 60) { D_(l) += f; E_(l) = 0.0; break; }
+            if (nsw >= u.swp_cap || nrot + (m - l) > u.rot_cap) { over = true; break; }
+            swp[nsw++] = make_int2(l, m);
+            double g = D_(l);
+            const double el = E_(l);
+            double pp = (D_(l + 1) - g) / (2.0 * el);
+            double r = sqrt(pp * pp + 1.0);
+            if (pp < 0) r = -r;
+            D_(l) = el / (pp + r);
+            D_(l + 1) = el * (pp + r);
+            const double dl1 = D_(l + 1);
+            double h = g - D_(l);
+            for (int i = l + 2; i < n; ++i) D_(i) -= h;
+            f += h;
+            pp = D_(m);
+            double c = 1.0, c2 = c, c3 = c, s = 0.0, s2 = 0.0;
+            const double el1 = E_(l + 1);
+            double ei = E_(m - 1), di = D_(m - 1);           // operands of the next rotation, fetched one ahead
+            for (int i = m - 1; i >= l; --i) {
+                const double e_i = ei, d_i = di;
+                if (i > l) { ei = E_(i - 1); di = D_(i - 1); }
+                c3 = c2; c2 = c; s2 = s;
+                g = c * e_i;
+                h = c * pp;
+                const double rr = pp * pp + e_i * e_i;
+                const double rinv = rsqrt(rr);
+                E_(i + 1) = s * (rr * rinv);
+                s = e_i * rinv;
+                c = pp * rinv;
+                pp = c * d_i - s * g;
+                D_(i + 1) = h + s * (c * g + s * d_i);
+                rot[nrot++] = make_double2(c, s);
+            }
+            pp = -s * s2 * c3 * el1 * E_(l) / dl1;
+            E_(l) = s * pp;
+            D_(l) = c * pp;
+            ++iter;
+        }
+    }
+    if (over) { u.nswp[inst] = -1; return; }
+    for (int k = 0; k < n; ++k) u.dg[(size_t)k * batch + inst] = D_(k);
+    u.nswp[inst] = nsw;
+#undef D_
+#undef E_
+}
+
+// replay the rotation log of the QL kernel on A = Q^T -> Z^T: thread r owns component r of every eigenvector; the log
+// is staged through shared memory in pieces (stage: 2 * STAGE doubles).
+constexpr int ROT_STAGE = 256;
+__device__ void ql_replay(double* A, const int lds, const int n, const double2* __restrict__ rot, const int2* __restrict__ swp,
+                          const int nsw, double2* stage) {
+    const int tid = threadIdx.x;
+    long long base = 0;
+    for (int sidx = 0; sidx < nsw; ++sidx) {
+        const int2 lm = swp[sidx];
+        const int l = lm.x, m = lm.y, cnt = m - l;
+        double fz = (tid < n) ? A[(size_t)m * lds + tid] : 0.0;
+        for (int done = 0; done < cnt; done += ROT_STAGE) {
+            const int piece = (cnt - done < ROT_STAGE) ? cnt - done : ROT_STAGE;
+            __syncthreads();                               // previous piece fully consumed
+            for (int q = tid; q < piece; q += UKF_THREADS) stage[q] = rot[base + done + q];
+            __syncthreads();
+            if (tid < n) {
+                int i = m - 1 - done;
+                double zi = A[(size_t)i * lds + tid];
+                for (int q = 0; q < piece; ++q, --i) {
+                    const double2 cs = stage[q];
+                    const double zn = (q + 1 < piece) ? A[(size_t)(i - 1) * lds + tid] : 0.0;   // next row, fetched ahead
+                    A[(size_t)(i + 1) * lds + tid] = cs.y * zi + cs.x * fz;
+                    fz = cs.x * zi - cs.y * fz;
+                    zi = zn;
+                }
+            }
+        }
+        if (tid < n) A[(size_t)l * lds + tid] = fz;
+        base += cnt;
+    }
+    __syncthreads();
 }
 
 // rows r0.. of S = Z sqrt(D+) Z^T:  out[q][c] = sum_k Zt[k][rows[q]] * sq[k] * Zt[k][c]   (thread per column c)
@@ -336,50 +517,31 @@ __device__ __forceinline__ void s_times(const double* Zt, const int lds, const i
     __syncthreads();
 }
 
+// ---- launch 1 of 3: Y = scale * sym(P) (ukf.cpp:112-114), landmark block of P_pred seeded with 2 w Y, Householder
+//      tridiagonalisation + explicit Q^T -> HBM scratch
 __global__ void __launch_bounds__(UKF_THREADS, 2)
-ukf_step_kernel(BatchState b, FilterConst fc, StepInputs in) {
+ukf_front_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     UkfSmem s;
     ukf_smem_carve(b, smem_raw, &s);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int inst = blockIdx.x;
     const int lds = b.lds;
     const int ldp = b.fixed_ld;                    // global leading dimension of P (fixed for the UKF)
-    const int nmp = ldg_of(b.n_max), nsm = 2 * b.n_max + 2;
-
     const int4 meta_in = b.meta[inst];
-    int nm = in.n_meas[inst];
-    int status = meta_in.y;
-    int M = meta_in.x;
-    const int M_start = M;
+    if (meta_in.y & SLAM_STATUS_SAME_STEP_REMATCH) return;
+    const int M = meta_in.x;
     const int n = 4 + 2 * M;                       // ukf.cpp:167 (state size of this step's sigma points)
-    const int ns = 2 * n + 1;
-    if (nm > b.max_meas) { nm = b.max_meas; status |= SLAM_STATUS_MEAS_OVERFLOW; }
     double* gP = b.P + (size_t)inst * b.p_stride;
-    double* gx = b.x + (size_t)inst * b.x_stride;
-
-    for (int i = tid; i < n; i += UKF_THREADS) { const double v = gx[i]; s.x[i] = v; }
-    for (int i = tid; i < M; i += UKF_THREADS) s.ids[i] = b.ids[(size_t)inst * b.max_lm + i];
-    for (int i = tid; i < 3 * nm; i += UKF_THREADS) s.meas[i] = in.meas[(size_t)inst * b.max_meas * 3 + i];
-    if (tid == 0) { s.iscr[0] = INT_MAX; s.iscr[1] = INT_MAX; s.iscr[2] = 0; }
     // P -> A (row loads are coalesced)
     for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
         const int i = idx / n, j = idx - i * n;
         s.A[(size_t)i * lds + j] = gP[(size_t)i * ldp + j];
     }
     __syncthreads();
-
-    // weights and scale are float-valued (ukf.cpp:35,114,175; SURVEY App. A)
     const float W0f = 0.2f;                                                // filter.h:207
-    const double W0 = (double)W0f;
     const double wgt = (double)((1 - W0f) / (2 * n));                      // :175
     const double scale = (double)((2 * M + 4) / (1 - W0f));                // :114
-    const double sw = W0 + (double)(2 * n) * wgt;                          // sum of the 2n+1 weights (not 1)
-    const float u_d = in.fwd[in.cmd_stride ? inst : 0], u_th = in.ang[in.cmd_stride ? inst : 0];
-    const float yaw_prior = yaw_of(s.x[2], s.x[3]);                        // :182 and :139 (prior x_t)
-    const double cy = (double)cos_f(yaw_prior), sy = (double)sin_f(yaw_prior);
-    const double Qd[4] = {fc.V00 * cy, fc.V00 * sy, fc.V11 * cy, fc.V11 * sy};   // :183-186
-
     // ---- nearestSPD input: Y = 0.5 (P + P^T) * scale (:112-114); and P_LL <- 2 w Y (landmark block of P_pred
     //      before the clipped-eigenvalue correction)
     for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
@@ -395,9 +557,71 @@ ukf_step_kernel(BatchState b, FilterConst fc, StepInputs in) {
         if (i >= 4 && j >= 4) gP[(size_t)i * ldp + j] = (2.0 * wgt) * s.A[(size_t)i * lds + j];
     }
     __syncthreads();
+    // ---- first half of the eigendecomposition (:116-118)
+    tridiag_q(s.A, lds, n, s.d, s.e, s.pool, s.Xp, s.red);     // Xp ([4][2 n_max + 2]) is free in this launch
+    double* Zg = u.Zg + (size_t)inst * u.n_max * u.n_max;
+    for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
+        const int i = idx / n, j = idx - i * n;
+        Zg[idx] = s.A[(size_t)i * lds + j];
+    }
+    for (int k = tid; k < n; k += UKF_THREADS) { u.dg[(size_t)k * b.batch + inst] = s.d[k]; u.eg[(size_t)k * b.batch + inst] = s.e[k]; }
+}
 
-    // ---- eigendecomposition (:116-118) -> s.d eigenvalues, s.A = Z^T
-    eigh_smem(s.A, lds, n, s.d, s.e, s.pool, s.red);
+// ---- launch 3 of 3: rotation replay -> Z^T, then the sigma-point algebra, updates, insertions, commit
+__global__ void __launch_bounds__(UKF_THREADS, 2)
+ukf_back_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    UkfSmem s;
+    ukf_smem_carve(b, smem_raw, &s);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int inst = blockIdx.x;
+    const int lds = b.lds;
+    const int ldp = b.fixed_ld;                    // global leading dimension of P (fixed for the UKF)
+    const int nmp = ldg_of(b.n_max), nsm = 2 * b.n_max + 2;
+
+    const int4 meta_in = b.meta[inst];
+    int nm = in.n_meas[inst];
+    int status = meta_in.y;
+    if (status & SLAM_STATUS_SAME_STEP_REMATCH) return;
+    int M = meta_in.x;
+    const int M_start = M;
+    const int n = 4 + 2 * M;                       // ukf.cpp:167 (state size of this step's sigma points)
+    const int ns = 2 * n + 1;
+    if (nm > b.max_meas) { nm = b.max_meas; status |= SLAM_STATUS_MEAS_OVERFLOW; }
+    double* gP = b.P + (size_t)inst * b.p_stride;
+    double* gx = b.x + (size_t)inst * b.x_stride;
+
+    for (int i = tid; i < n; i += UKF_THREADS) { const double v = gx[i]; s.x[i] = v; }
+    for (int i = tid; i < M; i += UKF_THREADS) s.ids[i] = b.ids[(size_t)inst * b.max_lm + i];
+    for (int i = tid; i < 3 * nm; i += UKF_THREADS) s.meas[i] = in.meas[(size_t)inst * b.max_meas * 3 + i];
+    if (tid == 0) { s.iscr[0] = INT_MAX; s.iscr[1] = INT_MAX; s.iscr[2] = 0; }
+    {
+        const double* Zg = u.Zg + (size_t)inst * u.n_max * u.n_max;
+        for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
+            const int i = idx / n, j = idx - i * n;
+            s.A[(size_t)i * lds + j] = Zg[idx];
+        }
+        for (int k = tid; k < n; k += UKF_THREADS) { s.d[k] = u.dg[(size_t)k * b.batch + inst]; s.e[k] = u.eg[(size_t)k * b.batch + inst]; }
+    }
+    __syncthreads();
+
+    // weights and scale are float-valued (ukf.cpp:35,114,175; SURVEY App. A)
+    const float W0f = 0.2f;                                                // filter.h:207
+    const double W0 = (double)W0f;
+    const double wgt = (double)((1 - W0f) / (2 * n));                      // :175
+    const double sw = W0 + (double)(2 * n) * wgt;                          // sum of the 2n+1 weights (not 1)
+    const float u_d = in.fwd[in.cmd_stride ? inst : 0], u_th = in.ang[in.cmd_stride ? inst : 0];
+    const float yaw_prior = yaw_of(s.x[2], s.x[3]);                        // :182 and :139 (prior x_t)
+    const double cy = (double)cos_f(yaw_prior), sy = (double)sin_f(yaw_prior);
+    const double Qd[4] = {fc.V00 * cy, fc.V00 * sy, fc.V11 * cy, fc.V11 * sy};   // :183-186
+
+    // ---- second half of the eigendecomposition (:116-118) -> s.d eigenvalues, s.A = Z^T
+    {
+        const int nsw = u.nswp[inst];
+        if (nsw >= 0) ql_replay(s.A, lds, n, u.rot + (size_t)inst * u.rot_cap, u.swp + (size_t)inst * u.swp_cap, nsw,
+                                reinterpret_cast<double2*>(s.pool));
+        else ql_serial(s.A, lds, n, s.d, s.e, s.pool, s.red);
+    }
 
     // ---- clip (:120) and sqrt; list of clipped eigenpairs
     if (tid == 0) {
@@ -669,12 +893,19 @@ ukf_step_kernel(BatchState b, FilterConst fc, StepInputs in) {
 
 size_t ukf_step_smem_bytes(const BatchState& b) { return ukf_smem_carve(b, nullptr, nullptr); }
 
+static size_t ql_smem_bytes(const BatchState& b) { return sizeof(double) * 2 * (size_t)b.n_max * QL_LANES; }
+
 cudaError_t ukf_step_configure(const BatchState& b) {
-    return cudaFuncSetAttribute(ukf_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b));
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(ukf_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b))) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(ukf_ql_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ql_smem_bytes(b));
 }
 
-cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, cudaStream_t st) {
-    ukf_step_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, fc, in);
+cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, const UkfScratch& u, cudaStream_t st) {
+    ukf_front_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, fc, in, u);
+    ukf_ql_kernel<<<(b.batch + QL_LANES - 1) / QL_LANES, QL_LANES, ql_smem_bytes(b), st>>>(u, b.meta, b.batch);
+    ukf_back_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, fc, in, u);
     return cudaGetLastError();
 }
 

@@ -1,13 +1,8 @@
 #!/bin/bash
+# ncu full capture of ekf_sweep_kernel launches: late chunks (full tile) and early chunks (small tile)
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_ekf_parity.py tests/test_gpu_sim_parity.py -m gpu -x -q 2>&1 | tail -3
 B="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline"
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ekf.json 2> gpurun_out/bench_ekf.err; tail -3 gpurun_out/bench_ekf.err
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:ekf_sweep_kernel -s 3 -c 1 -o gpurun_out/prof_sweep -f $B > gpurun_out/ncu_sweep.log 2>&1
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench_ekf.json'))
-print('value',d['value'],'e2e',d['e2e']['value'],d['e2e']['pipelined_value'])
-r=d['roofline']; print({k:r[k] for k in ('kernel','achieved','frac','kernel_ms_per_launch')}); s=r.get('step_kernel',r); print({k:s[k] for k in ('kernel','achieved','frac','kernel_ms_per_launch')})
-PY
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:ekf_sweep_kernel -s 52 -c 3 -o gpurun_out/prof_sweep_late -f $B > gpurun_out/ncu_sweep.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:ekf_sweep_kernel -s 10 -c 2 -o gpurun_out/prof_sweep_early -f $B >> gpurun_out/ncu_sweep.log 2>&1
+tail -3 gpurun_out/ncu_sweep.log
