@@ -177,9 +177,11 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
         b.sigma = nullptr;   // allocated lazily by slam_get_sigma_points
         UkfScratch& u = h->uk;
         u.n_max = b.n_max;
+        u.gen = 1; u.clip_lanes = 0;   // generation 2 is opt-in (slam_tune key 7) until it is the faster one
         u.rot_cap = 2LL * b.n_max * b.n_max;        // ~0.85 n^2 rotations are typical
         u.swp_cap = 6 * b.n_max;                    // ~1.7 n sweeps are typical
         CK(cudaMalloc(&u.Zg, sizeof(double) * (size_t)batch * b.n_max * b.n_max));
+        CK(cudaMalloc(&u.Yg, sizeof(double) * (size_t)batch * b.n_max * b.n_max));
         CK(cudaMalloc(&u.dg, sizeof(double) * (size_t)batch * b.n_max));
         CK(cudaMalloc(&u.eg, sizeof(double) * (size_t)batch * b.n_max));
         CK(cudaMalloc(&u.rot, sizeof(double2) * (size_t)batch * u.rot_cap));
@@ -218,7 +220,7 @@ int slam_destroy(slam_handle_t h) {
     BatchState& b = h->b;
     cudaFree(b.P); cudaFree(b.x); cudaFree(b.ids); cudaFree(b.meta);
     cudaFree(b.assoc); cudaFree(b.stats); cudaFree(b.sigma);
-    cudaFree(h->uk.Zg); cudaFree(h->uk.dg); cudaFree(h->uk.eg); cudaFree(h->uk.rot); cudaFree(h->uk.swp); cudaFree(h->uk.nswp);
+    cudaFree(h->uk.Zg); cudaFree(h->uk.Yg); cudaFree(h->uk.dg); cudaFree(h->uk.eg); cudaFree(h->uk.rot); cudaFree(h->uk.swp); cudaFree(h->uk.nswp);
     cudaFree(b.retry_list); cudaFree(b.retry_count); cudaFree(b.max_M); cudaFree(h->d_work); cudaFree(h->d_progress);
     if (h->h_run_hint) cudaFreeHost(h->h_run_hint);
     for (int i = 0; i < slam_filter::HINT_RING; ++i) if (h->run_ev[i]) cudaEventDestroy(h->run_ev[i]);
@@ -259,6 +261,11 @@ int slam_tune(slam_handle_t h, int key, int value) {
     } else if (key == 3) h->sweep_off = value;
     else if (key == 5) { if (value < 1) return fail(h, "slam_tune: the sweep chunk must be >= 1 step"); h->sweep_chunk = value; }
     else if (key == 6) h->sweep_headroom = value < 0 ? 0 : value;
+    else if (key == 7) { if (value != 1 && value != 2) return fail(h, "slam_tune: UKF generation must be 1 or 2"); h->uk.gen = value; }
+    else if (key == 8) {     // shrink the rotation log (test knob: forces the rescue pass); never beyond the allocation
+        const long long full = 2LL * h->b.n_max * h->b.n_max;
+        h->uk.rot_cap = (value <= 0 || value > full) ? full : value;
+    } else if (key == 9) h->uk.clip_lanes = value < 0 ? 0 : value;
     else return fail(h, "slam_tune: unknown key");
     return 0;
 }
@@ -331,7 +338,7 @@ static int do_step(slam_filter* h, const float* d_fwd, const float* d_ang, int c
     if (h->kind == SLAM_EKF_SLAM) {
         CK(launch_ekf_step(h->b, h->fc, in, phases, cap, h->force_threads, h->stream));
     }
-    else { CK(launch_ukf_step(h->b, h->fc, in, h->uk, h->stream)); h->launches += 2; }
+    else { int nl = 0; CK(launch_ukf_step(h->b, h->fc, in, h->uk, h->stream, &nl)); h->launches += nl; }
     if (h->profiling) { CK(cudaEventRecord(h->ev[h->ev_used + 1], h->stream)); h->ev_used += 2; }
     {
         const int slot = (int)(h->step_seq % slam_filter::HINT_RING);
@@ -339,7 +346,7 @@ static int do_step(slam_filter* h, const float* d_fwd, const float* d_ang, int c
         CK(cudaEventRecord(h->hint_ev[slot], h->stream));
         h->step_seq += 1;
     }
-    h->launches += (cap < h->b.max_lm) ? 2 : 1;
+    if (h->kind == SLAM_EKF_SLAM) h->launches += (cap < h->b.max_lm) ? 2 : 1;
     return 0;
 }
 

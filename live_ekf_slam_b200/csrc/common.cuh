@@ -179,7 +179,9 @@ cudaError_t ekf_step_configure(const BatchState& b);
 
 // HBM scratch between the three launches of a UKF step (csrc/ukf_batch.cu)
 struct UkfScratch {
-    double* Zg;         // [batch][n_max * n_max]  Q^T of the tridiagonalisation (compact, leading dimension n)
+    double* Zg;         // [batch][n_max * n_max]  generation 2: Householder reflectors by rows, tau on the diagonal;
+                        //                         generation 1 / rescue: Q^T of the tridiagonalisation (compact, ld n)
+    double* Yg;         // [batch][n_max * n_max]  generation 2: 2w * Y, the landmark-block seed of P_pred (compact, ld n)
     double* dg;         // [n_max][batch]  diagonal of T -> eigenvalues
     double* eg;         // [n_max][batch]  off-diagonal of T
     double2* rot;       // [batch][rot_cap]  (c, s) of every QL plane rotation, in generation order
@@ -188,8 +190,12 @@ struct UkfScratch {
     long long rot_cap;
     int swp_cap;
     int n_max;
+    int gen;            // 2 (default): reflector / rotation-log products, warp per instance; 1: explicit eigenvectors
+    int clip_lanes;     // test knob: max clipped eigenvectors riding beside pass A (0 = as many as fit)
 };
-cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, const UkfScratch& u, cudaStream_t st);
+// launches one UKF step; *launched receives the number of kernels launched
+cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, const UkfScratch& u, cudaStream_t st,
+                            int* launched);
 size_t ukf_step_smem_bytes(const BatchState& b);
 cudaError_t ukf_step_configure(const BatchState& b);
 

@@ -116,7 +116,7 @@ __device__ __forceinline__ float yaw_of(double c, double s) { return (float)rema
 // ql_serial: implicit QL on (d, e) (EISPACK tql2 organisation) with each sweep's rotations generated by one thread
 // and applied to A = Z^T by one thread per column.  Only the fall-back of the back kernel (rotation log overflow).
 // ---------------------------------------------------------------------------------------------------------
-__device__ void tridiag_q(double* A, const int lds, const int n, double* d, double* e, double* scratch, double* part, double* red) {
+__device__ void tridiag(double* A, const int lds, const int n, double* d, double* e, double* scratch, double* part, double* red) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* v = scratch;            // [n]
     double* p = scratch + n;        // [n]
@@ -212,7 +212,12 @@ __device__ void tridiag_q(double* A, const int lds, const int n, double* d, doub
     }
     if (tid == 0) { d[n - 1] = A[(size_t)(n - 1) * lds + (n - 1)]; e[n - 1] = 0.0; }
     __syncthreads();
+}
 
+// explicit orthogonal factor from the reflectors left in A by tridiag (tau in scratch[3n..4n)), transposed in place
+__device__ void form_qt(double* A, const int lds, const int n, double* scratch, double* part) {
+    const int tid = threadIdx.x;
+    double* tau = scratch + 3 * n;  // [n]
     // ---- explicit Q in place.  Shift the reflectors one column to the right (reflector k -> column k+1),
     //      first row/column of Q = unit vector, then dorg2r on the (n-1) x (n-1) trailing block.
     for (int i = tid; i < n; i += UKF_THREADS) {          // one thread per row, high column to low: no hazard
@@ -520,7 +525,7 @@ __device__ __forceinline__ void s_times(const double* Zt, const int lds, const i
 // ---- launch 1 of 3: Y = scale * sym(P) (ukf.cpp:112-114), landmark block of P_pred seeded with 2 w Y, Householder
 //      tridiagonalisation + explicit Q^T -> HBM scratch
 __global__ void __launch_bounds__(UKF_THREADS, 2)
-ukf_front_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u) {
+ukf_front_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, const int rescue) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     UkfSmem s;
     ukf_smem_carve(b, smem_raw, &s);
@@ -530,6 +535,7 @@ ukf_front_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u) {
     const int ldp = b.fixed_ld;                    // global leading dimension of P (fixed for the UKF)
     const int4 meta_in = b.meta[inst];
     if (meta_in.y & SLAM_STATUS_SAME_STEP_REMATCH) return;
+    if (rescue && u.nswp[inst] != -1) return;      // rescue pass: only instances whose rotation log overflowed
     const int M = meta_in.x;
     const int n = 4 + 2 * M;                       // ukf.cpp:167 (state size of this step's sigma points)
     double* gP = b.P + (size_t)inst * b.p_stride;
@@ -558,7 +564,8 @@ ukf_front_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u) {
     }
     __syncthreads();
     // ---- first half of the eigendecomposition (:116-118)
-    tridiag_q(s.A, lds, n, s.d, s.e, s.pool, s.Xp, s.red);     // Xp ([4][2 n_max + 2]) is free in this launch
+    tridiag(s.A, lds, n, s.d, s.e, s.pool, s.Xp, s.red);       // Xp ([4][2 n_max + 2]) is free in this launch
+    form_qt(s.A, lds, n, s.pool, s.Xp);
     double* Zg = u.Zg + (size_t)inst * u.n_max * u.n_max;
     for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
         const int i = idx / n, j = idx - i * n;
@@ -569,7 +576,7 @@ ukf_front_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u) {
 
 // ---- launch 3 of 3: rotation replay -> Z^T, then the sigma-point algebra, updates, insertions, commit
 __global__ void __launch_bounds__(UKF_THREADS, 2)
-ukf_back_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u) {
+ukf_back_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, const int rescue) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     UkfSmem s;
     ukf_smem_carve(b, smem_raw, &s);
@@ -583,6 +590,7 @@ ukf_back_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u) {
     int nm = in.n_meas[inst];
     int status = meta_in.y;
     if (status & SLAM_STATUS_SAME_STEP_REMATCH) return;
+    if (rescue && u.nswp[inst] != -1) return;      // rescue pass: only instances whose rotation log overflowed
     int M = meta_in.x;
     const int M_start = M;
     const int n = 4 + 2 * M;                       // ukf.cpp:167 (state size of this step's sigma points)
@@ -891,21 +899,628 @@ ukf_back_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u) {
     }
 }
 
+
+// =========================================================================================================
+// Generation 2 of the step (default): the eigenvector matrix Z = Q V is never formed.
+//
+// Everything the sigma-point algebra needs from S = Z sqrt(D+) Z^T is "S times a handful of vectors": the unit vectors
+// e_0..e_3 and e_li, e_li+1 of the landmarks being updated (rows of S), then g_0..g_3 and the (dz_i - dz_{i+n}) vectors
+// of the updates, plus the few eigenvectors z_k = Q V e_k whose eigenvalue was clipped (<= 4 in practice: the
+// negative Q entries of ukf.cpp:183-186 only make vehicle directions indefinite).  With Y = Q T Q^T (Householder
+// reflectors) and T = V D V^T (the QL kernel's plane-rotation log)
+//        S v = Q V sqrt(D+) V^T Q^T v
+// is evaluated by pushing the vectors through the reflectors, the rotation log, the scaling, and back: O(n^2) per
+// vector instead of the 4/3 n^3 (explicit Q) + ~4.7 n^3 (rotations applied to n eigenvector components) of the first
+// generation.  One WARP owns an instance; lane j carries vector j in a padded shared-memory tile W[n][33] (the odd
+// pitch makes both the lane = vector walks of the transforms and the lane = component walks of the sigma-point
+// algebra conflict free).  The k landmark updates of a step only couple through the running x_pred (K and S2 come
+// from the step's sigma points, ukf.cpp:305-339), so their S-products share the second pass, and P_pred is written
+// exactly once:  P = [vehicle | cross | 2w Y + (sum w) e e^T + clipped-eigenpair terms] - sum_q (K_q S2_q) K_q^T.
+//   ukf_front2_kernel  CTA per instance: Y, tridiagonalisation -> HBM scratch (reflectors + tau, 2wY, d, e); P untouched
+//   ukf_ql_kernel      thread per instance (shared with generation 1)
+//   ukf_back2_kernel   warp per instance: the two S-passes and the algebra
+// An instance whose rotation log overflowed (nswp = -1; never observed: the log holds 2 n^2 rotations, 2.4x the
+// typical count) is left untouched by ukf_back2_kernel and redone by the generation-1 kernels in rescue mode.
+// =========================================================================================================
+constexpr int WLD = 33;                  // pitch of the vector tile (doubles)
+constexpr int UPD_LD = 24;               // per-update scalars
+constexpr int UKF2_MAX_UPD = 14;         // 4 + 2 * updates <= 32 lanes
+
+struct UkfWarpSmem {
+    double* W;      // [n_max][WLD]   lane j = vector j
+    double* x;      // prior x_t
+    double* xp;     // running x_pred
+    double* sq;     // sqrt(max(d, 1e-8))
+    double* Xp;     // [4][nsm] propagated vehicle rows of the sigma points
+    double* z;      // [2][nsm] z / dz of the update being prepared
+    double* upd;    // [max_meas][UPD_LD]
+    double2* stage; // [64] rotation-log ring
+    double* corr;   // [32] 1e-8 - d_k of the clipped eigenvalues
+    int* clip;      // [32] their indices
+    int* ids;
+    float* meas;
+    int* assoc;
+    int* uq;        // measurement index of update q
+};
+
+__host__ __device__ inline size_t ukf_warp_carve(const BatchState& b, unsigned char* base, UkfWarpSmem* s) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
+    const int nmp = ldg_of(b.n_max), nsm = 2 * b.n_max + 2;
+    size_t oW = take(sizeof(double) * (size_t)b.n_max * WLD);
+    size_t ox = take(sizeof(double) * nmp), oxp = take(sizeof(double) * nmp), osq = take(sizeof(double) * nmp);
+    size_t oXp = take(sizeof(double) * 4 * nsm), oz = take(sizeof(double) * 2 * nsm);
+    size_t oupd = take(sizeof(double) * UPD_LD * (b.max_meas > 0 ? b.max_meas : 1));
+    size_t ostage = take(sizeof(double2) * 64);
+    size_t ocorr = take(sizeof(double) * 32), oclip = take(sizeof(int) * 32);
+    size_t oids = take(sizeof(int) * (b.max_lm + 1));
+    size_t omeas = take(sizeof(float) * 3 * (b.max_meas > 0 ? b.max_meas : 1));
+    size_t oassoc = take(sizeof(int) * (b.max_meas > 0 ? b.max_meas : 1));
+    size_t ouq = take(sizeof(int) * (b.max_meas > 0 ? b.max_meas : 1));
+    if (s) {
+        s->W = (double*)(base + oW); s->x = (double*)(base + ox); s->xp = (double*)(base + oxp); s->sq = (double*)(base + osq);
+        s->Xp = (double*)(base + oXp); s->z = (double*)(base + oz); s->upd = (double*)(base + oupd);
+        s->stage = (double2*)(base + ostage); s->corr = (double*)(base + ocorr); s->clip = (int*)(base + oclip);
+        s->ids = (int*)(base + oids); s->meas = (float*)(base + omeas); s->assoc = (int*)(base + oassoc); s->uq = (int*)(base + ouq);
+    }
+    return off;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// w <- H_k w over all reflectors, k ascending (Q^T w) or descending (Q w).  Row k of R: R[k] = tau_k at column k and
+// the reflector below it (v_k[k+1] = 1 stored).  Lanes are independent (lane = vector); reflector elements are
+// warp-uniform read-only loads.
+template <bool ASC>
+__device__ __forceinline__ void apply_reflectors(double* W, const int n, const int lane, const bool act,
+                                                 const double* __restrict__ R) {
+    for (int kk = 0; kk < n - 1; ++kk) {
+        const int k = ASC ? kk : n - 2 - kk;
+        const double* __restrict__ v = R + (size_t)k * n;
+        const double tau = __ldg(v + k);
+        if (tau == 0.0 || !act) continue;
+        double* w = W + lane;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int i = k + 1;
+        for (; i + 3 < n; i += 4) {
+            a0 += __ldg(v + i) * w[(i) * WLD];
+            a1 += __ldg(v + i + 1) * w[(i + 1) * WLD];
+            a2 += __ldg(v + i + 2) * w[(i + 2) * WLD];
+            a3 += __ldg(v + i + 3) * w[(i + 3) * WLD];
+        }
+        for (; i < n; ++i) a0 += __ldg(v + i) * w[i * WLD];
+        const double sc = tau * ((a0 + a1) + (a2 + a3));
+#pragma unroll 4
+        for (i = k + 1; i < n; ++i) w[i * WLD] -= sc * __ldg(v + i);
+    }
+}
+
+// u <- V^T u: the QL kernel's rotation log replayed in generation order on the vector components
+__device__ __forceinline__ void apply_rot_fwd(double* W, const int lane, const bool act, const double2* __restrict__ rot,
+                                              const int2* __restrict__ swp, const int nsw, const int nrot, double2* stage) {
+    int g = 0;
+    double2 pre = (lane < nrot) ? rot[lane] : make_double2(1.0, 0.0);
+    int2 lm_next = (nsw > 0) ? swp[0] : make_int2(0, 0);
+    double* w = W + lane;
+    for (int sidx = 0; sidx < nsw; ++sidx) {
+        const int2 lm = lm_next;
+        if (sidx + 1 < nsw) lm_next = swp[sidx + 1];
+        const int l = lm.x, m = lm.y;
+        double fz = 0.0, zi = 0.0;
+        if (act) { fz = w[m * WLD]; zi = w[(m - 1) * WLD]; }
+        for (int i = m - 1; i >= l; --i, ++g) {
+            if ((g & 31) == 0) {
+                __syncwarp();
+                stage[((g >> 5) & 1) * 32 + lane] = pre;
+                const int nx = g + 32 + lane;
+                pre = (nx < nrot) ? rot[nx] : make_double2(1.0, 0.0);
+                __syncwarp();
+            }
+            const double2 cs = stage[g & 63];
+            if (act) {
+                const double zn = (i > l) ? w[(i - 1) * WLD] : 0.0;
+                w[(i + 1) * WLD] = cs.y * zi + cs.x * fz;
+                fz = cs.x * zi - cs.y * fz;
+                zi = zn;
+            }
+        }
+        if (act) w[l * WLD] = fz;
+    }
+    __syncwarp();
+}
+
+// u <- V u: the log replayed backwards, every plane rotation inverted (each 2x2 step [[s,c],[c,-s]] is its own inverse)
+__device__ __forceinline__ void apply_rot_bwd(double* W, const int lane, const bool act, const double2* __restrict__ rot,
+                                              const int2* __restrict__ swp, const int nsw, const int nrot, double2* stage) {
+    if (nrot <= 0) return;
+    int g = nrot - 1;
+    {
+        const int c = g >> 5;
+        const int ix = c * 32 + lane;
+        const double2 cur = (ix < nrot) ? rot[ix] : make_double2(1.0, 0.0);
+        __syncwarp();
+        stage[(c & 1) * 32 + lane] = cur;
+        __syncwarp();
+    }
+    double2 pre = (g >= 32) ? rot[((g >> 5) - 1) * 32 + lane] : make_double2(1.0, 0.0);
+    int2 lm_next = swp[nsw - 1];
+    double* w = W + lane;
+    for (int sidx = nsw - 1; sidx >= 0; --sidx) {
+        const int2 lm = lm_next;
+        if (sidx > 0) lm_next = swp[sidx - 1];
+        const int l = lm.x, m = lm.y;
+        double fz = 0.0, a = 0.0;
+        if (act) { fz = w[l * WLD]; a = w[(l + 1) * WLD]; }
+        for (int i = l; i < m; ++i, --g) {
+            const double2 cs = stage[g & 63];
+            if (act) {
+                const double an = (i + 2 <= m) ? w[(i + 2) * WLD] : 0.0;
+                w[i * WLD] = cs.y * a + cs.x * fz;
+                fz = cs.x * a - cs.y * fz;
+                a = an;
+            }
+            if ((g & 31) == 0 && g > 0) {          // the next rotation (g - 1) opens chunk (g >> 5) - 1
+                const int c = (g >> 5) - 1;
+                __syncwarp();
+                stage[(c & 1) * 32 + lane] = pre;
+                pre = (c > 0) ? rot[(c - 1) * 32 + lane] : make_double2(1.0, 0.0);
+                __syncwarp();
+            }
+        }
+        if (act) w[m * WLD] = fz;
+    }
+    __syncwarp();
+}
+
+// ---- launch 1 of 3 (generation 2): Y = scale * sym(P) (ukf.cpp:112-114), tridiagonalisation; P is NOT modified
+__global__ void __launch_bounds__(UKF_THREADS, 2)
+ukf_front2_kernel(BatchState b, UkfScratch u) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    UkfSmem s;
+    ukf_smem_carve(b, smem_raw, &s);
+    const int tid = threadIdx.x;
+    const int inst = blockIdx.x;
+    const int lds = b.lds;
+    const int ldp = b.fixed_ld;
+    const int4 meta_in = b.meta[inst];
+    if (meta_in.y & SLAM_STATUS_SAME_STEP_REMATCH) return;
+    const int M = meta_in.x;
+    const int n = 4 + 2 * M;                       // ukf.cpp:167
+    const double* gP = b.P + (size_t)inst * b.p_stride;
+    for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
+        const int i = idx / n, j = idx - i * n;
+        s.A[(size_t)i * lds + j] = gP[(size_t)i * ldp + j];
+    }
+    __syncthreads();
+    const float W0f = 0.2f;                                                // filter.h:207
+    const double wgt = (double)((1 - W0f) / (2 * n));                      // :175
+    const double scale = (double)((2 * M + 4) / (1 - W0f));                // :114
+    for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
+        const int i = idx / n, j = idx - i * n;
+        if (j >= i) {
+            const double y = (0.5 * (s.A[(size_t)i * lds + j] + s.A[(size_t)j * lds + i])) * scale;
+            s.A[(size_t)i * lds + j] = y; s.A[(size_t)j * lds + i] = y;
+        }
+    }
+    __syncthreads();
+    double* Yg = u.Yg + (size_t)inst * u.n_max * u.n_max;
+    for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
+        const int i = idx / n, j = idx - i * n;
+        if (i >= 4 && j >= 4) Yg[idx] = (2.0 * wgt) * s.A[(size_t)i * lds + j];   // landmark block of P_pred before corrections
+    }
+    __syncthreads();
+    tridiag(s.A, lds, n, s.d, s.e, s.pool, s.Xp, s.red);
+    // reflector k (column k of A below the diagonal) -> row k of the scratch matrix, tau_k on its diagonal
+    double* Rg = u.Zg + (size_t)inst * u.n_max * u.n_max;
+    const double* tau = s.pool + 3 * n;
+    for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
+        const int k = idx / n, i = idx - k * n;
+        if (i > k) Rg[idx] = s.A[(size_t)i * lds + k];
+        else if (i == k) Rg[idx] = (k < n - 1) ? tau[k] : 0.0;
+    }
+    for (int k = tid; k < n; k += UKF_THREADS) { u.dg[(size_t)k * b.batch + inst] = s.d[k]; u.eg[(size_t)k * b.batch + inst] = s.e[k]; }
+}
+
+// ---- launch 3 of 3 (generation 2): warp per instance
+__global__ void __launch_bounds__(32)
+ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    UkfWarpSmem s;
+    ukf_warp_carve(b, smem_raw, &s);
+    const int lane = threadIdx.x;
+    const int inst = blockIdx.x;
+    const int ldp = b.fixed_ld;
+    const int nsm = 2 * b.n_max + 2;
+    const unsigned FULL = 0xffffffffu;
+
+    const int4 meta_in = b.meta[inst];
+    int nm = in.n_meas[inst];
+    int status = meta_in.y;
+    if (status & SLAM_STATUS_SAME_STEP_REMATCH) return;
+    const int nsw = u.nswp[inst];
+    if (nsw < 0) return;                           // rotation log overflow: redone by the rescue pass
+    int M = meta_in.x;
+    const int M_start = M;
+    const int n = 4 + 2 * M;                       // ukf.cpp:167
+    const int ns = 2 * n + 1;
+    if (nm > b.max_meas) { nm = b.max_meas; status |= SLAM_STATUS_MEAS_OVERFLOW; }
+    double* gP = b.P + (size_t)inst * b.p_stride;
+    double* gx = b.x + (size_t)inst * b.x_stride;
+    const double* __restrict__ R = u.Zg + (size_t)inst * u.n_max * u.n_max;
+    double* Yg = u.Yg + (size_t)inst * u.n_max * u.n_max;
+    const double2* __restrict__ rot = u.rot + (size_t)inst * u.rot_cap;
+    const int2* __restrict__ swp = u.swp + (size_t)inst * u.swp_cap;
+
+    for (int i = lane; i < n; i += 32) s.x[i] = gx[i];
+    for (int i = lane; i < M; i += 32) s.ids[i] = b.ids[(size_t)inst * b.max_lm + i];
+    for (int i = lane; i < 3 * nm; i += 32) s.meas[i] = in.meas[(size_t)inst * b.max_meas * 3 + i];
+    // eigenvalues: clip (:120), sqrt, ordered list of the clipped ones; total length of the rotation log
+    int nclip = 0;
+    for (int k0 = 0; k0 < n; k0 += 32) {
+        const int k = k0 + lane;
+        const double dk = (k < n) ? u.dg[(size_t)k * b.batch + inst] : 1.0;
+        const bool cl = (k < n) && (dk < 0.00000001);
+        const unsigned mask = __ballot_sync(FULL, cl);
+        const int pos = nclip + __popc(mask & ((1u << lane) - 1u));
+        if (cl && pos < 32) { s.clip[pos] = k; s.corr[pos] = 0.00000001 - dk; }
+        if (k < n) s.sq[k] = sqrt(cl ? 0.00000001 : dk);
+        nclip += __popc(mask);
+    }
+    int nrot = 0;
+    for (int q = lane; q < nsw; q += 32) { const int2 lm = swp[q]; nrot += lm.y - lm.x; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nrot += __shfl_xor_sync(FULL, nrot, o);
+    __syncwarp();
+
+    // weights and scale are float-valued (ukf.cpp:35,114,175)
+    const float W0f = 0.2f;                                                // filter.h:207
+    const double W0 = (double)W0f;
+    const double wgt = (double)((1 - W0f) / (2 * n));                      // :175
+    const double sw = W0 + (double)(2 * n) * wgt;                          // sum of the 2n+1 weights (not 1)
+    const float u_d = in.fwd[in.cmd_stride ? inst : 0], u_th = in.ang[in.cmd_stride ? inst : 0];
+    const float yaw_prior = yaw_of(s.x[2], s.x[3]);                        // :182 and :139 (prior x_t)
+    const double cy = (double)cos_f(yaw_prior), sy = (double)sin_f(yaw_prior);
+    const double Qd[4] = {fc.V00 * cy, fc.V00 * sy, fc.V11 * cy, fc.V11 * sy};   // :183-186
+
+    // ---- association of every measurement (:258-274): known-ID lookup against the landmarks of the step start
+    int nu = 0;
+    for (int l = 0; l < nm; ++l) {
+        const int id = (int)s.meas[3 * l];                                  // :258
+        int cand = INT_MAX;
+        for (int j = lane; j < M_start; j += 32) if (s.ids[j] == id) { cand = j; break; }   // :264-269
+        cand = __reduce_min_sync(FULL, cand);
+        if (lane == 0) {
+            s.assoc[l] = (cand == INT_MAX) ? -1 : cand;
+            if (cand != INT_MAX) s.uq[nu] = l;
+        }
+        if (cand != INT_MAX) ++nu;
+    }
+    __syncwarp();
+    const int nvec = 4 + 2 * nu;                    // lanes of the two S-passes
+    int ncf = 32 - nvec; if (ncf > nclip) ncf = nclip;   // clipped eigenvectors riding in pass A
+    if (u.clip_lanes > 0 && ncf > u.clip_lanes) ncf = u.clip_lanes;        // test knob
+
+    // ---- clipped eigenpairs that do not fit beside pass A (never in practice): z_k = Q V e_k, 32 at a time,
+    //      folded into the landmark-block seed  Yg += 2w (1e-8 - d_k) z_k z_k^T
+    for (int c0 = ncf; c0 < nclip && c0 < 32; c0 += 32) {
+        const int cnt = (nclip < 32 ? nclip : 32) - c0;
+        const bool act = lane < cnt;
+        for (int i = 0; i < n; ++i) s.W[i * WLD + lane] = (act && s.clip[c0 + lane] == i) ? 1.0 : 0.0;
+        __syncwarp();
+        apply_rot_bwd(s.W, lane, act, rot, swp, nsw, nrot, s.stage);
+        apply_reflectors<false>(s.W, n, lane, act, R);
+        __syncwarp();
+        for (int a = 4; a < n; ++a)
+            for (int c = 4 + lane; c < n; c += 32) {
+                double add = 0.0;
+                for (int q = 0; q < cnt; ++q) add += (2.0 * wgt) * s.corr[c0 + q] * s.W[a * WLD + q] * s.W[c * WLD + q];
+                Yg[(size_t)a * n + c] += add;
+            }
+        __syncwarp();
+    }
+    if (nclip > 32) status |= SLAM_STATUS_NAN;      // more than 32 non-positive directions: the covariance is garbage
+
+    // ---- pass A: S e_r for the vehicle rows and the rows of the landmarks being updated; clipped eigenvectors beside
+    {
+        int row = -1;
+        if (lane < 4) row = lane;
+        else if (lane < nvec) { const int q = (lane - 4) >> 1; row = s.assoc[s.uq[q]] * 2 + 4 + ((lane - 4) & 1); }   // :298
+        for (int i = 0; i < n; ++i) s.W[i * WLD + lane] = (i == row) ? 1.0 : 0.0;
+        const bool act = lane < nvec;
+        apply_reflectors<true>(s.W, n, lane, act, R);
+        apply_rot_fwd(s.W, lane, act, rot, swp, nsw, nrot, s.stage);
+        const bool isclip = lane >= nvec && lane < nvec + ncf;
+        const int ck = isclip ? s.clip[lane - nvec] : -1;
+        for (int i = 0; i < n; ++i) {
+            if (act) s.W[i * WLD + lane] *= s.sq[i];
+            else s.W[i * WLD + lane] = (i == ck) ? 1.0 : 0.0;
+        }
+        const bool act2 = act || isclip;
+        apply_rot_bwd(s.W, lane, act2, rot, swp, nsw, nrot, s.stage);
+        apply_reflectors<false>(s.W, n, lane, act2, R);
+        __syncwarp();
+    }
+
+    // ---- sigma points, vehicle rows (:214-226): X = x +- column of S, motion model per sigma point
+    for (int i = lane; i < ns; i += 32) {
+        double X[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const double xr = s.x[r];
+            X[r] = (i == 0) ? xr : (i <= n ? xr + s.W[(i - 1) * WLD + r] : xr - s.W[(i - 1 - n) * WLD + r]);
+        }
+        const float yaw = yaw_of(X[2], X[3]);                              // :128
+        const float ud = u_d + fc.v_d;
+        s.Xp[0 * nsm + i] = X[0] + (double)(ud * cos_f(yaw));              // :129 float product
+        s.Xp[1 * nsm + i] = X[1] + (double)(ud * sin_f(yaw));              // :130
+        const float fsum = yaw + u_th + fc.v_th;
+        const float new_yaw = (float)remainder((double)fsum, TWO_PI_REF);  // :131
+        s.Xp[2 * nsm + i] = (double)cos_f(new_yaw);                        // :132
+        s.Xp[3 * nsm + i] = (double)sin_f(new_yaw);                        // :133
+    }
+    __syncwarp();
+    // ---- mean (:228-232): vehicle rows by reduction, landmark rows analytically (sum w) * x
+    double xp0v[4];
+    {
+        double acc[4] = {0, 0, 0, 0};
+        for (int i = lane; i < ns; i += 32) {
+            const double wi = (i == 0) ? W0 : wgt;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] += wi * s.Xp[r * nsm + i];
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) xp0v[r] = warp_sum(acc[r]);
+        if (lane < 4) s.xp[lane] = xp0v[lane];
+        for (int r = 4 + lane; r < n; r += 32) s.xp[r] = sw * s.x[r];
+    }
+    __syncwarp();
+    // ---- covariance (:235-240), vehicle block: sum_i w_i dv_i dv_i^T + Q ; mv[a] = sum_i w_i dv_i[a]
+    double mv[4], vv[10];
+    {
+        double acc[14] = {0};
+        for (int i = lane; i < ns; i += 32) {
+            const double wi = (i == 0) ? W0 : wgt;
+            double dv[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) dv[r] = s.Xp[r * nsm + i] - xp0v[r];
+            int q = 0;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = a; c < 4; ++c) acc[q++] += (wi * dv[a]) * dv[c];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) acc[10 + a] += wi * dv[a];
+        }
+#pragma unroll
+        for (int k = 0; k < 14; ++k) acc[k] = warp_sum(acc[k]);
+        {
+            int q = 0;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = a; c < 4; ++c) { vv[q] = acc[q] + ((a == c) ? Qd[a] : 0.0); ++q; }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) mv[a] = acc[10 + a];
+    }
+    // ---- the updates' sigma-point statistics (:293-336), in message order; every update q leaves
+    //      hv = dz_i - dz_{i+n} in its two lanes of W (the S rows it read from them are dead by then)
+    for (int q = 0; q < nu; ++q) {
+        const int l = s.uq[q];
+        const int li = s.assoc[l] * 2 + 4;                                  // :298
+        const int c0 = 4 + 2 * q;
+        double* z0 = s.z;
+        double* z1 = s.z + nsm;
+        for (int i = lane; i < ns; i += 32) {                               // sensingModel per sigma point (:305-308)
+            double lx = s.x[li], ly = s.x[li + 1];
+            if (i >= 1 && i <= n) { lx += s.W[(i - 1) * WLD + c0]; ly += s.W[(i - 1) * WLD + c0 + 1]; }
+            else if (i > n) { lx -= s.W[(i - 1 - n) * WLD + c0]; ly -= s.W[(i - 1 - n) * WLD + c0 + 1]; }
+            const double dx = lx - s.Xp[0 * nsm + i], dy = ly - s.Xp[1 * nsm + i];
+            z0[i] = sqrt(dx * dx + dy * dy) + (double)fc.w_r;               // :144
+            z1[i] = remainder(atan2(dy, dx) - (double)yaw_prior + (double)fc.w_b, TWO_PI_REF);   // :145,156
+        }
+        __syncwarp();
+        double zest0 = 0.0;
+        for (int i = lane; i < ns; i += 32) zest0 += ((i == 0) ? W0 : wgt) * z0[i];   // :312-314
+        zest0 = warp_sum(zest0);
+        double acc[13] = {0};
+        for (int i = lane; i < ns; i += 32) {
+            const double wi = (i == 0) ? W0 : wgt;
+            const double d0 = z0[i] - zest0;
+            const double d1 = remainder(z1[i] - 0.0, TWO_PI_REF);           // z_est(1) is never accumulated (:310-314,321)
+            z0[i] = d0; z1[i] = d1;
+            acc[0] += (wi * d0) * d0; acc[1] += (wi * d0) * d1; acc[2] += (wi * d1) * d1;
+            acc[3] += wi * d0; acc[4] += wi * d1;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const double wd = wi * (s.Xp[a * nsm + i] - xp0v[a]);       // about the predicted mean; the running
+                acc[5 + 2 * a] += wd * d0; acc[6 + 2 * a] += wd * d1;       // x_pred enters below as a rank-1 shift
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 13; ++k) acc[k] = warp_sum(acc[k]);
+        __syncwarp();
+        if (lane == 0) {
+            double* ud = s.upd + q * UPD_LD;
+            const double S00 = acc[0] + fc.W00, S01 = acc[1], S11 = acc[2] + fc.W11;     // :326
+            ud[0] = S00; ud[1] = S01; ud[2] = S11; ud[3] = acc[3]; ud[4] = acc[4];
+            for (int a = 0; a < 8; ++a) ud[5 + a] = acc[5 + a];
+            // S2^-1 (:339, partial-pivot LU like Eigen's dynamic inverse)
+            const bool swpv = fabs(S01) > fabs(S00);
+            const double a00 = swpv ? S01 : S00, a01 = swpv ? S11 : S01;
+            const double a10 = swpv ? S00 : S01, a11 = swpv ? S01 : S11;
+            const double l10 = a10 / a00, u11 = a11 - l10 * a01;
+            const double b0c0 = swpv ? 0.0 : 1.0, b1c0 = swpv ? 1.0 : 0.0, b0c1 = swpv ? 1.0 : 0.0, b1c1 = swpv ? 0.0 : 1.0;
+            double y1 = b1c0 - l10 * b0c0;
+            const double i10 = y1 / u11, i00 = (b0c0 - a01 * i10) / a00;
+            y1 = b1c1 - l10 * b0c1;
+            const double i11 = y1 / u11, i01 = (b0c1 - a01 * i11) / a00;
+            ud[13] = i00; ud[14] = i01; ud[15] = i10; ud[16] = i11;
+            ud[17] = (double)s.meas[3 * l + 1] - zest0;                                   // innovation (:342-344)
+            ud[18] = remainder((double)s.meas[3 * l + 2] - 0.0, TWO_PI_REF);
+        }
+        for (int i = lane; i < n; i += 32) {
+            s.W[i * WLD + c0] = z0[1 + i] - z0[1 + n + i];
+            s.W[i * WLD + c0 + 1] = z1[1 + i] - z1[1 + n + i];
+        }
+        __syncwarp();
+    }
+    // g_a[i] = Xp[a][1+i] - Xp[a][1+n+i] -> lanes 0..3
+    for (int i = lane; i < n; i += 32)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) s.W[i * WLD + a] = s.Xp[a * nsm + 1 + i] - s.Xp[a * nsm + 1 + n + i];
+    __syncwarp();
+
+    // ---- pass B: S g_a and S hv for every update; the clipped eigenvectors stay put in their lanes
+    {
+        const bool act = lane < nvec;
+        apply_reflectors<true>(s.W, n, lane, act, R);
+        apply_rot_fwd(s.W, lane, act, rot, swp, nsw, nrot, s.stage);
+        if (act) for (int i = 0; i < n; ++i) s.W[i * WLD + lane] *= s.sq[i];
+        apply_rot_bwd(s.W, lane, act, rot, swp, nsw, nrot, s.stage);
+        apply_reflectors<false>(s.W, n, lane, act, R);
+        __syncwarp();
+    }
+
+    // ---- gains (:336-345) in message order: C uses the RUNNING x_pred; K_q overwrites the update's lanes of W
+    for (int q = 0; q < nu; ++q) {
+        const double* ud = s.upd + q * UPD_LD;
+        const int c0 = 4 + 2 * q;
+        const double sdz0 = ud[3], sdz1 = ud[4];
+        const double i00 = ud[13], i01 = ud[14], i10 = ud[15], i11 = ud[16], in0 = ud[17], in1 = ud[18];
+        for (int a = lane; a < n; a += 32) {
+            double c0v, c1v;
+            if (a < 4) {
+                const double sh = xp0v[a] - s.xp[a];
+                c0v = ud[5 + 2 * a] + sh * sdz0; c1v = ud[6 + 2 * a] + sh * sdz1;
+            } else {
+                const double fa = s.x[a] - s.xp[a];
+                c0v = fa * sdz0 + wgt * s.W[a * WLD + c0];
+                c1v = fa * sdz1 + wgt * s.W[a * WLD + c0 + 1];
+            }
+            const double k0 = c0v * i00 + c1v * i10, k1 = c0v * i01 + c1v * i11;
+            s.W[a * WLD + c0] = k0; s.W[a * WLD + c0 + 1] = k1;
+            s.xp[a] = s.xp[a] + (k0 * in0 + k1 * in1);
+        }
+    }
+    __syncwarp();
+
+    // ---- P_pred, written once (:235-240 then :348 per update, in message order)
+    for (int i = 0; i < n; ++i) {
+        const double ei = (i >= 4) ? s.x[i] - sw * s.x[i] : 0.0;
+        for (int j = lane; j < n; j += 32) {
+            double val;
+            if (i < 4 && j < 4) {
+                const int a = i < j ? i : j, c = i < j ? j : i;
+                val = vv[a * 4 - (a * (a - 1)) / 2 + (c - a)];
+            } else if (i < 4) {
+                const double eb = s.x[j] - sw * s.x[j];
+                val = wgt * s.W[j * WLD + i] + eb * mv[i];
+            } else if (j < 4) {
+                val = wgt * s.W[i * WLD + j] + ei * mv[j];
+            } else {
+                const double ej = s.x[j] - sw * s.x[j];
+                double add = sw * ei * ej;
+                for (int q = 0; q < ncf; ++q) add += (2.0 * wgt) * s.corr[q] * s.W[i * WLD + nvec + q] * s.W[j * WLD + nvec + q];
+                val = Yg[(size_t)i * n + j] + add;
+            }
+            for (int q = 0; q < nu; ++q) {
+                const double* ud = s.upd + q * UPD_LD;
+                const int c0 = 4 + 2 * q;
+                const double ki0 = s.W[i * WLD + c0], ki1 = s.W[i * WLD + c0 + 1];
+                const double ks0 = ki0 * ud[0] + ki1 * ud[1], ks1 = ki0 * ud[1] + ki1 * ud[2];
+                val -= ks0 * s.W[j * WLD + c0] + ks1 * s.W[j * WLD + c0 + 1];
+            }
+            gP[(size_t)i * ldp + j] = val;
+        }
+    }
+    __syncwarp();
+
+    // -------- landmarkInsertion for the unmatched measurements, in message order (:278-287,351-371)
+    for (int l = 0; l < nm; ++l) {
+        if (s.assoc[l] != -1) continue;
+        if (M >= b.max_lm) { status |= SLAM_STATUS_CAPACITY; continue; }
+        const int nn = 4 + 2 * M;
+        const float r = s.meas[3 * l + 1], bb = s.meas[3 * l + 2];
+        if (lane == 0) {
+            const float yaw = yaw_of(s.xp[2], s.xp[3]);                     // :356
+            const float yb = yaw + bb;
+            s.xp[nn] = s.xp[0] + (double)(r * cos_f(yb));                   // :358
+            s.xp[nn + 1] = s.xp[1] + (double)(r * sin_f(yb));               // :359
+            s.ids[M] = (int)s.meas[3 * l];                                  // :361
+        }
+        for (int i = lane; i < nn + 2; i += 32) {                           // :365-368, W block and zero cross terms
+            gP[(size_t)i * ldp + nn] = (i == nn) ? fc.W00 : 0.0;
+            gP[(size_t)i * ldp + nn + 1] = (i == nn + 1) ? fc.W11 : 0.0;
+            gP[(size_t)nn * ldp + i] = (i == nn) ? fc.W00 : 0.0;
+            gP[(size_t)(nn + 1) * ldp + i] = (i == nn + 1) ? fc.W11 : 0.0;
+        }
+        M += 1;
+        __syncwarp();
+    }
+
+    // ---- commit (:289-290)
+    const int n_out = 4 + 2 * M;
+    bool bad = false;
+    for (int i = lane; i < n_out; i += 32) {
+        const double v = s.xp[i];
+        gx[i] = v;
+        if (!isfinite(v)) bad = true;
+    }
+    bad = __any_sync(FULL, bad);
+    for (int i = lane + M_start; i < M; i += 32) b.ids[(size_t)inst * b.max_lm + i] = s.ids[i];
+    for (int i = lane; i < nm; i += 32) b.assoc[(size_t)inst * b.max_meas + i] = s.assoc[i];
+    if (lane == 0) {
+        if (bad) status |= SLAM_STATUS_NAN;
+        b.meta[inst] = make_int4(M, status, meta_in.z + 1, nm);             // timestep, :164
+        if (M > M_start) atomicMax(b.max_M, M);
+        double* st = b.stats + (size_t)inst * SLAM_NUM_STATS;
+        const double nd = (double)n;
+        st[8] += 16.0 * nd * nd + 16.0 * nd + 12.0 * nm + 8.0;
+        st[9] += 9.0 * nd * nd * nd + 2.0 * nd * nd * nd + 2.0 * nd * nd * (2.0 * nd + 1.0) + 12.0 * nu * nd * nd;
+        st[10] += nd;
+        st[11] += (double)nm;
+    }
+}
+
 size_t ukf_step_smem_bytes(const BatchState& b) { return ukf_smem_carve(b, nullptr, nullptr); }
 
 static size_t ql_smem_bytes(const BatchState& b) { return sizeof(double) * 2 * (size_t)b.n_max * QL_LANES; }
+
+static size_t ukf_warp_smem_bytes(const BatchState& b) { return ukf_warp_carve(b, nullptr, nullptr); }
 
 cudaError_t ukf_step_configure(const BatchState& b) {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(ukf_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_front2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b))) != cudaSuccess) return e;
     return cudaFuncSetAttribute(ukf_ql_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ql_smem_bytes(b));
 }
 
-cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, const UkfScratch& u, cudaStream_t st) {
-    ukf_front_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, fc, in, u);
-    ukf_ql_kernel<<<(b.batch + QL_LANES - 1) / QL_LANES, QL_LANES, ql_smem_bytes(b), st>>>(u, b.meta, b.batch);
-    ukf_back_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, fc, in, u);
+bool ukf_gen2_supported(const BatchState& b) { return b.max_meas <= UKF2_MAX_UPD && ukf_warp_smem_bytes(b) <= 227 * 1024; }
+
+cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, const UkfScratch& u, cudaStream_t st,
+                            int* launched) {
+    const int qblocks = (b.batch + QL_LANES - 1) / QL_LANES;
+    if (u.gen == 2 && ukf_gen2_supported(b)) {
+        ukf_front2_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, u);
+        ukf_ql_kernel<<<qblocks, QL_LANES, ql_smem_bytes(b), st>>>(u, b.meta, b.batch);
+        ukf_back2_kernel<<<b.batch, 32, ukf_warp_smem_bytes(b), st>>>(b, fc, in, u);
+        // rescue pass (generation-1 kernels, in-CTA QL): instances whose rotation log overflowed; everyone else exits at once
+        ukf_front_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, fc, in, u, 1);
+        ukf_back_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, fc, in, u, 1);
+        if (launched) *launched = 5;
+    } else {
+        ukf_front_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, fc, in, u, 0);
+        ukf_ql_kernel<<<qblocks, QL_LANES, ql_smem_bytes(b), st>>>(u, b.meta, b.batch);
+        ukf_back_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, fc, in, u, 0);
+        if (launched) *launched = 3;
+    }
     return cudaGetLastError();
 }
 

@@ -161,3 +161,34 @@ def test_ukf_filter_class(shim, oracle):
     assert H.normwise(sv[3:], xo[4:]) <= H.REL_TOL and abs(sv[2] - np.arctan2(xo[3], xo[2])) <= 1e-9
     msg = filt.publishState()
     assert msg["P"].size == of.n * of.n and msg["M"] == of.M
+
+
+@pytest.mark.parametrize("knobs", [((7, 1),), ((7, 2),), ((7, 2), (8, 600)), ((7, 2), (9, 1)), ((7, 2), (8, 2500), (9, 1))],
+                         ids=["generation1", "generation2", "rescue_pass_only", "clip_overflow_pass", "mixed_rescue"])
+def test_ukf_step_variants(shim, oracle, knobs):
+    """The same free-running batch through the alternative code paths of the UKF step: the generation-1 kernels
+    (explicit eigenvectors), a rotation log too small for any / for the later steps (rescue pass on the generation-1
+    kernels), and only one clipped eigenvector allowed beside the first S-pass (overflow pass into the seed)."""
+    p, lm, fwd, ang = H.config2(seed=4, steps=120, filt="ukf_slam")
+    op = H.oracle_params(oracle, p)
+    B = 5
+    fb = shim.FilterBatch(shim.UKF_SLAM, p.to_c(), B, 50, 8)
+    for k, v in knobs:
+        fb.tune(k, v)
+    fb.init(0, 0, 0)
+    streams = [H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=9, instance=i)[0] for i in range(B)]
+    ofs = []
+    for i in range(B):
+        of = oracle.OracleFilter(oracle.UKF_SLAM, op, 50)
+        of.init(0, 0, 0)
+        ofs.append(of)
+    for t in range(len(fwd)):
+        meas, n = fb.pack_meas([streams[i][t] for i in range(B)])
+        fb.step(fwd[t], ang[t], meas, n)
+        for i in range(B):
+            ofs[i].update(fwd[t], ang[t], streams[i][t], oracle.STRUCTURED)
+            if t % 10 == 0:
+                assert list(fb.assoc(i)) == list(ofs[i].assoc_log()), (t, i)
+    worst = max(_compare(fb, i, ofs[i]) for i in range(B))
+    assert (fb.all_status() == 0).all() and ofs[0].M >= 5
+    print("ukf variant", knobs, "worst normwise err", worst)
