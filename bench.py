@@ -148,6 +148,110 @@ def workload_config(args, instances):
             "parallelism": f"instances sharded over {args.gpus} GPU(s), no data-path collective; one all-reduce of error stats"}
 
 
+def fp64_ceiling(torch, n: int = 4096, reps: int = 5):
+    """Measured FP64 ceiling of this GPU: cuBLAS DGEMM (n^3) through torch.matmul, CUDA events (FP64 peak is not
+    in MEASURED_PEAKS.json, so the bench measures one and prints it next to the nominal figure)."""
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        torch.matmul(a, b)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        torch.matmul(a, b)
+    e1.record()
+    torch.cuda.synchronize()
+    return 2.0 * n ** 3 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12
+
+
+def run_mixed(args):
+    """BASELINE configs[4] at bench scale: half of every rank's instances run EKF-SLAM, half UKF-SLAM, concurrently on
+    the two handles' streams; instances are sharded over the ranks with no data-path collective and the error
+    statistics of both filter kinds meet in one all-reduce (NCCL over NVLink when world > 1)."""
+    import torch
+    import torch.distributed as dist
+    from live_ekf_slam_b200 import shim, parallel
+    rank, local, world = parallel.world_info()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    parallel.init_distributed("nccl", torch.device("cuda", local))
+    shim.load()
+    B, T, K, W = args.instances, args.filter_steps, args.steps, args.warmup
+    Bh = B // 2
+    arms = []
+    for name, kind, filt in (("ekf", shim.EKF_SLAM, "ekf_slam"), ("ukf", shim.UKF_SLAM, "ukf_slam")):
+        p, lm, fwd, ang = build_workload(filt, T)
+        fb = shim.FilterBatch(kind, p.to_c(), Bh, 50, args.max_meas, device=local)
+        # global instance id: EKF instances first, then UKF (shard-invariant Philox streams)
+        off = (0 if name == "ekf" else world * Bh) + rank * Bh
+        sim = shim.Simulator(fb, lm, seed=args.seed, instance_offset=off)
+        st = torch.cuda.ExternalStream(fb.stream, device=torch.device("cuda", local))
+        arms.append({"name": name, "fb": fb, "sim": sim, "p": p, "stream": st,
+                     "fwd": torch.from_numpy(fwd).cuda(), "ang": torch.from_numpy(ang).cuda()})
+    torch.cuda.synchronize()
+
+    def sweep():
+        for a in arms:
+            a["fb"].reset(*a["p"].init_pose)
+            a["sim"].reset(*a["p"].init_pose)
+            a["sim"].run_device(a["fwd"], a["ang"], 0, T, 0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        sweep()
+    barrier()
+    l0 = sum(a["fb"].kernel_launches for a in arms)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in arms]
+    barrier()
+    for a, (e0, _) in zip(arms, evs):
+        e0.record(a["stream"])
+    for _ in range(K):
+        sweep()
+    for a, (_, e1) in zip(arms, evs):
+        e1.record(a["stream"])
+    for a in arms:
+        a["fb"].synchronize()
+    barrier()
+    per_arm = [e0.elapsed_time(e1) for (e0, e1) in evs]
+    ms = max(per_arm)                                   # both arms start together; the job ends with the slower one
+    clk = clocks.stop() if rank == 0 else None
+    launches = sum(a["fb"].kernel_launches for a in arms) - l0
+    t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    value = world * 2 * Bh * T * K / (ms * 1e-3)
+    acc = {}
+    for a in arms:
+        st = parallel.allreduce_stats(a["fb"].stats(), torch.device("cuda", local))
+        acc[a["name"]] = parallel.derive_accuracy(st, world * Bh)
+    if rank == 0:
+        cfg = {"workload": f"{Bh} EKF-SLAM + {Bh} UKF-SLAM Monte-Carlo instances per GPU run concurrently, 50-landmark 5x10 grid map, "
+                           f"{T} filter steps per sweep (BASELINE configs[4] at bench scale)",
+               "instances_per_gpu": 2 * Bh, "filter_steps": T, "landmarks": 50,
+               "l2": "no explicit flush: the covariance working set of either arm exceeds the 126 MB L2 and is rewritten every step",
+               "parallelism": f"instances sharded over {world} GPU(s), no data-path collective; one all-reduce of error stats per filter kind"}
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": cfg, "clocks": clk, "e2e": None, "gpu_launches": int(launches),
+               "roofline": None, "cpu_baseline": None, "arm_ms_per_step": {a["name"]: t / K for a, t in zip(arms, per_arm)},
+               "accuracy": acc,
+               "note": "secondary configuration: e2e / roofline / cpu_baseline are reported by the single-kind lines (--filter ekf|ukf)"}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -169,6 +273,8 @@ def run_ours(args):
         fb.tune(3, 1)
     if args.cta_threads:
         fb.tune(2, args.cta_threads)
+    if args.filter == "ukf" and args.ukf_gen:
+        fb.tune(7, args.ukf_gen)
     stream = torch.cuda.ExternalStream(fb.stream, device=torch.device("cuda", local))
     d_fwd = torch.from_numpy(fwd).cuda()
     d_ang = torch.from_numpy(ang).cuda()
@@ -214,7 +320,7 @@ def run_ours(args):
     # ---- roofline: CUDA events on the launching stream around the kernel launches, separate sweeps.
     # (a) per-step streaming kernel (the one the per-call C-ABI path uses): P crosses HBM once each way per step.
     peak, peak_src = measured_peaks()
-    kname = "ekf_step_kernel" if args.filter == "ekf" else "ukf_step_kernel"
+    kname = "ekf_step_kernel" if args.filter == "ekf" else "ukf step (3 launches)"
     fb.tune(3, 1)                      # per-step launches
     fb.set_profiling(1)
     sweep()
@@ -249,7 +355,21 @@ def run_ours(args):
                              "for the HBM-streaming kernel of the per-call path)",
                     "step_kernel": step_roof}
     else:
-        roofline["kernel_share_of_sweep"] = k_ms / (ms / K) if ms > 0 else None
+        # the UKF step is FP64-compute bound (AI ~ n flop/B): report the nominal flops against a measured
+        # FP64 ceiling (cuBLAS DGEMM on this GPU); the streaming-model HBM view stays beside it
+        ceil_tf = fp64_ceiling(torch)
+        ach_tf = step_roof["algorithmic_gflops"] / 1e3
+        roofline = {"bound": "tensor", "kernel": "ukf step (ukf_front2_kernel + ukf_ql_kernel + ukf_back2_kernel)",
+                    "achieved": ach_tf, "peak": ceil_tf, "unit": "TFLOP/s", "frac": ach_tf / ceil_tf if ceil_tf > 0 else None,
+                    "peak_source": "measured here: cuBLAS DGEMM 4096^3 through torch.matmul (FP64 pipe / DMMA ceiling; "
+                                   "nominal B200 FP64 ~37-40 TFLOP/s); the kernels issue DFMA, not DMMA",
+                    "traffic": args.traffic_bytes, "kernel_ms_per_launch": step_roof["kernel_ms_per_launch"],
+                    "launches_timed": step_roof["launches_timed"], "mean_n": step_roof["mean_n"], "mean_k": step_roof["mean_k"],
+                    "kernel_share_of_sweep": k_ms / (ms / K) if ms > 0 else None,
+                    "model": "nominal flops of SURVEY 8d per update (9 n^3 eigh + 2 n^3 sqrt + 2 n^2 (2n+1) contraction + 12 k n^2); "
+                             "generation 2 of the step executes fewer (no explicit eigenvectors), so this is a "
+                             "throughput-equivalent rate, not an executed-flop rate",
+                    "hbm_view": step_roof}
 
     # ---- e2e: the per-step C-ABI call with HOST buffers (pinned), copies inside the timed region
     e2e = None
@@ -343,15 +463,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--filter", default="ekf", choices=["ekf", "ukf"])
+    ap.add_argument("--filter", default="ekf", choices=["ekf", "ukf", "mixed"])
     ap.add_argument("--instances", type=int, default=4096, help="filter instances per GPU")
     ap.add_argument("--filter-steps", type=int, default=1000)
     ap.add_argument("--max-meas", type=int, default=8)
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--e2e-sweeps", type=int, default=2)
-    ap.add_argument("--ref-instances-per-core", type=int, default=16)
+    ap.add_argument("--ref-instances-per-core", type=int, default=0, help="CPU baseline sample (0 = 16 for EKF, 1 for UKF)")
     ap.add_argument("--no-sweep", action="store_true", help="per-step launches on the value path (to profile ekf_step_kernel)")
     ap.add_argument("--cta-threads", type=int, default=0, help="force the CTA width of the EKF kernels (tuning)")
+    ap.add_argument("--ukf-gen", type=int, default=0, help="UKF step generation (slam_tune key 7); 0 = library default")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-traffic-bytes", type=float, default=None,
@@ -359,10 +480,14 @@ def main():
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/)")
     args = ap.parse_args()
+    if args.ref_instances_per_core <= 0:
+        args.ref_instances_per_core = 16 if args.filter == "ekf" else 1
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3   # timing rule: W >= 3
     if args.impl == "reference":
         return run_reference(args)
+    if args.filter == "mixed":
+        return run_mixed(args)
     return run_ours(args)
 
 

@@ -177,7 +177,7 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
         b.sigma = nullptr;   // allocated lazily by slam_get_sigma_points
         UkfScratch& u = h->uk;
         u.n_max = b.n_max;
-        u.gen = 1; u.clip_lanes = 0;   // generation 2 is opt-in (slam_tune key 7) until it is the faster one
+        u.gen = 2; u.clip_lanes = 0;
         u.rot_cap = 2LL * b.n_max * b.n_max;        // ~0.85 n^2 rotations are typical
         u.swp_cap = 6 * b.n_max;                    // ~1.7 n sweeps are typical
         CK(cudaMalloc(&u.Zg, sizeof(double) * (size_t)batch * b.n_max * b.n_max));

@@ -922,19 +922,21 @@ ukf_back_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, const
 // An instance whose rotation log overflowed (nswp = -1; never observed: the log holds 2 n^2 rotations, 2.4x the
 // typical count) is left untouched by ukf_back2_kernel and redone by the generation-1 kernels in rescue mode.
 // =========================================================================================================
-constexpr int WLD = 33;                  // pitch of the vector tile (doubles)
+// pitch of the vector tile (doubles): odd, >= the lanes a step can need (4 + 2 max_meas, + 4 clipped eigenvectors)
+__host__ __device__ inline int ukf_wcols(const BatchState& b) { const int c = 4 + 2 * b.max_meas + 4; return c > 32 ? 32 : c; }
+__host__ __device__ inline int ukf_wld(const BatchState& b) { return ukf_wcols(b) <= 24 ? 25 : 33; }   // compile-time variants of the kernel
 constexpr int UPD_LD = 24;               // per-update scalars
 constexpr int UKF2_MAX_UPD = 14;         // 4 + 2 * updates <= 32 lanes
 
 struct UkfWarpSmem {
-    double* W;      // [n_max][WLD]   lane j = vector j
+    double* W;      // [2 + n_max + 2][wld]   lane j = vector j; two spare rows on either side (prefetch overrun)
     double* x;      // prior x_t
     double* xp;     // running x_pred
     double* sq;     // sqrt(max(d, 1e-8))
     double* Xp;     // [4][nsm] propagated vehicle rows of the sigma points
     double* z;      // [2][nsm] z / dz of the update being prepared
     double* upd;    // [max_meas][UPD_LD]
-    double2* stage; // [64] rotation-log ring
+    double2* stage; // [2 + 64 + 2] rotation-log ring (spare entries for the prefetch overrun)
     double* corr;   // [32] 1e-8 - d_k of the clipped eigenvalues
     int* clip;      // [32] their indices
     int* ids;
@@ -947,20 +949,21 @@ __host__ __device__ inline size_t ukf_warp_carve(const BatchState& b, unsigned c
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
     const int nmp = ldg_of(b.n_max), nsm = 2 * b.n_max + 2;
-    size_t oW = take(sizeof(double) * (size_t)b.n_max * WLD);
+    const int wld = ukf_wld(b);
+    size_t oW = take(sizeof(double) * (size_t)(b.n_max + 4) * wld);
     size_t ox = take(sizeof(double) * nmp), oxp = take(sizeof(double) * nmp), osq = take(sizeof(double) * nmp);
     size_t oXp = take(sizeof(double) * 4 * nsm), oz = take(sizeof(double) * 2 * nsm);
     size_t oupd = take(sizeof(double) * UPD_LD * (b.max_meas > 0 ? b.max_meas : 1));
-    size_t ostage = take(sizeof(double2) * 64);
+    size_t ostage = take(sizeof(double2) * 68);
     size_t ocorr = take(sizeof(double) * 32), oclip = take(sizeof(int) * 32);
     size_t oids = take(sizeof(int) * (b.max_lm + 1));
     size_t omeas = take(sizeof(float) * 3 * (b.max_meas > 0 ? b.max_meas : 1));
     size_t oassoc = take(sizeof(int) * (b.max_meas > 0 ? b.max_meas : 1));
     size_t ouq = take(sizeof(int) * (b.max_meas > 0 ? b.max_meas : 1));
     if (s) {
-        s->W = (double*)(base + oW); s->x = (double*)(base + ox); s->xp = (double*)(base + oxp); s->sq = (double*)(base + osq);
+        s->W = (double*)(base + oW) + 2 * wld; s->x = (double*)(base + ox); s->xp = (double*)(base + oxp); s->sq = (double*)(base + osq);
         s->Xp = (double*)(base + oXp); s->z = (double*)(base + oz); s->upd = (double*)(base + oupd);
-        s->stage = (double2*)(base + ostage); s->corr = (double*)(base + ocorr); s->clip = (int*)(base + oclip);
+        s->stage = (double2*)(base + ostage) + 2; s->corr = (double*)(base + ocorr); s->clip = (int*)(base + oclip);
         s->ids = (int*)(base + oids); s->meas = (float*)(base + omeas); s->assoc = (int*)(base + oassoc); s->uq = (int*)(base + ouq);
     }
     return off;
@@ -972,61 +975,119 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// w <- H_k w over all reflectors, k ascending (Q^T w) or descending (Q w).  Row k of R: R[k] = tau_k at column k and
-// the reflector below it (v_k[k+1] = 1 stored).  Lanes are independent (lane = vector); reflector elements are
-// warp-uniform read-only loads.
-template <bool ASC>
-__device__ __forceinline__ void apply_reflectors(double* W, const int n, const int lane, const bool act,
+// w <- H_k w over all reflectors, k ascending (Q^T w) or descending (Q w), for the vectors in columns [0, nv).
+// Row k of R: tau_k at column k and the reflector below it (v_k[k+1] = 1 stored).  lane = COMPONENT here: a lane owns
+// the rows i = lane (mod 32) of the tile for the whole phase (no synchronisation between reflectors), the reflector is
+// one coalesced row load fetched one reflector ahead, and the nv dot products are reduced by shuffles four at a time.
+template <bool ASC, int NT, int WLD>
+__device__ __forceinline__ void apply_reflectors(double* W, const int n, const int lane, const int nv,
                                                  const double* __restrict__ R) {
-    for (int kk = 0; kk < n - 1; ++kk) {
-        const int k = ASC ? kk : n - 2 - kk;
-        const double* __restrict__ v = R + (size_t)k * n;
-        const double tau = __ldg(v + k);
-        if (tau == 0.0 || !act) continue;
-        double* w = W + lane;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int i = k + 1;
-        for (; i + 3 < n; i += 4) {
-            a0 += __ldg(v + i) * w[(i) * WLD];
-            a1 += __ldg(v + i + 1) * w[(i + 1) * WLD];
-            a2 += __ldg(v + i + 2) * w[(i + 2) * WLD];
-            a3 += __ldg(v + i + 3) * w[(i + 3) * WLD];
+    double va[NT], taua = 0.0;
+    auto loadk = [&](const int k, double (&dst)[NT], double& tau) {
+        if (k < 0 || k > n - 2) { tau = 0.0; return; }
+        const double* __restrict__ row = R + (size_t)k * n;
+        tau = __ldg(row + k);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { const int i = lane + 32 * t; dst[t] = (i > k && i < n) ? __ldg(row + i) : 0.0; }
+    };
+    const int step = ASC ? 1 : -1;
+    int k = ASC ? 0 : n - 2;
+    loadk(k, va, taua);
+    for (int kk = 0; kk < n - 1; ++kk, k += step) {
+        double v[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) v[t] = va[t];
+        const double tau = taua;
+        loadk(k + step, va, taua);
+        if (tau == 0.0) continue;
+        for (int j0 = 0; j0 < nv; j0 += 4) {
+            double w[NT][4];
+            double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const int i = lane + 32 * t;
+                if (i < n) {
+                    const double* wr = W + i * WLD + j0;
+                    w[t][0] = wr[0]; w[t][1] = wr[1]; w[t][2] = wr[2]; w[t][3] = wr[3];
+                    p0 += v[t] * w[t][0]; p1 += v[t] * w[t][1]; p2 += v[t] * w[t][2]; p3 += v[t] * w[t][3];
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+                p2 += __shfl_xor_sync(0xffffffffu, p2, o); p3 += __shfl_xor_sync(0xffffffffu, p3, o);
+            }
+            p0 *= tau; p1 *= tau; p2 *= tau; p3 *= tau;
+            const int left = nv - j0;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const int i = lane + 32 * t;
+                if (i < n && v[t] != 0.0) {
+                    double* wr = W + i * WLD + j0;
+                    wr[0] = w[t][0] - p0 * v[t];
+                    if (left > 1) wr[1] = w[t][1] - p1 * v[t];
+                    if (left > 2) wr[2] = w[t][2] - p2 * v[t];
+                    if (left > 3) wr[3] = w[t][3] - p3 * v[t];
+                }
+            }
         }
-        for (; i < n; ++i) a0 += __ldg(v + i) * w[i * WLD];
-        const double sc = tau * ((a0 + a1) + (a2 + a3));
-#pragma unroll 4
-        for (i = k + 1; i < n; ++i) w[i * WLD] -= sc * __ldg(v + i);
     }
+    __syncwarp();
 }
 
-// u <- V^T u: the QL kernel's rotation log replayed in generation order on the vector components
+// chunk c (32 rotations) of an instance's log, one entry per lane; identity beyond either end
+__device__ __forceinline__ double2 rot_chunk(const double2* __restrict__ rot, const int c, const int lane, const int nrot) {
+    const int ix = c * 32 + lane;
+    return (c >= 0 && ix < nrot) ? rot[ix] : make_double2(1.0, 0.0);
+}
+__device__ __forceinline__ int2 swp_at(const int2* __restrict__ swp, const int i, const int nsw) {
+    return (i >= 0 && i < nsw) ? swp[i] : make_int2(0, 0);
+}
+
+// u <- V^T u: the QL kernel's rotation log replayed in generation order on the vector components (lane = VECTOR; the
+// (c, s) stream is staged through a 2 x 32 shared-memory ring; the next chunk and the next sweep range are
+// fetched while the current ones are consumed)
+template <int WLD>
 __device__ __forceinline__ void apply_rot_fwd(double* W, const int lane, const bool act, const double2* __restrict__ rot,
                                               const int2* __restrict__ swp, const int nsw, const int nrot, double2* stage) {
     int g = 0;
-    double2 pre = (lane < nrot) ? rot[lane] : make_double2(1.0, 0.0);
-    int2 lm_next = (nsw > 0) ? swp[0] : make_int2(0, 0);
+    double2 q0 = rot_chunk(rot, 0, lane, nrot);
+    int2 lm0 = swp_at(swp, 0, nsw);
     double* w = W + lane;
     for (int sidx = 0; sidx < nsw; ++sidx) {
-        const int2 lm = lm_next;
-        if (sidx + 1 < nsw) lm_next = swp[sidx + 1];
+        const int2 lm = lm0;
+        lm0 = swp_at(swp, sidx + 1, nsw);
         const int l = lm.x, m = lm.y;
         double fz = 0.0, zi = 0.0;
         if (act) { fz = w[m * WLD]; zi = w[(m - 1) * WLD]; }
-        for (int i = m - 1; i >= l; --i, ++g) {
+        int i = m - 1;
+        while (i >= l) {
             if ((g & 31) == 0) {
+                const int c = g >> 5;
                 __syncwarp();
-                stage[((g >> 5) & 1) * 32 + lane] = pre;
-                const int nx = g + 32 + lane;
-                pre = (nx < nrot) ? rot[nx] : make_double2(1.0, 0.0);
+                stage[(c & 1) * 32 + lane] = q0;
+                q0 = rot_chunk(rot, c + 1, lane, nrot);
                 __syncwarp();
             }
-            const double2 cs = stage[g & 63];
+            int cnt = 32 - (g & 31);
+            if (cnt > i - l + 1) cnt = i - l + 1;
             if (act) {
-                const double zn = (i > l) ? w[(i - 1) * WLD] : 0.0;
-                w[(i + 1) * WLD] = cs.y * zi + cs.x * fz;
-                fz = cs.x * zi - cs.y * fz;
-                zi = zn;
+                const double2* __restrict__ st = stage + (g & 63);
+                double* wi = w + i * WLD;
+                double2 c0 = st[0], c1 = st[1];
+                double z1 = wi[-WLD];                               // row i - 1 (a spare row when i = 0)
+#pragma unroll 4
+                for (int q = 0; q < cnt; ++q) {
+                    const double2 c2 = st[q + 2];                   // operands two rotations ahead
+                    const double z2 = wi[-2 * WLD];
+                    const double t = c0.x * zi;
+                    wi[WLD] = fma(c0.x, fz, c0.y * zi);
+                    fz = fma(-c0.y, fz, t);
+                    zi = z1; z1 = z2; c0 = c1; c1 = c2;
+                    wi -= WLD;
+                }
             }
+            i -= cnt; g += cnt;
         }
         if (act) w[l * WLD] = fz;
     }
@@ -1034,40 +1095,53 @@ __device__ __forceinline__ void apply_rot_fwd(double* W, const int lane, const b
 }
 
 // u <- V u: the log replayed backwards, every plane rotation inverted (each 2x2 step [[s,c],[c,-s]] is its own inverse)
+template <int WLD>
 __device__ __forceinline__ void apply_rot_bwd(double* W, const int lane, const bool act, const double2* __restrict__ rot,
                                               const int2* __restrict__ swp, const int nsw, const int nrot, double2* stage) {
     if (nrot <= 0) return;
     int g = nrot - 1;
+    const int cl = g >> 5;
     {
-        const int c = g >> 5;
-        const int ix = c * 32 + lane;
-        const double2 cur = (ix < nrot) ? rot[ix] : make_double2(1.0, 0.0);
+        const double2 cur = rot_chunk(rot, cl, lane, nrot);
         __syncwarp();
-        stage[(c & 1) * 32 + lane] = cur;
+        stage[(cl & 1) * 32 + lane] = cur;
         __syncwarp();
     }
-    double2 pre = (g >= 32) ? rot[((g >> 5) - 1) * 32 + lane] : make_double2(1.0, 0.0);
-    int2 lm_next = swp[nsw - 1];
+    double2 q0 = rot_chunk(rot, cl - 1, lane, nrot);
+    int2 lm0 = swp_at(swp, nsw - 1, nsw);
     double* w = W + lane;
     for (int sidx = nsw - 1; sidx >= 0; --sidx) {
-        const int2 lm = lm_next;
-        if (sidx > 0) lm_next = swp[sidx - 1];
+        const int2 lm = lm0;
+        lm0 = swp_at(swp, sidx - 1, nsw);
         const int l = lm.x, m = lm.y;
         double fz = 0.0, a = 0.0;
         if (act) { fz = w[l * WLD]; a = w[(l + 1) * WLD]; }
-        for (int i = l; i < m; ++i, --g) {
-            const double2 cs = stage[g & 63];
+        int i = l;
+        while (i < m) {
+            int cnt = (g & 31) + 1;                              // rotations left in the staged chunk (going down)
+            if (cnt > m - i) cnt = m - i;
             if (act) {
-                const double an = (i + 2 <= m) ? w[(i + 2) * WLD] : 0.0;
-                w[i * WLD] = cs.y * a + cs.x * fz;
-                fz = cs.x * a - cs.y * fz;
-                a = an;
+                const double2* __restrict__ st = stage + (g & 63);
+                double* wi = w + i * WLD;
+                double2 c0 = st[0], c1 = st[-1];
+                double a1 = wi[2 * WLD];                            // row i + 2 (a spare row beyond n - 1)
+#pragma unroll 4
+                for (int q = 0; q < cnt; ++q) {
+                    const double2 c2 = st[-(q + 2)];                // operands two rotations ahead
+                    const double a2 = wi[3 * WLD];
+                    const double t = c0.x * a;
+                    wi[0] = fma(c0.x, fz, c0.y * a);
+                    fz = fma(-c0.y, fz, t);
+                    a = a1; a1 = a2; c0 = c1; c1 = c2;
+                    wi += WLD;
+                }
             }
-            if ((g & 31) == 0 && g > 0) {          // the next rotation (g - 1) opens chunk (g >> 5) - 1
-                const int c = (g >> 5) - 1;
+            i += cnt; g -= cnt;
+            if ((g & 31) == 31 && g > 0) {                       // the next rotation opens chunk g >> 5
+                const int c = g >> 5;
                 __syncwarp();
-                stage[(c & 1) * 32 + lane] = pre;
-                pre = (c > 0) ? rot[(c - 1) * 32 + lane] : make_double2(1.0, 0.0);
+                stage[(c & 1) * 32 + lane] = q0;
+                q0 = rot_chunk(rot, c - 1, lane, nrot);
                 __syncwarp();
             }
         }
@@ -1126,6 +1200,7 @@ ukf_front2_kernel(BatchState b, UkfScratch u) {
 }
 
 // ---- launch 3 of 3 (generation 2): warp per instance
+template <int wld>
 __global__ void __launch_bounds__(32)
 ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1136,6 +1211,9 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u) {
     const int ldp = b.fixed_ld;
     const int nsm = 2 * b.n_max + 2;
     const unsigned FULL = 0xffffffffu;
+    const int wcols = ukf_wcols(b);
+    double* const W_ = s.W;
+    const bool small_n = b.n_max <= 128;
 
     const int4 meta_in = b.meta[inst];
     int nm = in.n_meas[inst];
@@ -1201,23 +1279,22 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u) {
     }
     __syncwarp();
     const int nvec = 4 + 2 * nu;                    // lanes of the two S-passes
-    int ncf = 32 - nvec; if (ncf > nclip) ncf = nclip;   // clipped eigenvectors riding in pass A
+    int ncf = wcols - nvec; if (ncf > nclip) ncf = nclip;   // clipped eigenvectors riding in pass A
     if (u.clip_lanes > 0 && ncf > u.clip_lanes) ncf = u.clip_lanes;        // test knob
 
     // ---- clipped eigenpairs that do not fit beside pass A (never in practice): z_k = Q V e_k, 32 at a time,
     //      folded into the landmark-block seed  Yg += 2w (1e-8 - d_k) z_k z_k^T
-    for (int c0 = ncf; c0 < nclip && c0 < 32; c0 += 32) {
-        const int cnt = (nclip < 32 ? nclip : 32) - c0;
+    for (int c0 = ncf; c0 < nclip && c0 < 32; c0 += wcols) {
+        int cnt = (nclip < 32 ? nclip : 32) - c0; if (cnt > wcols) cnt = wcols;
         const bool act = lane < cnt;
-        for (int i = 0; i < n; ++i) s.W[i * WLD + lane] = (act && s.clip[c0 + lane] == i) ? 1.0 : 0.0;
+        if (lane < wcols) for (int i = 0; i < n; ++i) W_[i * wld + lane] = (act && s.clip[c0 + lane] == i) ? 1.0 : 0.0;
         __syncwarp();
-        apply_rot_bwd(s.W, lane, act, rot, swp, nsw, nrot, s.stage);
-        apply_reflectors<false>(s.W, n, lane, act, R);
-        __syncwarp();
+        apply_rot_bwd<wld>(W_, lane, act, rot, swp, nsw, nrot, s.stage);
+        if (small_n) apply_reflectors<false, 4, wld>(W_, n, lane, cnt, R); else apply_reflectors<false, 8, wld>(W_, n, lane, cnt, R);
         for (int a = 4; a < n; ++a)
             for (int c = 4 + lane; c < n; c += 32) {
                 double add = 0.0;
-                for (int q = 0; q < cnt; ++q) add += (2.0 * wgt) * s.corr[c0 + q] * s.W[a * WLD + q] * s.W[c * WLD + q];
+                for (int q = 0; q < cnt; ++q) add += (2.0 * wgt) * s.corr[c0 + q] * W_[a * wld + q] * W_[c * wld + q];
                 Yg[(size_t)a * n + c] += add;
             }
         __syncwarp();
@@ -1229,20 +1306,20 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u) {
         int row = -1;
         if (lane < 4) row = lane;
         else if (lane < nvec) { const int q = (lane - 4) >> 1; row = s.assoc[s.uq[q]] * 2 + 4 + ((lane - 4) & 1); }   // :298
-        for (int i = 0; i < n; ++i) s.W[i * WLD + lane] = (i == row) ? 1.0 : 0.0;
+        if (lane < wcols) for (int i = 0; i < n; ++i) W_[i * wld + lane] = (i == row) ? 1.0 : 0.0;
         const bool act = lane < nvec;
-        apply_reflectors<true>(s.W, n, lane, act, R);
-        apply_rot_fwd(s.W, lane, act, rot, swp, nsw, nrot, s.stage);
+        __syncwarp();
+        if (small_n) apply_reflectors<true, 4, wld>(W_, n, lane, nvec, R); else apply_reflectors<true, 8, wld>(W_, n, lane, nvec, R);
+        apply_rot_fwd<wld>(W_, lane, act, rot, swp, nsw, nrot, s.stage);
         const bool isclip = lane >= nvec && lane < nvec + ncf;
         const int ck = isclip ? s.clip[lane - nvec] : -1;
-        for (int i = 0; i < n; ++i) {
-            if (act) s.W[i * WLD + lane] *= s.sq[i];
-            else s.W[i * WLD + lane] = (i == ck) ? 1.0 : 0.0;
+        if (lane < wcols) for (int i = 0; i < n; ++i) {
+            if (act) W_[i * wld + lane] *= s.sq[i];
+            else W_[i * wld + lane] = (i == ck) ? 1.0 : 0.0;
         }
         const bool act2 = act || isclip;
-        apply_rot_bwd(s.W, lane, act2, rot, swp, nsw, nrot, s.stage);
-        apply_reflectors<false>(s.W, n, lane, act2, R);
-        __syncwarp();
+        apply_rot_bwd<wld>(W_, lane, act2, rot, swp, nsw, nrot, s.stage);
+        if (small_n) apply_reflectors<false, 4, wld>(W_, n, lane, nvec + ncf, R); else apply_reflectors<false, 8, wld>(W_, n, lane, nvec + ncf, R);
     }
 
     // ---- sigma points, vehicle rows (:214-226): X = x +- column of S, motion model per sigma point
@@ -1251,7 +1328,7 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const double xr = s.x[r];
-            X[r] = (i == 0) ? xr : (i <= n ? xr + s.W[(i - 1) * WLD + r] : xr - s.W[(i - 1 - n) * WLD + r]);
+            X[r] = (i == 0) ? xr : (i <= n ? xr + W_[(i - 1) * wld + r] : xr - W_[(i - 1 - n) * wld + r]);
         }
         const float yaw = yaw_of(X[2], X[3]);                              // :128
         const float ud = u_d + fc.v_d;
@@ -1317,8 +1394,8 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u) {
         double* z1 = s.z + nsm;
         for (int i = lane; i < ns; i += 32) {                               // sensingModel per sigma point (:305-308)
             double lx = s.x[li], ly = s.x[li + 1];
-            if (i >= 1 && i <= n) { lx += s.W[(i - 1) * WLD + c0]; ly += s.W[(i - 1) * WLD + c0 + 1]; }
-            else if (i > n) { lx -= s.W[(i - 1 - n) * WLD + c0]; ly -= s.W[(i - 1 - n) * WLD + c0 + 1]; }
+            if (i >= 1 && i <= n) { lx += W_[(i - 1) * wld + c0]; ly += W_[(i - 1) * wld + c0 + 1]; }
+            else if (i > n) { lx -= W_[(i - 1 - n) * wld + c0]; ly -= W_[(i - 1 - n) * wld + c0 + 1]; }
             const double dx = lx - s.Xp[0 * nsm + i], dy = ly - s.Xp[1 * nsm + i];
             z0[i] = sqrt(dx * dx + dy * dy) + (double)fc.w_r;               // :144
             z1[i] = remainder(atan2(dy, dx) - (double)yaw_prior + (double)fc.w_b, TWO_PI_REF);   // :145,156
@@ -1364,26 +1441,25 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u) {
             ud[18] = remainder((double)s.meas[3 * l + 2] - 0.0, TWO_PI_REF);
         }
         for (int i = lane; i < n; i += 32) {
-            s.W[i * WLD + c0] = z0[1 + i] - z0[1 + n + i];
-            s.W[i * WLD + c0 + 1] = z1[1 + i] - z1[1 + n + i];
+            W_[i * wld + c0] = z0[1 + i] - z0[1 + n + i];
+            W_[i * wld + c0 + 1] = z1[1 + i] - z1[1 + n + i];
         }
         __syncwarp();
     }
     // g_a[i] = Xp[a][1+i] - Xp[a][1+n+i] -> lanes 0..3
     for (int i = lane; i < n; i += 32)
 #pragma unroll
-        for (int a = 0; a < 4; ++a) s.W[i * WLD + a] = s.Xp[a * nsm + 1 + i] - s.Xp[a * nsm + 1 + n + i];
+        for (int a = 0; a < 4; ++a) W_[i * wld + a] = s.Xp[a * nsm + 1 + i] - s.Xp[a * nsm + 1 + n + i];
     __syncwarp();
 
     // ---- pass B: S g_a and S hv for every update; the clipped eigenvectors stay put in their lanes
     {
         const bool act = lane < nvec;
-        apply_reflectors<true>(s.W, n, lane, act, R);
-        apply_rot_fwd(s.W, lane, act, rot, swp, nsw, nrot, s.stage);
-        if (act) for (int i = 0; i < n; ++i) s.W[i * WLD + lane] *= s.sq[i];
-        apply_rot_bwd(s.W, lane, act, rot, swp, nsw, nrot, s.stage);
-        apply_reflectors<false>(s.W, n, lane, act, R);
-        __syncwarp();
+        if (small_n) apply_reflectors<true, 4, wld>(W_, n, lane, nvec, R); else apply_reflectors<true, 8, wld>(W_, n, lane, nvec, R);
+        apply_rot_fwd<wld>(W_, lane, act, rot, swp, nsw, nrot, s.stage);
+        if (act) for (int i = 0; i < n; ++i) W_[i * wld + lane] *= s.sq[i];
+        apply_rot_bwd<wld>(W_, lane, act, rot, swp, nsw, nrot, s.stage);
+        if (small_n) apply_reflectors<false, 4, wld>(W_, n, lane, nvec, R); else apply_reflectors<false, 8, wld>(W_, n, lane, nvec, R);
     }
 
     // ---- gains (:336-345) in message order: C uses the RUNNING x_pred; K_q overwrites the update's lanes of W
@@ -1399,11 +1475,11 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u) {
                 c0v = ud[5 + 2 * a] + sh * sdz0; c1v = ud[6 + 2 * a] + sh * sdz1;
             } else {
                 const double fa = s.x[a] - s.xp[a];
-                c0v = fa * sdz0 + wgt * s.W[a * WLD + c0];
-                c1v = fa * sdz1 + wgt * s.W[a * WLD + c0 + 1];
+                c0v = fa * sdz0 + wgt * W_[a * wld + c0];
+                c1v = fa * sdz1 + wgt * W_[a * wld + c0 + 1];
             }
             const double k0 = c0v * i00 + c1v * i10, k1 = c0v * i01 + c1v * i11;
-            s.W[a * WLD + c0] = k0; s.W[a * WLD + c0 + 1] = k1;
+            W_[a * wld + c0] = k0; W_[a * wld + c0 + 1] = k1;
             s.xp[a] = s.xp[a] + (k0 * in0 + k1 * in1);
         }
     }
@@ -1412,30 +1488,41 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u) {
     // ---- P_pred, written once (:235-240 then :348 per update, in message order)
     for (int i = 0; i < n; ++i) {
         const double ei = (i >= 4) ? s.x[i] - sw * s.x[i] : 0.0;
-        for (int j = lane; j < n; j += 32) {
-            double val;
-            if (i < 4 && j < 4) {
-                const int a = i < j ? i : j, c = i < j ? j : i;
-                val = vv[a * 4 - (a * (a - 1)) / 2 + (c - a)];
-            } else if (i < 4) {
-                const double eb = s.x[j] - sw * s.x[j];
-                val = wgt * s.W[j * WLD + i] + eb * mv[i];
-            } else if (j < 4) {
-                val = wgt * s.W[i * WLD + j] + ei * mv[j];
-            } else {
-                const double ej = s.x[j] - sw * s.x[j];
-                double add = sw * ei * ej;
-                for (int q = 0; q < ncf; ++q) add += (2.0 * wgt) * s.corr[q] * s.W[i * WLD + nvec + q] * s.W[j * WLD + nvec + q];
-                val = Yg[(size_t)i * n + j] + add;
+        for (int jb = 0; jb < n; jb += 128) {
+            double yv[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {                       // the row's seed loads go out together
+                const int j = jb + lane + 32 * t;
+                yv[t] = (i >= 4 && j >= 4 && j < n) ? Yg[(size_t)i * n + j] : 0.0;
             }
-            for (int q = 0; q < nu; ++q) {
-                const double* ud = s.upd + q * UPD_LD;
-                const int c0 = 4 + 2 * q;
-                const double ki0 = s.W[i * WLD + c0], ki1 = s.W[i * WLD + c0 + 1];
-                const double ks0 = ki0 * ud[0] + ki1 * ud[1], ks1 = ki0 * ud[1] + ki1 * ud[2];
-                val -= ks0 * s.W[j * WLD + c0] + ks1 * s.W[j * WLD + c0 + 1];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int j = jb + lane + 32 * t;
+                if (j >= n) continue;
+                double val;
+                if (i < 4 && j < 4) {
+                    const int a = i < j ? i : j, c = i < j ? j : i;
+                    val = vv[a * 4 - (a * (a - 1)) / 2 + (c - a)];
+                } else if (i < 4) {
+                    const double eb = s.x[j] - sw * s.x[j];
+                    val = wgt * W_[j * wld + i] + eb * mv[i];
+                } else if (j < 4) {
+                    val = wgt * W_[i * wld + j] + ei * mv[j];
+                } else {
+                    const double ej = s.x[j] - sw * s.x[j];
+                    double add = sw * ei * ej;
+                    for (int q = 0; q < ncf; ++q) add += (2.0 * wgt) * s.corr[q] * W_[i * wld + nvec + q] * W_[j * wld + nvec + q];
+                    val = yv[t] + add;
+                }
+                for (int q = 0; q < nu; ++q) {
+                    const double* ud = s.upd + q * UPD_LD;
+                    const int c0 = 4 + 2 * q;
+                    const double ki0 = W_[i * wld + c0], ki1 = W_[i * wld + c0 + 1];
+                    const double ks0 = ki0 * ud[0] + ki1 * ud[1], ks1 = ki0 * ud[1] + ki1 * ud[2];
+                    val -= ks0 * W_[j * wld + c0] + ks1 * W_[j * wld + c0 + 1];
+                }
+                gP[(size_t)i * ldp + j] = val;
             }
-            gP[(size_t)i * ldp + j] = val;
         }
     }
     __syncwarp();
@@ -1498,11 +1585,12 @@ cudaError_t ukf_step_configure(const BatchState& b) {
     if ((e = cudaFuncSetAttribute(ukf_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_front2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ukf_back2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back2_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back2_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b))) != cudaSuccess) return e;
     return cudaFuncSetAttribute(ukf_ql_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ql_smem_bytes(b));
 }
 
-bool ukf_gen2_supported(const BatchState& b) { return b.max_meas <= UKF2_MAX_UPD && ukf_warp_smem_bytes(b) <= 227 * 1024; }
+bool ukf_gen2_supported(const BatchState& b) { return b.max_meas <= UKF2_MAX_UPD && b.n_max <= 256 && ukf_warp_smem_bytes(b) <= 227 * 1024; }
 
 cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, const UkfScratch& u, cudaStream_t st,
                             int* launched) {
@@ -1510,7 +1598,8 @@ cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const St
     if (u.gen == 2 && ukf_gen2_supported(b)) {
         ukf_front2_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, u);
         ukf_ql_kernel<<<qblocks, QL_LANES, ql_smem_bytes(b), st>>>(u, b.meta, b.batch);
-        ukf_back2_kernel<<<b.batch, 32, ukf_warp_smem_bytes(b), st>>>(b, fc, in, u);
+        if (ukf_wld(b) == 25) ukf_back2_kernel<25><<<b.batch, 32, ukf_warp_smem_bytes(b), st>>>(b, fc, in, u);
+        else ukf_back2_kernel<33><<<b.batch, 32, ukf_warp_smem_bytes(b), st>>>(b, fc, in, u);
         // rescue pass (generation-1 kernels, in-CTA QL): instances whose rotation log overflowed; everyone else exits at once
         ukf_front_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, fc, in, u, 1);
         ukf_back_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, fc, in, u, 1);

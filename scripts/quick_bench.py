@@ -17,6 +17,8 @@ def main():
     fb = shim.FilterBatch(kind, p.to_c(), B, 50, 8)
     sim = shim.Simulator(fb, lm, seed=1)
     reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+    if len(sys.argv) > 5:
+        fb.tune(7, int(sys.argv[5]))
     for rep in range(reps):
         fb.reset(0, 0, 0)
         sim.reset()
