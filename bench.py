@@ -469,7 +469,7 @@ def main():
     ap.add_argument("--max-meas", type=int, default=8)
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--e2e-sweeps", type=int, default=2)
-    ap.add_argument("--ref-instances-per-core", type=int, default=0, help="CPU baseline sample (0 = 16 for EKF, 1 for UKF)")
+    ap.add_argument("--ref-instances-per-core", type=int, default=0, help="CPU baseline sample (0 = 16 for EKF, 8 for UKF)")
     ap.add_argument("--no-sweep", action="store_true", help="per-step launches on the value path (to profile ekf_step_kernel)")
     ap.add_argument("--cta-threads", type=int, default=0, help="force the CTA width of the EKF kernels (tuning)")
     ap.add_argument("--ukf-gen", type=int, default=0, help="UKF step generation (slam_tune key 7); 0 = library default")
@@ -481,7 +481,7 @@ def main():
                     help="dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/)")
     args = ap.parse_args()
     if args.ref_instances_per_core <= 0:
-        args.ref_instances_per_core = 16 if args.filter == "ekf" else 1
+        args.ref_instances_per_core = 16 if args.filter == "ekf" else 8
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3   # timing rule: W >= 3
     if args.impl == "reference":

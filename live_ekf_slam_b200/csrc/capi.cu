@@ -31,6 +31,7 @@ struct slam_filter {
     bool large = false;
     LargeState lg{};
     UkfScratch uk{};                  // HBM scratch between the three launches of a UKF step
+    UkfStreams uks{};                 // slices of the batch run front -> QL -> back on their own streams
     int* h_nmeas_pin = nullptr;       // pinned scratch for the host-side measurement count
     // per-launch timing of the filter-step kernel
     // capacity hint: device max(M) read back with a lag of HINT_LAG launches (never waited on in steady state)
@@ -178,6 +179,12 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
         UkfScratch& u = h->uk;
         u.n_max = b.n_max;
         u.gen = 2; u.clip_lanes = 0;
+        h->uks.nsub = 1;
+        CK(cudaEventCreateWithFlags(&h->uks.fork, cudaEventDisableTiming));
+        for (int k = 0; k < UKF_MAX_SUB - 1; ++k) {
+            CK(cudaStreamCreateWithFlags(&h->uks.aux[k], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&h->uks.join[k], cudaEventDisableTiming));
+        }
         u.rot_cap = 2LL * b.n_max * b.n_max;        // ~0.85 n^2 rotations are typical
         u.swp_cap = 6 * b.n_max;                    // ~1.7 n sweeps are typical
         CK(cudaMalloc(&u.Zg, sizeof(double) * (size_t)batch * b.n_max * b.n_max));
@@ -239,6 +246,11 @@ int slam_destroy(slam_handle_t h) {
     cudaFree(h->d_fwd); cudaFree(h->d_ang); cudaFree(h->d_meas); cudaFree(h->d_nmeas);
     cudaFree(h->d_traj_fwd); cudaFree(h->d_traj_ang); cudaFree(h->d_out);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    if (h->uks.fork) cudaEventDestroy(h->uks.fork);
+    for (int k = 0; k < UKF_MAX_SUB - 1; ++k) {
+        if (h->uks.aux[k]) { cudaStreamSynchronize(h->uks.aux[k]); cudaStreamDestroy(h->uks.aux[k]); }
+        if (h->uks.join[k]) cudaEventDestroy(h->uks.join[k]);
+    }
     cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -266,6 +278,7 @@ int slam_tune(slam_handle_t h, int key, int value) {
         const long long full = 2LL * h->b.n_max * h->b.n_max;
         h->uk.rot_cap = (value <= 0 || value > full) ? full : value;
     } else if (key == 9) h->uk.clip_lanes = value < 0 ? 0 : value;
+    else if (key == 10) { if (value < 1 || value > UKF_MAX_SUB) return fail(h, "slam_tune: UKF slices must be 1..8"); h->uks.nsub = value; }
     else return fail(h, "slam_tune: unknown key");
     return 0;
 }
@@ -338,7 +351,7 @@ static int do_step(slam_filter* h, const float* d_fwd, const float* d_ang, int c
     if (h->kind == SLAM_EKF_SLAM) {
         CK(launch_ekf_step(h->b, h->fc, in, phases, cap, h->force_threads, h->stream));
     }
-    else { int nl = 0; CK(launch_ukf_step(h->b, h->fc, in, h->uk, h->stream, &nl)); h->launches += nl; }
+    else { int nl = 0; CK(launch_ukf_step(h->b, h->fc, in, h->uk, h->stream, h->uks, &nl)); h->launches += nl; }
     if (h->profiling) { CK(cudaEventRecord(h->ev[h->ev_used + 1], h->stream)); h->ev_used += 2; }
     {
         const int slot = (int)(h->step_seq % slam_filter::HINT_RING);

@@ -193,9 +193,17 @@ struct UkfScratch {
     int gen;            // 2 (default): reflector / rotation-log products, warp per instance; 1: explicit eigenvectors
     int clip_lanes;     // test knob: max clipped eigenvectors riding beside pass A (0 = as many as fit)
 };
+// streams / events of the sliced generation-2 step (owned by the handle)
+constexpr int UKF_MAX_SUB = 8;
+struct UkfStreams {
+    int nsub = 1;                               // slices of the batch (1 = everything on the handle's stream)
+    cudaStream_t aux[UKF_MAX_SUB - 1] = {};
+    cudaEvent_t fork = nullptr;
+    cudaEvent_t join[UKF_MAX_SUB - 1] = {};
+};
 // launches one UKF step; *launched receives the number of kernels launched
 cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, const UkfScratch& u, cudaStream_t st,
-                            int* launched);
+                            const UkfStreams& xs, int* launched);
 size_t ukf_step_smem_bytes(const BatchState& b);
 cudaError_t ukf_step_configure(const BatchState& b);
 

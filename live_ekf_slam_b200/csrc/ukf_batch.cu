@@ -357,19 +357,26 @@ __device__ void ql_serial(double* A, const int lds, const int n, double* d, doub
 // ---------------------------------------------------------------------------------------------------------
 constexpr int QL_LANES = 32;
 
+// SMEM = false: (d, e) are worked on in place in the HBM scratch ([k][instance], coalesced over the lanes, L1/L2 cached; the
+// operands of a rotation are fetched one rotation ahead), so the kernel needs no shared memory and its 32-thread CTAs
+// co-reside with the other slices' front / back kernels.  On overflow dg / eg are then clobbered: only for callers that
+// redo the tridiagonalisation (the generation-2 rescue pass).
+template <bool SMEM>
 __global__ void __launch_bounds__(QL_LANES)
-ukf_ql_kernel(UkfScratch u, const int4* __restrict__ meta, const int batch) {
+ukf_ql_kernel(UkfScratch u, const int4* __restrict__ meta, const int batch, const int i0, const int i1) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
-    const int inst = blockIdx.x * QL_LANES + lane;
-    if (inst >= batch) return;
+    const int inst = i0 + blockIdx.x * QL_LANES + lane;
+    if (inst >= i1) return;
     if (meta[inst].y & SLAM_STATUS_SAME_STEP_REMATCH) return;
     const int n = 4 + 2 * meta[inst].x;
     double* sd = reinterpret_cast<double*>(smem_raw);           // [n_max][32]
     double* se = sd + (size_t)u.n_max * QL_LANES;               // [n_max][32]
-#define D_(k) sd[(k) * QL_LANES + lane]
-#define E_(k) se[(k) * QL_LANES + lane]
-    for (int k = 0; k < n; ++k) { D_(k) = u.dg[(size_t)k * batch + inst]; E_(k) = u.eg[(size_t)k * batch + inst]; }
+    double* const gd = u.dg + inst;
+    double* const ge = u.eg + inst;
+#define D_(k) (*(SMEM ? sd + (k) * QL_LANES + lane : gd + (size_t)(k) * batch))
+#define E_(k) (*(SMEM ? se + (k) * QL_LANES + lane : ge + (size_t)(k) * batch))
+    if (SMEM) for (int k = 0; k < n; ++k) { D_(k) = u.dg[(size_t)k * batch + inst]; E_(k) = u.eg[(size_t)k * batch + inst]; }
     double2* rot = u.rot + (size_t)inst * u.rot_cap;
     int2* swp = u.swp + (size_t)inst * u.swp_cap;
     long long nrot = 0;
@@ -395,7 +402,17 @@ ukf_ql_kernel(UkfScratch u, const int4* __restrict__ meta, const int batch) {
             D_(l + 1) = el * (pp + r);
             const double dl1 = D_(l + 1);
             double h = g - D_(l);
-            for (int i = l + 2; i < n; ++i) D_(i) -= h;
+            {
+                int i = l + 2;
+                for (; i + 7 < n; i += 8) {                       // loads first, stores after: eight in flight (HBM variant)
+                    double t8[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) t8[j] = D_(i + j);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) D_(i + j) = t8[j] - h;
+                }
+                for (; i < n; ++i) D_(i) -= h;
+            }
             f += h;
             pp = D_(m);
             double c = 1.0, c2 = c, c3 = c, s = 0.0, s2 = 0.0;
@@ -423,7 +440,7 @@ ukf_ql_kernel(UkfScratch u, const int4* __restrict__ meta, const int batch) {
         }
     }
     if (over) { u.nswp[inst] = -1; return; }
-    for (int k = 0; k < n; ++k) u.dg[(size_t)k * batch + inst] = D_(k);
+    if (SMEM) for (int k = 0; k < n; ++k) u.dg[(size_t)k * batch + inst] = D_(k);
     u.nswp[inst] = nsw;
 #undef D_
 #undef E_
@@ -1152,12 +1169,12 @@ __device__ __forceinline__ void apply_rot_bwd(double* W, const int lane, const b
 
 // ---- launch 1 of 3 (generation 2): Y = scale * sym(P) (ukf.cpp:112-114), tridiagonalisation; P is NOT modified
 __global__ void __launch_bounds__(UKF_THREADS, 2)
-ukf_front2_kernel(BatchState b, UkfScratch u) {
+ukf_front2_kernel(BatchState b, UkfScratch u, const int i0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     UkfSmem s;
     ukf_smem_carve(b, smem_raw, &s);
     const int tid = threadIdx.x;
-    const int inst = blockIdx.x;
+    const int inst = i0 + blockIdx.x;
     const int lds = b.lds;
     const int ldp = b.fixed_ld;
     const int4 meta_in = b.meta[inst];
@@ -1202,12 +1219,12 @@ ukf_front2_kernel(BatchState b, UkfScratch u) {
 // ---- launch 3 of 3 (generation 2): warp per instance
 template <int wld>
 __global__ void __launch_bounds__(32)
-ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u) {
+ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, const int i0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     UkfWarpSmem s;
     ukf_warp_carve(b, smem_raw, &s);
     const int lane = threadIdx.x;
-    const int inst = blockIdx.x;
+    const int inst = i0 + blockIdx.x;
     const int ldp = b.fixed_ld;
     const int nsm = 2 * b.n_max + 2;
     const unsigned FULL = 0xffffffffu;
@@ -1587,26 +1604,51 @@ cudaError_t ukf_step_configure(const BatchState& b) {
     if ((e = cudaFuncSetAttribute(ukf_front2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back2_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back2_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b))) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(ukf_ql_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ql_smem_bytes(b));
+    return cudaFuncSetAttribute(ukf_ql_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ql_smem_bytes(b));
 }
 
 bool ukf_gen2_supported(const BatchState& b) { return b.max_meas <= UKF2_MAX_UPD && b.n_max <= 256 && ukf_warp_smem_bytes(b) <= 227 * 1024; }
 
 cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, const UkfScratch& u, cudaStream_t st,
-                            int* launched) {
+                            const UkfStreams& xs, int* launched) {
     const int qblocks = (b.batch + QL_LANES - 1) / QL_LANES;
     if (u.gen == 2 && ukf_gen2_supported(b)) {
-        ukf_front2_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, u);
-        ukf_ql_kernel<<<qblocks, QL_LANES, ql_smem_bytes(b), st>>>(u, b.meta, b.batch);
-        if (ukf_wld(b) == 25) ukf_back2_kernel<25><<<b.batch, 32, ukf_warp_smem_bytes(b), st>>>(b, fc, in, u);
-        else ukf_back2_kernel<33><<<b.batch, 32, ukf_warp_smem_bytes(b), st>>>(b, fc, in, u);
+        // Optionally (slam_tune key 10; default 1 = off) the batch is cut into nsub contiguous slices, each with its own
+        // front -> QL -> back chain on its own stream, so that the QL kernel -- a pure latency chain, one thread per
+        // instance, ~0.8 n^2 dependent rotations -- can run under the other slices' kernels.  Measured on B200 (4096
+        // instances, n -> 104): 2 % faster with the shared-memory QL (which cannot co-reside: front and back fill the
+        // SMs' shared memory), 30 % SLOWER with the shared-memory-free QL (1.15-wave launches; the chain stretches when it
+        // shares schedulers) -- kept as a knob, not a default.
+        int nsub = xs.nsub < 1 ? 1 : xs.nsub;
+        if (nsub > UKF_MAX_SUB) nsub = UKF_MAX_SUB;
+        if (b.batch < 64 * nsub) nsub = 1;
+        cudaError_t e;
+        if (nsub > 1) {
+            if ((e = cudaEventRecord(xs.fork, st)) != cudaSuccess) return e;
+            for (int k = 1; k < nsub; ++k) if ((e = cudaStreamWaitEvent(xs.aux[k - 1], xs.fork, 0)) != cudaSuccess) return e;
+        }
+        const size_t fsm = ukf_step_smem_bytes(b), wsm = ukf_warp_smem_bytes(b);
+        for (int k = 0; k < nsub; ++k) {
+            const int i0 = (int)((long long)b.batch * k / nsub), i1 = (int)((long long)b.batch * (k + 1) / nsub);
+            if (i1 <= i0) continue;
+            cudaStream_t sk = (k == 0) ? st : xs.aux[k - 1];
+            ukf_front2_kernel<<<i1 - i0, UKF_THREADS, fsm, sk>>>(b, u, i0);
+            if (nsub == 1) ukf_ql_kernel<true><<<(i1 - i0 + QL_LANES - 1) / QL_LANES, QL_LANES, ql_smem_bytes(b), sk>>>(u, b.meta, b.batch, i0, i1);
+            else ukf_ql_kernel<false><<<(i1 - i0 + QL_LANES - 1) / QL_LANES, QL_LANES, 0, sk>>>(u, b.meta, b.batch, i0, i1);
+            if (ukf_wld(b) == 25) ukf_back2_kernel<25><<<i1 - i0, 32, wsm, sk>>>(b, fc, in, u, i0);
+            else ukf_back2_kernel<33><<<i1 - i0, 32, wsm, sk>>>(b, fc, in, u, i0);
+        }
+        for (int k = 1; k < nsub; ++k) {
+            if ((e = cudaEventRecord(xs.join[k - 1], xs.aux[k - 1])) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(st, xs.join[k - 1], 0)) != cudaSuccess) return e;
+        }
         // rescue pass (generation-1 kernels, in-CTA QL): instances whose rotation log overflowed; everyone else exits at once
-        ukf_front_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, fc, in, u, 1);
-        ukf_back_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, fc, in, u, 1);
-        if (launched) *launched = 5;
+        ukf_front_kernel<<<b.batch, UKF_THREADS, fsm, st>>>(b, fc, in, u, 1);
+        ukf_back_kernel<<<b.batch, UKF_THREADS, fsm, st>>>(b, fc, in, u, 1);
+        if (launched) *launched = 3 * nsub + 2;
     } else {
         ukf_front_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, fc, in, u, 0);
-        ukf_ql_kernel<<<qblocks, QL_LANES, ql_smem_bytes(b), st>>>(u, b.meta, b.batch);
+        ukf_ql_kernel<true><<<qblocks, QL_LANES, ql_smem_bytes(b), st>>>(u, b.meta, b.batch, 0, b.batch);
         ukf_back_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, fc, in, u, 0);
         if (launched) *launched = 3;
     }

@@ -19,6 +19,8 @@ def main():
     reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
     if len(sys.argv) > 5:
         fb.tune(7, int(sys.argv[5]))
+    if len(sys.argv) > 6:
+        fb.tune(10, int(sys.argv[6]))
     for rep in range(reps):
         fb.reset(0, 0, 0)
         sim.reset()

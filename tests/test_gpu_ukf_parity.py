@@ -192,3 +192,30 @@ def test_ukf_step_variants(shim, oracle, knobs):
     worst = max(_compare(fb, i, ofs[i]) for i in range(B))
     assert (fb.all_status() == 0).all() and ofs[0].M >= 5
     print("ukf variant", knobs, "worst normwise err", worst)
+
+
+def test_ukf_sliced_batch(shim, oracle):
+    """The batch cut into slices that run front -> QL -> back on separate streams (slam_tune key 10): instances on both
+    sides of a slice boundary against the oracle, and the whole batch against the unsliced run bit for bit."""
+    p, lm, fwd, ang = H.config2(seed=6, steps=70, filt="ukf_slam")
+    op = H.oracle_params(oracle, p)
+    B = 150
+    runs = []
+    for nsub in (1, 2):
+        fb = shim.FilterBatch(shim.UKF_SLAM, p.to_c(), B, 50, 8)
+        fb.tune(10, nsub)
+        fb.init(0, 0, 0)
+        sim = shim.Simulator(fb, lm, seed=21)
+        sim.run(fwd, ang)
+        fb.synchronize()
+        runs.append(fb)
+    for i in (0, 74, 75, 149):
+        stream, _ = H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=21, instance=i)
+        of = oracle.OracleFilter(oracle.UKF_SLAM, op, 50)
+        of.init(0, 0, 0)
+        for t in range(len(fwd)):
+            of.update(fwd[t], ang[t], stream[t], oracle.STRUCTURED)
+        _compare(runs[1], i, of)
+    for i in range(0, B, 7):
+        assert np.array_equal(runs[0].state(i), runs[1].state(i)) and np.array_equal(runs[0].cov(i), runs[1].cov(i))
+    assert (runs[1].all_status() == 0).all()
