@@ -26,7 +26,9 @@ extern "C" {
 
 /* FilterChoice, localization_pkg/include/localization_pkg/filter.h:44-51 (same numeric values) */
 #define SLAM_EKF_SLAM 1
+#define SLAM_UKF_LOC  2   /* UKF localisation on the true map (ukf.cpp:146-154,262,272,296-302); state stays (x,y,cos,sin) */
 #define SLAM_UKF_SLAM 3
+#define SLAM_NAIVE    5   /* NaiveFilter, filter.h:325-370: command propagation only */
 
 /* per-instance status bits (replace the reference's uncaught std::runtime_error / eigen_assert, filter.h:5) */
 #define SLAM_STATUS_NAN               1  /* state or covariance became non-finite                               */
@@ -34,6 +36,8 @@ extern "C" {
                                          /* reference indexes x_t out of range there (ekf.cpp:115) and dies      */
 #define SLAM_STATUS_CAPACITY          4  /* an insertion was dropped: max_landmarks reached                      */
 #define SLAM_STATUS_MEAS_OVERFLOW     8  /* a step delivered more than max_meas measurements (extra ones dropped)*/
+#define SLAM_STATUS_BAD_ID           16  /* UKF_LOC: a detection's id is outside the true map (the reference reads */
+                                         /* map[] out of range there, ukf.cpp:152); the detection is skipped      */
 
 /* What Filter::readCommonParams reads from params.yaml (filter.h:105-121) plus the simulator's
  * constraints (base_pkg/config/params.yaml:27-32).  yaml values go in unchanged; with
@@ -55,10 +59,14 @@ typedef struct slam_sim*    slam_sim_t;
 
 /* ---- construction: replaces `filter = std::make_unique<EKF|UKF>(); filter->readParams(config)`
  *      (localization_pkg/src/localization_node.cpp:33-47, ekf.cpp:4-27, ukf.cpp:3-29).
- *      kind: SLAM_EKF_SLAM | SLAM_UKF_SLAM.  max_landmarks bounds M; max_meas bounds detections/step. */
+ *      kind: SLAM_EKF_SLAM | SLAM_UKF_SLAM | SLAM_UKF_LOC | SLAM_NAIVE.  max_landmarks bounds M (UKF_LOC: the
+ *      size of the true map); max_meas bounds detections/step. */
 int  slam_create(int kind, const slam_params* params, int batch, int max_landmarks, int max_meas,
                  int device, slam_handle_t* out);
 int  slam_destroy(slam_handle_t h);
+/* UKF_LOC only: the true map, as the /truth/landmarks message the reference stores in Filter::map (filter.h:68,
+ * localization_node.cpp:66-75): float32 [id, x, y] * n_landmarks with id == index.  HOST pointer; copied. */
+int  slam_set_map(slam_handle_t h, const float* map_id_x_y, int n_landmarks);
 const char* slam_last_error(slam_handle_t h);          /* h may be NULL: error of the last failed create */
 void* slam_stream(slam_handle_t h);                    /* the handle's cudaStream_t */
 int  slam_synchronize(slam_handle_t h);

@@ -31,6 +31,8 @@ struct slam_filter {
     bool large = false;
     LargeState lg{};
     UkfScratch uk{};                  // HBM scratch between the three launches of a UKF step
+    float* d_map = nullptr;           // UKF_LOC: device copy of the true map
+    int map_cap = 0;
     UkfStreams uks{};                 // slices of the batch run front -> QL -> back on their own streams
     int* h_nmeas_pin = nullptr;       // pinned scratch for the host-side measurement count
     // per-launch timing of the filter-step kernel
@@ -93,8 +95,10 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
     slam_filter* h = nullptr;
     if (!out) return fail(h, "slam_create: out is NULL");
     *out = nullptr;
-    if (kind != SLAM_EKF_SLAM && kind != SLAM_UKF_SLAM)
-        return fail(h, "Invalid filter choice (expected SLAM_EKF_SLAM or SLAM_UKF_SLAM).");   // localization_node.cpp:44
+    if (kind != SLAM_EKF_SLAM && kind != SLAM_UKF_SLAM && kind != SLAM_UKF_LOC && kind != SLAM_NAIVE)
+        return fail(h, "Invalid filter choice (expected SLAM_EKF_SLAM, SLAM_UKF_SLAM, SLAM_UKF_LOC or SLAM_NAIVE).");   // localization_node.cpp:44
+    const int map_size = max_landmarks;
+    if (kind == SLAM_UKF_LOC || kind == SLAM_NAIVE) max_landmarks = 1;      // the state never holds landmarks
     if (!params) return fail(h, "slam_create: params is NULL");
     if (batch < 1 || max_landmarks < 1 || max_meas < 1) return fail(h, "slam_create: batch, max_landmarks and max_meas must be >= 1");
     int ndev = 0;
@@ -115,6 +119,8 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
     else { fc.W00 = params->W_00; fc.W11 = params->W_11; }
     fc.v_d = params->v_d; fc.v_th = params->v_th; fc.w_r = params->w_r; fc.w_b = params->w_b;
     fc.min_sep = params->min_landmark_separation; fc.id_known = params->landmark_id_is_known;
+    fc.loc = (kind == SLAM_UKF_LOC); fc.n_map = 0; fc.map = nullptr;
+    h->map_cap = map_size;
     SimConst& sc = h->sc;
     sc.V_00 = params->V_00; sc.V_11 = params->V_11; sc.W_00 = params->W_00; sc.W_11 = params->W_11;
     sc.d_max = params->d_max; sc.th_max = params->th_max; sc.range_max = params->range_max;
@@ -122,7 +128,7 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
 
     BatchState& b = h->b;
     b.batch = batch; b.max_lm = max_landmarks; b.max_meas = max_meas;
-    b.base = (kind == SLAM_EKF_SLAM) ? 3 : 4;
+    b.base = (kind == SLAM_EKF_SLAM || kind == SLAM_NAIVE) ? 3 : 4;
     b.n_max = b.base + 2 * max_landmarks;
     b.lds = lds_of(b.n_max);
     b.x_stride = ldg_of(b.n_max);
@@ -131,7 +137,8 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
     b.fixed_ld = ldg_of(b.n_max);      // row-major layouts (UKF, large map): rows of P keep a fixed stride in HBM
     b.ps2g = 0;
 
-    const size_t smem = (kind == SLAM_EKF_SLAM) ? ekf_step_smem_bytes(b) : ukf_step_smem_bytes(b);
+    const size_t smem = (kind == SLAM_EKF_SLAM || kind == SLAM_NAIVE) ? ekf_step_smem_bytes(b) : ukf_step_smem_bytes(b);
+    if (kind == SLAM_UKF_LOC && !ukf_gen2_supported(b)) { delete h; h = nullptr; return fail(h, "slam_create: UKF_LOC needs max_meas <= 14"); }
     if (smem > (size_t)prop.sharedMemPerBlockOptin) {
         if (kind == SLAM_EKF_SLAM && batch == 1 && max_meas <= 256) {
             h->large = true;                       // P stays in HBM: large-map path
@@ -173,7 +180,7 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
     CK(cudaMallocHost(&h->h_hint, sizeof(int) * slam_filter::HINT_RING));
     for (int i = 0; i < slam_filter::HINT_RING; ++i) { h->h_hint[i] = 0; CK(cudaEventCreateWithFlags(&h->hint_ev[i], cudaEventDisableTiming)); }
     CK(cudaMalloc(&b.stats, sizeof(double) * (size_t)batch * SLAM_NUM_STATS));
-    if (kind == SLAM_UKF_SLAM) {
+    if (kind == SLAM_UKF_SLAM || kind == SLAM_UKF_LOC) {
         b.sigma_stride = (long long)b.n_max * (2 * b.n_max + 1);
         b.sigma = nullptr;   // allocated lazily by slam_get_sigma_points
         UkfScratch& u = h->uk;
@@ -186,6 +193,7 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
             CK(cudaEventCreateWithFlags(&h->uks.join[k], cudaEventDisableTiming));
         }
         u.rot_cap = 2LL * b.n_max * b.n_max;        // ~0.85 n^2 rotations are typical
+        if (u.rot_cap < 256) u.rot_cap = 256;
         u.swp_cap = 6 * b.n_max;                    // ~1.7 n sweeps are typical
         CK(cudaMalloc(&u.Zg, sizeof(double) * (size_t)batch * b.n_max * b.n_max));
         CK(cudaMalloc(&u.Yg, sizeof(double) * (size_t)batch * b.n_max * b.n_max));
@@ -215,9 +223,22 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
         CK(cudaMallocHost(&h->h_nmeas_pin, sizeof(int)));
     } else if (kind == SLAM_EKF_SLAM) {
         CK(ekf_step_configure(b));
-    } else CK(ukf_step_configure(b));
+    } else if (kind != SLAM_NAIVE) CK(ukf_step_configure(b));
     *out = h;
     return slam_init(h, 0.f, 0.f, 0.f);
+}
+
+int slam_set_map(slam_handle_t h, const float* map_id_x_y, int n_landmarks) {
+    if (!h) return 1;
+    if (h->kind != SLAM_UKF_LOC) return fail(h, "slam_set_map: only the localisation-only UKF keeps the true map (filter.h:68)");
+    if (!map_id_x_y || n_landmarks < 0) return fail(h, "slam_set_map: bad arguments");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_map); h->d_map = nullptr;
+    CK(cudaMalloc(&h->d_map, sizeof(float) * 3 * (size_t)(n_landmarks > 0 ? n_landmarks : 1)));
+    CK(cudaMemcpy(h->d_map, map_id_x_y, sizeof(float) * 3 * (size_t)n_landmarks, cudaMemcpyHostToDevice));
+    h->fc.map = h->d_map; h->fc.n_map = n_landmarks;
+    return 0;
 }
 
 int slam_destroy(slam_handle_t h) {
@@ -227,6 +248,7 @@ int slam_destroy(slam_handle_t h) {
     BatchState& b = h->b;
     cudaFree(b.P); cudaFree(b.x); cudaFree(b.ids); cudaFree(b.meta);
     cudaFree(b.assoc); cudaFree(b.stats); cudaFree(b.sigma);
+    cudaFree(h->d_map);
     cudaFree(h->uk.Zg); cudaFree(h->uk.Yg); cudaFree(h->uk.dg); cudaFree(h->uk.eg); cudaFree(h->uk.rot); cudaFree(h->uk.swp); cudaFree(h->uk.nswp);
     cudaFree(b.retry_list); cudaFree(b.retry_count); cudaFree(b.max_M); cudaFree(h->d_work); cudaFree(h->d_progress);
     if (h->h_run_hint) cudaFreeHost(h->h_run_hint);
@@ -275,7 +297,8 @@ int slam_tune(slam_handle_t h, int key, int value) {
     else if (key == 6) h->sweep_headroom = value < 0 ? 0 : value;
     else if (key == 7) { if (value != 1 && value != 2) return fail(h, "slam_tune: UKF generation must be 1 or 2"); h->uk.gen = value; }
     else if (key == 8) {     // shrink the rotation log (test knob: forces the rescue pass); never beyond the allocation
-        const long long full = 2LL * h->b.n_max * h->b.n_max;
+        long long full = 2LL * h->b.n_max * h->b.n_max;
+        if (full < 256) full = 256;
         h->uk.rot_cap = (value <= 0 || value > full) ? full : value;
     } else if (key == 9) h->uk.clip_lanes = value < 0 ? 0 : value;
     else if (key == 10) { if (value < 1 || value > UKF_MAX_SUB) return fail(h, "slam_tune: UKF slices must be 1..8"); h->uks.nsub = value; }
@@ -351,6 +374,7 @@ static int do_step(slam_filter* h, const float* d_fwd, const float* d_ang, int c
     if (h->kind == SLAM_EKF_SLAM) {
         CK(launch_ekf_step(h->b, h->fc, in, phases, cap, h->force_threads, h->stream));
     }
+    else if (h->kind == SLAM_NAIVE) { CK(launch_naive_step(h->b, in, h->stream)); h->launches += 1; }
     else { int nl = 0; CK(launch_ukf_step(h->b, h->fc, in, h->uk, h->stream, h->uks, &nl)); h->launches += nl; }
     if (h->profiling) { CK(cudaEventRecord(h->ev[h->ev_used + 1], h->stream)); h->ev_used += 2; }
     {
@@ -448,7 +472,7 @@ int slam_get_state(slam_handle_t h, int inst, double* x, int* n) {
 
 int slam_get_state_vector(slam_handle_t h, int inst, double* xv, int* n) {
     if (check_inst(h, inst)) return 1;
-    if (h->kind == SLAM_EKF_SLAM) return slam_get_state(h, inst, xv, n);   // ekf.cpp:182-185
+    if (h->kind == SLAM_EKF_SLAM || h->kind == SLAM_NAIVE) return slam_get_state(h, inst, xv, n);   // ekf.cpp:182-185, filter.h:349-352
     std::vector<double> raw(h->b.x_stride);
     int nr = 0;
     if (slam_get_state(h, inst, raw.data(), &nr)) return 1;
@@ -509,7 +533,7 @@ int slam_get_assoc(slam_handle_t h, int inst, int* slot, int* k) {
 
 int slam_get_sigma_points(slam_handle_t h, int inst, double* X, int* n) {
     if (check_inst(h, inst)) return 1;
-    if (h->kind != SLAM_UKF_SLAM) return fail(h, "slam_get_sigma_points: UKF only");
+    if (h->kind != SLAM_UKF_SLAM && h->kind != SLAM_UKF_LOC) return fail(h, "slam_get_sigma_points: UKF only");
     return fail(h, "slam_get_sigma_points: sigma points are not materialised by the batched UKF kernel yet");
 }
 

@@ -53,6 +53,9 @@ struct FilterConst {
     float v_d, v_th, w_r, w_b;
     float min_sep;
     int id_known;
+    int loc;             // UKF localisation-only mode (FilterChoice::UKF_LOC): landmarks come from the true map
+    int n_map;           // landmarks in `map`
+    const float* map;    // device copy of /truth/landmarks, float32 [id, x, y]*  (filter.h:68)
 };
 
 struct SimConst {
@@ -205,6 +208,8 @@ struct UkfStreams {
 cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, const UkfScratch& u, cudaStream_t st,
                             const UkfStreams& xs, int* launched);
 size_t ukf_step_smem_bytes(const BatchState& b);
+bool ukf_gen2_supported(const BatchState& b);
+cudaError_t launch_naive_step(const BatchState& b, const StepInputs& in, cudaStream_t st);
 cudaError_t ukf_step_configure(const BatchState& b);
 
 // single large-map EKF instance (csrc/ekf_large.cu): P stays in HBM with a fixed leading dimension

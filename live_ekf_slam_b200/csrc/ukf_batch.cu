@@ -553,6 +553,7 @@ ukf_front_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
     const int4 meta_in = b.meta[inst];
     if (meta_in.y & SLAM_STATUS_SAME_STEP_REMATCH) return;
     if (rescue && u.nswp[inst] != -1) return;      // rescue pass: only instances whose rotation log overflowed
+    if (fc.loc) return;                            // (n = 4 never overflows the log; generation 1 has no map branch)
     const int M = meta_in.x;
     const int n = 4 + 2 * M;                       // ukf.cpp:167 (state size of this step's sigma points)
     double* gP = b.P + (size_t)inst * b.p_stride;
@@ -608,6 +609,7 @@ ukf_back_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, const
     int status = meta_in.y;
     if (status & SLAM_STATUS_SAME_STEP_REMATCH) return;
     if (rescue && u.nswp[inst] != -1) return;      // rescue pass: only instances whose rotation log overflowed
+    if (fc.loc) return;
     int M = meta_in.x;
     const int M_start = M;
     const int n = 4 + 2 * M;                       // ukf.cpp:167 (state size of this step's sigma points)
@@ -1286,8 +1288,12 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
     for (int l = 0; l < nm; ++l) {
         const int id = (int)s.meas[3 * l];                                  // :258
         int cand = INT_MAX;
-        for (int j = lane; j < M_start; j += 32) if (s.ids[j] == id) { cand = j; break; }   // :264-269
-        cand = __reduce_min_sync(FULL, cand);
+        if (fc.loc) {                                                        // :262,272,300-302: every detection updates, by map id
+            if (id >= 0 && id < fc.n_map) cand = id; else status |= SLAM_STATUS_BAD_ID;   // the reference reads map[] out of range
+        } else {
+            for (int j = lane; j < M_start; j += 32) if (s.ids[j] == id) { cand = j; break; }   // :264-269
+            cand = __reduce_min_sync(FULL, cand);
+        }
         if (lane == 0) {
             s.assoc[l] = (cand == INT_MAX) ? -1 : cand;
             if (cand != INT_MAX) s.uq[nu] = l;
@@ -1322,7 +1328,7 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
     {
         int row = -1;
         if (lane < 4) row = lane;
-        else if (lane < nvec) { const int q = (lane - 4) >> 1; row = s.assoc[s.uq[q]] * 2 + 4 + ((lane - 4) & 1); }   // :298
+        else if (lane < nvec && !fc.loc) { const int q = (lane - 4) >> 1; row = s.assoc[s.uq[q]] * 2 + 4 + ((lane - 4) & 1); }   // :298
         if (lane < wcols) for (int i = 0; i < n; ++i) W_[i * wld + lane] = (i == row) ? 1.0 : 0.0;
         const bool act = lane < nvec;
         __syncwarp();
@@ -1405,14 +1411,18 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
     //      hv = dz_i - dz_{i+n} in its two lanes of W (the S rows it read from them are dead by then)
     for (int q = 0; q < nu; ++q) {
         const int l = s.uq[q];
-        const int li = s.assoc[l] * 2 + 4;                                  // :298
+        const int li = fc.loc ? 0 : s.assoc[l] * 2 + 4;                     // :298
         const int c0 = 4 + 2 * q;
         double* z0 = s.z;
         double* z1 = s.z + nsm;
         for (int i = lane; i < ns; i += 32) {                               // sensingModel per sigma point (:305-308)
-            double lx = s.x[li], ly = s.x[li + 1];
-            if (i >= 1 && i <= n) { lx += W_[(i - 1) * wld + c0]; ly += W_[(i - 1) * wld + c0 + 1]; }
-            else if (i > n) { lx -= W_[(i - 1 - n) * wld + c0]; ly -= W_[(i - 1 - n) * wld + c0 + 1]; }
+            double lx, ly;
+            if (fc.loc) { lx = (double)fc.map[3 * s.assoc[l] + 1]; ly = (double)fc.map[3 * s.assoc[l] + 2]; }   // :152-153 (true map, float)
+            else {
+                lx = s.x[li]; ly = s.x[li + 1];
+                if (i >= 1 && i <= n) { lx += W_[(i - 1) * wld + c0]; ly += W_[(i - 1) * wld + c0 + 1]; }
+                else if (i > n) { lx -= W_[(i - 1 - n) * wld + c0]; ly -= W_[(i - 1 - n) * wld + c0 + 1]; }
+            }
             const double dx = lx - s.Xp[0 * nsm + i], dy = ly - s.Xp[1 * nsm + i];
             z0[i] = sqrt(dx * dx + dy * dy) + (double)fc.w_r;               // :144
             z1[i] = remainder(atan2(dy, dx) - (double)yaw_prior + (double)fc.w_b, TWO_PI_REF);   // :145,156
@@ -1457,7 +1467,7 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
             ud[17] = (double)s.meas[3 * l + 1] - zest0;                                   // innovation (:342-344)
             ud[18] = remainder((double)s.meas[3 * l + 2] - 0.0, TWO_PI_REF);
         }
-        for (int i = lane; i < n; i += 32) {
+        if (!fc.loc) for (int i = lane; i < n; i += 32) {                   // (localisation: the state has no landmark rows)
             W_[i * wld + c0] = z0[1 + i] - z0[1 + n + i];
             W_[i * wld + c0 + 1] = z1[1 + i] - z1[1 + n + i];
         }
@@ -1545,7 +1555,7 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
     __syncwarp();
 
     // -------- landmarkInsertion for the unmatched measurements, in message order (:278-287,351-371)
-    for (int l = 0; l < nm; ++l) {
+    for (int l = 0; l < nm && !fc.loc; ++l) {
         if (s.assoc[l] != -1) continue;
         if (M >= b.max_lm) { status |= SLAM_STATUS_CAPACITY; continue; }
         const int nn = 4 + 2 * M;
@@ -1605,6 +1615,25 @@ cudaError_t ukf_step_configure(const BatchState& b) {
     if ((e = cudaFuncSetAttribute(ukf_back2_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back2_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b))) != cudaSuccess) return e;
     return cudaFuncSetAttribute(ukf_ql_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ql_smem_bytes(b));
+}
+
+// NaiveFilter::update, filter.h:342-348: measurements ignored, pose propagated by the command (one thread per instance)
+__global__ void naive_step_kernel(BatchState b, StepInputs in) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.batch) return;
+    double* x = b.x + (size_t)i * b.x_stride;
+    const float fwd = in.fwd[in.cmd_stride ? i : 0], ang = in.ang[in.cmd_stride ? i : 0];
+    const double th = x[2];
+    x[0] = x[0] + (double)fwd * cos(th);
+    x[1] = x[1] + (double)fwd * sin(th);
+    x[2] = remainder(th + (double)ang, TWO_PI_REF);
+    int4 m = b.meta[i];
+    m.z += 1; m.w = 0;
+    b.meta[i] = m;
+}
+cudaError_t launch_naive_step(const BatchState& b, const StepInputs& in, cudaStream_t st) {
+    naive_step_kernel<<<(b.batch + 127) / 128, 128, 0, st>>>(b, in);
+    return cudaGetLastError();
 }
 
 bool ukf_gen2_supported(const BatchState& b) { return b.max_meas <= UKF2_MAX_UPD && b.n_max <= 256 && ukf_warp_smem_bytes(b) <= 227 * 1024; }

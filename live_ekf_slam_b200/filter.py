@@ -46,8 +46,18 @@ class Filter:
     def readParams(self, config):
         """config: the parsed params.yaml dict (YAML::Node in the reference) or a Params."""
         self._params = config if isinstance(config, Params) else from_yaml_dict(config)
-        self._batch = shim.FilterBatch(self._kind, self._params.to_c(), 1, self._max_landmarks, self._max_meas,
+        kind = self._kind
+        if self.type == FilterChoice.UKF_LOC:      # localization_node.cpp:36-38 overrides UKF's type before readParams
+            kind = shim.UKF_LOC
+        self._batch = shim.FilterBatch(kind, self._params.to_c(), 1, self._max_landmarks, self._max_meas,
                                        self._device)
+
+    def setMap(self, landmarks):
+        """The /truth/landmarks message (flat float32 [id, x, y]*) the node copies into Filter::map
+        (localization_node.cpp: landmark callback; filter.h:68).  Only the localisation-only UKF reads it."""
+        self.map = [float(v) for v in np.asarray(landmarks, dtype=np.float32).reshape(-1)]
+        if self.type == FilterChoice.UKF_LOC:
+            self._need().set_map(np.asarray(self.map, dtype=np.float32))
 
     def _need(self) -> shim.FilterBatch:
         if self._batch is None:
@@ -116,7 +126,8 @@ class Filter:
         return self._need().cov(0)
 
     def setupStatePublisher(self, node=None):   # filter.h:65 (ROS plumbing; the topic name is kept for the shim)
-        self.state_topic = {FilterChoice.EKF_SLAM: "/state/ekf", FilterChoice.UKF_SLAM: "/state/ukf"}.get(self.type)
+        self.state_topic = {FilterChoice.EKF_SLAM: "/state/ekf", FilterChoice.UKF_SLAM: "/state/ukf",
+                            FilterChoice.UKF_LOC: "/state/ukf", FilterChoice.NAIVE_COMMAND_PROPAGATION: "/state/naive"}.get(self.type)
 
     def publishState(self) -> dict:
         raise NotImplementedError
@@ -140,7 +151,7 @@ class EKF(Filter):
 
 
 class UKF(Filter):
-    """filter.h:177-223, ukf.cpp (UKF_SLAM)."""
+    """filter.h:177-223, ukf.cpp (UKF_SLAM; UKF_LOC when `type` is overridden as localization_node.cpp:36-38 does)."""
     type = FilterChoice.UKF_SLAM
     _kind = shim.UKF_SLAM
 
@@ -157,6 +168,17 @@ class UKF(Filter):
                     M=len(ids), landmarks=lm, P=P.astype(np.float32).reshape(-1))
 
 
+class NaiveFilter(Filter):
+    """filter.h:325-370: ignores the measurements and propagates the pose by the command."""
+    type = FilterChoice.NAIVE_COMMAND_PROPAGATION
+    _kind = shim.NAIVE
+
+    def publishState(self) -> dict:
+        """NaiveState.msg fields as filter.h:358-368 fills them."""
+        x = self.x_t
+        return dict(timestep=self.timestep, x_v=np.float32(x[0]), y_v=np.float32(x[1]), yaw_v=np.float32(x[2]))
+
+
 def make_filter(config, **kw) -> Filter:
     """localization_node.cpp:28-47: choose the derived class from `filter:` and read its params."""
     p = config if isinstance(config, Params) else from_yaml_dict(config)
@@ -164,9 +186,12 @@ def make_filter(config, **kw) -> Filter:
         f: Filter = EKF(**kw)
     elif p.filter == "ukf_slam":
         f = UKF(**kw)
-    elif p.filter in ("ukf_loc", "pose_graph"):
-        raise RuntimeError(f"filter '{p.filter}' is outside the B200 hot path (SURVEY.md section 8f); "
-                           "use ekf_slam or ukf_slam")
+    elif p.filter == "ukf_loc":
+        f = UKF(**kw)
+        f.type = FilterChoice.UKF_LOC              # localization_node.cpp:36-38: override the default of UKF_SLAM
+    elif p.filter == "pose_graph":
+        raise RuntimeError("filter 'pose_graph' is outside the B200 hot path (SURVEY.md section 8f); "
+                           "use ekf_slam, ukf_slam or ukf_loc")
     else:
         raise RuntimeError("Invalid filter choice in params.yaml.")   # localization_node.cpp:44
     f.readParams(p)

@@ -112,18 +112,35 @@ protected:
     int kind() const override { return SLAM_EKF_SLAM; }
 };
 
-class UKF : public Filter {   // filter.h:177-223
+class UKF : public Filter {   // filter.h:177-223; `type` may be overridden to UKF_LOC before readParams (localization_node.cpp:36-38)
 public:
     UKF() { type = FilterChoice::UKF_SLAM; }
+    // the /truth/landmarks message, float32 [id, x, y]*, kept in Filter::map (filter.h:68); read by the localisation-only mode
+    void setMap(const std::vector<float>& landmarks) {
+        map = landmarks;
+        if (type == FilterChoice::UKF_LOC) { need(); check(slam_set_map(h_, map.data(), (int)(map.size() / 3))); }
+    }
 protected:
-    int kind() const override { return SLAM_UKF_SLAM; }
+    int kind() const override { return type == FilterChoice::UKF_LOC ? SLAM_UKF_LOC : SLAM_UKF_SLAM; }
+};
+
+class NaiveFilter : public Filter {   // filter.h:325-370
+public:
+    NaiveFilter() { type = FilterChoice::NAIVE_COMMAND_PROPAGATION; }
+protected:
+    int kind() const override { return SLAM_NAIVE; }
 };
 
 // localization_node.cpp:33-45
 inline std::unique_ptr<Filter> make_filter(const std::string& filter_choice_str) {
     if (filter_choice_str == "ekf_slam") return std::make_unique<EKF>();
     if (filter_choice_str == "ukf_slam") return std::make_unique<UKF>();
-    if (filter_choice_str == "ukf_loc" || filter_choice_str == "pose_graph")
+    if (filter_choice_str == "ukf_loc") {
+        auto f = std::make_unique<UKF>();
+        f->type = FilterChoice::UKF_LOC;                   // localization_node.cpp:38: override the default of UKF_SLAM
+        return f;
+    }
+    if (filter_choice_str == "pose_graph")
         throw std::runtime_error("filter '" + filter_choice_str + "' is outside the B200 hot path (SURVEY.md 8f)");
     throw std::runtime_error("Invalid filter choice in params.yaml.");
 }

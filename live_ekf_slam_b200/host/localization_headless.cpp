@@ -29,7 +29,7 @@ int main() {
         }
         const auto P = filter->covariance();
         const auto x = filter->getStateVector();
-        const size_t n = x.size() + (choice == "ukf_slam" ? 1 : 0);
+        const size_t n = x.size() + ((choice == "ukf_slam" || choice == "ukf_loc") ? 1 : 0);
         double tr = 0;
         for (size_t i = 0; i < n; ++i) tr += P[i * n + i];
         std::printf("trace %.17g ids", tr);

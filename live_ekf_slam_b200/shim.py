@@ -16,13 +16,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libslam_filter.so")
 
 EKF_SLAM = 1   # FilterChoice::EKF_SLAM, filter.h:46
+UKF_LOC = 2    # FilterChoice::UKF_LOC, filter.h:47 (localisation on the true map)
 UKF_SLAM = 3   # FilterChoice::UKF_SLAM, filter.h:48
-STATUS_NAN, STATUS_SAME_STEP_REMATCH, STATUS_CAPACITY, STATUS_MEAS_OVERFLOW = 1, 2, 4, 8
+NAIVE = 5      # FilterChoice::NAIVE_COMMAND_PROPAGATION, filter.h:50 (NaiveFilter, filter.h:325-370)
+STATUS_NAN, STATUS_SAME_STEP_REMATCH, STATUS_CAPACITY, STATUS_MEAS_OVERFLOW, STATUS_BAD_ID = 1, 2, 4, 8, 16
 NUM_STATS = 12
 
 #: every symbol include/slam_filter.h declares (tests check the built library exports all of them)
 ABI_SYMBOLS = (
-    "slam_create", "slam_destroy", "slam_last_error", "slam_stream", "slam_synchronize", "slam_batch", "slam_kind",
+    "slam_create", "slam_destroy", "slam_set_map", "slam_last_error", "slam_stream", "slam_synchronize", "slam_batch", "slam_kind",
     "slam_init", "slam_step", "slam_step_device", "slam_predict", "slam_update", "slam_predict_device",
     "slam_update_device", "slam_get_timestep", "slam_get_num_landmarks", "slam_get_status", "slam_get_state",
     "slam_get_state_vector", "slam_get_cov", "slam_get_landmark_ids", "slam_get_assoc", "slam_get_sigma_points",
@@ -50,6 +52,7 @@ def load(path: str | None = None):
     vp, ip, fp, dp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_double)
     L.slam_create.argtypes = [C.c_int, C.POINTER(SlamParams), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.slam_destroy.argtypes = [vp]
+    L.slam_set_map.argtypes = [vp, fp, C.c_int]
     L.slam_last_error.argtypes = [vp]
     L.slam_last_error.restype = C.c_char_p
     L.slam_stream.argtypes = [vp]
@@ -145,7 +148,7 @@ class FilterBatch:
         self._L = load()
         self._h = C.c_void_p()
         self.kind, self.batch, self.max_landmarks, self.max_meas, self.device = kind, batch, max_landmarks, max_meas, device
-        self.base = 3 if kind == EKF_SLAM else 4
+        self.base = 3 if kind in (EKF_SLAM, NAIVE) else 4
         self._params = params
         rc = self._L.slam_create(kind, C.byref(params), batch, max_landmarks, max_meas, device, C.byref(self._h))
         if rc != 0:
@@ -179,6 +182,18 @@ class FilterBatch:
     @property
     def kernel_launches(self) -> int:
         return int(self._L.slam_kernel_launches(self._h))
+
+    def set_map(self, lm_xy):
+        """UKF_LOC: the true map the reference receives on /truth/landmarks and keeps in Filter::map (filter.h:68):
+        float32 [id, x, y]* with id == index.  Accepts [N,2] coordinates or the flat wire format."""
+        a = np.asarray(lm_xy)
+        if a.ndim == 2 and a.shape[1] == 2:
+            m = np.zeros((len(a), 3), dtype=np.float32)
+            m[:, 0] = np.arange(len(a)); m[:, 1:] = a.astype(np.float32)
+        else:
+            m = np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3)
+        m = np.ascontiguousarray(m.reshape(-1))
+        self._ck(self._L.slam_set_map(self._h, m.ctypes.data_as(C.POINTER(C.c_float)), m.size // 3))
 
     # -- Filter interface (filter.h:59-61)
     def init(self, x_0: float, y_0: float, yaw_0: float):

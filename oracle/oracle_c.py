@@ -16,10 +16,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libslam_oracle.so")
 
 EKF_SLAM = 1
+UKF_LOC = 2
 UKF_SLAM = 3
+NAIVE = 5
 DENSE = 0
 STRUCTURED = 1
 ERR_NAN, ERR_SAME_STEP_REMATCH, ERR_CAPACITY = 1, 2, 4
+ERR_BAD_ID = 16
 
 
 class OracleParams(C.Structure):
@@ -69,6 +72,7 @@ def lib():
     L.oracle_create.argtypes = [C.c_int, pp, C.c_int]
     L.oracle_destroy.argtypes = [C.c_void_p]
     L.oracle_init.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
+    L.oracle_set_map.argtypes = [C.c_void_p, fp, C.c_int]
     L.oracle_update.argtypes = [C.c_void_p, C.c_float, C.c_float, fp, C.c_int, C.c_int]
     L.oracle_predict.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_int]
     L.oracle_measure.argtypes = [C.c_void_p, fp, C.c_int, C.c_int]
@@ -115,7 +119,7 @@ class OracleFilter:
         self.kind = kind
         self.params = params or make_params()
         self.max_landmarks = max_landmarks
-        self.base = 3 if kind == EKF_SLAM else 4
+        self.base = 3 if kind in (EKF_SLAM, NAIVE) else 4
         self._h = _handle if _handle is not None else lib().oracle_create(kind, C.byref(self.params), max_landmarks)
         if not self._h:
             raise RuntimeError("Invalid filter choice")
@@ -130,6 +134,13 @@ class OracleFilter:
 
     def init(self, x0: float, y0: float, yaw0: float):
         lib().oracle_init(self._h, x0, y0, yaw0)
+
+    def set_map(self, lm_xy):
+        """UKF_LOC: the true map (filter.h:68), sent as the /truth/landmarks wire format float32 [id, x, y]*."""
+        lm = np.asarray(lm_xy, dtype=np.float64).reshape(-1, 2)
+        m = np.zeros((len(lm), 3), dtype=np.float32)
+        m[:, 0] = np.arange(len(lm)); m[:, 1:] = lm.astype(np.float32)
+        lib().oracle_set_map(self._h, _fp(np.ascontiguousarray(m.reshape(-1))), len(lm))
 
     def update(self, fwd: float, ang: float, meas, mode: int = DENSE) -> int:
         m = np.ascontiguousarray(np.asarray(meas, dtype=np.float32).reshape(-1))

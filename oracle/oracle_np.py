@@ -143,6 +143,14 @@ class UKFNP(FilterNP):
         self.P_t = np.diag([1e-2 * 1e-2, 1e-2 * 1e-2, 0.005 * 0.005, 0.005 * 0.005])
         self.X = None
         self.X_pred = None
+        self.loc = False        # FilterChoice::UKF_LOC (localization_node.cpp:36-38): landmarks from the true map
+        self.map = None         # float32 [id, x, y]*, filter.h:68
+
+    def set_map(self, lm_xy):
+        lm = np.asarray(lm_xy, dtype=np.float64).reshape(-1, 2)
+        m = np.zeros((len(lm), 3), dtype=np.float32)
+        m[:, 0] = np.arange(len(lm)); m[:, 1:] = lm.astype(np.float32)
+        self.map = m.reshape(-1)
 
     @staticmethod
     def _yaw(x):
@@ -207,17 +215,23 @@ class UKFNP(FilterNP):
         for l in range(len(meas)):
             ident = int(meas[l, 0]); r = F(meas[l, 1]); b = F(meas[l, 2])
             lm_i = -1
-            for j in range(self.M):
-                if self.lm_IDs[j] == ident:
-                    lm_i = j
-                    break
-            self.assoc.append(lm_i)
-            if lm_i == -1:
-                new.append(l)
-                continue
-            li = lm_i * 2 + 4
-            dx = Xp[li, :] - Xp[0, :]
-            dy = Xp[li + 1, :] - Xp[1, :]
+            if self.loc:                                     # ukf.cpp:262,272,300-302
+                lm_i = ident
+                self.assoc.append(lm_i)
+                dx = float(self.map[lm_i * 3 + 1]) - Xp[0, :]    # :152-153
+                dy = float(self.map[lm_i * 3 + 2]) - Xp[1, :]
+            else:
+                for j in range(self.M):
+                    if self.lm_IDs[j] == ident:
+                        lm_i = j
+                        break
+                self.assoc.append(lm_i)
+                if lm_i == -1:
+                    new.append(l)
+                    continue
+                li = lm_i * 2 + 4
+                dx = Xp[li, :] - Xp[0, :]
+                dy = Xp[li + 1, :] - Xp[1, :]
             z0 = np.sqrt(dx * dx + dy * dy) + float(self.w_r)
             z1 = np.array([math.remainder(math.atan2(dy[c], dx[c]) - float(yaw_prior) + float(self.w_b), TWO_PI)
                            for c in range(2 * n + 1)])

@@ -49,6 +49,7 @@ struct oracle_filter {
     int X_rows;                  /* current row count of X (ukf.cpp:169) */
     double *vec1, *vec2;
     int *assoc; int n_assoc, assoc_cap;
+    float *map; int n_map;       /* UKF_LOC: the true map, [id, x, y]* float32 (filter.h:68, /truth/landmarks) */
 };
 
 /* ------------------------------------------------------------------ helpers */
@@ -227,10 +228,11 @@ void oracle_eigh(const double* A, int n, double* evals, double* evecs) {
 
 /* ------------------------------------------------------------------ create / init */
 oracle_filter* oracle_create(int kind, const oracle_params* p, int max_landmarks) {
-    if (kind != ORACLE_EKF_SLAM && kind != ORACLE_UKF_SLAM) return NULL;
+    if (kind != ORACLE_EKF_SLAM && kind != ORACLE_UKF_SLAM && kind != ORACLE_UKF_LOC && kind != ORACLE_NAIVE) return NULL;
+    if (kind == ORACLE_UKF_LOC || kind == ORACLE_NAIVE) max_landmarks = 1;   /* the state never holds landmarks */
     oracle_filter* f = (oracle_filter*)calloc(1, sizeof(*f));
     f->kind = kind;
-    f->base = (kind == ORACLE_EKF_SLAM) ? 3 : 4;
+    f->base = (kind == ORACLE_EKF_SLAM || kind == ORACLE_NAIVE) ? 3 : 4;
     f->p = *p;
     /* Filter::readCommonParams, filter.h:105-121 */
     f->V[0][0] = 1; f->V[1][1] = 1; f->V[0][1] = f->V[1][0] = 0;     /* :107 */
@@ -253,7 +255,7 @@ oracle_filter* oracle_create(int kind, const oracle_params* p, int max_landmarks
     f->P_t[0] = f->P_pred[0] = 0.01 * 0.01;
     f->P_t[ld + 1] = f->P_pred[ld + 1] = 0.01 * 0.01;
     f->P_t[2 * ld + 2] = f->P_pred[2 * ld + 2] = 0.005 * 0.005;
-    if (kind == ORACLE_UKF_SLAM) {
+    if (kind == ORACLE_UKF_SLAM || kind == ORACLE_UKF_LOC) {
         f->P_t[3 * ld + 3] = f->P_pred[3 * ld + 3] = 0.005 * 0.005;
         size_t ns = (size_t)f->ncap * (2 * f->ncap + 1);
         f->X = dalloc(ns); f->X_pred = dalloc(ns);
@@ -268,12 +270,20 @@ void oracle_destroy(oracle_filter* f) {
     if (!f) return;
     free(f->x_t); free(f->x_pred); free(f->P_t); free(f->P_pred);
     free(f->w1); free(f->w2); free(f->w3); free(f->w4); free(f->vec1); free(f->vec2);
-    free(f->lm_ids); free(f->assoc); free(f->X); free(f->X_pred); free(f->Wts); free(f->Qd);
+    free(f->lm_ids); free(f->assoc); free(f->X); free(f->X_pred); free(f->Wts); free(f->Qd); free(f->map);
     free(f);
 }
 
+/* the /truth/landmarks message the localisation-only UKF keeps as `map` (filter.h:68, localization_node.cpp:66-75) */
+void oracle_set_map(oracle_filter* f, const float* map_id_x_y, int n_landmarks) {
+    free(f->map);
+    f->map = (float*)malloc(sizeof(float) * 3 * (size_t)(n_landmarks > 0 ? n_landmarks : 1));
+    memcpy(f->map, map_id_x_y, sizeof(float) * 3 * (size_t)n_landmarks);
+    f->n_map = n_landmarks;
+}
+
 void oracle_init(oracle_filter* f, float x0, float y0, float yaw0) {
-    if (f->kind == ORACLE_EKF_SLAM) {
+    if (f->kind == ORACLE_EKF_SLAM || f->kind == ORACLE_NAIVE) {
         f->x_t[0] = x0; f->x_t[1] = y0; f->x_t[2] = yaw0;                /* ekf.cpp:31 */
     } else {
         f->x_t[0] = x0; f->x_t[1] = y0; f->x_t[2] = cos_f(yaw0); f->x_t[3] = sin_f(yaw0); /* ukf.cpp:33 */
@@ -553,10 +563,12 @@ static void ukf_motion_model(const oracle_filter* f, const double* x, int n, flo
     out[3] = (double)sin_f(new_yaw);
 }
 
-/* ukf.cpp:137-159 (UKF_SLAM branch) */
+/* ukf.cpp:137-159 (both branches: SLAM reads the landmark from the sigma point, localisation from the true map) */
 static void ukf_sensing_model(const oracle_filter* f, const double* x, int lm_i, double z[2]) {
     const float yaw = ukf_yaw(f->x_t);                 /* prior x_t, same for every sigma point (:139) */
-    const double dx = x[lm_i] - x[0], dy = x[lm_i + 1] - x[1];
+    double dx, dy;
+    if (f->kind == ORACLE_UKF_SLAM) { dx = x[lm_i] - x[0]; dy = x[lm_i + 1] - x[1]; }                         /* :144-145 */
+    else { dx = (double)f->map[lm_i * 3 + 1] - x[0]; dy = (double)f->map[lm_i * 3 + 2] - x[1]; }              /* :152-153 */
     z[0] = sqrt(dx * dx + dy * dy) + (double)f->p.w_r;
     z[1] = atan2(dy, dx) - (double)yaw + (double)f->p.w_b;
     z[1] = remainder(z[1], 2 * PI_REF);
@@ -616,7 +628,7 @@ static void ukf_prediction(oracle_filter* f, float u_d, float u_th, int mode) {
 /* ukf.cpp:293-349 */
 static void ukf_landmark_update(oracle_filter* f, int lm_slot, float r, float b) {
     const int n = 4 + 2 * f->M, ld = f->ncap, ns = 2 * n + 1;
-    const int lm_i = lm_slot * 2 + 4;                                  /* :298 */
+    const int lm_i = (f->kind == ORACLE_UKF_SLAM) ? lm_slot * 2 + 4 : lm_slot;   /* :296-302 (localisation: lm_i = id) */
     double* Z = f->w1; /* 2 x ns, column c at Z[2c] */
     for (int c = 0; c < ns; ++c) ukf_sensing_model(f, f->X_pred + (size_t)c * ld, lm_i, Z + 2 * c);   /* :305-308 */
     double z_est[2] = {0.0, 0.0};
@@ -699,6 +711,12 @@ static int ukf_update(oracle_filter* f, float u_d, float u_th, const float* lm_m
         const int id = (int)lm_meas[l * 3];
         const float r = lm_meas[l * 3 + 1], b = lm_meas[l * 3 + 2];
         int lm_i = -1;
+        if (f->kind == ORACLE_UKF_LOC) {                               /* :262,272: every detection is an update, by map id */
+            if (id < 0 || id >= f->n_map) { f->status |= ORACLE_ERR_BAD_ID; log_assoc(f, -1); continue; }   /* the reference reads map[] out of range */
+            log_assoc(f, id);
+            ukf_landmark_update(f, id, r, b);
+            continue;
+        }
         for (int j = 0; j < f->M; ++j) if (f->lm_ids[j] == id) { lm_i = j; break; }
         log_assoc(f, lm_i);
         if (lm_i == -1) new_idx[n_new++] = l; else ukf_landmark_update(f, lm_i, r, b);
@@ -718,6 +736,14 @@ static int ukf_update(oracle_filter* f, float u_d, float u_th, const float* lm_m
 int oracle_update(oracle_filter* f, float fwd, float ang, const float* meas, int n_meas, int mode) {
     if (f->status & ORACLE_ERR_SAME_STEP_REMATCH) return f->status;
     if (f->kind == ORACLE_EKF_SLAM) { ekf_predict(f, fwd, ang, mode); ekf_measure(f, meas, n_meas, mode); }
+    else if (f->kind == ORACLE_NAIVE) {
+        /* NaiveFilter::update, filter.h:342-348: measurements ignored, pose propagated by the command */
+        f->timestep += 1;
+        const double th = f->x_t[2];
+        f->x_t[0] = f->x_t[0] + (double)fwd * cos(th);
+        f->x_t[1] = f->x_t[1] + (double)fwd * sin(th);
+        f->x_t[2] = remainder(th + (double)ang, 2 * PI_REF);
+    }
     else ukf_update(f, fwd, ang, meas, n_meas, mode);
     if (has_nan(f)) f->status |= ORACLE_ERR_NAN;
     return f->status;
@@ -799,6 +825,12 @@ int oracle_run_instance(int kind, const oracle_params* p, const double* lm_xy, i
     oracle_filter* f = oracle_create(kind, p, max_landmarks);
     if (!f) return -1;
     oracle_init(f, 0.0f, 0.0f, 0.0f);                       /* params.yaml:19-22 */
+    if (kind == ORACLE_UKF_LOC) {                           /* /truth/landmarks: [id, x, y]* float32, ids ascending (sim_node.py:190-196) */
+        float* mp = (float*)malloc(sizeof(float) * 3 * (size_t)(n_lm > 0 ? n_lm : 1));
+        for (int j = 0; j < n_lm; ++j) { mp[3 * j] = (float)j; mp[3 * j + 1] = (float)lm_xy[2 * j]; mp[3 * j + 2] = (float)lm_xy[2 * j + 1]; }
+        oracle_set_map(f, mp, n_lm);
+        free(mp);
+    }
     double truth[3] = {0.0, 0.0, 0.0};                      /* sim_node.py:32 */
     const int cap = n_lm > 0 ? n_lm : 1;
     float* meas = (float*)malloc(sizeof(float) * 3 * (size_t)cap);
@@ -807,7 +839,7 @@ int oracle_run_instance(int kind, const oracle_params* p, const double* lm_xy, i
         oracle_update(f, cmd_fwd[t], cmd_ang[t], meas, k, mode);
         if (pose_trace) {
             pose_trace[3 * t] = f->x_t[0]; pose_trace[3 * t + 1] = f->x_t[1];
-            pose_trace[3 * t + 2] = (kind == ORACLE_EKF_SLAM) ? f->x_t[2] : remainder(atan2(f->x_t[3], f->x_t[2]), 2 * PI_REF);
+            pose_trace[3 * t + 2] = (f->base == 3) ? f->x_t[2] : remainder(atan2(f->x_t[3], f->x_t[2]), 2 * PI_REF);
         }
         if (truth_trace) { truth_trace[3 * t] = truth[0]; truth_trace[3 * t + 1] = truth[1]; truth_trace[3 * t + 2] = truth[2]; }
     }

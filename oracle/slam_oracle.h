@@ -16,7 +16,8 @@
  * Reference files restated (paths under ekf_ws/src/):
  *   localization_pkg/include/localization_pkg/filter.h:79-121   fields, readCommonParams
  *   localization_pkg/src/ekf.cpp:4-34,37-179,182-220            EKF
- *   localization_pkg/src/ukf.cpp:3-45,106-371                   UKF
+ *   localization_pkg/src/ukf.cpp:3-45,106-371                   UKF (SLAM and localisation-only branches)
+ *   localization_pkg/include/localization_pkg/filter.h:325-370  NaiveFilter
  *   base_pkg/src/sim_node.py:209-250                            measurement generator
  */
 #ifndef SLAM_ORACLE_H
@@ -42,8 +43,8 @@ typedef struct oracle_params {
     double d_max, th_max, range_max, fov_min, fov_max;
 } oracle_params;
 
-enum { ORACLE_EKF_SLAM = 1, ORACLE_UKF_SLAM = 3 };              /* FilterChoice filter.h:44-51 */
-enum { ORACLE_OK = 0, ORACLE_ERR_NAN = 1, ORACLE_ERR_SAME_STEP_REMATCH = 2, ORACLE_ERR_CAPACITY = 4 };
+enum { ORACLE_EKF_SLAM = 1, ORACLE_UKF_LOC = 2, ORACLE_UKF_SLAM = 3, ORACLE_NAIVE = 5 };   /* FilterChoice filter.h:44-51 */
+enum { ORACLE_OK = 0, ORACLE_ERR_NAN = 1, ORACLE_ERR_SAME_STEP_REMATCH = 2, ORACLE_ERR_CAPACITY = 4, ORACLE_ERR_BAD_ID = 16 };
 /* evaluation mode: 0 = dense-faithful (the reference's literal O(n^3) products; CPU baseline)
  *                  1 = structured (identical arithmetic with exact-zero terms skipped) */
 enum { ORACLE_DENSE = 0, ORACLE_STRUCTURED = 1 };
@@ -54,6 +55,8 @@ void  oracle_set_trig_mode(int mode);   /* 0 = pinned (float)cos((double)x) [D-1
 oracle_filter* oracle_create(int kind, const oracle_params* p, int max_landmarks);
 void  oracle_destroy(oracle_filter* f);
 void  oracle_init(oracle_filter* f, float x0, float y0, float yaw0);
+/* UKF_LOC: the true map as the /truth/landmarks wire format, float32 [id, x, y]* with id == index (filter.h:68) */
+void  oracle_set_map(oracle_filter* f, const float* map_id_x_y, int n_landmarks);
 /* one reference Filter::update(): predict + all landmark updates/insertions */
 int   oracle_update(oracle_filter* f, float fwd, float ang, const float* meas, int n_meas, int mode);
 /* split form (EKF only): predict alone, then update alone */

@@ -156,3 +156,62 @@ def test_trig_pinning_deviation_rate(oracle):
     oracle.set_trig_mode(0)
     dev = max(H.normwise(out[0][0], out[1][0]), H.normwise(out[0][1], out[1][1]))
     assert dev < 1e-4                                    # documented in DESIGN.md: float-ulp sized, far above 1e-9
+
+
+def test_ukf_loc_c_vs_numpy(oracle):
+    """Localisation-only UKF (FilterChoice::UKF_LOC, ukf.cpp:146-154,262,272,296-302): C oracle vs NumPy restatement."""
+    p, lm, fwd, ang = H.config2(seed=5, steps=200, filt="ukf_slam")
+    op = H.oracle_params(oracle, p)
+    fc = oracle.OracleFilter(oracle.UKF_LOC, op, 50)
+    fn = oracle_np.UKFNP(dict(oracle.DEFAULTS))
+    fn.loc = True
+    fc.init(0, 0, 0); fn.init(0, 0, 0)
+    fc.set_map(lm); fn.set_map(lm)
+    stream, _ = H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=6, instance=0)
+    worst, n_upd = 0.0, 0
+    for t in range(len(fwd)):
+        fc.update(fwd[t], ang[t], stream[t], oracle.DENSE)
+        fn.update(fwd[t], ang[t], stream[t])
+        assert list(fc.assoc_log()) == fn.assoc == [int(v) for v in stream[t][:, 0]], t    # slot = map id
+        n_upd += len(stream[t])
+        worst = max(worst, H.normwise(fc.state(), fn.x_t), H.normwise(fc.cov(), fn.P_t))
+    assert fc.n == 4 and fc.M == 0 and fn.M == 0 and n_upd > 100
+    assert worst <= 1e-11
+
+
+def test_ukf_loc_predict_only_equals_ukf_slam_bitwise(oracle):
+    """Without detections the two UKF modes run the same code (ukf.cpp:161-241): bitwise equal states."""
+    op = H.oracle_params(oracle, H.Params(filter="ukf_slam"))
+    a = oracle.OracleFilter(oracle.UKF_SLAM, op, 4)
+    b = oracle.OracleFilter(oracle.UKF_LOC, op, 4)
+    a.init(0.3, -0.2, 0.4); b.init(0.3, -0.2, 0.4)
+    b.set_map(np.zeros((1, 2)))
+    for t in range(25):
+        a.update(0.07, 0.01 * (t % 3), [])
+        b.update(0.07, 0.01 * (t % 3), [])
+    assert np.array_equal(a.state(), b.state()) and np.array_equal(a.cov(), b.cov())
+
+
+def test_ukf_loc_bad_id_flag(oracle):
+    op = H.oracle_params(oracle, H.Params(filter="ukf_slam"))
+    f = oracle.OracleFilter(oracle.UKF_LOC, op, 4)
+    f.init(0, 0, 0)
+    f.set_map(np.array([[1.0, 0.5], [2.0, -0.5]]))
+    f.update(0.05, 0.0, np.array([[7, 1.0, 0.1]], dtype=np.float32))      # id 7 is not in the 2-landmark map
+    assert f.status & oracle.ERR_BAD_ID and list(f.assoc_log()) == [-1]
+
+
+def test_naive_filter_kat(oracle):
+    """NaiveFilter::update (filter.h:342-348): x += fwd cos(yaw), y += fwd sin(yaw), yaw = remainder(yaw + ang, 2 pi),
+    float32 command widened to double; measurements ignored."""
+    op = H.oracle_params(oracle, H.Params())
+    f = oracle.OracleFilter(oracle.NAIVE, op, 1)
+    f.init(1.0, 2.0, 0.5)
+    x = np.array([1.0, 2.0, 0.5])
+    for t in range(40):
+        fwd, ang = np.float32(0.1), np.float32(0.3)
+        f.update(fwd, ang, np.array([[3, 1.0, 0.0]], dtype=np.float32))
+        x = np.array([x[0] + float(fwd) * np.cos(x[2]), x[1] + float(fwd) * np.sin(x[2]),
+                      np.remainder(x[2] + float(fwd) * 0 + float(ang) + np.pi, 2 * np.pi) - np.pi])
+    assert f.n == 3 and f.timestep == 40
+    assert np.abs(f.state() - x).max() <= 1e-12
