@@ -186,7 +186,7 @@ int  slam_build_info(char* buf, int cap);             /* arch, compile flags */
  * key 6: headroom of the sweep kernel's tile; key 7: UKF step generation (2 = reflector / rotation-log products, warp
  * per instance, default; 1 = explicit eigenvector matrix, CTA per instance); key 8: capacity of the UKF rotation log
  * (shrinking it forces the rescue pass); key 9: max clipped eigenvectors riding beside the first S-pass; key 10: slices of the UKF batch that run their
- * front -> QL -> back chains on separate streams (1..8).
+ * front -> QL -> back chains on separate streams (1..8); key 11: 0 = skip the narrow-tile first pass of the UKF back kernel.
  * Results never depend on any of them (keys 7-9: up to rounding, inside the parity tolerance). */
 int  slam_tune(slam_handle_t h, int key, int value);
 

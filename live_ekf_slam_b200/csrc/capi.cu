@@ -202,6 +202,9 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
         CK(cudaMalloc(&u.rot, sizeof(double2) * (size_t)batch * u.rot_cap));
         CK(cudaMalloc(&u.swp, sizeof(int2) * (size_t)batch * u.swp_cap));
         CK(cudaMalloc(&u.nswp, sizeof(int) * batch));
+        CK(cudaMalloc(&u.defer, sizeof(int) * batch));
+        CK(cudaMemset(u.defer, 0, sizeof(int) * batch));
+        u.narrow = 1;
     }
     CK(cudaMalloc(&h->d_fwd, sizeof(float) * batch));
     CK(cudaMalloc(&h->d_ang, sizeof(float) * batch));
@@ -249,7 +252,7 @@ int slam_destroy(slam_handle_t h) {
     cudaFree(b.P); cudaFree(b.x); cudaFree(b.ids); cudaFree(b.meta);
     cudaFree(b.assoc); cudaFree(b.stats); cudaFree(b.sigma);
     cudaFree(h->d_map);
-    cudaFree(h->uk.Zg); cudaFree(h->uk.Yg); cudaFree(h->uk.dg); cudaFree(h->uk.eg); cudaFree(h->uk.rot); cudaFree(h->uk.swp); cudaFree(h->uk.nswp);
+    cudaFree(h->uk.Zg); cudaFree(h->uk.Yg); cudaFree(h->uk.dg); cudaFree(h->uk.eg); cudaFree(h->uk.rot); cudaFree(h->uk.swp); cudaFree(h->uk.nswp); cudaFree(h->uk.defer);
     cudaFree(b.retry_list); cudaFree(b.retry_count); cudaFree(b.max_M); cudaFree(h->d_work); cudaFree(h->d_progress);
     if (h->h_run_hint) cudaFreeHost(h->h_run_hint);
     for (int i = 0; i < slam_filter::HINT_RING; ++i) if (h->run_ev[i]) cudaEventDestroy(h->run_ev[i]);
@@ -301,6 +304,7 @@ int slam_tune(slam_handle_t h, int key, int value) {
         if (full < 256) full = 256;
         h->uk.rot_cap = (value <= 0 || value > full) ? full : value;
     } else if (key == 9) h->uk.clip_lanes = value < 0 ? 0 : value;
+    else if (key == 11) h->uk.narrow = value ? 1 : 0;
     else if (key == 10) { if (value < 1 || value > UKF_MAX_SUB) return fail(h, "slam_tune: UKF slices must be 1..8"); h->uks.nsub = value; }
     else return fail(h, "slam_tune: unknown key");
     return 0;

@@ -189,6 +189,8 @@ struct UkfScratch {
     double* eg;         // [n_max][batch]  off-diagonal of T
     double2* rot;       // [batch][rot_cap]  (c, s) of every QL plane rotation, in generation order
     int2* swp;          // [batch][swp_cap]  (l, m) range of every QL sweep
+    int* defer;         // [batch]  generation 2: 1 = this step's updates did not fit the narrow tile (full-width pass takes it)
+    int narrow;         // 1 (default): narrow-tile first pass + full-width deferred pass; 0: full-width tile only
     int* nswp;          // [batch]  number of sweeps logged; -1: log overflow (the back kernel redoes the QL itself)
     long long rot_cap;
     int swp_cap;

@@ -943,7 +943,11 @@ ukf_back_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, const
 // =========================================================================================================
 // pitch of the vector tile (doubles): odd, >= the lanes a step can need (4 + 2 max_meas, + 4 clipped eigenvectors)
 __host__ __device__ inline int ukf_wcols(const BatchState& b) { const int c = 4 + 2 * b.max_meas + 4; return c > 32 ? 32 : c; }
-__host__ __device__ inline int ukf_wld(const BatchState& b) { return ukf_wcols(b) <= 24 ? 25 : 33; }   // compile-time variants of the kernel
+__host__ __device__ inline int ukf_wld(const BatchState& b) { const int c = ukf_wcols(b); return c <= 12 ? 13 : (c <= 24 ? 25 : 33); }   // compile-time variants
+// The typical step needs far fewer lanes (4 + 2 * 1.5 updates + <= 4 clipped), so the batch first goes through a NARROW
+// tile (pitch 13: up to 4 updates; 27 KB of shared memory per instance -> 8 instances in flight per SM instead of 6); an
+// instance with more updates in this step flags itself and is taken by a second launch with the full-width tile.
+constexpr int UKF_NARROW_WLD = 13;
 constexpr int UPD_LD = 24;               // per-update scalars
 constexpr int UKF2_MAX_UPD = 14;         // 4 + 2 * updates <= 32 lanes
 
@@ -964,11 +968,10 @@ struct UkfWarpSmem {
     int* uq;        // measurement index of update q
 };
 
-__host__ __device__ inline size_t ukf_warp_carve(const BatchState& b, unsigned char* base, UkfWarpSmem* s) {
+__host__ __device__ inline size_t ukf_warp_carve(const BatchState& b, const int wld, unsigned char* base, UkfWarpSmem* s) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
     const int nmp = ldg_of(b.n_max), nsm = 2 * b.n_max + 2;
-    const int wld = ukf_wld(b);
     size_t oW = take(sizeof(double) * (size_t)(b.n_max + 4) * wld);
     size_t ox = take(sizeof(double) * nmp), oxp = take(sizeof(double) * nmp), osq = take(sizeof(double) * nmp);
     size_t oXp = take(sizeof(double) * 4 * nsm), oz = take(sizeof(double) * 2 * nsm);
@@ -1221,16 +1224,16 @@ ukf_front2_kernel(BatchState b, UkfScratch u, const int i0) {
 // ---- launch 3 of 3 (generation 2): warp per instance
 template <int wld>
 __global__ void __launch_bounds__(32)
-ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, const int i0) {
+ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, const int i0, const int pass) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     UkfWarpSmem s;
-    ukf_warp_carve(b, smem_raw, &s);
+    ukf_warp_carve(b, wld, smem_raw, &s);
     const int lane = threadIdx.x;
     const int inst = i0 + blockIdx.x;
     const int ldp = b.fixed_ld;
     const int nsm = 2 * b.n_max + 2;
     const unsigned FULL = 0xffffffffu;
-    const int wcols = ukf_wcols(b);
+    const int wcols = wld - 1 < ukf_wcols(b) ? wld - 1 : ukf_wcols(b);
     double* const W_ = s.W;
     const bool small_n = b.n_max <= 128;
 
@@ -1240,6 +1243,7 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
     if (status & SLAM_STATUS_SAME_STEP_REMATCH) return;
     const int nsw = u.nswp[inst];
     if (nsw < 0) return;                           // rotation log overflow: redone by the rescue pass
+    if (pass == 1 && !u.defer[inst]) return;       // full-width pass: only the instances the narrow pass handed over
     int M = meta_in.x;
     const int M_start = M;
     const int n = 4 + 2 * M;                       // ukf.cpp:167
@@ -1301,6 +1305,11 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
         if (cand != INT_MAX) ++nu;
     }
     __syncwarp();
+    if (pass == 0) {                                // narrow tile: hand the instance over if its updates do not fit
+        const bool over = 4 + 2 * nu > wcols;
+        if (lane == 0) u.defer[inst] = over ? 1 : 0;
+        if (over) return;
+    }
     const int nvec = 4 + 2 * nu;                    // lanes of the two S-passes
     int ncf = wcols - nvec; if (ncf > nclip) ncf = nclip;   // clipped eigenvectors riding in pass A
     if (u.clip_lanes > 0 && ncf > u.clip_lanes) ncf = u.clip_lanes;        // test knob
@@ -1605,15 +1614,16 @@ size_t ukf_step_smem_bytes(const BatchState& b) { return ukf_smem_carve(b, nullp
 
 static size_t ql_smem_bytes(const BatchState& b) { return sizeof(double) * 2 * (size_t)b.n_max * QL_LANES; }
 
-static size_t ukf_warp_smem_bytes(const BatchState& b) { return ukf_warp_carve(b, nullptr, nullptr); }
+static size_t ukf_warp_smem_bytes(const BatchState& b, int wld = 0) { return ukf_warp_carve(b, wld ? wld : ukf_wld(b), nullptr, nullptr); }
 
 cudaError_t ukf_step_configure(const BatchState& b) {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(ukf_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_front2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ukf_back2_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ukf_back2_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back2_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 13))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back2_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 25))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back2_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 33))) != cudaSuccess) return e;
     return cudaFuncSetAttribute(ukf_ql_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ql_smem_bytes(b));
 }
 
@@ -1657,6 +1667,7 @@ cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const St
             for (int k = 1; k < nsub; ++k) if ((e = cudaStreamWaitEvent(xs.aux[k - 1], xs.fork, 0)) != cudaSuccess) return e;
         }
         const size_t fsm = ukf_step_smem_bytes(b), wsm = ukf_warp_smem_bytes(b);
+        int nback = 0;
         for (int k = 0; k < nsub; ++k) {
             const int i0 = (int)((long long)b.batch * k / nsub), i1 = (int)((long long)b.batch * (k + 1) / nsub);
             if (i1 <= i0) continue;
@@ -1664,8 +1675,12 @@ cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const St
             ukf_front2_kernel<<<i1 - i0, UKF_THREADS, fsm, sk>>>(b, u, i0);
             if (nsub == 1) ukf_ql_kernel<true><<<(i1 - i0 + QL_LANES - 1) / QL_LANES, QL_LANES, ql_smem_bytes(b), sk>>>(u, b.meta, b.batch, i0, i1);
             else ukf_ql_kernel<false><<<(i1 - i0 + QL_LANES - 1) / QL_LANES, QL_LANES, 0, sk>>>(u, b.meta, b.batch, i0, i1);
-            if (ukf_wld(b) == 25) ukf_back2_kernel<25><<<i1 - i0, 32, wsm, sk>>>(b, fc, in, u, i0);
-            else ukf_back2_kernel<33><<<i1 - i0, 32, wsm, sk>>>(b, fc, in, u, i0);
+            const int full = ukf_wld(b);
+            const bool two_pass = u.narrow && full > UKF_NARROW_WLD;
+            if (two_pass || full == 13) ukf_back2_kernel<13><<<i1 - i0, 32, ukf_warp_smem_bytes(b, 13), sk>>>(b, fc, in, u, i0, two_pass ? 0 : 2);
+            if (full == 25) ukf_back2_kernel<25><<<i1 - i0, 32, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
+            else if (full == 33) ukf_back2_kernel<33><<<i1 - i0, 32, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
+            nback += (two_pass ? 2 : 1);
         }
         for (int k = 1; k < nsub; ++k) {
             if ((e = cudaEventRecord(xs.join[k - 1], xs.aux[k - 1])) != cudaSuccess) return e;
@@ -1674,7 +1689,7 @@ cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const St
         // rescue pass (generation-1 kernels, in-CTA QL): instances whose rotation log overflowed; everyone else exits at once
         ukf_front_kernel<<<b.batch, UKF_THREADS, fsm, st>>>(b, fc, in, u, 1);
         ukf_back_kernel<<<b.batch, UKF_THREADS, fsm, st>>>(b, fc, in, u, 1);
-        if (launched) *launched = 3 * nsub + 2;
+        if (launched) *launched = 2 * nsub + nback + 2;
     } else {
         ukf_front_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, fc, in, u, 0);
         ukf_ql_kernel<true><<<qblocks, QL_LANES, ql_smem_bytes(b), st>>>(u, b.meta, b.batch, 0, b.batch);

@@ -163,8 +163,8 @@ def test_ukf_filter_class(shim, oracle):
     assert msg["P"].size == of.n * of.n and msg["M"] == of.M
 
 
-@pytest.mark.parametrize("knobs", [((7, 1),), ((7, 2),), ((7, 2), (8, 600)), ((7, 2), (9, 1)), ((7, 2), (8, 2500), (9, 1))],
-                         ids=["generation1", "generation2", "rescue_pass_only", "clip_overflow_pass", "mixed_rescue"])
+@pytest.mark.parametrize("knobs", [((7, 1),), ((7, 2),), ((7, 2), (8, 600)), ((7, 2), (9, 1)), ((7, 2), (8, 2500), (9, 1)), ((7, 2), (11, 0))],
+                         ids=["generation1", "generation2", "rescue_pass_only", "clip_overflow_pass", "mixed_rescue", "full_width_tile_only"])
 def test_ukf_step_variants(shim, oracle, knobs):
     """The same free-running batch through the alternative code paths of the UKF step: the generation-1 kernels
     (explicit eigenvectors), a rotation log too small for any / for the later steps (rescue pass on the generation-1
@@ -219,3 +219,29 @@ def test_ukf_sliced_batch(shim, oracle):
     for i in range(0, B, 7):
         assert np.array_equal(runs[0].state(i), runs[1].state(i)) and np.array_equal(runs[0].cov(i), runs[1].cov(i))
     assert (runs[1].all_status() == 0).all()
+
+
+def test_ukf_narrow_tile_hand_over(shim, oracle):
+    """Steps with more than four updates do not fit the narrow tile of the back kernel: the instance flags itself and the
+    full-width pass of the same step takes it; its neighbour (fewer updates) stays on the narrow pass."""
+    p = H.Params(filter="ukf_slam")
+    op = H.oracle_params(oracle, p)
+    fb = shim.FilterBatch(shim.UKF_SLAM, p.to_c(), 2, 10, 8)
+    fb.init(0, 0, 0)
+    ofs = [oracle.OracleFilter(oracle.UKF_SLAM, op, 10) for _ in range(2)]
+    for of in ofs:
+        of.init(0, 0, 0)
+    six = np.array([[i, 1.0 + 0.2 * i, -0.5 + 0.2 * i] for i in range(6)], dtype=np.float32)
+    script = [(six, six[:2]),                       # step 1: insertions only
+              (six + np.float32([0, 0.01, -0.01]), six[:2]),      # step 2: six updates (hand-over) / two updates (narrow)
+              (six[1:4], six[:1]),                  # step 3: three updates / one
+              (six[::-1].copy(), np.zeros((0, 3), np.float32))]   # step 4: six updates in reverse message order / none
+    for ma, mb in script:
+        meas, n = fb.pack_meas([ma, mb])
+        fb.step(0.05, 0.01, meas, n)
+        ofs[0].update(0.05, 0.01, ma)
+        ofs[1].update(0.05, 0.01, mb)
+        for i in range(2):
+            assert list(fb.assoc(i)) == list(ofs[i].assoc_log())
+            _compare(fb, i, ofs[i])
+    assert (fb.all_status() == 0).all() and fb.num_landmarks(0) == 6
