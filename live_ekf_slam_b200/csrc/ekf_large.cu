@@ -58,8 +58,8 @@ __global__ void lm_predict_cols(LargeState L, FilterConst fc, const float* fwd) 
 }
 
 // ---- the sequential part of the step: ONE persistent kernel walks the measurements (ekf.cpp:73-174); the CTAs own
-// slices of the state and meet at a software grid barrier twice per measurement (after the association vote and
-// after x_pred / U / G of the measurement are published).  All CTAs are co-resident (cooperative launch).
+// slices of the state and meet at a software grid barrier once per measurement (after x_pred / U / G of the
+// measurement are published; the association vote is evaluated redundantly by every CTA).  All CTAs are co-resident (cooperative launch).
 constexpr int LM_THREADS = 256;
 constexpr int LM_WARPS = LM_THREADS / 32;
 constexpr int LM_SPAN = 32;      // state indices owned by a CTA per pass (one per lane); the warps split the q range
@@ -86,10 +86,8 @@ __global__ void __launch_bounds__(LM_THREADS) lm_front(LargeState L, FilterConst
     __shared__ int s_min;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ld = L.ld;
-    const int jlm = blockIdx.x * LM_THREADS + tid;        // landmark slot this thread votes for
     const size_t ustride = (size_t)L.n_max * 2, gstride = (size_t)2 * ld;
     unsigned* bar = reinterpret_cast<unsigned*>(L.cur + 8);
-    int* slots = L.ctl;                                   // [max_meas], preset to INT_MAX by the host
     unsigned gen = 0;
     // replicated bookkeeping: every thread of every CTA tracks the same (m, M, status)
     const int M_start = L.cur[3];
@@ -108,21 +106,27 @@ __global__ void __launch_bounds__(LM_THREADS) lm_front(LargeState L, FilterConst
             }
         }
         __syncthreads();
+        // every CTA scans all M landmarks itself (16 KB of L2-resident state): the vote needs no grid barrier
         int cand = INT_MAX;
-        for (int j = jlm; j < M; j += gridDim.x * LM_THREADS) {
-            if (!fc.id_known) {
-                const float x_diff = (float)fabs(s_sc[12] - __ldcg(L.xp + 3 + 2 * j));     // :91
-                const float y_diff = (float)fabs(s_sc[13] - __ldcg(L.xp + 4 + 2 * j));     // :92
-                if (x_diff < fc.min_sep && y_diff < fc.min_sep) { cand = j; break; }
-            } else if (__ldcg(L.ids + j) == (int)meas[3 * l]) { cand = j; break; }         // :101-108
+        if (!fc.id_known) {
+            const double xd = s_sc[12], yd = s_sc[13];
+#pragma unroll 4
+            for (int j = tid; j < M; j += LM_THREADS) {            // no early exit: the loads of all candidates stay in flight
+                const double lx = __ldcg(L.xp + 3 + 2 * j), ly = __ldcg(L.xp + 4 + 2 * j);
+                const float x_diff = (float)fabs(xd - lx);                                 // :91
+                const float y_diff = (float)fabs(yd - ly);                                 // :92
+                if (x_diff < fc.min_sep && y_diff < fc.min_sep && j < cand) cand = j;      // ascending j: the first match stays
+            }
+        } else {
+            const int want = (int)meas[3 * l];
+#pragma unroll 4
+            for (int j = tid; j < M; j += LM_THREADS)
+                if (__ldcg(L.ids + j) == want && j < cand) cand = j;                       // :101-108
         }
         cand = __reduce_min_sync(0xffffffffu, cand);
         if ((tid & 31) == 0 && cand != INT_MAX) atomicMin(&s_min, cand);
         __syncthreads();
-        if (tid == 0 && s_min != INT_MAX) atomicMin(&slots[l], s_min);
-        grid_sync(bar, gridDim.x, gen);
-        int slot = __ldcg(slots + l);
-        if (slot == 0x7f7f7f7f) slot = INT_MAX;
+        const int slot = s_min;
         int kind = 0;
         if (status & SLAM_STATUS_SAME_STEP_REMATCH) kind = 0;                  // dead for the rest of the step
         else if (slot != INT_MAX) {
@@ -147,9 +151,7 @@ __global__ void __launch_bounds__(LM_THREADS) lm_front(LargeState L, FilterConst
                 const double dd = (double)dist, d2 = (double)(dist * dist);
                 s_sc[0] = -(dx) / dd; s_sc[1] = -(dy) / dd; s_sc[2] = 0.0; s_sc[3] = dx / dd; s_sc[4] = dy / dd;
                 s_sc[5] = dy / d2; s_sc[6] = -(dx) / d2; s_sc[7] = -1.0; s_sc[8] = -(dy) / d2; s_sc[9] = dx / d2;
-                const float ang = (float)remainder(atan2(dy, dx) - xv2, TWO_PI_REF);
-                s_sc[10] = (double)(r - dist - fc.w_r);
-                s_sc[11] = (double)(bb - ang - fc.w_b);
+                (void)xv2;
             }
             __syncthreads();
             double H[10];
@@ -177,6 +179,7 @@ __global__ void __launch_bounds__(LM_THREADS) lm_front(LargeState L, FilterConst
                 double g0[5], g1[5];
 #pragma unroll
                 for (int cc = 0; cc < 5; ++cc) { g0[cc] = 0.0; g1[cc] = 0.0; }
+#pragma unroll 2
                 for (int q = lane; q < m; q += 32) {
                     const double* Gq = L.G + q * gstride;
 #pragma unroll
@@ -207,16 +210,21 @@ __global__ void __launch_bounds__(LM_THREADS) lm_front(LargeState L, FilterConst
                         S00 += g0[cc] * H[cc]; S01 += g0[cc] * H[5 + cc]; S10 += g1[cc] * H[cc]; S11 += g1[cc] * H[5 + cc];
                     }
                     S00 += fc.W00; S11 += fc.W11;
-                    const bool sw = fabs(S10) > fabs(S00);
-                    const double a00 = sw ? S10 : S00, a01 = sw ? S11 : S01, a10 = sw ? S00 : S10, a11 = sw ? S01 : S11;
-                    const double l10 = a10 / a00, u11 = a11 - l10 * a01;
-                    const double b0c0 = sw ? 0.0 : 1.0, b1c0 = sw ? 1.0 : 0.0, b0c1 = sw ? 1.0 : 0.0, b1c1 = sw ? 0.0 : 1.0;
-                    double y1 = b1c0 - l10 * b0c0;
-                    const double i10 = y1 / u11, i00 = (b0c0 - a01 * i10) / a00;
-                    y1 = b1c1 - l10 * b0c1;
-                    const double i11 = y1 / u11, i01 = (b0c1 - a01 * i11) / a00;
+                    // S^-1 (:135) by the adjugate: one division on the dependent chain instead of the three of the LU form
+                    // (same value to a few ulp; S = H P H^T + W is well conditioned, W = I under the reference's noise bug)
+                    const double rdet = 1.0 / (S00 * S11 - S01 * S10);
+                    const double i00 = S11 * rdet, i01 = -S01 * rdet, i10 = -S10 * rdet, i11 = S00 * rdet;
                     s_Sinv[0] = i00; s_Sinv[1] = i01; s_Sinv[2] = i10; s_Sinv[3] = i11;
                 }
+            } else if (tid == 32) {
+                // innovation (:129-131), off the critical path: the atan2 / remainder chain runs while warp 0 builds S
+                const int i = slot * 2 + 3;
+                const double xv0 = __ldcg(L.xp + 0), xv1 = __ldcg(L.xp + 1), xv2 = __ldcg(L.xp + 2);
+                const double dx = L.x[i] - xv0, dy = L.x[i + 1] - xv1;
+                const float dist = (float)sqrt(dx * dx + dy * dy);
+                const float ang = (float)remainder(atan2(dy, dx) - xv2, TWO_PI_REF);
+                s_sc[10] = (double)(r - dist - fc.w_r);
+                s_sc[11] = (double)(bb - ang - fc.w_b);
             }
             __syncthreads();
             for (int base = blockIdx.x * LM_SPAN; base < n; base += gridDim.x * LM_SPAN) {
@@ -234,6 +242,7 @@ __global__ void __launch_bounds__(LM_THREADS) lm_front(LargeState L, FilterConst
 #pragma unroll
                         for (int c = 0; c < 5; ++c) { const double pv = __ldcg(row + hc[c]); a0 += pv * H[c]; a1 += pv * H[5 + c]; }
                     }
+#pragma unroll 4
                     for (int q = warp; q < m; q += LM_WARPS) {  // low-rank corrections, q range split over the warps
                         const double* Gq = L.G + q * gstride;
                         const double ga = __ldcg(Gq + idx), gb = __ldcg(Gq + ld + idx);
