@@ -90,3 +90,34 @@ def test_shard_invariance(shim, oracle):
     for j in range(4):
         np.testing.assert_array_equal(full.state(8 + j), shard.state(j))
         np.testing.assert_array_equal(full.cov(8 + j), shard.cov(j))
+
+
+def test_sim_wide_kernel_large_map(shim, oracle):
+    """Few vehicles on a large map take the CTA-per-vehicle generator (32 warps, chunk counts scanned in shared memory):
+    same messages, in ascending-id order, as the oracle; overflow beyond max_meas truncates identically."""
+    from live_ekf_slam_b200 import workload as wl
+    p = H.Params(filter="ekf_slam")
+    op = H.oracle_params(oracle, p)
+    rng = np.random.default_rng(5)
+    lm = wl.random_map_fast(1500, p.map_bound, 0.3, rng)
+    fwd, ang = wl.tsp_trajectory(lm, p, rng, 60)
+    B, seed = 2, 99
+    fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), B, 50, 64)
+    sim = shim.Simulator(fb, lm, seed=seed, instance_offset=0)
+    truths = [np.zeros(3) for _ in range(B)]
+    n_msgs, flips = 0, 0
+    for t in range(len(fwd)):
+        sim.step(fwd[t], ang[t], t)
+        m, n = sim.meas()
+        tr = sim.truth()
+        for i in range(B):
+            ref = oracle.sim_step(op, truths[i], fwd[t], ang[t], lm, seed, i, t)[:64]
+            assert n[i] == len(ref), (t, i, n[i], len(ref))
+            got = m[i, : n[i]]
+            np.testing.assert_array_equal(got[:, 0], ref[:, 0])
+            if not np.array_equal(got, ref):
+                np.testing.assert_allclose(got, ref, rtol=1.3e-7, atol=0)
+                flips += int((got != ref).sum())
+            n_msgs += len(ref)
+            assert np.abs(tr[i] - truths[i]).max() <= 1e-12
+    assert n_msgs > 2000 and flips <= 2
