@@ -316,6 +316,9 @@ def run_ours(args):
 
     # ---- accuracy statistics of the last sweep, summed over ranks (the only collective on this path)
     st = parallel.allreduce_stats(fb.stats(), torch.device("cuda", local))   # NCCL over NVLink when world > 1
+    # per-run average position error (the reference's one number per run, plotting_node.py:195-218): on-device histogram,
+    # exact counts merged over the ranks, quantiles read off the merged histogram (1 cm bins)
+    run_hist = parallel.allreduce_histogram(fb.error_histogram(0.0, 10.0, 1000), torch.device("cuda", local))
 
     # ---- roofline: CUDA events on the launching stream around the kernel launches, separate sweeps.
     # (a) per-step streaming kernel (the one the per-call C-ABI path uses): P crosses HBM once each way per step.
@@ -450,7 +453,8 @@ def run_ours(args):
                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "config": workload_config(args, B), "clocks": clk, "e2e": e2e,
                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-               "accuracy": parallel.derive_accuracy(st, world * B)}
+               "accuracy": dict(parallel.derive_accuracy(st, world * B),
+                                per_run_avg_pos_err_m=parallel.histogram_summary(run_hist, 0.0, 10.0))}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

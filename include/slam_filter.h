@@ -172,6 +172,14 @@ int  slam_run_io(slam_handle_t h, const float* cmd_fwd, const float* cmd_ang, in
 int  slam_accumulate_error(slam_handle_t h, slam_sim_t s);
 int  slam_get_stats(slam_handle_t h, double* out /* SLAM_NUM_STATS */);
 int  slam_reset_stats(slam_handle_t h);
+/* Per-run accuracy analytics at Monte-Carlo scale.  The reference reduces every run to ONE number, the average position
+ * error of the vehicle history (compute_average_error, base_pkg/src/plotting_node.py:195-218), and tabulates it over the
+ * recorded runs of a setting (base_pkg/src/make_bar_graphs.py:11-18,55).  Here that number is produced on the device for
+ * every instance of the batch (avg_err[batch], may be NULL) together with its histogram: counts[0] = runs below lo,
+ * counts[1 + k] = runs in [lo + k (hi-lo)/nbins, lo + (k+1) (hi-lo)/nbins), counts[nbins + 1] = runs at or above hi
+ * (or non-finite).  HOST pointers; synchronises.  Ranks all-reduce `counts` (SUM, exact integers). */
+int  slam_get_error_histogram(slam_handle_t h, double lo, double hi, int nbins, long long* counts /* nbins + 2 */,
+                              double* avg_err /* batch, or NULL */);
 
 /* ---- introspection for the benchmark harness */
 long long slam_kernel_launches(slam_handle_t h);      /* kernels launched by this handle so far */

@@ -910,6 +910,27 @@ int slam_get_stats(slam_handle_t h, double* out) {
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
+int slam_get_error_histogram(slam_handle_t h, double lo, double hi, int nbins, long long* counts, double* avg_err) {
+    if (!h) return 1;
+    if (!(hi > lo) || nbins < 1 || nbins > 8190 || !counts) return fail(h, "slam_get_error_histogram: need lo < hi, 1 <= nbins <= 8190, counts != NULL");
+    CK(cudaSetDevice(h->device));
+    unsigned long long* d_cnt = nullptr;
+    double* d_avg = nullptr;
+    CK(cudaMalloc(&d_cnt, sizeof(unsigned long long) * (nbins + 2)));
+    if (cudaMalloc(&d_avg, sizeof(double) * h->b.batch) != cudaSuccess) { cudaFree(d_cnt); return fail(h, "slam_get_error_histogram: out of memory"); }
+    int rc = 0;
+    do {
+        if (cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * (nbins + 2), h->stream) != cudaSuccess) { rc = 1; break; }
+        if (launch_error_histogram(h->b, d_avg, d_cnt, lo, hi, nbins, h->stream) != cudaSuccess) { rc = 1; break; }
+        h->launches += 1;
+        if (cudaMemcpyAsync(counts, d_cnt, sizeof(long long) * (nbins + 2), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { rc = 1; break; }
+        if (avg_err && cudaMemcpyAsync(avg_err, d_avg, sizeof(double) * h->b.batch, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { rc = 1; break; }
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = 1; break; }
+    } while (false);
+    cudaFree(d_cnt); cudaFree(d_avg);
+    if (rc) return fail(h, "slam_get_error_histogram: CUDA error");
+    return 0;
+}
 int slam_reset_stats(slam_handle_t h) {
     if (!h) return 1;
     CK(cudaMemsetAsync(h->b.stats, 0, sizeof(double) * (size_t)h->b.batch * SLAM_NUM_STATS, h->stream));

@@ -267,6 +267,8 @@ cudaError_t launch_ekf_sweep(const BatchState& b, const FilterConst& fc, const S
 cudaError_t launch_sim_step(const SimState& s, const SimConst& sc, const float* d_fwd, const float* d_ang,
                             int cmd_stride, uint32_t step, cudaStream_t st);
 cudaError_t launch_accumulate_error(const BatchState& b, const SimState& s, cudaStream_t st);
+cudaError_t launch_error_histogram(const BatchState& b, double* d_avg, unsigned long long* d_counts, double lo, double hi, int nbins,
+                                   cudaStream_t st);
 cudaError_t launch_reduce_stats(const BatchState& b, double* d_out, cudaStream_t st);
 cudaError_t launch_poses(const BatchState& b, double* d_out, cudaStream_t st);
 cudaError_t launch_reset(const BatchState& b, double x0, double y0, double a2, double a3, cudaStream_t st);

@@ -182,6 +182,36 @@ cudaError_t launch_reduce_stats(const BatchState& b, double* d_out, cudaStream_t
     return cudaGetLastError();
 }
 
+// Per-run accuracy analytics (plotting_node.py:195-218 computes ONE number per run, the average position error, which
+// make_bar_graphs.py then tabulates over the ten recorded runs of a setting).  At Monte-Carlo scale the same number is
+// produced for every instance on the device together with its histogram: avg[i] = sum |e_pos| / steps; bin 0 counts runs
+// below `lo`, bin nbins + 1 runs at or above `hi` (and non-finite ones).  Counts are exact integers, so ranks all-reduce
+// them (SUM) and percentiles are read off the merged histogram.
+__global__ void error_histogram_kernel(BatchState b, double* avg_out, unsigned long long* counts, double lo, double hi, int nbins) {
+    extern __shared__ unsigned int sh_cnt[];
+    for (int k = threadIdx.x; k < nbins + 2; k += blockDim.x) sh_cnt[k] = 0u;
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < b.batch) {
+        const double* st = b.stats + (size_t)i * SLAM_NUM_STATS;
+        const double e = st[0] > 0.0 ? st[4] / st[0] : 0.0;          // avg_err = sum(errors) / num_iters, :214
+        if (avg_out) avg_out[i] = e;
+        int bin;
+        if (!(e >= lo)) bin = isfinite(e) ? 0 : nbins + 1;
+        else if (!(e < hi)) bin = nbins + 1;
+        else { bin = 1 + (int)((e - lo) / (hi - lo) * nbins); if (bin > nbins) bin = nbins; }
+        atomicAdd(&sh_cnt[bin], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nbins + 2; k += blockDim.x) if (sh_cnt[k]) atomicAdd(&counts[k], (unsigned long long)sh_cnt[k]);
+}
+
+cudaError_t launch_error_histogram(const BatchState& b, double* d_avg, unsigned long long* d_counts, double lo, double hi, int nbins,
+                                   cudaStream_t st) {
+    error_histogram_kernel<<<(b.batch + 255) / 256, 256, sizeof(unsigned int) * (nbins + 2), st>>>(b, d_avg, d_counts, lo, hi, nbins);
+    return cudaGetLastError();
+}
+
 // vehicle pose (x, y, yaw) of every instance -> [batch][3]
 __global__ void poses_kernel(BatchState b, double* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

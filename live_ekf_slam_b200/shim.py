@@ -32,7 +32,7 @@ ABI_SYMBOLS = (
     "slam_sim_create", "slam_sim_destroy", "slam_sim_reset", "slam_sim_step", "slam_sim_step_device",
     "slam_sim_meas", "slam_sim_n_meas", "slam_sim_get_truth", "slam_sim_get_meas",
     "slam_run", "slam_run_device", "slam_reset", "slam_step_io", "slam_run_io", "slam_set_profiling", "slam_get_profile",
-    "slam_accumulate_error", "slam_get_stats", "slam_reset_stats",
+    "slam_accumulate_error", "slam_get_stats", "slam_reset_stats", "slam_get_error_histogram",
     "slam_kernel_launches", "slam_build_info", "slam_tune",
 )
 
@@ -98,6 +98,7 @@ def load(path: str | None = None):
     L.slam_accumulate_error.argtypes = [vp, vp]
     L.slam_get_stats.argtypes = [vp, dp]
     L.slam_reset_stats.argtypes = [vp]
+    L.slam_get_error_histogram.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_longlong), dp]
     L.slam_kernel_launches.argtypes = [vp]
     L.slam_kernel_launches.restype = C.c_longlong
     L.slam_build_info.argtypes = [C.c_char_p, C.c_int]
@@ -333,6 +334,16 @@ class FilterBatch:
 
     def reset_stats(self):
         self._ck(self._L.slam_reset_stats(self._h))
+
+    def error_histogram(self, lo: float, hi: float, nbins: int, per_instance: bool = False):
+        """Histogram of the per-run average position error (plotting_node.py:195-218) over the batch: int64
+        counts[nbins + 2] (under / bins / over) and, optionally, the per-instance averages (the ekf.csv column of the
+        reference's recorded runs, make_bar_graphs.py:11-18)."""
+        counts = np.zeros(nbins + 2, dtype=np.int64)
+        avg = np.zeros(self.batch) if per_instance else None
+        self._ck(self._L.slam_get_error_histogram(self._h, lo, hi, nbins, counts.ctypes.data_as(C.POINTER(C.c_longlong)),
+                                                  avg.ctypes.data_as(C.POINTER(C.c_double)) if avg is not None else None))
+        return (counts, avg) if per_instance else counts
 
 
 class Simulator:

@@ -1,8 +1,4 @@
 #!/bin/bash
-# quick GPU visit: parity tests + one bench line per filter
 set -u
-mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -25 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_ekf.json 2> gpurun_out/bench_ekf.err; tail -3 gpurun_out/bench_ekf.err
-cat gpurun_out/bench_ekf.json
+timeout 900 python -m pytest tests/test_gpu_sim_parity.py tests/test_abi.py -m gpu -x -q 2>&1 | tail -4
+timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['accuracy'])"

@@ -121,3 +121,30 @@ def test_sim_wide_kernel_large_map(shim, oracle):
             n_msgs += len(ref)
             assert np.abs(tr[i] - truths[i]).max() <= 1e-12
     assert n_msgs > 2000 and flips <= 2
+
+
+def test_error_histogram_vs_oracle_runs(shim, oracle):
+    """slam_get_error_histogram: the per-run average position error (plotting_node.py:195-218) of every instance against
+    oracle runs of the same instances, and the on-device histogram against numpy on those numbers (exact counts)."""
+    p, lm, fwd, ang = H.config2(seed=1, steps=150)
+    op = H.oracle_params(oracle, p)
+    B, seed = 40, 77
+    fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), B, 50, 8)
+    fb.init(0, 0, 0)
+    sim = shim.Simulator(fb, lm, seed=seed)
+    sim.run(fwd, ang)
+    fb.synchronize()
+    lo, hi, nb = 0.0, 0.5, 25
+    counts, avg = fb.error_histogram(lo, hi, nb, per_instance=True)
+    for i in (0, 7, 39):
+        st, pose, truth, _ = oracle.run_instance(oracle.EKF_SLAM, op, lm, fwd, ang, seed, i, 50, oracle.STRUCTURED)
+        ref = np.sqrt(((pose[:, :2] - truth[:, :2]) ** 2).sum(axis=1)).mean()
+        assert abs(avg[i] - ref) <= 1e-9 * max(1.0, ref), (i, avg[i], ref)
+    ref_counts = np.zeros(nb + 2, dtype=np.int64)
+    for v in avg:
+        k = 0 if v < lo else (nb + 1 if v >= hi else 1 + min(int((v - lo) / (hi - lo) * nb), nb - 1))
+        ref_counts[k] += 1
+    np.testing.assert_array_equal(counts, ref_counts)
+    assert counts.sum() == B and abs(avg.mean() - fb.stats()[4] / fb.stats()[0]) <= 1e-12
+    with pytest.raises(shim.SlamError):
+        fb.error_histogram(1.0, 1.0, 4)

@@ -33,8 +33,18 @@ for g in range(first, first + cnt):
     stats[0] += T; stats[1] += (e[:, 0] ** 2).sum(); stats[2] += (e[:, 1] ** 2).sum(); stats[3] += (e[:, 2] ** 2).sum()
     stats[4] += np.sqrt(e[:, 0] ** 2 + e[:, 1] ** 2).sum()
     finals[g] = pose[-1].tolist()
+    avg_errs = globals().setdefault("avg_errs", [])
+    avg_errs.append(float(np.sqrt(e[:, 0] ** 2 + e[:, 1] ** 2).sum() / T))       # plotting_node.py:212-214, one number per run
 tot = parallel.allreduce_stats(stats)
-print("RESULT " + json.dumps({"rank": rank, "world": world, "stats": tot.tolist(), "finals": finals}), flush=True)
+# per-run average errors -> histogram (the layout of slam_get_error_histogram), merged over the ranks
+LO, HI, NB = 0.0, 2.0, 40
+counts = np.zeros(NB + 2, dtype=np.int64)
+for v in globals().get("avg_errs", []):
+    k = 0 if v < LO else (NB + 1 if v >= HI else 1 + min(int((v - LO) / (HI - LO) * NB), NB - 1))
+    counts[k] += 1
+hist = parallel.allreduce_histogram(counts)
+print("RESULT " + json.dumps({"rank": rank, "world": world, "stats": tot.tolist(), "finals": finals,
+                              "hist": hist.tolist(), "summary": parallel.histogram_summary(hist, LO, HI)}), flush=True)
 if world > 1:
     dist.destroy_process_group()
 '''
@@ -77,3 +87,19 @@ def test_two_rank_gloo_sweep_matches_single_process():
         assert finals[k] == v                      # instance results do not depend on the sharding
     np.testing.assert_allclose(two[0]["stats"], single["stats"], rtol=1e-12)
     assert two[0]["stats"][0] == 6 * 120
+    # the merged histogram of per-run average errors is exact and identical on every rank
+    assert two[0]["hist"] == two[1]["hist"] == single["hist"] and sum(single["hist"]) == 6
+    sm = two[0]["summary"]
+    assert sm["runs"] == 6 and sm["p50"] is not None and sm["p50"] <= sm["p90"] <= sm["p99"]
+    assert abs(sm["mean_binned"] - single["stats"][4] / single["stats"][0]) <= sm["bin_width"]
+
+
+def test_histogram_summary_edges():
+    import sys as _s
+    _s.path.insert(0, ROOT)
+    from live_ekf_slam_b200 import parallel
+    counts = np.array([1, 0, 5, 3, 1, 2], dtype=np.int64)          # below | 4 bins of width 0.25 | above
+    sm = parallel.histogram_summary(counts, 0.0, 1.0)
+    assert sm["runs"] == 12 and sm["below_lo"] == 1 and sm["at_or_above_hi"] == 2 and sm["bin_width"] == 0.25
+    assert sm["p50"] == 0.5 and sm["p90"] is None                 # the 90th percentile lies in the overflow bin
+    assert parallel.histogram_summary(np.zeros(6, dtype=np.int64), 0.0, 1.0)["p50"] is None
