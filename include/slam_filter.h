@@ -124,6 +124,13 @@ int  slam_set_state(slam_handle_t h, int inst, const double* x, const double* P_
 int  slam_sim_create(slam_handle_t h, const double* lm_xy, int n_lm, uint64_t seed,
                      uint32_t instance_offset, slam_sim_t* out);
 int  slam_sim_destroy(slam_sim_t s);
+/* Precomputed command trajectories for the whole batch on the device (replaces the host pre-pass generate_trajectory,
+ * base_pkg/src/sim_node.py:63-152, run once per Monte-Carlo instance): noisy copy of the map, nearest-neighbour tour,
+ * one clamped command per step.  Map noise: Philox keyed (seed; global instance, landmark id, 0, 1).  d_fwd / d_ang:
+ * DEVICE buffers [T][batch] float32 (the Command.msg wire values), usable as slam_run_device(..., cmd_stride = 1, ...).
+ * landmark_noise / visitation_threshold / bound: params.yaml:90,91,70. */
+int  slam_sim_make_trajectories(slam_sim_t s, double landmark_noise, double visitation_threshold, double bound,
+                                double x_0, double y_0, double yaw_0, int T, float* d_fwd, float* d_ang);
 int  slam_sim_reset(slam_sim_t s, double x_0, double y_0, double yaw_0);
 /* one get_cmd() for every vehicle; commands are HOST (slam_sim_step) or DEVICE (…_device) float32.
  * Results stay on the device: slam_sim_meas()/slam_sim_n_meas() return the DEVICE buffers

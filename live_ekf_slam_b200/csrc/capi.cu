@@ -608,6 +608,18 @@ int slam_sim_create(slam_handle_t h, const double* lm_xy, int n_lm, uint64_t see
     *out = s;
     return slam_sim_reset(s, 0.0, 0.0, 0.0);
 }
+int slam_sim_make_trajectories(slam_sim_t s, double landmark_noise, double visitation_threshold, double bound,
+                               double x_0, double y_0, double yaw_0, int T, float* d_fwd, float* d_ang) {
+    if (!s) return 1;
+    slam_filter* h = s->owner;
+    if (!d_fwd || !d_ang || T < 1) return fail(h, "slam_sim_make_trajectories: bad argument");
+    if (s->s.n_lm > 256) return fail(h, "slam_sim_make_trajectories: at most 256 landmarks (per-thread tour state)");
+    CK(cudaSetDevice(h->device));
+    TspParams tp{landmark_noise, visitation_threshold, bound, x_0, y_0, yaw_0, T};
+    CK(launch_tsp_trajectories(s->s, h->sc, tp, d_fwd, d_ang, h->stream));
+    h->launches += 1;
+    return 0;
+}
 int slam_sim_destroy(slam_sim_t s) {
     if (!s) return 0;
     cudaSetDevice(s->owner->device);

@@ -245,6 +245,13 @@ struct SimState {
     uint32_t instance_offset;
     uint32_t k0, k1;
 };
+// sim_node.py:63-152 trajectory generation parameters (params.yaml:70-73,90-91 + the start pose)
+struct TspParams {
+    double landmark_noise, visitation_threshold, bound;
+    double x0, y0, yaw0;
+    int T;
+};
+cudaError_t launch_tsp_trajectories(const SimState& s, const SimConst& sc, const TspParams& tp, float* d_fwd, float* d_ang, cudaStream_t st);
 // One chunk of a Monte-Carlo sweep / trajectory replay (csrc/ekf_batch.cu: ekf_sweep_kernel).
 struct SweepArgs {
     const float* cmd_fwd;  // device, [T] (cmd_stride 0) or [T][batch], already offset to the chunk

@@ -182,6 +182,70 @@ cudaError_t launch_reduce_stats(const BatchState& b, double* d_out, cudaStream_t
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Precomputed command trajectories on the device, one Monte-Carlo instance per thread (sim_node.py:63-152,
+// generate_trajectory): a noisy copy of the map (uniform +-landmark_noise, clamped 1 m inside the region, :83-87), the
+// nearest-neighbour tour from the start pose (:89-112, first minimum wins), then one command per step that drives at most
+// d_max / th_max towards the current goal and rotates the tour when within visitation_threshold (:118-152).  The
+// reference draws the map noise from an unseeded random.random(); here Philox keyed (seed; instance, landmark id, 0, 1).
+// Output: the float32 wire values of Command.msg:3-5, [T][batch] (cmd_stride 1 of slam_run_device).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TSP_MAX_LM = 256;
+__global__ void tsp_trajectory_kernel(SimState s, SimConst sc, TspParams tp, float* __restrict__ fwd_out, float* __restrict__ ang_out) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= s.batch) return;
+    const int N = s.n_lm;
+    const uint32_t inst = s.instance_offset + (uint32_t)w;
+    double nx[TSP_MAX_LM], ny[TSP_MAX_LM];
+    short path[TSP_MAX_LM];
+    unsigned char seen[TSP_MAX_LM];
+    const double lo = -tp.bound + 1, hi = tp.bound - 1;
+    for (int i = 0; i < N; ++i) {
+        uint32_t rn[4];
+        philox4x32_10(inst, (uint32_t)i, 0u, 1u, s.k0, s.k1, rn);
+        const double ax = s.lm_xy[2 * i] + 2 * tp.landmark_noise * uniform53(rn[0], rn[1]) - tp.landmark_noise;
+        const double ay = s.lm_xy[2 * i + 1] + 2 * tp.landmark_noise * uniform53(rn[2], rn[3]) - tp.landmark_noise;
+        nx[i] = fmax(lo, fmin(ax, hi)); ny[i] = fmax(lo, fmin(ay, hi));
+        seen[i] = 0;
+    }
+    double x = tp.x0, y = tp.y0, th = tp.yaw0;
+    auto dist = [](double ax, double ay, double bx, double by) { const double dx = ax - bx, dy = ay - by; return sqrt(dx * dx + dy * dy); };
+    int cur = 0;
+    double best = dist(nx[0], ny[0], x, y);
+    for (int i = 0; i < N; ++i) { const double d = dist(nx[i], ny[i], x, y); if (d < best) { cur = i; best = d; } }
+    path[0] = (short)cur; seen[cur] = 1;
+    for (int k = 1; k < N; ++k) {
+        int g = -1; double bd = -1.0;
+        for (int i = 0; i < N; ++i) {
+            if (seen[i]) continue;
+            const double d = dist(nx[i], ny[i], nx[cur], ny[cur]);
+            if (bd < 0 || d < bd) { g = i; bd = d; }
+        }
+        path[k] = (short)g; seen[g] = 1; cur = g;
+    }
+    int head = 0;
+    for (int t = 0; t < tp.T; ++t) {
+        if (dist(x, y, nx[path[head]], ny[path[head]]) < tp.visitation_threshold) head = (head + 1 == N) ? 0 : head + 1;
+        const double gx = nx[path[head]], gy = ny[path[head]];
+        double d = dist(gx, gy, x, y);
+        const double gb = atan2(gy - y, gx - x);
+        double hdg = remainder(gb - th, TWO_PI_REF);
+        d = fmin(d, sc.d_max);
+        if (fabs(hdg) > sc.th_max) hdg = (hdg > 0) ? sc.th_max : -sc.th_max;
+        double sn, cs;
+        sincos(th, &sn, &cs);
+        x = x + d * cs; y = y + d * sn; th = th + hdg;
+        fwd_out[(size_t)t * s.batch + w] = (float)d;
+        ang_out[(size_t)t * s.batch + w] = (float)hdg;
+    }
+}
+
+cudaError_t launch_tsp_trajectories(const SimState& s, const SimConst& sc, const TspParams& tp, float* d_fwd, float* d_ang, cudaStream_t st) {
+    if (s.n_lm > TSP_MAX_LM) return cudaErrorInvalidValue;
+    tsp_trajectory_kernel<<<(s.batch + 63) / 64, 64, 0, st>>>(s, sc, tp, d_fwd, d_ang);
+    return cudaGetLastError();
+}
+
 // Per-run accuracy analytics (plotting_node.py:195-218 computes ONE number per run, the average position error, which
 // make_bar_graphs.py then tabulates over the ten recorded runs of a setting).  At Monte-Carlo scale the same number is
 // produced for every instance on the device together with its histogram: avg[i] = sum |e_pos| / steps; bin 0 counts runs

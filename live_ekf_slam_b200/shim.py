@@ -29,7 +29,7 @@ ABI_SYMBOLS = (
     "slam_update_device", "slam_get_timestep", "slam_get_num_landmarks", "slam_get_status", "slam_get_state",
     "slam_get_state_vector", "slam_get_cov", "slam_get_landmark_ids", "slam_get_assoc", "slam_get_sigma_points",
     "slam_get_poses", "slam_get_all_status", "slam_get_all_num_landmarks", "slam_set_state",
-    "slam_sim_create", "slam_sim_destroy", "slam_sim_reset", "slam_sim_step", "slam_sim_step_device",
+    "slam_sim_create", "slam_sim_destroy", "slam_sim_make_trajectories", "slam_sim_reset", "slam_sim_step", "slam_sim_step_device",
     "slam_sim_meas", "slam_sim_n_meas", "slam_sim_get_truth", "slam_sim_get_meas",
     "slam_run", "slam_run_device", "slam_reset", "slam_step_io", "slam_run_io", "slam_set_profiling", "slam_get_profile",
     "slam_accumulate_error", "slam_get_stats", "slam_reset_stats", "slam_get_error_histogram",
@@ -79,6 +79,7 @@ def load(path: str | None = None):
     L.slam_set_state.argtypes = [vp, C.c_int, dp, dp, ip, C.c_int, C.c_int]
     L.slam_sim_create.argtypes = [vp, dp, C.c_int, C.c_uint64, C.c_uint32, C.POINTER(vp)]
     L.slam_sim_destroy.argtypes = [vp]
+    L.slam_sim_make_trajectories.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, vp, vp]
     L.slam_sim_reset.argtypes = [vp, C.c_double, C.c_double, C.c_double]
     L.slam_sim_step.argtypes = [vp, vp, vp, C.c_int, C.c_uint32]
     L.slam_sim_step_device.argtypes = [vp, vp, vp, C.c_int, C.c_uint32]
@@ -409,6 +410,12 @@ class Simulator:
 
     def run_device(self, d_fwd, d_ang, cmd_stride: int, T: int, first_step: int = 0):
         self._f._ck(self._L.slam_run_device(self._f._h, self._s, _ptr(d_fwd), _ptr(d_ang), cmd_stride, T, first_step))
+
+    def make_trajectories(self, landmark_noise: float, visitation_threshold: float, bound: float, pose0, T: int, d_fwd, d_ang):
+        """generate_trajectory (sim_node.py:63-152) for every instance on the device: fills the DEVICE buffers d_fwd / d_ang
+        ([T][batch] float32, e.g. torch tensors) with per-instance command trajectories (use with run_device(..., cmd_stride=1))."""
+        self._f._ck(self._L.slam_sim_make_trajectories(self._s, landmark_noise, visitation_threshold, bound,
+                                                       pose0[0], pose0[1], pose0[2], T, _ptr(d_fwd), _ptr(d_ang)))
 
     def accumulate_error(self):
         self._f._ck(self._L.slam_accumulate_error(self._f._h, self._s))

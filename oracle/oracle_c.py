@@ -94,6 +94,8 @@ def lib():
     L.oracle_bench.argtypes = [C.c_int, pp, dp, C.c_int, fp, fp, C.c_int, C.c_uint64, C.c_int, C.c_int,
                                C.c_int, C.c_int, C.POINTER(C.c_longlong)]
     L.oracle_eigh.argtypes = [dp, C.c_int, dp, dp]
+    L.oracle_tsp_trajectory.argtypes = [pp, dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                        C.c_int, C.c_uint64, C.c_uint32, fp, fp]
     L.oracle_set_trig_mode.argtypes = [C.c_int]
     _lib = L
     return L
@@ -221,6 +223,18 @@ def sim_step(params: OracleParams, truth: np.ndarray, fwd, ang, lm_xy: np.ndarra
     k = lib().oracle_sim_step(C.byref(params), _dp(truth), np.float32(fwd), np.float32(ang), _dp(lm), len(lm),
                               seed, instance, step, _fp(out), len(lm))
     return out[: 3 * k].reshape(k, 3).copy()
+
+
+def tsp_trajectory(params: OracleParams, lm_xy, landmark_noise, visitation_threshold, bound, pose0, T, seed, instance):
+    """sim_node.py:63-152 for one Monte-Carlo instance; returns (fwd float32[T], ang float32[T])."""
+    lm = np.ascontiguousarray(lm_xy, dtype=np.float64).reshape(-1, 2)
+    fwd = np.zeros(T, dtype=np.float32)
+    ang = np.zeros(T, dtype=np.float32)
+    rc = lib().oracle_tsp_trajectory(C.byref(params), _dp(lm), len(lm), landmark_noise, visitation_threshold, bound,
+                                     pose0[0], pose0[1], pose0[2], T, seed, instance, _fp(fwd), _fp(ang))
+    if rc != 0:
+        raise ValueError("oracle_tsp_trajectory: bad arguments")
+    return fwd, ang
 
 
 def run_instance(kind, params, lm_xy, cmd_fwd, cmd_ang, seed, instance, max_landmarks, mode=STRUCTURED, keep=False):

@@ -817,6 +817,57 @@ int oracle_sim_step(const oracle_params* p, double truth[3], float fwd, float an
     return k;
 }
 
+/* ------------------------------------------------------------------ generate_trajectory, sim_node.py:63-152
+ * noisy copy of the map (:83-87), nearest-neighbour tour from the start pose (:89-112), one clamped command per step,
+ * rotating the tour when within the visitation threshold (:118-152).  Map noise: Philox keyed (seed; instance, id, 0, 1)
+ * (deviation D-5; the reference uses the unseeded random.random()). */
+static double tsp_norm(double ax, double ay, double bx, double by) { const double dx = ax - bx, dy = ay - by; return sqrt(dx * dx + dy * dy); }
+int oracle_tsp_trajectory(const oracle_params* p, const double* lm_xy, int n_lm, double landmark_noise,
+                          double visitation_threshold, double bound, double x0, double y0, double yaw0, int T,
+                          uint64_t seed, uint32_t instance, float* fwd_out, float* ang_out) {
+    if (n_lm < 1 || T < 0) return -1;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    double* nx = dalloc((size_t)n_lm); double* ny = dalloc((size_t)n_lm);
+    int* path = (int*)calloc((size_t)n_lm, sizeof(int));
+    char* seen = (char*)calloc((size_t)n_lm, 1);
+    const double lo = -bound + 1, hi = bound - 1;                                  /* :86-87 */
+    for (int i = 0; i < n_lm; ++i) {
+        uint32_t rn[4];
+        oracle_philox(instance, (uint32_t)i, 0u, 1u, k0, k1, rn);
+        const double ax = lm_xy[2 * i] + 2 * landmark_noise * oracle_uniform(rn[0], rn[1]) - landmark_noise;      /* :84 */
+        const double ay = lm_xy[2 * i + 1] + 2 * landmark_noise * oracle_uniform(rn[2], rn[3]) - landmark_noise;  /* :85 */
+        nx[i] = fmax(lo, fmin(ax, hi)); ny[i] = fmax(lo, fmin(ay, hi));
+    }
+    double x = x0, y = y0, th = yaw0;
+    int cur = 0;
+    double best = tsp_norm(nx[0], ny[0], x, y);                                    /* :90-96 */
+    for (int i = 0; i < n_lm; ++i) { const double d = tsp_norm(nx[i], ny[i], x, y); if (d < best) { cur = i; best = d; } }
+    path[0] = cur; seen[cur] = 1;
+    for (int k = 1; k < n_lm; ++k) {                                               /* :100-112 */
+        int g = -1; double bd = -1.0;
+        for (int i = 0; i < n_lm; ++i) {
+            if (seen[i]) continue;
+            const double d = tsp_norm(nx[i], ny[i], nx[cur], ny[cur]);
+            if (bd < 0 || d < bd) { g = i; bd = d; }
+        }
+        path[k] = g; seen[g] = 1; cur = g;
+    }
+    int head = 0;
+    for (int t = 0; t < T; ++t) {                                                  /* :118-152 */
+        if (tsp_norm(x, y, nx[path[head]], ny[path[head]]) < visitation_threshold) head = (head + 1 == n_lm) ? 0 : head + 1;
+        const double gx = nx[path[head]], gy = ny[path[head]];
+        double d = tsp_norm(gx, gy, x, y);
+        const double gb = atan2(gy - y, gx - x);
+        double hdg = remainder(gb - th, 2 * PI_REF);
+        d = fmin(d, p->d_max);
+        if (fabs(hdg) > p->th_max) hdg = (hdg > 0) ? p->th_max : -p->th_max;
+        x = x + d * cos(th); y = y + d * sin(th); th = th + hdg;
+        fwd_out[t] = (float)d; ang_out[t] = (float)hdg;
+    }
+    free(nx); free(ny); free(path); free(seen);
+    return 0;
+}
+
 /* ------------------------------------------------------------------ Monte-Carlo instance + CPU timing */
 int oracle_run_instance(int kind, const oracle_params* p, const double* lm_xy, int n_lm,
                         const float* cmd_fwd, const float* cmd_ang, int T,

@@ -19,6 +19,7 @@
  *   localization_pkg/src/ukf.cpp:3-45,106-371                   UKF (SLAM and localisation-only branches)
  *   localization_pkg/include/localization_pkg/filter.h:325-370  NaiveFilter
  *   base_pkg/src/sim_node.py:209-250                            measurement generator
+ *   base_pkg/src/sim_node.py:63-152                             command trajectory generator
  */
 #ifndef SLAM_ORACLE_H
 #define SLAM_ORACLE_H
@@ -84,6 +85,12 @@ double oracle_uniform(uint32_t hi, uint32_t lo);
 int   oracle_sim_step(const oracle_params* p, double truth[3], float fwd, float ang,
                       const double* lm_xy, int n_lm, uint64_t seed, uint32_t instance, uint32_t step,
                       float* meas_out, int cap);
+
+/* generate_trajectory, sim_node.py:63-152: the precomputed command trajectory of one Monte-Carlo instance
+ * (noisy map copy keyed (seed; instance, id, 0, 1), nearest-neighbour tour, clamped commands); float32 wire values out. */
+int   oracle_tsp_trajectory(const oracle_params* p, const double* lm_xy, int n_lm, double landmark_noise,
+                            double visitation_threshold, double bound, double x0, double y0, double yaw0, int T,
+                            uint64_t seed, uint32_t instance, float* fwd_out, float* ang_out);
 
 /* whole Monte-Carlo instance: simulator + filter for T steps (used for traces and CPU timing).
  * pose_trace (optional) receives T*3 doubles (x,y,yaw estimate); truth_trace (optional) T*3. */

@@ -148,3 +148,42 @@ def test_error_histogram_vs_oracle_runs(shim, oracle):
     assert counts.sum() == B and abs(avg.mean() - fb.stats()[4] / fb.stats()[0]) <= 1e-12
     with pytest.raises(shim.SlamError):
         fb.error_histogram(1.0, 1.0, 4)
+
+
+def test_device_tsp_trajectories(shim, oracle):
+    """slam_sim_make_trajectories: per-instance command trajectories generated on the device (sim_node.py:63-152) against
+    the CPU restatement, then a sweep driven by them (cmd_stride = 1) against oracle runs with the same commands."""
+    import torch
+    p, lm, _, _ = H.config2(seed=0, steps=10)
+    op = H.oracle_params(oracle, p)
+    B, T, seed, off = 24, 300, 4242, 5
+    fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), B, 50, 8)
+    fb.init(*p.init_pose)
+    sim = shim.Simulator(fb, lm, seed=seed, instance_offset=off)
+    d_fwd = torch.zeros((T, B), dtype=torch.float32, device="cuda")
+    d_ang = torch.zeros((T, B), dtype=torch.float32, device="cuda")
+    sim.make_trajectories(p.landmark_noise, p.visitation_threshold, p.map_bound, p.init_pose, T, d_fwd, d_ang)
+    fb.synchronize()
+    fwd, ang = d_fwd.cpu().numpy(), d_ang.cpu().numpy()
+    flips = 0
+    refs = {}
+    for i in range(B):
+        rf, ra = oracle.tsp_trajectory(op, lm, p.landmark_noise, p.visitation_threshold, p.map_bound, p.init_pose, T, seed, off + i)
+        refs[i] = (rf, ra)
+        assert np.abs(fwd[:, i] - rf).max() <= 1e-7 and np.abs(ang[:, i] - ra).max() <= 1e-7, i
+        # while the vehicle converges on its goal the heading command is the residual of a cancellation (gb - th): its
+        # absolute error stays ~1e-16 (device vs glibc atan2, FMA contraction) whatever its size; commands of visible size
+        # may only flip a last float32 bit
+        np.testing.assert_allclose(ang[:, i], ra, rtol=2.5e-7, atol=1e-12)
+        np.testing.assert_allclose(fwd[:, i], rf, rtol=2.5e-7, atol=0)
+        big = np.abs(ra) > 1e-6
+        flips += int((fwd[:, i] != rf).sum() + (ang[big, i] != ra[big]).sum())
+    assert flips <= 6, flips
+    assert not np.array_equal(ang[:, 0], ang[:, 1])
+    sim.run_device(d_fwd, d_ang, 1, T, 0)
+    fb.synchronize()
+    for i in (0, 11, 23):
+        st, pose, truth, keep = oracle.run_instance(oracle.EKF_SLAM, op, lm, fwd[:, i].copy(), ang[:, i].copy(), seed, off + i, 50,
+                                                    oracle.STRUCTURED, keep=True)
+        assert fb.num_landmarks(i) == keep.M and list(fb.landmark_ids(i)) == list(keep.landmark_ids())
+        assert H.normwise(fb.state(i), keep.state()) <= H.REL_TOL and H.normwise(fb.cov(i), keep.cov()) <= H.REL_TOL

@@ -215,3 +215,33 @@ def test_naive_filter_kat(oracle):
                       np.remainder(x[2] + float(fwd) * 0 + float(ang) + np.pi, 2 * np.pi) - np.pi])
     assert f.n == 3 and f.timestep == 40
     assert np.abs(f.state() - x).max() <= 1e-12
+
+
+def test_tsp_trajectory_c_vs_python_workload(oracle):
+    """generate_trajectory (sim_node.py:63-152): the C restatement against the independently written Python one
+    (live_ekf_slam_b200/workload.py) fed the same Philox uniforms for the map noise."""
+    from live_ekf_slam_b200 import workload as wl
+    p = H.Params()
+    op = H.oracle_params(oracle, p)
+    lm = wl.grid_map_5x10()
+    seed, inst, T = 2024, 17, 600
+
+    class PhiloxStream:                      # the draws of the C generator in the order the Python one consumes them
+        def __init__(self):
+            self.i, self.half = 0, 0
+        def random(self):
+            rn = oracle.philox(inst, self.i, 0, 1, seed & 0xFFFFFFFF, seed >> 32)
+            v = oracle.uniform(rn[0], rn[1]) if self.half == 0 else oracle.uniform(rn[2], rn[3])
+            self.half ^= 1
+            if self.half == 0:
+                self.i += 1
+            return v
+
+    fc, ac = oracle.tsp_trajectory(op, lm, p.landmark_noise, p.visitation_threshold, p.map_bound, p.init_pose, T, seed, inst)
+    fp, ap = wl.tsp_trajectory(lm, p, PhiloxStream(), T)
+    # sqrt vs ** (1/2) (deviation D-4) can flip the last float32 bit of a few commands
+    assert np.abs(fc - fp).max() <= 1e-7 and np.abs(ac - ap).max() <= 1e-7
+    assert (fc != fp).sum() + (ac != ap).sum() <= 4
+    assert fc.max() <= np.float32(p.d_max) and np.abs(ac).max() <= np.float32(p.th_max)
+    f2, a2 = oracle.tsp_trajectory(op, lm, p.landmark_noise, p.visitation_threshold, p.map_bound, p.init_pose, T, seed, inst + 1)
+    assert not np.array_equal(ac, a2)                                   # per-instance tours differ
