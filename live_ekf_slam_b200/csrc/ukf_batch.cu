@@ -357,6 +357,16 @@ __device__ void ql_serial(double* A, const int lds, const int n, double* d, doub
 // ---------------------------------------------------------------------------------------------------------
 constexpr int QL_LANES = 32;
 
+// 1/sqrt(x) for normal positive x to ~1 ulp: rsqrt.approx.ftz.f64 (relative error < 2^-22.9) refined by one third-order step
+// y (1 + e/2 + 3 e^2 / 8), e = 1 - x y^2: four dependent FP64 operations instead of the library routine's two Newton steps
+// plus range fix-ups (the arguments here are sums of squares of matrix entries, never subnormal).
+__device__ __forceinline__ double ql_rsqrt(const double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-(x * y), y, 1.0);
+    return fma(y * e, fma(0.375, e, 0.5), y);
+}
+
 // SMEM = false: (d, e) are worked on in place in the HBM scratch ([k][instance], coalesced over the lanes, L1/L2 cached; the
 // operands of a rotation are fetched one rotation ahead), so the kernel needs no shared memory and its 32-thread CTAs
 // co-reside with the other slices' front / back kernels.  On overflow dg / eg are then clobbered: only for callers that
@@ -424,12 +434,16 @@ ukf_ql_kernel(UkfScratch u, const int4* __restrict__ meta, const int batch, cons
                 c3 = c2; c2 = c; s2 = s;
                 g = c * e_i;
                 h = c * pp;
-                const double rr = pp * pp + e_i * e_i;
-                const double rinv = rsqrt(rr);
+                // The rotation chain is the critical path of the whole kernel (one thread per instance, nothing to overlap
+                // with): pp -> rr -> 1/sqrt(rr) -> pp'.  u is off the chain (it only needs the previous c), so the new pp is ONE
+                // multiply after the reciprocal square root, and that is a 23-bit hardware seed + one cubically convergent step.
+                const double rr = fma(pp, pp, e_i * e_i);
+                const double u = fma(pp, d_i, -(e_i * g));          // = r * (c' d_i - s' g)
+                const double rinv = ql_rsqrt(rr);
                 E_(i + 1) = s * (rr * rinv);
                 s = e_i * rinv;
                 c = pp * rinv;
-                pp = c * d_i - s * g;
+                pp = u * rinv;
                 D_(i + 1) = h + s * (c * g + s * d_i);
                 rot[nrot++] = make_double2(c, s);
             }

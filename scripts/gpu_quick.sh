@@ -1,3 +1,10 @@
 #!/bin/bash
 set -u
-timeout 900 python -m pytest tests/test_gpu_sim_parity.py tests/test_abi.py -m gpu -x -q 2>&1 | tail -12
+O=gpurun_out/r01g
+mkdir -p $O
+timeout 1500 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
+tail -6 $O/pytest_gpu.log
+timeout 600 python scripts/quick_bench.py 4096 1000 ukf 1 2 1 2>&1 | tail -1 | tee $O/quick_ukf.txt
+U="python bench.py --filter ukf --steps 1 --warmup 3 --filter-steps 1000 --no-e2e --no-cpu-baseline"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 7600 -c 160 --csv --log-file $O/launches_ukf.csv $U > $O/ncu_launch_ukf.log 2>&1
+python scripts/ncu_summary.py launch $O/launches_ukf.csv $O/launches_ukf.txt; cat $O/launches_ukf.txt

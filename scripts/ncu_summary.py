@@ -39,9 +39,10 @@ def full(rep, out):
         src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-skip", "0", "--launch-count", "1"],
                              capture_output=True, text=True).stdout
         srows = list(csv.reader(io.StringIO(src)))
-        if len(srows) > 2:
-            h = srows[1]
-            body = [r for r in srows[2:] if len(r) == len(h)]
+        hi = next((k for k, r in enumerate(srows) if "# Samples" in r), None)
+        if hi is not None:
+            h = srows[hi]
+            body = [r for r in srows[hi + 1:] if len(r) == len(h) and r != h and (r[h.index("# Samples")] or "0").isdigit()]
             stalls = [c for c in h if c.startswith("stall_") and "Not Issued" not in c]
             tot = {s: sum(int(r[h.index(s)] or 0) for r in body) for s in stalls}
             n = sum(int(r[h.index("# Samples")] or 0) for r in body)

@@ -200,7 +200,7 @@ def test_edge_cases(shim, oracle):
     assert fb.status(0) & shim.STATUS_MEAS_OVERFLOW
     # (d) invalid filter choice fails loudly (localization_node.cpp:44)
     with pytest.raises(shim.SlamError):
-        shim.FilterBatch(2, p.to_c(), 1, 2, 2)
+        shim.FilterBatch(4, p.to_c(), 1, 2, 2)             # 4 = POSE_GRAPH_SLAM: not on the B200 path (localization_node.cpp:44)
 
 
 def test_same_step_rematch_is_flagged(shim, oracle):
