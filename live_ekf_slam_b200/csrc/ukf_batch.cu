@@ -970,7 +970,8 @@ struct UkfWarpSmem {
     double* x;      // prior x_t
     double* xp;     // running x_pred
     double* sq;     // sqrt(max(d, 1e-8))
-    double* Xp;     // [4][nsm] propagated vehicle rows of the sigma points
+    double* Xp;     // [2][nsm] propagated vehicle rows x, y of the sigma points
+    float* Xcs;     // [2][nsm] rows cos, sin: float VALUES in the reference (ukf.cpp:132-133), stored as such (lossless)
     double* z;      // [2][nsm] z / dz of the update being prepared
     double* upd;    // [max_meas][UPD_LD]
     double2* stage; // [2 + 64 + 2] rotation-log ring (spare entries for the prefetch overrun)
@@ -988,8 +989,9 @@ __host__ __device__ inline size_t ukf_warp_carve(const BatchState& b, const int 
     const int nmp = ldg_of(b.n_max), nsm = 2 * b.n_max + 2;
     size_t oW = take(sizeof(double) * (size_t)(b.n_max + 4) * wld);
     size_t ox = take(sizeof(double) * nmp), oxp = take(sizeof(double) * nmp), osq = take(sizeof(double) * nmp);
-    size_t oXp = take(sizeof(double) * 4 * nsm), oz = take(sizeof(double) * 2 * nsm);
-    size_t oupd = take(sizeof(double) * UPD_LD * (b.max_meas > 0 ? b.max_meas : 1));
+    size_t oXp = take(sizeof(double) * 2 * nsm), oXcs = take(sizeof(float) * 2 * nsm), oz = take(sizeof(double) * 2 * nsm);
+    int nupd = (wld - 5) / 2; if (nupd > b.max_meas) nupd = b.max_meas; if (nupd < 1) nupd = 1;     // updates a tile of this pitch can hold
+    size_t oupd = take(sizeof(double) * UPD_LD * nupd);
     size_t ostage = take(sizeof(double2) * 68);
     size_t ocorr = take(sizeof(double) * 32), oclip = take(sizeof(int) * 32);
     size_t oids = take(sizeof(int) * (b.max_lm + 1));
@@ -998,7 +1000,7 @@ __host__ __device__ inline size_t ukf_warp_carve(const BatchState& b, const int 
     size_t ouq = take(sizeof(int) * (b.max_meas > 0 ? b.max_meas : 1));
     if (s) {
         s->W = (double*)(base + oW) + 2 * wld; s->x = (double*)(base + ox); s->xp = (double*)(base + oxp); s->sq = (double*)(base + osq);
-        s->Xp = (double*)(base + oXp); s->z = (double*)(base + oz); s->upd = (double*)(base + oupd);
+        s->Xp = (double*)(base + oXp); s->Xcs = (float*)(base + oXcs); s->z = (double*)(base + oz); s->upd = (double*)(base + oupd);
         s->stage = (double2*)(base + ostage) + 2; s->corr = (double*)(base + ocorr); s->clip = (int*)(base + oclip);
         s->ids = (int*)(base + oids); s->meas = (float*)(base + omeas); s->assoc = (int*)(base + oassoc); s->uq = (int*)(base + ouq);
     }
@@ -1382,10 +1384,11 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
         s.Xp[1 * nsm + i] = X[1] + (double)(ud * sin_f(yaw));              // :130
         const float fsum = yaw + u_th + fc.v_th;
         const float new_yaw = (float)remainder((double)fsum, TWO_PI_REF);  // :131
-        s.Xp[2 * nsm + i] = (double)cos_f(new_yaw);                        // :132
-        s.Xp[3 * nsm + i] = (double)sin_f(new_yaw);                        // :133
+        s.Xcs[0 * nsm + i] = cos_f(new_yaw);                               // :132
+        s.Xcs[1 * nsm + i] = sin_f(new_yaw);                               // :133
     }
     __syncwarp();
+    auto XP = [&](const int r, const int i) -> double { return r < 2 ? s.Xp[r * nsm + i] : (double)s.Xcs[(r - 2) * nsm + i]; };
     // ---- mean (:228-232): vehicle rows by reduction, landmark rows analytically (sum w) * x
     double xp0v[4];
     {
@@ -1393,7 +1396,7 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
         for (int i = lane; i < ns; i += 32) {
             const double wi = (i == 0) ? W0 : wgt;
 #pragma unroll
-            for (int r = 0; r < 4; ++r) acc[r] += wi * s.Xp[r * nsm + i];
+            for (int r = 0; r < 4; ++r) acc[r] += wi * XP(r, i);
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) xp0v[r] = warp_sum(acc[r]);
@@ -1409,7 +1412,7 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
             const double wi = (i == 0) ? W0 : wgt;
             double dv[4];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) dv[r] = s.Xp[r * nsm + i] - xp0v[r];
+            for (int r = 0; r < 4; ++r) dv[r] = XP(r, i) - xp0v[r];
             int q = 0;
 #pragma unroll
             for (int a = 0; a < 4; ++a)
@@ -1464,7 +1467,7 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
             acc[3] += wi * d0; acc[4] += wi * d1;
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
-                const double wd = wi * (s.Xp[a * nsm + i] - xp0v[a]);       // about the predicted mean; the running
+                const double wd = wi * (XP(a, i) - xp0v[a]);                // about the predicted mean; the running
                 acc[5 + 2 * a] += wd * d0; acc[6 + 2 * a] += wd * d1;       // x_pred enters below as a rank-1 shift
             }
         }
@@ -1499,7 +1502,7 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
     // g_a[i] = Xp[a][1+i] - Xp[a][1+n+i] -> lanes 0..3
     for (int i = lane; i < n; i += 32)
 #pragma unroll
-        for (int a = 0; a < 4; ++a) W_[i * wld + a] = s.Xp[a * nsm + 1 + i] - s.Xp[a * nsm + 1 + n + i];
+        for (int a = 0; a < 4; ++a) W_[i * wld + a] = XP(a, 1 + i) - XP(a, 1 + n + i);
     __syncwarp();
 
     // ---- pass B: S g_a and S hv for every update; the clipped eigenvectors stay put in their lanes

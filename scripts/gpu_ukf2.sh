@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-O=gpurun_out/r01f
+O=gpurun_out/r01g
 mkdir -p $O
 timeout 1200 python -m pytest tests/test_gpu_ukf_parity.py tests/test_gpu_loc_naive.py -m gpu -x -q > $O/pytest_ukf.log 2>&1; echo "pytest rc=$?" >> $O/pytest_ukf.log
 tail -8 $O/pytest_ukf.log
