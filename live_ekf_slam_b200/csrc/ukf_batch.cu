@@ -972,7 +972,6 @@ struct UkfWarpSmem {
     double* sq;     // sqrt(max(d, 1e-8))
     double* Xp;     // [2][nsm] propagated vehicle rows x, y of the sigma points
     float* Xcs;     // [2][nsm] rows cos, sin: float VALUES in the reference (ukf.cpp:132-133), stored as such (lossless)
-    double* z;      // [2][nsm] z / dz of the update being prepared
     double* upd;    // [max_meas][UPD_LD]
     double2* stage; // [2 + 64 + 2] rotation-log ring (spare entries for the prefetch overrun)
     double* corr;   // [32] 1e-8 - d_k of the clipped eigenvalues
@@ -989,7 +988,7 @@ __host__ __device__ inline size_t ukf_warp_carve(const BatchState& b, const int 
     const int nmp = ldg_of(b.n_max), nsm = 2 * b.n_max + 2;
     size_t oW = take(sizeof(double) * (size_t)(b.n_max + 4) * wld);
     size_t ox = take(sizeof(double) * nmp), oxp = take(sizeof(double) * nmp), osq = take(sizeof(double) * nmp);
-    size_t oXp = take(sizeof(double) * 2 * nsm), oXcs = take(sizeof(float) * 2 * nsm), oz = take(sizeof(double) * 2 * nsm);
+    size_t oXp = take(sizeof(double) * 2 * nsm), oXcs = take(sizeof(float) * 2 * nsm);
     int nupd = (wld - 5) / 2; if (nupd > b.max_meas) nupd = b.max_meas; if (nupd < 1) nupd = 1;     // updates a tile of this pitch can hold
     size_t oupd = take(sizeof(double) * UPD_LD * nupd);
     size_t ostage = take(sizeof(double2) * 68);
@@ -1000,7 +999,7 @@ __host__ __device__ inline size_t ukf_warp_carve(const BatchState& b, const int 
     size_t ouq = take(sizeof(int) * (b.max_meas > 0 ? b.max_meas : 1));
     if (s) {
         s->W = (double*)(base + oW) + 2 * wld; s->x = (double*)(base + ox); s->xp = (double*)(base + oxp); s->sq = (double*)(base + osq);
-        s->Xp = (double*)(base + oXp); s->Xcs = (float*)(base + oXcs); s->z = (double*)(base + oz); s->upd = (double*)(base + oupd);
+        s->Xp = (double*)(base + oXp); s->Xcs = (float*)(base + oXcs); s->upd = (double*)(base + oupd);
         s->stage = (double2*)(base + ostage) + 2; s->corr = (double*)(base + ocorr); s->clip = (int*)(base + oclip);
         s->ids = (int*)(base + oids); s->meas = (float*)(base + omeas); s->assoc = (int*)(base + oassoc); s->uq = (int*)(base + ouq);
     }
@@ -1239,7 +1238,7 @@ ukf_front2_kernel(BatchState b, UkfScratch u, const int i0) {
 
 // ---- launch 3 of 3 (generation 2): warp per instance
 template <int wld>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, 10)        // ten one-warp CTAs per SM: <= 200 registers per thread
 ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, const int i0, const int pass) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     UkfWarpSmem s;
@@ -1439,36 +1438,48 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
         const int l = s.uq[q];
         const int li = fc.loc ? 0 : s.assoc[l] * 2 + 4;                     // :298
         const int c0 = 4 + 2 * q;
-        double* z0 = s.z;
-        double* z1 = s.z + nsm;
-        for (int i = lane; i < ns; i += 32) {                               // sensingModel per sigma point (:305-308)
-            double lx, ly;
-            if (fc.loc) { lx = (double)fc.map[3 * s.assoc[l] + 1]; ly = (double)fc.map[3 * s.assoc[l] + 2]; }   // :152-153 (true map, float)
-            else {
-                lx = s.x[li]; ly = s.x[li + 1];
-                if (i >= 1 && i <= n) { lx += W_[(i - 1) * wld + c0]; ly += W_[(i - 1) * wld + c0 + 1]; }
-                else if (i > n) { lx -= W_[(i - 1 - n) * wld + c0]; ly -= W_[(i - 1 - n) * wld + c0 + 1]; }
-            }
+        // sensingModel of sigma point i (:305-308); sgn / row select the column of S it was built from (0: the mean point)
+        const double mlx = fc.loc ? (double)fc.map[3 * s.assoc[l] + 1] : s.x[li];             // :152-153 (true map, float) / :144
+        const double mly = fc.loc ? (double)fc.map[3 * s.assoc[l] + 2] : s.x[li + 1];
+        auto sense = [&](const int i, const double sgn, const int row, double& a0, double& a1) {
+            double lx = mlx, ly = mly;
+            if (!fc.loc && sgn != 0.0) { lx += sgn * W_[row * wld + c0]; ly += sgn * W_[row * wld + c0 + 1]; }
             const double dx = lx - s.Xp[0 * nsm + i], dy = ly - s.Xp[1 * nsm + i];
-            z0[i] = sqrt(dx * dx + dy * dy) + (double)fc.w_r;               // :144
-            z1[i] = remainder(atan2(dy, dx) - (double)yaw_prior + (double)fc.w_b, TWO_PI_REF);   // :145,156
-        }
-        __syncwarp();
+            a0 = sqrt(dx * dx + dy * dy) + (double)fc.w_r;                  // :144
+            a1 = remainder(atan2(dy, dx) - (double)yaw_prior + (double)fc.w_b, TWO_PI_REF);   // :145,156
+        };
+        // The measurement predictions are not stored (their 3.4 KB per instance is what separated 9 from 10 instances per
+        // SM, i.e. four from three rounds of CTAs): a first pass gives the range mean (:312-314), a second one recomputes
+        // them pair by pair -- lane i owns sigma points 1 + i and 1 + n + i, so dz_i - dz_{i+n} never leaves the lane.
         double zest0 = 0.0;
-        for (int i = lane; i < ns; i += 32) zest0 += ((i == 0) ? W0 : wgt) * z0[i];   // :312-314
+        for (int i = lane; i < ns; i += 32) {
+            double a0, a1;
+            sense(i, i == 0 ? 0.0 : (i <= n ? 1.0 : -1.0), i <= n ? i - 1 : i - 1 - n, a0, a1);
+            zest0 += ((i == 0) ? W0 : wgt) * a0;
+        }
         zest0 = warp_sum(zest0);
         double acc[13] = {0};
-        for (int i = lane; i < ns; i += 32) {
-            const double wi = (i == 0) ? W0 : wgt;
-            const double d0 = z0[i] - zest0;
-            const double d1 = remainder(z1[i] - 0.0, TWO_PI_REF);           // z_est(1) is never accumulated (:310-314,321)
-            z0[i] = d0; z1[i] = d1;
+        auto accum = [&](const int i, const double wi, const double a0, const double a1, double& d0, double& d1) {
+            d0 = a0 - zest0;
+            d1 = remainder(a1 - 0.0, TWO_PI_REF);                           // z_est(1) is never accumulated (:310-314,321)
             acc[0] += (wi * d0) * d0; acc[1] += (wi * d0) * d1; acc[2] += (wi * d1) * d1;
             acc[3] += wi * d0; acc[4] += wi * d1;
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
                 const double wd = wi * (XP(a, i) - xp0v[a]);                // about the predicted mean; the running
                 acc[5 + 2 * a] += wd * d0; acc[6 + 2 * a] += wd * d1;       // x_pred enters below as a rank-1 shift
+            }
+        };
+        if (lane == 0) { double a0, a1, d0, d1; sense(0, 0.0, 0, a0, a1); accum(0, W0, a0, a1, d0, d1); }
+        for (int i = lane; i < n; i += 32) {
+            double a0, a1, b0, b1, da0, da1, db0, db1;
+            sense(1 + i, 1.0, i, a0, a1);
+            sense(1 + n + i, -1.0, i, b0, b1);
+            accum(1 + i, wgt, a0, a1, da0, da1);
+            accum(1 + n + i, wgt, b0, b1, db0, db1);
+            if (!fc.loc) {                                                  // hv overwrites the S rows this lane just read
+                W_[i * wld + c0] = da0 - db0;
+                W_[i * wld + c0 + 1] = da1 - db1;
             }
         }
 #pragma unroll
@@ -1492,10 +1503,6 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
             ud[13] = i00; ud[14] = i01; ud[15] = i10; ud[16] = i11;
             ud[17] = (double)s.meas[3 * l + 1] - zest0;                                   // innovation (:342-344)
             ud[18] = remainder((double)s.meas[3 * l + 2] - 0.0, TWO_PI_REF);
-        }
-        if (!fc.loc) for (int i = lane; i < n; i += 32) {                   // (localisation: the state has no landmark rows)
-            W_[i * wld + c0] = z0[1 + i] - z0[1 + n + i];
-            W_[i * wld + c0 + 1] = z1[1 + i] - z1[1 + n + i];
         }
         __syncwarp();
     }
