@@ -484,6 +484,8 @@ def main():
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/)")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: if the environment turns NCCL's banner on (NCCL_DEBUG=VERSION|INFO), send it to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.ref_instances_per_core <= 0:
         args.ref_instances_per_core = 16 if args.filter == "ekf" else 8
     if args.warmup < 3 and args.impl == "ours":
