@@ -484,7 +484,10 @@ def main():
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/)")
     args = ap.parse_args()
-    # stdout carries exactly one JSON line: if the environment turns NCCL's banner on (NCCL_DEBUG=VERSION|INFO), send it to stderr
+    # stdout carries exactly one JSON line: NCCL_DEBUG=VERSION (set in this image) makes NCCL print its banner on stdout
+    # whatever NCCL_DEBUG_FILE says, so the banner is switched off; INFO / TRACE logs are sent to stderr
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.ref_instances_per_core <= 0:
         args.ref_instances_per_core = 16 if args.filter == "ekf" else 8
