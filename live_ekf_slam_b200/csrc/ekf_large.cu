@@ -347,9 +347,18 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, const double
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+// 16-byte global -> shared copy without a register round trip (LDGSTS); bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, const int bytes) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(sa), "l"(gsrc), "r"(bytes) : "memory");
+}
+constexpr size_t LM_GEMM_SMEM = sizeof(double) * 2 * (GT * GLDA + GK * GLDB);   // two stages of (A tile, B tile)
+
+// P <- P + U G on the FP64 tensor cores (DMMA m8n8k4), 64 x 64 tile of P per CTA, K = 2 (updates of the step) in chunks of
+// 32 staged through a two-deep cp.async pipeline: the next chunk's U / G tiles stream into shared memory while the current
+// one feeds the tensor cores (ncu of the synchronous version: long-scoreboard stalls 40 % of the samples at 12 warps per SM).
 __global__ void __launch_bounds__(128) lm_gemm(LargeState L) {
-    __shared__ double sA[GT * GLDA];    // [row][k]
-    __shared__ double sB[GK * GLDB];    // [k][col]
+    extern __shared__ __align__(16) double lm_gemm_smem[];
     const int m = L.cur[0];
     const int n = 3 + 2 * L.cur[1];
     if (m == 0) return;
@@ -360,6 +369,35 @@ __global__ void __launch_bounds__(128) lm_gemm(LargeState L) {
     const int ld = L.ld;
     const size_t ustride = (size_t)L.n_max * 2, gstride = (size_t)2 * ld;
     const int g = lane >> 2, t4 = lane & 3;
+    const int K2 = 2 * m;
+    const int nchunk = (K2 + GK - 1) / GK;
+    // stage chunk c into buffer b: A = U[rows row0..+64][k0..k0+32) as 16-byte (k even, k odd) pairs, contiguous over the rows
+    // of one update; B = G[k0..k0+32)[cols col0..+64) as 16-byte column pairs
+    auto stage = [&](const int c, const int bsel) {
+        double* sA = lm_gemm_smem + (size_t)bsel * (GT * GLDA + GK * GLDB);
+        double* sB = sA + GT * GLDA;
+        const int k0 = c * GK;
+#pragma unroll
+        for (int j = 0; j < (GT * GK / 2) / 128; ++j) {
+            const int e = tid + 128 * j;
+            const int kp = e >> 6, r = e & 63;                 // update pair index within the chunk, row
+            const int kk = k0 + 2 * kp, gr = row0 + r;
+            const bool ok = kk < K2 && gr < n;
+            const double* src = ok ? L.U + (size_t)(kk >> 1) * ustride + 2 * (size_t)gr : L.U;
+            cp_async16(sA + r * GLDA + 2 * kp, src, ok ? 16 : 0);
+        }
+#pragma unroll
+        for (int j = 0; j < (GK * GT / 2) / 128; ++j) {
+            const int e = tid + 128 * j;
+            const int k = e >> 5, cp = e & 31;                 // k within the chunk, column pair
+            const int kk = k0 + k, gc = col0 + 2 * cp;
+            const bool ok = kk < K2 && gc < n;
+            const double* src = ok ? L.G + (size_t)(kk >> 1) * gstride + (size_t)(kk & 1) * ld + gc : L.G;
+            cp_async16(sB + k * GLDB + 2 * cp, src, ok ? 16 : 0);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(0, 0);
     double acc[4][4][2];
     // C fragments: row = g, cols = 2*t4, 2*t4+1 within each 8x8 tile
 #pragma unroll
@@ -370,24 +408,16 @@ __global__ void __launch_bounds__(128) lm_gemm(LargeState L) {
             acc[a][bq][0] = (r < n && c < n) ? L.P[(size_t)r * ld + c] : 0.0;
             acc[a][bq][1] = (r < n && c + 1 < n) ? L.P[(size_t)r * ld + c + 1] : 0.0;
         }
-    const int K2 = 2 * m;
-    for (int k0 = 0; k0 < K2; k0 += GK) {
-        // stage A = U[rows row0..+64][k0..k0+32) and B = G[k0..k0+32)[cols col0..+64)
-        for (int e = tid; e < GT * GK; e += 128) {
-            const int r = e / GK, k = e - r * GK;
-            const int kk = k0 + k, gr = row0 + r;
-            double v = 0.0;
-            if (kk < K2 && gr < n) v = L.U[(size_t)(kk >> 1) * ustride + 2 * (size_t)gr + (kk & 1)];
-            sA[r * GLDA + k] = v;
-        }
-        for (int e = tid; e < GK * GT; e += 128) {
-            const int k = e / GT, c = e - k * GT;
-            const int kk = k0 + k, gc = col0 + c;
-            double v = 0.0;
-            if (kk < K2 && gc < n) v = L.G[(size_t)(kk >> 1) * gstride + (size_t)(kk & 1) * ld + gc];
-            sB[k * GLDB + c] = v;
+    for (int c = 0; c < nchunk; ++c) {
+        if (c + 1 < nchunk) {
+            stage(c + 1, (c + 1) & 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
+        const double* sA = lm_gemm_smem + (size_t)(c & 1) * (GT * GLDA + GK * GLDB);
+        const double* sB = sA + GT * GLDA;
 #pragma unroll
         for (int ks = 0; ks < GK; ks += 4) {
             double af[4], bf[4];
@@ -459,7 +489,13 @@ cudaError_t launch_ekf_large_step(const LargeState& L, const FilterConst& fc, co
         e = cudaLaunchCooperativeKernel((const void*)lm_front, dim3(gm), dim3(LM_THREADS), args, 0, st);
         if (e != cudaSuccess) return e;
         const int gt = (n_upper + GT - 1) / GT;
-        lm_gemm<<<dim3(gt, gt), 128, 0, st>>>(L);
+        static bool gemm_configured = false;        // 72 KB of dynamic shared memory (two pipeline stages) needs the opt-in
+        if (!gemm_configured) {
+            e = cudaFuncSetAttribute(lm_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_GEMM_SMEM);
+            if (e != cudaSuccess) return e;
+            gemm_configured = true;
+        }
+        lm_gemm<<<dim3(gt, gt), 128, LM_GEMM_SMEM, st>>>(L);
         *launches += 2;
     }
     lm_commit<<<gb, tb, 0, st>>>(L, n_meas);
