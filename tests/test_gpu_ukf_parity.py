@@ -245,3 +245,28 @@ def test_ukf_narrow_tile_hand_over(shim, oracle):
             assert list(fb.assoc(i)) == list(ofs[i].assoc_log())
             _compare(fb, i, ofs[i])
     assert (fb.all_status() == 0).all() and fb.num_landmarks(0) == 6
+
+
+@pytest.mark.parametrize("max_lm,max_meas", [(70, 8), (70, 16)], ids=["n_max_144_generation2", "max_meas_16_generation1_fallback"])
+def test_ukf_capacity_variants(shim, oracle, max_lm, max_meas):
+    """Handle capacities beyond the benchmark's: n_max = 144 takes the 8-row-slot reflector products of generation 2;
+    max_meas = 16 exceeds the lanes of the generation-2 tile, so the library falls back to the generation-1 kernels."""
+    p, lm, fwd, ang = H.config2(seed=8, steps=90, filt="ukf_slam")
+    op = H.oracle_params(oracle, p)
+    B = 3
+    fb = shim.FilterBatch(shim.UKF_SLAM, p.to_c(), B, max_lm, max_meas)
+    fb.init(0, 0, 0)
+    streams = [H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=12, instance=i)[0] for i in range(B)]
+    ofs = []
+    for i in range(B):
+        of = oracle.OracleFilter(oracle.UKF_SLAM, op, max_lm)
+        of.init(0, 0, 0)
+        ofs.append(of)
+    for t in range(len(fwd)):
+        meas, n = fb.pack_meas([streams[i][t] for i in range(B)])
+        fb.step(fwd[t], ang[t], meas, n)
+        for i in range(B):
+            ofs[i].update(fwd[t], ang[t], streams[i][t], oracle.STRUCTURED)
+    worst = max(_compare(fb, i, ofs[i]) for i in range(B))
+    assert (fb.all_status() == 0).all() and ofs[0].M >= 4
+    print("ukf capacity variant", max_lm, max_meas, "worst", worst)
