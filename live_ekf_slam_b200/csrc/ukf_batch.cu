@@ -16,7 +16,10 @@
 // the UKF batch is FP64-compute bound, not HBM bound.  P stays in global memory (L2) with a fixed
 // leading dimension; only Z lives in shared memory, which lets two CTAs share an SM.
 //
-// A step is THREE launches, split where the parallelism changes shape:
+// Two generations of the step live here.  Generation 2 (default; second half of the file) never forms the eigenvector
+// matrix: front2 (tridiagonalisation only) -> ukf_ql_kernel -> back2 (warp per instance; S*v through the reflectors and
+// the rotation log), with the generation-1 kernels below kept as its rescue pass and as the fall-back for handle
+// capacities the generation-2 tile cannot hold.  Generation 1 is THREE launches, split where the parallelism changes shape:
 //   ukf_front_kernel  CTA per instance: Y, Householder tridiagonalisation, explicit Q^T  -> HBM scratch (d, e, Q^T)
 //   ukf_ql_kernel     THREAD per instance: implicit QL on (d, e) -- a serial chain of ~0.85 n^2 plane rotations, each a
 //                     dependent rsqrt; one lane per filter runs thousands of these chains side by side instead of
