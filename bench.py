@@ -333,6 +333,7 @@ def run_ours(args):
     loc = fb.stats()
     step_roof = {"bound": "hbm", "kernel": kname, "achieved": loc[8] / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0,
                  "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": args.traffic_bytes,
+                 "traffic_source": "ncu --set full capture of a late launch (n ~ 97), profiles/r01d_ekf_step_full.txt" if args.traffic_bytes else None,
                  "algorithmic_bytes_per_launch": loc[8] / max(k_n, 1), "kernel_ms_per_launch": k_ms / max(k_n, 1),
                  "launches_timed": int(k_n), "mean_n": loc[10] / max(loc[0], 1), "mean_k": loc[11] / max(loc[0], 1),
                  "algorithmic_gflops": loc[9] / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0}
@@ -349,6 +350,9 @@ def run_ours(args):
         ach = loc2[8] / (s_ms * 1e-3) / 1e9 if s_ms > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": "ekf_sweep_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "peak_source": peak_src, "traffic": args.sweep_traffic_bytes,
+                    "traffic_source": ("ncu --set full capture of a late launch, profiles/r01d_ekf_sweep_full.txt: far below the "
+                                       "streaming-model bytes because P stays in shared memory across the steps of a launch")
+                                      if args.sweep_traffic_bytes else None,
                     "algorithmic_bytes_per_launch": loc2[8] / max(s_n, 1), "kernel_ms_per_launch": s_ms / max(s_n, 1),
                     "launches_timed": int(s_n), "kernel_share_of_sweep": s_ms / (ms / K) if ms > 0 else None,
                     "mean_n": loc2[10] / max(loc2[0], 1), "mean_k": loc2[11] / max(loc2[0], 1),
@@ -480,15 +484,23 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-traffic-bytes", type=float, default=None,
-                    help="dram bytes per launch of ekf_sweep_kernel from the committed ncu capture (profiles/)")
+                    help="dram bytes per launch of ekf_sweep_kernel from an ncu --set full capture (default: the committed one)")
     ap.add_argument("--traffic-bytes", type=float, default=None,
-                    help="dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/)")
+                    help="dram bytes per launch of the per-step kernel from an ncu --set full capture (default: the committed one)")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: NCCL_DEBUG=VERSION (set in this image) makes NCCL print its banner on stdout
     # whatever NCCL_DEBUG_FILE says, so the banner is switched off; INFO / TRACE logs are sent to stderr
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the default
+    # EKF configuration (late launches of the first sweep, 4096 instances): profiles/r01d_ekf_sweep_full.txt
+    # (146.35 + 90.59 MB) and profiles/r01d_ekf_step_full.txt (160.15 + 99.47 MB)
+    if args.filter == "ekf" and args.instances == 4096 and args.filter_steps == 1000:
+        if args.sweep_traffic_bytes is None:
+            args.sweep_traffic_bytes = 146.353152e6 + 90.594816e6
+        if args.traffic_bytes is None:
+            args.traffic_bytes = 160.148224e6 + 99.465216e6
     if args.ref_instances_per_core <= 0:
         args.ref_instances_per_core = 16 if args.filter == "ekf" else 8
     if args.warmup < 3 and args.impl == "ours":
