@@ -245,3 +245,17 @@ def test_tsp_trajectory_c_vs_python_workload(oracle):
     assert fc.max() <= np.float32(p.d_max) and np.abs(ac).max() <= np.float32(p.th_max)
     f2, a2 = oracle.tsp_trajectory(op, lm, p.landmark_noise, p.visitation_threshold, p.map_bound, p.init_pose, T, seed, inst + 1)
     assert not np.array_equal(ac, a2)                                   # per-instance tours differ
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+@pytest.mark.parametrize("known", [True, False])
+def test_ekf_c_vs_numpy_more_seeds(oracle, seed, known):
+    """More trajectories / noise streams for the two independent restatements (known and unknown association)."""
+    worst, f = _run_pair(oracle, oracle.EKF_SLAM, oracle_np.EKFNP, 140, seed=seed, known=known)
+    assert worst <= 1e-12 and f.M >= 4
+
+
+@pytest.mark.parametrize("seed", [21, 22])
+def test_ukf_c_vs_numpy_more_seeds(oracle, seed):
+    worst, f = _run_pair(oracle, oracle.UKF_SLAM, oracle_np.UKFNP, 90, seed=seed)
+    assert worst <= 1e-11 and f.M >= 3
