@@ -108,7 +108,12 @@ int  slam_get_state_vector(slam_handle_t h, int inst, double* xv, int* n);  /* (
 int  slam_get_cov(slam_handle_t h, int inst, double* P_rowmajor, int* n);   /* n*n row-major (ekf.cpp:211-217) */
 int  slam_get_landmark_ids(slam_handle_t h, int inst, int* ids, int* M);    /* lm_IDs, filter.h:70 */
 int  slam_get_assoc(slam_handle_t h, int inst, int* slot, int* k);          /* last step: slot index or -1 (new) per measurement */
-int  slam_get_sigma_points(slam_handle_t h, int inst, double* X, int* n);   /* UKF X, point-major (ukf.cpp:91-99) */
+/* UKF sigma points of the last update() (ukf.cpp:214-220), flattened point-major exactly as UKFState.X is filled
+ * (ukf.cpp:91-99): X[j*n + i] = component i of sigma point j, j = 0..2n, with n = 4 + 2M of that update's PRIOR (the
+ * matrix keeps the size it had when the step started, ukf.cpp:167-171).  X must hold (4 + 2 max_landmarks) *
+ * (2 (4 + 2 max_landmarks) + 1) doubles.  Before the first update: the constructor's 4 x 9 zeros (ukf.cpp:20).
+ * Materialised on demand from the factors the step left on the device; getter-only cost. */
+int  slam_get_sigma_points(slam_handle_t h, int inst, double* X, int* n);
 int  slam_get_poses(slam_handle_t h, double* xyyaw);                        /* [batch][3] vehicle pose estimates */
 int  slam_get_all_status(slam_handle_t h, int* status);                     /* [batch] */
 int  slam_get_all_num_landmarks(slam_handle_t h, int* M);                   /* [batch] */

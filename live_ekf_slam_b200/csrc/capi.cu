@@ -204,6 +204,9 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
         CK(cudaMalloc(&u.nswp, sizeof(int) * batch));
         CK(cudaMalloc(&u.defer, sizeof(int) * batch));
         CK(cudaMemset(u.defer, 0, sizeof(int) * batch));
+        CK(cudaMalloc(&u.xprior, sizeof(double) * (size_t)batch * b.n_max));
+        CK(cudaMalloc(&u.sigfmt, sizeof(int2) * batch));
+        CK(cudaMemset(u.sigfmt, 0, sizeof(int2) * batch));
         u.narrow = 1;
     }
     CK(cudaMalloc(&h->d_fwd, sizeof(float) * batch));
@@ -252,7 +255,7 @@ int slam_destroy(slam_handle_t h) {
     cudaFree(b.P); cudaFree(b.x); cudaFree(b.ids); cudaFree(b.meta);
     cudaFree(b.assoc); cudaFree(b.stats); cudaFree(b.sigma);
     cudaFree(h->d_map);
-    cudaFree(h->uk.Zg); cudaFree(h->uk.Yg); cudaFree(h->uk.dg); cudaFree(h->uk.eg); cudaFree(h->uk.rot); cudaFree(h->uk.swp); cudaFree(h->uk.nswp); cudaFree(h->uk.defer);
+    cudaFree(h->uk.Zg); cudaFree(h->uk.Yg); cudaFree(h->uk.dg); cudaFree(h->uk.eg); cudaFree(h->uk.rot); cudaFree(h->uk.swp); cudaFree(h->uk.nswp); cudaFree(h->uk.defer); cudaFree(h->uk.xprior); cudaFree(h->uk.sigfmt);
     cudaFree(b.retry_list); cudaFree(b.retry_count); cudaFree(b.max_M); cudaFree(h->d_work); cudaFree(h->d_progress);
     if (h->h_run_hint) cudaFreeHost(h->h_run_hint);
     for (int i = 0; i < slam_filter::HINT_RING; ++i) if (h->run_ev[i]) cudaEventDestroy(h->run_ev[i]);
@@ -328,6 +331,7 @@ int slam_init(slam_handle_t h, float x_0, float y_0, float yaw_0) {
     CK(cudaMemsetAsync(b.ids, 0, sizeof(int) * (size_t)b.batch * b.max_lm, h->stream));
     CK(cudaMemsetAsync(b.max_M, 0, sizeof(int), h->stream));
     h->step_seq = 0; h->hint_base = 0;
+    if (h->uk.sigfmt) CK(cudaMemsetAsync(h->uk.sigfmt, 0, sizeof(int2) * b.batch, h->stream));
     CK(cudaMemsetAsync(b.assoc, 0xff, sizeof(int) * (size_t)b.batch * b.max_meas, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
@@ -538,7 +542,25 @@ int slam_get_assoc(slam_handle_t h, int inst, int* slot, int* k) {
 int slam_get_sigma_points(slam_handle_t h, int inst, double* X, int* n) {
     if (check_inst(h, inst)) return 1;
     if (h->kind != SLAM_UKF_SLAM && h->kind != SLAM_UKF_LOC) return fail(h, "slam_get_sigma_points: UKF only");
-    return fail(h, "slam_get_sigma_points: sigma points are not materialised by the batched UKF kernel yet");
+    if (!X) return fail(h, "slam_get_sigma_points: X is NULL");
+    CK(cudaSetDevice(h->device));
+    int2 sf = make_int2(0, 0);
+    CK(cudaMemcpyAsync(&sf, h->uk.sigfmt + inst, sizeof(int2), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (sf.x == 0) {
+        // no update() yet: X is the constructor's 4 x 9 zero matrix (ukf.cpp:20)
+        for (int i = 0; i < 4 * 9; ++i) X[i] = 0.0;
+        if (n) *n = 4;
+        return 0;
+    }
+    const int nn = sf.y;
+    if (!h->b.sigma) CK(cudaMalloc(&h->b.sigma, sizeof(double) * (size_t)h->b.sigma_stride));   // one instance's X
+    CK(launch_ukf_sigma_points(h->b, h->uk, inst, sf.x, nn, h->b.sigma, h->stream));
+    h->launches += 1;
+    CK(cudaMemcpyAsync(X, h->b.sigma, sizeof(double) * (size_t)nn * (2 * nn + 1), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (n) *n = nn;
+    return 0;
 }
 
 int slam_get_poses(slam_handle_t h, double* xyyaw) {
@@ -798,6 +820,7 @@ int slam_reset(slam_handle_t h, float x_0, float y_0, float yaw_0) {
     if (h->b.base == 4) { a2 = (double)(float)std::cos((double)yaw_0); a3 = (double)(float)std::sin((double)yaw_0); }   // ukf.cpp:33 (D-1)
     CK(launch_reset(h->b, (double)x_0, (double)y_0, a2, a3, h->stream));
     CK(cudaMemsetAsync(h->b.max_M, 0, sizeof(int), h->stream));
+    if (h->uk.sigfmt) CK(cudaMemsetAsync(h->uk.sigfmt, 0, sizeof(int2) * h->b.batch, h->stream));
     h->step_seq = 0; h->hint_base = 0;
     h->launches += 1;
     return 0;

@@ -196,6 +196,10 @@ struct UkfScratch {
     int swp_cap;
     int n_max;
     int gen;            // 2 (default): reflector / rotation-log products, warp per instance; 1: explicit eigenvectors
+    double* xprior;     // [batch][n_max]  x_t at the start of the last step: column 0 of the sigma-point matrix X (ukf.cpp:214)
+    int2* sigfmt;       // [batch]  what the scratch holds of the last step's sqrt factor, for slam_get_sigma_points:
+                        //          .x = 0 nothing yet (X is the constructor's 4 x 9 zero matrix, ukf.cpp:20), 2 = reflectors (Zg) +
+                        //          rotation log + eigenvalues (dg), 1 = explicit Z^T (Zg, compact) + sqrt(max(d, 1e-8)) (dg); .y = n
     int clip_lanes;     // test knob: max clipped eigenvectors riding beside pass A (0 = as many as fit)
 };
 // streams / events of the sliced generation-2 step (owned by the handle)
@@ -210,6 +214,8 @@ struct UkfStreams {
 cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, const UkfScratch& u, cudaStream_t st,
                             const UkfStreams& xs, int* launched);
 size_t ukf_step_smem_bytes(const BatchState& b);
+// X of the last UKF step of one instance (ukf.cpp:214-220), point-major n x (2n+1), into the DEVICE buffer d_X; n, fmt from sigfmt
+cudaError_t launch_ukf_sigma_points(const BatchState& b, const UkfScratch& u, int inst, int fmt, int n, double* d_X, cudaStream_t st);
 bool ukf_gen2_supported(const BatchState& b);
 cudaError_t launch_naive_step(const BatchState& b, const StepInputs& in, cudaStream_t st);
 cudaError_t ukf_step_configure(const BatchState& b);

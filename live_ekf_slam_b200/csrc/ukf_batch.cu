@@ -922,9 +922,22 @@ ukf_back_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, const
     for (int i = tid + M_start; i < M; i += UKF_THREADS) b.ids[(size_t)inst * b.max_lm + i] = s.ids[i];
     for (int i = tid; i < nm; i += UKF_THREADS) b.assoc[(size_t)inst * b.max_meas + i] = s.assoc[i];
     __syncthreads();
+    // what slam_get_sigma_points needs of this step (ukf.cpp:214-220): the prior x_t and the factor of S = Z sqrt(D+) Z^T
+    {
+        double* Zg = u.Zg + (size_t)inst * u.n_max * u.n_max;
+        for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
+            const int i = idx / n, j = idx - i * n;
+            Zg[idx] = s.A[(size_t)i * lds + j];
+        }
+        for (int k = tid; k < n; k += UKF_THREADS) {
+            u.dg[(size_t)k * b.batch + inst] = s.d[k];
+            u.xprior[(size_t)inst * u.n_max + k] = s.x[k];
+        }
+    }
     if (tid == 0) {
         if (s.iscr[2]) status |= SLAM_STATUS_NAN;
         b.meta[inst] = make_int4(M, status, meta_in.z + 1, nm);             // timestep, :164
+        u.sigfmt[inst] = make_int2(1, n);
         if (M > M_start) atomicMax(b.max_M, M);
         double* st = b.stats + (size_t)inst * SLAM_NUM_STATS;
         const double nd = (double)n;
@@ -1274,7 +1287,7 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
     const double2* __restrict__ rot = u.rot + (size_t)inst * u.rot_cap;
     const int2* __restrict__ swp = u.swp + (size_t)inst * u.swp_cap;
 
-    for (int i = lane; i < n; i += 32) s.x[i] = gx[i];
+    for (int i = lane; i < n; i += 32) { const double v = gx[i]; s.x[i] = v; u.xprior[(size_t)inst * u.n_max + i] = v; }
     for (int i = lane; i < M; i += 32) s.ids[i] = b.ids[(size_t)inst * b.max_lm + i];
     for (int i = lane; i < 3 * nm; i += 32) s.meas[i] = in.meas[(size_t)inst * b.max_meas * 3 + i];
     // eigenvalues: clip (:120), sqrt, ordered list of the clipped ones; total length of the rotation log
@@ -1627,6 +1640,7 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
     if (lane == 0) {
         if (bad) status |= SLAM_STATUS_NAN;
         b.meta[inst] = make_int4(M, status, meta_in.z + 1, nm);             // timestep, :164
+        u.sigfmt[inst] = make_int2(2, n);                                   // reflectors + rotation log + eigenvalues stay in the scratch
         if (M > M_start) atomicMax(b.max_M, M);
         double* st = b.stats + (size_t)inst * SLAM_NUM_STATS;
         const double nd = (double)n;
@@ -1634,6 +1648,69 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
         st[9] += 9.0 * nd * nd * nd + 2.0 * nd * nd * nd + 2.0 * nd * nd * (2.0 * nd + 1.0) + 12.0 * nu * nd * nd;
         st[10] += nd;
         st[11] += (double)nm;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// slam_get_sigma_points: the matrix X of the last step (ukf.cpp:214-220; published point-major by ukf.cpp:91-99),
+//   X[:,0] = x_t,  X[:,1+c] = x_t + S e_c,  X[:,1+n+c] = x_t - S e_c,   S = sqrt(nearestSPD) of the step's prior.
+// The step kernels never form S; it is materialised here, on demand, from what the step left in the scratch.
+// Generation 2: S e_c = Q V sqrt(D+) V^T Q^T e_c -- one warp per block of 32 columns pushes unit vectors through the
+// reflectors and the rotation log exactly like pass A of ukf_back2_kernel.  Generation 1 / rescue: explicit Z^T.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+ukf_sigma2_kernel(BatchState b, UkfScratch u, const int inst, const int n, double* __restrict__ X) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int wld = 33;
+    UkfWarpSmem s;
+    ukf_warp_carve(b, wld, smem_raw, &s);
+    const int lane = threadIdx.x;
+    const int c0 = blockIdx.x * 32;
+    const int cnt = (n - c0 < 32) ? n - c0 : 32;
+    const unsigned FULL = 0xffffffffu;
+    double* const W_ = s.W;
+    const double* __restrict__ R = u.Zg + (size_t)inst * u.n_max * u.n_max;
+    const double2* __restrict__ rot = u.rot + (size_t)inst * u.rot_cap;
+    const int2* __restrict__ swp = u.swp + (size_t)inst * u.swp_cap;
+    const int nsw = u.nswp[inst];
+    for (int k = lane; k < n; k += 32) {
+        const double dk = u.dg[(size_t)k * b.batch + inst];
+        s.sq[k] = sqrt(dk < 0.00000001 ? 0.00000001 : dk);                  // ukf.cpp:120 and the eigen-sqrt (D-3)
+        s.x[k] = u.xprior[(size_t)inst * u.n_max + k];
+    }
+    int nrot = 0;
+    for (int q = lane; q < nsw; q += 32) { const int2 lm = swp[q]; nrot += lm.y - lm.x; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nrot += __shfl_xor_sync(FULL, nrot, o);
+    const bool act = lane < cnt;
+    for (int i = 0; i < n; ++i) W_[i * wld + lane] = (act && i == c0 + lane) ? 1.0 : 0.0;
+    __syncwarp();
+    if (b.n_max <= 128) apply_reflectors<true, 4, wld>(W_, n, lane, cnt, R); else apply_reflectors<true, 8, wld>(W_, n, lane, cnt, R);
+    apply_rot_fwd<wld>(W_, lane, act, rot, swp, nsw, nrot, s.stage);
+    if (act) for (int i = 0; i < n; ++i) W_[i * wld + lane] *= s.sq[i];
+    __syncwarp();
+    apply_rot_bwd<wld>(W_, lane, act, rot, swp, nsw, nrot, s.stage);
+    if (b.n_max <= 128) apply_reflectors<false, 4, wld>(W_, n, lane, cnt, R); else apply_reflectors<false, 8, wld>(W_, n, lane, cnt, R);
+    // lanes walk the components: consecutive addresses of one sigma point
+    for (int c = 0; c < cnt; ++c)
+        for (int i = lane; i < n; i += 32) {
+            const double sv = W_[i * wld + c], xi = s.x[i];
+            X[(size_t)(1 + c0 + c) * n + i] = xi + sv;
+            X[(size_t)(1 + n + c0 + c) * n + i] = xi - sv;
+        }
+    if (blockIdx.x == 0) for (int i = lane; i < n; i += 32) X[i] = s.x[i];
+}
+
+__global__ void ukf_sigma1_kernel(BatchState b, UkfScratch u, const int inst, const int n, double* __restrict__ X) {
+    const double* __restrict__ Zt = u.Zg + (size_t)inst * u.n_max * u.n_max;   // [k][i], compact
+    const double* __restrict__ xp = u.xprior + (size_t)inst * u.n_max;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n * n; idx += gridDim.x * blockDim.x) {
+        const int c = idx / n, i = idx - c * n;
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) acc += Zt[(size_t)k * n + i] * (u.dg[(size_t)k * b.batch + inst] * Zt[(size_t)k * n + c]);
+        X[(size_t)(1 + c) * n + i] = xp[i] + acc;
+        X[(size_t)(1 + n + c) * n + i] = xp[i] - acc;
+        if (c == 0) X[i] = xp[i];
     }
 }
 
@@ -1651,7 +1728,15 @@ cudaError_t ukf_step_configure(const BatchState& b) {
     if ((e = cudaFuncSetAttribute(ukf_back2_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 13))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back2_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 25))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back2_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 33))) != cudaSuccess) return e;
+    if (ukf_warp_smem_bytes(b, 33) <= 227 * 1024 &&
+        (e = cudaFuncSetAttribute(ukf_sigma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 33))) != cudaSuccess) return e;
     return cudaFuncSetAttribute(ukf_ql_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ql_smem_bytes(b));
+}
+
+cudaError_t launch_ukf_sigma_points(const BatchState& b, const UkfScratch& u, int inst, int fmt, int n, double* d_X, cudaStream_t st) {
+    if (fmt == 2) ukf_sigma2_kernel<<<(n + 31) / 32, 32, ukf_warp_smem_bytes(b, 33), st>>>(b, u, inst, n, d_X);
+    else ukf_sigma1_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(b, u, inst, n, d_X);
+    return cudaGetLastError();
 }
 
 // NaiveFilter::update, filter.h:342-348: measurements ignored, pose propagated by the command (one thread per instance)

@@ -156,7 +156,7 @@ class UKF(Filter):
     _kind = shim.UKF_SLAM
 
     def publishState(self) -> dict:
-        """UKFState.msg fields as ukf.cpp:60-104 fills them (X is not materialised by the batched kernel)."""
+        """UKFState.msg fields as ukf.cpp:60-104 fills them, X included (point-major, ukf.cpp:91-99)."""
         x, P, ids = self.x_t, self.P_t, self.lm_IDs
         lm = np.zeros(3 * len(ids), dtype=np.float32)
         for i, ident in enumerate(ids):
@@ -165,7 +165,12 @@ class UKF(Filter):
             lm[3 * i + 2] = x[5 + 2 * i]
         yaw = np.remainder(np.arctan2(x[3], x[2]) + np.pi, 2 * np.pi) - np.pi
         return dict(timestep=self.timestep, x_v=np.float32(x[0]), y_v=np.float32(x[1]), yaw_v=np.float32(yaw),
-                    M=len(ids), landmarks=lm, P=P.astype(np.float32).reshape(-1))
+                    M=len(ids), landmarks=lm, P=P.astype(np.float32).reshape(-1),
+                    X=self._need().sigma_points(0).astype(np.float32).reshape(-1))
+
+    @property
+    def X(self) -> np.ndarray:                 # filter.h:199 (n x (2n+1), column j = sigma point j)
+        return self._need().sigma_points(0).T.copy()
 
 
 class NaiveFilter(Filter):

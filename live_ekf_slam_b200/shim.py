@@ -279,6 +279,15 @@ class FilterBatch:
         self._ck(self._L.slam_get_assoc(self._h, inst, a.ctypes.data_as(C.POINTER(C.c_int)), C.byref(k)))
         return a[: k.value].copy()
 
+    def sigma_points(self, inst=0) -> np.ndarray:
+        """UKF: X of the last update, shape (2n+1, n): row j = sigma point j, i.e. the flattened array is UKFState.X
+        exactly as ukf.cpp:91-99 fills it (n = 4 + 2M of that update's prior; 4 x 9 zeros before the first update)."""
+        nmax = self.base + 2 * self.max_landmarks
+        X = np.zeros(nmax * (2 * nmax + 1))
+        n = C.c_int()
+        self._ck(self._L.slam_get_sigma_points(self._h, inst, X.ctypes.data_as(C.POINTER(C.c_double)), C.byref(n)))
+        return X[: n.value * (2 * n.value + 1)].reshape(2 * n.value + 1, n.value).copy()
+
     def poses(self) -> np.ndarray:
         out = np.zeros((self.batch, 3))
         self._ck(self._L.slam_get_poses(self._h, out.ctypes.data_as(C.POINTER(C.c_double))))

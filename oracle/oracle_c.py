@@ -84,6 +84,7 @@ def lib():
     L.oracle_get_landmark_ids.argtypes = [C.c_void_p, ip]
     L.oracle_get_assoc_log.argtypes = [C.c_void_p, ip, C.c_int]
     L.oracle_get_sigma_points.argtypes = [C.c_void_p, dp]
+    L.oracle_sigma_rows.argtypes = [C.c_void_p]
     L.oracle_philox.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]
     L.oracle_uniform.restype = C.c_double
     L.oracle_uniform.argtypes = [C.c_uint32, C.c_uint32]
@@ -200,10 +201,11 @@ class OracleFilter:
 
     def sigma_points(self) -> np.ndarray:
         """UKF sigma points X, shape (2n+1, n): row j = sigma point j (ukf.cpp:91-99 wire order)."""
-        n = self.n  # NB X has the row count of the step's start; callers use it right after update
-        buf = np.zeros((2 * self.max_landmarks + 4 + 2) * (2 * (2 * self.max_landmarks + 6) + 1))
-        lib().oracle_get_sigma_points(self._h, _dp(buf))
-        return buf
+        n = lib().oracle_sigma_rows(self._h)   # X keeps the row count of the last step's start (ukf.cpp:167-171)
+        buf = np.zeros((2 * n + 1) * max(n, 1))
+        if n:
+            lib().oracle_get_sigma_points(self._h, _dp(buf))
+        return buf.reshape(2 * n + 1, n)
 
 
 def philox(c0, c1, c2, c3, k0, k1):

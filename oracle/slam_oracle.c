@@ -321,6 +321,7 @@ int oracle_get_assoc_log(const oracle_filter* f, int* idx, int cap) {
     memcpy(idx, f->assoc, sizeof(int) * k);
     return f->n_assoc;
 }
+int oracle_sigma_rows(const oracle_filter* f) { return f->X ? f->X_rows : 0; }
 void oracle_get_sigma_points(const oracle_filter* f, double* Xo) {
     if (!f->X) return;
     int n = f->X_rows;

@@ -74,6 +74,7 @@ void  oracle_get_state(const oracle_filter* f, double* x);          /* raw x_t, 
 void  oracle_get_cov(const oracle_filter* f, double* P_rowmajor);   /* n*n, row-major */
 void  oracle_get_landmark_ids(const oracle_filter* f, int* ids);
 int   oracle_get_assoc_log(const oracle_filter* f, int* idx, int cap); /* per measurement of the last step: slot index or -1 (new) */
+int   oracle_sigma_rows(const oracle_filter* f);                              /* rows of X (ukf.cpp:169): n of the last step's prior */
 void  oracle_get_sigma_points(const oracle_filter* f, double* X_colmajor); /* UKF: n*(2n+1), ukf.cpp:91-99 order */
 
 /* Philox4x32-10 counter RNG shared (by definition) with the GPU workload source */

@@ -270,3 +270,76 @@ def test_ukf_capacity_variants(shim, oracle, max_lm, max_meas):
     worst = max(_compare(fb, i, ofs[i]) for i in range(B))
     assert (fb.all_status() == 0).all() and ofs[0].M >= 4
     print("ukf capacity variant", max_lm, max_meas, "worst", worst)
+
+
+@pytest.mark.parametrize("knobs", [(), ((7, 1),), ((8, 600),)], ids=["generation2", "generation1", "rescue_pass"])
+def test_ukf_sigma_points_getter(shim, oracle, knobs):
+    """slam_get_sigma_points: X of the last update (ukf.cpp:214-220, published point-major by ukf.cpp:91-99), materialised
+    on demand from the factors the step kernels leave on the device, against the oracle's X after the same update.
+    X keeps the size of the step's PRIOR (ukf.cpp:167-171) even when the step inserted landmarks."""
+    p, lm, fwd, ang = H.config2(seed=5, steps=140, filt="ukf_slam")
+    op = H.oracle_params(oracle, p)
+    B = 3
+    fb = shim.FilterBatch(shim.UKF_SLAM, p.to_c(), B, 50, 8)
+    for k, v in knobs:
+        fb.tune(k, v)
+    fb.init(0, 0, 0)
+    X0 = fb.sigma_points(1)
+    assert X0.shape == (9, 4) and not X0.any()                  # the constructor's zero matrix (ukf.cpp:20)
+    streams = [H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=13, instance=i)[0] for i in range(B)]
+    ofs = []
+    for i in range(B):
+        of = oracle.OracleFilter(oracle.UKF_SLAM, op, 50)
+        of.init(0, 0, 0)
+        ofs.append(of)
+    checked, grew, worst = 0, 0, 0.0
+    for t in range(len(fwd)):
+        n_before = [o.n for o in ofs]
+        meas, n = fb.pack_meas([streams[i][t] for i in range(B)])
+        fb.step(fwd[t], ang[t], meas, n)
+        for i in range(B):
+            ofs[i].update(fwd[t], ang[t], streams[i][t], oracle.STRUCTURED)
+        if t % 9 == 0 or t == len(fwd) - 1 or any(o.n != nb for o, nb in zip(ofs, n_before)):
+            for i in range(B):
+                X, Xo = fb.sigma_points(i), ofs[i].sigma_points()
+                assert X.shape == Xo.shape == (2 * n_before[i] + 1, n_before[i]), (t, i, X.shape, Xo.shape)
+                e = H.normwise(X, Xo)
+                assert e <= H.REL_TOL, (t, i, e)
+                worst = max(worst, e)
+                checked += 1
+                grew += int(ofs[i].n != n_before[i])
+    assert checked > 40 and grew > 5 and ofs[0].M >= 5
+    # the wire layout: UKFState.X is X flattened column by column (ukf.cpp:93-97)
+    from live_ekf_slam_b200.filter import make_filter
+    filt = make_filter(p, max_landmarks=50, max_meas=8)
+    filt.init(0, 0, 0)
+    of = oracle.OracleFilter(oracle.UKF_SLAM, op, 50)
+    of.init(0, 0, 0)
+    for t in range(40):
+        filt.update((fwd[t], ang[t]), streams[0][t].reshape(-1))
+        of.update(fwd[t], ang[t], streams[0][t], oracle.STRUCTURED)
+    msg = filt.publishState()
+    Xo = of.sigma_points()
+    assert msg["X"].dtype == np.float32 and msg["X"].size == Xo.size
+    np.testing.assert_allclose(msg["X"], Xo.reshape(-1).astype(np.float32), rtol=2e-7, atol=1e-9)
+    assert filt.X.shape == (Xo.shape[1], Xo.shape[0])
+    print("ukf sigma points worst normwise err", worst, "checked", checked)
+
+
+def test_ukf_loc_sigma_points(shim, oracle):
+    p, lm, fwd, ang = H.config2(seed=2, steps=40, filt="ukf_slam")
+    op = H.oracle_params(oracle, p)
+    fb = shim.FilterBatch(shim.UKF_LOC, p.to_c(), 2, len(lm), 8)
+    fb.set_map(lm)
+    fb.init(0, 0, 0)
+    of = oracle.OracleFilter(oracle.UKF_LOC, op, len(lm))
+    of.init(0, 0, 0)
+    of.set_map(lm)
+    stream, _ = H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=3, instance=0)
+    for t in range(len(fwd)):
+        meas, n = fb.pack_meas([stream[t], stream[t]])
+        fb.step(fwd[t], ang[t], meas, n)
+        of.update(fwd[t], ang[t], stream[t], oracle.STRUCTURED)
+        X, Xo = fb.sigma_points(1), of.sigma_points()
+        assert X.shape == Xo.shape == (9, 4)
+        assert H.normwise(X, Xo) <= H.REL_TOL
