@@ -145,6 +145,10 @@ class UKFNP(FilterNP):
         self.X_pred = None
         self.loc = False        # FilterChoice::UKF_LOC (localization_node.cpp:36-38): landmarks from the true map
         self.map = None         # float32 [id, x, y]*, filter.h:68
+        # WHAT-IF switches, off by default (= the reference).  Only tests/test_ukf_divergence_bisection.py turns them on, to
+        # attribute the UKF's large position error to individual reference lines:
+        self.whatif_bearing_mean = False    # accumulate z_est(1) too (the reference never does, ukf.cpp:310-314)
+        self.whatif_per_sigma_yaw = False   # sensing model with each sigma point's own yaw (the reference uses x_t's, ukf.cpp:139)
 
     def set_map(self, lm_xy):
         lm = np.asarray(lm_xy, dtype=np.float64).reshape(-1, 2)
@@ -233,18 +237,21 @@ class UKFNP(FilterNP):
                 dx = Xp[li, :] - Xp[0, :]
                 dy = Xp[li + 1, :] - Xp[1, :]
             z0 = np.sqrt(dx * dx + dy * dy) + float(self.w_r)
-            z1 = np.array([math.remainder(math.atan2(dy[c], dx[c]) - float(yaw_prior) + float(self.w_b), TWO_PI)
+            yaws = ([float(self._yaw(Xp[:, c])) for c in range(2 * n + 1)] if self.whatif_per_sigma_yaw
+                    else [float(yaw_prior)] * (2 * n + 1))
+            z1 = np.array([math.remainder(math.atan2(dy[c], dx[c]) - yaws[c] + float(self.w_b), TWO_PI)
                            for c in range(2 * n + 1)])
             zest0 = 0.0
             for c in range(2 * n + 1):
                 zest0 += Wts[c] * z0[c]
+            zest1 = float(np.dot(Wts, z1)) if self.whatif_bearing_mean else 0.0
             d0 = z0 - zest0
-            d1 = np.array([math.remainder(v, TWO_PI) for v in z1])
+            d1 = np.array([math.remainder(v - zest1, TWO_PI) for v in z1])
             Dz = np.stack([d0, d1])
             S = (Dz * Wts) @ Dz.T + self.W
             Cm = ((Xp - x_pred[:, None]) * Wts) @ Dz.T
             K = Cm @ np.linalg.inv(S)
-            innov = np.array([float(r) - zest0, math.remainder(float(b) - 0.0, TWO_PI)])
+            innov = np.array([float(r) - zest0, math.remainder(float(b) - zest1, TWO_PI)])
             x_pred = x_pred + K @ innov
             P_pred = P_pred - K @ S @ K.T
         for l in new:

@@ -53,3 +53,49 @@ def oracle_meas_stream(oc, op, lm, fwd, ang, seed, instance):
         out.append(oc.sim_step(op, truth, fwd[t], ang[t], lm, seed, instance, t))
         tr.append(truth.copy())
     return out, np.asarray(tr)
+
+
+#: non-default noise settings: the float adds `d_d + v_d` (ekf.cpp:57-58), `u_d + v_d` (ukf.cpp:129-131), the
+#: all-float innovation `r - dist - w_r` (ekf.cpp:130-131), the sensing-model offsets (ukf.cpp:144-145) and the corrected-noise
+#: branch of readCommonParams (filter.h:105-121 without the V/W mix-up) are only exercised away from the yaml defaults.
+PARAM_VARIANTS = {
+    "noise_means": dict(v_d=0.003, v_th=-0.002, w_r=0.004, w_b=-0.003),
+    "no_noise_bug": dict(compat_noise_bug=False),
+    "no_noise_bug_means_covs": dict(compat_noise_bug=False, v_d=-0.002, v_th=0.0015, w_r=-0.005, w_b=0.002,
+                                    V_00=0.02, V_11=0.002, W_00=0.02, W_11=0.005),
+}
+
+
+def variant_params(name, filt="ekf_slam", known=True):
+    p = Params(filter=filt)
+    for k, v in PARAM_VARIANTS[name].items():
+        setattr(p, k, v)
+    p.landmark_id_is_known = known
+    return p
+
+
+def variant_workload(name, filt="ekf_slam", known=True, seed=0, steps=200):
+    """5x10 grid + shared TSP trajectory (config 2 shape) under a non-default noise setting"""
+    p = variant_params(name, filt, known)
+    rng = np.random.default_rng(seed)
+    lm = wl.grid_map_5x10()
+    fwd, ang = wl.tsp_trajectory(lm, p, rng, steps)
+    return p, lm, fwd, ang
+
+
+def device_message_stream(shim, p, lm, fwd, ang, B, seed, offset, max_meas=8, max_lm=50):
+    """The messages the ON-DEVICE simulator emits for B vehicles, recorded step by step from a twin handle (same Philox
+    streams as any other handle with the same seed / offset): list over t of (meas [B][max_meas][3], n [B]) plus the truth
+    trace [T][B][3].  Feeding the oracle the device's own messages keeps free-running comparisons at the 1e-9 bar: the
+    device libm and glibc differ in the last float32 bit of r / b on a few of every several thousand messages."""
+    tw = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), B, max_lm, max_meas)
+    tsim = shim.Simulator(tw, lm, seed=seed, instance_offset=offset)
+    msgs, truth = [], []
+    for t in range(len(fwd)):
+        tsim.step(fwd[t], ang[t], t)
+        m, n = tsim.meas()
+        msgs.append((m.copy(), n.copy()))
+        truth.append(tsim.truth().copy())
+    tsim.close()
+    tw.close()
+    return msgs, np.asarray(truth)

@@ -345,12 +345,17 @@ def test_sweep_kernel_matches_per_step_launches(shim, oracle, threads, chunk, ca
         assert H.normwise(a["x"][i], b["x"][i]) <= 1e-12 and H.normwise(a["P"][i], b["P"][i]) <= 1e-12
     assert (a["status"] == 0).all() and (b["status"] == 0).all()
     np.testing.assert_allclose(a["stats"], b["stats"], rtol=1e-9)
-    # and against the oracle, free running
+    # and against the oracle, free running on the device simulator's own messages (1e-9 bar)
     op = H.oracle_params(oracle, p)
+    msgs, _ = H.device_message_stream(shim, p, lm, fwd, ang, B, 77, 1000)
     for i in range(0, B, 9):
-        st, pose, tr, filt = oracle.run_instance(oracle.EKF_SLAM, op, lm, fwd, ang, 77, 1000 + i, 50, oracle.STRUCTURED, keep=True)
-        assert st == 0 and a["ids"][i] == list(filt.landmark_ids())
-        assert H.normwise(a["x"][i], filt.state()) <= H.REL_TOL and H.normwise(a["P"][i], filt.cov()) <= 1e-8
+        filt = oracle.OracleFilter(oracle.EKF_SLAM, op, 50)
+        filt.init(0, 0, 0)
+        for t in range(len(fwd)):
+            m, n = msgs[t]
+            filt.update(fwd[t], ang[t], m[i, : n[i]], oracle.STRUCTURED)
+        assert filt.status == 0 and a["ids"][i] == list(filt.landmark_ids())
+        assert H.normwise(a["x"][i], filt.state()) <= H.REL_TOL and H.normwise(a["P"][i], filt.cov()) <= H.REL_TOL
 
 
 def test_sweep_kernel_freezes_dead_instance(shim, oracle):
