@@ -178,9 +178,13 @@ int  slam_run_io(slam_handle_t h, const float* cmd_fwd, const float* cmd_ang, in
  *      (the reference's only metric, plotting_node.py:212-214), [5]=sum 3-dof pose NEES (extension),
  *      [6]=instances with non-zero status, [7]=sum of M; work counters kept by the step kernels:
  *      [8]=sum of algorithmic HBM bytes (16 n^2 + 16 n + 12 (k+j) + 8 per update), [9]=sum of
- *      algorithmic flops (EKF 4 k n^2; UKF 9n^3+2n^3+2n^2(2n+1)+12kn^2), [10]=sum of n, [11]=sum of k+j.
+ *      algorithmic flops (EKF 4 k n^2; UKF 9n^3+2n^3+2n^2(2n+1)+12kn^2), [10]=sum of n, [11]=sum of k+j;
+ *      and what the kernels really do, as a model kept beside the algorithmic figures: [12]=sum of the HBM bytes the
+ *      launches move for an instance (batched EKF: the PACKED lower triangle each way -- once per step on the per-step
+ *      kernel, once per chunk on the sweep kernel), [13]=sum of the flops they execute (batched EKF: the lower
+ *      triangle only, ~2 k n^2; UKF generation 2: tridiagonalisation + QL + the S-products).
  *      Ranks all-reduce this vector (SUM). */
-#define SLAM_NUM_STATS 12
+#define SLAM_NUM_STATS 14
 int  slam_accumulate_error(slam_handle_t h, slam_sim_t s);
 int  slam_get_stats(slam_handle_t h, double* out /* SLAM_NUM_STATS */);
 int  slam_reset_stats(slam_handle_t h);
@@ -195,7 +199,9 @@ int  slam_get_error_histogram(slam_handle_t h, double lo, double hi, int nbins, 
 
 /* ---- introspection for the benchmark harness */
 long long slam_kernel_launches(slam_handle_t h);      /* kernels launched by this handle so far */
-/* per-launch device timing of the filter-step kernel (CUDA events on the handle's stream) */
+/* per-launch device timing (CUDA events on the handle's stream).  on = 1: the filter-step kernel(s) of every Filter::update
+ * (forces per-step launches), 2: the persistent sweep kernel of slam_run*, 3: large-map path, the closing DMMA contraction
+ * (lm_gemm) only, 0: off */
 int  slam_set_profiling(slam_handle_t h, int on);
 int  slam_get_profile(slam_handle_t h, double* total_ms, long long* launches);  /* synchronises; resets the pool */
 int  slam_build_info(char* buf, int cap);             /* arch, compile flags */

@@ -57,8 +57,11 @@ struct slam_filter {
     float* d_rmeas[2] = {nullptr, nullptr}; int* d_rn[2] = {nullptr, nullptr}; double* d_rposes[2] = {nullptr, nullptr};
     int r_chunk_cap = 0;              // steps the replay buffers hold
     cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
+    unsigned long long* d_hist = nullptr; int hist_cap = 0;   // scratch of slam_get_error_histogram (grown on demand, kept)
+    double* d_avg = nullptr;
     bool profiling = false;           // per-launch events around the per-step filter kernel
     bool profiling_sweep = false;     // events around the persistent sweep kernel
+    bool profiling_gemm = false;      // large map: events around lm_gemm only
     std::vector<cudaEvent_t> ev;      // pairs
     size_t ev_used = 0;
     std::string err;
@@ -227,6 +230,7 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
         CK(cudaMalloc(&g.sc, sizeof(double) * 16));
         CK(cudaMemset(g.cur, 0, sizeof(int) * 16));
         CK(cudaMallocHost(&h->h_nmeas_pin, sizeof(int)));
+        CK(ekf_large_configure());
     } else if (kind == SLAM_EKF_SLAM) {
         CK(ekf_step_configure(b));
     } else if (kind != SLAM_NAIVE) CK(ukf_step_configure(b));
@@ -254,7 +258,7 @@ int slam_destroy(slam_handle_t h) {
     BatchState& b = h->b;
     cudaFree(b.P); cudaFree(b.x); cudaFree(b.ids); cudaFree(b.meta);
     cudaFree(b.assoc); cudaFree(b.stats); cudaFree(b.sigma);
-    cudaFree(h->d_map);
+    cudaFree(h->d_map); cudaFree(h->d_hist); cudaFree(h->d_avg);
     cudaFree(h->uk.Zg); cudaFree(h->uk.Yg); cudaFree(h->uk.dg); cudaFree(h->uk.eg); cudaFree(h->uk.rot); cudaFree(h->uk.swp); cudaFree(h->uk.nswp); cudaFree(h->uk.defer); cudaFree(h->uk.xprior); cudaFree(h->uk.sigfmt);
     cudaFree(b.retry_list); cudaFree(b.retry_count); cudaFree(b.max_M); cudaFree(h->d_work); cudaFree(h->d_progress);
     if (h->h_run_hint) cudaFreeHost(h->h_run_hint);
@@ -347,16 +351,19 @@ static int do_step(slam_filter* h, const float* d_fwd, const float* d_ang, int c
         CK(cudaStreamSynchronize(h->stream));
         int nm = *h->h_nmeas_pin;
         if (nm > h->b.max_meas) nm = h->b.max_meas;
-        if (h->profiling) {
+        if (h->profiling || h->profiling_gemm) {
             if (h->ev_used + 2 > h->ev.size()) {
                 const size_t old = h->ev.size();
                 h->ev.resize(old + 4096);
                 for (size_t i = old; i < h->ev.size(); ++i) CK(cudaEventCreate(&h->ev[i]));
             }
-            CK(cudaEventRecord(h->ev[h->ev_used], h->stream));
+            if (h->profiling) CK(cudaEventRecord(h->ev[h->ev_used], h->stream));
         }
-        CK(launch_ekf_large_step(h->lg, h->fc, d_fwd, d_ang, d_meas, nm, h->b.n_max, h->stream, &h->launches));
-        if (h->profiling) { CK(cudaEventRecord(h->ev[h->ev_used + 1], h->stream)); h->ev_used += 2; }
+        const bool pg = h->profiling_gemm && nm > 0;      // events around the closing DMMA contraction only
+        CK(launch_ekf_large_step(h->lg, h->fc, d_fwd, d_ang, d_meas, nm, h->b.n_max, h->stream, &h->launches,
+                                 pg ? h->ev[h->ev_used] : nullptr, pg ? h->ev[h->ev_used + 1] : nullptr));
+        if (h->profiling) CK(cudaEventRecord(h->ev[h->ev_used + 1], h->stream));
+        if (h->profiling || pg) h->ev_used += 2;
         return 0;
     }
     StepInputs in{d_fwd, d_ang, cmd_stride, d_meas, d_nmeas};
@@ -908,8 +915,9 @@ int slam_run_io(slam_handle_t h, const float* cmd_fwd, const float* cmd_ang, int
 
 int slam_set_profiling(slam_handle_t h, int on) {
     if (!h) return 1;
-    h->profiling = on == 1;           // 1: per-step kernel (forces the per-step path), 2: sweep kernel
+    h->profiling = on == 1;           // 1: per-step kernel (forces the per-step path), 2: sweep kernel, 3: lm_gemm (large map)
     h->profiling_sweep = on == 2;
+    h->profiling_gemm = on == 3 && h->large;
     h->ev_used = 0;
     return 0;
 }
@@ -949,10 +957,14 @@ int slam_get_error_histogram(slam_handle_t h, double lo, double hi, int nbins, l
     if (!h) return 1;
     if (!(hi > lo) || nbins < 1 || nbins > 8190 || !counts) return fail(h, "slam_get_error_histogram: need lo < hi, 1 <= nbins <= 8190, counts != NULL");
     CK(cudaSetDevice(h->device));
-    unsigned long long* d_cnt = nullptr;
-    double* d_avg = nullptr;
-    CK(cudaMalloc(&d_cnt, sizeof(unsigned long long) * (nbins + 2)));
-    if (cudaMalloc(&d_avg, sizeof(double) * h->b.batch) != cudaSuccess) { cudaFree(d_cnt); return fail(h, "slam_get_error_histogram: out of memory"); }
+    if (h->hist_cap < nbins + 2) {
+        cudaFree(h->d_hist); h->d_hist = nullptr; h->hist_cap = 0;
+        CK(cudaMalloc(&h->d_hist, sizeof(unsigned long long) * (nbins + 2)));
+        h->hist_cap = nbins + 2;
+    }
+    if (!h->d_avg) CK(cudaMalloc(&h->d_avg, sizeof(double) * h->b.batch));
+    unsigned long long* d_cnt = h->d_hist;
+    double* d_avg = h->d_avg;
     int rc = 0;
     do {
         if (cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * (nbins + 2), h->stream) != cudaSuccess) { rc = 1; break; }
@@ -962,7 +974,6 @@ int slam_get_error_histogram(slam_handle_t h, double lo, double hi, int nbins, l
         if (avg_err && cudaMemcpyAsync(avg_err, d_avg, sizeof(double) * h->b.batch, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { rc = 1; break; }
         if (cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = 1; break; }
     } while (false);
-    cudaFree(d_cnt); cudaFree(d_avg);
     if (rc) return fail(h, "slam_get_error_histogram: CUDA error");
     return 0;
 }

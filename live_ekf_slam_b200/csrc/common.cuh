@@ -164,6 +164,13 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 #endif
 
+// SMs of the current device (grids of the persistent / cooperative kernels are sized from it, never from a constant)
+inline int device_sm_count() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 1;
+    return sms;
+}
+
 // host-side launchers (defined in the .cu files, called from capi.cu)
 struct StepInputs {
     const float* fwd;      // device
@@ -236,8 +243,10 @@ struct LargeState {
     double* stats;
     int ld, n_max, max_lm, max_meas;
 };
+cudaError_t ekf_large_configure();      // per handle / device: opt-in shared memory of the contraction kernel
 cudaError_t launch_ekf_large_step(const LargeState& L, const FilterConst& fc, const float* d_fwd, const float* d_ang,
-                                  const float* d_meas, int n_meas, int n_upper, cudaStream_t st, long long* launches);
+                                  const float* d_meas, int n_meas, int n_upper, cudaStream_t st, long long* launches,
+                                  cudaEvent_t gemm_ev0 = nullptr, cudaEvent_t gemm_ev1 = nullptr);
 
 struct SimState {
     double* truth;         // [batch][3]

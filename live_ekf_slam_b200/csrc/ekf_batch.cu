@@ -431,13 +431,18 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
 }
 
 // algorithmic work of one update, using the live n at the end of the step
-__device__ __forceinline__ void ekf_work_terms(const int n, const int nm, const int n_upd, double (&w)[4]) {
+// w[4]: flops the kernel executes for the step's rank-2 updates: the lower triangle only, 16 per 2x2 block = ~2 k n^2
+__device__ __forceinline__ void ekf_work_terms(const int n, const int nm, const int n_upd, double (&w)[5]) {
     const double nd = (double)n;
     w[0] += 16.0 * nd * nd + 16.0 * nd + 12.0 * nm + 8.0;
     w[1] += 4.0 * (double)n_upd * nd * nd;
     w[2] += nd;
     w[3] += (double)nm;
+    const double A = 0.5 * (nd + 1.0);
+    w[4] += 8.0 * (double)n_upd * A * (A + 1.0);
 }
+// bytes one pass of the packed covariance over HBM moves (one direction): two planes of A (A + 1) doubles, A = 2 + M
+__device__ __forceinline__ double ekf_plane_bytes(const int M) { return 16.0 * (double)bpl_plane_doubles(2 + M); }
 
 // stage the packed covariance of an instance with M landmarks: one bulk copy per plane, both on one mbarrier
 __device__ __forceinline__ void ekf_load_P(const BatchState& b, const EkfSmem& s, const int ps2, const double* gP, const int M) {
@@ -520,10 +525,12 @@ __device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterCo
         b.meta[inst] = make_int4(M, status, meta_in.z + ((phases & STEP_PREDICT) ? 1 : 0),   // timestep, :39
                                  (phases & STEP_UPDATE) ? nm : meta_in.w);
         if (M > M_start) atomicMax(b.max_M, M);
-        double w[4] = {0, 0, 0, 0};
+        double w[5] = {0, 0, 0, 0, 0};
         ekf_work_terms(n, nm, n_upd, w);
         double* st = b.stats + (size_t)inst * SLAM_NUM_STATS;
-        st[8] += w[0]; st[9] += w[1]; st[10] += w[2]; st[11] += w[3];
+        st[8] += w[0]; st[9] += w[1]; st[10] += w[2]; st[11] += w[3]; st[13] += w[4];
+        // bytes this launch really moved for the instance: packed P in and out, x in and out, ids, message, meta
+        st[12] += ekf_plane_bytes(M_start) + ekf_plane_bytes(M) + 8.0 * (n0 + n) + 4.0 * M + 12.0 * nm + 4.0 * nm + 32.0;
         // shared memory may be reused / released once the bulk engine has READ it; global visibility of the writes
         // is guaranteed at kernel completion
         bulk_wait_read();
@@ -679,7 +686,8 @@ ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, SweepA
             if (tid == 0) { s.iscr[IS_NAN] = 0; s.iscr[IS_DEAD] = 0; s.iscr[IS_OVER] = 0; ekf_load_P(b, s, ps2, gP, M); }
             for (int i = tid; i < n0; i += NT) s.x[i] = gx[i];
             for (int i = tid; i < M; i += NT) s.ids[i] = b.ids[(size_t)inst * b.max_lm + i];
-            double wacc[4] = {0, 0, 0, 0};               // work counters, carried by thread 0
+            double wacc[5] = {0, 0, 0, 0, 0};            // work counters, carried by thread 0
+            double moved = ekf_plane_bytes(M) + 8.0 * n0 + 4.0 * M + 16.0;   // HBM bytes this chunk really moves for the instance
             int timestep = meta_in.z, nm = 0;
             if (warp == 0) mbar_wait(s.bar, parity);
             Sync::sync();
@@ -736,7 +744,9 @@ ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, SweepA
                     b.meta[inst] = make_int4(M, status, timestep, (T > 0 && !frozen) ? nm : (frozen ? 0 : meta_in.w));
                     if (M > M_first) atomicMax(b.max_M, M);
                     double* st = b.stats + (size_t)inst * SLAM_NUM_STATS;
-                    st[8] += wacc[0]; st[9] += wacc[1]; st[10] += wacc[2]; st[11] += wacc[3];
+                    st[8] += wacc[0]; st[9] += wacc[1]; st[10] += wacc[2]; st[11] += wacc[3]; st[13] += wacc[4];
+                    // P and x go back once per chunk; per step only the message (replay: 12 nm + 4 in, 24 out) crosses HBM
+                    st[12] += moved + ekf_plane_bytes(M) + 8.0 * n + 4.0 * (M - M_first) + (REPLAY ? 12.0 * wacc[3] + 28.0 * T : 8.0 * T);
                     a.progress[inst] = a.t0 + T;
                     bulk_wait_read();    // the tile is re-filled by the next instance
                 }
@@ -873,7 +883,8 @@ cudaError_t launch_ekf_step(const BatchState& b, const FilterConst& fc, const St
     int per_sm = 1;
     int rthreads = pick_threads(rsmem, &per_sm);
     if (force_threads) { rthreads = force_threads; per_sm = (int)(SMEM_PER_SM / (rsmem + SMEM_CTA_RESERVED)) > 0 ? (int)(SMEM_PER_SM / (rsmem + SMEM_CTA_RESERVED)) : 1; }
-    const int grid = b.batch < 148 * per_sm ? b.batch : 148 * per_sm;
+    const int sms = device_sm_count();
+    const int grid = b.batch < sms * per_sm ? b.batch : sms * per_sm;
     return launch_step_threads(rthreads, grid, rsmem, st, b, fc, in, phases, R);
 }
 
@@ -906,7 +917,8 @@ static cudaError_t launch_sweep_t(const BatchState& b, const FilterConst& fc, co
     if (force_threads == 32) best = 0; else if (force_threads == 64) best = 1; else if (force_threads == 128) best = 2;
     else if (force_threads >= 256) best = 3;
     const int per_sm = occ[best] > 0 ? occ[best] : 1;
-    const int grid = b.batch < 148 * per_sm ? b.batch : 148 * per_sm;
+    const int sms = device_sm_count();
+    const int grid = b.batch < sms * per_sm ? b.batch : sms * per_sm;
     switch (cws[best]) {
         case 1: sweep_go<1, REPLAY>(grid, smem, st, b, fc, sim, sc, a, L); break;
         case 2: sweep_go<2, REPLAY>(grid, smem, st, b, fc, sim, sc, a, L); break;

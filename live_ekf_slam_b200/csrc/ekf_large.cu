@@ -458,13 +458,23 @@ __global__ void lm_commit(LargeState L, int n_meas) {
         L.stats[9] += 4.0 * (double)L.cur[0] * nd * nd;
         L.stats[10] += nd;
         L.stats[11] += (double)n_meas;
+        // really moved: P once each way through lm_gemm + the 5 rows / 5 columns per measurement; U and G written and re-read
+        L.stats[12] += 16.0 * nd * nd + (double)L.cur[0] * (80.0 * nd + 64.0 * nd);
+        L.stats[13] += 4.0 * (double)L.cur[0] * nd * nd;
     }
+}
+
+// 72 KB of dynamic shared memory (two pipeline stages) needs the opt-in; per device, so it is done for every handle
+// (slam_create, after cudaSetDevice) rather than once per process
+cudaError_t ekf_large_configure() {
+    return cudaFuncSetAttribute(lm_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_GEMM_SMEM);
 }
 
 // One reference EKF::update for the large-map instance.  n_meas is known on the host; meas is a DEVICE pointer to
 // [n_meas][3] float32.
 cudaError_t launch_ekf_large_step(const LargeState& L, const FilterConst& fc, const float* d_fwd, const float* d_ang,
-                                  const float* d_meas, int n_meas, int n_upper, cudaStream_t st, long long* launches) {
+                                  const float* d_meas, int n_meas, int n_upper, cudaStream_t st, long long* launches,
+                                  cudaEvent_t gemm_ev0, cudaEvent_t gemm_ev1) {
     const int tb = 256;
     const int gb = (n_upper + tb - 1) / tb;
     cudaError_t e;
@@ -483,19 +493,16 @@ cudaError_t launch_ekf_large_step(const LargeState& L, const FilterConst& fc, co
     *launches += 2;
     if (kcap > 0) {
         int gm = (n_upper + LM_SPAN - 1) / LM_SPAN;                // one CTA per 32 state indices, all co-resident
-        if (gm > 148) gm = 148;
+        const int sms = device_sm_count();
+        if (gm > sms) gm = sms;
         LargeState Lc = L; FilterConst fcc = fc; const float* mp = d_meas; int nm = kcap;
         void* args[] = {&Lc, &fcc, &mp, &nm};
         e = cudaLaunchCooperativeKernel((const void*)lm_front, dim3(gm), dim3(LM_THREADS), args, 0, st);
         if (e != cudaSuccess) return e;
         const int gt = (n_upper + GT - 1) / GT;
-        static bool gemm_configured = false;        // 72 KB of dynamic shared memory (two pipeline stages) needs the opt-in
-        if (!gemm_configured) {
-            e = cudaFuncSetAttribute(lm_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_GEMM_SMEM);
-            if (e != cudaSuccess) return e;
-            gemm_configured = true;
-        }
+        if (gemm_ev0) cudaEventRecord(gemm_ev0, st);
         lm_gemm<<<dim3(gt, gt), 128, LM_GEMM_SMEM, st>>>(L);
+        if (gemm_ev1) cudaEventRecord(gemm_ev1, st);
         *launches += 2;
     }
     lm_commit<<<gb, tb, 0, st>>>(L, n_meas);

@@ -945,6 +945,10 @@ ukf_back_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, const
         st[9] += 9.0 * nd * nd * nd + 2.0 * nd * nd * nd + 2.0 * nd * nd * (2.0 * nd + 1.0) + 12.0 * n_upd * nd * nd;
         st[10] += nd;
         st[11] += (double)nm;
+        // generation 1 moves P (front: read + seed write; back: corrections, updates), Q^T out and in; executes the explicit
+        // eigenvector route: 4/3 n^3 (tridiagonal) + 4/3 n^3 (Q) + ~5 n^3 (rotations on n components) + the S-products
+        st[12] += 8.0 * nd * nd * (6.0 + 2.0 * n_upd);
+        st[13] += (8.0 / 3.0 + 5.0) * nd * nd * nd + 4.0 * nd * nd * (8.0 + 4.0 * n_upd);
     }
 }
 
@@ -1302,6 +1306,12 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
         if (k < n) s.sq[k] = sqrt(cl ? 0.00000001 : dk);
         nclip += __popc(mask);
     }
+    if (nclip > 32) {
+        // more clipped directions than the 32 correction slots of this kernel (the reference clips any number, ukf.cpp:120):
+        // handled like a rotation-log overflow -- the instance is left untouched and redone by the generation-1 rescue pass
+        if (lane == 0) u.nswp[inst] = -1;
+        return;
+    }
     int nrot = 0;
     for (int q = lane; q < nsw; q += 32) { const int2 lm = swp[q]; nrot += lm.y - lm.x; }
 #pragma unroll
@@ -1362,7 +1372,6 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
             }
         __syncwarp();
     }
-    if (nclip > 32) status |= SLAM_STATUS_NAN;      // more than 32 non-positive directions: the covariance is garbage
 
     // ---- pass A: S e_r for the vehicle rows and the rows of the landmarks being updated; clipped eigenvectors beside
     {
@@ -1648,6 +1657,13 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
         st[9] += 9.0 * nd * nd * nd + 2.0 * nd * nd * nd + 2.0 * nd * nd * (2.0 * nd + 1.0) + 12.0 * nu * nd * nd;
         st[10] += nd;
         st[11] += (double)nm;
+        // bytes the three launches really move for the instance: P in (front) and out (back), reflectors + seed out and in,
+        // the rotation log out (QL) and in four times (two S-passes, forward and backward)
+        st[12] += 8.0 * nd * nd * 6.0 + 16.0 * (double)nrot * 5.0;
+        // flops they execute: tridiagonalisation 4/3 n^3, QL ~25 per rotation, per vector of the two S-passes 12 per
+        // rotation (forward + backward replay) and 4 n^2 (Q^T and Q through the reflectors), P_pred assembly
+        st[13] += 4.0 / 3.0 * nd * nd * nd + 25.0 * (double)nrot + (double)(2 * nvec + ncf) * (12.0 * (double)nrot + 4.0 * nd * nd)
+                  + nd * nd * (2.0 + 8.0 * nu + 2.0 * ncf);
     }
 }
 

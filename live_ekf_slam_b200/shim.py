@@ -20,7 +20,7 @@ UKF_LOC = 2    # FilterChoice::UKF_LOC, filter.h:47 (localisation on the true ma
 UKF_SLAM = 3   # FilterChoice::UKF_SLAM, filter.h:48
 NAIVE = 5      # FilterChoice::NAIVE_COMMAND_PROPAGATION, filter.h:50 (NaiveFilter, filter.h:325-370)
 STATUS_NAN, STATUS_SAME_STEP_REMATCH, STATUS_CAPACITY, STATUS_MEAS_OVERFLOW, STATUS_BAD_ID = 1, 2, 4, 8, 16
-NUM_STATS = 12
+NUM_STATS = 14
 
 #: every symbol include/slam_filter.h declares (tests check the built library exports all of them)
 ABI_SYMBOLS = (

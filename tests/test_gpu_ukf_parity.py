@@ -343,3 +343,37 @@ def test_ukf_loc_sigma_points(shim, oracle):
         X, Xo = fb.sigma_points(1), of.sigma_points()
         assert X.shape == Xo.shape == (9, 4)
         assert H.normwise(X, Xo) <= H.REL_TOL
+
+
+def test_ukf_many_clipped_eigenvalues_take_the_rescue_pass(shim, oracle):
+    """nearestSPD clips ANY number of non-positive eigenvalues (ukf.cpp:120).  The warp-per-instance kernel carries at most 32
+    clipped eigenvectors; an instance with more is left untouched and redone by the generation-1 rescue pass in the same step
+    (it used to be flagged NaN).  Teacher-forced: a covariance whose 40 landmark directions are all negative."""
+    p = H.Params(filter="ukf_slam")
+    op = H.oracle_params(oracle, p)
+    M = 20
+    n = 4 + 2 * M
+    rng = np.random.default_rng(2)
+    x = np.concatenate([[0.3, -0.2, np.cos(0.4), np.sin(0.4)], rng.uniform(-3, 3, 2 * M)])
+    A = rng.normal(size=(n, n)) * 1e-3
+    P = -(A @ A.T) - 1e-4 * np.eye(n)                     # negative definite: every eigenvalue is clipped to 1e-8
+    P[:4, :4] = np.diag([1e-2, 1e-2, 1e-3, 1e-3])
+    P[:4, 4:] = 0.0
+    P[4:, :4] = 0.0
+    ids = np.arange(M, dtype=np.int32)
+    fb = shim.FilterBatch(shim.UKF_SLAM, p.to_c(), 2, 50, 8)
+    fb.init(0, 0, 0)
+    of = oracle.OracleFilter(oracle.UKF_SLAM, op, 50)
+    of.init(0, 0, 0)
+    fb.set_state(1, x, P, ids, 7)
+    of.set_state(x, P, ids, 7)
+    m = np.array([[3, 2.0, 0.3], [11, 1.5, -0.4], [40, 2.5, 0.1]], dtype=np.float32)    # two updates and one insertion
+    meas, nm = fb.pack_meas([[], m])
+    fb.step(0.05, 0.01, meas, nm)
+    of.update(0.05, 0.01, m, oracle.STRUCTURED)
+    assert fb.status(1) == 0 and of.status == 0
+    assert list(fb.assoc(1)) == list(of.assoc_log()) == [3, 11, -1]
+    _compare(fb, 1, of)
+    X, Xo = fb.sigma_points(1), of.sigma_points()
+    assert X.shape == Xo.shape and H.normwise(X, Xo) <= H.REL_TOL
+    assert fb.status(0) == 0 and fb.timestep(0) == 1
