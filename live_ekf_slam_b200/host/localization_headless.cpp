@@ -28,7 +28,7 @@ int main(int argc, char** argv) {
             const YamlNode config = load_yaml_subset(argv[1]);                 // :29-30
             choice = config["filter"].as_string();                             // :33
             filter = make_filter(choice);                                      // :34-45
-            filter->setCapacity(50, 16);
+            filter->setCapacity(50, choice == "ukf_loc" ? 14 : 16);      // (the localisation-only kernel holds at most 14 detections per message)
             filter->readParams(config);                                        // :47
             dt = config["dt"].as_float();                                      // :86
             if (argc > 2 && std::string(argv[2]) != "default") dt = std::stof(argv[2]);   // :180-184
@@ -52,7 +52,7 @@ int main(int argc, char** argv) {
             choice = tok;
             std::cin >> steps;
             filter = make_filter(choice);
-            filter->setCapacity(50, 16);
+            filter->setCapacity(50, choice == "ukf_loc" ? 14 : 16);      // (the localisation-only kernel holds at most 14 detections per message)
             filter->readParams(default_params());
         }
         // setupStatePublisher (:186-189): the sink stands in for the ROS topic
