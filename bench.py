@@ -276,6 +276,9 @@ def measure_batch(cx: Ctx, filt: str, B: int, T: int, K: int, W: int, warm_T: in
     loc_value = fb.stats()
     st = parallel.allreduce_stats(loc_value, cx.dev)                        # NCCL over NVLink when world > 1
     acc = parallel.derive_accuracy(st, cx.world * B)
+    if filt == "ukf":
+        r = fb.ukf_routes()
+        acc["ukf_route_instance_steps"] = {"dense_gen3": int(r[0]), "ql_gen2": int(r[1]), "explicit_gen1_or_rescue": int(r[2])}
     if with_hist:
         # per-run average position error (the reference's one number per run, plotting_node.py:195-218): on-device histogram,
         # exact counts merged over the ranks, quantiles read off the merged histogram (1 cm bins)

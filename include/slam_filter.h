@@ -205,12 +205,19 @@ long long slam_kernel_launches(slam_handle_t h);      /* kernels launched by thi
 int  slam_set_profiling(slam_handle_t h, int on);
 int  slam_get_profile(slam_handle_t h, double* total_ms, long long* launches);  /* synchronises; resets the pool */
 int  slam_build_info(char* buf, int cap);             /* arch, compile flags */
+/* UKF: instance-steps taken so far by each route of the step (see slam_tune key 7): out[0] = parallel eigensolver + dense
+ * products (generation 3), out[1] = QL rotation log (generation 2, or an instance generation 3 declined), out[2] = explicit
+ * eigenvector matrix (generation 1, or the rescue pass).  Synchronises. */
+int  slam_get_ukf_routes(slam_handle_t h, long long* out /* 3 */);
 /* tuning / test knobs.  key 0: force the shared-memory landmark capacity of the first pass (0 = automatic;
  * instances that do not fit are drained by the full-capacity retry pass); key 1: headroom (landmarks) added to
  * the stale max(M) hint of the per-step launches; key 2: CTA width of the EKF kernels (0 = automatic); key 3: 1 =
  * slam_run* uses per-step launches instead of the persistent sweep kernel; key 5: steps per sweep-kernel launch;
- * key 6: headroom of the sweep kernel's tile; key 7: UKF step generation (2 = reflector / rotation-log products, warp
- * per instance, default; 1 = explicit eigenvector matrix, CTA per instance); key 8: capacity of the UKF rotation log
+ * key 6: headroom of the sweep kernel's tile; key 7: UKF step generation (3 = parallel tridiagonal eigensolver + dense products
+ * with its eigenvectors, default; 2 = QL rotation log replayed on the vectors, warp per instance; 1 = explicit eigenvector matrix,
+ * CTA per instance); key 12: largest cluster of close eigenvalues the generation-3 eigensolver re-orthogonalises itself (larger
+ * clusters send the instance down the generation-2 route in the same step; 1 forces that route for any cluster); key 13: 0 = the
+ * one-warp-per-instance back kernel of generation 3 instead of the multi-warp one; key 8: capacity of the UKF rotation log
  * (shrinking it forces the rescue pass); key 9: max clipped eigenvectors riding beside the first S-pass; key 10: slices of the UKF batch that run their
  * front -> QL -> back chains on separate streams (1..8); key 11: 0 = skip the narrow-tile first pass of the UKF back kernel.
  * Results never depend on any of them (keys 7-9: up to rounding, inside the parity tolerance). */

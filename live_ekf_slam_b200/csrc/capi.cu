@@ -188,7 +188,7 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
         b.sigma = nullptr;   // allocated lazily by slam_get_sigma_points
         UkfScratch& u = h->uk;
         u.n_max = b.n_max;
-        u.gen = 2; u.clip_lanes = 0;
+        u.gen = 3; u.clip_lanes = 0; u.maxc = 16; u.multiwarp = 1;
         h->uks.nsub = 1;
         CK(cudaEventCreateWithFlags(&h->uks.fork, cudaEventDisableTiming));
         for (int k = 0; k < UKF_MAX_SUB - 1; ++k) {
@@ -200,6 +200,8 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
         u.swp_cap = 6 * b.n_max;                    // ~1.7 n sweeps are typical
         CK(cudaMalloc(&u.Zg, sizeof(double) * (size_t)batch * b.n_max * b.n_max));
         CK(cudaMalloc(&u.Yg, sizeof(double) * (size_t)batch * b.n_max * b.n_max));
+        CK(cudaMalloc(&u.Vg, sizeof(double) * (size_t)batch * b.n_max * b.n_max));
+        CK(cudaMalloc(&u.VTg, sizeof(double) * (size_t)batch * b.n_max * b.n_max));
         CK(cudaMalloc(&u.dg, sizeof(double) * (size_t)batch * b.n_max));
         CK(cudaMalloc(&u.eg, sizeof(double) * (size_t)batch * b.n_max));
         CK(cudaMalloc(&u.rot, sizeof(double2) * (size_t)batch * u.rot_cap));
@@ -209,6 +211,8 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
         CK(cudaMemset(u.defer, 0, sizeof(int) * batch));
         CK(cudaMalloc(&u.xprior, sizeof(double) * (size_t)batch * b.n_max));
         CK(cudaMalloc(&u.sigfmt, sizeof(int2) * batch));
+        CK(cudaMalloc(&u.routes, sizeof(unsigned long long) * 4));
+        CK(cudaMemset(u.routes, 0, sizeof(unsigned long long) * 4));
         CK(cudaMemset(u.sigfmt, 0, sizeof(int2) * batch));
         u.narrow = 1;
     }
@@ -259,7 +263,7 @@ int slam_destroy(slam_handle_t h) {
     cudaFree(b.P); cudaFree(b.x); cudaFree(b.ids); cudaFree(b.meta);
     cudaFree(b.assoc); cudaFree(b.stats); cudaFree(b.sigma);
     cudaFree(h->d_map); cudaFree(h->d_hist); cudaFree(h->d_avg);
-    cudaFree(h->uk.Zg); cudaFree(h->uk.Yg); cudaFree(h->uk.dg); cudaFree(h->uk.eg); cudaFree(h->uk.rot); cudaFree(h->uk.swp); cudaFree(h->uk.nswp); cudaFree(h->uk.defer); cudaFree(h->uk.xprior); cudaFree(h->uk.sigfmt);
+    cudaFree(h->uk.Zg); cudaFree(h->uk.Yg); cudaFree(h->uk.Vg); cudaFree(h->uk.VTg); cudaFree(h->uk.dg); cudaFree(h->uk.eg); cudaFree(h->uk.rot); cudaFree(h->uk.swp); cudaFree(h->uk.nswp); cudaFree(h->uk.defer); cudaFree(h->uk.xprior); cudaFree(h->uk.sigfmt); cudaFree(h->uk.routes);
     cudaFree(b.retry_list); cudaFree(b.retry_count); cudaFree(b.max_M); cudaFree(h->d_work); cudaFree(h->d_progress);
     if (h->h_run_hint) cudaFreeHost(h->h_run_hint);
     for (int i = 0; i < slam_filter::HINT_RING; ++i) if (h->run_ev[i]) cudaEventDestroy(h->run_ev[i]);
@@ -305,7 +309,9 @@ int slam_tune(slam_handle_t h, int key, int value) {
     } else if (key == 3) h->sweep_off = value;
     else if (key == 5) { if (value < 1) return fail(h, "slam_tune: the sweep chunk must be >= 1 step"); h->sweep_chunk = value; }
     else if (key == 6) h->sweep_headroom = value < 0 ? 0 : value;
-    else if (key == 7) { if (value != 1 && value != 2) return fail(h, "slam_tune: UKF generation must be 1 or 2"); h->uk.gen = value; }
+    else if (key == 7) { if (value < 1 || value > 3) return fail(h, "slam_tune: UKF generation must be 1, 2 or 3"); h->uk.gen = value; }
+    else if (key == 12) h->uk.maxc = value < 0 ? 0 : value;
+    else if (key == 13) h->uk.multiwarp = value ? 1 : 0;
     else if (key == 8) {     // shrink the rotation log (test knob: forces the rescue pass); never beyond the allocation
         long long full = 2LL * h->b.n_max * h->b.n_max;
         if (full < 256) full = 256;
@@ -314,6 +320,15 @@ int slam_tune(slam_handle_t h, int key, int value) {
     else if (key == 11) h->uk.narrow = value ? 1 : 0;
     else if (key == 10) { if (value < 1 || value > UKF_MAX_SUB) return fail(h, "slam_tune: UKF slices must be 1..8"); h->uks.nsub = value; }
     else return fail(h, "slam_tune: unknown key");
+    return 0;
+}
+
+int slam_get_ukf_routes(slam_handle_t h, long long* out) {
+    if (!h || !out) return 1;
+    if (!h->uk.routes) return fail(h, "slam_get_ukf_routes: UKF only");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(out, h->uk.routes, sizeof(long long) * 3, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

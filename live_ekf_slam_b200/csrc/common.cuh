@@ -202,7 +202,13 @@ struct UkfScratch {
     long long rot_cap;
     int swp_cap;
     int n_max;
-    int gen;            // 2 (default): reflector / rotation-log products, warp per instance; 1: explicit eigenvectors
+    int gen;            // 3 (default): parallel tridiagonal eigensolver + dense products with its eigenvectors; 2: QL rotation
+                        // log replayed on the vectors, warp per instance; 1: explicit eigenvector matrix of Y, CTA per instance
+    double* Vg;         // [batch][n_max * n_max]  generation 3: V[i][k], eigenvectors of the tridiagonal matrix (compact, ld n)
+    double* VTg;        // [batch][n_max * n_max]  generation 3: its transpose (work space of the eigensolver before)
+    unsigned long long* routes;   // [4] instance-steps taken by: dense route (gen 3), QL route (gen 2), gen-1 / rescue, (spare)
+    int multiwarp;      // generation 3: 1 (default) = back kernel with one warp per group of four vectors, 0 = one warp per instance
+    int maxc;           // generation 3: largest cluster of close eigenvalues handled in the kernel (larger: QL route)
     double* xprior;     // [batch][n_max]  x_t at the start of the last step: column 0 of the sigma-point matrix X (ukf.cpp:214)
     int2* sigfmt;       // [batch]  what the scratch holds of the last step's sqrt factor, for slam_get_sigma_points:
                         //          .x = 0 nothing yet (X is the constructor's 4 x 9 zero matrix, ukf.cpp:20), 2 = reflectors (Zg) +

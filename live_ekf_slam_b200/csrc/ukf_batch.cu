@@ -27,6 +27,7 @@
 //   ukf_back_kernel   CTA per instance: replays the rotation log on Q^T (thread per eigenvector component), then the
 //                     sigma-point algebra, landmark updates and insertions.
 #include "common.cuh"
+#include "eig3.cuh"
 
 #include <climits>
 
@@ -376,12 +377,13 @@ __device__ __forceinline__ double ql_rsqrt(const double x) {
 // redo the tridiagonalisation (the generation-2 rescue pass).
 template <bool SMEM>
 __global__ void __launch_bounds__(QL_LANES)
-ukf_ql_kernel(UkfScratch u, const int4* __restrict__ meta, const int batch, const int i0, const int i1) {
+ukf_ql_kernel(UkfScratch u, const int4* __restrict__ meta, const int batch, const int i0, const int i1, const int only_flagged) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const int inst = i0 + blockIdx.x * QL_LANES + lane;
     if (inst >= i1) return;
     if (meta[inst].y & SLAM_STATUS_SAME_STEP_REMATCH) return;
+    if (only_flagged && u.nswp[inst] != -2) return;     // generation 3: only the instances the parallel eigensolver declined
     const int n = 4 + 2 * meta[inst].x;
     double* sd = reinterpret_cast<double*>(smem_raw);           // [n_max][32]
     double* se = sd + (size_t)u.n_max * QL_LANES;               // [n_max][32]
@@ -938,6 +940,7 @@ ukf_back_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, const
         if (s.iscr[2]) status |= SLAM_STATUS_NAN;
         b.meta[inst] = make_int4(M, status, meta_in.z + 1, nm);             // timestep, :164
         u.sigfmt[inst] = make_int2(1, n);
+        atomicAdd(u.routes + 2, 1ull);
         if (M > M_start) atomicMax(b.max_M, M);
         double* st = b.stats + (size_t)inst * SLAM_NUM_STATS;
         const double nd = (double)n;
@@ -1000,6 +1003,7 @@ struct UkfWarpSmem {
     float* meas;
     int* assoc;
     int* uq;        // measurement index of update q
+    int* ctl;       // [8] multi-warp back kernel: nu, nclip, status bits shared by warp 0
 };
 
 __host__ __device__ inline size_t ukf_warp_carve(const BatchState& b, const int wld, unsigned char* base, UkfWarpSmem* s) {
@@ -1017,11 +1021,12 @@ __host__ __device__ inline size_t ukf_warp_carve(const BatchState& b, const int 
     size_t omeas = take(sizeof(float) * 3 * (b.max_meas > 0 ? b.max_meas : 1));
     size_t oassoc = take(sizeof(int) * (b.max_meas > 0 ? b.max_meas : 1));
     size_t ouq = take(sizeof(int) * (b.max_meas > 0 ? b.max_meas : 1));
+    size_t octl = take(sizeof(int) * 8);
     if (s) {
         s->W = (double*)(base + oW) + 2 * wld; s->x = (double*)(base + ox); s->xp = (double*)(base + oxp); s->sq = (double*)(base + osq);
         s->Xp = (double*)(base + oXp); s->Xcs = (float*)(base + oXcs); s->upd = (double*)(base + oupd);
         s->stage = (double2*)(base + ostage) + 2; s->corr = (double*)(base + ocorr); s->clip = (int*)(base + oclip);
-        s->ids = (int*)(base + oids); s->meas = (float*)(base + omeas); s->assoc = (int*)(base + oassoc); s->uq = (int*)(base + ouq);
+        s->ids = (int*)(base + oids); s->meas = (float*)(base + omeas); s->assoc = (int*)(base + oassoc); s->uq = (int*)(base + ouq); s->ctl = (int*)(base + octl);
     }
     return off;
 }
@@ -1038,7 +1043,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // one coalesced row load fetched one reflector ahead, and the nv dot products are reduced by shuffles four at a time.
 template <bool ASC, int NT, int WLD>
 __device__ __forceinline__ void apply_reflectors(double* W, const int n, const int lane, const int nv,
-                                                 const double* __restrict__ R) {
+                                                 const double* __restrict__ R, const int j_lo = 0, const int j_step = 4) {
     double va[NT], taua = 0.0;
     auto loadk = [&](const int k, double (&dst)[NT], double& tau) {
         if (k < 0 || k > n - 2) { tau = 0.0; return; }
@@ -1057,7 +1062,7 @@ __device__ __forceinline__ void apply_reflectors(double* W, const int n, const i
         const double tau = taua;
         loadk(k + step, va, taua);
         if (tau == 0.0) continue;
-        for (int j0 = 0; j0 < nv; j0 += 4) {
+        for (int j0 = j_lo; j0 < nv; j0 += j_step) {         // (a warp of the multi-warp kernel owns the groups j_lo, j_lo + j_step, ..)
             double w[NT][4];
             double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
 #pragma unroll
@@ -1256,8 +1261,232 @@ ukf_front2_kernel(BatchState b, UkfScratch u, const int i0) {
     for (int k = tid; k < n; k += UKF_THREADS) { u.dg[(size_t)k * b.batch + inst] = s.d[k]; u.eg[(size_t)k * b.batch + inst] = s.e[k]; }
 }
 
-// ---- launch 3 of 3 (generation 2): warp per instance
-template <int wld>
+// =========================================================================================================
+// Generation 3 (default): the tridiagonal eigenproblem T = V D V^T is solved in parallel INSIDE an instance (eig3.cuh:
+// thread t <-> eigenpair t; bisection on Sturm counts, twisted-factorisation inverse iteration, Gram-Schmidt only inside
+// clusters of close eigenvalues) and V is written out explicitly, so that the back kernel evaluates
+//      S v = Q V sqrt(D+) V^T Q^T v
+// with two dense n x n products per S-pass instead of replaying ~0.85 n^2 plane rotations serially on every vector, and the
+// one-thread-per-instance QL chain disappears from the step.  An instance the solver declines (cluster larger than `maxc`,
+// residual above tolerance, non-finite pivots) is flagged nswp = -2 and takes the generation-2 route (QL kernel + rotation
+// replay) in the same step; nswp = -3 marks "explicit V in the scratch".
+//   scratch:  Vg  [batch][n^2]  V[i][k]  = component i of eigenvector k of T (rows contiguous over k)
+//             VTg [batch][n^2]  VT[k][i] = the transpose (rows contiguous over i); doubles as the solver's per-thread work space
+// =========================================================================================================
+struct Eig3Smem {
+    double *d, *e, *e2, *lam, *lt, *red;
+    eig3::De* de;       // {d[i], e[i-1]^2} packed for the Sturm recurrence
+    int *b0, *b1, *crank, *cfirst, *tw, *flag;
+};
+__host__ __device__ inline size_t eig3_carve(const int n_max, const int nt, unsigned char* base, Eig3Smem* s) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
+    const size_t od = take(8 * n_max), oe = take(8 * n_max), oe2 = take(8 * n_max), ol = take(8 * n_max), olt = take(8 * n_max), ored = take(8 * 40);
+    const size_t ode = take(16 * n_max);
+    const size_t ob0 = take(4 * n_max), ob1 = take(4 * n_max), ocr = take(4 * n_max), ocf = take(4 * n_max), otw = take(4 * n_max), ofl = take(4 * 8);
+    if (s) {
+        s->d = (double*)(base + od); s->e = (double*)(base + oe); s->e2 = (double*)(base + oe2); s->lam = (double*)(base + ol);
+        s->lt = (double*)(base + olt); s->red = (double*)(base + ored); s->de = (eig3::De*)(base + ode);
+        s->b0 = (int*)(base + ob0); s->b1 = (int*)(base + ob1); s->crank = (int*)(base + ocr); s->cfirst = (int*)(base + ocf);
+        s->tw = (int*)(base + otw); s->flag = (int*)(base + ofl);
+    }
+    return off;
+}
+
+template <int NT>
+__device__ __forceinline__ double cta_max(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double m = red[0];
+#pragma unroll
+    for (int w = 1; w < NT / 32; ++w) m = fmax(m, red[w]);
+    return m;
+}
+
+// ---- launch 2 of 3 (generation 3): CTA per instance, thread t <-> eigenpair t of the tridiagonal matrix
+template <int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT)      // <= 64 registers: the bisection is a latency chain, hidden by resident warps only
+ukf_eig3_kernel(BatchState b, UkfScratch u, const int i0, const int maxc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Eig3Smem s;
+    eig3_carve(u.n_max, NT, smem_raw, &s);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int inst = i0 + blockIdx.x;
+    const int4 meta_in = b.meta[inst];
+    if (meta_in.y & SLAM_STATUS_SAME_STEP_REMATCH) return;
+    const int n = 4 + 2 * meta_in.x;
+    double* const Vg = u.Vg + (size_t)inst * u.n_max * u.n_max;       // [i][k], compact leading dimension n
+    double* const Wg = u.VTg + (size_t)inst * u.n_max * u.n_max;      // work space now, V^T at the end
+    const bool live = t < n;
+    if (live) { s.d[t] = u.dg[(size_t)t * b.batch + inst]; s.e[t] = (t < n - 1) ? u.eg[(size_t)t * b.batch + inst] : 0.0; }
+    if (t == 0) { s.flag[0] = 0; s.flag[1] = 0; }
+    __syncthreads();
+    // |T| (largest absolute row sum), then the splits (eig3.cuh, step 1)
+    double rs = 0.0;
+    if (live) rs = fabs(s.d[t]) + (t > 0 ? fabs(s.e[t - 1]) : 0.0) + fabs(s.e[t]);
+    const double tn = cta_max<NT>(rs, s.red);
+    if (live && t < n - 1 && fabs(s.e[t]) <= eig3::EPS * (fabs(s.d[t]) + fabs(s.d[t + 1]))) s.e[t] = 0.0;
+    __syncthreads();
+    double e2v = 0.0;
+    if (live) { e2v = s.e[t] * s.e[t]; s.e2[t] = e2v; s.de[t].d = s.d[t]; if (t + 1 < n) s.de[t + 1].e2 = e2v; if (t == 0) s.de[0].e2 = 0.0; }
+    const double e2max = cta_max<NT>(e2v, s.red);
+    const double pivmin = fmax(2.2250738585072014e-308 * fmax(1.0, e2max), 1e-300);
+    const double pivf = eig3::EPS * tn;
+    int a = 0, bb = 0;
+    double lam = 0.0;
+    if (live) {
+        a = t; while (a > 0 && s.e[a - 1] != 0.0) --a;
+        bb = t + 1; while (bb < n && s.e[bb - 1] != 0.0) ++bb;
+        s.b0[t] = a; s.b1[t] = bb;
+        lam = eig3::bisect(s.d, s.e, s.de, a, bb, t - a, pivmin);
+        s.lam[t] = lam;
+    }
+    __syncthreads();
+    // clusters inside a block (neighbours closer than 1e-3 |T|, LAPACK dstein) and dstein's perturbation of coincident shifts
+    int crank = 0, cfirst = t;
+    double x = lam;
+    if (live) {
+        const double ortol = 1.0e-3 * tn;
+        while (t - crank > a && s.lam[t - crank] - s.lam[t - crank - 1] < ortol && crank <= maxc) ++crank;
+        cfirst = t - crank;
+        if (crank >= maxc && crank > 0) s.flag[0] = 1;               // cluster too large for the in-kernel Gram-Schmidt
+        x = s.lam[cfirst];
+        for (int q = cfirst + 1; q <= t; ++q) {
+            const double lq = s.lam[q], pert = 10.0 * eig3::EPS * fabs(lq);
+            x = (lq - x < pert) ? x + pert : lq;
+        }
+        s.crank[t] = crank; s.cfirst[t] = cfirst;
+    }
+    const int maxrank = (int)cta_max<NT>((double)crank, s.red);
+    if (s.flag[0]) { if (t == 0) u.nswp[inst] = -2; return; }
+    // eigenvectors: twisted factorisation, z in column t of V, factors in column t of the work space
+    const eig3::Slot z{Vg + t, n}, w{Wg + t, n};
+    int tw = a;
+    bool bad = false;
+    if (live) {
+        for (int i = 0; i < a; ++i) z.set(i, 0.0);
+        for (int i = bb; i < n; ++i) z.set(i, 0.0);
+        if (bb - a == 1) z.set(a, 1.0);
+        else {
+            double n2 = 1.0;
+            tw = eig3::twisted_vector(s.d, s.e, s.e2, a, bb, x, pivf, z, w, &n2);
+            const double sc = rsqrt(n2);
+            if (!(n2 > 0.0) || !isfinite(n2)) bad = true;
+#pragma unroll 4
+            for (int i = a; i < bb; ++i) z.set(i, z.get(i) * sc);
+        }
+    }
+    // modified Gram-Schmidt inside clusters, one rank per round; then one refinement step for cluster members and again
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) {
+            if (maxrank == 0) break;
+            const bool incl = live && bb - a > 1 && (crank > 0 || (t + 1 < bb && s.crank[t + 1] > 0));
+            if (incl) {
+                const double n2 = eig3::twisted_solve(s.e, a, bb, tw, z, w);
+                const double sc = rsqrt(n2);
+                if (!(n2 > 0.0) || !isfinite(n2)) bad = true;
+                for (int i = a; i < bb; ++i) z.set(i, z.get(i) * sc);
+            }
+        }
+        // one rank per round; inside a round every WARP takes cluster members (lanes stride over the components: the dot
+        // products and updates of a member are 32 wide instead of a serial chain of dependent global loads in one thread)
+        for (int r = 1; r <= maxrank; ++r) {
+            __syncthreads();                       // (global memory: visible to the CTA after the barrier)
+            for (int m = warp; m < n; m += NT / 32) {
+                if (s.crank[m] != r) continue;     // warp-uniform
+                const int ma = s.b0[m], mb = s.b1[m];
+                double* zm = Vg + m;
+                for (int q = s.cfirst[m]; q < m; ++q) {
+                    const double* zq = Vg + q;
+                    double dot = 0.0;
+                    for (int i = ma + lane; i < mb; i += 32) dot += zq[(size_t)i * n] * zm[(size_t)i * n];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                    for (int i = ma + lane; i < mb; i += 32) zm[(size_t)i * n] -= dot * zq[(size_t)i * n];
+                }
+                double n2 = 0.0;
+                for (int i = ma + lane; i < mb; i += 32) { const double v = zm[(size_t)i * n]; n2 += v * v; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+                // unit vector before: a tiny remainder means nearly dependent vectors.  In the first pass the twisted vectors of a
+                // pathologically close pair may coincide (the refinement step separates them); after it, decline the instance
+                if (pass == 1 && !(n2 > 1.0e-6) && lane == 0) s.flag[1] = 1;
+                const double sc = rsqrt(n2);
+                for (int i = ma + lane; i < mb; i += 32) zm[(size_t)i * n] *= sc;
+            }
+        }
+        __syncthreads();
+    }
+    // residual |(T - lambda I) z| against |T|
+    if (live && bb - a > 1) {
+        const double r = eig3::residual_inf(s.d, s.e, a, bb, lam, z, 1.0);
+        if (!(r <= 1.0e-12 * tn)) bad = true;
+    }
+    if (bad) s.flag[1] = 1;
+    __syncthreads();
+    if (s.flag[1]) { if (t == 0) u.nswp[inst] = -2; return; }        // dg / eg untouched: the QL route takes the instance
+    // V^T: every thread reads its column of V (coalesced over the threads) and writes it as row t of the transpose -- four
+    // loads in flight, consecutive addresses per thread (the sectors merge in L2); no shared-memory tile, which would cap the
+    // CTAs per SM of this latency-bound kernel.  The work space is dead by now (barrier above).  Eigenvalues over diag(T).
+    if (live) {
+        double* row = Wg + (size_t)t * n;
+        int i = 0;
+        for (; i + 3 < n; i += 4) {
+            const double v0 = z.get(i), v1 = z.get(i + 1), v2 = z.get(i + 2), v3 = z.get(i + 3);
+            row[i] = v0; row[i + 1] = v1; row[i + 2] = v2; row[i + 3] = v3;
+        }
+        for (; i < n; ++i) row[i] = z.get(i);
+        u.dg[(size_t)t * b.batch + inst] = lam;
+    }
+    if (t == 0) u.nswp[inst] = -3;
+}
+
+// W[:, j] <- rs .* (Mat^T W[:, j]) for the columns j < ncols of the warp's vector tile (written back only for j < jw):
+// out[c][j] = rs[c] * sum_r Mat[r][c] W[r][j], Mat row-major with leading dimension n.  Lane <-> output rows c = lane + 32 t
+// (coalesced row loads of Mat), the inputs W[r][*] are shared-memory broadcasts, JB columns accumulate in registers.
+template <int NTT, int WLD>
+__device__ __forceinline__ void dense_apply(double* W, const double* __restrict__ Mat, const int n, const int lane, const int ncols,
+                                            const int jw, const double* rs) {
+    constexpr int JB = (NTT <= 4) ? 12 : 6;
+    for (int j0 = 0; j0 < ncols; j0 += JB) {
+        double acc[NTT][JB];
+#pragma unroll
+        for (int q = 0; q < NTT; ++q)
+#pragma unroll
+            for (int j = 0; j < JB; ++j) acc[q][j] = 0.0;
+#pragma unroll 2
+        for (int r = 0; r < n; ++r) {
+            double m[NTT];
+#pragma unroll
+            for (int q = 0; q < NTT; ++q) { const int c = lane + 32 * q; m[q] = (c < n) ? __ldg(Mat + (size_t)r * n + c) : 0.0; }
+            const double* wr = W + r * WLD + j0;
+#pragma unroll
+            for (int j = 0; j < JB; ++j) {
+                const double wv = wr[j];
+#pragma unroll
+                for (int q = 0; q < NTT; ++q) acc[q][j] = fma(m[q], wv, acc[q][j]);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < NTT; ++q) {
+            const int c = lane + 32 * q;
+            if (c < n) {
+                const double sc = rs ? rs[c] : 1.0;
+#pragma unroll
+                for (int j = 0; j < JB; ++j) if (j0 + j < jw) W[c * WLD + j0 + j] = acc[q][j] * sc;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- launch 3 of 3 (generations 2 and 3): warp per instance.  DENSE = false: S-products through the QL rotation log
+// (generation 2, and the fall-back of generation 3); DENSE = true: through the explicit eigenvectors of T (generation 3).
+template <int wld, bool DENSE>
 __global__ void __launch_bounds__(32, 10)        // ten one-warp CTAs per SM: <= 200 registers per thread
 ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, const int i0, const int pass) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1277,7 +1506,8 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
     int status = meta_in.y;
     if (status & SLAM_STATUS_SAME_STEP_REMATCH) return;
     const int nsw = u.nswp[inst];
-    if (nsw < 0) return;                           // rotation log overflow: redone by the rescue pass
+    if (DENSE ? (nsw != -3) : (nsw < 0)) return;   // not this route: rotation log overflow (-1, rescue pass), declined by the
+                                                   // parallel eigensolver (-2, QL route) or solved by it (-3, dense route)
     if (pass == 1 && !u.defer[inst]) return;       // full-width pass: only the instances the narrow pass handed over
     int M = meta_in.x;
     const int M_start = M;
@@ -1290,6 +1520,8 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
     double* Yg = u.Yg + (size_t)inst * u.n_max * u.n_max;
     const double2* __restrict__ rot = u.rot + (size_t)inst * u.rot_cap;
     const int2* __restrict__ swp = u.swp + (size_t)inst * u.swp_cap;
+    const double* __restrict__ Vm = u.Vg + (size_t)inst * u.n_max * u.n_max;      // generation 3: V[i][k] and its transpose
+    const double* __restrict__ VTm = u.VTg + (size_t)inst * u.n_max * u.n_max;
 
     for (int i = lane; i < n; i += 32) { const double v = gx[i]; s.x[i] = v; u.xprior[(size_t)inst * u.n_max + i] = v; }
     for (int i = lane; i < M; i += 32) s.ids[i] = b.ids[(size_t)inst * b.max_lm + i];
@@ -1313,7 +1545,7 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
         return;
     }
     int nrot = 0;
-    for (int q = lane; q < nsw; q += 32) { const int2 lm = swp[q]; nrot += lm.y - lm.x; }
+    if (!DENSE) for (int q = lane; q < nsw; q += 32) { const int2 lm = swp[q]; nrot += lm.y - lm.x; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nrot += __shfl_xor_sync(FULL, nrot, o);
     __syncwarp();
@@ -1362,7 +1594,8 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
         const bool act = lane < cnt;
         if (lane < wcols) for (int i = 0; i < n; ++i) W_[i * wld + lane] = (act && s.clip[c0 + lane] == i) ? 1.0 : 0.0;
         __syncwarp();
-        apply_rot_bwd<wld>(W_, lane, act, rot, swp, nsw, nrot, s.stage);
+        if (DENSE) { if (small_n) dense_apply<4, wld>(W_, VTm, n, lane, cnt, cnt, nullptr); else dense_apply<8, wld>(W_, VTm, n, lane, cnt, cnt, nullptr); }
+        else apply_rot_bwd<wld>(W_, lane, act, rot, swp, nsw, nrot, s.stage);
         if (small_n) apply_reflectors<false, 4, wld>(W_, n, lane, cnt, R); else apply_reflectors<false, 8, wld>(W_, n, lane, cnt, R);
         for (int a = 4; a < n; ++a)
             for (int c = 4 + lane; c < n; c += 32) {
@@ -1382,15 +1615,23 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
         const bool act = lane < nvec;
         __syncwarp();
         if (small_n) apply_reflectors<true, 4, wld>(W_, n, lane, nvec, R); else apply_reflectors<true, 8, wld>(W_, n, lane, nvec, R);
-        apply_rot_fwd<wld>(W_, lane, act, rot, swp, nsw, nrot, s.stage);
         const bool isclip = lane >= nvec && lane < nvec + ncf;
         const int ck = isclip ? s.clip[lane - nvec] : -1;
-        if (lane < wcols) for (int i = 0; i < n; ++i) {
-            if (act) W_[i * wld + lane] *= s.sq[i];
-            else W_[i * wld + lane] = (i == ck) ? 1.0 : 0.0;
+        if (DENSE) {
+            // sqrt(D+) V^T (.) for the active columns, unit vectors e_ck in the clipped columns, then V (.) for all of them
+            if (small_n) dense_apply<4, wld>(W_, Vm, n, lane, nvec, nvec, s.sq); else dense_apply<8, wld>(W_, Vm, n, lane, nvec, nvec, s.sq);
+            if (lane < wcols && !act) for (int i = 0; i < n; ++i) W_[i * wld + lane] = (i == ck) ? 1.0 : 0.0;
+            __syncwarp();
+            if (small_n) dense_apply<4, wld>(W_, VTm, n, lane, nvec + ncf, nvec + ncf, nullptr); else dense_apply<8, wld>(W_, VTm, n, lane, nvec + ncf, nvec + ncf, nullptr);
+        } else {
+            apply_rot_fwd<wld>(W_, lane, act, rot, swp, nsw, nrot, s.stage);
+            if (lane < wcols) for (int i = 0; i < n; ++i) {
+                if (act) W_[i * wld + lane] *= s.sq[i];
+                else W_[i * wld + lane] = (i == ck) ? 1.0 : 0.0;
+            }
+            const bool act2 = act || isclip;
+            apply_rot_bwd<wld>(W_, lane, act2, rot, swp, nsw, nrot, s.stage);
         }
-        const bool act2 = act || isclip;
-        apply_rot_bwd<wld>(W_, lane, act2, rot, swp, nsw, nrot, s.stage);
         if (small_n) apply_reflectors<false, 4, wld>(W_, n, lane, nvec + ncf, R); else apply_reflectors<false, 8, wld>(W_, n, lane, nvec + ncf, R);
     }
 
@@ -1541,9 +1782,14 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
     {
         const bool act = lane < nvec;
         if (small_n) apply_reflectors<true, 4, wld>(W_, n, lane, nvec, R); else apply_reflectors<true, 8, wld>(W_, n, lane, nvec, R);
-        apply_rot_fwd<wld>(W_, lane, act, rot, swp, nsw, nrot, s.stage);
-        if (act) for (int i = 0; i < n; ++i) W_[i * wld + lane] *= s.sq[i];
-        apply_rot_bwd<wld>(W_, lane, act, rot, swp, nsw, nrot, s.stage);
+        if (DENSE) {
+            if (small_n) { dense_apply<4, wld>(W_, Vm, n, lane, nvec, nvec, s.sq); dense_apply<4, wld>(W_, VTm, n, lane, nvec, nvec, nullptr); }
+            else { dense_apply<8, wld>(W_, Vm, n, lane, nvec, nvec, s.sq); dense_apply<8, wld>(W_, VTm, n, lane, nvec, nvec, nullptr); }
+        } else {
+            apply_rot_fwd<wld>(W_, lane, act, rot, swp, nsw, nrot, s.stage);
+            if (act) for (int i = 0; i < n; ++i) W_[i * wld + lane] *= s.sq[i];
+            apply_rot_bwd<wld>(W_, lane, act, rot, swp, nsw, nrot, s.stage);
+        }
         if (small_n) apply_reflectors<false, 4, wld>(W_, n, lane, nvec, R); else apply_reflectors<false, 8, wld>(W_, n, lane, nvec, R);
     }
 
@@ -1649,7 +1895,8 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
     if (lane == 0) {
         if (bad) status |= SLAM_STATUS_NAN;
         b.meta[inst] = make_int4(M, status, meta_in.z + 1, nm);             // timestep, :164
-        u.sigfmt[inst] = make_int2(2, n);                                   // reflectors + rotation log + eigenvalues stay in the scratch
+        atomicAdd(u.routes + (DENSE ? 0 : 1), 1ull);
+        u.sigfmt[inst] = make_int2(DENSE ? 3 : 2, n);                       // reflectors + (rotation log | explicit V) + eigenvalues stay in the scratch
         if (M > M_start) atomicMax(b.max_M, M);
         double* st = b.stats + (size_t)inst * SLAM_NUM_STATS;
         const double nd = (double)n;
@@ -1667,6 +1914,461 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
     }
 }
 
+// One group of JB columns (j0 .. j0 + JB) of dense_apply, for the multi-warp back kernel: each warp owns its columns.
+template <int NTT, int WLD, int JB>
+__device__ __forceinline__ void dense_cols(double* W, const double* __restrict__ Mat, const int n, const int lane, const int j0,
+                                           const int jw, const double* rs) {
+    double acc[NTT][JB];
+#pragma unroll
+    for (int q = 0; q < NTT; ++q)
+#pragma unroll
+        for (int j = 0; j < JB; ++j) acc[q][j] = 0.0;
+#pragma unroll 4
+    for (int r = 0; r < n; ++r) {
+        double m[NTT];
+#pragma unroll
+        for (int q = 0; q < NTT; ++q) { const int c = lane + 32 * q; m[q] = (c < n) ? __ldg(Mat + (size_t)r * n + c) : 0.0; }
+        const double* wr = W + r * WLD + j0;
+#pragma unroll
+        for (int j = 0; j < JB; ++j) {
+            const double wv = wr[j];
+#pragma unroll
+            for (int q = 0; q < NTT; ++q) acc[q][j] = fma(m[q], wv, acc[q][j]);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < NTT; ++q) {
+        const int c = lane + 32 * q;
+        if (c < n) {
+            const double sc = rs ? rs[c] : 1.0;
+#pragma unroll
+            for (int j = 0; j < JB; ++j) if (j0 + j < jw) W[c * WLD + j0 + j] = acc[q][j] * sc;
+        }
+    }
+    __syncwarp();
+}
+
+// ---- launch 3 of 3 (generation 3, default): the back kernel with NW = (wld - 1) / 4 WARPS per instance.  Same algebra and the
+// same shared-memory tile as ukf_back2_kernel<wld, true>; the column groups of the vector tile (4 vectors each) are owned by
+// different warps, so the reflector products -- a chain of n - 1 dependent dot / update steps per vector group, half of the
+// single-warp kernel's time -- and the dense V / V^T products run NW wide; the updates' sigma-point statistics are spread over
+// the warps by update, the rows of the P_pred assembly by row.  Small scalar phases are evaluated redundantly by every warp.
+template <int wld>
+__global__ void __launch_bounds__(32 * ((wld - 1) / 4), (wld == 13) ? 4 : 2)
+ukf_back3_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, const int i0, const int pass) {
+    constexpr int NW = (wld - 1) / 4, NTHR = 32 * NW;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    UkfWarpSmem s;
+    ukf_warp_carve(b, wld, smem_raw, &s);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int inst = i0 + blockIdx.x;
+    const int ldp = b.fixed_ld;
+    const int nsm = 2 * b.n_max + 2;
+    const unsigned FULL = 0xffffffffu;
+    const int wcols = wld - 1 < ukf_wcols(b) ? wld - 1 : ukf_wcols(b);
+    double* const W_ = s.W;
+    const bool small_n = b.n_max <= 128;
+
+    const int4 meta_in = b.meta[inst];
+    int nm = in.n_meas[inst];
+    int status = meta_in.y;
+    if (status & SLAM_STATUS_SAME_STEP_REMATCH) return;
+    if (u.nswp[inst] != -3) return;                // only instances the parallel eigensolver solved (explicit V in the scratch)
+    if (pass == 1 && !u.defer[inst]) return;       // full-width pass: only the instances the narrow pass handed over
+    int M = meta_in.x;
+    const int M_start = M;
+    const int n = 4 + 2 * M;                       // ukf.cpp:167
+    const int ns = 2 * n + 1;
+    if (nm > b.max_meas) { nm = b.max_meas; status |= SLAM_STATUS_MEAS_OVERFLOW; }
+    double* gP = b.P + (size_t)inst * b.p_stride;
+    double* gx = b.x + (size_t)inst * b.x_stride;
+    const double* __restrict__ R = u.Zg + (size_t)inst * u.n_max * u.n_max;
+    double* Yg = u.Yg + (size_t)inst * u.n_max * u.n_max;
+    const double* __restrict__ Vm = u.Vg + (size_t)inst * u.n_max * u.n_max;
+    const double* __restrict__ VTm = u.VTg + (size_t)inst * u.n_max * u.n_max;
+
+    for (int i = tid; i < n; i += NTHR) { const double v = gx[i]; s.x[i] = v; u.xprior[(size_t)inst * u.n_max + i] = v; }
+    for (int i = tid; i < M; i += NTHR) s.ids[i] = b.ids[(size_t)inst * b.max_lm + i];
+    for (int i = tid; i < 3 * nm; i += NTHR) s.meas[i] = in.meas[(size_t)inst * b.max_meas * 3 + i];
+    __syncthreads();
+    if (warp == 0) {
+        // eigenvalues: clip (:120), sqrt, ordered list of the clipped ones
+        int nclip = 0;
+        for (int k0 = 0; k0 < n; k0 += 32) {
+            const int k = k0 + lane;
+            const double dk = (k < n) ? u.dg[(size_t)k * b.batch + inst] : 1.0;
+            const bool cl = (k < n) && (dk < 0.00000001);
+            const unsigned mask = __ballot_sync(FULL, cl);
+            const int pos = nclip + __popc(mask & ((1u << lane) - 1u));
+            if (cl && pos < 32) { s.clip[pos] = k; s.corr[pos] = 0.00000001 - dk; }
+            if (k < n) s.sq[k] = sqrt(cl ? 0.00000001 : dk);
+            nclip += __popc(mask);
+        }
+        // association of every measurement (:258-274): known-ID lookup against the landmarks of the step start
+        int nu = 0, st = 0;
+        for (int l = 0; l < nm; ++l) {
+            const int id = (int)s.meas[3 * l];                                  // :258
+            int cand = INT_MAX;
+            if (fc.loc) {                                                        // :262,272,300-302: every detection updates, by map id
+                if (id >= 0 && id < fc.n_map) cand = id; else st |= SLAM_STATUS_BAD_ID;
+            } else {
+                for (int j = lane; j < M_start; j += 32) if (s.ids[j] == id) { cand = j; break; }   // :264-269
+                cand = __reduce_min_sync(FULL, cand);
+            }
+            if (lane == 0) {
+                s.assoc[l] = (cand == INT_MAX) ? -1 : cand;
+                if (cand != INT_MAX) s.uq[nu] = l;
+            }
+            if (cand != INT_MAX) ++nu;
+        }
+        if (lane == 0) { s.ctl[0] = nu; s.ctl[1] = nclip; s.ctl[2] = st; }
+    }
+    __syncthreads();
+    const int nu = s.ctl[0], nclip = s.ctl[1];
+    status |= s.ctl[2];
+    if (nclip > 32) { if (tid == 0) u.nswp[inst] = -1; return; }       // (see ukf_back2_kernel: the rescue pass takes the instance)
+
+    // weights and scale are float-valued (ukf.cpp:35,114,175)
+    const float W0f = 0.2f;                                                // filter.h:207
+    const double W0 = (double)W0f;
+    const double wgt = (double)((1 - W0f) / (2 * n));                      // :175
+    const double sw = W0 + (double)(2 * n) * wgt;                          // sum of the 2n+1 weights (not 1)
+    const float u_d = in.fwd[in.cmd_stride ? inst : 0], u_th = in.ang[in.cmd_stride ? inst : 0];
+    const float yaw_prior = yaw_of(s.x[2], s.x[3]);                        // :182 and :139 (prior x_t)
+    const double cy = (double)cos_f(yaw_prior), sy = (double)sin_f(yaw_prior);
+    const double Qd[4] = {fc.V00 * cy, fc.V00 * sy, fc.V11 * cy, fc.V11 * sy};   // :183-186
+
+    if (pass == 0) {                                // narrow tile: hand the instance over if its updates do not fit
+        const bool over = 4 + 2 * nu > wcols;
+        if (tid == 0) u.defer[inst] = over ? 1 : 0;
+        if (over) return;
+    }
+    const int nvec = 4 + 2 * nu;                    // columns of the two S-passes
+    int ncf = wcols - nvec; if (ncf > nclip) ncf = nclip;   // clipped eigenvectors riding in pass A
+    if (u.clip_lanes > 0 && ncf > u.clip_lanes) ncf = u.clip_lanes;        // test knob
+    const int jown = 4 * warp;                      // this warp's column group of the vector tile
+
+    // ---- clipped eigenpairs that do not fit beside pass A (never in practice): z_k = Q V e_k, folded into the landmark-block seed
+    for (int c0 = ncf; c0 < nclip && c0 < 32; c0 += wcols) {
+        int cnt = (nclip < 32 ? nclip : 32) - c0; if (cnt > wcols) cnt = wcols;
+        for (int i = warp; i < n; i += NW) if (lane < wcols) W_[i * wld + lane] = (lane < cnt && s.clip[c0 + lane] == i) ? 1.0 : 0.0;
+        __syncthreads();
+        if (jown < cnt) {
+            if (small_n) { dense_cols<4, wld, 4>(W_, VTm, n, lane, jown, cnt, nullptr); apply_reflectors<false, 4, wld>(W_, n, lane, cnt, R, jown, 4 * NW); }
+            else { dense_cols<8, wld, 4>(W_, VTm, n, lane, jown, cnt, nullptr); apply_reflectors<false, 8, wld>(W_, n, lane, cnt, R, jown, 4 * NW); }
+        }
+        __syncthreads();
+        for (int a = 4 + warp; a < n; a += NW)
+            for (int c = 4 + lane; c < n; c += 32) {
+                double add = 0.0;
+                for (int q = 0; q < cnt; ++q) add += (2.0 * wgt) * s.corr[c0 + q] * W_[a * wld + q] * W_[c * wld + q];
+                Yg[(size_t)a * n + c] += add;
+            }
+        __syncthreads();
+    }
+
+    // ---- pass A: S e_r for the vehicle rows and the rows of the landmarks being updated; clipped eigenvectors beside
+    {
+        int row = -1;
+        if (lane < 4) row = lane;
+        else if (lane < nvec && !fc.loc) { const int q = (lane - 4) >> 1; row = s.assoc[s.uq[q]] * 2 + 4 + ((lane - 4) & 1); }   // :298
+        for (int i = warp; i < n; i += NW) if (lane < wcols) W_[i * wld + lane] = (i == row) ? 1.0 : 0.0;
+        __syncthreads();
+        if (jown < nvec + ncf) {
+            if (jown < nvec) {
+                if (small_n) { apply_reflectors<true, 4, wld>(W_, n, lane, nvec, R, jown, 4 * NW); dense_cols<4, wld, 4>(W_, Vm, n, lane, jown, nvec, s.sq); }
+                else { apply_reflectors<true, 8, wld>(W_, n, lane, nvec, R, jown, 4 * NW); dense_cols<8, wld, 4>(W_, Vm, n, lane, jown, nvec, s.sq); }
+            }
+            // unit vectors e_ck (in the eigenbasis) in the clipped columns of this group
+            for (int j = (jown > nvec ? jown : nvec); j < jown + 4 && j < nvec + ncf; ++j) {
+                const int ck = s.clip[j - nvec];
+                for (int i = lane; i < n; i += 32) W_[i * wld + j] = (i == ck) ? 1.0 : 0.0;
+            }
+            __syncwarp();
+            if (small_n) { dense_cols<4, wld, 4>(W_, VTm, n, lane, jown, nvec + ncf, nullptr); apply_reflectors<false, 4, wld>(W_, n, lane, nvec + ncf, R, jown, 4 * NW); }
+            else { dense_cols<8, wld, 4>(W_, VTm, n, lane, jown, nvec + ncf, nullptr); apply_reflectors<false, 8, wld>(W_, n, lane, nvec + ncf, R, jown, 4 * NW); }
+        }
+        __syncthreads();
+    }
+
+    // ---- sigma points, vehicle rows (:214-226): X = x +- column of S, motion model per sigma point
+    for (int i = tid; i < ns; i += NTHR) {
+        double X[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const double xr = s.x[r];
+            X[r] = (i == 0) ? xr : (i <= n ? xr + W_[(i - 1) * wld + r] : xr - W_[(i - 1 - n) * wld + r]);
+        }
+        const float yaw = yaw_of(X[2], X[3]);                              // :128
+        const float ud = u_d + fc.v_d;
+        s.Xp[0 * nsm + i] = X[0] + (double)(ud * cos_f(yaw));              // :129 float product
+        s.Xp[1 * nsm + i] = X[1] + (double)(ud * sin_f(yaw));              // :130
+        const float fsum = yaw + u_th + fc.v_th;
+        const float new_yaw = (float)remainder((double)fsum, TWO_PI_REF);  // :131
+        s.Xcs[0 * nsm + i] = cos_f(new_yaw);                               // :132
+        s.Xcs[1 * nsm + i] = sin_f(new_yaw);                               // :133
+    }
+    __syncthreads();
+    auto XP = [&](const int r, const int i) -> double { return r < 2 ? s.Xp[r * nsm + i] : (double)s.Xcs[(r - 2) * nsm + i]; };
+    // ---- mean (:228-232) and vehicle block of the covariance (:235-240): every warp evaluates them (same lane order, same values)
+    double xp0v[4];
+    {
+        double acc[4] = {0, 0, 0, 0};
+        for (int i = lane; i < ns; i += 32) {
+            const double wi = (i == 0) ? W0 : wgt;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] += wi * XP(r, i);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) xp0v[r] = warp_sum(acc[r]);
+        if (warp == 0 && lane < 4) s.xp[lane] = xp0v[lane];
+        for (int r = 4 + tid; r < n; r += NTHR) s.xp[r] = sw * s.x[r];
+    }
+    double mv[4], vv[10];
+    {
+        double acc[14] = {0};
+        for (int i = lane; i < ns; i += 32) {
+            const double wi = (i == 0) ? W0 : wgt;
+            double dv[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) dv[r] = XP(r, i) - xp0v[r];
+            int q = 0;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = a; c < 4; ++c) acc[q++] += (wi * dv[a]) * dv[c];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) acc[10 + a] += wi * dv[a];
+        }
+#pragma unroll
+        for (int k = 0; k < 14; ++k) acc[k] = warp_sum(acc[k]);
+        {
+            int q = 0;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = a; c < 4; ++c) { vv[q] = acc[q] + ((a == c) ? Qd[a] : 0.0); ++q; }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) mv[a] = acc[10 + a];
+    }
+    // ---- the updates' sigma-point statistics (:293-336): update q on warp q mod NW; it leaves hv = dz_i - dz_{i+n} in its two
+    //      columns of W (the S rows it read from them are dead by then)
+    for (int q = warp; q < nu; q += NW) {
+        const int l = s.uq[q];
+        const int li = fc.loc ? 0 : s.assoc[l] * 2 + 4;                     // :298
+        const int c0 = 4 + 2 * q;
+        const double mlx = fc.loc ? (double)fc.map[3 * s.assoc[l] + 1] : s.x[li];             // :152-153 (true map, float) / :144
+        const double mly = fc.loc ? (double)fc.map[3 * s.assoc[l] + 2] : s.x[li + 1];
+        auto sense = [&](const int i, const double sgn, const int row, double& a0, double& a1) {
+            double lx = mlx, ly = mly;
+            if (!fc.loc && sgn != 0.0) { lx += sgn * W_[row * wld + c0]; ly += sgn * W_[row * wld + c0 + 1]; }
+            const double dx = lx - s.Xp[0 * nsm + i], dy = ly - s.Xp[1 * nsm + i];
+            a0 = sqrt(dx * dx + dy * dy) + (double)fc.w_r;                  // :144
+            a1 = remainder(atan2(dy, dx) - (double)yaw_prior + (double)fc.w_b, TWO_PI_REF);   // :145,156
+        };
+        double zest0 = 0.0;
+        for (int i = lane; i < ns; i += 32) {
+            double a0, a1;
+            sense(i, i == 0 ? 0.0 : (i <= n ? 1.0 : -1.0), i <= n ? i - 1 : i - 1 - n, a0, a1);
+            zest0 += ((i == 0) ? W0 : wgt) * a0;
+        }
+        zest0 = warp_sum(zest0);
+        double acc[13] = {0};
+        auto accum = [&](const int i, const double wi, const double a0, const double a1, double& d0, double& d1) {
+            d0 = a0 - zest0;
+            d1 = remainder(a1 - 0.0, TWO_PI_REF);                           // z_est(1) is never accumulated (:310-314,321)
+            acc[0] += (wi * d0) * d0; acc[1] += (wi * d0) * d1; acc[2] += (wi * d1) * d1;
+            acc[3] += wi * d0; acc[4] += wi * d1;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const double wd = wi * (XP(a, i) - xp0v[a]);
+                acc[5 + 2 * a] += wd * d0; acc[6 + 2 * a] += wd * d1;
+            }
+        };
+        if (lane == 0) { double a0, a1, d0, d1; sense(0, 0.0, 0, a0, a1); accum(0, W0, a0, a1, d0, d1); }
+        for (int i = lane; i < n; i += 32) {
+            double a0, a1, b0, b1, da0, da1, db0, db1;
+            sense(1 + i, 1.0, i, a0, a1);
+            sense(1 + n + i, -1.0, i, b0, b1);
+            accum(1 + i, wgt, a0, a1, da0, da1);
+            accum(1 + n + i, wgt, b0, b1, db0, db1);
+            if (!fc.loc) {
+                W_[i * wld + c0] = da0 - db0;
+                W_[i * wld + c0 + 1] = da1 - db1;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 13; ++k) acc[k] = warp_sum(acc[k]);
+        __syncwarp();
+        if (lane == 0) {
+            double* ud = s.upd + q * UPD_LD;
+            const double S00 = acc[0] + fc.W00, S01 = acc[1], S11 = acc[2] + fc.W11;     // :326
+            ud[0] = S00; ud[1] = S01; ud[2] = S11; ud[3] = acc[3]; ud[4] = acc[4];
+            for (int a = 0; a < 8; ++a) ud[5 + a] = acc[5 + a];
+            const bool swpv = fabs(S01) > fabs(S00);                        // S2^-1 (:339, partial-pivot LU like Eigen's dynamic inverse)
+            const double a00 = swpv ? S01 : S00, a01 = swpv ? S11 : S01;
+            const double a10 = swpv ? S00 : S01, a11 = swpv ? S01 : S11;
+            const double l10 = a10 / a00, u11 = a11 - l10 * a01;
+            const double b0c0 = swpv ? 0.0 : 1.0, b1c0 = swpv ? 1.0 : 0.0, b0c1 = swpv ? 1.0 : 0.0, b1c1 = swpv ? 0.0 : 1.0;
+            double y1 = b1c0 - l10 * b0c0;
+            const double i10 = y1 / u11, i00 = (b0c0 - a01 * i10) / a00;
+            y1 = b1c1 - l10 * b0c1;
+            const double i11 = y1 / u11, i01 = (b0c1 - a01 * i11) / a00;
+            ud[13] = i00; ud[14] = i01; ud[15] = i10; ud[16] = i11;
+            ud[17] = (double)s.meas[3 * l + 1] - zest0;                                   // innovation (:342-344)
+            ud[18] = remainder((double)s.meas[3 * l + 2] - 0.0, TWO_PI_REF);
+        }
+    }
+    __syncthreads();
+    // g_a[i] = Xp[a][1+i] - Xp[a][1+n+i] -> columns 0..3
+    for (int i = tid; i < n; i += NTHR)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) W_[i * wld + a] = XP(a, 1 + i) - XP(a, 1 + n + i);
+    __syncthreads();
+
+    // ---- pass B: S g_a and S hv for every update; the clipped eigenvectors stay put in their columns
+    if (jown < nvec) {
+        if (small_n) {
+            apply_reflectors<true, 4, wld>(W_, n, lane, nvec, R, jown, 4 * NW);
+            dense_cols<4, wld, 4>(W_, Vm, n, lane, jown, nvec, s.sq);
+            dense_cols<4, wld, 4>(W_, VTm, n, lane, jown, nvec, nullptr);
+            apply_reflectors<false, 4, wld>(W_, n, lane, nvec, R, jown, 4 * NW);
+        } else {
+            apply_reflectors<true, 8, wld>(W_, n, lane, nvec, R, jown, 4 * NW);
+            dense_cols<8, wld, 4>(W_, Vm, n, lane, jown, nvec, s.sq);
+            dense_cols<8, wld, 4>(W_, VTm, n, lane, jown, nvec, nullptr);
+            apply_reflectors<false, 8, wld>(W_, n, lane, nvec, R, jown, 4 * NW);
+        }
+    }
+    __syncthreads();
+
+    // ---- gains (:336-345): C uses the RUNNING x_pred, which couples the updates only through the thread's own component a:
+    //      every thread walks the updates in message order for its components; K_q overwrites the update's columns of W
+    for (int a = tid; a < n; a += NTHR) {
+        double xpa = s.xp[a];
+        for (int q = 0; q < nu; ++q) {
+            const double* ud = s.upd + q * UPD_LD;
+            const int c0 = 4 + 2 * q;
+            const double sdz0 = ud[3], sdz1 = ud[4];
+            double c0v, c1v;
+            if (a < 4) {
+                const double sh = xp0v[a] - xpa;
+                c0v = ud[5 + 2 * a] + sh * sdz0; c1v = ud[6 + 2 * a] + sh * sdz1;
+            } else {
+                const double fa = s.x[a] - xpa;
+                c0v = fa * sdz0 + wgt * W_[a * wld + c0];
+                c1v = fa * sdz1 + wgt * W_[a * wld + c0 + 1];
+            }
+            const double k0 = c0v * ud[13] + c1v * ud[15], k1 = c0v * ud[14] + c1v * ud[16];
+            W_[a * wld + c0] = k0; W_[a * wld + c0 + 1] = k1;
+            xpa = xpa + (k0 * ud[17] + k1 * ud[18]);
+        }
+        s.xp[a] = xpa;
+    }
+    __syncthreads();
+
+    // ---- P_pred, written once (:235-240 then :348 per update, in message order); rows spread over the warps
+    for (int i = warp; i < n; i += NW) {
+        const double ei = (i >= 4) ? s.x[i] - sw * s.x[i] : 0.0;
+        for (int jb = 0; jb < n; jb += 128) {
+            double yv[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int j = jb + lane + 32 * t;
+                yv[t] = (i >= 4 && j >= 4 && j < n) ? Yg[(size_t)i * n + j] : 0.0;
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int j = jb + lane + 32 * t;
+                if (j >= n) continue;
+                double val;
+                if (i < 4 && j < 4) {
+                    const int a = i < j ? i : j, c = i < j ? j : i;
+                    val = vv[a * 4 - (a * (a - 1)) / 2 + (c - a)];
+                } else if (i < 4) {
+                    const double eb = s.x[j] - sw * s.x[j];
+                    val = wgt * W_[j * wld + i] + eb * mv[i];
+                } else if (j < 4) {
+                    val = wgt * W_[i * wld + j] + ei * mv[j];
+                } else {
+                    const double ej = s.x[j] - sw * s.x[j];
+                    double add = sw * ei * ej;
+                    for (int q = 0; q < ncf; ++q) add += (2.0 * wgt) * s.corr[q] * W_[i * wld + nvec + q] * W_[j * wld + nvec + q];
+                    val = yv[t] + add;
+                }
+                for (int q = 0; q < nu; ++q) {
+                    const double* ud = s.upd + q * UPD_LD;
+                    const int c0 = 4 + 2 * q;
+                    const double ki0 = W_[i * wld + c0], ki1 = W_[i * wld + c0 + 1];
+                    const double ks0 = ki0 * ud[0] + ki1 * ud[1], ks1 = ki0 * ud[1] + ki1 * ud[2];
+                    val -= ks0 * W_[j * wld + c0] + ks1 * W_[j * wld + c0 + 1];
+                }
+                gP[(size_t)i * ldp + j] = val;
+            }
+        }
+    }
+    __syncthreads();
+
+    // -------- landmarkInsertion for the unmatched measurements, in message order (:278-287,351-371); warp 0 writes
+    for (int l = 0; l < nm && !fc.loc; ++l) {
+        if (s.assoc[l] != -1) continue;
+        if (M >= b.max_lm) { status |= SLAM_STATUS_CAPACITY; continue; }
+        const int nn = 4 + 2 * M;
+        if (warp == 0) {
+            const float r = s.meas[3 * l + 1], bb = s.meas[3 * l + 2];
+            if (lane == 0) {
+                const float yaw = yaw_of(s.xp[2], s.xp[3]);                     // :356
+                const float yb = yaw + bb;
+                s.xp[nn] = s.xp[0] + (double)(r * cos_f(yb));                   // :358
+                s.xp[nn + 1] = s.xp[1] + (double)(r * sin_f(yb));               // :359
+                s.ids[M] = (int)s.meas[3 * l];                                  // :361
+            }
+            for (int i = lane; i < nn + 2; i += 32) {                           // :365-368, W block and zero cross terms
+                gP[(size_t)i * ldp + nn] = (i == nn) ? fc.W00 : 0.0;
+                gP[(size_t)i * ldp + nn + 1] = (i == nn + 1) ? fc.W11 : 0.0;
+                gP[(size_t)nn * ldp + i] = (i == nn) ? fc.W00 : 0.0;
+                gP[(size_t)(nn + 1) * ldp + i] = (i == nn + 1) ? fc.W11 : 0.0;
+            }
+        }
+        M += 1;
+    }
+    __syncthreads();
+
+    // ---- commit (:289-290)
+    const int n_out = 4 + 2 * M;
+    int bad = 0;
+    for (int i = tid; i < n_out; i += NTHR) {
+        const double v = s.xp[i];
+        gx[i] = v;
+        if (!isfinite(v)) bad = 1;
+    }
+    bad = __syncthreads_or(bad);
+    for (int i = tid + M_start; i < M; i += NTHR) b.ids[(size_t)inst * b.max_lm + i] = s.ids[i];
+    for (int i = tid; i < nm; i += NTHR) b.assoc[(size_t)inst * b.max_meas + i] = s.assoc[i];
+    if (tid == 0) {
+        if (bad) status |= SLAM_STATUS_NAN;
+        b.meta[inst] = make_int4(M, status, meta_in.z + 1, nm);             // timestep, :164
+        atomicAdd(u.routes + 0, 1ull);
+        u.sigfmt[inst] = make_int2(3, n);
+        if (M > M_start) atomicMax(b.max_M, M);
+        double* st = b.stats + (size_t)inst * SLAM_NUM_STATS;
+        const double nd = (double)n;
+        st[8] += 16.0 * nd * nd + 16.0 * nd + 12.0 * nm + 8.0;
+        st[9] += 9.0 * nd * nd * nd + 2.0 * nd * nd * nd + 2.0 * nd * nd * (2.0 * nd + 1.0) + 12.0 * nu * nd * nd;
+        st[10] += nd;
+        st[11] += (double)nm;
+        // bytes the three launches really move for the instance: P in (front) and out (back), reflectors + seed out and in, V and
+        // V^T out (eigensolver, with its work space) and in twice each (two S-passes)
+        st[12] += 8.0 * nd * nd * (6.0 + 2.0 + 4.0 + 4.0);
+        // flops they execute: tridiagonalisation 4/3 n^3, eigensolver ~55 Sturm sweeps of 3 n per eigenvalue + ~40 n per vector,
+        // per vector of the two S-passes 4 n^2 (V^T, V) + 4 n^2 (Q^T, Q through the reflectors), P_pred assembly
+        st[13] += 4.0 / 3.0 * nd * nd * nd + nd * nd * (165.0 + 40.0) + (double)(2 * nvec + ncf) * 8.0 * nd * nd
+                  + nd * nd * (2.0 + 8.0 * nu + 2.0 * ncf);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // slam_get_sigma_points: the matrix X of the last step (ukf.cpp:214-220; published point-major by ukf.cpp:91-99),
 //   X[:,0] = x_t,  X[:,1+c] = x_t + S e_c,  X[:,1+n+c] = x_t - S e_c,   S = sqrt(nearestSPD) of the step's prior.
@@ -1674,6 +2376,7 @@ ukf_back2_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
 // Generation 2: S e_c = Q V sqrt(D+) V^T Q^T e_c -- one warp per block of 32 columns pushes unit vectors through the
 // reflectors and the rotation log exactly like pass A of ukf_back2_kernel.  Generation 1 / rescue: explicit Z^T.
 // ---------------------------------------------------------------------------------------------------------
+template <bool DENSE>
 __global__ void __launch_bounds__(32)
 ukf_sigma2_kernel(BatchState b, UkfScratch u, const int inst, const int n, double* __restrict__ X) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1688,7 +2391,9 @@ ukf_sigma2_kernel(BatchState b, UkfScratch u, const int inst, const int n, doubl
     const double* __restrict__ R = u.Zg + (size_t)inst * u.n_max * u.n_max;
     const double2* __restrict__ rot = u.rot + (size_t)inst * u.rot_cap;
     const int2* __restrict__ swp = u.swp + (size_t)inst * u.swp_cap;
-    const int nsw = u.nswp[inst];
+    const int nsw = DENSE ? 0 : u.nswp[inst];
+    const double* __restrict__ Vm = u.Vg + (size_t)inst * u.n_max * u.n_max;
+    const double* __restrict__ VTm = u.VTg + (size_t)inst * u.n_max * u.n_max;
     for (int k = lane; k < n; k += 32) {
         const double dk = u.dg[(size_t)k * b.batch + inst];
         s.sq[k] = sqrt(dk < 0.00000001 ? 0.00000001 : dk);                  // ukf.cpp:120 and the eigen-sqrt (D-3)
@@ -1702,10 +2407,15 @@ ukf_sigma2_kernel(BatchState b, UkfScratch u, const int inst, const int n, doubl
     for (int i = 0; i < n; ++i) W_[i * wld + lane] = (act && i == c0 + lane) ? 1.0 : 0.0;
     __syncwarp();
     if (b.n_max <= 128) apply_reflectors<true, 4, wld>(W_, n, lane, cnt, R); else apply_reflectors<true, 8, wld>(W_, n, lane, cnt, R);
-    apply_rot_fwd<wld>(W_, lane, act, rot, swp, nsw, nrot, s.stage);
-    if (act) for (int i = 0; i < n; ++i) W_[i * wld + lane] *= s.sq[i];
-    __syncwarp();
-    apply_rot_bwd<wld>(W_, lane, act, rot, swp, nsw, nrot, s.stage);
+    if (DENSE) {
+        if (b.n_max <= 128) { dense_apply<4, wld>(W_, Vm, n, lane, cnt, cnt, s.sq); dense_apply<4, wld>(W_, VTm, n, lane, cnt, cnt, nullptr); }
+        else { dense_apply<8, wld>(W_, Vm, n, lane, cnt, cnt, s.sq); dense_apply<8, wld>(W_, VTm, n, lane, cnt, cnt, nullptr); }
+    } else {
+        apply_rot_fwd<wld>(W_, lane, act, rot, swp, nsw, nrot, s.stage);
+        if (act) for (int i = 0; i < n; ++i) W_[i * wld + lane] *= s.sq[i];
+        __syncwarp();
+        apply_rot_bwd<wld>(W_, lane, act, rot, swp, nsw, nrot, s.stage);
+    }
     if (b.n_max <= 128) apply_reflectors<false, 4, wld>(W_, n, lane, cnt, R); else apply_reflectors<false, 8, wld>(W_, n, lane, cnt, R);
     // lanes walk the components: consecutive addresses of one sigma point
     for (int c = 0; c < cnt; ++c)
@@ -1741,16 +2451,29 @@ cudaError_t ukf_step_configure(const BatchState& b) {
     if ((e = cudaFuncSetAttribute(ukf_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_front2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ukf_back2_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 13))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ukf_back2_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 25))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ukf_back2_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 33))) != cudaSuccess) return e;
-    if (ukf_warp_smem_bytes(b, 33) <= 227 * 1024 &&
-        (e = cudaFuncSetAttribute(ukf_sigma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 33))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back2_kernel<13, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 13))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back2_kernel<25, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 25))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back2_kernel<33, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 33))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back2_kernel<13, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 13))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back2_kernel<25, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 25))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back2_kernel<33, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 33))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back3_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 13))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back3_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 25))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back3_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 33))) != cudaSuccess) return e;
+    if (ukf_warp_smem_bytes(b, 33) <= 227 * 1024) {
+        if ((e = cudaFuncSetAttribute(ukf_sigma2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 33))) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(ukf_sigma2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 33))) != cudaSuccess) return e;
+    }
+    if (b.n_max <= 256) {
+        if ((e = cudaFuncSetAttribute(ukf_eig3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig3_carve(b.n_max, 128, nullptr, nullptr))) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(ukf_eig3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig3_carve(b.n_max, 256, nullptr, nullptr))) != cudaSuccess) return e;
+    }
     return cudaFuncSetAttribute(ukf_ql_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ql_smem_bytes(b));
 }
 
 cudaError_t launch_ukf_sigma_points(const BatchState& b, const UkfScratch& u, int inst, int fmt, int n, double* d_X, cudaStream_t st) {
-    if (fmt == 2) ukf_sigma2_kernel<<<(n + 31) / 32, 32, ukf_warp_smem_bytes(b, 33), st>>>(b, u, inst, n, d_X);
+    if (fmt == 3) ukf_sigma2_kernel<true><<<(n + 31) / 32, 32, ukf_warp_smem_bytes(b, 33), st>>>(b, u, inst, n, d_X);
+    else if (fmt == 2) ukf_sigma2_kernel<false><<<(n + 31) / 32, 32, ukf_warp_smem_bytes(b, 33), st>>>(b, u, inst, n, d_X);
     else ukf_sigma1_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(b, u, inst, n, d_X);
     return cudaGetLastError();
 }
@@ -1779,7 +2502,8 @@ bool ukf_gen2_supported(const BatchState& b) { return b.max_meas <= UKF2_MAX_UPD
 cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const StepInputs& in, const UkfScratch& u, cudaStream_t st,
                             const UkfStreams& xs, int* launched) {
     const int qblocks = (b.batch + QL_LANES - 1) / QL_LANES;
-    if (u.gen == 2 && ukf_gen2_supported(b)) {
+    if (u.gen >= 2 && ukf_gen2_supported(b)) {
+        const bool gen3 = u.gen == 3;
         // Optionally (slam_tune key 10; default 1 = off) the batch is cut into nsub contiguous slices, each with its own
         // front -> QL -> back chain on its own stream, so that the QL kernel -- a pure latency chain, one thread per
         // instance, ~0.8 n^2 dependent rotations -- can run under the other slices' kernels.  Measured on B200 (4096
@@ -1801,13 +2525,28 @@ cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const St
             if (i1 <= i0) continue;
             cudaStream_t sk = (k == 0) ? st : xs.aux[k - 1];
             ukf_front2_kernel<<<i1 - i0, UKF_THREADS, fsm, sk>>>(b, u, i0);
-            if (nsub == 1) ukf_ql_kernel<true><<<(i1 - i0 + QL_LANES - 1) / QL_LANES, QL_LANES, ql_smem_bytes(b), sk>>>(u, b.meta, b.batch, i0, i1);
-            else ukf_ql_kernel<false><<<(i1 - i0 + QL_LANES - 1) / QL_LANES, QL_LANES, 0, sk>>>(u, b.meta, b.batch, i0, i1);
             const int full = ukf_wld(b);
             const bool two_pass = u.narrow && full > UKF_NARROW_WLD;
-            if (two_pass || full == 13) ukf_back2_kernel<13><<<i1 - i0, 32, ukf_warp_smem_bytes(b, 13), sk>>>(b, fc, in, u, i0, two_pass ? 0 : 2);
-            if (full == 25) ukf_back2_kernel<25><<<i1 - i0, 32, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
-            else if (full == 33) ukf_back2_kernel<33><<<i1 - i0, 32, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
+            if (gen3) {
+                // parallel eigensolver + dense S-products; the instances it declines (nswp = -2) go on to the QL route below
+                if (b.n_max <= 128) ukf_eig3_kernel<128><<<i1 - i0, 128, eig3_carve(b.n_max, 128, nullptr, nullptr), sk>>>(b, u, i0, u.maxc);
+                else ukf_eig3_kernel<256><<<i1 - i0, 256, eig3_carve(b.n_max, 256, nullptr, nullptr), sk>>>(b, u, i0, u.maxc);
+                if (u.multiwarp) {
+                    if (two_pass || full == 13) ukf_back3_kernel<13><<<i1 - i0, 96, ukf_warp_smem_bytes(b, 13), sk>>>(b, fc, in, u, i0, two_pass ? 0 : 2);
+                    if (full == 25) ukf_back3_kernel<25><<<i1 - i0, 192, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
+                    else if (full == 33) ukf_back3_kernel<33><<<i1 - i0, 256, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
+                } else {
+                    if (two_pass || full == 13) ukf_back2_kernel<13, true><<<i1 - i0, 32, ukf_warp_smem_bytes(b, 13), sk>>>(b, fc, in, u, i0, two_pass ? 0 : 2);
+                    if (full == 25) ukf_back2_kernel<25, true><<<i1 - i0, 32, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
+                    else if (full == 33) ukf_back2_kernel<33, true><<<i1 - i0, 32, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
+                }
+                nback += 1 + (two_pass ? 2 : 1);
+            }
+            if (nsub == 1) ukf_ql_kernel<true><<<(i1 - i0 + QL_LANES - 1) / QL_LANES, QL_LANES, ql_smem_bytes(b), sk>>>(u, b.meta, b.batch, i0, i1, gen3 ? 1 : 0);
+            else ukf_ql_kernel<false><<<(i1 - i0 + QL_LANES - 1) / QL_LANES, QL_LANES, 0, sk>>>(u, b.meta, b.batch, i0, i1, gen3 ? 1 : 0);
+            if (two_pass || full == 13) ukf_back2_kernel<13, false><<<i1 - i0, 32, ukf_warp_smem_bytes(b, 13), sk>>>(b, fc, in, u, i0, two_pass ? 0 : 2);
+            if (full == 25) ukf_back2_kernel<25, false><<<i1 - i0, 32, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
+            else if (full == 33) ukf_back2_kernel<33, false><<<i1 - i0, 32, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
             nback += (two_pass ? 2 : 1);
         }
         for (int k = 1; k < nsub; ++k) {
@@ -1820,7 +2559,7 @@ cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const St
         if (launched) *launched = 2 * nsub + nback + 2;
     } else {
         ukf_front_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, fc, in, u, 0);
-        ukf_ql_kernel<true><<<qblocks, QL_LANES, ql_smem_bytes(b), st>>>(u, b.meta, b.batch, 0, b.batch);
+        ukf_ql_kernel<true><<<qblocks, QL_LANES, ql_smem_bytes(b), st>>>(u, b.meta, b.batch, 0, b.batch, 0);
         ukf_back_kernel<<<b.batch, UKF_THREADS, ukf_step_smem_bytes(b), st>>>(b, fc, in, u, 0);
         if (launched) *launched = 3;
     }

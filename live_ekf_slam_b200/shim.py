@@ -33,7 +33,7 @@ ABI_SYMBOLS = (
     "slam_sim_meas", "slam_sim_n_meas", "slam_sim_get_truth", "slam_sim_get_meas",
     "slam_run", "slam_run_device", "slam_reset", "slam_step_io", "slam_run_io", "slam_set_profiling", "slam_get_profile",
     "slam_accumulate_error", "slam_get_stats", "slam_reset_stats", "slam_get_error_histogram",
-    "slam_kernel_launches", "slam_build_info", "slam_tune",
+    "slam_kernel_launches", "slam_build_info", "slam_tune", "slam_get_ukf_routes",
 )
 
 _lib = None
@@ -104,6 +104,7 @@ def load(path: str | None = None):
     L.slam_kernel_launches.restype = C.c_longlong
     L.slam_build_info.argtypes = [C.c_char_p, C.c_int]
     L.slam_tune.argtypes = [vp, C.c_int, C.c_int]
+    L.slam_get_ukf_routes.argtypes = [vp, C.POINTER(C.c_longlong)]
     if path is None:
         _lib = L
     return L
@@ -323,6 +324,12 @@ class FilterBatch:
         """slam_run_io: a whole recorded run through HOST buffers (numpy arrays, pinned torch tensors or raw
         addresses); asynchronous -- synchronize() before reading poses_out."""
         self._ck(self._L.slam_run_io(self._h, _ptr(fwd), _ptr(ang), cmd_stride, _ptr(meas), _ptr(n_meas), _ptr(poses_out), T))
+
+    def ukf_routes(self) -> np.ndarray:
+        """instance-steps taken by the dense (generation 3), QL (generation 2) and explicit-eigenvector / rescue routes"""
+        out = np.zeros(3, dtype=np.int64)
+        self._ck(self._L.slam_get_ukf_routes(self._h, out.ctypes.data_as(C.POINTER(C.c_longlong))))
+        return out
 
     def tune(self, key: int, value: int):
         self._ck(self._L.slam_tune(self._h, key, value))

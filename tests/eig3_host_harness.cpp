@@ -1,0 +1,103 @@
+// Host harness for csrc/eig3.cuh: runs the per-thread building blocks of the generation-3 tridiagonal eigensolver with the
+// kernel's orchestration (ukf_eig3_kernel: splits, bisection, clusters, twisted vectors, Gram-Schmidt rounds, refinement,
+// residual check) emulated thread by thread on the CPU.  stdin: n maxc, then d[0..n), e[0..n-1).  stdout: status line
+// ("ok" | "declined <why>"), then lambda[0..n), then V row by row (V[i][k] = component i of eigenvector k).
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <algorithm>
+#include <cmath>
+#include "../live_ekf_slam_b200/csrc/eig3.cuh"
+
+using namespace slam::eig3;
+
+int main() {
+    int n = 0, maxc = 16;
+    if (scanf("%d %d", &n, &maxc) != 2) return 2;
+    std::vector<double> d(n), e(n, 0.0), e2(n), lam(n), xs(n);
+    for (int i = 0; i < n; ++i) if (scanf("%lf", &d[i]) != 1) return 2;
+    for (int i = 0; i + 1 < n; ++i) if (scanf("%lf", &e[i]) != 1) return 2;
+    double tn = 0.0;
+    for (int t = 0; t < n; ++t) tn = std::max(tn, std::fabs(d[t]) + (t > 0 ? std::fabs(e[t - 1]) : 0.0) + std::fabs(e[t]));
+    std::vector<double> e0 = e;
+    for (int t = 0; t + 1 < n; ++t) if (std::fabs(e0[t]) <= EPS * (std::fabs(d[t]) + std::fabs(d[t + 1]))) e[t] = 0.0;
+    double e2max = 0.0;
+    for (int t = 0; t < n; ++t) { e2[t] = e[t] * e[t]; e2max = std::max(e2max, e2[t]); }
+    const double pivmin = std::max(2.2250738585072014e-308 * std::max(1.0, e2max), 1e-300), pivf = EPS * tn;
+    std::vector<int> b0(n), b1(n), crank(n), cfirst(n), tw(n);
+    std::vector<De> de(n);
+    for (int t = 0; t < n; ++t) de[t] = De{d[t], t > 0 ? e2[t - 1] : 0.0};
+    for (int t = 0; t < n; ++t) {
+        int a = t; while (a > 0 && e[a - 1] != 0.0) --a;
+        int b = t + 1; while (b < n && e[b - 1] != 0.0) ++b;
+        b0[t] = a; b1[t] = b;
+        lam[t] = bisect(d.data(), e.data(), de.data(), a, b, t - a, pivmin);
+    }
+    int maxrank = 0;
+    for (int t = 0; t < n; ++t) {
+        const int a = b0[t];
+        const double ortol = 1.0e-3 * tn;
+        int cr = 0;
+        while (t - cr > a && lam[t - cr] - lam[t - cr - 1] < ortol && cr <= maxc) ++cr;
+        if (cr >= maxc && cr > 0) { printf("declined cluster\n"); return 0; }
+        crank[t] = cr; cfirst[t] = t - cr; maxrank = std::max(maxrank, cr);
+        double x = lam[cfirst[t]];
+        for (int q = cfirst[t] + 1; q <= t; ++q) { const double lq = lam[q], pert = 10.0 * EPS * std::fabs(lq); x = (lq - x < pert) ? x + pert : lq; }
+        xs[t] = x;
+    }
+    std::vector<double> V((size_t)n * n, 0.0), W((size_t)n * n, 0.0);
+    bool bad = false;
+    for (int t = 0; t < n; ++t) {
+        const Slot z{V.data() + t, n}, w{W.data() + t, n};
+        const int a = b0[t], b = b1[t];
+        tw[t] = a;
+        if (b - a == 1) { z.set(a, 1.0); continue; }
+        double n2 = 1.0;
+        tw[t] = twisted_vector(d.data(), e.data(), e2.data(), a, b, xs[t], pivf, z, w, &n2);
+        if (!(n2 > 0.0) || !std::isfinite(n2)) bad = true;
+        const double sc = 1.0 / std::sqrt(n2);
+        for (int i = a; i < b; ++i) z.set(i, z.get(i) * sc);
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) {
+            if (maxrank == 0) break;
+            for (int t = 0; t < n; ++t) {
+                const int a = b0[t], b = b1[t];
+                const bool incl = b - a > 1 && (crank[t] > 0 || (t + 1 < b && crank[t + 1] > 0));
+                if (!incl) continue;
+                const Slot z{V.data() + t, n}, w{W.data() + t, n};
+                const double n2 = twisted_solve(e.data(), a, b, tw[t], z, w);
+                if (!(n2 > 0.0) || !std::isfinite(n2)) bad = true;
+                const double sc = 1.0 / std::sqrt(n2);
+                for (int i = a; i < b; ++i) z.set(i, z.get(i) * sc);
+            }
+        }
+        for (int r = 1; r <= maxrank; ++r)
+            for (int t = 0; t < n; ++t) if (crank[t] == r) {
+                const Slot z{V.data() + t, n};
+                const int a = b0[t], b = b1[t];
+                for (int q = cfirst[t]; q < t; ++q) {
+                    double dot = 0.0;
+                    for (int i = a; i < b; ++i) dot += V[(size_t)i * n + q] * z.get(i);
+                    for (int i = a; i < b; ++i) z.set(i, z.get(i) - dot * V[(size_t)i * n + q]);
+                }
+                double n2 = 0.0;
+                for (int i = a; i < b; ++i) n2 += z.get(i) * z.get(i);
+                if (pass == 1 && !(n2 > 1.0e-6)) bad = true;    // (first pass: twisted vectors of a pathologically close pair may coincide; the refinement separates them)
+                if (getenv("EIG3_DEBUG")) fprintf(stderr, "mgs pass %d t=%d n2=%g\n", pass, t, n2);
+                const double sc = 1.0 / std::sqrt(n2);
+                for (int i = a; i < b; ++i) z.set(i, z.get(i) * sc);
+            }
+    }
+    for (int t = 0; t < n; ++t) {
+        const int a = b0[t], b = b1[t];
+        if (b - a == 1) continue;
+        const double r = residual_inf(d.data(), e.data(), a, b, lam[t], Slot{V.data() + t, n}, 1.0);
+        if (!(r <= 1.0e-12 * tn)) bad = true;
+    }
+    if (bad) { printf("declined residual\n"); return 0; }
+    printf("ok\n");
+    for (int t = 0; t < n; ++t) printf("%.17g\n", lam[t]);
+    for (int i = 0; i < n; ++i) { for (int k = 0; k < n; ++k) printf("%.17g ", V[(size_t)i * n + k]); printf("\n"); }
+    return 0;
+}

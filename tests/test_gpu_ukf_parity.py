@@ -163,12 +163,18 @@ def test_ukf_filter_class(shim, oracle):
     assert msg["P"].size == of.n * of.n and msg["M"] == of.M
 
 
-@pytest.mark.parametrize("knobs", [((7, 1),), ((7, 2),), ((7, 2), (8, 600)), ((7, 2), (9, 1)), ((7, 2), (8, 2500), (9, 1)), ((7, 2), (11, 0))],
-                         ids=["generation1", "generation2", "rescue_pass_only", "clip_overflow_pass", "mixed_rescue", "full_width_tile_only"])
+@pytest.mark.parametrize("knobs", [((7, 1),), ((7, 2),), ((7, 2), (8, 600)), ((7, 2), (9, 1)), ((7, 2), (8, 2500), (9, 1)), ((7, 2), (11, 0)),
+                                   ((7, 3),), ((7, 3), (12, 1)), ((7, 3), (12, 1), (8, 600)), ((7, 3), (9, 1)), ((7, 3), (11, 0)),
+                                   ((7, 3), (13, 0)), ((7, 3), (13, 0), (9, 1))],
+                         ids=["generation1", "generation2", "rescue_pass_only", "clip_overflow_pass", "mixed_rescue", "full_width_tile_only",
+                              "generation3", "gen3_clusters_take_the_ql_route", "gen3_ql_route_then_rescue", "gen3_clip_overflow_pass",
+                              "gen3_full_width_tile_only", "gen3_single_warp_back_kernel", "gen3_single_warp_clip_overflow"])
 def test_ukf_step_variants(shim, oracle, knobs):
     """The same free-running batch through the alternative code paths of the UKF step: the generation-1 kernels
     (explicit eigenvectors), a rotation log too small for any / for the later steps (rescue pass on the generation-1
-    kernels), and only one clipped eigenvector allowed beside the first S-pass (overflow pass into the seed)."""
+    kernels), only one clipped eigenvector allowed beside the first S-pass (overflow pass into the seed); generation 3
+    (parallel tridiagonal eigensolver + dense products, the default) alone, with every cluster of close eigenvalues declined
+    (those instances take the QL route of generation 2 in the same step), and with that route's log too small as well."""
     p, lm, fwd, ang = H.config2(seed=4, steps=120, filt="ukf_slam")
     op = H.oracle_params(oracle, p)
     B = 5
@@ -272,7 +278,8 @@ def test_ukf_capacity_variants(shim, oracle, max_lm, max_meas):
     print("ukf capacity variant", max_lm, max_meas, "worst", worst)
 
 
-@pytest.mark.parametrize("knobs", [(), ((7, 1),), ((8, 600),)], ids=["generation2", "generation1", "rescue_pass"])
+@pytest.mark.parametrize("knobs", [(), ((7, 2),), ((7, 1),), ((7, 2), (8, 600)), ((7, 3), (12, 1))],
+                         ids=["generation3", "generation2", "generation1", "rescue_pass", "gen3_ql_route"])
 def test_ukf_sigma_points_getter(shim, oracle, knobs):
     """slam_get_sigma_points: X of the last update (ukf.cpp:214-220, published point-major by ukf.cpp:91-99), materialised
     on demand from the factors the step kernels leave on the device, against the oracle's X after the same update.
