@@ -160,7 +160,9 @@ int  slam_run_device(slam_handle_t h, slam_sim_t s, const float* d_cmd_fwd, cons
 /* Filter::init executed on the device (no host staging, asynchronous): used between Monte-Carlo sweeps */
 int  slam_reset(slam_handle_t h, float x_0, float y_0, float yaw_0);
 /* Filter::update + the pose read-back of publishState in one asynchronous call: HOST buffers in, HOST poses
- * [batch][3] out (pinned memory makes both copies truly asynchronous); the caller synchronises. */
+ * [batch][3] out; the caller synchronises (slam_synchronize) before reading poses_out.  With PINNED host buffers
+ * (cudaHostAlloc / cudaHostRegister / torch pin_memory) the kernels read the inputs and write the poses in place over
+ * PCIe -- no staging copies, one kernel launch per tick for the batched EKF; pageable buffers are staged through copies. */
 int  slam_step_io(slam_handle_t h, const float* fwd, const float* ang, int cmd_stride,
                   const float* meas, const int* n_meas, double* poses_out);
 
@@ -217,7 +219,8 @@ int  slam_get_ukf_routes(slam_handle_t h, long long* out /* 3 */);
  * with its eigenvectors, default; 2 = QL rotation log replayed on the vectors, warp per instance; 1 = explicit eigenvector matrix,
  * CTA per instance); key 12: largest cluster of close eigenvalues the generation-3 eigensolver re-orthogonalises itself (larger
  * clusters send the instance down the generation-2 route in the same step; 1 forces that route for any cluster); key 13: 0 = the
- * one-warp-per-instance back kernel of generation 3 instead of the multi-warp one; key 8: capacity of the UKF rotation log
+ * one-warp-per-instance back kernel of generation 3 instead of the multi-warp one; key 14: 1 = slam_step_io always stages its
+ * buffers through device copies, even when they are pinned host memory the kernels could read in place; key 8: capacity of the UKF rotation log
  * (shrinking it forces the rescue pass); key 9: max clipped eigenvectors riding beside the first S-pass; key 10: slices of the UKF batch that run their
  * front -> QL -> back chains on separate streams (1..8); key 11: 0 = skip the narrow-tile first pass of the UKF back kernel.
  * Results never depend on any of them (keys 7-9: up to rounding, inside the parity tolerance). */

@@ -57,6 +57,10 @@ struct slam_filter {
     float* d_rmeas[2] = {nullptr, nullptr}; int* d_rn[2] = {nullptr, nullptr}; double* d_rposes[2] = {nullptr, nullptr};
     int r_chunk_cap = 0;              // steps the replay buffers hold
     cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
+    static constexpr int MAX_MAPPED = 8;          // verified pinned-host ranges (slam_step_io zero-copy path)
+    uintptr_t mapped_lo[MAX_MAPPED] = {}, mapped_hi[MAX_MAPPED] = {};
+    int n_mapped = 0, mapped_next = 0;
+    int no_zero_copy = 0;                          // slam_tune key 14: force the staged path (tests compare both)
     unsigned long long* d_hist = nullptr; int hist_cap = 0;   // scratch of slam_get_error_histogram (grown on demand, kept)
     double* d_avg = nullptr;
     bool profiling = false;           // per-launch events around the per-step filter kernel
@@ -171,16 +175,21 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
     CK(cudaMalloc(&b.meta, sizeof(int4) * batch));
     CK(cudaMalloc(&b.assoc, sizeof(int) * (size_t)batch * b.max_meas));
     CK(cudaMalloc(&b.retry_list, sizeof(int) * batch));
-    CK(cudaMalloc(&b.retry_count, sizeof(int)));
+    CK(cudaMalloc(&b.retry_count, 2 * sizeof(int)));
     CK(cudaMalloc(&b.max_M, sizeof(int)));
     CK(cudaMalloc(&h->d_work, 2 * sizeof(int)));
     CK(cudaMalloc(&h->d_progress, sizeof(int) * batch));
     CK(cudaMemset(h->d_progress, 0, sizeof(int) * batch));
     CK(cudaMallocHost(&h->h_run_hint, sizeof(int) * slam_filter::HINT_RING));
     for (int i = 0; i < slam_filter::HINT_RING; ++i) CK(cudaEventCreateWithFlags(&h->run_ev[i], cudaEventDisableTiming));
-    CK(cudaMemset(b.retry_count, 0, sizeof(int)));
+    CK(cudaMemset(b.retry_count, 0, 2 * sizeof(int)));
     CK(cudaMemset(b.max_M, 0, sizeof(int)));
-    CK(cudaMallocHost(&h->h_hint, sizeof(int) * slam_filter::HINT_RING));
+    CK(cudaHostAlloc(&h->h_hint, sizeof(int) * slam_filter::HINT_RING, cudaHostAllocMapped));
+    b.hint_host = nullptr;
+    if (kind == SLAM_EKF_SLAM) {      // the batched EKF's retry pass posts max(M) into h_hint[0] itself
+        int* dptr = nullptr;
+        if (cudaHostGetDevicePointer(&dptr, h->h_hint, 0) == cudaSuccess) b.hint_host = dptr; else cudaGetLastError();
+    }
     for (int i = 0; i < slam_filter::HINT_RING; ++i) { h->h_hint[i] = 0; CK(cudaEventCreateWithFlags(&h->hint_ev[i], cudaEventDisableTiming)); }
     CK(cudaMalloc(&b.stats, sizeof(double) * (size_t)batch * SLAM_NUM_STATS));
     if (kind == SLAM_UKF_SLAM || kind == SLAM_UKF_LOC) {
@@ -312,6 +321,7 @@ int slam_tune(slam_handle_t h, int key, int value) {
     else if (key == 7) { if (value < 1 || value > 3) return fail(h, "slam_tune: UKF generation must be 1, 2 or 3"); h->uk.gen = value; }
     else if (key == 12) h->uk.maxc = value < 0 ? 0 : value;
     else if (key == 13) h->uk.multiwarp = value ? 1 : 0;
+    else if (key == 14) h->no_zero_copy = value ? 1 : 0;
     else if (key == 8) {     // shrink the rotation log (test knob: forces the rescue pass); never beyond the allocation
         long long full = 2LL * h->b.n_max * h->b.n_max;
         if (full < 256) full = 256;
@@ -350,6 +360,7 @@ int slam_init(slam_handle_t h, float x_0, float y_0, float yaw_0) {
     CK(cudaMemsetAsync(b.ids, 0, sizeof(int) * (size_t)b.batch * b.max_lm, h->stream));
     CK(cudaMemsetAsync(b.max_M, 0, sizeof(int), h->stream));
     h->step_seq = 0; h->hint_base = 0;
+    if (h->h_hint) h->h_hint[0] = 0;
     if (h->uk.sigfmt) CK(cudaMemsetAsync(h->uk.sigfmt, 0, sizeof(int2) * b.batch, h->stream));
     CK(cudaMemsetAsync(b.assoc, 0xff, sizeof(int) * (size_t)b.batch * b.max_meas, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -357,7 +368,7 @@ int slam_init(slam_handle_t h, float x_0, float y_0, float yaw_0) {
 }
 
 static int do_step(slam_filter* h, const float* d_fwd, const float* d_ang, int cmd_stride, const float* d_meas,
-                   const int* d_nmeas, int phases) {
+                   const int* d_nmeas, int phases, double* fused_poses = nullptr) {
     CK(cudaSetDevice(h->device));
     if (h->large) {
         if (phases != (STEP_PREDICT | STEP_UPDATE)) return fail(h, "split predict/update is not available on the large-map path");
@@ -381,7 +392,7 @@ static int do_step(slam_filter* h, const float* d_fwd, const float* d_ang, int c
         if (h->profiling || pg) h->ev_used += 2;
         return 0;
     }
-    StepInputs in{d_fwd, d_ang, cmd_stride, d_meas, d_nmeas};
+    StepInputs in{d_fwd, d_ang, cmd_stride, d_meas, d_nmeas, fused_poses};
     if (h->kind != SLAM_EKF_SLAM && phases != (STEP_PREDICT | STEP_UPDATE))
         return fail(h, "split predict/update is defined for EKF_SLAM only: the UKF update stage consumes the sigma points of the same call (ukf.cpp:305-337)");
     if (h->profiling) {
@@ -394,12 +405,24 @@ static int do_step(slam_filter* h, const float* d_fwd, const float* d_ang, int c
     }
     // capacity for this launch: max(M) as it was HINT_LAG launches ago (its copy has long completed, so the wait
     // below never blocks in steady state but bounds how far the host can run ahead) plus headroom
+    const bool posted_hint = h->kind == SLAM_EKF_SLAM && !h->large && h->b.hint_host != nullptr;
     int cap = h->b.max_lm;
     if (h->cap_force > 0) cap = h->cap_force;
     else if (h->step_seq >= slam_filter::HINT_LAG) {
-        const int slot = (int)((h->step_seq - slam_filter::HINT_LAG) % slam_filter::HINT_RING);
-        CK(cudaEventSynchronize(h->hint_ev[slot]));
-        cap = h->h_hint[slot] + h->cap_headroom;
+        if (posted_hint) {
+            // max(M) as the retry pass of an earlier launch posted it into mapped host memory (stale values are conservative:
+            // too small a tile only sends instances to the retry pass).  Every 8th launch leaves an event behind and waits for
+            // the one of 16 launches ago, which bounds how far the host can run ahead of the device.
+            if ((h->step_seq & 7) == 0) {
+                const int slot = (int)((h->step_seq >> 3) % slam_filter::HINT_RING);
+                if (h->step_seq >= 24) CK(cudaEventSynchronize(h->hint_ev[(slot + slam_filter::HINT_RING - 2) % slam_filter::HINT_RING]));
+            }
+            cap = *(volatile int*)&h->h_hint[0] + h->cap_headroom;
+        } else {
+            const int slot = (int)((h->step_seq - slam_filter::HINT_LAG) % slam_filter::HINT_RING);
+            CK(cudaEventSynchronize(h->hint_ev[slot]));
+            cap = h->h_hint[slot] + h->cap_headroom;
+        }
     } else cap = h->hint_base + (int)(h->step_seq + 1) * h->b.max_meas;      // M can grow by at most max_meas per step
     if (h->kind == SLAM_EKF_SLAM) {
         CK(launch_ekf_step(h->b, h->fc, in, phases, cap, h->force_threads, h->stream));
@@ -407,13 +430,16 @@ static int do_step(slam_filter* h, const float* d_fwd, const float* d_ang, int c
     else if (h->kind == SLAM_NAIVE) { CK(launch_naive_step(h->b, in, h->stream)); h->launches += 1; }
     else { int nl = 0; CK(launch_ukf_step(h->b, h->fc, in, h->uk, h->stream, h->uks, &nl)); h->launches += nl; }
     if (h->profiling) { CK(cudaEventRecord(h->ev[h->ev_used + 1], h->stream)); h->ev_used += 2; }
-    {
+    if (posted_hint) {
+        if ((h->step_seq & 7) == 0) CK(cudaEventRecord(h->hint_ev[(int)((h->step_seq >> 3) % slam_filter::HINT_RING)], h->stream));
+        h->step_seq += 1;
+    } else {
         const int slot = (int)(h->step_seq % slam_filter::HINT_RING);
         CK(cudaMemcpyAsync(&h->h_hint[slot], h->b.max_M, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaEventRecord(h->hint_ev[slot], h->stream));
         h->step_seq += 1;
     }
-    if (h->kind == SLAM_EKF_SLAM) h->launches += (cap < h->b.max_lm) ? 2 : 1;
+    if (h->kind == SLAM_EKF_SLAM) h->launches += (cap < h->b.max_lm || posted_hint) ? 2 : 1;
     return 0;
 }
 
@@ -844,16 +870,75 @@ int slam_reset(slam_handle_t h, float x_0, float y_0, float yaw_0) {
     CK(cudaMemsetAsync(h->b.max_M, 0, sizeof(int), h->stream));
     if (h->uk.sigfmt) CK(cudaMemsetAsync(h->uk.sigfmt, 0, sizeof(int2) * h->b.batch, h->stream));
     h->step_seq = 0; h->hint_base = 0;
+    if (h->h_hint) h->h_hint[0] = 0;
     h->launches += 1;
     return 0;
 }
 
+// Is [p, p + bytes) pinned host memory the device can address at the same pointer value (cudaHostAlloc / cudaHostRegister /
+// torch pin_memory under unified addressing)?  Verified ranges are remembered per handle, so a caller that walks through one
+// big pinned buffer tick after tick pays the driver query once.
+static bool host_mapped(slam_filter* h, const void* p, size_t bytes) {
+    const uintptr_t a = (uintptr_t)p;
+    for (int i = 0; i < h->n_mapped; ++i)
+        if (a >= h->mapped_lo[i] && a + bytes <= h->mapped_hi[i]) return true;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (at.type != cudaMemoryTypeHost || at.devicePointer != p) return false;
+    // extent of the allocation (driver API through the runtime's entry-point lookup: no link-time dependency on libcuda)
+    typedef int (*attr_fn)(void*, int, unsigned long long);
+    static attr_fn fn = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &f, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) fn = (attr_fn)f;
+        else cudaGetLastError();
+    }
+    unsigned long long start = 0;
+    size_t size = 0;
+    uintptr_t lo = a, hi = a + bytes;
+    if (fn && fn(&start, 11 /* CU_POINTER_ATTRIBUTE_RANGE_START_ADDR */, (unsigned long long)a) == 0 &&
+        fn(&size, 12 /* CU_POINTER_ATTRIBUTE_RANGE_SIZE */, (unsigned long long)a) == 0 && start && size) {
+        lo = (uintptr_t)start; hi = lo + size;
+        if (a + bytes > hi) return false;
+    }
+    const int slot = h->n_mapped < slam_filter::MAX_MAPPED ? h->n_mapped++ : (h->mapped_next++ % slam_filter::MAX_MAPPED);
+    h->mapped_lo[slot] = lo; h->mapped_hi[slot] = hi;
+    return true;
+}
+
+// Filter::update + the pose read-back of publishState in one asynchronous call.  When the caller's buffers are pinned (mapped)
+// host memory the kernels read them and write the poses IN PLACE over PCIe: no staging copies, and for the batched EKF no
+// separate pose kernel either (one launch per tick).  Pageable buffers take the staged path (copies on the handle's stream).
 int slam_step_io(slam_handle_t h, const float* fwd, const float* ang, int cmd_stride, const float* meas, const int* n_meas, double* poses_out) {
-    if (slam_step(h, fwd, ang, cmd_stride, meas, n_meas)) return 1;
-    if (poses_out) {
-        CK(launch_poses(h->b, h->d_out, h->stream));
+    if (!h) return 1;
+    if (!fwd || !ang || !meas || !n_meas) return fail(h, "slam_step_io: NULL argument");
+    CK(cudaSetDevice(h->device));
+    const BatchState& b = h->b;
+    const size_t nc = cmd_stride ? (size_t)b.batch : 1;
+    const bool zero_copy = !h->large && !h->no_zero_copy && host_mapped(h, fwd, sizeof(float) * nc) && host_mapped(h, ang, sizeof(float) * nc) &&
+                           host_mapped(h, meas, sizeof(float) * 3 * (size_t)b.batch * b.max_meas) && host_mapped(h, n_meas, sizeof(int) * b.batch);
+    const bool poses_mapped = poses_out && !h->no_zero_copy && host_mapped(h, poses_out, sizeof(double) * 3 * b.batch);
+    const bool fuse = poses_mapped && h->kind == SLAM_EKF_SLAM && !h->large;
+    if (zero_copy) {
+        // the float4 path of the gather kernel needs a 16-byte aligned message block; a small batch reads in place
+        const size_t mf = 3 * (size_t)b.batch * b.max_meas;
+        if (b.batch >= 64 && ((uintptr_t)meas & 15) == 0) {
+            CK(launch_gather_inputs(fwd, ang, (int)nc, n_meas, meas, b.batch, (int)mf, h->d_fwd, h->d_ang, h->d_nmeas, h->d_meas, h->stream));
+            h->launches += 1;
+            if (do_step(h, h->d_fwd, h->d_ang, cmd_stride, h->d_meas, h->d_nmeas, STEP_PREDICT | STEP_UPDATE, fuse ? poses_out : nullptr)) return 1;
+        } else if (do_step(h, fwd, ang, cmd_stride, meas, n_meas, STEP_PREDICT | STEP_UPDATE, fuse ? poses_out : nullptr)) return 1;
+    } else {
+        if (stage_cmd(h, fwd, ang, cmd_stride) || stage_meas(h, meas, n_meas)) return 1;
+        if (do_step(h, h->d_fwd, h->d_ang, cmd_stride, h->d_meas, h->d_nmeas, STEP_PREDICT | STEP_UPDATE, fuse ? poses_out : nullptr)) return 1;
+    }
+    if (poses_out && !fuse) {
+        double* dst = poses_mapped ? poses_out : h->d_out;
+        CK(launch_poses(h->b, dst, h->stream));
         h->launches += 1;
-        CK(cudaMemcpyAsync(poses_out, h->d_out, sizeof(double) * 3 * h->b.batch, cudaMemcpyDeviceToHost, h->stream));
+        if (!poses_mapped) CK(cudaMemcpyAsync(poses_out, h->d_out, sizeof(double) * 3 * h->b.batch, cudaMemcpyDeviceToHost, h->stream));
     }
     return 0;
 }

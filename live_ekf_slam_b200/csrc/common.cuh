@@ -29,7 +29,8 @@ struct BatchState {
     int4* meta;        // [batch] {M, status, timestep, n_assoc}: one 16-byte load per instance at kernel entry
     int* assoc;
     int* retry_list;   // [batch] instances deferred by a capacity-limited launch
-    int* retry_count;  // [1]
+    int* retry_count;  // [2]: [0] deferred instances of this step, [1] CTAs of the retry pass that have finished
+    int* hint_host;    // mapped pinned host word (or null): the retry pass posts max_M there -- the capacity hint without a copy
     int* max_M;        // [1] running max of M over the batch (capacity hint for the next launches)
     double* stats;     // [batch][SLAM_NUM_STATS] per-instance accumulators
     double* sigma;     // UKF only: [batch][sigma_stride] sigma points X (point-major), optional
@@ -178,7 +179,10 @@ struct StepInputs {
     int cmd_stride;        // 0 shared / 1 per instance
     const float* meas;     // device [batch][max_meas][3]
     const int* n_meas;     // device [batch]
+    double* poses;         // optional [batch][3]: the batched EKF step kernel writes the committed vehicle pose itself (the
+                           // pose read-back of publishState fused into the step); device or MAPPED PINNED HOST memory
 };
+// (all StepInputs pointers may be mapped pinned host memory: the kernels then read the caller's buffers over PCIe directly)
 
 enum { STEP_PREDICT = 1, STEP_UPDATE = 2 };
 
@@ -299,6 +303,8 @@ cudaError_t launch_error_histogram(const BatchState& b, double* d_avg, unsigned 
                                    cudaStream_t st);
 cudaError_t launch_reduce_stats(const BatchState& b, double* d_out, cudaStream_t st);
 cudaError_t launch_poses(const BatchState& b, double* d_out, cudaStream_t st);
+cudaError_t launch_gather_inputs(const float* h_fwd, const float* h_ang, int ncmd, const int* h_n, const float* h_meas, int batch,
+                                 int meas_floats, float* d_fwd, float* d_ang, int* d_n, float* d_meas, cudaStream_t st);
 cudaError_t launch_reset(const BatchState& b, double x0, double y0, double a2, double a3, cudaStream_t st);
 
 }  // namespace slam

@@ -473,7 +473,10 @@ __device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterCo
     const int4 meta_in = b.meta[inst];
     int nm = (phases & STEP_UPDATE) ? in.n_meas[inst] : 0;
     int status = meta_in.y;
-    if (status & SLAM_STATUS_SAME_STEP_REMATCH) return false;   // the reference process is dead past this point
+    if (status & SLAM_STATUS_SAME_STEP_REMATCH) {               // the reference process is dead past this point
+        if (in.poses && tid < 3) in.poses[3 * (size_t)inst + tid] = b.x[(size_t)inst * b.x_stride + tid];   // frozen pose
+        return false;
+    }
     int M = meta_in.x;
     const int M_start = M;
     const int n0 = 3 + 2 * M;
@@ -507,6 +510,7 @@ __device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterCo
     if (!alive) {
         // frozen at the last committed state (global memory still holds it): only the status word changes
         if (tid == 0) b.meta[inst] = make_int4(meta_in.x, status, meta_in.z, 0);
+        if (in.poses && tid < 3) in.poses[3 * (size_t)inst + tid] = gx[tid];
         return true;
     }
     const int n = 3 + 2 * M;
@@ -517,6 +521,7 @@ __device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterCo
     }
     for (int i = tid + M_start; i < M; i += THREADS) b.ids[(size_t)inst * b.max_lm + i] = s.ids[i];
     for (int i = tid; i < nm; i += THREADS) { const int a = s.assoc[i]; b.assoc[(size_t)inst * b.max_meas + i] = a < 0 ? -1 : a; }
+    if (in.poses && tid < 3) in.poses[3 * (size_t)inst + tid] = s.x[tid];      // publishState's pose, fused (ekf.cpp:196-198)
     fence_proxy_async();     // generic-proxy writes of P must be visible to the bulk-copy engine
     CtaSync<THREADS>::sync();
     if (tid == 0) {
@@ -560,6 +565,15 @@ ekf_step_kernel(BatchState b, FilterConst fc, StepInputs in, int phases, EkfLaun
     for (int q = blockIdx.x; q < count; q += gridDim.x) {
         if (ekf_instance<THREADS>(b, fc, in, phases, L, s, b.retry_list[q], parity)) parity ^= 1u;
         CtaSync<THREADS>::sync();
+    }
+    // the last CTA to finish re-arms the list for the next step (no memset on the stream) and posts the capacity hint into
+    // mapped host memory (no copy, no event: max(M) only grows between resets, so a stale value is merely conservative)
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(b.retry_count + 1, 1) == (int)gridDim.x - 1) {
+            b.retry_count[0] = 0; b.retry_count[1] = 0;
+            if (b.hint_host) { *(volatile int*)b.hint_host = *(volatile int*)b.max_M; __threadfence_system(); }
+        }
     }
 }
 
@@ -811,7 +825,21 @@ static int step_occupancy(size_t smem) {
 
 // CTA width for a tile: the width that keeps the most instances resident per SM (shared memory, registers and the
 // 2048-thread limit decide); among equals the wider CTA (more lanes on each instance's O(n^2) sweep).
+static int pick_threads_uncached(size_t smem, int* per_sm_out);
+// (five occupancy queries per call are far too slow for a per-tick launch path: remembered per tile size)
 static int pick_threads(size_t smem, int* per_sm_out) {
+    struct Entry { size_t smem; int threads, per_sm; };
+    static Entry cache[128];
+    static int n_cache = 0;
+    for (int i = 0; i < n_cache; ++i)
+        if (cache[i].smem == smem) { if (per_sm_out) *per_sm_out = cache[i].per_sm; return cache[i].threads; }
+    int per_sm = 1;
+    const int th = pick_threads_uncached(smem, &per_sm);
+    if (n_cache < 128) cache[n_cache++] = Entry{smem, th, per_sm};
+    if (per_sm_out) *per_sm_out = per_sm;
+    return th;
+}
+static int pick_threads_uncached(size_t smem, int* per_sm_out) {
     const int widths[5] = {32, 64, 128, 256, 512};
     const int occ[5] = {step_occupancy<32>(smem), step_occupancy<64>(smem), step_occupancy<128>(smem),
                         step_occupancy<256>(smem), step_occupancy<512>(smem)};
@@ -872,19 +900,19 @@ cudaError_t launch_ekf_step(const BatchState& b, const FilterConst& fc, const St
     const bool limited = cap_hint > 0 && cap_hint < b.max_lm;
     const EkfLaunch L = make_launch(b, limited ? cap_hint : b.max_lm, 0);
     const size_t smem = (size_t)L.smem_bytes;
-    if (limited) {
-        cudaError_t e = cudaMemsetAsync(b.retry_count, 0, sizeof(int), st);
-        if (e != cudaSuccess) return e;
-    }
+    // (the deferred-instance counter is re-armed by the retry pass itself: no memset on the stream)
     cudaError_t e = launch_step_threads(force_threads ? force_threads : pick_threads(smem, nullptr), b.batch, smem, st, b, fc, in, phases, L);
-    if (e != cudaSuccess || !limited) return e;
+    if (e != cudaSuccess || (!limited && !b.hint_host)) return e;      // (the retry pass also posts the capacity hint)
     const EkfLaunch R = make_launch(b, b.max_lm, 1);
     const size_t rsmem = (size_t)R.smem_bytes;
     int per_sm = 1;
     int rthreads = pick_threads(rsmem, &per_sm);
     if (force_threads) { rthreads = force_threads; per_sm = (int)(SMEM_PER_SM / (rsmem + SMEM_CTA_RESERVED)) > 0 ? (int)(SMEM_PER_SM / (rsmem + SMEM_CTA_RESERVED)) : 1; }
-    const int sms = device_sm_count();
-    const int grid = b.batch < sms * per_sm ? b.batch : sms * per_sm;
+    // deferrals are rare (the tile has headroom): one CTA per SM drains them, and an empty pass costs a launch of 148 CTAs
+    static int sms = 0;
+    if (!sms) sms = device_sm_count();
+    const int grid = b.batch < sms ? b.batch : sms;
+    (void)per_sm;
     return launch_step_threads(rthreads, grid, rsmem, st, b, fc, in, phases, R);
 }
 

@@ -357,13 +357,22 @@ constexpr size_t LM_GEMM_SMEM = sizeof(double) * 2 * (GT * GLDA + GK * GLDB);   
 // P <- P + U G on the FP64 tensor cores (DMMA m8n8k4), 64 x 64 tile of P per CTA, K = 2 (updates of the step) in chunks of
 // 32 staged through a two-deep cp.async pipeline: the next chunk's U / G tiles stream into shared memory while the current
 // one feeds the tensor cores (ncu of the synchronous version: long-scoreboard stalls 40 % of the samples at 12 warps per SM).
+// Only the tiles ON OR BELOW the diagonal are computed: sum_q K_q G_q = sum_q P H^T S^-1 H P is symmetric (the batched kernels
+// already keep P packed-symmetric, ekf_batch.cu), so a tile (ty, tx), ty > tx, is written to (ty, tx) and, transposed, to
+// (tx, ty); a diagonal tile keeps its lower half and mirrors it.  Half the flops and half the reads of the full square.
 __global__ void __launch_bounds__(128) lm_gemm(LargeState L) {
     extern __shared__ __align__(16) double lm_gemm_smem[];
     const int m = L.cur[0];
     const int n = 3 + 2 * L.cur[1];
     if (m == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int row0 = blockIdx.y * GT, col0 = blockIdx.x * GT;
+    // linear index over the lower-triangular tiles, row by row: tile t = ty (ty + 1) / 2 + tx, 0 <= tx <= ty
+    int ty = (int)((sqrt(8.0 * (double)blockIdx.x + 1.0) - 1.0) * 0.5);
+    while ((ty + 1) * (ty + 2) / 2 <= (int)blockIdx.x) ++ty;
+    while (ty * (ty + 1) / 2 > (int)blockIdx.x) --ty;
+    const int tx = (int)blockIdx.x - ty * (ty + 1) / 2;
+    const int row0 = ty * GT, col0 = tx * GT;
+    const bool diag = ty == tx;
     if (row0 >= n || col0 >= n) return;
     const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;
     const int ld = L.ld;
@@ -437,8 +446,15 @@ __global__ void __launch_bounds__(128) lm_gemm(LargeState L) {
 #pragma unroll
         for (int bq = 0; bq < 4; ++bq) {
             const int r = row0 + wr + a * 8 + g, c = col0 + wc + bq * 8 + 2 * t4;
-            if (r < n && c < n) L.P[(size_t)r * ld + c] = acc[a][bq][0];
-            if (r < n && c + 1 < n) L.P[(size_t)r * ld + c + 1] = acc[a][bq][1];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int cc = c + h2;
+                if (r >= n || cc >= n) continue;
+                if (diag && cc > r) continue;                       // upper half of a diagonal tile: the mirror image writes it
+                const double v = acc[a][bq][h2];
+                L.P[(size_t)r * ld + cc] = v;
+                if (cc != r) L.P[(size_t)cc * ld + r] = v;          // mirror (8 consecutive doubles per group of lanes with equal t4)
+            }
         }
 }
 
@@ -459,8 +475,8 @@ __global__ void lm_commit(LargeState L, int n_meas) {
         L.stats[10] += nd;
         L.stats[11] += (double)n_meas;
         // really moved: P once each way through lm_gemm + the 5 rows / 5 columns per measurement; U and G written and re-read
-        L.stats[12] += 16.0 * nd * nd + (double)L.cur[0] * (80.0 * nd + 64.0 * nd);
-        L.stats[13] += 4.0 * (double)L.cur[0] * nd * nd;
+        L.stats[12] += 12.0 * nd * nd + (double)L.cur[0] * (80.0 * nd + 64.0 * nd);   // lower triangle read, full square written
+        L.stats[13] += 2.0 * (double)L.cur[0] * nd * nd;                               // the contraction runs on the lower triangle
     }
 }
 
@@ -501,7 +517,7 @@ cudaError_t launch_ekf_large_step(const LargeState& L, const FilterConst& fc, co
         if (e != cudaSuccess) return e;
         const int gt = (n_upper + GT - 1) / GT;
         if (gemm_ev0) cudaEventRecord(gemm_ev0, st);
-        lm_gemm<<<dim3(gt, gt), 128, LM_GEMM_SMEM, st>>>(L);
+        lm_gemm<<<gt * (gt + 1) / 2, 128, LM_GEMM_SMEM, st>>>(L);
         if (gemm_ev1) cudaEventRecord(gemm_ev1, st);
         *launches += 2;
     }

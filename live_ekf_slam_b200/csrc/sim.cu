@@ -286,6 +286,30 @@ __global__ void poses_kernel(BatchState b, double* out) {
     out[3 * i + 2] = (b.base == 3) ? x[2] : remainder(atan2(x[3], x[2]), TWO_PI_REF);   // ukf.cpp:71
 }
 
+// One tick's inputs from MAPPED PINNED HOST memory into the handle's HBM staging buffers, read by a wide grid with 16-byte
+// loads: the whole message block crosses PCIe once at bandwidth, instead of every step CTA stalling on a few dependent
+// round trips (and instead of four separate small DMA copies on the stream).
+__global__ void gather_inputs_kernel(const float* __restrict__ h_fwd, const float* __restrict__ h_ang, const int ncmd,
+                                     const int* __restrict__ h_n, const float* __restrict__ h_meas, const int batch, const int meas_floats,
+                                     float* d_fwd, float* d_ang, int* d_n, float* d_meas) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const int n4 = meas_floats >> 2;
+    const float4* src = reinterpret_cast<const float4*>(h_meas);
+    float4* dst = reinterpret_cast<float4*>(d_meas);
+    for (int i = tid; i < n4; i += nth) dst[i] = src[i];
+    for (int i = (n4 << 2) + tid; i < meas_floats; i += nth) d_meas[i] = h_meas[i];
+    for (int i = tid; i < batch; i += nth) d_n[i] = h_n[i];
+    for (int i = tid; i < ncmd; i += nth) { d_fwd[i] = h_fwd[i]; d_ang[i] = h_ang[i]; }
+}
+cudaError_t launch_gather_inputs(const float* h_fwd, const float* h_ang, int ncmd, const int* h_n, const float* h_meas, int batch,
+                                 int meas_floats, float* d_fwd, float* d_ang, int* d_n, float* d_meas, cudaStream_t st) {
+    int blocks = (meas_floats / 4 + 255) / 256;
+    if (blocks > 296) blocks = 296;
+    if (blocks < 1) blocks = 1;
+    gather_inputs_kernel<<<blocks, 256, 0, st>>>(h_fwd, h_ang, ncmd, h_n, h_meas, batch, meas_floats, d_fwd, d_ang, d_n, d_meas);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_poses(const BatchState& b, double* d_out, cudaStream_t st) {
     poses_kernel<<<(b.batch + 127) / 128, 128, 0, st>>>(b, d_out);
     return cudaGetLastError();

@@ -442,3 +442,60 @@ def test_run_io_generic_path_unknown_ids(shim, oracle):
             of.update(fwd[t], ang[t], streams[i][t], oracle.STRUCTURED)
         _compare(fb, i, of)
         assert np.abs(out[-1, i] - of.state()[:3]).max() <= H.FINAL_TOL
+
+
+@pytest.mark.parametrize("kind,B", [("ekf", 12), ("ukf", 12), ("ekf", 80)], ids=["ekf", "ukf", "ekf_gathered_inputs"])
+def test_step_io_zero_copy_matches_staged(shim, oracle, kind, B):
+    """slam_step_io with PINNED host buffers: the kernels read the command / message buffers and write the poses in place
+    over PCIe (batched EKF: pose write fused into the step kernel, one launch per tick).  Must equal the staged path
+    (slam_tune key 14) and pageable numpy buffers, tick by tick."""
+    import torch
+    filt = "ekf_slam" if kind == "ekf" else "ukf_slam"
+    p, lm, fwd, ang = H.config2(seed=9, steps=70, filt=filt)
+    op = H.oracle_params(oracle, p)
+    T, mm = len(fwd), 8
+    skind = shim.EKF_SLAM if kind == "ekf" else shim.UKF_SLAM
+    streams = [H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=4, instance=i)[0] for i in range(B)]
+    probe = shim.FilterBatch(skind, p.to_c(), B, 50, mm)
+    h_meas = torch.zeros((T, B, mm, 3), dtype=torch.float32).pin_memory()
+    h_n = torch.zeros((T, B), dtype=torch.int32).pin_memory()
+    for t in range(T):
+        m, n = probe.pack_meas([streams[i][t] for i in range(B)])
+        h_meas[t].copy_(torch.from_numpy(m)); h_n[t].copy_(torch.from_numpy(n))
+    h_fwd = torch.from_numpy(fwd.copy()).pin_memory()
+    h_ang = torch.from_numpy(ang.copy()).pin_memory()
+    runs = []
+    for mode in ("zero_copy", "staged", "pageable"):
+        fb = shim.FilterBatch(skind, p.to_c(), B, 50, mm)
+        fb.tune(14, 1 if mode == "staged" else 0)
+        fb.init(0, 0, 0)
+        if mode == "pageable":
+            poses = np.zeros((T, B, 3))
+            l0 = fb.kernel_launches
+            for t in range(T):
+                fb.step_io(fwd[t:t + 1].copy(), ang[t:t + 1].copy(), 0, h_meas[t].numpy().copy(), h_n[t].numpy().copy(), poses[t])
+                fb.synchronize()
+        else:
+            h_pose = torch.full((T, B, 3), float("nan"), dtype=torch.float64).pin_memory()
+            l0 = fb.kernel_launches
+            for t in range(T):
+                fb.step_io(h_fwd.data_ptr() + 4 * t, h_ang.data_ptr() + 4 * t, 0, h_meas[t].data_ptr(), h_n[t].data_ptr(), h_pose[t].data_ptr())
+                fb.synchronize()
+                assert torch.isfinite(h_pose[t]).all()        # readable right after the tick's synchronize
+            poses = h_pose.numpy().copy()
+        runs.append(dict(poses=poses, x=[fb.state(i) for i in range(B)], P=[fb.cov(i) for i in range(B)], launches=fb.kernel_launches - l0))
+    for other in runs[1:]:
+        np.testing.assert_array_equal(runs[0]["poses"], other["poses"])
+        for i in range(B):
+            np.testing.assert_array_equal(runs[0]["x"][i], other["x"][i])
+            np.testing.assert_array_equal(runs[0]["P"][i], other["P"][i])
+    if kind == "ekf" and B < 64:
+        assert runs[0]["launches"] < runs[1]["launches"]       # no separate pose kernel on the zero-copy path (small batch: inputs read in place)
+    okind = oracle.EKF_SLAM if kind == "ekf" else oracle.UKF_SLAM
+    of = oracle.OracleFilter(okind, op, 50)
+    of.init(0, 0, 0)
+    for t in range(T):
+        of.update(fwd[t], ang[t], streams[5][t], oracle.STRUCTURED)
+        xo = of.state()
+        yaw = xo[2] if kind == "ekf" else np.arctan2(xo[3], xo[2])
+        assert np.abs(runs[0]["poses"][t, 5] - [xo[0], xo[1], yaw]).max() <= H.FINAL_TOL
