@@ -136,6 +136,14 @@ int  slam_sim_destroy(slam_sim_t s);
  * landmark_noise / visitation_threshold / bound: params.yaml:90,91,70. */
 int  slam_sim_make_trajectories(slam_sim_t s, double landmark_noise, double visitation_threshold, double bound,
                                 double x_0, double y_0, double yaw_0, int T, float* d_fwd, float* d_ang);
+/* generate_landmarks (base_pkg/src/sim_node.py:155-206) on the device, ONE MAP PER simulated vehicle (Monte-Carlo sweeps over
+ * random maps, like the reference's recorded runs): map_type 0 = "grid" (:165-176; the lattice np.arange(-bound + step/2, bound,
+ * step)^2, ids row-major, n_landmarks ignored), 1 = "random" / "rand" (:177-188 on the blank occupancy map: uniform positions in
+ * [-bound, bound)^2 at least min_sep apart, rejection sampled; Philox keyed (seed; global instance, attempt, 0, 2)).  The "demo"
+ * and "igvc1" choices are fixed coordinate tables: pass them to slam_sim_create.  Replaces the simulator's shared map; *n_out =
+ * landmarks per map.  The filter handle's max_landmarks must cover it.  Other map_type values fail like sim_node.py:196-198. */
+int  slam_sim_make_maps(slam_sim_t s, int map_type, int n_landmarks, double bound, double grid_step, double min_sep, int* n_out);
+int  slam_sim_get_map(slam_sim_t s, int inst, double* lm_xy /* [n_lm][2] */, int* n_lm);   /* a vehicle's map to HOST memory */
 int  slam_sim_reset(slam_sim_t s, double x_0, double y_0, double yaw_0);
 /* one get_cmd() for every vehicle; commands are HOST (slam_sim_step) or DEVICE (…_device) float32.
  * Results stay on the device: slam_sim_meas()/slam_sim_n_meas() return the DEVICE buffers

@@ -669,7 +669,7 @@ int slam_sim_create(slam_handle_t h, const double* lm_xy, int n_lm, uint64_t see
     st.k0 = (uint32_t)seed; st.k1 = (uint32_t)(seed >> 32);
     CK(cudaMalloc(&s->d_lm, sizeof(double) * 2 * (size_t)n_lm));
     CK(cudaMemcpy(s->d_lm, lm_xy, sizeof(double) * 2 * (size_t)n_lm, cudaMemcpyHostToDevice));
-    st.lm_xy = s->d_lm;
+    st.lm_xy = s->d_lm; st.lm_stride = 0;
     CK(cudaMalloc(&st.truth, sizeof(double) * 3 * (size_t)st.batch));
     CK(cudaMalloc(&st.meas, sizeof(float) * 3 * (size_t)st.batch * st.max_meas));
     CK(cudaMalloc(&st.n_meas, sizeof(int) * st.batch));
@@ -688,6 +688,47 @@ int slam_sim_make_trajectories(slam_sim_t s, double landmark_noise, double visit
     TspParams tp{landmark_noise, visitation_threshold, bound, x_0, y_0, yaw_0, T};
     CK(launch_tsp_trajectories(s->s, h->sc, tp, d_fwd, d_ang, h->stream));
     h->launches += 1;
+    return 0;
+}
+int slam_sim_make_maps(slam_sim_t s, int map_type, int n_landmarks, double bound, double grid_step, double min_sep, int* n_out) {
+    if (!s) return 1;
+    slam_filter* h = s->owner;
+    if (map_type != 0 && map_type != 1) return fail(h, "Invalid map_type provided.");            // sim_node.py:196-198
+    if (!(bound > 0)) return fail(h, "slam_sim_make_maps: bound must be positive");
+    int n = n_landmarks;
+    if (map_type == 0) {
+        if (!(grid_step > 0)) return fail(h, "slam_sim_make_maps: grid_step must be positive");
+        const double start = -bound + grid_step / 2;
+        const int cnt = (int)std::ceil((bound - start) / grid_step);                              // len(np.arange(start, bound, step))
+        n = cnt * cnt;
+    }
+    if (n < 1) return fail(h, "slam_sim_make_maps: no landmarks");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    double* maps = nullptr; int* d_fail = nullptr;
+    CK(cudaMalloc(&maps, sizeof(double) * 2 * (size_t)n * s->s.batch));
+    if (cudaMalloc(&d_fail, sizeof(int) * s->s.batch) != cudaSuccess) { cudaFree(maps); return fail(h, "slam_sim_make_maps: out of memory"); }
+    std::vector<int> hf(s->s.batch, 0);
+    bool ok = launch_make_maps(s->s, map_type, n, bound, grid_step, min_sep, maps, d_fail, h->stream) == cudaSuccess &&
+              cudaMemcpyAsync(hf.data(), d_fail, sizeof(int) * s->s.batch, cudaMemcpyDeviceToHost, h->stream) == cudaSuccess &&
+              cudaStreamSynchronize(h->stream) == cudaSuccess;
+    cudaFree(d_fail);
+    h->launches += 1;
+    if (ok) for (int f : hf) if (f) ok = false;
+    if (!ok) { cudaFree(maps); return fail(h, "slam_sim_make_maps: a map could not be completed (min_landmark_separation too large for the bounds?)"); }
+    cudaFree(s->d_lm);
+    s->d_lm = maps;
+    s->s.lm_xy = maps; s->s.n_lm = n; s->s.lm_stride = 2LL * n;
+    if (n_out) *n_out = n;
+    return 0;
+}
+int slam_sim_get_map(slam_sim_t s, int inst, double* lm_xy, int* n_lm) {
+    if (!s) return 1;
+    slam_filter* h = s->owner;
+    if (inst < 0 || inst >= s->s.batch || !lm_xy) return fail(h, "slam_sim_get_map: bad argument");
+    CK(cudaMemcpyAsync(lm_xy, s->s.lm_xy + (size_t)inst * s->s.lm_stride, sizeof(double) * 2 * (size_t)s->s.n_lm, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (n_lm) *n_lm = s->s.n_lm;
     return 0;
 }
 int slam_sim_destroy(slam_sim_t s) {

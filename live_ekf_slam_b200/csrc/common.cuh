@@ -260,7 +260,8 @@ cudaError_t launch_ekf_large_step(const LargeState& L, const FilterConst& fc, co
 
 struct SimState {
     double* truth;         // [batch][3]
-    const double* lm_xy;   // [n_lm][2]
+    const double* lm_xy;   // [n_lm][2] shared by the batch (lm_stride 0), or [batch][n_lm][2] (lm_stride = 2 n_lm) after slam_sim_make_maps
+    long long lm_stride;   // doubles between the maps of consecutive vehicles (0: one shared map)
     float* meas;           // [batch][max_meas][3]
     int* n_meas;           // [batch]
     int* overflow;         // [batch] detections dropped because max_meas was reached
@@ -276,6 +277,9 @@ struct TspParams {
     double x0, y0, yaw0;
     int T;
 };
+// generate_landmarks (sim_node.py:155-206) for every vehicle on the device; map_type 0 = grid, 1 = random
+cudaError_t launch_make_maps(const SimState& s, int map_type, int n_lm, double bound, double grid_step, double min_sep, double* d_maps,
+                             int* d_fail, cudaStream_t st);
 cudaError_t launch_tsp_trajectories(const SimState& s, const SimConst& sc, const TspParams& tp, float* d_fwd, float* d_ang, cudaStream_t st);
 // One chunk of a Monte-Carlo sweep / trajectory replay (csrc/ekf_batch.cu: ekf_sweep_kernel).
 struct SweepArgs {

@@ -652,7 +652,7 @@ ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, SweepA
                         for (int i = lane; i < 3 * nm_last; i += 32) w.meas[p][i] = src[i];
                         if (lane == 0) w.nm[p] = count;         // raw count: the consumers flag the overflow
                     } else {
-                        const int count = sim_get_cmd_warp(lane, sc, sim.lm_xy, sim.n_lm, b.max_meas, sim.k0, sim.k1,
+                        const int count = sim_get_cmd_warp(lane, sc, sim.lm_xy + (size_t)inst * sim.lm_stride, sim.n_lm, b.max_meas, sim.k0, sim.k1,
                                                            sim.instance_offset + (uint32_t)inst, a.first_step + (uint32_t)t,
                                                            a.cmd_fwd[(size_t)t * cstep + coff], a.cmd_ang[(size_t)t * cstep + coff],
                                                            tr, w.meas[p]);

@@ -17,7 +17,7 @@ sim_step_kernel(SimState s, SimConst sc, const float* __restrict__ fwd, const fl
     double* trg = s.truth + 3 * (size_t)w;
     double tr[3] = {trg[0], trg[1], trg[2]};
     __syncwarp();
-    const int count = sim_get_cmd_warp(lane, sc, s.lm_xy, s.n_lm, s.max_meas, s.k0, s.k1, s.instance_offset + (uint32_t)w,
+    const int count = sim_get_cmd_warp(lane, sc, s.lm_xy + (size_t)w * s.lm_stride, s.n_lm, s.max_meas, s.k0, s.k1, s.instance_offset + (uint32_t)w,
                                        step, fwd[cmd_stride ? w : 0], ang[cmd_stride ? w : 0], tr,
                                        s.meas + (size_t)w * s.max_meas * 3);
     if (lane == 0) {
@@ -59,7 +59,8 @@ sim_step_wide_kernel(SimState s, SimConst sc, const float* __restrict__ fwd, con
         bool vis = false;
         double r = 0.0, beta = 0.0;
         if (chunk < nch && id < s.n_lm) {
-            const double dx = s.lm_xy[2 * id] - tx, dy = s.lm_xy[2 * id + 1] - ty;
+            const double* lmw = s.lm_xy + (size_t)w * s.lm_stride;
+            const double dx = lmw[2 * id] - tx, dy = lmw[2 * id + 1] - ty;
             r = sqrt(dx * dx + dy * dy);                                    // :235
             if (!(r > sc.range_max)) {                                      // :239
                 beta = wrap_2pi(atan2(dy, dx) - tyaw);                      // :236-237
@@ -203,8 +204,9 @@ __global__ void tsp_trajectory_kernel(SimState s, SimConst sc, TspParams tp, flo
     for (int i = 0; i < N; ++i) {
         uint32_t rn[4];
         philox4x32_10(inst, (uint32_t)i, 0u, 1u, s.k0, s.k1, rn);
-        const double ax = s.lm_xy[2 * i] + 2 * tp.landmark_noise * uniform53(rn[0], rn[1]) - tp.landmark_noise;
-        const double ay = s.lm_xy[2 * i + 1] + 2 * tp.landmark_noise * uniform53(rn[2], rn[3]) - tp.landmark_noise;
+        const double* lmw = s.lm_xy + (size_t)w * s.lm_stride;
+        const double ax = lmw[2 * i] + 2 * tp.landmark_noise * uniform53(rn[0], rn[1]) - tp.landmark_noise;
+        const double ay = lmw[2 * i + 1] + 2 * tp.landmark_noise * uniform53(rn[2], rn[3]) - tp.landmark_noise;
         nx[i] = fmax(lo, fmin(ax, hi)); ny[i] = fmax(lo, fmin(ay, hi));
         seen[i] = 0;
     }
@@ -243,6 +245,56 @@ __global__ void tsp_trajectory_kernel(SimState s, SimConst sc, TspParams tp, flo
 cudaError_t launch_tsp_trajectories(const SimState& s, const SimConst& sc, const TspParams& tp, float* d_fwd, float* d_ang, cudaStream_t st) {
     if (s.n_lm > TSP_MAX_LM) return cudaErrorInvalidValue;
     tsp_trajectory_kernel<<<(s.batch + 63) / 64, 64, 0, st>>>(s, sc, tp, d_fwd, d_ang);
+    return cudaGetLastError();
+}
+
+// generate_landmarks, ekf_ws/src/base_pkg/src/sim_node.py:155-206, one map per simulated vehicle, one thread per vehicle.
+//   map_type 0 "grid"   (:165-176): the lattice np.arange(-bound + step / 2, bound, step) squared, ids row-major -- the same for
+//                       every vehicle; n_lm = count^2 is computed by the host with numpy's arange length rule.
+//   map_type 1 "random" (:177-188): positions uniform in [-bound, bound)^2, rejected when closer than min_sep to an accepted
+//                       landmark (the occupancy test of :182 always passes on the blank map the benchmarks use).  The reference
+//                       draws from random.random(); here attempt a of vehicle i draws Philox (seed; i, a, 0, 2) (deviation D-5).
+// fail[w] = 1 when a vehicle's map could not be completed in 64 n_lm attempts (min_sep too large for the area).
+__global__ void make_maps_kernel(SimState s, const int map_type, const int n_lm, const double bound, const double grid_step,
+                                 const double min_sep, double* __restrict__ maps, int* __restrict__ fail) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= s.batch) return;
+    double* lm = maps + (size_t)w * 2 * n_lm;
+    if (map_type == 0) {
+        const double start = -bound + grid_step / 2;
+        int cnt = 0;
+        while (cnt * cnt < n_lm) ++cnt;
+        for (int r = 0; r < cnt; ++r)
+            for (int c = 0; c < cnt; ++c) {      // np.arange's fill: start + i * delta, delta = (start + step) - start, no FMA contraction
+                const double delta = __dadd_rn(__dadd_rn(start, grid_step), -start);
+                lm[2 * (r * cnt + c)] = __dadd_rn(start, __dmul_rn((double)r, delta));
+                lm[2 * (r * cnt + c) + 1] = __dadd_rn(start, __dmul_rn((double)c, delta));
+            }
+        fail[w] = 0;
+        return;
+    }
+    const uint32_t inst = s.instance_offset + (uint32_t)w;
+    int have = 0;
+    for (uint32_t a = 0; have < n_lm && a < 64u * (uint32_t)n_lm; ++a) {
+        uint32_t rn[4];
+        philox4x32_10(inst, a, 0u, 2u, s.k0, s.k1, rn);
+        // (explicit roundings: the map must be bit-identical to the CPU restatement, so no FMA contraction here)
+        const double px = __dadd_rn(__dmul_rn(2 * bound, uniform53(rn[0], rn[1])), -bound);                               // :180
+        const double py = __dadd_rn(__dmul_rn(2 * bound, uniform53(rn[2], rn[3])), -bound);
+        bool close = false;
+        for (int q = 0; q < have && !close; ++q) {
+            const double dx = lm[2 * q] - px, dy = lm[2 * q + 1] - py;
+            close = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))) < min_sep;                                        // :184
+        }
+        if (close) continue;
+        lm[2 * have] = px; lm[2 * have + 1] = py;                                                                          // :186-187
+        ++have;
+    }
+    fail[w] = (have < n_lm) ? 1 : 0;
+}
+cudaError_t launch_make_maps(const SimState& s, int map_type, int n_lm, double bound, double grid_step, double min_sep, double* d_maps,
+                             int* d_fail, cudaStream_t st) {
+    make_maps_kernel<<<(s.batch + 63) / 64, 64, 0, st>>>(s, map_type, n_lm, bound, grid_step, min_sep, d_maps, d_fail);
     return cudaGetLastError();
 }
 

@@ -29,7 +29,7 @@ ABI_SYMBOLS = (
     "slam_update_device", "slam_get_timestep", "slam_get_num_landmarks", "slam_get_status", "slam_get_state",
     "slam_get_state_vector", "slam_get_cov", "slam_get_landmark_ids", "slam_get_assoc", "slam_get_sigma_points",
     "slam_get_poses", "slam_get_all_status", "slam_get_all_num_landmarks", "slam_set_state",
-    "slam_sim_create", "slam_sim_destroy", "slam_sim_make_trajectories", "slam_sim_reset", "slam_sim_step", "slam_sim_step_device",
+    "slam_sim_create", "slam_sim_destroy", "slam_sim_make_trajectories", "slam_sim_make_maps", "slam_sim_get_map", "slam_sim_reset", "slam_sim_step", "slam_sim_step_device",
     "slam_sim_meas", "slam_sim_n_meas", "slam_sim_get_truth", "slam_sim_get_meas",
     "slam_run", "slam_run_device", "slam_reset", "slam_step_io", "slam_run_io", "slam_set_profiling", "slam_get_profile",
     "slam_accumulate_error", "slam_get_stats", "slam_reset_stats", "slam_get_error_histogram",
@@ -81,6 +81,8 @@ def load(path: str | None = None):
     L.slam_sim_destroy.argtypes = [vp]
     L.slam_sim_make_trajectories.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, vp, vp]
     L.slam_sim_reset.argtypes = [vp, C.c_double, C.c_double, C.c_double]
+    L.slam_sim_make_maps.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, ip]
+    L.slam_sim_get_map.argtypes = [vp, C.c_int, dp, ip]
     L.slam_sim_step.argtypes = [vp, vp, vp, C.c_int, C.c_uint32]
     L.slam_sim_step_device.argtypes = [vp, vp, vp, C.c_int, C.c_uint32]
     L.slam_sim_meas.argtypes = [vp]
@@ -432,6 +434,20 @@ class Simulator:
         ([T][batch] float32, e.g. torch tensors) with per-instance command trajectories (use with run_device(..., cmd_stride=1))."""
         self._f._ck(self._L.slam_sim_make_trajectories(self._s, landmark_noise, visitation_threshold, bound,
                                                        pose0[0], pose0[1], pose0[2], T, _ptr(d_fwd), _ptr(d_ang)))
+
+    def make_maps(self, map_type: str, n_landmarks: int, bound: float, grid_step: float = 4.0, min_sep: float = 0.05) -> int:
+        """generate_landmarks (sim_node.py:155-206) on the device, one map per vehicle: "grid" or "random" / "rand"."""
+        code = {"grid": 0, "random": 1, "rand": 1}.get(map_type, -1)
+        n = C.c_int()
+        self._f._ck(self._L.slam_sim_make_maps(self._s, code, n_landmarks, bound, grid_step, min_sep, C.byref(n)))
+        self.n_lm = n.value
+        return n.value
+
+    def get_map(self, inst: int = 0) -> np.ndarray:
+        lm = np.zeros((self.n_lm, 2))
+        n = C.c_int()
+        self._f._ck(self._L.slam_sim_get_map(self._s, inst, lm.ctypes.data_as(C.POINTER(C.c_double)), C.byref(n)))
+        return lm[: n.value]
 
     def accumulate_error(self):
         self._f._ck(self._L.slam_accumulate_error(self._f._h, self._s))

@@ -98,6 +98,7 @@ def lib():
     L.oracle_tsp_trajectory.argtypes = [pp, dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                         C.c_int, C.c_uint64, C.c_uint32, fp, fp]
     L.oracle_set_trig_mode.argtypes = [C.c_int]
+    L.oracle_make_map.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint32, dp, C.c_int]
     _lib = L
     return L
 
@@ -237,6 +238,16 @@ def tsp_trajectory(params: OracleParams, lm_xy, landmark_noise, visitation_thres
     if rc != 0:
         raise ValueError("oracle_tsp_trajectory: bad arguments")
     return fwd, ang
+
+
+def make_map(map_type: str, n_landmarks: int, bound: float, grid_step: float, min_sep: float, seed: int, instance: int, cap: int = 4096):
+    """sim_node.py:155-206 ("grid" | "random"); returns lm_xy [n,2]."""
+    code = {"grid": 0, "random": 1, "rand": 1}.get(map_type, -1)
+    buf = np.zeros((cap, 2))
+    n = lib().oracle_make_map(code, n_landmarks, bound, grid_step, min_sep, seed, instance, _dp(buf), cap)
+    if n < 0:
+        raise ValueError("Invalid map_type provided." if n == -1 else "map could not be completed")
+    return buf[:n].copy()
 
 
 def run_instance(kind, params, lm_xy, cmd_fwd, cmd_ang, seed, instance, max_landmarks, mode=STRUCTURED, keep=False):

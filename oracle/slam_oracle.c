@@ -823,6 +823,44 @@ int oracle_sim_step(const oracle_params* p, double truth[3], float fwd, float an
  * rotating the tour when within the visitation threshold (:118-152).  Map noise: Philox keyed (seed; instance, id, 0, 1)
  * (deviation D-5; the reference uses the unseeded random.random()). */
 static double tsp_norm(double ax, double ay, double bx, double by) { const double dx = ax - bx, dy = ay - by; return sqrt(dx * dx + dy * dy); }
+/* generate_landmarks, sim_node.py:155-206: map_type 0 "grid" (:165-176), 1 "random" (:177-188, blank occupancy map).  Returns the
+ * number of landmarks written to lm_xy ([cap][2]), or -1 (invalid map_type, :196-198) / -2 (capacity or attempts exhausted).
+ * Random draws: Philox (seed; instance, attempt, 0, 2), two uniforms per attempt in the order of :180 (deviation D-5). */
+int oracle_make_map(int map_type, int n_landmarks, double bound, double grid_step, double min_sep, uint64_t seed, uint32_t instance,
+                    double* lm_xy, int cap) {
+    if (map_type == 0) {
+        const double shift = grid_step / 2;                                            /* :166 */
+        int id = 0;
+        const double start = -bound + shift;
+        const int cnt = (int)ceil((bound - start) / grid_step);                       /* len(np.arange(start, bound, step)) */
+        /* np.arange fills start + i * delta with delta = (start + step) - start as rounded (numpy's arange fill) */
+        const volatile double next = start + grid_step;
+        const double delta = next - start;
+        for (int r = 0; r < cnt; ++r)
+            for (int c = 0; c < cnt; ++c) {                                            /* :168-171 */
+                if (id >= cap) return -2;
+                lm_xy[2 * id] = start + r * delta; lm_xy[2 * id + 1] = start + c * delta;
+                ++id;
+            }
+        return id;
+    }
+    if (map_type != 1) return -1;
+    if (n_landmarks > cap) return -2;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    int have = 0;
+    for (uint32_t a = 0; have < n_landmarks && a < 64u * (uint32_t)n_landmarks; ++a) { /* :179 */
+        uint32_t rn[4];
+        oracle_philox(instance, a, 0u, 2u, k0, k1, rn);
+        const double px = 2 * bound * oracle_uniform(rn[0], rn[1]) - bound, py = 2 * bound * oracle_uniform(rn[2], rn[3]) - bound;   /* :180 */
+        int close = 0;
+        for (int q = 0; q < have && !close; ++q) close = tsp_norm(lm_xy[2 * q], lm_xy[2 * q + 1], px, py) < min_sep;                  /* :184 */
+        if (close) continue;
+        lm_xy[2 * have] = px; lm_xy[2 * have + 1] = py;                                /* :186-187 */
+        ++have;
+    }
+    return have < n_landmarks ? -2 : have;
+}
+
 int oracle_tsp_trajectory(const oracle_params* p, const double* lm_xy, int n_lm, double landmark_noise,
                           double visitation_threshold, double bound, double x0, double y0, double yaw0, int T,
                           uint64_t seed, uint32_t instance, float* fwd_out, float* ang_out) {

@@ -89,6 +89,8 @@ int   oracle_sim_step(const oracle_params* p, double truth[3], float fwd, float 
 
 /* generate_trajectory, sim_node.py:63-152: the precomputed command trajectory of one Monte-Carlo instance
  * (noisy map copy keyed (seed; instance, id, 0, 1), nearest-neighbour tour, clamped commands); float32 wire values out. */
+int   oracle_make_map(int map_type, int n_landmarks, double bound, double grid_step, double min_sep, uint64_t seed, uint32_t instance,
+                      double* lm_xy, int cap);   /* sim_node.py:155-206: 0 grid, 1 random; returns n or < 0 */
 int   oracle_tsp_trajectory(const oracle_params* p, const double* lm_xy, int n_lm, double landmark_noise,
                             double visitation_threshold, double bound, double x0, double y0, double yaw0, int T,
                             uint64_t seed, uint32_t instance, float* fwd_out, float* ang_out);
