@@ -85,7 +85,7 @@ __host__ __device__ inline size_t ukf_smem_carve(const BatchState& b, unsigned c
 }
 
 // sum NV per-thread values over the CTA; every thread receives the totals.  Two barriers.
-template <int NV>
+template <int NV, int NWARPS = UKF_WARPS>
 __device__ __forceinline__ void block_sum(double (&v)[NV], double* red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -93,14 +93,14 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* red) {
         double t = v[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) red[k * UKF_WARPS + warp] = t;
+        if (lane == 0) red[k * NWARPS + warp] = t;
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         double t = 0.0;
 #pragma unroll
-        for (int w = 0; w < UKF_WARPS; ++w) t += red[k * UKF_WARPS + w];
+        for (int w = 0; w < NWARPS; ++w) t += red[k * NWARPS + w];
         v[k] = t;
     }
     __syncthreads();
@@ -120,6 +120,28 @@ __device__ __forceinline__ float yaw_of(double c, double s) { return (float)rema
 // ql_serial: implicit QL on (d, e) (EISPACK tql2 organisation) with each sweep's rotations generated by one thread
 // and applied to A = Z^T by one thread per column.  Only the fall-back of the back kernel (rotation log overflow).
 // ---------------------------------------------------------------------------------------------------------
+// One Householder step's scalars for column k (rows k+1..n-1 hold the column below the diagonal): warp 0 only.
+// Writes tau[k], e[k], d[k] and (tk, scal) into slot[0..1].
+__device__ __forceinline__ void householder_scalars(const double* A, const int lds, const int n, const int k, const int lane,
+                                                    double* d, double* e, double* tau, double* slot) {
+    double ss = 0.0;
+    for (int i = k + 2 + lane; i < n; i += 32) { const double a = A[(size_t)i * lds + k]; ss += a * a; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) {
+        const double alpha = A[(size_t)(k + 1) * lds + k];
+        double tk = 0.0, scal = 0.0, beta = alpha;
+        if (ss != 0.0) {
+            beta = -copysign(sqrt(alpha * alpha + ss), alpha);
+            tk = (beta - alpha) / beta;
+            scal = 1.0 / (alpha - beta);
+        }
+        tau[k] = tk; e[k] = beta; d[k] = A[(size_t)k * lds + k];
+        slot[0] = tk; slot[1] = scal;
+    }
+}
+
+template <int NT>
 __device__ void tridiag(double* A, const int lds, const int n, double* d, double* e, double* scratch, double* part, double* red) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* v = scratch;            // [n]
@@ -127,46 +149,34 @@ __device__ void tridiag(double* A, const int lds, const int n, double* d, double
     double* w = scratch + 2 * n;    // [n]
     double* tau = scratch + 3 * n;  // [n]
 
-    // ---- reduction to tridiagonal form: A = Q T Q^T
+    // ---- reduction to tridiagonal form: A = Q T Q^T.  The scalar chain of a step (column norm, sqrt, two divisions: ~20 % of the
+    // kernel when every warp waited for it at a barrier) is OVERLAPPED with the previous step's rank-2 update: warp 0 updates
+    // column k+1 of the trailing block first and goes on to the next step's scalars while the other warps update the rest.
+    // (tk, scal) of step k live in red[2 (k & 1) ..]: double buffered, so the readers of step k never race the writer of k+1.
+    if (warp == 0 && n > 1) householder_scalars(A, lds, n, 0, lane, d, e, tau, red);
+    __syncthreads();
     for (int k = 0; k < n - 1; ++k) {
         const int m0 = k + 1;                      // first row/col of the trailing block
         const int m = n - m0;                      // its size
-        if (warp == 0) {
-            double ss = 0.0;
-            for (int i = k + 2 + lane; i < n; i += 32) { const double a = A[(size_t)i * lds + k]; ss += a * a; }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-            if (lane == 0) {
-                const double alpha = A[(size_t)m0 * lds + k];
-                double tk = 0.0, scal = 0.0, beta = alpha;
-                if (ss != 0.0) {
-                    beta = -copysign(sqrt(alpha * alpha + ss), alpha);
-                    tk = (beta - alpha) / beta;
-                    scal = 1.0 / (alpha - beta);
-                }
-                tau[k] = tk; e[k] = beta; d[k] = A[(size_t)k * lds + k];
-                red[0] = tk; red[1] = scal;
-            }
-        }
-        __syncthreads();
-        const double tk = red[0], scal = red[1];
+        const double tk = red[2 * (k & 1)], scal = red[2 * (k & 1) + 1];
+        double* next_slot = red + 2 * ((k + 1) & 1);
         if (tk != 0.0) {                            // uniform
-            for (int i = m0 + tid; i < n; i += UKF_THREADS) {
+            for (int i = m0 + tid; i < n; i += NT) {
                 const double vi = (i == m0) ? 1.0 : A[(size_t)i * lds + k] * scal;
                 v[i] = vi;
                 A[(size_t)i * lds + k] = vi;        // keep the reflector in column k
             }
             __syncthreads();
             // 2-D mapping: thread -> (column c, row group g); rows of group g: m0 + g*rb .. (exclusive end clipped)
-            int G = UKF_THREADS / m; if (G > 8) G = 8; if (G < 1) G = 1;
+            int G = NT / m; if (G > 8) G = 8; if (G < 1) G = 1;
             const int g = tid / m, cl = tid - g * m;
             const int rb = (m + G - 1) / G;
             const bool act = g < G;
             const int c = m0 + cl;
             const int r_lo = m0 + g * rb, r_hi = (r_lo + rb < n) ? r_lo + rb : n;
             // p = tau * A22 * v  (column c of the symmetric block, conflict-free), and p^T v
-            if (m > UKF_THREADS) {                  // (never for n_max <= 256) one group, strided columns
-                for (int cc = m0 + tid; cc < n; cc += UKF_THREADS) {
+            if (m > NT) {                  // (never for n_max <= 256) one group, strided columns
+                for (int cc = m0 + tid; cc < n; cc += NT) {
                     double acc = 0.0;
                     for (int i = m0; i < n; ++i) acc += A[(size_t)i * lds + cc] * v[i];
                     part[cc] = acc;
@@ -183,35 +193,59 @@ __device__ void tridiag(double* A, const int lds, const int n, double* d, double
             }
             __syncthreads();
             double pv[1] = {0.0};
-            const int Gs = (m > UKF_THREADS) ? 1 : G;
-            for (int cc = m0 + tid; cc < n; cc += UKF_THREADS) {
+            const int Gs = (m > NT) ? 1 : G;
+            for (int cc = m0 + tid; cc < n; cc += NT) {
                 double acc = 0.0;
                 for (int q = 0; q < Gs; ++q) acc += part[q * n + cc];
                 acc *= tk;
                 p[cc] = acc;
                 pv[0] += acc * v[cc];
             }
-            block_sum<1>(pv, red + 8);
+            block_sum<1, NT / 32>(pv, red + 8);
             const double a2 = -0.5 * tk * pv[0];
-            for (int cc = m0 + tid; cc < n; cc += UKF_THREADS) w[cc] = p[cc] + a2 * v[cc];
+            for (int cc = m0 + tid; cc < n; cc += NT) w[cc] = p[cc] + a2 * v[cc];
             __syncthreads();
             // A22 -= v w^T + w v^T   (both triangles kept; the two products are added symmetrically)
-            if (m > UKF_THREADS) {
-                for (int cc = m0 + tid; cc < n; cc += UKF_THREADS) {
-                    const double vc = v[cc], wc = w[cc];
-                    for (int i = m0; i < n; ++i) {
-                        const double t1 = __dmul_rn(v[i], wc), t2 = __dmul_rn(w[i], vc);
-                        A[(size_t)i * lds + cc] -= __dadd_rn(t1, t2);
+            if (NT > 32 && warp == 0) {
+                // column m0 (rows m0..n-1), then the NEXT step's scalars from it; row m0 beyond the diagonal is dead from here on
+                const double vc = v[m0], wc = w[m0];
+                for (int i = m0 + lane; i < n; i += 32) {
+                    const double t1 = __dmul_rn(v[i], wc), t2 = __dmul_rn(w[i], vc);
+                    A[(size_t)i * lds + m0] -= __dadd_rn(t1, t2);
+                }
+                __syncwarp();
+                if (m0 < n - 1) householder_scalars(A, lds, n, m0, lane, d, e, tau, next_slot);
+            } else {
+                // the rest of the block: rows and columns m0+1..n-1, on the remaining NT - 32 threads
+                const int c_lo = (NT > 32) ? m0 + 1 : m0, mm = n - c_lo;
+                const int t2 = (NT > 32) ? tid - 32 : tid, T2 = (NT > 32) ? NT - 32 : NT;
+                if (mm > 0) {
+                    if (mm > T2) {
+                        for (int cc = c_lo + t2; cc < n; cc += T2) {
+                            const double vc = v[cc], wc = w[cc];
+                            for (int i = c_lo; i < n; ++i) {
+                                const double t1 = __dmul_rn(v[i], wc), t2b = __dmul_rn(w[i], vc);
+                                A[(size_t)i * lds + cc] -= __dadd_rn(t1, t2b);
+                            }
+                        }
+                    } else {
+                        int G2 = T2 / mm; if (G2 > 8) G2 = 8; if (G2 < 1) G2 = 1;
+                        const int g2 = t2 / mm, cl2 = t2 - g2 * mm;
+                        const int rb2 = (mm + G2 - 1) / G2;
+                        if (g2 < G2) {
+                            const int c2 = c_lo + cl2;
+                            const int lo2 = c_lo + g2 * rb2, hi2 = (lo2 + rb2 < n) ? lo2 + rb2 : n;
+                            const double vc = v[c2], wc = w[c2];
+                            for (int i = lo2; i < hi2; ++i) {
+                                const double t1 = __dmul_rn(v[i], wc), t2b = __dmul_rn(w[i], vc);
+                                A[(size_t)i * lds + c2] -= __dadd_rn(t1, t2b);
+                            }
+                        }
                     }
                 }
-            } else if (act) {
-                const double vc = v[c], wc = w[c];
-                for (int i = r_lo; i < r_hi; ++i) {
-                    const double t1 = __dmul_rn(v[i], wc), t2 = __dmul_rn(w[i], vc);
-                    A[(size_t)i * lds + c] -= __dadd_rn(t1, t2);
-                }
+                if (NT == 32) { __syncwarp(); if (m0 < n - 1) householder_scalars(A, lds, n, m0, lane, d, e, tau, next_slot); }
             }
-        }
+        } else if (warp == 0 && m0 < n - 1) householder_scalars(A, lds, n, m0, lane, d, e, tau, next_slot);   // nothing to update
         __syncthreads();
     }
     if (tid == 0) { d[n - 1] = A[(size_t)(n - 1) * lds + (n - 1)]; e[n - 1] = 0.0; }
@@ -601,7 +635,7 @@ ukf_front_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
     }
     __syncthreads();
     // ---- first half of the eigendecomposition (:116-118)
-    tridiag(s.A, lds, n, s.d, s.e, s.pool, s.Xp, s.red);       // Xp ([4][2 n_max + 2]) is free in this launch
+    tridiag<UKF_THREADS>(s.A, lds, n, s.d, s.e, s.pool, s.Xp, s.red);       // Xp ([4][2 n_max + 2]) is free in this launch
     form_qt(s.A, lds, n, s.pool, s.Xp);
     double* Zg = u.Zg + (size_t)inst * u.n_max * u.n_max;
     for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
@@ -1213,7 +1247,8 @@ __device__ __forceinline__ void apply_rot_bwd(double* W, const int lane, const b
 }
 
 // ---- launch 1 of 3 (generation 2): Y = scale * sym(P) (ukf.cpp:112-114), tridiagonalisation; P is NOT modified
-__global__ void __launch_bounds__(UKF_THREADS, 2)
+constexpr int FRONT2_THREADS = 256;      // (512 threads measured slower: 3.79 -> 4.11 ms; the Householder steps are barrier bound)
+__global__ void __launch_bounds__(FRONT2_THREADS, 2)
 ukf_front2_kernel(BatchState b, UkfScratch u, const int i0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     UkfSmem s;
@@ -1227,7 +1262,7 @@ ukf_front2_kernel(BatchState b, UkfScratch u, const int i0) {
     const int M = meta_in.x;
     const int n = 4 + 2 * M;                       // ukf.cpp:167
     const double* gP = b.P + (size_t)inst * b.p_stride;
-    for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
+    for (int idx = tid; idx < n * n; idx += FRONT2_THREADS) {
         const int i = idx / n, j = idx - i * n;
         s.A[(size_t)i * lds + j] = gP[(size_t)i * ldp + j];
     }
@@ -1235,7 +1270,7 @@ ukf_front2_kernel(BatchState b, UkfScratch u, const int i0) {
     const float W0f = 0.2f;                                                // filter.h:207
     const double wgt = (double)((1 - W0f) / (2 * n));                      // :175
     const double scale = (double)((2 * M + 4) / (1 - W0f));                // :114
-    for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
+    for (int idx = tid; idx < n * n; idx += FRONT2_THREADS) {
         const int i = idx / n, j = idx - i * n;
         if (j >= i) {
             const double y = (0.5 * (s.A[(size_t)i * lds + j] + s.A[(size_t)j * lds + i])) * scale;
@@ -1244,21 +1279,21 @@ ukf_front2_kernel(BatchState b, UkfScratch u, const int i0) {
     }
     __syncthreads();
     double* Yg = u.Yg + (size_t)inst * u.n_max * u.n_max;
-    for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
+    for (int idx = tid; idx < n * n; idx += FRONT2_THREADS) {
         const int i = idx / n, j = idx - i * n;
         if (i >= 4 && j >= 4) Yg[idx] = (2.0 * wgt) * s.A[(size_t)i * lds + j];   // landmark block of P_pred before corrections
     }
     __syncthreads();
-    tridiag(s.A, lds, n, s.d, s.e, s.pool, s.Xp, s.red);
+    tridiag<FRONT2_THREADS>(s.A, lds, n, s.d, s.e, s.pool, s.Xp, s.red);
     // reflector k (column k of A below the diagonal) -> row k of the scratch matrix, tau_k on its diagonal
     double* Rg = u.Zg + (size_t)inst * u.n_max * u.n_max;
     const double* tau = s.pool + 3 * n;
-    for (int idx = tid; idx < n * n; idx += UKF_THREADS) {
+    for (int idx = tid; idx < n * n; idx += FRONT2_THREADS) {
         const int k = idx / n, i = idx - k * n;
         if (i > k) Rg[idx] = s.A[(size_t)i * lds + k];
         else if (i == k) Rg[idx] = (k < n - 1) ? tau[k] : 0.0;
     }
-    for (int k = tid; k < n; k += UKF_THREADS) { u.dg[(size_t)k * b.batch + inst] = s.d[k]; u.eg[(size_t)k * b.batch + inst] = s.e[k]; }
+    for (int k = tid; k < n; k += FRONT2_THREADS) { u.dg[(size_t)k * b.batch + inst] = s.d[k]; u.eg[(size_t)k * b.batch + inst] = s.e[k]; }
 }
 
 // =========================================================================================================
@@ -2524,7 +2559,7 @@ cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const St
             const int i0 = (int)((long long)b.batch * k / nsub), i1 = (int)((long long)b.batch * (k + 1) / nsub);
             if (i1 <= i0) continue;
             cudaStream_t sk = (k == 0) ? st : xs.aux[k - 1];
-            ukf_front2_kernel<<<i1 - i0, UKF_THREADS, fsm, sk>>>(b, u, i0);
+            ukf_front2_kernel<<<i1 - i0, FRONT2_THREADS, fsm, sk>>>(b, u, i0);
             const int full = ukf_wld(b);
             const bool two_pass = u.narrow && full > UKF_NARROW_WLD;
             if (gen3) {
