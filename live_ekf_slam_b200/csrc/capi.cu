@@ -372,11 +372,7 @@ static int do_step(slam_filter* h, const float* d_fwd, const float* d_ang, int c
     CK(cudaSetDevice(h->device));
     if (h->large) {
         if (phases != (STEP_PREDICT | STEP_UPDATE)) return fail(h, "split predict/update is not available on the large-map path");
-        // the per-measurement kernels are launched from the host: the detection count must be known here
-        CK(cudaMemcpyAsync(h->h_nmeas_pin, d_nmeas, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        int nm = *h->h_nmeas_pin;
-        if (nm > h->b.max_meas) nm = h->b.max_meas;
+        // (the detection count stays on the device: the step is asynchronous like every other path)
         if (h->profiling || h->profiling_gemm) {
             if (h->ev_used + 2 > h->ev.size()) {
                 const size_t old = h->ev.size();
@@ -385,8 +381,8 @@ static int do_step(slam_filter* h, const float* d_fwd, const float* d_ang, int c
             }
             if (h->profiling) CK(cudaEventRecord(h->ev[h->ev_used], h->stream));
         }
-        const bool pg = h->profiling_gemm && nm > 0;      // events around the closing DMMA contraction only
-        CK(launch_ekf_large_step(h->lg, h->fc, d_fwd, d_ang, d_meas, nm, h->b.n_max, h->stream, &h->launches,
+        const bool pg = h->profiling_gemm;                // events around the closing DMMA contraction only
+        CK(launch_ekf_large_step(h->lg, h->fc, d_fwd, d_ang, d_meas, d_nmeas, h->b.n_max, h->stream, &h->launches,
                                  pg ? h->ev[h->ev_used] : nullptr, pg ? h->ev[h->ev_used + 1] : nullptr));
         if (h->profiling) CK(cudaEventRecord(h->ev[h->ev_used + 1], h->stream));
         if (h->profiling || pg) h->ev_used += 2;

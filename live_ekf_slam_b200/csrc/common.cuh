@@ -255,7 +255,7 @@ struct LargeState {
 };
 cudaError_t ekf_large_configure();      // per handle / device: opt-in shared memory of the contraction kernel
 cudaError_t launch_ekf_large_step(const LargeState& L, const FilterConst& fc, const float* d_fwd, const float* d_ang,
-                                  const float* d_meas, int n_meas, int n_upper, cudaStream_t st, long long* launches,
+                                  const float* d_meas, const int* d_nmeas, int n_upper, cudaStream_t st, long long* launches,
                                   cudaEvent_t gemm_ev0 = nullptr, cudaEvent_t gemm_ev1 = nullptr);
 
 struct SimState {

@@ -77,7 +77,8 @@ __device__ __forceinline__ void grid_sync(unsigned* counter, const unsigned nblo
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(LM_THREADS) lm_front(LargeState L, FilterConst fc, const float* meas, const int n_meas) {
+__global__ void __launch_bounds__(LM_THREADS) lm_front(LargeState L, FilterConst fc, const float* meas, const int* __restrict__ d_nmeas) {
+    const int n_meas = (*d_nmeas < L.max_meas) ? *d_nmeas : L.max_meas;      // the detection count never visits the host
     __shared__ double s_cq[LM_QMAX][4];   // (H K_q)   [r][s]
     __shared__ double s_eq[LM_QMAX][4];   // (G_q H^T) [s][r]
     __shared__ double s_sc[16];           // H[10], nu[2], cb, sb / x_detected, y_detected
@@ -459,7 +460,8 @@ __global__ void __launch_bounds__(128) lm_gemm(LargeState L) {
 }
 
 // ---- commit (ekf.cpp:176-177)
-__global__ void lm_commit(LargeState L, int n_meas) {
+__global__ void lm_commit(LargeState L, const int* __restrict__ d_nmeas) {
+    const int n_meas = (*d_nmeas < L.max_meas) ? *d_nmeas : L.max_meas;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int status = L.cur[2];
     const bool dead = (status & SLAM_STATUS_SAME_STEP_REMATCH) != 0;
@@ -486,43 +488,43 @@ cudaError_t ekf_large_configure() {
     return cudaFuncSetAttribute(lm_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_GEMM_SMEM);
 }
 
-// One reference EKF::update for the large-map instance.  n_meas is known on the host; meas is a DEVICE pointer to
-// [n_meas][3] float32.
+// U and G are zero-extended for landmarks inserted later in the step: clear the rows of this step's measurements (the count is
+// read on the device, so the cost follows the message, not max_meas)
+__global__ void lm_clear(LargeState L, const int* __restrict__ d_nmeas) {
+    const int nm = (*d_nmeas < L.max_meas) ? *d_nmeas : L.max_meas;
+    const size_t nu = (size_t)nm * L.n_max * 2, ng = (size_t)nm * 2 * L.ld;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nu + ng; i += (size_t)gridDim.x * blockDim.x) {
+        if (i < nu) L.U[i] = 0.0; else L.G[i - nu] = 0.0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) L.cur[8] = 0;        // grid-barrier counter of lm_front
+}
+
+// One reference EKF::update for the large-map instance.  meas: DEVICE pointer to [max_meas][3] float32, d_nmeas: DEVICE pointer to
+// the detection count -- nothing of the step depends on the host knowing it, so a step is five asynchronous launches.
 cudaError_t launch_ekf_large_step(const LargeState& L, const FilterConst& fc, const float* d_fwd, const float* d_ang,
-                                  const float* d_meas, int n_meas, int n_upper, cudaStream_t st, long long* launches,
+                                  const float* d_meas, const int* d_nmeas, int n_upper, cudaStream_t st, long long* launches,
                                   cudaEvent_t gemm_ev0, cudaEvent_t gemm_ev1) {
     const int tb = 256;
     const int gb = (n_upper + tb - 1) / tb;
     cudaError_t e;
-    const int kcap = n_meas < L.max_meas ? n_meas : L.max_meas;
-    if (kcap > LM_QMAX) return cudaErrorInvalidValue;
-    if (kcap > 0) {
-        // U and G are zero-extended for landmarks inserted later in the step: clear what the step can touch;
-        // association slots start at INT_MAX (0x7f7f7f7f is large enough and memset-able); barrier counter at 0
-        e = cudaMemsetAsync(L.U, 0, sizeof(double) * (size_t)kcap * L.n_max * 2, st); if (e != cudaSuccess) return e;
-        e = cudaMemsetAsync(L.G, 0, sizeof(double) * (size_t)kcap * 2 * L.ld, st); if (e != cudaSuccess) return e;
-        e = cudaMemsetAsync(L.ctl, 0x7f, sizeof(int) * (size_t)L.max_meas, st); if (e != cudaSuccess) return e;
-        e = cudaMemsetAsync(L.cur + 8, 0, sizeof(int), st); if (e != cudaSuccess) return e;
-    }
+    if (L.max_meas > LM_QMAX) return cudaErrorInvalidValue;
+    static int sms = 0;
+    if (!sms) sms = device_sm_count();
+    lm_clear<<<2 * sms, 256, 0, st>>>(L, d_nmeas);
     lm_predict_rows<<<gb, tb, 0, st>>>(L, fc, d_fwd, d_ang);
     lm_predict_cols<<<gb, tb, 0, st>>>(L, fc, d_fwd);
-    *launches += 2;
-    if (kcap > 0) {
-        int gm = (n_upper + LM_SPAN - 1) / LM_SPAN;                // one CTA per 32 state indices, all co-resident
-        const int sms = device_sm_count();
-        if (gm > sms) gm = sms;
-        LargeState Lc = L; FilterConst fcc = fc; const float* mp = d_meas; int nm = kcap;
-        void* args[] = {&Lc, &fcc, &mp, &nm};
-        e = cudaLaunchCooperativeKernel((const void*)lm_front, dim3(gm), dim3(LM_THREADS), args, 0, st);
-        if (e != cudaSuccess) return e;
-        const int gt = (n_upper + GT - 1) / GT;
-        if (gemm_ev0) cudaEventRecord(gemm_ev0, st);
-        lm_gemm<<<gt * (gt + 1) / 2, 128, LM_GEMM_SMEM, st>>>(L);
-        if (gemm_ev1) cudaEventRecord(gemm_ev1, st);
-        *launches += 2;
-    }
-    lm_commit<<<gb, tb, 0, st>>>(L, n_meas);
-    *launches += 1;
+    int gm = (n_upper + LM_SPAN - 1) / LM_SPAN;                    // one CTA per 32 state indices, all co-resident
+    if (gm > sms) gm = sms;
+    LargeState Lc = L; FilterConst fcc = fc; const float* mp = d_meas; const int* np = d_nmeas;
+    void* args[] = {&Lc, &fcc, &mp, &np};
+    e = cudaLaunchCooperativeKernel((const void*)lm_front, dim3(gm), dim3(LM_THREADS), args, 0, st);
+    if (e != cudaSuccess) return e;
+    const int gt = (n_upper + GT - 1) / GT;
+    if (gemm_ev0) cudaEventRecord(gemm_ev0, st);
+    lm_gemm<<<gt * (gt + 1) / 2, 128, LM_GEMM_SMEM, st>>>(L);
+    if (gemm_ev1) cudaEventRecord(gemm_ev1, st);
+    lm_commit<<<gb, tb, 0, st>>>(L, d_nmeas);
+    *launches += 6;
     return cudaGetLastError();
 }
 

@@ -1030,6 +1030,7 @@ struct UkfWarpSmem {
     double* Xp;     // [2][nsm] propagated vehicle rows x, y of the sigma points
     float* Xcs;     // [2][nsm] rows cos, sin: float VALUES in the reference (ukf.cpp:132-133), stored as such (lossless)
     double* upd;    // [max_meas][UPD_LD]
+    double* veh;    // [24] multi-warp back kernel: xp0v[4], mv[4], vv[10] (vehicle mean / covariance terms) shared by the warps
     double2* stage; // [2 + 64 + 2] rotation-log ring (spare entries for the prefetch overrun)
     double* corr;   // [32] 1e-8 - d_k of the clipped eigenvalues
     int* clip;      // [32] their indices
@@ -1049,6 +1050,7 @@ __host__ __device__ inline size_t ukf_warp_carve(const BatchState& b, const int 
     size_t oXp = take(sizeof(double) * 2 * nsm), oXcs = take(sizeof(float) * 2 * nsm);
     int nupd = (wld - 5) / 2; if (nupd > b.max_meas) nupd = b.max_meas; if (nupd < 1) nupd = 1;     // updates a tile of this pitch can hold
     size_t oupd = take(sizeof(double) * UPD_LD * nupd);
+    size_t oveh = take(sizeof(double) * 24);
     size_t ostage = take(sizeof(double2) * 68);
     size_t ocorr = take(sizeof(double) * 32), oclip = take(sizeof(int) * 32);
     size_t oids = take(sizeof(int) * (b.max_lm + 1));
@@ -1058,7 +1060,7 @@ __host__ __device__ inline size_t ukf_warp_carve(const BatchState& b, const int 
     size_t octl = take(sizeof(int) * 8);
     if (s) {
         s->W = (double*)(base + oW) + 2 * wld; s->x = (double*)(base + ox); s->xp = (double*)(base + oxp); s->sq = (double*)(base + osq);
-        s->Xp = (double*)(base + oXp); s->Xcs = (float*)(base + oXcs); s->upd = (double*)(base + oupd);
+        s->Xp = (double*)(base + oXp); s->Xcs = (float*)(base + oXcs); s->upd = (double*)(base + oupd); s->veh = (double*)(base + oveh);
         s->stage = (double2*)(base + ostage) + 2; s->corr = (double*)(base + ocorr); s->clip = (int*)(base + oclip);
         s->ids = (int*)(base + oids); s->meas = (float*)(base + omeas); s->assoc = (int*)(base + oassoc); s->uq = (int*)(base + ouq); s->ctl = (int*)(base + octl);
     }
@@ -1989,8 +1991,9 @@ __device__ __forceinline__ void dense_cols(double* W, const double* __restrict__
 // different warps, so the reflector products -- a chain of n - 1 dependent dot / update steps per vector group, half of the
 // single-warp kernel's time -- and the dense V / V^T products run NW wide; the updates' sigma-point statistics are spread over
 // the warps by update, the rows of the P_pred assembly by row.  Small scalar phases are evaluated redundantly by every warp.
-template <int wld>
-__global__ void __launch_bounds__(32 * ((wld - 1) / 4), (wld == 13) ? 4 : 2)
+template <int wld, int NTT>      // NTT = row slots per lane: 4 (n_max <= 128) or 8 -- a template parameter so that the small case does not
+                                 // carry the register allocation of the large one
+__global__ void __launch_bounds__(32 * ((wld - 1) / 4), (wld == 13) ? (NTT == 4 ? 6 : 4) : 2)
 ukf_back3_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, const int i0, const int pass) {
     constexpr int NW = (wld - 1) / 4, NTHR = 32 * NW;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -2003,7 +2006,6 @@ ukf_back3_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
     const unsigned FULL = 0xffffffffu;
     const int wcols = wld - 1 < ukf_wcols(b) ? wld - 1 : ukf_wcols(b);
     double* const W_ = s.W;
-    const bool small_n = b.n_max <= 128;
 
     const int4 meta_in = b.meta[inst];
     int nm = in.n_meas[inst];
@@ -2072,7 +2074,6 @@ ukf_back3_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
     const float u_d = in.fwd[in.cmd_stride ? inst : 0], u_th = in.ang[in.cmd_stride ? inst : 0];
     const float yaw_prior = yaw_of(s.x[2], s.x[3]);                        // :182 and :139 (prior x_t)
     const double cy = (double)cos_f(yaw_prior), sy = (double)sin_f(yaw_prior);
-    const double Qd[4] = {fc.V00 * cy, fc.V00 * sy, fc.V11 * cy, fc.V11 * sy};   // :183-186
 
     if (pass == 0) {                                // narrow tile: hand the instance over if its updates do not fit
         const bool over = 4 + 2 * nu > wcols;
@@ -2090,8 +2091,8 @@ ukf_back3_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
         for (int i = warp; i < n; i += NW) if (lane < wcols) W_[i * wld + lane] = (lane < cnt && s.clip[c0 + lane] == i) ? 1.0 : 0.0;
         __syncthreads();
         if (jown < cnt) {
-            if (small_n) { dense_cols<4, wld, 4>(W_, VTm, n, lane, jown, cnt, nullptr); apply_reflectors<false, 4, wld>(W_, n, lane, cnt, R, jown, 4 * NW); }
-            else { dense_cols<8, wld, 4>(W_, VTm, n, lane, jown, cnt, nullptr); apply_reflectors<false, 8, wld>(W_, n, lane, cnt, R, jown, 4 * NW); }
+            dense_cols<NTT, wld, 4>(W_, VTm, n, lane, jown, cnt, nullptr);
+            apply_reflectors<false, NTT, wld>(W_, n, lane, cnt, R, jown, 4 * NW);
         }
         __syncthreads();
         for (int a = 4 + warp; a < n; a += NW)
@@ -2112,8 +2113,8 @@ ukf_back3_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
         __syncthreads();
         if (jown < nvec + ncf) {
             if (jown < nvec) {
-                if (small_n) { apply_reflectors<true, 4, wld>(W_, n, lane, nvec, R, jown, 4 * NW); dense_cols<4, wld, 4>(W_, Vm, n, lane, jown, nvec, s.sq); }
-                else { apply_reflectors<true, 8, wld>(W_, n, lane, nvec, R, jown, 4 * NW); dense_cols<8, wld, 4>(W_, Vm, n, lane, jown, nvec, s.sq); }
+                apply_reflectors<true, NTT, wld>(W_, n, lane, nvec, R, jown, 4 * NW);
+                dense_cols<NTT, wld, 4>(W_, Vm, n, lane, jown, nvec, s.sq);
             }
             // unit vectors e_ck (in the eigenbasis) in the clipped columns of this group
             for (int j = (jown > nvec ? jown : nvec); j < jown + 4 && j < nvec + ncf; ++j) {
@@ -2121,8 +2122,8 @@ ukf_back3_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
                 for (int i = lane; i < n; i += 32) W_[i * wld + j] = (i == ck) ? 1.0 : 0.0;
             }
             __syncwarp();
-            if (small_n) { dense_cols<4, wld, 4>(W_, VTm, n, lane, jown, nvec + ncf, nullptr); apply_reflectors<false, 4, wld>(W_, n, lane, nvec + ncf, R, jown, 4 * NW); }
-            else { dense_cols<8, wld, 4>(W_, VTm, n, lane, jown, nvec + ncf, nullptr); apply_reflectors<false, 8, wld>(W_, n, lane, nvec + ncf, R, jown, 4 * NW); }
+            dense_cols<NTT, wld, 4>(W_, VTm, n, lane, jown, nvec + ncf, nullptr);
+            apply_reflectors<false, NTT, wld>(W_, n, lane, nvec + ncf, R, jown, 4 * NW);
         }
         __syncthreads();
     }
@@ -2146,22 +2147,21 @@ ukf_back3_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
     }
     __syncthreads();
     auto XP = [&](const int r, const int i) -> double { return r < 2 ? s.Xp[r * nsm + i] : (double)s.Xcs[(r - 2) * nsm + i]; };
-    // ---- mean (:228-232) and vehicle block of the covariance (:235-240): every warp evaluates them (same lane order, same values)
-    double xp0v[4];
-    {
-        double acc[4] = {0, 0, 0, 0};
-        for (int i = lane; i < ns; i += 32) {
-            const double wi = (i == 0) ? W0 : wgt;
+    // ---- mean (:228-232) and vehicle block of the covariance (:235-240): warp 0, results in shared memory for everybody
+    //      (s.veh: xp0v[0..4), mv[4..8), vv[8..18)) -- they are read late, and registers are what caps the CTAs per SM here
+    if (warp == 0) {
+        double xp0v[4];
+        {
+            double acc[4] = {0, 0, 0, 0};
+            for (int i = lane; i < ns; i += 32) {
+                const double wi = (i == 0) ? W0 : wgt;
 #pragma unroll
-            for (int r = 0; r < 4; ++r) acc[r] += wi * XP(r, i);
+                for (int r = 0; r < 4; ++r) acc[r] += wi * XP(r, i);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) xp0v[r] = warp_sum(acc[r]);
+            if (lane < 4) { s.xp[lane] = xp0v[lane]; s.veh[lane] = xp0v[lane]; }
         }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) xp0v[r] = warp_sum(acc[r]);
-        if (warp == 0 && lane < 4) s.xp[lane] = xp0v[lane];
-        for (int r = 4 + tid; r < n; r += NTHR) s.xp[r] = sw * s.x[r];
-    }
-    double mv[4], vv[10];
-    {
         double acc[14] = {0};
         for (int i = lane; i < ns; i += 32) {
             const double wi = (i == 0) ? W0 : wgt;
@@ -2178,16 +2178,19 @@ ukf_back3_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
         }
 #pragma unroll
         for (int k = 0; k < 14; ++k) acc[k] = warp_sum(acc[k]);
-        {
+        if (lane == 0) {
+            const double Qd[4] = {fc.V00 * cy, fc.V00 * sy, fc.V11 * cy, fc.V11 * sy};   // :183-186
             int q = 0;
-#pragma unroll
             for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int c = a; c < 4; ++c) { vv[q] = acc[q] + ((a == c) ? Qd[a] : 0.0); ++q; }
+                for (int c = a; c < 4; ++c) { s.veh[8 + q] = acc[q] + ((a == c) ? Qd[a] : 0.0); ++q; }
+            for (int a = 0; a < 4; ++a) s.veh[4 + a] = acc[10 + a];
         }
-#pragma unroll
-        for (int a = 0; a < 4; ++a) mv[a] = acc[10 + a];
     }
+    for (int r = 4 + tid; r < n; r += NTHR) s.xp[r] = sw * s.x[r];
+    __syncthreads();
+    const double* const xp0v = s.veh;
+    const double* const mv = s.veh + 4;
+    const double* const vv = s.veh + 8;
     // ---- the updates' sigma-point statistics (:293-336): update q on warp q mod NW; it leaves hv = dz_i - dz_{i+n} in its two
     //      columns of W (the S rows it read from them are dead by then)
     for (int q = warp; q < nu; q += NW) {
@@ -2265,17 +2268,10 @@ ukf_back3_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
 
     // ---- pass B: S g_a and S hv for every update; the clipped eigenvectors stay put in their columns
     if (jown < nvec) {
-        if (small_n) {
-            apply_reflectors<true, 4, wld>(W_, n, lane, nvec, R, jown, 4 * NW);
-            dense_cols<4, wld, 4>(W_, Vm, n, lane, jown, nvec, s.sq);
-            dense_cols<4, wld, 4>(W_, VTm, n, lane, jown, nvec, nullptr);
-            apply_reflectors<false, 4, wld>(W_, n, lane, nvec, R, jown, 4 * NW);
-        } else {
-            apply_reflectors<true, 8, wld>(W_, n, lane, nvec, R, jown, 4 * NW);
-            dense_cols<8, wld, 4>(W_, Vm, n, lane, jown, nvec, s.sq);
-            dense_cols<8, wld, 4>(W_, VTm, n, lane, jown, nvec, nullptr);
-            apply_reflectors<false, 8, wld>(W_, n, lane, nvec, R, jown, 4 * NW);
-        }
+        apply_reflectors<true, NTT, wld>(W_, n, lane, nvec, R, jown, 4 * NW);
+        dense_cols<NTT, wld, 4>(W_, Vm, n, lane, jown, nvec, s.sq);
+        dense_cols<NTT, wld, 4>(W_, VTm, n, lane, jown, nvec, nullptr);
+        apply_reflectors<false, NTT, wld>(W_, n, lane, nvec, R, jown, 4 * NW);
     }
     __syncthreads();
 
@@ -2492,9 +2488,12 @@ cudaError_t ukf_step_configure(const BatchState& b) {
     if ((e = cudaFuncSetAttribute(ukf_back2_kernel<13, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 13))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back2_kernel<25, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 25))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back2_kernel<33, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 33))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ukf_back3_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 13))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ukf_back3_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 25))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ukf_back3_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 33))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back3_kernel<13, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 13))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back3_kernel<25, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 25))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back3_kernel<33, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 33))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back3_kernel<13, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 13))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back3_kernel<25, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 25))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back3_kernel<33, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 33))) != cudaSuccess) return e;
     if (ukf_warp_smem_bytes(b, 33) <= 227 * 1024) {
         if ((e = cudaFuncSetAttribute(ukf_sigma2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 33))) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(ukf_sigma2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 33))) != cudaSuccess) return e;
@@ -2567,9 +2566,15 @@ cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const St
                 if (b.n_max <= 128) ukf_eig3_kernel<128><<<i1 - i0, 128, eig3_carve(b.n_max, 128, nullptr, nullptr), sk>>>(b, u, i0, u.maxc);
                 else ukf_eig3_kernel<256><<<i1 - i0, 256, eig3_carve(b.n_max, 256, nullptr, nullptr), sk>>>(b, u, i0, u.maxc);
                 if (u.multiwarp) {
-                    if (two_pass || full == 13) ukf_back3_kernel<13><<<i1 - i0, 96, ukf_warp_smem_bytes(b, 13), sk>>>(b, fc, in, u, i0, two_pass ? 0 : 2);
-                    if (full == 25) ukf_back3_kernel<25><<<i1 - i0, 192, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
-                    else if (full == 33) ukf_back3_kernel<33><<<i1 - i0, 256, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
+                    if (b.n_max <= 128) {
+                        if (two_pass || full == 13) ukf_back3_kernel<13, 4><<<i1 - i0, 96, ukf_warp_smem_bytes(b, 13), sk>>>(b, fc, in, u, i0, two_pass ? 0 : 2);
+                        if (full == 25) ukf_back3_kernel<25, 4><<<i1 - i0, 192, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
+                        else if (full == 33) ukf_back3_kernel<33, 4><<<i1 - i0, 256, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
+                    } else {
+                        if (two_pass || full == 13) ukf_back3_kernel<13, 8><<<i1 - i0, 96, ukf_warp_smem_bytes(b, 13), sk>>>(b, fc, in, u, i0, two_pass ? 0 : 2);
+                        if (full == 25) ukf_back3_kernel<25, 8><<<i1 - i0, 192, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
+                        else if (full == 33) ukf_back3_kernel<33, 8><<<i1 - i0, 256, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
+                    }
                 } else {
                     if (two_pass || full == 13) ukf_back2_kernel<13, true><<<i1 - i0, 32, ukf_warp_smem_bytes(b, 13), sk>>>(b, fc, in, u, i0, two_pass ? 0 : 2);
                     if (full == 25) ukf_back2_kernel<25, true><<<i1 - i0, 32, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
