@@ -179,7 +179,9 @@ int  slam_step_io(slam_handle_t h, const float* fwd, const float* ang, int cmd_s
  * HOST buffers (pinned memory makes the copies overlap the kernels): cmd_fwd/cmd_ang [T] (cmd_stride 0) or
  * [T][batch]; meas [T][batch][max_meas][3]; n_meas [T][batch]; poses_out [T][batch][3] (may be NULL).  Chunks of the
  * run are uploaded, filtered and downloaded in a three-stage pipeline; known-ID EKF batches keep each filter resident
- * in shared memory for a whole chunk.  The caller synchronises (slam_synchronize) before reading poses_out. */
+ * in shared memory for a whole chunk.  Available on every path (the HBM-resident large map runs per-step launches).  The caller
+ * synchronises (slam_synchronize) before reading poses_out. */
+/* (Available on every path, the HBM-resident large map included.) */
 int  slam_run_io(slam_handle_t h, const float* cmd_fwd, const float* cmd_ang, int cmd_stride,
                  const float* meas, const int* n_meas, double* poses_out, int T);
 
@@ -191,8 +193,8 @@ int  slam_run_io(slam_handle_t h, const float* cmd_fwd, const float* cmd_ang, in
  *      algorithmic flops (EKF 4 k n^2; UKF 9n^3+2n^3+2n^2(2n+1)+12kn^2), [10]=sum of n, [11]=sum of k+j;
  *      and what the kernels really do, as a model kept beside the algorithmic figures: [12]=sum of the HBM bytes the
  *      launches move for an instance (batched EKF: the PACKED lower triangle each way -- once per step on the per-step
- *      kernel, once per chunk on the sweep kernel), [13]=sum of the flops they execute (batched EKF: the lower
- *      triangle only, ~2 k n^2; UKF generation 2: tridiagonalisation + QL + the S-products).
+ *      kernel, once per chunk on the sweep kernel), [13]=sum of the flops they execute (batched EKF and large map:
+ *      the lower triangle only, half of 4 k n^2; UKF: tridiagonalisation + eigensolver + the S-products, a model).
  *      Ranks all-reduce this vector (SUM). */
 #define SLAM_NUM_STATS 14
 int  slam_accumulate_error(slam_handle_t h, slam_sim_t s);

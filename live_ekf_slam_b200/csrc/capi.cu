@@ -989,7 +989,6 @@ int slam_run_io(slam_handle_t h, const float* cmd_fwd, const float* cmd_ang, int
                 const int* n_meas, double* poses_out, int T) {
     if (!h) return 1;
     if (!cmd_fwd || !cmd_ang || !meas || !n_meas || T < 0) return fail(h, "slam_run_io: bad argument");
-    if (h->large) return fail(h, "slam_run_io: not available on the large-map path (use slam_step)");
     CK(cudaSetDevice(h->device));
     const BatchState& b = h->b;
     const size_t per = cmd_stride ? (size_t)b.batch : 1;

@@ -432,14 +432,12 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
 
 // algorithmic work of one update, using the live n at the end of the step
 // w[4]: flops the kernel executes for the step's rank-2 updates: the lower triangle only, 16 per 2x2 block = ~2 k n^2
-__device__ __forceinline__ void ekf_work_terms(const int n, const int nm, const int n_upd, double (&w)[5]) {
+__device__ __forceinline__ void ekf_work_terms(const int n, const int nm, const int n_upd, double (&w)[4]) {
     const double nd = (double)n;
     w[0] += 16.0 * nd * nd + 16.0 * nd + 12.0 * nm + 8.0;
     w[1] += 4.0 * (double)n_upd * nd * nd;
     w[2] += nd;
     w[3] += (double)nm;
-    const double A = 0.5 * (nd + 1.0);
-    w[4] += 8.0 * (double)n_upd * A * (A + 1.0);
 }
 // bytes one pass of the packed covariance over HBM moves (one direction): two planes of A (A + 1) doubles, A = 2 + M
 __device__ __forceinline__ double ekf_plane_bytes(const int M) { return 16.0 * (double)bpl_plane_doubles(2 + M); }
@@ -530,10 +528,10 @@ __device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterCo
         b.meta[inst] = make_int4(M, status, meta_in.z + ((phases & STEP_PREDICT) ? 1 : 0),   // timestep, :39
                                  (phases & STEP_UPDATE) ? nm : meta_in.w);
         if (M > M_start) atomicMax(b.max_M, M);
-        double w[5] = {0, 0, 0, 0, 0};
+        double w[4] = {0, 0, 0, 0};
         ekf_work_terms(n, nm, n_upd, w);
         double* st = b.stats + (size_t)inst * SLAM_NUM_STATS;
-        st[8] += w[0]; st[9] += w[1]; st[10] += w[2]; st[11] += w[3]; st[13] += w[4];
+        st[8] += w[0]; st[9] += w[1]; st[10] += w[2]; st[11] += w[3]; st[13] += 0.5 * w[1];
         // bytes this launch really moved for the instance: packed P in and out, x in and out, ids, message, meta
         st[12] += ekf_plane_bytes(M_start) + ekf_plane_bytes(M) + 8.0 * (n0 + n) + 4.0 * M + 12.0 * nm + 4.0 * nm + 32.0;
         // shared memory may be reused / released once the bulk engine has READ it; global visibility of the writes
@@ -637,6 +635,7 @@ ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, SweepA
         if (producer) {
             // ================= producer warp: messages ahead, per-step outputs behind =================
             double tr[3] = {0, 0, 0};
+            const double* const lm_mine = REPLAY ? nullptr : sim.lm_xy + (size_t)inst * sim.lm_stride;   // this vehicle's map
             if (!REPLAY) { const double* t = sim.truth + 3 * (size_t)inst; tr[0] = t[0]; tr[1] = t[1]; tr[2] = t[2]; }
             double trp[2][3] = {{0, 0, 0}, {0, 0, 0}};   // truth of the step with parity p
             double eacc[6] = {0, 0, 0, 0, 0, 0};
@@ -652,7 +651,7 @@ ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, SweepA
                         for (int i = lane; i < 3 * nm_last; i += 32) w.meas[p][i] = src[i];
                         if (lane == 0) w.nm[p] = count;         // raw count: the consumers flag the overflow
                     } else {
-                        const int count = sim_get_cmd_warp(lane, sc, sim.lm_xy + (size_t)inst * sim.lm_stride, sim.n_lm, b.max_meas, sim.k0, sim.k1,
+                        const int count = sim_get_cmd_warp(lane, sc, lm_mine, sim.n_lm, b.max_meas, sim.k0, sim.k1,
                                                            sim.instance_offset + (uint32_t)inst, a.first_step + (uint32_t)t,
                                                            a.cmd_fwd[(size_t)t * cstep + coff], a.cmd_ang[(size_t)t * cstep + coff],
                                                            tr, w.meas[p]);
@@ -700,8 +699,7 @@ ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, SweepA
             if (tid == 0) { s.iscr[IS_NAN] = 0; s.iscr[IS_DEAD] = 0; s.iscr[IS_OVER] = 0; ekf_load_P(b, s, ps2, gP, M); }
             for (int i = tid; i < n0; i += NT) s.x[i] = gx[i];
             for (int i = tid; i < M; i += NT) s.ids[i] = b.ids[(size_t)inst * b.max_lm + i];
-            double wacc[5] = {0, 0, 0, 0, 0};            // work counters, carried by thread 0
-            double moved = ekf_plane_bytes(M) + 8.0 * n0 + 4.0 * M + 16.0;   // HBM bytes this chunk really moves for the instance
+            double wacc[4] = {0, 0, 0, 0};               // work counters, carried by thread 0
             int timestep = meta_in.z, nm = 0;
             if (warp == 0) mbar_wait(s.bar, parity);
             Sync::sync();
@@ -758,9 +756,12 @@ ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, SweepA
                     b.meta[inst] = make_int4(M, status, timestep, (T > 0 && !frozen) ? nm : (frozen ? 0 : meta_in.w));
                     if (M > M_first) atomicMax(b.max_M, M);
                     double* st = b.stats + (size_t)inst * SLAM_NUM_STATS;
-                    st[8] += wacc[0]; st[9] += wacc[1]; st[10] += wacc[2]; st[11] += wacc[3]; st[13] += wacc[4];
-                    // P and x go back once per chunk; per step only the message (replay: 12 nm + 4 in, 24 out) crosses HBM
-                    st[12] += moved + ekf_plane_bytes(M) + 8.0 * n + 4.0 * (M - M_first) + (REPLAY ? 12.0 * wacc[3] + 28.0 * T : 8.0 * T);
+                    st[8] += wacc[0]; st[9] += wacc[1]; st[10] += wacc[2]; st[11] += wacc[3];
+                    st[13] += 0.5 * wacc[1];     // executed: the lower triangle only = half of 4 k n^2 (+ ~4/n for the diagonal blocks; kept out of the step loop)
+                    // HBM bytes this chunk really moves for the instance: P and x in and out once per chunk; per step only the
+                    // message (replay: 12 nm + 4 in, 24 out) crosses HBM
+                    st[12] += ekf_plane_bytes(M_first) + ekf_plane_bytes(M) + 8.0 * (n0 + n) + 4.0 * M + 16.0
+                              + (REPLAY ? 12.0 * wacc[3] + 28.0 * T : 8.0 * T);
                     a.progress[inst] = a.t0 + T;
                     bulk_wait_read();    // the tile is re-filled by the next instance
                 }

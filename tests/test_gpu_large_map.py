@@ -140,3 +140,34 @@ def test_large_map_baseline_size_teacher_forced(shim, oracle):
     for t, n0, k, j in report[len(early):]:
         assert n0 >= 3503 and k >= 60, (t, n0, k)                          # BASELINE size: n >= 3500, k >= 60
     print("large map full size: (t, n, updates, insertions) =", report, "worst normwise err", worst)
+
+
+def test_large_map_run_io(shim, oracle):
+    """slam_run_io on the large-map path (the step is asynchronous now: the detection count stays on the device): a recorded run
+    through HOST buffers against per-step slam_step calls and the oracle."""
+    p, lm, fwd, ang = dense_workload(100, 3.0, 50, seed=7, known=False)
+    op = H.oracle_params(oracle, p)
+    T, mm = len(fwd), 128
+    stream, _ = H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=3, instance=0)
+    ref = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 1, 100, mm)
+    ref.init(0, 0, 0)
+    meas = np.zeros((T, 1, mm, 3), dtype=np.float32)
+    nm = np.zeros((T, 1), dtype=np.int32)
+    ref_poses = np.zeros((T, 1, 3))
+    of = oracle.OracleFilter(oracle.EKF_SLAM, op, 100)
+    of.init(0, 0, 0)
+    for t in range(T):
+        meas[t], nm[t] = ref.pack_meas([stream[t]])
+        ref.step(fwd[t], ang[t], meas[t], nm[t])
+        ref_poses[t] = ref.poses()
+        of.update(fwd[t], ang[t], stream[t], oracle.STRUCTURED)
+    fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), 1, 100, mm)
+    fb.tune(5, 16)
+    fb.init(0, 0, 0)
+    out = np.zeros((T, 1, 3))
+    fb.run_io(fwd, ang, 0, meas, nm, out, T)
+    fb.synchronize()
+    np.testing.assert_array_equal(out, ref_poses)
+    np.testing.assert_array_equal(fb.cov(0), ref.cov(0))
+    assert fb.num_landmarks(0) == of.M and fb.timestep(0) == T
+    assert H.normwise(fb.state(0), of.state()) <= H.REL_TOL and H.normwise(fb.cov(0), of.cov()) <= H.REL_TOL
