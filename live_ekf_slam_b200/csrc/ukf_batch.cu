@@ -1373,12 +1373,27 @@ ukf_eig3_kernel(BatchState b, UkfScratch u, const int i0, const int maxc) {
     const double pivmin = fmax(2.2250738585072014e-308 * fmax(1.0, e2max), 1e-300);
     const double pivf = eig3::EPS * tn;
     int a = 0, bb = 0;
-    double lam = 0.0;
+    double lam = 0.0, glo = 0.0, ghi = 0.0;
     if (live) {
         a = t; while (a > 0 && s.e[a - 1] != 0.0) --a;
         bb = t + 1; while (bb < n && s.e[bb - 1] != 0.0) ++bb;
         s.b0[t] = a; s.b1[t] = bb;
-        lam = eig3::bisect(s.d, s.e, s.de, a, bb, t - a, pivmin);
+        if (bb - a > 1) {
+            // multisection start: one Sturm count per thread on a uniform grid over the block's Gershgorin interval, shared below
+            eig3::block_bounds(s.d, s.e, a, bb, pivmin, glo, ghi);
+            const double x0 = eig3::grid_point(glo, ghi, t - a, bb - a);
+            s.lt[t] = x0;
+            s.tw[t] = eig3::sturm_count(s.de, a, bb, x0);
+        }
+    }
+    __syncthreads();
+    if (live) {
+        if (bb - a == 1) lam = s.d[a];
+        else {
+            double lo = glo, hi = ghi;
+            eig3::bracket_from_grid(s.lt, s.tw, a, bb, t - a, lo, hi);
+            lam = eig3::bisect_bracket(s.de, a, bb, t - a, lo, hi, 2.0 * eig3::EPS * tn + 2.0 * pivmin);
+        }
         s.lam[t] = lam;
     }
     __syncthreads();

@@ -27,11 +27,24 @@ int main() {
     std::vector<int> b0(n), b1(n), crank(n), cfirst(n), tw(n);
     std::vector<De> de(n);
     for (int t = 0; t < n; ++t) de[t] = De{d[t], t > 0 ? e2[t - 1] : 0.0};
+    std::vector<double> px(n, 0.0), glo(n, 0.0), ghi(n, 0.0);
+    std::vector<int> pc(n, 0);
     for (int t = 0; t < n; ++t) {
         int a = t; while (a > 0 && e[a - 1] != 0.0) --a;
         int b = t + 1; while (b < n && e[b - 1] != 0.0) ++b;
         b0[t] = a; b1[t] = b;
-        lam[t] = bisect(d.data(), e.data(), de.data(), a, b, t - a, pivmin);
+        if (b - a > 1) {                           // multisection start, as in the kernel
+            block_bounds(d.data(), e.data(), a, b, pivmin, glo[t], ghi[t]);
+            px[t] = grid_point(glo[t], ghi[t], t - a, b - a);
+            pc[t] = sturm_count(de.data(), a, b, px[t]);
+        }
+    }
+    for (int t = 0; t < n; ++t) {
+        const int a = b0[t], b = b1[t];
+        if (b - a == 1) { lam[t] = d[a]; continue; }
+        double lo = glo[t], hi = ghi[t];
+        bracket_from_grid(px.data(), pc.data(), a, b, t - a, lo, hi);
+        lam[t] = bisect_bracket(de.data(), a, b, t - a, lo, hi, 2.0 * EPS * tn + 2.0 * pivmin);
     }
     int maxrank = 0;
     for (int t = 0; t < n; ++t) {
