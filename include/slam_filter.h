@@ -230,7 +230,9 @@ int  slam_get_ukf_routes(slam_handle_t h, long long* out /* 3 */);
  * CTA per instance); key 12: largest cluster of close eigenvalues the generation-3 eigensolver re-orthogonalises itself (larger
  * clusters send the instance down the generation-2 route in the same step; 1 forces that route for any cluster); key 13: 0 = the
  * one-warp-per-instance back kernel of generation 3 instead of the multi-warp one; key 14: 1 = slam_step_io always stages its
- * buffers through device copies, even when they are pinned host memory the kernels could read in place; key 8: capacity of the UKF rotation log
+ * buffers through device copies, even when they are pinned host memory the kernels could read in place; key 15: 0 = the generation-3
+ * eigensolver builds its eigenvectors in the global scratch instead of a shared-memory tile; key 16: 1 = (test knob) the tile
+ * kernel hands every instance with a cluster of close eigenvalues to the global-scratch kernel, as if it needed the refinement step; key 8: capacity of the UKF rotation log
  * (shrinking it forces the rescue pass); key 9: max clipped eigenvectors riding beside the first S-pass; key 10: slices of the UKF batch that run their
  * front -> QL -> back chains on separate streams (1..8); key 11: 0 = skip the narrow-tile first pass of the UKF back kernel.
  * Results never depend on any of them (keys 7-9: up to rounding, inside the parity tolerance). */

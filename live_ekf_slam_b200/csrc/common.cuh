@@ -213,6 +213,8 @@ struct UkfScratch {
     unsigned long long* routes;   // [4] instance-steps taken by: dense route (gen 3), QL route (gen 2), gen-1 / rescue, (spare)
     int multiwarp;      // generation 3: 1 (default) = back kernel with one warp per group of four vectors, 0 = one warp per instance
     int maxc;           // generation 3: largest cluster of close eigenvalues handled in the kernel (larger: QL route)
+    int refine_all;     // test knob: the tile kernel hands EVERY instance with a cluster to the two-array kernel (as if it needed refinement)
+    int eig3_tile;      // generation 3: 1 (default) = eigenvectors built in a shared-memory tile when it fits twice per SM, 0 = in the global scratch
     double* xprior;     // [batch][n_max]  x_t at the start of the last step: column 0 of the sigma-point matrix X (ukf.cpp:214)
     int2* sigfmt;       // [batch]  what the scratch holds of the last step's sqrt factor, for slam_get_sigma_points:
                         //          .x = 0 nothing yet (X is the constructor's 4 x 9 zero matrix, ukf.cpp:20), 2 = reflectors (Zg) +

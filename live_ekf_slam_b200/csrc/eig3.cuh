@@ -34,6 +34,11 @@ namespace eig3 {
 constexpr double EPS = 2.220446049250313e-16;
 constexpr int MAXC_DEFAULT = 16;          // largest cluster re-orthogonalised in the kernel; larger ones fall back to QL
 constexpr int MAX_BISECT = 64;
+// Gram-Schmidt inside a cluster: a (unit) vector that keeps less than this much of its norm^2 after the projections was nearly
+// parallel to an earlier member, so the subtraction amplified its error -- only then are the cluster members refined by one
+// more inverse-iteration step and orthogonalised again.  (Twisted-factorisation vectors of eigenvalues 1e-3 |T| ... 1e-9 |T|
+// apart are orthogonal to ~eps |T| / gap already: the projections remove ~1e-13 ... 1e-7 and nothing needs repair.)
+constexpr double REFINE_BELOW = 0.75;
 
 // strided view of a per-thread work vector: element i of thread t lives at base[i * stride] (stride = threads' pitch, so the
 // accesses of a warp coalesce)
@@ -82,31 +87,49 @@ EIG3_HD int popcount32(const uint32_t v) {
 // counted by popc every 28 terms.  An exactly vanishing p_i needs no special case: with e_i != 0 inside a block its
 // neighbours have opposite signs, so (s, +0, -s) and (s, -0, -s) both show exactly one change.  The pair (p_i-1, p_i) is
 // rescaled by 2^-+400 when it leaves [2^-400, 2^400] (checked every fourth term: one term grows by at most ~(2 |T|)^2).
-EIG3_HD int sturm_count(const De* de, const int a, const int b, const double x) {
+// WANT_F: also return the last term, p_n(x) = det(T_block - x I) = fm * 2^fs -- the function whose root the eigenvalue is.
+struct Fval { double m; int s; };
+template <bool WANT_F>
+EIG3_HD int sturm_core(const De* de, const int a, const int b, const double x, Fval* f) {
     double pm1 = 1.0, p = de[a].d - x;
     uint32_t bits = shift_in_sign(0u, p);            // bit 1: sign of p_0 (+), bit 0: sign of p_1
     int cnt = (int)(bits & 1u);
+    int sexp = 0;
     bits &= 1u;
+#ifdef EIG3_PREFETCH
+    De nx0 = de[(a + 1 < b) ? a + 1 : a], nx1 = de[(a + 2 < b) ? a + 2 : a];     // the next two terms' operands, fetched ahead of the chain
+#endif
     for (int i0 = a + 1; i0 < b; i0 += 28) {
         const int kmax = (b - i0 < 28) ? b - i0 : 28;
         for (int k = 0; k < kmax; ++k) {
+#ifdef EIG3_PREFETCH
+            const De v = nx0;
+            nx0 = nx1;
+            nx1 = de[(i0 + k + 2 < b) ? i0 + k + 2 : a];
+#else
             const De v = de[i0 + k];
+#endif
             const double pn = fma(v.d - x, p, -(v.e2 * pm1));
             pm1 = p; p = pn;
             bits = shift_in_sign(bits, p);
             if ((k & 3) == 3) {
                 const uint32_t ex = hi_word(p) & 0x7ff00000u;
                 if (ex - 0x26f00000u > 0x58f00000u - 0x26f00000u) {                 // one unsigned compare: outside [2^-400, 2^400] (rare)
-                    const double sc = (ex > 0x58f00000u) ? 3.87259191484932e-121 : 2.5822498780869086e+120;    // 2^-400 : 2^400
+                    const bool big = ex > 0x58f00000u;
+                    const double sc = big ? 3.87259191484932e-121 : 2.5822498780869086e+120;    // 2^-400 : 2^400
                     p *= sc; pm1 *= sc;
+                    if (WANT_F) sexp += big ? 400 : -400;
                 }
             }
         }
         cnt += popcount32((bits ^ (bits >> 1)) & ((1u << kmax) - 1u));   // changes among the kmax + 1 most recent signs
         bits &= 1u;
     }
+    if (WANT_F) { f->m = p; f->s = sexp; }
     return cnt;
 }
+EIG3_HD int sturm_count(const De* de, const int a, const int b, const double x) { return sturm_core<false>(de, a, b, x, nullptr); }
+EIG3_HD int sturm_eval(const De* de, const int a, const int b, const double x, Fval* f) { return sturm_core<true>(de, a, b, x, f); }
 
 // Gershgorin interval of the block [a, b), widened like dstebz
 EIG3_HD void block_bounds(const double* d, const double* e, const int a, const int b, const double pivmin, double& lo, double& hi) {
@@ -142,9 +165,9 @@ EIG3_HD double bisect(const double* d, const double* e, const De* de, const int 
     return bisect_bracket(de, a, b, j, lo, hi, 2.0 * EPS * tnorm + 2.0 * pivmin);
 }
 
-// Multisection start (the kernel runs it once per CTA before the bisection): the threads of a block evaluate the Sturm count on
-// a uniform grid of nb points over the block's Gershgorin interval, one point each, and share (point, count); every thread then
-// starts its bisection from the grid cell that brackets its eigenvalue -- log2(nb) steps saved for one extra Sturm sweep.
+// Multisection start (the kernel runs it once per CTA before the root search): the threads of a block evaluate the Sturm count
+// on a uniform grid of nb points over the block's Gershgorin interval, one point each, and share (point, count, p_n); every
+// thread then starts from the grid cell that brackets its eigenvalue -- log2(nb) steps saved for one extra Sturm sweep.
 EIG3_HD double grid_point(const double glo, const double ghi, const int j, const int nb) {
     return glo + ((double)j + 0.5) * ((ghi - glo) / (double)nb);
 }
@@ -153,6 +176,73 @@ EIG3_HD void bracket_from_grid(const double* px, const int* pc, const int a, con
         const double x = px[q];
         if (pc[q] > j) hi = fmin(hi, x); else lo = fmax(lo, x);
     }
+}
+
+// State of one end of a bracket: the point, the Sturm count there and (when `known`) p_n there
+struct End { double x; int c; Fval f; bool known; };
+// the same search as bracket_from_grid, also returning which grid point (or -1: the Gershgorin end) each side came from
+EIG3_HD void bracket_from_grid2(const double* px, const int* pc, const int a, const int b, const int j, double& lo, double& hi,
+                                int& qlo, int& qhi) {
+    qlo = -1; qhi = -1;
+    for (int q = a; q < b; ++q) {
+        const double x = px[q];
+        if (pc[q] > j) { if (x < hi) { hi = x; qhi = q; } }
+        else if (x > lo) { lo = x; qlo = q; }
+    }
+}
+
+// j-th smallest eigenvalue of the block from a bracket lo.c <= j < hi.c, to hi - lo <= tol.  While the bracket holds more than
+// one eigenvalue (or p_n is unknown at an end) the step is a bisection; once the eigenvalue is ISOLATED, p_n changes sign across
+// the bracket exactly once and the step is a secant step on p_n with the Illinois modification (an end kept twice has its
+// function value halved, which pulls that end in: superlinear, ~1.44 per evaluation, against one bit per evaluation).  Every
+// step is decided by the Sturm count at the new point, so the bracket invariant is the bisection's.  Two safeguards:
+//   * the proposal is kept 0.75 tol inside the bracket (Brent's minimal step: a root next to an end closes the bracket in one
+//     move, so the search ends when the ESTIMATE has converged, not only when both ends have);
+//   * a secant step that did not reduce |p_n| at its end by at least 4x was taken where p_n is far from linear (a wide bracket of
+//     a degree-n polynomial): the next step is a bisection -- at worst two evaluations per halving.
+EIG3_HD bool fval_reduced(const Fval& fnew, const Fval& fold) {      // |fnew| < |fold| / 4
+    if (fnew.s != fold.s) return fnew.s < fold.s;
+    return fabs(fnew.m) * 4.0 < fabs(fold.m);
+}
+EIG3_HD double root_bracket(const De* de, const int a, const int b, const int j, End lo, End hi, const double tol, int* nevals) {
+    int side = 0, ne = 0;
+    bool bisect_next = false;
+    for (int it = 0; it < 2 * MAX_BISECT; ++it) {
+        const double w = hi.x - lo.x;
+        if (w <= tol) break;
+        const int ds = hi.f.s - lo.f.s;
+        bool secant = hi.c - lo.c == 1 && lo.known && hi.known && !bisect_next && w > 1.5 * tol && ds <= 400 && ds >= -400;
+        double x = 0.5 * (lo.x + hi.x);
+        if (secant) {
+            double r = hi.f.m / lo.f.m;                               // p_n(hi) / p_n(lo) < 0
+            if (ds != 0) r *= (ds > 0) ? 2.5822498780869086e+120 : 3.87259191484932e-121;
+            if (r < 0.0) {
+                x = lo.x + w / (1.0 - r);
+                x = fmin(fmax(x, lo.x + 0.75 * tol), hi.x - 0.75 * tol);
+            } else secant = false;
+        }
+        if (x <= lo.x || x >= hi.x) break;                           // adjacent doubles
+        Fval f;
+        const int c = sturm_eval(de, a, b, x, &f);
+        ++ne;
+        bisect_next = false;
+        if (c > j) {
+            if (secant) bisect_next = !fval_reduced(f, hi.f);
+            hi.x = x; hi.c = c; hi.f = f; hi.known = true;
+            if (side == 1) lo.f.m *= 0.5;
+            side = 1;
+        } else {
+            if (secant) bisect_next = !fval_reduced(f, lo.f);
+            lo.x = x; lo.c = c; lo.f = f; lo.known = true;
+            if (side == -1) hi.f.m *= 0.5;
+            side = -1;
+        }
+#ifdef EIG3_TRACE_ROOT
+        if (EIG3_TRACE_ROOT(j)) fprintf(stderr, "    it %d secant %d x %.17g c %d f %.3e s %d  lo %.17g hi %.17g\n", it, (int)secant, x, c, f.m, f.s, lo.x, hi.x);
+#endif
+    }
+    if (nevals) *nevals = ne;
+    return 0.5 * (lo.x + hi.x);
 }
 
 // Twisted factorisation of T - x I on the block [a, b) and the eigenvector it yields.  z: the thread's vector (on exit the
@@ -221,6 +311,55 @@ EIG3_HD int twisted_vector(const double* d, const double* e, const double* e2, c
         }
     }
     z.set(k, 1.0); w.set(k, gk);
+    *nrm2 = s2;
+    return k;
+}
+
+// The same eigenvector in ONE work vector (the shared-memory variant of the kernel: a column of an n x n tile per thread, no
+// second array): the pivots are overwritten by the vector's components as the recurrences consume them.  Nothing is kept for a
+// refinement step -- the caller hands such (rare) instances to the two-array routine above.
+EIG3_HD int twisted_vector1(const double* d, const double* e, const double* e2, const int a, const int b, const double x,
+                            const double pivf, const Slot z, double* nrm2) {
+    double dp = d[a] - x;
+    for (int i = a; i < b - 1; ++i) {
+        if (fabs(dp) < pivf) dp = -pivf;
+        z.set(i, dp);
+        dp = (d[i + 1] - x) - e2[i] / dp;
+    }
+    if (fabs(dp) < pivf) dp = -pivf;
+    z.set(b - 1, dp);
+    double dm = d[b - 1] - x;
+    if (fabs(dm) < pivf) dm = -pivf;
+    int k = b - 1;
+    double gk = dp + dm - (d[b - 1] - x), best = fabs(gk);
+    for (int i = b - 1; i > a; --i) {
+        double dn = (d[i - 1] - x) - e2[i - 1] / dm;
+        if (fabs(dn) < pivf) dn = -pivf;
+        const double g = z.get(i - 1) + dn - (d[i - 1] - x);
+        if (fabs(g) <= best) { best = fabs(g); gk = g; k = i - 1; }
+        dm = dn;
+    }
+    dm = d[b - 1] - x;
+    if (fabs(dm) < pivf) dm = -pivf;
+    for (int i = b - 1; i > k; --i) {
+        z.set(i, dm);
+        double dn = (d[i - 1] - x) - e2[i - 1] / dm;
+        if (fabs(dn) < pivf) dn = -pivf;
+        dm = dn;
+    }
+    double s2 = 1.0, zi = 1.0;
+    for (int i = k - 1; i >= a; --i) {
+        zi = -(e[i] / z.get(i)) * zi;
+        z.set(i, zi);
+        s2 += zi * zi;
+    }
+    zi = 1.0;
+    for (int i = k; i < b - 1; ++i) {
+        zi = -(e[i] / z.get(i + 1)) * zi;
+        z.set(i + 1, zi);
+        s2 += zi * zi;
+    }
+    z.set(k, 1.0);
     *nrm2 = s2;
     return k;
 }

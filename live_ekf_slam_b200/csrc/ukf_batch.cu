@@ -1311,23 +1311,44 @@ ukf_front2_kernel(BatchState b, UkfScratch u, const int i0) {
 //             VTg [batch][n^2]  VT[k][i] = the transpose (rows contiguous over i); doubles as the solver's per-thread work space
 // =========================================================================================================
 struct Eig3Smem {
-    double *d, *e, *e2, *lam, *lt, *red;
+    double *d, *e, *e2, *lam, *lt, *red, *gm;
     eig3::De* de;       // {d[i], e[i-1]^2} packed for the Sturm recurrence
-    int *b0, *b1, *crank, *cfirst, *tw, *flag;
+    int *b0, *b1, *crank, *cfirst, *tw, *flag, *gs;     // (lt, tw, gm, gs): the multisection grid -- point, count, p_n = gm 2^gs
+    double* tile;       // shared-memory variant: n x (n_max | 1) work tile, column t = thread t's vector
 };
-__host__ __device__ inline size_t eig3_carve(const int n_max, const int nt, unsigned char* base, Eig3Smem* s) {
+__host__ __device__ inline size_t eig3_carve(const int n_max, const int nt, unsigned char* base, Eig3Smem* s, const bool tile = false) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
     const size_t od = take(8 * n_max), oe = take(8 * n_max), oe2 = take(8 * n_max), ol = take(8 * n_max), olt = take(8 * n_max), ored = take(8 * 40);
-    const size_t ode = take(16 * n_max);
+    const size_t ode = take(16 * n_max), ogm = take(8 * n_max), ogs = take(4 * n_max);
     const size_t ob0 = take(4 * n_max), ob1 = take(4 * n_max), ocr = take(4 * n_max), ocf = take(4 * n_max), otw = take(4 * n_max), ofl = take(4 * 8);
+    const size_t oti = tile ? take((size_t)8 * n_max * (n_max | 1)) : 0;
     if (s) {
+        s->tile = (double*)(base + oti);
         s->d = (double*)(base + od); s->e = (double*)(base + oe); s->e2 = (double*)(base + oe2); s->lam = (double*)(base + ol);
         s->lt = (double*)(base + olt); s->red = (double*)(base + ored); s->de = (eig3::De*)(base + ode);
         s->b0 = (int*)(base + ob0); s->b1 = (int*)(base + ob1); s->crank = (int*)(base + ocr); s->cfirst = (int*)(base + ocf);
-        s->tw = (int*)(base + otw); s->flag = (int*)(base + ofl);
+        s->tw = (int*)(base + otw); s->flag = (int*)(base + ofl); s->gm = (double*)(base + ogm); s->gs = (int*)(base + ogs);
     }
     return off;
+}
+
+// Size classes of the shared-memory variant: the tile (and with it the CTAs per SM) is sized by the class, not by the batch's
+// capacity, so an instance with few landmarks runs at 4 CTAs per SM and only the largest ones at 2.  One launch per class; a CTA
+// whose instance belongs to another class exits at once.  caps[k] = largest n of class k (ascending), returns the class count;
+// 0 = the variant is not used (n_max beyond what fits twice per SM, or 128 threads).
+inline int eig3_classes(const BatchState& b, int caps[4]) {
+    if (b.n_max > 128) return 0;
+    static const int per_sm[3] = {4, 3, 2};        // (<= 128 registers per thread: four CTAs of 128 threads at most)
+    int nc = 0, prev = 0;
+    for (int k = 0; k < 3; ++k) {
+        const size_t budget = (size_t)(227 * 1024) / per_sm[k] - 1024;
+        int cap = prev;
+        while (cap < b.n_max && eig3_carve(cap + 1, 128, nullptr, nullptr, true) <= budget) ++cap;
+        if (cap > prev) { caps[nc++] = cap; prev = cap; }
+        if (cap >= b.n_max) return nc;
+    }
+    return 0;                                      // the largest instances would not fit twice per SM
 }
 
 template <int NT>
@@ -1344,22 +1365,66 @@ __device__ __forceinline__ double cta_max(double v, double* red) {
 }
 
 // ---- launch 2 of 3 (generation 3): CTA per instance, thread t <-> eigenpair t of the tridiagonal matrix
-template <int NT>
-__global__ void __launch_bounds__(NT, 1024 / NT)      // <= 64 registers: the bisection is a latency chain, hidden by resident warps only
-ukf_eig3_kernel(BatchState b, UkfScratch u, const int i0, const int maxc) {
+// modified Gram-Schmidt inside the clusters of an instance, vectors = columns of `base` (leading dimension ld; global scratch or
+// the shared-memory tile).  Every WARP takes whole clusters, round robin, and walks the members of a cluster in order (lanes
+// stride over the components: dot products and updates are 32 wide; __syncwarp orders a member's stores before the next
+// member's loads).  flag[2]: a projection removed a sizeable part of a vector (first pass); flag[1]: still dependent (second).
+__device__ __forceinline__ void eig3_gram_schmidt(const Eig3Smem& s, double* base, const int ld, const int n, const int warp, const int lane,
+                                                  const int nwarps, const int pass) {
+    int ord = 0;
+    for (int m0 = 0; m0 + 1 < n; ++m0) {
+        if (s.crank[m0] != 0 || s.crank[m0 + 1] == 0) continue;          // m0: first index of a cluster
+        if ((ord++ % nwarps) != warp) continue;
+        const int ma = s.b0[m0], mb = s.b1[m0];
+        for (int m = m0 + 1; m < mb && s.crank[m] > 0; ++m) {
+            double* zm = base + m;
+            for (int q = m0; q < m; ++q) {
+                const double* zq = base + q;
+                double dot = 0.0;
+                for (int i = ma + lane; i < mb; i += 32) dot += zq[(size_t)i * ld] * zm[(size_t)i * ld];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                for (int i = ma + lane; i < mb; i += 32) zm[(size_t)i * ld] -= dot * zq[(size_t)i * ld];
+            }
+            double n2 = 0.0;
+            for (int i = ma + lane; i < mb; i += 32) { const double v = zm[(size_t)i * ld]; n2 += v * v; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+            // unit vector before: a small remainder means nearly dependent vectors.  In the first pass the twisted vectors of a
+            // pathologically close pair may coincide (the refinement step separates them); after it, decline the instance
+            if (pass == 0 && !(n2 > eig3::REFINE_BELOW) && lane == 0) s.flag[2] = 1;
+            if (pass == 1 && !(n2 > 1.0e-6) && lane == 0) s.flag[1] = 1;
+            const double sc = rsqrt(n2);
+            for (int i = ma + lane; i < mb; i += 32) zm[(size_t)i * ld] *= sc;
+            __syncwarp();
+        }
+    }
+}
+
+// TILE = true (default when the tile fits twice per SM): the eigenvectors are built in a shared-memory tile, column t = thread t.
+// The pivot and vector recurrences are chains of dependent divisions that read back what they wrote a moment ago; in the global
+// scratch (TILE = false) every such read-back is an L2 round trip inside the chain (stores do not allocate in L1), which made
+// the kernel wait on memory, not on arithmetic.  From the tile, V and V^T go out once, coalesced.  An instance that needs the
+// refinement step (nearly parallel twisted vectors; the tile keeps no factors) is flagged nswp = -4 and re-done by the
+// TILE = false kernel, launched behind this one with only_flagged = 1.
+template <int NT, bool TILE>
+__global__ void __launch_bounds__(NT, TILE ? 4 : 1024 / NT)      // TILE = false: <= 64 registers, the latency chains are hidden by resident warps only
+ukf_eig3_kernel(BatchState b, UkfScratch u, const int i0, const int maxc, const int only_flagged, const int nlo, const int ncap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Eig3Smem s;
-    eig3_carve(u.n_max, NT, smem_raw, &s);
+    eig3_carve(ncap, NT, smem_raw, &s, TILE);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int inst = i0 + blockIdx.x;
     const int4 meta_in = b.meta[inst];
     if (meta_in.y & SLAM_STATUS_SAME_STEP_REMATCH) return;
+    if (only_flagged && u.nswp[inst] != -4) return;
     const int n = 4 + 2 * meta_in.x;
+    if (TILE && (n <= nlo || n > ncap)) return;    // size classes: this launch's tile holds nlo < n <= ncap (see eig3_classes)
     double* const Vg = u.Vg + (size_t)inst * u.n_max * u.n_max;       // [i][k], compact leading dimension n
     double* const Wg = u.VTg + (size_t)inst * u.n_max * u.n_max;      // work space now, V^T at the end
     const bool live = t < n;
     if (live) { s.d[t] = u.dg[(size_t)t * b.batch + inst]; s.e[t] = (t < n - 1) ? u.eg[(size_t)t * b.batch + inst] : 0.0; }
-    if (t == 0) { s.flag[0] = 0; s.flag[1] = 0; }
+    if (t == 0) { s.flag[0] = 0; s.flag[1] = 0; s.flag[2] = 0; }
     __syncthreads();
     // |T| (largest absolute row sum), then the splits (eig3.cuh, step 1)
     double rs = 0.0;
@@ -1382,8 +1447,10 @@ ukf_eig3_kernel(BatchState b, UkfScratch u, const int i0, const int maxc) {
             // multisection start: one Sturm count per thread on a uniform grid over the block's Gershgorin interval, shared below
             eig3::block_bounds(s.d, s.e, a, bb, pivmin, glo, ghi);
             const double x0 = eig3::grid_point(glo, ghi, t - a, bb - a);
+            eig3::Fval f0;
             s.lt[t] = x0;
-            s.tw[t] = eig3::sturm_count(s.de, a, bb, x0);
+            s.tw[t] = eig3::sturm_eval(s.de, a, bb, x0, &f0);
+            s.gm[t] = f0.m; s.gs[t] = f0.s;
         }
     }
     __syncthreads();
@@ -1391,8 +1458,17 @@ ukf_eig3_kernel(BatchState b, UkfScratch u, const int i0, const int maxc) {
         if (bb - a == 1) lam = s.d[a];
         else {
             double lo = glo, hi = ghi;
-            eig3::bracket_from_grid(s.lt, s.tw, a, bb, t - a, lo, hi);
+            int qlo, qhi;
+            eig3::bracket_from_grid2(s.lt, s.tw, a, bb, t - a, lo, hi, qlo, qhi);
+#ifdef EIG3_PURE_BISECTION
             lam = eig3::bisect_bracket(s.de, a, bb, t - a, lo, hi, 2.0 * eig3::EPS * tn + 2.0 * pivmin);
+#else
+            // bisection until the eigenvalue is alone in its bracket, then secant steps on p_n (eig3.cuh: root_bracket)
+            eig3::End el{lo, 0, eig3::Fval{0.0, 0}, qlo >= 0}, eh{hi, bb - a, eig3::Fval{0.0, 0}, qhi >= 0};
+            if (qlo >= 0) { el.c = s.tw[qlo]; el.f.m = s.gm[qlo]; el.f.s = s.gs[qlo]; }
+            if (qhi >= 0) { eh.c = s.tw[qhi]; eh.f.m = s.gm[qhi]; eh.f.s = s.gs[qhi]; }
+            lam = eig3::root_bracket(s.de, a, bb, t - a, el, eh, 2.0 * eig3::EPS * tn + 2.0 * pivmin, nullptr);
+#endif
         }
         s.lam[t] = lam;
     }
@@ -1414,6 +1490,46 @@ ukf_eig3_kernel(BatchState b, UkfScratch u, const int i0, const int maxc) {
     }
     const int maxrank = (int)cta_max<NT>((double)crank, s.red);
     if (s.flag[0]) { if (t == 0) u.nswp[inst] = -2; return; }
+    if constexpr (TILE) {
+        const int ldw = ncap | 1;                  // odd: rows (consecutive t) and columns (consecutive i) are both conflict free
+        const eig3::Slot zt{s.tile + t, ldw};
+        bool badt = false;
+        if (live) {
+            for (int i = 0; i < a; ++i) zt.set(i, 0.0);
+            for (int i = bb; i < n; ++i) zt.set(i, 0.0);
+            if (bb - a == 1) zt.set(a, 1.0);
+            else {
+                double n2 = 1.0;
+                eig3::twisted_vector1(s.d, s.e, s.e2, a, bb, x, pivf, zt, &n2);
+                const double sc = rsqrt(n2);
+                if (!(n2 > 0.0) || !isfinite(n2)) badt = true;
+#pragma unroll 4
+                for (int i = a; i < bb; ++i) zt.set(i, zt.get(i) * sc);
+            }
+        }
+        if (maxrank > 0) {
+            __syncthreads();
+            eig3_gram_schmidt(s, s.tile, ldw, n, warp, lane, NT / 32, 0);
+        }
+        __syncthreads();
+        if (s.flag[2] || (u.refine_all && maxrank > 0)) { if (t == 0) u.nswp[inst] = -4; return; }     // needs the refinement step: the two-array kernel re-does it
+        if (live && bb - a > 1) {
+            const double r = eig3::residual_inf(s.d, s.e, a, bb, lam, zt, 1.0);
+            if (!(r <= 1.0e-12 * tn)) badt = true;
+        }
+        if (badt) s.flag[1] = 1;
+        __syncthreads();
+        if (s.flag[1]) { if (t == 0) u.nswp[inst] = -2; return; }
+        if (live) {
+#pragma unroll 4
+            for (int i = 0; i < n; ++i) Vg[(size_t)i * n + t] = s.tile[i * ldw + t];          // V[i][k = t]
+#pragma unroll 4
+            for (int k = 0; k < n; ++k) Wg[(size_t)k * n + t] = s.tile[t * ldw + k];          // V^T[k][i = t] = V[i = t][k]
+            u.dg[(size_t)t * b.batch + inst] = lam;
+        }
+        if (t == 0) u.nswp[inst] = -3;
+        return;
+    }
     // eigenvectors: twisted factorisation, z in column t of V, factors in column t of the work space
     const eig3::Slot z{Vg + t, n}, w{Wg + t, n};
     int tw = a;
@@ -1431,10 +1547,12 @@ ukf_eig3_kernel(BatchState b, UkfScratch u, const int i0, const int maxc) {
             for (int i = a; i < bb; ++i) z.set(i, z.get(i) * sc);
         }
     }
-    // modified Gram-Schmidt inside clusters, one rank per round; then one refinement step for cluster members and again
+    // modified Gram-Schmidt inside clusters; then, ONLY IF a projection removed a sizeable part of some vector (nearly parallel
+    // twisted vectors: eig3.cuh REFINE_BELOW), one refinement step for the cluster members and Gram-Schmidt again
     for (int pass = 0; pass < 2; ++pass) {
+        if (maxrank == 0) break;
         if (pass == 1) {
-            if (maxrank == 0) break;
+            if (!s.flag[2]) break;                 // CTA-uniform: written before the barrier that ended pass 0
             const bool incl = live && bb - a > 1 && (crank > 0 || (t + 1 < bb && s.crank[t + 1] > 0));
             if (incl) {
                 const double n2 = eig3::twisted_solve(s.e, a, bb, tw, z, w);
@@ -1443,33 +1561,8 @@ ukf_eig3_kernel(BatchState b, UkfScratch u, const int i0, const int maxc) {
                 for (int i = a; i < bb; ++i) z.set(i, z.get(i) * sc);
             }
         }
-        // one rank per round; inside a round every WARP takes cluster members (lanes stride over the components: the dot
-        // products and updates of a member are 32 wide instead of a serial chain of dependent global loads in one thread)
-        for (int r = 1; r <= maxrank; ++r) {
-            __syncthreads();                       // (global memory: visible to the CTA after the barrier)
-            for (int m = warp; m < n; m += NT / 32) {
-                if (s.crank[m] != r) continue;     // warp-uniform
-                const int ma = s.b0[m], mb = s.b1[m];
-                double* zm = Vg + m;
-                for (int q = s.cfirst[m]; q < m; ++q) {
-                    const double* zq = Vg + q;
-                    double dot = 0.0;
-                    for (int i = ma + lane; i < mb; i += 32) dot += zq[(size_t)i * n] * zm[(size_t)i * n];
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-                    for (int i = ma + lane; i < mb; i += 32) zm[(size_t)i * n] -= dot * zq[(size_t)i * n];
-                }
-                double n2 = 0.0;
-                for (int i = ma + lane; i < mb; i += 32) { const double v = zm[(size_t)i * n]; n2 += v * v; }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
-                // unit vector before: a tiny remainder means nearly dependent vectors.  In the first pass the twisted vectors of a
-                // pathologically close pair may coincide (the refinement step separates them); after it, decline the instance
-                if (pass == 1 && !(n2 > 1.0e-6) && lane == 0) s.flag[1] = 1;
-                const double sc = rsqrt(n2);
-                for (int i = ma + lane; i < mb; i += 32) zm[(size_t)i * n] *= sc;
-            }
-        }
+        __syncthreads();                           // (global memory: the vectors are visible to the CTA after the barrier)
+        eig3_gram_schmidt(s, Vg, n, n, warp, lane, NT / 32, pass);
         __syncthreads();
     }
     // residual |(T - lambda I) z| against |T|
@@ -2514,8 +2607,10 @@ cudaError_t ukf_step_configure(const BatchState& b) {
         if ((e = cudaFuncSetAttribute(ukf_sigma2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 33))) != cudaSuccess) return e;
     }
     if (b.n_max <= 256) {
-        if ((e = cudaFuncSetAttribute(ukf_eig3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig3_carve(b.n_max, 128, nullptr, nullptr))) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(ukf_eig3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig3_carve(b.n_max, 256, nullptr, nullptr))) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(ukf_eig3_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig3_carve(b.n_max, 128, nullptr, nullptr))) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(ukf_eig3_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig3_carve(b.n_max, 256, nullptr, nullptr))) != cudaSuccess) return e;
+        int caps[4];
+        if (eig3_classes(b, caps) > 0 && (e = cudaFuncSetAttribute(ukf_eig3_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig3_carve(b.n_max, 128, nullptr, nullptr, true))) != cudaSuccess) return e;
     }
     return cudaFuncSetAttribute(ukf_ql_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ql_smem_bytes(b));
 }
@@ -2578,8 +2673,13 @@ cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const St
             const bool two_pass = u.narrow && full > UKF_NARROW_WLD;
             if (gen3) {
                 // parallel eigensolver + dense S-products; the instances it declines (nswp = -2) go on to the QL route below
-                if (b.n_max <= 128) ukf_eig3_kernel<128><<<i1 - i0, 128, eig3_carve(b.n_max, 128, nullptr, nullptr), sk>>>(b, u, i0, u.maxc);
-                else ukf_eig3_kernel<256><<<i1 - i0, 256, eig3_carve(b.n_max, 256, nullptr, nullptr), sk>>>(b, u, i0, u.maxc);
+                int caps[4];
+                const int ncls = u.eig3_tile ? eig3_classes(b, caps) : 0;
+                for (int c = 0; c < ncls; ++c)
+                    ukf_eig3_kernel<128, true><<<i1 - i0, 128, eig3_carve(caps[c], 128, nullptr, nullptr, true), sk>>>(b, u, i0, u.maxc, 0, c ? caps[c - 1] : 0, caps[c]);
+                if (b.n_max <= 128) ukf_eig3_kernel<128, false><<<i1 - i0, 128, eig3_carve(b.n_max, 128, nullptr, nullptr), sk>>>(b, u, i0, u.maxc, ncls ? 1 : 0, 0, b.n_max);
+                else ukf_eig3_kernel<256, false><<<i1 - i0, 256, eig3_carve(b.n_max, 256, nullptr, nullptr), sk>>>(b, u, i0, u.maxc, 0, 0, b.n_max);
+                nback += ncls;
                 if (u.multiwarp) {
                     if (b.n_max <= 128) {
                         if (two_pass || full == 13) ukf_back3_kernel<13, 4><<<i1 - i0, 96, ukf_warp_smem_bytes(b, 13), sk>>>(b, fc, in, u, i0, two_pass ? 0 : 2);

@@ -7,6 +7,9 @@
 #include <vector>
 #include <algorithm>
 #include <cmath>
+#ifdef TRACEJ
+#define EIG3_TRACE_ROOT(j) ((j) == TRACEJ)
+#endif
 #include "../live_ekf_slam_b200/csrc/eig3.cuh"
 
 using namespace slam::eig3;
@@ -29,6 +32,8 @@ int main() {
     for (int t = 0; t < n; ++t) de[t] = De{d[t], t > 0 ? e2[t - 1] : 0.0};
     std::vector<double> px(n, 0.0), glo(n, 0.0), ghi(n, 0.0);
     std::vector<int> pc(n, 0);
+    std::vector<Fval> pf(n, Fval{0.0, 0});
+    long evals = 0; int evmax = 0;
     for (int t = 0; t < n; ++t) {
         int a = t; while (a > 0 && e[a - 1] != 0.0) --a;
         int b = t + 1; while (b < n && e[b - 1] != 0.0) ++b;
@@ -36,16 +41,23 @@ int main() {
         if (b - a > 1) {                           // multisection start, as in the kernel
             block_bounds(d.data(), e.data(), a, b, pivmin, glo[t], ghi[t]);
             px[t] = grid_point(glo[t], ghi[t], t - a, b - a);
-            pc[t] = sturm_count(de.data(), a, b, px[t]);
+            pc[t] = sturm_eval(de.data(), a, b, px[t], &pf[t]);
         }
     }
     for (int t = 0; t < n; ++t) {
         const int a = b0[t], b = b1[t];
         if (b - a == 1) { lam[t] = d[a]; continue; }
         double lo = glo[t], hi = ghi[t];
-        bracket_from_grid(px.data(), pc.data(), a, b, t - a, lo, hi);
-        lam[t] = bisect_bracket(de.data(), a, b, t - a, lo, hi, 2.0 * EPS * tn + 2.0 * pivmin);
+        int qlo, qhi;
+        bracket_from_grid2(px.data(), pc.data(), a, b, t - a, lo, hi, qlo, qhi);
+        const End el{lo, qlo >= 0 ? pc[qlo] : 0, qlo >= 0 ? pf[qlo] : Fval{0.0, 0}, qlo >= 0};
+        const End eh{hi, qhi >= 0 ? pc[qhi] : b - a, qhi >= 0 ? pf[qhi] : Fval{0.0, 0}, qhi >= 0};
+        int ne = 0;
+        lam[t] = root_bracket(de.data(), a, b, t - a, el, eh, 2.0 * EPS * tn + 2.0 * pivmin, &ne);
+        evals += ne; evmax = std::max(evmax, ne);
+        if (getenv("EIG3_TRACE")) fprintf(stderr, "  t %d ne %d lam %.17g lo %.17g hi %.17g clo %d chi %d klo %d khi %d\n", t, ne, lam[t], lo, hi, el.c, eh.c, (int)el.known, (int)eh.known);
     }
+    fprintf(stderr, "evals mean %.1f max %d\n", (double)evals / n, evmax);
     int maxrank = 0;
     for (int t = 0; t < n; ++t) {
         const int a = b0[t];
@@ -71,9 +83,10 @@ int main() {
         const double sc = 1.0 / std::sqrt(n2);
         for (int i = a; i < b; ++i) z.set(i, z.get(i) * sc);
     }
+    bool refine = false;        // set by the first Gram-Schmidt pass: some vector lost more than a quarter of its norm^2
     for (int pass = 0; pass < 2; ++pass) {
         if (pass == 1) {
-            if (maxrank == 0) break;
+            if (maxrank == 0 || !refine) break;
             for (int t = 0; t < n; ++t) {
                 const int a = b0[t], b = b1[t];
                 const bool incl = b - a > 1 && (crank[t] > 0 || (t + 1 < b && crank[t + 1] > 0));
@@ -96,6 +109,7 @@ int main() {
                 }
                 double n2 = 0.0;
                 for (int i = a; i < b; ++i) n2 += z.get(i) * z.get(i);
+                if (pass == 0 && !(n2 > REFINE_BELOW)) refine = true;
                 if (pass == 1 && !(n2 > 1.0e-6)) bad = true;    // (first pass: twisted vectors of a pathologically close pair may coincide; the refinement separates them)
                 if (getenv("EIG3_DEBUG")) fprintf(stderr, "mgs pass %d t=%d n2=%g\n", pass, t, n2);
                 const double sc = 1.0 / std::sqrt(n2);
@@ -108,6 +122,7 @@ int main() {
         const double r = residual_inf(d.data(), e.data(), a, b, lam[t], Slot{V.data() + t, n}, 1.0);
         if (!(r <= 1.0e-12 * tn)) bad = true;
     }
+    fprintf(stderr, "refine %d maxrank %d\n", (int)refine, maxrank);
     if (bad) { printf("declined residual\n"); return 0; }
     printf("ok\n");
     for (int t = 0; t < n; ++t) printf("%.17g\n", lam[t]);

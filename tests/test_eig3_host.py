@@ -89,6 +89,13 @@ def test_eig3_adversarial(harness):
     Yb = np.zeros((46, 46)); Yb[:30, :30] = B @ B.T; Yb[30:, 30:] = np.eye(16) * 132.5       # eight freshly inserted landmarks
     cases["after_insertion"] = tridiag_of(Yb)
     cases["indefinite"] = tridiag_of(B @ B.T - 3.0 * np.eye(30))
+    # close pairs over the whole range between "numerically orthogonal already" and "coincident": the refinement step after
+    # the first Gram-Schmidt pass is taken only when a projection removed a sizeable part of a vector (eig3.cuh REFINE_BELOW)
+    for gap in (1e-4, 1e-6, 1e-8, 1e-10, 1e-12, 1e-14):
+        Qr, _ = np.linalg.qr(rng.normal(size=(24, 24)))
+        base = np.sort(rng.uniform(0.5, 40.0, 12))
+        ev = np.concatenate([base, base + gap * 40.0])
+        cases["pairs_gap_%g" % gap] = tridiag_of((Qr * ev) @ Qr.T)
     cases["zero_matrix"] = (np.zeros(7), np.zeros(7))
     cases["n_is_1"] = (np.array([2.5]), np.zeros(1))
     for name, (d, e) in cases.items():
