@@ -1250,19 +1250,51 @@ __device__ __forceinline__ void apply_rot_bwd(double* W, const int lane, const b
 
 // ---- launch 1 of 3 (generation 2): Y = scale * sym(P) (ukf.cpp:112-114), tridiagonalisation; P is NOT modified
 constexpr int FRONT2_THREADS = 256;      // (512 threads measured slower: 3.79 -> 4.11 ms; the Householder steps are barrier bound)
-__global__ void __launch_bounds__(FRONT2_THREADS, 2)
-ukf_front2_kernel(BatchState b, UkfScratch u, const int i0) {
+// Shared memory of the kernel, sized by a CLASS of instance sizes (ncap = largest n of the class), not by the batch's capacity:
+// the Householder steps are barrier and latency bound, so the instances with few landmarks run at 4 CTAs per SM instead of 2.
+struct Front2Smem { double *A, *d, *e, *pool, *part, *red; };
+__host__ __device__ inline size_t front2_carve(const int ncap, unsigned char* base, Front2Smem* s) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
+    const size_t oA = take(sizeof(double) * (size_t)ncap * lds_of(ncap));
+    const size_t od = take(sizeof(double) * ncap), oe = take(sizeof(double) * ncap);
+    const size_t opool = take(sizeof(double) * 4 * ncap), opart = take(sizeof(double) * (8 * ncap + 8)), ored = take(sizeof(double) * 32);
+    if (s) {
+        s->A = (double*)(base + oA); s->d = (double*)(base + od); s->e = (double*)(base + oe);
+        s->pool = (double*)(base + opool); s->part = (double*)(base + opart); s->red = (double*)(base + ored);
+    }
+    return off;
+}
+// classes for MINB = 4, 3, 2 CTAs per SM (register budget 64 / 80 / 128 per thread); caps ascending, returns the count
+inline int front2_classes(const BatchState& b, int caps[3], int minb[3]) {
+    static const int per_sm[3] = {4, 3, 2};
+    int nc = 0, prev = 0;
+    for (int k = 0; k < 3; ++k) {
+        const size_t budget = (size_t)(227 * 1024) / per_sm[k] - 1024;
+        int cap = prev;
+        while (cap < b.n_max && front2_carve(cap + 1, nullptr, nullptr) <= budget) ++cap;
+        if (k == 2) cap = b.n_max;                 // the last class takes whatever is left (one CTA per SM beyond 2 x 113 KB)
+        if (cap > prev) { caps[nc] = cap; minb[nc] = per_sm[k]; ++nc; prev = cap; }
+        if (cap >= b.n_max) break;
+    }
+    return nc;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(FRONT2_THREADS, MINB)
+ukf_front2_kernel(BatchState b, UkfScratch u, const int i0, const int nlo, const int ncap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    UkfSmem s;
-    ukf_smem_carve(b, smem_raw, &s);
+    Front2Smem s;
+    front2_carve(ncap, smem_raw, &s);
     const int tid = threadIdx.x;
     const int inst = i0 + blockIdx.x;
-    const int lds = b.lds;
+    const int lds = lds_of(ncap);
     const int ldp = b.fixed_ld;
     const int4 meta_in = b.meta[inst];
     if (meta_in.y & SLAM_STATUS_SAME_STEP_REMATCH) return;
     const int M = meta_in.x;
     const int n = 4 + 2 * M;                       // ukf.cpp:167
+    if (n <= nlo || n > ncap) return;              // another class's launch takes this instance
     const double* gP = b.P + (size_t)inst * b.p_stride;
     for (int idx = tid; idx < n * n; idx += FRONT2_THREADS) {
         const int i = idx / n, j = idx - i * n;
@@ -1286,7 +1318,7 @@ ukf_front2_kernel(BatchState b, UkfScratch u, const int i0) {
         if (i >= 4 && j >= 4) Yg[idx] = (2.0 * wgt) * s.A[(size_t)i * lds + j];   // landmark block of P_pred before corrections
     }
     __syncthreads();
-    tridiag<FRONT2_THREADS>(s.A, lds, n, s.d, s.e, s.pool, s.Xp, s.red);
+    tridiag<FRONT2_THREADS>(s.A, lds, n, s.d, s.e, s.pool, s.part, s.red);
     // reflector k (column k of A below the diagonal) -> row k of the scratch matrix, tau_k on its diagonal
     double* Rg = u.Zg + (size_t)inst * u.n_max * u.n_max;
     const double* tau = s.pool + 3 * n;
@@ -2589,7 +2621,9 @@ cudaError_t ukf_step_configure(const BatchState& b) {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(ukf_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ukf_front2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_front2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)front2_carve(b.n_max, nullptr, nullptr))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_front2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 75 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_front2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back2_kernel<13, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 13))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back2_kernel<25, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 25))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back2_kernel<33, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 33))) != cudaSuccess) return e;
@@ -2668,7 +2702,18 @@ cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const St
             const int i0 = (int)((long long)b.batch * k / nsub), i1 = (int)((long long)b.batch * (k + 1) / nsub);
             if (i1 <= i0) continue;
             cudaStream_t sk = (k == 0) ? st : xs.aux[k - 1];
-            ukf_front2_kernel<<<i1 - i0, FRONT2_THREADS, fsm, sk>>>(b, u, i0);
+            {
+                int caps[3], minb[3];
+                const int ncls = front2_classes(b, caps, minb);
+                for (int c = 0; c < ncls; ++c) {
+                    const int lo = c ? caps[c - 1] : 0;
+                    const size_t sm = front2_carve(caps[c], nullptr, nullptr);
+                    if (minb[c] == 4) ukf_front2_kernel<4><<<i1 - i0, FRONT2_THREADS, sm, sk>>>(b, u, i0, lo, caps[c]);
+                    else if (minb[c] == 3) ukf_front2_kernel<3><<<i1 - i0, FRONT2_THREADS, sm, sk>>>(b, u, i0, lo, caps[c]);
+                    else ukf_front2_kernel<2><<<i1 - i0, FRONT2_THREADS, sm, sk>>>(b, u, i0, lo, caps[c]);
+                }
+                nback += ncls - 1;
+            }
             const int full = ukf_wld(b);
             const bool two_pass = u.narrow && full > UKF_NARROW_WLD;
             if (gen3) {
