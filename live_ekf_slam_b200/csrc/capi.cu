@@ -248,6 +248,22 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
         CK(ekf_step_configure(b));
     } else if (kind != SLAM_NAIVE) CK(ukf_step_configure(b));
     *out = h;
+    // development aid: SLAM_TUNE="key=value,key=value" applies slam_tune() settings to every handle of the process, so that one
+    // binary can be A/B-measured through an unmodified caller (bench.py).  Results never depend on the keys (see slam_tune).
+    if (const char* env = getenv("SLAM_TUNE")) {
+        const char* p = env;
+        while (*p) {
+            char* end = nullptr;
+            const long key = strtol(p, &end, 10);
+            if (end == p || *end != '=') break;
+            p = end + 1;
+            const long value = strtol(p, &end, 10);
+            if (end == p) break;
+            if (slam_tune(h, (int)key, (int)value) != 0) return 1;
+            p = (*end == ',') ? end + 1 : end;
+            if (*end != ',' ) break;
+        }
+    }
     return slam_init(h, 0.f, 0.f, 0.f);
 }
 
@@ -329,7 +345,7 @@ int slam_tune(slam_handle_t h, int key, int value) {
         if (full < 256) full = 256;
         h->uk.rot_cap = (value <= 0 || value > full) ? full : value;
     } else if (key == 9) h->uk.clip_lanes = value < 0 ? 0 : value;
-    else if (key == 11) h->uk.narrow = value ? 1 : 0;
+    else if (key == 11) h->uk.narrow = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (key == 10) { if (value < 1 || value > UKF_MAX_SUB) return fail(h, "slam_tune: UKF slices must be 1..8"); h->uks.nsub = value; }
     else return fail(h, "slam_tune: unknown key");
     return 0;

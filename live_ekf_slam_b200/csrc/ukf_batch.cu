@@ -2133,8 +2133,8 @@ __device__ __forceinline__ void dense_cols(double* W, const double* __restrict__
 // the warps by update, the rows of the P_pred assembly by row.  Small scalar phases are evaluated redundantly by every warp.
 template <int wld, int NTT>      // NTT = row slots per lane: 4 (n_max <= 128) or 8 -- a template parameter so that the small case does not
                                  // carry the register allocation of the large one
-__global__ void __launch_bounds__(32 * ((wld - 1) / 4), (wld == 13) ? (NTT == 4 ? 6 : 4) : 2)
-ukf_back3_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, const int i0, const int pass) {
+__global__ void __launch_bounds__(32 * ((wld - 1) / 4), (wld == 9) ? (NTT == 4 ? 9 : 6) : (wld == 13) ? (NTT == 4 ? 6 : 4) : 2)
+ukf_back3_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, const int i0, const int stage, const int last) {
     constexpr int NW = (wld - 1) / 4, NTHR = 32 * NW;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     UkfWarpSmem s;
@@ -2152,7 +2152,7 @@ ukf_back3_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
     int status = meta_in.y;
     if (status & SLAM_STATUS_SAME_STEP_REMATCH) return;
     if (u.nswp[inst] != -3) return;                // only instances the parallel eigensolver solved (explicit V in the scratch)
-    if (pass == 1 && !u.defer[inst]) return;       // full-width pass: only the instances the narrow pass handed over
+    if (stage > 0 && u.defer[inst] != stage) return;       // a wider pass: only the instances the pass before handed over
     int M = meta_in.x;
     const int M_start = M;
     const int n = 4 + 2 * M;                       // ukf.cpp:167
@@ -2215,9 +2215,10 @@ ukf_back3_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
     const float yaw_prior = yaw_of(s.x[2], s.x[3]);                        // :182 and :139 (prior x_t)
     const double cy = (double)cos_f(yaw_prior), sy = (double)sin_f(yaw_prior);
 
-    if (pass == 0) {                                // narrow tile: hand the instance over if its updates do not fit
-        const bool over = 4 + 2 * nu > wcols;
-        if (tid == 0) u.defer[inst] = over ? 1 : 0;
+    if (!last) {                                    // narrow tile: hand the instance over if its updates do not fit (the narrowest
+                                                    // tile also when the clipped eigenvectors would not ride beside them)
+        const bool over = 4 + 2 * nu + (stage == 0 && wld < 13 ? nclip : 0) > wcols;
+        if (tid == 0) u.defer[inst] = over ? stage + 1 : 0;
         if (over) return;
     }
     const int nvec = 4 + 2 * nu;                    // columns of the two S-passes
@@ -2633,6 +2634,8 @@ cudaError_t ukf_step_configure(const BatchState& b) {
     if ((e = cudaFuncSetAttribute(ukf_back3_kernel<13, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 13))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back3_kernel<25, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 25))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back3_kernel<33, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 33))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back3_kernel<9, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 9))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ukf_back3_kernel<9, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 9))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back3_kernel<13, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 13))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back3_kernel<25, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 25))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back3_kernel<33, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 33))) != cudaSuccess) return e;
@@ -2726,15 +2729,35 @@ cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const St
                 else ukf_eig3_kernel<256, false><<<i1 - i0, 256, eig3_carve(b.n_max, 256, nullptr, nullptr), sk>>>(b, u, i0, u.maxc, 0, 0, b.n_max);
                 nback += ncls;
                 if (u.multiwarp) {
+                    // tiles of 8, 12 and `full` - 1 vector columns (2, 3, (full - 1) / 4 warps): an instance runs in the narrowest
+                    // one that holds its 4 + 2 k columns, the others see it only in the hand-over word
+                    const size_t sm9 = ukf_warp_smem_bytes(b, 9), sm13 = ukf_warp_smem_bytes(b, 13);
                     if (b.n_max <= 128) {
-                        if (two_pass || full == 13) ukf_back3_kernel<13, 4><<<i1 - i0, 96, ukf_warp_smem_bytes(b, 13), sk>>>(b, fc, in, u, i0, two_pass ? 0 : 2);
-                        if (full == 25) ukf_back3_kernel<25, 4><<<i1 - i0, 192, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
-                        else if (full == 33) ukf_back3_kernel<33, 4><<<i1 - i0, 256, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
+                        if (u.narrow) {
+                            const int s13 = u.narrow >= 2 ? 1 : 0;
+                            if (s13) ukf_back3_kernel<9, 4><<<i1 - i0, 64, sm9, sk>>>(b, fc, in, u, i0, 0, 0);
+                            ukf_back3_kernel<13, 4><<<i1 - i0, 96, sm13, sk>>>(b, fc, in, u, i0, s13, full == 13 ? 1 : 0);
+                            if (full == 25) ukf_back3_kernel<25, 4><<<i1 - i0, 192, wsm, sk>>>(b, fc, in, u, i0, s13 + 1, 1);
+                            else if (full == 33) ukf_back3_kernel<33, 4><<<i1 - i0, 256, wsm, sk>>>(b, fc, in, u, i0, s13 + 1, 1);
+                        } else {
+                            if (full == 13) ukf_back3_kernel<13, 4><<<i1 - i0, 96, sm13, sk>>>(b, fc, in, u, i0, 0, 1);
+                            else if (full == 25) ukf_back3_kernel<25, 4><<<i1 - i0, 192, wsm, sk>>>(b, fc, in, u, i0, 0, 1);
+                            else ukf_back3_kernel<33, 4><<<i1 - i0, 256, wsm, sk>>>(b, fc, in, u, i0, 0, 1);
+                        }
                     } else {
-                        if (two_pass || full == 13) ukf_back3_kernel<13, 8><<<i1 - i0, 96, ukf_warp_smem_bytes(b, 13), sk>>>(b, fc, in, u, i0, two_pass ? 0 : 2);
-                        if (full == 25) ukf_back3_kernel<25, 8><<<i1 - i0, 192, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
-                        else if (full == 33) ukf_back3_kernel<33, 8><<<i1 - i0, 256, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
+                        if (u.narrow) {
+                            const int s13 = u.narrow >= 2 ? 1 : 0;
+                            if (s13) ukf_back3_kernel<9, 8><<<i1 - i0, 64, sm9, sk>>>(b, fc, in, u, i0, 0, 0);
+                            ukf_back3_kernel<13, 8><<<i1 - i0, 96, sm13, sk>>>(b, fc, in, u, i0, s13, full == 13 ? 1 : 0);
+                            if (full == 25) ukf_back3_kernel<25, 8><<<i1 - i0, 192, wsm, sk>>>(b, fc, in, u, i0, s13 + 1, 1);
+                            else if (full == 33) ukf_back3_kernel<33, 8><<<i1 - i0, 256, wsm, sk>>>(b, fc, in, u, i0, s13 + 1, 1);
+                        } else {
+                            if (full == 13) ukf_back3_kernel<13, 8><<<i1 - i0, 96, sm13, sk>>>(b, fc, in, u, i0, 0, 1);
+                            else if (full == 25) ukf_back3_kernel<25, 8><<<i1 - i0, 192, wsm, sk>>>(b, fc, in, u, i0, 0, 1);
+                            else ukf_back3_kernel<33, 8><<<i1 - i0, 256, wsm, sk>>>(b, fc, in, u, i0, 0, 1);
+                        }
                     }
+                    nback += u.narrow >= 2 ? 1 : 0;
                 } else {
                     if (two_pass || full == 13) ukf_back2_kernel<13, true><<<i1 - i0, 32, ukf_warp_smem_bytes(b, 13), sk>>>(b, fc, in, u, i0, two_pass ? 0 : 2);
                     if (full == 25) ukf_back2_kernel<25, true><<<i1 - i0, 32, wsm, sk>>>(b, fc, in, u, i0, two_pass ? 1 : 2);
