@@ -301,7 +301,7 @@ def measure_batch(cx: Ctx, filt: str, B: int, T: int, K: int, W: int, warm_T: in
         fb.tune(3, 0)
         loc = fb.stats()
     n_upd = max(loc[0], 1)
-    step_roof = {"kernel": "ekf_step_kernel" if filt == "ekf" else "ukf step (ukf_front2_kernel + ukf_ql_kernel + ukf_back2_kernel)",
+    step_roof = {"kernel": "ekf_step_kernel" if filt == "ekf" else "ukf step (ukf_front2_kernel + ukf_eig3_kernel + ukf_back3_kernel; the size-class and hand-over launches of each included)",
                  "kernel_ms_per_launch": k_ms / max(k_n, 1), "launches_timed": int(k_n),
                  "mean_n": loc[10] / n_upd, "mean_k": loc[11] / n_upd,
                  "algorithmic_bytes_per_launch": loc[8] / max(k_n, 1), "moved_bytes_per_launch_model": loc[12] / max(k_n, 1),

@@ -2532,11 +2532,12 @@ ukf_back3_kernel(BatchState b, FilterConst fc, StepInputs in, UkfScratch u, cons
         st[10] += nd;
         st[11] += (double)nm;
         // bytes the three launches really move for the instance: P in (front) and out (back), reflectors + seed out and in, V and
-        // V^T out (eigensolver, with its work space) and in twice each (two S-passes)
-        st[12] += 8.0 * nd * nd * (6.0 + 2.0 + 4.0 + 4.0);
-        // flops they execute: tridiagonalisation 4/3 n^3, eigensolver ~55 Sturm sweeps of 3 n per eigenvalue + ~40 n per vector,
+        // V^T out (eigensolver; its work space is the shared-memory tile) and in twice each (two S-passes)
+        st[12] += 8.0 * nd * nd * (6.0 + 2.0 + 2.0 + 4.0);
+        // flops they execute: tridiagonalisation 4/3 n^3, eigensolver ~15 Sturm sweeps of 3 n per eigenvalue (grid + bisection until
+        // isolated + secant steps) + ~40 n per vector,
         // per vector of the two S-passes 4 n^2 (V^T, V) + 4 n^2 (Q^T, Q through the reflectors), P_pred assembly
-        st[13] += 4.0 / 3.0 * nd * nd * nd + nd * nd * (165.0 + 40.0) + (double)(2 * nvec + ncf) * 8.0 * nd * nd
+        st[13] += 4.0 / 3.0 * nd * nd * nd + nd * nd * (45.0 + 40.0) + (double)(2 * nvec + ncf) * 8.0 * nd * nd
                   + nd * nd * (2.0 + 8.0 * nu + 2.0 * ncf);
     }
 }
