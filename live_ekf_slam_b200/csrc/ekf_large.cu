@@ -64,12 +64,14 @@ constexpr int LM_THREADS = 256;
 constexpr int LM_WARPS = LM_THREADS / 32;
 constexpr int LM_SPAN = 32;      // state indices owned by a CTA per pass (one per lane); the warps split the q range
 constexpr int LM_QMAX = 256;     // max updates per step held in the coefficient tables
+constexpr int LM_PF = 10;        // q-iterations per warp whose operands are fetched ahead of the tables (7 warps: covers 70 updates per step)
 
 __device__ __forceinline__ void grid_sync(unsigned* counter, const unsigned nblocks, unsigned& gen) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
+        // arrive: a release reduction (no return value, so the poll below starts at once; cumulative with the bar.sync above,
+        // which ordered the CTA's stores before it)
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(counter) : "memory");
         const unsigned target = (++gen) * nblocks;
         unsigned v;
         do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while (v < target);
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(LM_THREADS) lm_front(LargeState L, FilterConst
     __shared__ double s_sc[16];           // H[10], nu[2], cb, sb / x_detected, y_detected
     __shared__ double s_Sinv[4];
     __shared__ double s_part[4][LM_WARPS][LM_SPAN];       // per-warp partial sums of the low-rank corrections
-    __shared__ int s_min;
+    __shared__ int s_min[2];          // vote result, double buffered: measurement l + 1's word is reset while l's is in use
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ld = L.ld;
     const size_t ustride = (size_t)L.n_max * 2, gstride = (size_t)2 * ld;
@@ -93,41 +95,49 @@ __global__ void __launch_bounds__(LM_THREADS) lm_front(LargeState L, FilterConst
     // replicated bookkeeping: every thread of every CTA tracks the same (m, M, status)
     const int M_start = L.cur[3];
     int m = 0, M = M_start, status = L.cur[2];
+    if (tid == 0) s_min[0] = INT_MAX;
+    __syncthreads();
 
     for (int l = 0; l < n_meas; ++l) {
         const float r = meas[3 * l + 1], bb = meas[3 * l + 2];
-        // -------- association vote (:79-109): first match in ascending slot order = global min
-        if (tid == 0) {
-            s_min = INT_MAX;
-            if (!fc.id_known) {
-                double sa, ca;
-                sincos(__ldcg(L.xp + 2) + (double)bb, &sa, &ca);
-                s_sc[12] = (double)(float)(__ldcg(L.xp + 0) + (double)r * ca);   // float x_detected, :87
-                s_sc[13] = (double)(float)(__ldcg(L.xp + 1) + (double)r * sa);   // float y_detected, :88
-            }
-        }
-        __syncthreads();
-        // every CTA scans all M landmarks itself (16 KB of L2-resident state): the vote needs no grid barrier
+        // -------- association vote (:79-109): first match in ascending slot order = global min.
+        // Every CTA scans all M landmarks itself (16 KB of L2-resident state): the vote needs no grid barrier.  Every THREAD
+        // derives the detected position from its own loads of the running vehicle estimate, so those loads and the landmark
+        // loads are one L2 round trip; a thread that sees a match fetches that landmark's stale x_t (what H is built from) at
+        // once, so the winner can publish H without another round trip.
+        const double xv0 = __ldcg(L.xp + 0), xv1 = __ldcg(L.xp + 1), xv2 = __ldcg(L.xp + 2);
+        if (tid == 0) s_min[(l + 1) & 1] = INT_MAX;
         int cand = INT_MAX;
+        double lxs = 0.0, lys = 0.0;
         if (!fc.id_known) {
-            const double xd = s_sc[12], yd = s_sc[13];
+            double sa, ca;
+            sincos(xv2 + (double)bb, &sa, &ca);
+            const double xd = (double)(float)(xv0 + (double)r * ca);   // float x_detected, :87
+            const double yd = (double)(float)(xv1 + (double)r * sa);   // float y_detected, :88
 #pragma unroll 4
             for (int j = tid; j < M; j += LM_THREADS) {            // no early exit: the loads of all candidates stay in flight
                 const double lx = __ldcg(L.xp + 3 + 2 * j), ly = __ldcg(L.xp + 4 + 2 * j);
                 const float x_diff = (float)fabs(xd - lx);                                 // :91
                 const float y_diff = (float)fabs(yd - ly);                                 // :92
-                if (x_diff < fc.min_sep && y_diff < fc.min_sep && j < cand) cand = j;      // ascending j: the first match stays
+                if (x_diff < fc.min_sep && y_diff < fc.min_sep && j < cand) {              // ascending j: the first match stays
+                    cand = j;
+                    if (j < M_start) { lxs = L.x[2 * j + 3]; lys = L.x[2 * j + 4]; }
+                }
             }
         } else {
             const int want = (int)meas[3 * l];
 #pragma unroll 4
             for (int j = tid; j < M; j += LM_THREADS)
-                if (__ldcg(L.ids + j) == want && j < cand) cand = j;                       // :101-108
+                if (__ldcg(L.ids + j) == want && j < cand) {                               // :101-108
+                    cand = j;
+                    if (j < M_start) { lxs = L.x[2 * j + 3]; lys = L.x[2 * j + 4]; }
+                }
         }
+        const int mine = cand;
         cand = __reduce_min_sync(0xffffffffu, cand);
-        if ((tid & 31) == 0 && cand != INT_MAX) atomicMin(&s_min, cand);
+        if ((tid & 31) == 0 && cand != INT_MAX) atomicMin(&s_min[l & 1], cand);
         __syncthreads();
-        const int slot = s_min;
+        const int slot = s_min[l & 1];
         int kind = 0;
         if (status & SLAM_STATUS_SAME_STEP_REMATCH) kind = 0;                  // dead for the rest of the step
         else if (slot != INT_MAX) {
@@ -143,60 +153,112 @@ __global__ void __launch_bounds__(LM_THREADS) lm_front(LargeState L, FilterConst
         if (kind == 1) {
             // -------- deferred landmark update (:110-140)
             const int hc[5] = {0, 1, 2, slot * 2 + 3, slot * 2 + 4};
-            if (tid == 0) {
-                // landmark from the stale x_t, vehicle from the running x_pred (:115-131)
-                const int i = slot * 2 + 3;
-                const double xv0 = __ldcg(L.xp + 0), xv1 = __ldcg(L.xp + 1), xv2 = __ldcg(L.xp + 2);
-                const double dx = L.x[i] - xv0, dy = L.x[i + 1] - xv1;
+            if (mine == slot) {
+                // the winner of the vote: landmark from the stale x_t, vehicle from the running x_pred (:115-131)
+                const double dx = lxs - xv0, dy = lys - xv1;
                 const float dist = (float)sqrt(dx * dx + dy * dy);
                 const double dd = (double)dist, d2 = (double)(dist * dist);
                 s_sc[0] = -(dx) / dd; s_sc[1] = -(dy) / dd; s_sc[2] = 0.0; s_sc[3] = dx / dd; s_sc[4] = dy / dd;
                 s_sc[5] = dy / d2; s_sc[6] = -(dx) / d2; s_sc[7] = -1.0; s_sc[8] = -(dy) / d2; s_sc[9] = dx / d2;
-                (void)xv2;
+                s_sc[14] = lxs; s_sc[15] = lys;
             }
-            __syncthreads();
+            // Everything the rest of this measurement reads from memory depends on the slot only -- not on H, not on S -- and is
+            // fetched NOW, into one register array with two layouts, so that the loads fly under the winner's H arithmetic:
+            //   warps 1..7: operands of this CTA's slice of the rank-2 pass, LM_PF q-iterations x (G_q[0][idx], G_q[1][idx], U_q[idx]);
+            //   warp 0:     operands of the coefficient tables and of S, two q-iterations x (K_q[hc], G_q[.][hc]).
+            // A longer update list (m > 7 LM_PF resp. 64) loads the rest in place.
+            const int idx0 = blockIdx.x * LM_SPAN + lane;
+            constexpr int LM_RW = LM_WARPS - 1;                                 // warps that share the q range of the rank-2 pass
+            double pf[4 * LM_PF];
+            double pf_p[5], pv[5], xp0 = 0.0;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) { pf_p[c] = 0.0; pv[c] = 0.0; }
+            if (warp == 0) {
+                if (idx0 < n) {
+                    xp0 = __ldcg(L.xp + idx0);
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) pf_p[c] = __ldcg(L.P + (size_t)hc[c] * ld + idx0);        // column idx of H P_0
+                }
+                if (lane < 5) {
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) pv[c] = __ldcg(L.P + (size_t)hc[c] * ld + hc[lane]);
+                }
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int q = lane + 32 * t;
+                    if (q < m) {
+                        const double* Uq = L.U + q * ustride;          // holds -K_q
+                        const double* Gq = L.G + q * gstride;
+#pragma unroll
+                        for (int c = 0; c < 5; ++c) {
+                            pf[20 * t + c] = -__ldcg(Uq + 2 * hc[c]); pf[20 * t + 5 + c] = -__ldcg(Uq + 2 * hc[c] + 1);
+                            pf[20 * t + 10 + c] = __ldcg(Gq + hc[c]); pf[20 * t + 15 + c] = __ldcg(Gq + ld + hc[c]);
+                        }
+                    }
+                }
+            } else if (idx0 < n) {
+                if (warp == 1) {
+                    const double* row = L.P + (size_t)idx0 * ld;                                          // row idx of P_0 H^T
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) pf_p[c] = __ldcg(row + hc[c]);
+                }
+#pragma unroll
+                for (int t = 0; t < LM_PF; ++t) {
+                    const int q = (warp - 1) + t * LM_RW;
+                    if (q < m) {
+                        const double* Gq = L.G + q * gstride;
+                        pf[4 * t] = __ldcg(Gq + idx0); pf[4 * t + 1] = __ldcg(Gq + ld + idx0);
+                        const double2 u = __ldcg(reinterpret_cast<const double2*>(L.U + q * ustride + 2 * (size_t)idx0));   // -K_q[i]
+                        pf[4 * t + 2] = u.x; pf[4 * t + 3] = u.y;
+                    }
+                }
+            }
+            __syncthreads();                                                   // H visible
             double H[10];
 #pragma unroll
             for (int q = 0; q < 10; ++q) H[q] = s_sc[q];
-            // coefficient tables for the earlier updates of this step
-            for (int q = tid; q < m; q += LM_THREADS) {
-                const double* Uq = L.U + q * ustride;          // holds -K_q
-                const double* Gq = L.G + q * gstride;
-                double c00 = 0, c01 = 0, c10 = 0, c11 = 0, e00 = 0, e01 = 0, e10 = 0, e11 = 0;
-#pragma unroll
-                for (int c = 0; c < 5; ++c) {
-                    const double k0 = -__ldcg(Uq + 2 * hc[c]), k1 = -__ldcg(Uq + 2 * hc[c] + 1);
-                    c00 += H[c] * k0; c01 += H[c] * k1; c10 += H[5 + c] * k0; c11 += H[5 + c] * k1;
-                    const double g0 = __ldcg(Gq + hc[c]), g1 = __ldcg(Gq + ld + hc[c]);
-                    e00 += g0 * H[c]; e01 += g0 * H[5 + c]; e10 += g1 * H[c]; e11 += g1 * H[5 + c];
-                }
-                s_cq[q][0] = c00; s_cq[q][1] = c01; s_cq[q][2] = c10; s_cq[q][3] = c11;
-                s_eq[q][0] = e00; s_eq[q][1] = e01; s_eq[q][2] = e10; s_eq[q][3] = e11;
-            }
-            __syncthreads();
-            // S = (H P_m)[.,hc] H^T + W (:133), evaluated redundantly per CTA; S^-1 by partial-pivot LU (:135)
             if (warp == 0) {
-                // columns hc[0..4] of H P_m: lanes split the q range, lane cc < 5 adds the P_0 part of column hc[cc]
+                // coefficient tables for the earlier updates of this step and, from the same operands, the columns hc[0..4] of
+                // H P_m: lanes split the q range, lane cc < 5 adds the P_0 part of column hc[cc]
                 double g0[5], g1[5];
 #pragma unroll
                 for (int cc = 0; cc < 5; ++cc) { g0[cc] = 0.0; g1[cc] = 0.0; }
-#pragma unroll 2
-                for (int q = lane; q < m; q += 32) {
-                    const double* Gq = L.G + q * gstride;
+                auto table_row = [&](const int q, const double* k0, const double* k1, const double* ga, const double* gb) {
+                    double c00 = 0, c01 = 0, c10 = 0, c11 = 0, e00 = 0, e01 = 0, e10 = 0, e11 = 0;
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) {
+                        c00 += H[c] * k0[c]; c01 += H[c] * k1[c]; c10 += H[5 + c] * k0[c]; c11 += H[5 + c] * k1[c];
+                        e00 += ga[c] * H[c]; e01 += ga[c] * H[5 + c]; e10 += gb[c] * H[c]; e11 += gb[c] * H[5 + c];
+                    }
+                    s_cq[q][0] = c00; s_cq[q][1] = c01; s_cq[q][2] = c10; s_cq[q][3] = c11;
+                    s_eq[q][0] = e00; s_eq[q][1] = e01; s_eq[q][2] = e10; s_eq[q][3] = e11;
 #pragma unroll
                     for (int cc = 0; cc < 5; ++cc) {
-                        const double a0 = __ldcg(Gq + hc[cc]), a1 = __ldcg(Gq + ld + hc[cc]);
-                        g0[cc] -= s_cq[q][0] * a0 + s_cq[q][1] * a1;
-                        g1[cc] -= s_cq[q][2] * a0 + s_cq[q][3] * a1;
+                        g0[cc] -= c00 * ga[cc] + c01 * gb[cc];
+                        g1[cc] -= c10 * ga[cc] + c11 * gb[cc];
                     }
+                };
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int q = lane + 32 * t;
+                    if (q < m) table_row(q, pf + 20 * t, pf + 20 * t + 5, pf + 20 * t + 10, pf + 20 * t + 15);
+                }
+                for (int q = lane + 64; q < m; q += 32) {       // (beyond 64 updates in a step: operands loaded in place)
+                    const double* Uq = L.U + q * ustride;
+                    const double* Gq = L.G + q * gstride;
+                    double k0[5], k1[5], ga[5], gb[5];
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) {
+                        k0[c] = -__ldcg(Uq + 2 * hc[c]); k1[c] = -__ldcg(Uq + 2 * hc[c] + 1);
+                        ga[c] = __ldcg(Gq + hc[c]); gb[c] = __ldcg(Gq + ld + hc[c]);
+                    }
+                    table_row(q, k0, k1, ga, gb);
                 }
 #pragma unroll
                 for (int cc = 0; cc < 5; ++cc) {
                     if (lane == cc) {
-                        for (int c = 0; c < 5; ++c) {
-                            const double pv = __ldcg(L.P + (size_t)hc[c] * ld + hc[cc]);
-                            g0[cc] += H[c] * pv; g1[cc] += H[5 + c] * pv;
-                        }
+#pragma unroll
+                        for (int c = 0; c < 5; ++c) { g0[cc] += H[c] * pv[c]; g1[cc] += H[5 + c] * pv[c]; }
                     }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
@@ -219,9 +281,7 @@ __global__ void __launch_bounds__(LM_THREADS) lm_front(LargeState L, FilterConst
                 }
             } else if (tid == 32) {
                 // innovation (:129-131), off the critical path: the atan2 / remainder chain runs while warp 0 builds S
-                const int i = slot * 2 + 3;
-                const double xv0 = __ldcg(L.xp + 0), xv1 = __ldcg(L.xp + 1), xv2 = __ldcg(L.xp + 2);
-                const double dx = L.x[i] - xv0, dy = L.x[i + 1] - xv1;
+                const double dx = s_sc[14] - xv0, dy = s_sc[15] - xv1;
                 const float dist = (float)sqrt(dx * dx + dy * dy);
                 const float ang = (float)remainder(atan2(dy, dx) - xv2, TWO_PI_REF);
                 s_sc[10] = (double)(r - dist - fc.w_r);
@@ -230,28 +290,44 @@ __global__ void __launch_bounds__(LM_THREADS) lm_front(LargeState L, FilterConst
             __syncthreads();
             for (int base = blockIdx.x * LM_SPAN; base < n; base += gridDim.x * LM_SPAN) {
                 const int idx = base + lane;                   // this lane's row i and column j
+                const bool first = base == (int)(blockIdx.x * LM_SPAN);
                 double g0 = 0, g1 = 0, a0 = 0, a1 = 0;
                 if (idx < n) {
                     if (warp == 0) {
 #pragma unroll
                         for (int c = 0; c < 5; ++c) {          // column idx of H P_0
-                            const double pv = __ldcg(L.P + (size_t)hc[c] * ld + idx);
-                            g0 += H[c] * pv; g1 += H[5 + c] * pv;
+                            const double pvv = first ? pf_p[c] : __ldcg(L.P + (size_t)hc[c] * ld + idx);
+                            g0 += H[c] * pvv; g1 += H[5 + c] * pvv;
                         }
-                    } else if (warp == 1) {
-                        const double* row = L.P + (size_t)idx * ld;    // row idx of P_0 H^T
+                        if (!first) xp0 = __ldcg(L.xp + idx);
+                    } else {
+                        if (warp == 1) {
+                            const double* row = L.P + (size_t)idx * ld;    // row idx of P_0 H^T
 #pragma unroll
-                        for (int c = 0; c < 5; ++c) { const double pv = __ldcg(row + hc[c]); a0 += pv * H[c]; a1 += pv * H[5 + c]; }
-                    }
+                            for (int c = 0; c < 5; ++c) { const double pvv = first ? pf_p[c] : __ldcg(row + hc[c]); a0 += pvv * H[c]; a1 += pvv * H[5 + c]; }
+                        }
+                        if (first) {
+#pragma unroll
+                            for (int t = 0; t < LM_PF; ++t) {       // low-rank corrections from the prefetched operands
+                                const int q = (warp - 1) + t * LM_RW;
+                                if (q < m) {
+                                    g0 -= s_cq[q][0] * pf[4 * t] + s_cq[q][1] * pf[4 * t + 1];
+                                    g1 -= s_cq[q][2] * pf[4 * t] + s_cq[q][3] * pf[4 * t + 1];
+                                    a0 += pf[4 * t + 2] * s_eq[q][0] + pf[4 * t + 3] * s_eq[q][2];
+                                    a1 += pf[4 * t + 2] * s_eq[q][1] + pf[4 * t + 3] * s_eq[q][3];
+                                }
+                            }
+                        }
 #pragma unroll 4
-                    for (int q = warp; q < m; q += LM_WARPS) {  // low-rank corrections, q range split over the warps
-                        const double* Gq = L.G + q * gstride;
-                        const double ga = __ldcg(Gq + idx), gb = __ldcg(Gq + ld + idx);
-                        g0 -= s_cq[q][0] * ga + s_cq[q][1] * gb;
-                        g1 -= s_cq[q][2] * ga + s_cq[q][3] * gb;
-                        const double2 u = __ldcg(reinterpret_cast<const double2*>(L.U + q * ustride + 2 * (size_t)idx));   // -K_q[i]
-                        a0 += u.x * s_eq[q][0] + u.y * s_eq[q][2];
-                        a1 += u.x * s_eq[q][1] + u.y * s_eq[q][3];
+                        for (int q = (warp - 1) + (first ? LM_PF * LM_RW : 0); q < m; q += LM_RW) {  // (the rest,) q range split over warps 1..7
+                            const double* Gq = L.G + q * gstride;
+                            const double ga = __ldcg(Gq + idx), gb = __ldcg(Gq + ld + idx);
+                            g0 -= s_cq[q][0] * ga + s_cq[q][1] * gb;
+                            g1 -= s_cq[q][2] * ga + s_cq[q][3] * gb;
+                            const double2 u = __ldcg(reinterpret_cast<const double2*>(L.U + q * ustride + 2 * (size_t)idx));   // -K_q[i]
+                            a0 += u.x * s_eq[q][0] + u.y * s_eq[q][2];
+                            a1 += u.x * s_eq[q][1] + u.y * s_eq[q][3];
+                        }
                     }
                 }
                 s_part[0][warp][lane] = g0; s_part[1][warp][lane] = g1; s_part[2][warp][lane] = a0; s_part[3][warp][lane] = a1;
@@ -267,11 +343,11 @@ __global__ void __launch_bounds__(LM_THREADS) lm_front(LargeState L, FilterConst
                     const double k0 = a0 * s_Sinv[0] + a1 * s_Sinv[2];
                     const double k1 = a0 * s_Sinv[1] + a1 * s_Sinv[3];
                     *reinterpret_cast<double2*>(L.U + m * ustride + 2 * (size_t)idx) = make_double2(-k0, -k1);
-                    double xv = __ldcg(L.xp + idx) + (k0 * s_sc[10] + k1 * s_sc[11]);   // :138
+                    double xv = xp0 + (k0 * s_sc[10] + k1 * s_sc[11]);                  // :138
                     if (idx == 2) xv = remainder(xv, TWO_PI_REF);                       // :139
                     L.xp[idx] = xv;
                 }
-                __syncthreads();
+                if (base + (int)(gridDim.x * LM_SPAN) < n) __syncthreads();            // (s_part is reused by the next pass)
             }
             m += 1;
         } else if (kind == 2) {
