@@ -64,6 +64,7 @@ constexpr int LM_THREADS = 256;
 constexpr int LM_WARPS = LM_THREADS / 32;
 constexpr int LM_SPAN = 32;      // state indices owned by a CTA per pass (one per lane); the warps split the q range
 constexpr int LM_QMAX = 256;     // max updates per step held in the coefficient tables
+constexpr int LM_VPF = 8;        // landmark estimates per thread fetched ahead of the vote's sincos (covers 2048 landmarks)
 constexpr int LM_PF = 10;        // q-iterations per warp whose operands are fetched ahead of the tables (7 warps: covers 70 updates per step)
 
 __device__ __forceinline__ void grid_sync(unsigned* counter, const unsigned nblocks, unsigned& gen) {
@@ -110,16 +111,36 @@ __global__ void __launch_bounds__(LM_THREADS) lm_front(LargeState L, FilterConst
         int cand = INT_MAX;
         double lxs = 0.0, lys = 0.0;
         if (!fc.id_known) {
+            // the landmark estimates first (LM_VPF per thread in registers: M <= 256 LM_VPF), THEN the sincos that waits for xv2:
+            // one round trip for both
+            double plx[LM_VPF], ply[LM_VPF];
+#pragma unroll
+            for (int t = 0; t < LM_VPF; ++t) {
+                const int j = tid + t * LM_THREADS;
+                if (j < M) { plx[t] = __ldcg(L.xp + 3 + 2 * j); ply[t] = __ldcg(L.xp + 4 + 2 * j); }
+            }
             double sa, ca;
             sincos(xv2 + (double)bb, &sa, &ca);
             const double xd = (double)(float)(xv0 + (double)r * ca);   // float x_detected, :87
             const double yd = (double)(float)(xv1 + (double)r * sa);   // float y_detected, :88
+#pragma unroll
+            for (int t = 0; t < LM_VPF; ++t) {                      // ascending j: the first match stays
+                const int j = tid + t * LM_THREADS;
+                if (j < M) {
+                    const float x_diff = (float)fabs(xd - plx[t]);                             // :91
+                    const float y_diff = (float)fabs(yd - ply[t]);                             // :92
+                    if (x_diff < fc.min_sep && y_diff < fc.min_sep && j < cand) {
+                        cand = j;
+                        if (j < M_start) { lxs = L.x[2 * j + 3]; lys = L.x[2 * j + 4]; }
+                    }
+                }
+            }
 #pragma unroll 4
-            for (int j = tid; j < M; j += LM_THREADS) {            // no early exit: the loads of all candidates stay in flight
+            for (int j = tid + LM_VPF * LM_THREADS; j < M; j += LM_THREADS) {   // (larger maps) no early exit: the loads stay in flight
                 const double lx = __ldcg(L.xp + 3 + 2 * j), ly = __ldcg(L.xp + 4 + 2 * j);
                 const float x_diff = (float)fabs(xd - lx);                                 // :91
                 const float y_diff = (float)fabs(yd - ly);                                 // :92
-                if (x_diff < fc.min_sep && y_diff < fc.min_sep && j < cand) {              // ascending j: the first match stays
+                if (x_diff < fc.min_sep && y_diff < fc.min_sep && j < cand) {
                     cand = j;
                     if (j < M_start) { lxs = L.x[2 * j + 3]; lys = L.x[2 * j + 4]; }
                 }
