@@ -14,26 +14,31 @@ tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
 cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
-lines, cur, infn = [], None, False
+sections, cur, name = collections.OrderedDict(), None, None      # one entry per .text section (template instantiation) that matches
 for ln in dis:
     m = re.match(r"\s*\.text\.(\S+):", ln)
     if m:
-        infn = kern in m.group(1)
+        name = m.group(1) if kern in m.group(1) else None
+        if name:
+            sections[name] = []
         continue
-    if not infn:
+    if not name:
         continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m:
         cur = (os.path.basename(m.group(1)), int(m.group(2)))
         continue
     if re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+\S", ln):
-        lines.append(cur)
+        sections[name].append(cur)
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 h = rows[1]; data = rows[2:]
 iS, iSrc = h.index("# Samples"), h.index("Source")
-if len(lines) != len(data):
-    print(f"warning: {len(lines)} disassembled instructions vs {len(data)} profiled", file=sys.stderr)
+# the instantiation that was profiled: the section with the same number of instructions
+lines = next((v for v in sections.values() if len(v) == len(data)), None)
+if lines is None:
+    lines = max(sections.values(), key=len) if sections else []
+    print(f"warning: no section with {len(data)} instructions among {[len(v) for v in sections.values()]}", file=sys.stderr)
 agg = collections.Counter()
 tot = 0
 for k, r in enumerate(data):
