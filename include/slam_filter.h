@@ -234,7 +234,7 @@ int  slam_get_ukf_routes(slam_handle_t h, long long* out /* 3 */);
  * eigensolver builds its eigenvectors in the global scratch instead of a shared-memory tile; key 16: 1 = (test knob) the tile
  * kernel hands every instance with a cluster of close eigenvalues to the global-scratch kernel, as if it needed the refinement step; key 8: capacity of the UKF rotation log
  * (shrinking it forces the rescue pass); key 9: max clipped eigenvectors riding beside the first S-pass; key 10: slices of the UKF batch that run their
- * front -> QL -> back chains on separate streams (1..8); key 11: narrow-tile passes of the UKF back kernel before the full-width
+ * chains of launches on separate streams (1..8; 0 = automatic, the default: 2 for generation 3 from 2048 instances, else 1); key 11: narrow-tile passes of the UKF back kernel before the full-width
  * one: 1 (default) = a 12-column pass, 2 = an 8-column pass before it (measured 1 % slower on BASELINE configs[2]), 0 = none.  The environment variable
  * SLAM_TUNE="key=value,..." applies the same settings to every handle the process creates (a measuring aid).
  * Results never depend on any of them (keys 7-9: up to rounding, inside the parity tolerance). */

@@ -198,7 +198,7 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
         UkfScratch& u = h->uk;
         u.n_max = b.n_max;
         u.gen = 3; u.clip_lanes = 0; u.maxc = 16; u.multiwarp = 1; u.eig3_tile = 1; u.refine_all = 0;
-        h->uks.nsub = 1;
+        h->uks.nsub = 0;                            // automatic (slam_tune key 10)
         CK(cudaEventCreateWithFlags(&h->uks.fork, cudaEventDisableTiming));
         for (int k = 0; k < UKF_MAX_SUB - 1; ++k) {
             CK(cudaStreamCreateWithFlags(&h->uks.aux[k], cudaStreamNonBlocking));
@@ -346,7 +346,7 @@ int slam_tune(slam_handle_t h, int key, int value) {
         h->uk.rot_cap = (value <= 0 || value > full) ? full : value;
     } else if (key == 9) h->uk.clip_lanes = value < 0 ? 0 : value;
     else if (key == 11) h->uk.narrow = value < 0 ? 0 : (value > 2 ? 2 : value);
-    else if (key == 10) { if (value < 1 || value > UKF_MAX_SUB) return fail(h, "slam_tune: UKF slices must be 1..8"); h->uks.nsub = value; }
+    else if (key == 10) { if (value < 0 || value > UKF_MAX_SUB) return fail(h, "slam_tune: UKF slices must be 0 (automatic) or 1..8"); h->uks.nsub = value; }
     else return fail(h, "slam_tune: unknown key");
     return 0;
 }

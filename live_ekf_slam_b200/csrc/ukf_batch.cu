@@ -2700,13 +2700,13 @@ cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const St
     const int qblocks = (b.batch + QL_LANES - 1) / QL_LANES;
     if (u.gen >= 2 && ukf_gen2_supported(b)) {
         const bool gen3 = u.gen == 3;
-        // Optionally (slam_tune key 10; default 1 = off) the batch is cut into nsub contiguous slices, each with its own
-        // front -> QL -> back chain on its own stream, so that the QL kernel -- a pure latency chain, one thread per
-        // instance, ~0.8 n^2 dependent rotations -- can run under the other slices' kernels.  Measured on B200 (4096
-        // instances, n -> 104): 2 % faster with the shared-memory QL (which cannot co-reside: front and back fill the
-        // SMs' shared memory), 30 % SLOWER with the shared-memory-free QL (1.15-wave launches; the chain stretches when it
-        // shares schedulers) -- kept as a knob, not a default.
-        int nsub = xs.nsub < 1 ? 1 : xs.nsub;
+        // The batch is cut into nsub contiguous slices (slam_tune key 10; 0 = automatic), each with its own chain of launches on its
+        // own stream, so that one slice's kernels run under the tails of the other's (every launch ends with a partial wave, and
+        // the size-class launches have several).  Generation 3, 4096 instances: 2 slices 2.6 % faster than 1 (3 slices 1.8 %, 4
+        // slices 1.1 %): automatic = 2 from 2048 instances.  Generation 2 keeps 1: its QL kernel is a pure latency chain, one
+        // thread per instance, that stretches when it shares schedulers (measured 30 % SLOWER in slices with the shared-memory-free
+        // variant that can co-reside; 2 % faster with the shared-memory one, which cannot).
+        int nsub = xs.nsub > 0 ? xs.nsub : ((gen3 && b.batch >= 2048) ? 2 : 1);
         if (nsub > UKF_MAX_SUB) nsub = UKF_MAX_SUB;
         if (b.batch < 64 * nsub) nsub = 1;
         cudaError_t e;
