@@ -1105,6 +1105,54 @@ __device__ __forceinline__ void apply_reflectors(double* W, const int n, const i
     const int step = ASC ? 1 : -1;
     int k = ASC ? 0 : n - 2;
     loadk(k, va, taua);
+    if (j_lo < nv && j_lo + j_step >= nv) {
+        // ONE group of four vectors for this warp (always so in the multi-warp kernel): the lane's rows of the group stay in
+        // registers over all n - 1 reflectors -- per reflector 16 + 16 FMA and the shuffles, no shared-memory traffic at all
+        // (the tile was read and written back for every reflector: half of this phase's instructions)
+        double w[NT][4];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const int i = lane + 32 * t;
+            const double* wr = W + i * WLD + j_lo;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) w[t][c] = (i < n) ? wr[c] : 0.0;
+        }
+        for (int kk = 0; kk < n - 1; ++kk, k += step) {
+            double v[NT];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) v[t] = va[t];
+            const double tau = taua;
+            loadk(k + step, va, taua);
+            if (tau == 0.0) continue;
+            double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) { p0 += v[t] * w[t][0]; p1 += v[t] * w[t][1]; p2 += v[t] * w[t][2]; p3 += v[t] * w[t][3]; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+                p2 += __shfl_xor_sync(0xffffffffu, p2, o); p3 += __shfl_xor_sync(0xffffffffu, p3, o);
+            }
+            p0 *= tau; p1 *= tau; p2 *= tau; p3 *= tau;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                if (v[t] != 0.0) { w[t][0] -= p0 * v[t]; w[t][1] -= p1 * v[t]; w[t][2] -= p2 * v[t]; w[t][3] -= p3 * v[t]; }
+            }
+        }
+        const int left = nv - j_lo;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const int i = lane + 32 * t;
+            if (i < n) {
+                double* wr = W + i * WLD + j_lo;
+                wr[0] = w[t][0];
+                if (left > 1) wr[1] = w[t][1];
+                if (left > 2) wr[2] = w[t][2];
+                if (left > 3) wr[3] = w[t][3];
+            }
+        }
+        __syncwarp();
+        return;
+    }
     for (int kk = 0; kk < n - 1; ++kk, k += step) {
         double v[NT];
 #pragma unroll
