@@ -15,6 +15,9 @@ cap() {  # name, kernel regex, skip, object, command...
 U="python bench.py --filter ukf --steps 1 --warmup 0 --filter-steps 1000 --no-e2e --no-cpu-baseline"
 L="python bench.py --filter large --steps 1 --warmup 0 --no-e2e --no-cpu-baseline"
 C=live_ekf_slam_b200/csrc
-cap eig3 ukf_eig3_kernel 3602 $C/ukf_batch.o $U
-cap front2 ukf_front2_kernel 2702 $C/ukf_batch.o $U
-cap back3 ukf_back3_kernel 1800 $C/ukf_batch.o $U
+# launch indices: filter step 900 with two batch slices (4 eig3 tile/hand-over launches, 3 front2 classes, 2 back3 widths per slice)
+cap eig3 ukf_eig3_kernel 7202 $C/ukf_batch.o $U
+cap front2 ukf_front2_kernel 5402 $C/ukf_batch.o $U
+cap back3 ukf_back3_kernel 3600 $C/ukf_batch.o $U
+cap lm_front lm_front 2800 $C/ekf_large.o $L
+cap lm_gemm lm_gemm 2800 $C/ekf_large.o $L
