@@ -232,7 +232,9 @@ int  slam_get_ukf_routes(slam_handle_t h, long long* out /* 3 */);
  * one-warp-per-instance back kernel of generation 3 instead of the multi-warp one; key 14: 1 = slam_step_io always stages its
  * buffers through device copies, even when they are pinned host memory the kernels could read in place; key 15: 0 = the generation-3
  * eigensolver builds its eigenvectors in the global scratch instead of a shared-memory tile; key 16: 1 = (test knob) the tile
- * kernel hands every instance with a cluster of close eigenvalues to the global-scratch kernel, as if it needed the refinement step; key 8: capacity of the UKF rotation log
+ * kernel hands every instance with a cluster of close eigenvalues to the global-scratch kernel, as if it needed the refinement step;
+ * key 17: storage of the UKF tridiagonalisation in shared memory: 2 (default) = the full square while it fits four times per
+ * SM, the packed lower triangle beyond; 1 = packed for every size; 0 = full square for every size; key 8: capacity of the UKF rotation log
  * (shrinking it forces the rescue pass); key 9: max clipped eigenvectors riding beside the first S-pass; key 10: slices of the UKF batch that run their
  * chains of launches on separate streams (1..8; 0 = automatic, the default: 2 for generation 3 from 2048 instances, else 1); key 11: narrow-tile passes of the UKF back kernel before the full-width
  * one: 1 (default) = a 12-column pass, 2 = an 8-column pass before it (measured 1 % slower on BASELINE configs[2]), 0 = none.  The environment variable

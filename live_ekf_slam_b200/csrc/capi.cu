@@ -197,7 +197,7 @@ int slam_create(int kind, const slam_params* params, int batch, int max_landmark
         b.sigma = nullptr;   // allocated lazily by slam_get_sigma_points
         UkfScratch& u = h->uk;
         u.n_max = b.n_max;
-        u.gen = 3; u.clip_lanes = 0; u.maxc = 16; u.multiwarp = 1; u.eig3_tile = 1; u.refine_all = 0;
+        u.gen = 3; u.clip_lanes = 0; u.maxc = 16; u.multiwarp = 1; u.eig3_tile = 1; u.refine_all = 0; u.front_packed = 2;
         h->uks.nsub = 0;                            // automatic (slam_tune key 10)
         CK(cudaEventCreateWithFlags(&h->uks.fork, cudaEventDisableTiming));
         for (int k = 0; k < UKF_MAX_SUB - 1; ++k) {
@@ -339,6 +339,7 @@ int slam_tune(slam_handle_t h, int key, int value) {
     else if (key == 13) h->uk.multiwarp = value ? 1 : 0;
     else if (key == 15) h->uk.eig3_tile = value ? 1 : 0;
     else if (key == 16) h->uk.refine_all = value ? 1 : 0;
+    else if (key == 17) h->uk.front_packed = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (key == 14) h->no_zero_copy = value ? 1 : 0;
     else if (key == 8) {     // shrink the rotation log (test knob: forces the rescue pass); never beyond the allocation
         long long full = 2LL * h->b.n_max * h->b.n_max;

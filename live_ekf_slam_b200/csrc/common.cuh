@@ -213,6 +213,7 @@ struct UkfScratch {
     unsigned long long* routes;   // [4] instance-steps taken by: dense route (gen 3), QL route (gen 2), gen-1 / rescue, (spare)
     int multiwarp;      // generation 3: 1 (default) = back kernel with one warp per group of four vectors, 0 = one warp per instance
     int maxc;           // generation 3: largest cluster of close eigenvalues handled in the kernel (larger: QL route)
+    int front_packed;   // front kernel's matrix in shared memory: 2 (default) = full square while it fits 4x per SM, packed lower triangle beyond; 1 = packed; 0 = full
     int refine_all;     // test knob: the tile kernel hands EVERY instance with a cluster to the two-array kernel (as if it needed refinement)
     int eig3_tile;      // generation 3: 1 (default) = eigenvectors built in a shared-memory tile when it fits twice per SM, 0 = in the global scratch
     double* xprior;     // [batch][n_max]  x_t at the start of the last step: column 0 of the sigma-point matrix X (ukf.cpp:214)

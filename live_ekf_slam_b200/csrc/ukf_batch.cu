@@ -266,6 +266,132 @@ __device__ void tridiag(double* A, const int lds, const int n, double* d, double
     __syncthreads();
 }
 
+// ---- The same reduction on the PACKED lower triangle (row i holds columns 0..i at tri_off(i)): half the shared memory, so the
+// front kernel of generations 2 / 3 keeps FOUR CTAs per SM up to n = 109 where the full square allowed two from n = 90 (the
+// Householder steps are latency bound: residency is the lever).  The symmetric product reads A(i, c) through
+// the symmetric address (column part: consecutive lanes, consecutive words; row part: a thread walks its own row, the rows of a
+// warp start at triangular offsets = two-way bank conflicts), the rank-2 update touches each stored element once (no mirror,
+// exact symmetry by construction, two FMAs per element).  Same reflector storage on exit: v_k in column k below the diagonal.
+__device__ __forceinline__ int tri_off(const int i) { return (i * (i + 1)) >> 1; }
+
+__device__ __forceinline__ void householder_scalars_packed(const double* A, const int n, const int k, const int lane,
+                                                           double* d, double* e, double* tau, double* slot) {
+    double ss = 0.0;
+    for (int i = k + 2 + lane; i < n; i += 32) { const double a = A[tri_off(i) + k]; ss += a * a; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) {
+        const double alpha = A[tri_off(k + 1) + k];
+        double tk = 0.0, scal = 0.0, beta = alpha;
+        if (ss != 0.0) {
+            beta = -copysign(sqrt(alpha * alpha + ss), alpha);
+            tk = (beta - alpha) / beta;
+            scal = 1.0 / (alpha - beta);
+        }
+        tau[k] = tk; e[k] = beta; d[k] = A[tri_off(k) + k];
+        slot[0] = tk; slot[1] = scal;
+    }
+}
+
+constexpr int TRIP_GMAX = 4;             // row groups of the symmetric product (partial sums in part[TRIP_GMAX][n])
+template <int NT>
+__device__ void tridiag_packed(double* A, const int n, double* d, double* e, double* scratch, double* part, double* red) {
+    static_assert(NT > 32, "warp 0 runs one step ahead of the other warps");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* v = scratch;            // [n]
+    double* p = scratch + n;        // [n]
+    double* w = scratch + 2 * n;    // [n]
+    double* tau = scratch + 3 * n;  // [n]
+    if (warp == 0 && n > 1) householder_scalars_packed(A, n, 0, lane, d, e, tau, red);
+    __syncthreads();
+    for (int k = 0; k < n - 1; ++k) {
+        const int m0 = k + 1;                      // first row/col of the trailing block
+        const int m = n - m0;                      // its size
+        const double tk = red[2 * (k & 1)], scal = red[2 * (k & 1) + 1];
+        double* next_slot = red + 2 * ((k + 1) & 1);
+        if (tk != 0.0) {                            // uniform
+            for (int i = m0 + tid; i < n; i += NT) {
+                const int o = tri_off(i) + k;
+                const double vi = (i == m0) ? 1.0 : A[o] * scal;
+                v[i] = vi;
+                A[o] = vi;                          // keep the reflector in column k
+            }
+            __syncthreads();
+            // thread -> (index c, row group g): p[c] = sum_i A(i, c) v[i] over the rows of the group; A(i, c) = stored(c, i) for i < c
+            // (the thread's own row, contiguous), stored(i, c) for i >= c (column c, the lanes of a warp side by side)
+            int G = NT / m; if (G > TRIP_GMAX) G = TRIP_GMAX; if (G < 1) G = 1;
+            const int g = tid / m, cl = tid - g * m;
+            const int rb = (m + G - 1) / G;
+            const int c = m0 + cl;
+            if (g < G) {                            // (m <= NT: n_max <= 256)
+                const int r_lo = m0 + g * rb, r_hi = (r_lo + rb < n) ? r_lo + rb : n;
+                int r_mid = c > r_lo ? c : r_lo; if (r_mid > r_hi) r_mid = r_hi;
+                double a0 = 0.0, a1 = 0.0;
+                const double* row = A + tri_off(c);
+                int i = r_lo;
+                for (; i + 1 < r_mid; i += 2) { a0 = fma(row[i], v[i], a0); a1 = fma(row[i + 1], v[i + 1], a1); }
+                if (i < r_mid) { a0 = fma(row[i], v[i], a0); ++i; }
+                int o = tri_off(i) + c;
+                for (; i + 1 < r_hi; i += 2) {
+                    a0 = fma(A[o], v[i], a0);
+                    a1 = fma(A[o + i + 1], v[i + 1], a1);
+                    o += 2 * i + 3;                 // tri_off(i + 2) - tri_off(i)
+                }
+                if (i < r_hi) a0 = fma(A[o], v[i], a0);
+                part[g * n + c] = a0 + a1;
+            }
+            __syncthreads();
+            double pv[1] = {0.0};
+            for (int cc = m0 + tid; cc < n; cc += NT) {
+                double acc = 0.0;
+                for (int q = 0; q < G; ++q) acc += part[q * n + cc];
+                acc *= tk;
+                p[cc] = acc;
+                pv[0] += acc * v[cc];
+            }
+            block_sum<1, NT / 32>(pv, red + 8);
+            const double a2 = -0.5 * tk * pv[0];
+            for (int cc = m0 + tid; cc < n; cc += NT) w[cc] = p[cc] + a2 * v[cc];
+            __syncthreads();
+            // stored part of A22 -= v w^T + w v^T
+            if (warp == 0) {
+                // column m0 (rows m0..n-1), then the NEXT step's scalars from it
+                const double vc = v[m0], wc = w[m0];
+                for (int i = m0 + lane; i < n; i += 32) {
+                    const int o = tri_off(i) + m0;
+                    A[o] = fma(-v[i], wc, fma(-w[i], vc, A[o]));
+                }
+                __syncwarp();
+                if (m0 < n - 1) householder_scalars_packed(A, n, m0, lane, d, e, tau, next_slot);
+            } else {
+                // columns m0+1..n-1 on the remaining NT - 32 threads: thread -> (column c2, row group), rows >= c2 only
+                const int c_lo = m0 + 1, mm = n - c_lo;
+                const int t2 = tid - 32, T2 = NT - 32;
+                if (mm > 0) {
+                    int G2 = T2 / mm; if (G2 > 8) G2 = 8; if (G2 < 1) G2 = 1;
+                    const int g2 = t2 / mm, cl2 = t2 - g2 * mm;
+                    const int rb2 = (mm + G2 - 1) / G2;
+                    if (g2 < G2) {
+                        const int c2 = c_lo + cl2;
+                        const int lo2 = c_lo + g2 * rb2, hi2 = (lo2 + rb2 < n) ? lo2 + rb2 : n;
+                        const double vc = v[c2], wc = w[c2];
+                        int i = lo2 > c2 ? lo2 : c2;
+                        int o = tri_off(i) + c2;
+#pragma unroll 2
+                        for (; i < hi2; ++i) {
+                            A[o] = fma(-v[i], wc, fma(-w[i], vc, A[o]));
+                            o += i + 1;
+                        }
+                    }
+                }
+            }
+        } else if (warp == 0 && m0 < n - 1) householder_scalars_packed(A, n, m0, lane, d, e, tau, next_slot);   // nothing to update
+        __syncthreads();
+    }
+    if (tid == 0) { d[n - 1] = A[tri_off(n - 1) + (n - 1)]; e[n - 1] = 0.0; }
+    __syncthreads();
+}
+
 // explicit orthogonal factor from the reflectors left in A by tridiag (tau in scratch[3n..4n)), transposed in place
 __device__ void form_qt(double* A, const int lds, const int n, double* scratch, double* part) {
     const int tid = threadIdx.x;
@@ -1315,12 +1441,12 @@ constexpr int FRONT2_THREADS = 256;      // (512 threads measured slower: 3.79 -
 // Shared memory of the kernel, sized by a CLASS of instance sizes (ncap = largest n of the class), not by the batch's capacity:
 // the Householder steps are barrier and latency bound, so the instances with few landmarks run at 4 CTAs per SM instead of 2.
 struct Front2Smem { double *A, *d, *e, *pool, *part, *red; };
-__host__ __device__ inline size_t front2_carve(const int ncap, unsigned char* base, Front2Smem* s) {
+__host__ __device__ inline size_t front2_carve(const int ncap, unsigned char* base, Front2Smem* s, const bool packed = true) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
-    const size_t oA = take(sizeof(double) * (size_t)ncap * lds_of(ncap));
+    const size_t oA = take(sizeof(double) * (packed ? (size_t)ncap * (ncap + 1) / 2 : (size_t)ncap * lds_of(ncap)));
     const size_t od = take(sizeof(double) * ncap), oe = take(sizeof(double) * ncap);
-    const size_t opool = take(sizeof(double) * 4 * ncap), opart = take(sizeof(double) * (8 * ncap + 8)), ored = take(sizeof(double) * 32);
+    const size_t opool = take(sizeof(double) * 4 * ncap), opart = take(sizeof(double) * ((packed ? TRIP_GMAX : 8) * ncap + 8)), ored = take(sizeof(double) * 32);
     if (s) {
         s->A = (double*)(base + oA); s->d = (double*)(base + od); s->e = (double*)(base + oe);
         s->pool = (double*)(base + opool); s->part = (double*)(base + opart); s->red = (double*)(base + ored);
@@ -1328,13 +1454,13 @@ __host__ __device__ inline size_t front2_carve(const int ncap, unsigned char* ba
     return off;
 }
 // classes for MINB = 4, 3, 2 CTAs per SM (register budget 64 / 80 / 128 per thread); caps ascending, returns the count
-inline int front2_classes(const BatchState& b, int caps[3], int minb[3]) {
+inline int front2_classes(const BatchState& b, int caps[3], int minb[3], const bool packed) {
     static const int per_sm[3] = {4, 3, 2};
     int nc = 0, prev = 0;
     for (int k = 0; k < 3; ++k) {
         const size_t budget = (size_t)(227 * 1024) / per_sm[k] - 1024;
         int cap = prev;
-        while (cap < b.n_max && front2_carve(cap + 1, nullptr, nullptr) <= budget) ++cap;
+        while (cap < b.n_max && front2_carve(cap + 1, nullptr, nullptr, packed) <= budget) ++cap;
         if (k == 2) cap = b.n_max;                 // the last class takes whatever is left (one CTA per SM beyond 2 x 113 KB)
         if (cap > prev) { caps[nc] = cap; minb[nc] = per_sm[k]; ++nc; prev = cap; }
         if (cap >= b.n_max) break;
@@ -1342,12 +1468,12 @@ inline int front2_classes(const BatchState& b, int caps[3], int minb[3]) {
     return nc;
 }
 
-template <int MINB>
+template <int MINB, bool PACKED>
 __global__ void __launch_bounds__(FRONT2_THREADS, MINB)
 ukf_front2_kernel(BatchState b, UkfScratch u, const int i0, const int nlo, const int ncap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Front2Smem s;
-    front2_carve(ncap, smem_raw, &s);
+    front2_carve(ncap, smem_raw, &s, PACKED);
     const int tid = threadIdx.x;
     const int inst = i0 + blockIdx.x;
     const int lds = lds_of(ncap);
@@ -1358,36 +1484,57 @@ ukf_front2_kernel(BatchState b, UkfScratch u, const int i0, const int nlo, const
     const int n = 4 + 2 * M;                       // ukf.cpp:167
     if (n <= nlo || n > ncap) return;              // another class's launch takes this instance
     const double* gP = b.P + (size_t)inst * b.p_stride;
-    for (int idx = tid; idx < n * n; idx += FRONT2_THREADS) {
-        const int i = idx / n, j = idx - i * n;
-        s.A[(size_t)i * lds + j] = gP[(size_t)i * ldp + j];
-    }
-    __syncthreads();
     const float W0f = 0.2f;                                                // filter.h:207
     const double wgt = (double)((1 - W0f) / (2 * n));                      // :175
     const double scale = (double)((2 * M + 4) / (1 - W0f));                // :114
-    for (int idx = tid; idx < n * n; idx += FRONT2_THREADS) {
-        const int i = idx / n, j = idx - i * n;
-        if (j >= i) {
-            const double y = (0.5 * (s.A[(size_t)i * lds + j] + s.A[(size_t)j * lds + i])) * scale;
-            s.A[(size_t)i * lds + j] = y; s.A[(size_t)j * lds + i] = y;
-        }
-    }
-    __syncthreads();
     double* Yg = u.Yg + (size_t)inst * u.n_max * u.n_max;
-    for (int idx = tid; idx < n * n; idx += FRONT2_THREADS) {
-        const int i = idx / n, j = idx - i * n;
-        if (i >= 4 && j >= 4) Yg[idx] = (2.0 * wgt) * s.A[(size_t)i * lds + j];   // landmark block of P_pred before corrections
-    }
-    __syncthreads();
-    tridiag<FRONT2_THREADS>(s.A, lds, n, s.d, s.e, s.pool, s.part, s.red);
-    // reflector k (column k of A below the diagonal) -> row k of the scratch matrix, tau_k on its diagonal
     double* Rg = u.Zg + (size_t)inst * u.n_max * u.n_max;
     const double* tau = s.pool + 3 * n;
-    for (int idx = tid; idx < n * n; idx += FRONT2_THREADS) {
-        const int k = idx / n, i = idx - k * n;
-        if (i > k) Rg[idx] = s.A[(size_t)i * lds + k];
-        else if (i == k) Rg[idx] = (k < n - 1) ? tau[k] : 0.0;
+    if constexpr (PACKED) {
+        // Y = scale * sym(P), lower triangle only: (i, j <= i) from P[j][i] + P[i][j] (the mirror element straight from global memory)
+        for (int idx = tid; idx < n * n; idx += FRONT2_THREADS) {
+            const int i = idx / n, j = idx - i * n;
+            if (j <= i) s.A[tri_off(i) + j] = (0.5 * (gP[(size_t)j * ldp + i] + gP[(size_t)i * ldp + j])) * scale;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < n * n; idx += FRONT2_THREADS) {
+            const int i = idx / n, j = idx - i * n;
+            if (i >= 4 && j >= 4) Yg[idx] = (2.0 * wgt) * s.A[i >= j ? tri_off(i) + j : tri_off(j) + i];   // landmark block of P_pred before corrections
+        }
+        __syncthreads();
+        tridiag_packed<FRONT2_THREADS>(s.A, n, s.d, s.e, s.pool, s.part, s.red);
+        // reflector k (column k of A below the diagonal) -> row k of the scratch matrix, tau_k on its diagonal
+        for (int idx = tid; idx < n * n; idx += FRONT2_THREADS) {
+            const int k = idx / n, i = idx - k * n;
+            if (i > k) Rg[idx] = s.A[tri_off(i) + k];
+            else if (i == k) Rg[idx] = (k < n - 1) ? tau[k] : 0.0;
+        }
+    } else {
+        for (int idx = tid; idx < n * n; idx += FRONT2_THREADS) {
+            const int i = idx / n, j = idx - i * n;
+            s.A[(size_t)i * lds + j] = gP[(size_t)i * ldp + j];
+        }
+        __syncthreads();
+        for (int idx = tid; idx < n * n; idx += FRONT2_THREADS) {
+            const int i = idx / n, j = idx - i * n;
+            if (j >= i) {
+                const double y = (0.5 * (s.A[(size_t)i * lds + j] + s.A[(size_t)j * lds + i])) * scale;
+                s.A[(size_t)i * lds + j] = y; s.A[(size_t)j * lds + i] = y;
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < n * n; idx += FRONT2_THREADS) {
+            const int i = idx / n, j = idx - i * n;
+            if (i >= 4 && j >= 4) Yg[idx] = (2.0 * wgt) * s.A[(size_t)i * lds + j];   // landmark block of P_pred before corrections
+        }
+        __syncthreads();
+        tridiag<FRONT2_THREADS>(s.A, lds, n, s.d, s.e, s.pool, s.part, s.red);
+        // reflector k (column k of A below the diagonal) -> row k of the scratch matrix, tau_k on its diagonal
+        for (int idx = tid; idx < n * n; idx += FRONT2_THREADS) {
+            const int k = idx / n, i = idx - k * n;
+            if (i > k) Rg[idx] = s.A[(size_t)i * lds + k];
+            else if (i == k) Rg[idx] = (k < n - 1) ? tau[k] : 0.0;
+        }
     }
     for (int k = tid; k < n; k += FRONT2_THREADS) { u.dg[(size_t)k * b.batch + inst] = s.d[k]; u.eg[(size_t)k * b.batch + inst] = s.e[k]; }
 }
@@ -2685,9 +2832,17 @@ cudaError_t ukf_step_configure(const BatchState& b) {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(ukf_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_step_smem_bytes(b))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ukf_front2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)front2_carve(b.n_max, nullptr, nullptr))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ukf_front2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 75 * 1024)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ukf_front2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024)) != cudaSuccess) return e;
+    {
+        size_t fp = front2_carve(b.n_max, nullptr, nullptr, true), ff = front2_carve(b.n_max, nullptr, nullptr, false);
+        if (fp > 227 * 1024) fp = 227 * 1024;
+        if (ff > 227 * 1024) ff = 227 * 1024;
+        if ((e = cudaFuncSetAttribute(ukf_front2_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(ukf_front2_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 75 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(ukf_front2_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(ukf_front2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(ukf_front2_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 75 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(ukf_front2_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024)) != cudaSuccess) return e;
+    }
     if ((e = cudaFuncSetAttribute(ukf_back2_kernel<13, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 13))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back2_kernel<25, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 25))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ukf_back2_kernel<33, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ukf_warp_smem_bytes(b, 33))) != cudaSuccess) return e;
@@ -2769,14 +2924,28 @@ cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const St
             if (i1 <= i0) continue;
             cudaStream_t sk = (k == 0) ? st : xs.aux[k - 1];
             {
-                int caps[3], minb[3];
-                const int ncls = front2_classes(b, caps, minb);
+                // classes: (largest n, CTAs per SM, packed?) ascending.  front_packed = 2 (default, hybrid): the full square while it
+                // fits four times per SM (column pairs, no bank conflicts), the packed triangle beyond; 1 = packed only; 0 = full only
+                int capsf[3], minbf[3], capsp[3], minbp[3], cap_[6], minb_[6], pk_[6], ncls = 0;
+                const int nf = u.front_packed != 1 ? front2_classes(b, capsf, minbf, false) : 0;
+                const int np_ = u.front_packed != 0 ? front2_classes(b, capsp, minbp, true) : 0;
+                int covered = 0;
+                for (int c = 0; c < nf; ++c)
+                    if (u.front_packed == 0 || minbf[c] == 4) { cap_[ncls] = capsf[c]; minb_[ncls] = minbf[c]; pk_[ncls] = 0; covered = capsf[c]; ++ncls; }
+                for (int c = 0; c < np_; ++c)
+                    if (capsp[c] > covered) { cap_[ncls] = capsp[c]; minb_[ncls] = minbp[c]; pk_[ncls] = 1; covered = capsp[c]; ++ncls; }
                 for (int c = 0; c < ncls; ++c) {
-                    const int lo = c ? caps[c - 1] : 0;
-                    const size_t sm = front2_carve(caps[c], nullptr, nullptr);
-                    if (minb[c] == 4) ukf_front2_kernel<4><<<i1 - i0, FRONT2_THREADS, sm, sk>>>(b, u, i0, lo, caps[c]);
-                    else if (minb[c] == 3) ukf_front2_kernel<3><<<i1 - i0, FRONT2_THREADS, sm, sk>>>(b, u, i0, lo, caps[c]);
-                    else ukf_front2_kernel<2><<<i1 - i0, FRONT2_THREADS, sm, sk>>>(b, u, i0, lo, caps[c]);
+                    const int lo = c ? cap_[c - 1] : 0;
+                    const size_t sm = front2_carve(cap_[c], nullptr, nullptr, pk_[c] != 0);
+                    if (pk_[c]) {
+                        if (minb_[c] == 4) ukf_front2_kernel<4, true><<<i1 - i0, FRONT2_THREADS, sm, sk>>>(b, u, i0, lo, cap_[c]);
+                        else if (minb_[c] == 3) ukf_front2_kernel<3, true><<<i1 - i0, FRONT2_THREADS, sm, sk>>>(b, u, i0, lo, cap_[c]);
+                        else ukf_front2_kernel<2, true><<<i1 - i0, FRONT2_THREADS, sm, sk>>>(b, u, i0, lo, cap_[c]);
+                    } else {
+                        if (minb_[c] == 4) ukf_front2_kernel<4, false><<<i1 - i0, FRONT2_THREADS, sm, sk>>>(b, u, i0, lo, cap_[c]);
+                        else if (minb_[c] == 3) ukf_front2_kernel<3, false><<<i1 - i0, FRONT2_THREADS, sm, sk>>>(b, u, i0, lo, cap_[c]);
+                        else ukf_front2_kernel<2, false><<<i1 - i0, FRONT2_THREADS, sm, sk>>>(b, u, i0, lo, cap_[c]);
+                    }
                 }
                 nback += ncls - 1;
             }

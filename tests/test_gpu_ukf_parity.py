@@ -165,11 +165,12 @@ def test_ukf_filter_class(shim, oracle):
 
 @pytest.mark.parametrize("knobs", [((7, 1),), ((7, 2),), ((7, 2), (8, 600)), ((7, 2), (9, 1)), ((7, 2), (8, 2500), (9, 1)), ((7, 2), (11, 0)),
                                    ((7, 3),), ((7, 3), (12, 1)), ((7, 3), (12, 1), (8, 600)), ((7, 3), (9, 1)), ((7, 3), (11, 0)),
-                                   ((7, 3), (13, 0)), ((7, 3), (13, 0), (9, 1)), ((7, 3), (15, 0)), ((7, 3), (15, 0), (12, 1)), ((7, 3), (16, 1)), ((7, 3), (11, 2))],
+                                   ((7, 3), (13, 0)), ((7, 3), (13, 0), (9, 1)), ((7, 3), (15, 0)), ((7, 3), (15, 0), (12, 1)), ((7, 3), (16, 1)), ((7, 3), (11, 2)), ((7, 3), (17, 0)), ((7, 2), (17, 0)), ((7, 3), (17, 1))],
                          ids=["generation1", "generation2", "rescue_pass_only", "clip_overflow_pass", "mixed_rescue", "full_width_tile_only",
                               "generation3", "gen3_clusters_take_the_ql_route", "gen3_ql_route_then_rescue", "gen3_clip_overflow_pass",
                               "gen3_full_width_tile_only", "gen3_single_warp_back_kernel", "gen3_single_warp_clip_overflow",
-                              "gen3_global_scratch_eigenvectors", "gen3_global_scratch_ql_route", "gen3_tile_hands_over_clusters", "gen3_three_tile_widths"])
+                              "gen3_global_scratch_eigenvectors", "gen3_global_scratch_ql_route", "gen3_tile_hands_over_clusters", "gen3_three_tile_widths",
+                              "gen3_full_square_tridiagonalisation", "gen2_full_square_tridiagonalisation", "gen3_packed_tridiagonalisation"])
 def test_ukf_step_variants(shim, oracle, knobs):
     """The same free-running batch through the alternative code paths of the UKF step: the generation-1 kernels
     (explicit eigenvectors), a rotation log too small for any / for the later steps (rescue pass on the generation-1
