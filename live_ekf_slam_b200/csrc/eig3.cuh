@@ -364,6 +364,68 @@ EIG3_HD int twisted_vector1(const double* d, const double* e, const double* e2, 
     return k;
 }
 
+// twisted_vector1 with the backward pivots D-_i PARKED in a second (global-memory) slot during the first backward sweep instead of
+// being recomputed by a second sweep down to the twist: the stores are fire-and-forget, and the upward recurrence -- whose
+// pivots do not depend on the running component -- fetches them back eight at a time, one batch ahead, so the round trip stays off
+// the chain.  Removes up to n dependent divisions (n/2 on average, but the CTA waits for its slowest thread) from 3.5 n.
+// Same arithmetic, same values as twisted_vector1.
+EIG3_HD int twisted_vector1g(const double* d, const double* e, const double* e2, const int a, const int b, const double x,
+                             const double pivf, const Slot z, const Slot g, double* nrm2) {
+    double dp = d[a] - x;
+    for (int i = a; i < b - 1; ++i) {
+        if (fabs(dp) < pivf) dp = -pivf;
+        z.set(i, dp);
+        dp = (d[i + 1] - x) - e2[i] / dp;
+    }
+    if (fabs(dp) < pivf) dp = -pivf;
+    z.set(b - 1, dp);
+    double dm = d[b - 1] - x;
+    if (fabs(dm) < pivf) dm = -pivf;
+    int k = b - 1;
+    double gk = dp + dm - (d[b - 1] - x), best = fabs(gk);
+    for (int i = b - 1; i > a; --i) {
+        g.set(i, dm);                                          // D-_i
+        double dn = (d[i - 1] - x) - e2[i - 1] / dm;
+        if (fabs(dn) < pivf) dn = -pivf;
+        const double gg = z.get(i - 1) + dn - (d[i - 1] - x);
+        if (fabs(gg) <= best) { best = fabs(gg); gk = gg; k = i - 1; }
+        dm = dn;
+    }
+    double s2 = 1.0, zi = 1.0;
+    for (int i = k - 1; i >= a; --i) {
+        zi = -(e[i] / z.get(i)) * zi;
+        z.set(i, zi);
+        s2 += zi * zi;
+    }
+    zi = 1.0;
+    {
+        constexpr int PB = 8;
+        double cur[PB], nxt[PB];
+        int i0 = k;
+#pragma unroll
+        for (int q = 0; q < PB; ++q) cur[q] = (i0 + q + 1 < b) ? g.get(i0 + q + 1) : 1.0;
+        while (i0 < b - 1) {
+#pragma unroll
+            for (int q = 0; q < PB; ++q) nxt[q] = (i0 + PB + q + 1 < b) ? g.get(i0 + PB + q + 1) : 1.0;
+#pragma unroll
+            for (int q = 0; q < PB; ++q) {
+                const int i = i0 + q;
+                if (i < b - 1) {
+                    zi = -(e[i] / cur[q]) * zi;
+                    z.set(i + 1, zi);
+                    s2 += zi * zi;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < PB; ++q) cur[q] = nxt[q];
+            i0 += PB;
+        }
+    }
+    z.set(k, 1.0);
+    *nrm2 = s2;
+    return k;
+}
+
 // One inverse-iteration step through the kept factors: solves N_k D_k N_k^T y = z in place (z <- y, unnormalised) on the
 // block [a, b) with twist index k.  Returns sum y_i^2.
 EIG3_HD double twisted_solve(const double* e, const int a, const int b, const int k, const Slot z, const Slot w) {

@@ -1741,7 +1741,11 @@ ukf_eig3_kernel(BatchState b, UkfScratch u, const int i0, const int maxc, const 
             if (bb - a == 1) zt.set(a, 1.0);
             else {
                 double n2 = 1.0;
+#ifdef EIG3_SECOND_SWEEP
                 eig3::twisted_vector1(s.d, s.e, s.e2, a, bb, x, pivf, zt, &n2);
+#else
+                eig3::twisted_vector1g(s.d, s.e, s.e2, a, bb, x, pivf, zt, eig3::Slot{Wg + t, n}, &n2);   // D- parked in the (still unused) V^T region
+#endif
                 const double sc = rsqrt(n2);
                 if (!(n2 > 0.0) || !isfinite(n2)) badt = true;
 #pragma unroll 4
