@@ -230,8 +230,10 @@ int  slam_get_ukf_routes(slam_handle_t h, long long* out /* 3 */);
  * CTA per instance); key 12: largest cluster of close eigenvalues the generation-3 eigensolver re-orthogonalises itself (larger
  * clusters send the instance down the generation-2 route in the same step; 1 forces that route for any cluster); key 13: 0 = the
  * one-warp-per-instance back kernel of generation 3 instead of the multi-warp one; key 14: 1 = slam_step_io always stages its
- * buffers through device copies, even when they are pinned host memory the kernels could read in place; key 15: 0 = the generation-3
- * eigensolver builds its eigenvectors in the global scratch instead of a shared-memory tile; key 16: 1 = (test knob) the tile
+ * buffers through device copies, even when they are pinned host memory the kernels could read in place; key 15: where the generation-3
+ * eigensolver builds its eigenvectors: 1 (default) = a shared-memory tile for every size class, 0 = the global scratch (pivots
+ * prefetched in batches ahead of the division chains), 2 = the tile for the classes that fit three times per SM, the global
+ * scratch beyond (measured equal to 1 on BASELINE configs[2]); key 16: 1 = (test knob) the tile
  * kernel hands every instance with a cluster of close eigenvalues to the global-scratch kernel, as if it needed the refinement step;
  * key 17: storage of the UKF tridiagonalisation in shared memory: 2 (default) = the full square while it fits four times per
  * SM, the packed lower triangle beyond; 1 = packed for every size; 0 = full square for every size; key 8: capacity of the UKF rotation log

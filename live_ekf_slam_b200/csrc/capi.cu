@@ -337,7 +337,7 @@ int slam_tune(slam_handle_t h, int key, int value) {
     else if (key == 7) { if (value < 1 || value > 3) return fail(h, "slam_tune: UKF generation must be 1, 2 or 3"); h->uk.gen = value; }
     else if (key == 12) h->uk.maxc = value < 0 ? 0 : value;
     else if (key == 13) h->uk.multiwarp = value ? 1 : 0;
-    else if (key == 15) h->uk.eig3_tile = value ? 1 : 0;
+    else if (key == 15) h->uk.eig3_tile = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (key == 16) h->uk.refine_all = value ? 1 : 0;
     else if (key == 17) h->uk.front_packed = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (key == 14) h->no_zero_copy = value ? 1 : 0;

@@ -315,6 +315,101 @@ EIG3_HD int twisted_vector(const double* d, const double* e, const double* e2, c
     return k;
 }
 
+// twisted_vector with every read-back BATCHED: the recurrences read pivots they (or an earlier sweep) stored in the strided work
+// vectors -- global memory in the kernel, an L2 round trip each -- but no pivot depends on the running value of its chain, so
+// PB of them are fetched one batch ahead and the chain of dependent divisions never waits for memory.  The backward pivots are
+// parked in w during the first backward sweep (no second sweep).  Same arithmetic and same results as twisted_vector.
+template <int PB>
+EIG3_HD int twisted_vector_pf(const double* d, const double* e, const double* e2, const int a, const int b, const double x,
+                              const double pivf, const Slot z, const Slot w, double* nrm2) {
+    double dp = d[a] - x;
+    for (int i = a; i < b - 1; ++i) {
+        if (fabs(dp) < pivf) dp = -pivf;
+        z.set(i, dp);
+        dp = (d[i + 1] - x) - e2[i] / dp;
+    }
+    if (fabs(dp) < pivf) dp = -pivf;
+    z.set(b - 1, dp);
+    double dm = d[b - 1] - x;
+    if (fabs(dm) < pivf) dm = -pivf;
+    int k = b - 1;
+    double gk = dp + dm - (d[b - 1] - x), best = fabs(gk);
+    double cur[PB], nxt[PB];
+    {   // backward sweep, i = b-1 .. a+1: gamma_i-1 needs D+_i-1 = z[i-1]
+        int i0 = b - 1;
+#pragma unroll
+        for (int q = 0; q < PB; ++q) cur[q] = (i0 - q - 1 >= a) ? z.get(i0 - q - 1) : 0.0;
+        while (i0 > a) {
+#pragma unroll
+            for (int q = 0; q < PB; ++q) nxt[q] = (i0 - PB - q - 1 >= a) ? z.get(i0 - PB - q - 1) : 0.0;
+#pragma unroll
+            for (int q = 0; q < PB; ++q) {
+                const int i = i0 - q;
+                if (i > a) {
+                    w.set(i, dm);                              // D-_i
+                    double dn = (d[i - 1] - x) - e2[i - 1] / dm;
+                    if (fabs(dn) < pivf) dn = -pivf;
+                    const double g = cur[q] + dn - (d[i - 1] - x);
+                    if (fabs(g) <= best) { best = fabs(g); gk = g; k = i - 1; }
+                    dm = dn;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < PB; ++q) cur[q] = nxt[q];
+            i0 -= PB;
+        }
+    }
+    if (fabs(gk) < pivf) gk = pivf;
+    double s2 = 1.0, zi = 1.0;
+    {   // downward, i = k-1 .. a: pivot D+_i = z[i]; the factor moves to w[i], the component takes its place
+        int i0 = k - 1;
+#pragma unroll
+        for (int q = 0; q < PB; ++q) cur[q] = (i0 - q >= a) ? z.get(i0 - q) : 1.0;
+        while (i0 >= a) {
+#pragma unroll
+            for (int q = 0; q < PB; ++q) nxt[q] = (i0 - PB - q >= a) ? z.get(i0 - PB - q) : 1.0;
+#pragma unroll
+            for (int q = 0; q < PB; ++q) {
+                const int i = i0 - q;
+                if (i >= a) {
+                    const double piv = cur[q];
+                    zi = -(e[i] / piv) * zi;
+                    w.set(i, piv); z.set(i, zi);
+                    s2 += zi * zi;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < PB; ++q) cur[q] = nxt[q];
+            i0 -= PB;
+        }
+    }
+    zi = 1.0;
+    {   // upward, i = k .. b-2: pivot D-_i+1 = w[i+1] (parked above, stays there)
+        int i0 = k;
+#pragma unroll
+        for (int q = 0; q < PB; ++q) cur[q] = (i0 + q + 1 < b) ? w.get(i0 + q + 1) : 1.0;
+        while (i0 < b - 1) {
+#pragma unroll
+            for (int q = 0; q < PB; ++q) nxt[q] = (i0 + PB + q + 1 < b) ? w.get(i0 + PB + q + 1) : 1.0;
+#pragma unroll
+            for (int q = 0; q < PB; ++q) {
+                const int i = i0 + q;
+                if (i < b - 1) {
+                    zi = -(e[i] / cur[q]) * zi;
+                    z.set(i + 1, zi);
+                    s2 += zi * zi;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < PB; ++q) cur[q] = nxt[q];
+            i0 += PB;
+        }
+    }
+    z.set(k, 1.0); w.set(k, gk);
+    *nrm2 = s2;
+    return k;
+}
+
 // The same eigenvector in ONE work vector (the shared-memory variant of the kernel: a column of an n x n tile per thread, no
 // second array): the pivots are overwritten by the vector's components as the recurrences consume them.  Nothing is kept for a
 // refinement step -- the caller hands such (rare) instances to the two-array routine above.
@@ -472,6 +567,28 @@ EIG3_HD double residual_inf(const double* d, const double* e, const int a, const
         zm = zc; zc = zn;
     }
     return r * fabs(scale);
+}
+
+// residual_inf with the vector fetched PB components at a time (global work vectors: one round trip per batch, not per component)
+template <int PB>
+EIG3_HD double residual_inf_pf(const double* d, const double* e, const int a, const int b, const double x, const Slot z) {
+    double r = 0.0, zm = 0.0, zc = z.get(a);
+    double buf[PB];
+    for (int i0 = a; i0 < b; i0 += PB) {
+#pragma unroll
+        for (int q = 0; q < PB; ++q) buf[q] = (i0 + q + 1 < b) ? z.get(i0 + q + 1) : 0.0;
+#pragma unroll
+        for (int q = 0; q < PB; ++q) {
+            const int i = i0 + q;
+            if (i < b) {
+                const double zn = buf[q];
+                const double v = (i > a ? e[i - 1] * zm : 0.0) + (d[i] - x) * zc + (i + 1 < b ? e[i] * zn : 0.0);
+                r = fmax(r, fabs(v));
+                zm = zc; zc = zn;
+            }
+        }
+    }
+    return r;
 }
 
 }  // namespace eig3

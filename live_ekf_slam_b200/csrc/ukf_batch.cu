@@ -1578,7 +1578,7 @@ __host__ __device__ inline size_t eig3_carve(const int n_max, const int nt, unsi
 // capacity, so an instance with few landmarks runs at 4 CTAs per SM and only the largest ones at 2.  One launch per class; a CTA
 // whose instance belongs to another class exits at once.  caps[k] = largest n of class k (ascending), returns the class count;
 // 0 = the variant is not used (n_max beyond what fits twice per SM, or 128 threads).
-inline int eig3_classes(const BatchState& b, int caps[4]) {
+inline int eig3_classes(const BatchState& b, int caps[4], int* per = nullptr) {
     if (b.n_max > 128) return 0;
     static const int per_sm[3] = {4, 3, 2};        // (<= 128 registers per thread: four CTAs of 128 threads at most)
     int nc = 0, prev = 0;
@@ -1586,7 +1586,7 @@ inline int eig3_classes(const BatchState& b, int caps[4]) {
         const size_t budget = (size_t)(227 * 1024) / per_sm[k] - 1024;
         int cap = prev;
         while (cap < b.n_max && eig3_carve(cap + 1, 128, nullptr, nullptr, true) <= budget) ++cap;
-        if (cap > prev) { caps[nc++] = cap; prev = cap; }
+        if (cap > prev) { if (per) per[nc] = per_sm[k]; caps[nc++] = cap; prev = cap; }
         if (cap >= b.n_max) return nc;
     }
     return 0;                                      // the largest instances would not fit twice per SM
@@ -1649,7 +1649,7 @@ __device__ __forceinline__ void eig3_gram_schmidt(const Eig3Smem& s, double* bas
 // refinement step (nearly parallel twisted vectors; the tile keeps no factors) is flagged nswp = -4 and re-done by the
 // TILE = false kernel, launched behind this one with only_flagged = 1.
 template <int NT, bool TILE>
-__global__ void __launch_bounds__(NT, TILE ? 4 : 1024 / NT)      // TILE = false: <= 64 registers, the latency chains are hidden by resident warps only
+__global__ void __launch_bounds__(NT, TILE ? 4 : 512 / NT)       // 128 registers: room for the batches of pivots fetched ahead of the chains
 ukf_eig3_kernel(BatchState b, UkfScratch u, const int i0, const int maxc, const int only_flagged, const int nlo, const int ncap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Eig3Smem s;
@@ -1658,9 +1658,10 @@ ukf_eig3_kernel(BatchState b, UkfScratch u, const int i0, const int maxc, const 
     const int inst = i0 + blockIdx.x;
     const int4 meta_in = b.meta[inst];
     if (meta_in.y & SLAM_STATUS_SAME_STEP_REMATCH) return;
-    if (only_flagged && u.nswp[inst] != -4) return;
     const int n = 4 + 2 * meta_in.x;
     if (TILE && (n <= nlo || n > ncap)) return;    // size classes: this launch's tile holds nlo < n <= ncap (see eig3_classes)
+    if (!TILE && only_flagged && u.nswp[inst] != -4 && n <= nlo) return;     // behind the tile launches: the instances they handed over
+                                                                             // and the sizes (n > nlo) no tile class was launched for
     double* const Vg = u.Vg + (size_t)inst * u.n_max * u.n_max;       // [i][k], compact leading dimension n
     double* const Wg = u.VTg + (size_t)inst * u.n_max * u.n_max;      // work space now, V^T at the end
     const bool live = t < n;
@@ -1785,10 +1786,10 @@ ukf_eig3_kernel(BatchState b, UkfScratch u, const int i0, const int maxc, const 
         if (bb - a == 1) z.set(a, 1.0);
         else {
             double n2 = 1.0;
-            tw = eig3::twisted_vector(s.d, s.e, s.e2, a, bb, x, pivf, z, w, &n2);
+            tw = eig3::twisted_vector_pf<8>(s.d, s.e, s.e2, a, bb, x, pivf, z, w, &n2);   // every read-back one batch ahead of its chain
             const double sc = rsqrt(n2);
             if (!(n2 > 0.0) || !isfinite(n2)) bad = true;
-#pragma unroll 4
+#pragma unroll 8
             for (int i = a; i < bb; ++i) z.set(i, z.get(i) * sc);
         }
     }
@@ -1812,7 +1813,7 @@ ukf_eig3_kernel(BatchState b, UkfScratch u, const int i0, const int maxc, const 
     }
     // residual |(T - lambda I) z| against |T|
     if (live && bb - a > 1) {
-        const double r = eig3::residual_inf(s.d, s.e, a, bb, lam, z, 1.0);
+        const double r = eig3::residual_inf_pf<8>(s.d, s.e, a, bb, lam, z);
         if (!(r <= 1.0e-12 * tn)) bad = true;
     }
     if (bad) s.flag[1] = 1;
@@ -1824,9 +1825,12 @@ ukf_eig3_kernel(BatchState b, UkfScratch u, const int i0, const int maxc, const 
     if (live) {
         double* row = Wg + (size_t)t * n;
         int i = 0;
-        for (; i + 3 < n; i += 4) {
-            const double v0 = z.get(i), v1 = z.get(i + 1), v2 = z.get(i + 2), v3 = z.get(i + 3);
-            row[i] = v0; row[i + 1] = v1; row[i + 2] = v2; row[i + 3] = v3;
+        for (; i + 7 < n; i += 8) {
+            double v8[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v8[q] = z.get(i + q);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) row[i + q] = v8[q];
         }
         for (; i < n; ++i) row[i] = z.get(i);
         u.dg[(size_t)t * b.batch + inst] = lam;
@@ -2957,11 +2961,14 @@ cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const St
             const bool two_pass = u.narrow && full > UKF_NARROW_WLD;
             if (gen3) {
                 // parallel eigensolver + dense S-products; the instances it declines (nswp = -2) go on to the QL route below
-                int caps[4];
-                const int ncls = u.eig3_tile ? eig3_classes(b, caps) : 0;
+                // tile classes (eig3_tile = 1: all of them; 2: only those that fit at least three times per SM -- the sizes beyond go to the
+                // global-scratch kernel, whose chains prefetch their pivots and which keeps 4 CTAs per SM at any size)
+                int caps[4], per[4];
+                int ncls = u.eig3_tile ? eig3_classes(b, caps, per) : 0;
+                if (u.eig3_tile == 2) while (ncls > 0 && per[ncls - 1] < 3) --ncls;
                 for (int c = 0; c < ncls; ++c)
                     ukf_eig3_kernel<128, true><<<i1 - i0, 128, eig3_carve(caps[c], 128, nullptr, nullptr, true), sk>>>(b, u, i0, u.maxc, 0, c ? caps[c - 1] : 0, caps[c]);
-                if (b.n_max <= 128) ukf_eig3_kernel<128, false><<<i1 - i0, 128, eig3_carve(b.n_max, 128, nullptr, nullptr), sk>>>(b, u, i0, u.maxc, ncls ? 1 : 0, 0, b.n_max);
+                if (b.n_max <= 128) ukf_eig3_kernel<128, false><<<i1 - i0, 128, eig3_carve(b.n_max, 128, nullptr, nullptr), sk>>>(b, u, i0, u.maxc, ncls ? 1 : 0, ncls ? caps[ncls - 1] : 0, b.n_max);
                 else ukf_eig3_kernel<256, false><<<i1 - i0, 256, eig3_carve(b.n_max, 256, nullptr, nullptr), sk>>>(b, u, i0, u.maxc, 0, 0, b.n_max);
                 nback += ncls;
                 if (u.multiwarp) {

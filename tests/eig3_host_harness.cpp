@@ -78,7 +78,7 @@ int main() {
         tw[t] = a;
         if (b - a == 1) { z.set(a, 1.0); continue; }
         double n2 = 1.0;
-        tw[t] = twisted_vector(d.data(), e.data(), e2.data(), a, b, xs[t], pivf, z, w, &n2);
+        tw[t] = twisted_vector_pf<8>(d.data(), e.data(), e2.data(), a, b, xs[t], pivf, z, w, &n2);
         if (!(n2 > 0.0) || !std::isfinite(n2)) bad = true;
         const double sc = 1.0 / std::sqrt(n2);
         for (int i = a; i < b; ++i) z.set(i, z.get(i) * sc);
