@@ -114,6 +114,41 @@ def test_ukf_teacher_forced_single_steps(shim, oracle):
     print("ukf teacher-forced worst", worst)
 
 
+@pytest.mark.parametrize("knobs", [(), ((17, 0),), ((17, 1),), ((15, 0),), ((15, 2),), ((10, 1),), ((7, 2),)],
+                         ids=["default", "full_square_tridiagonalisation", "packed_tridiagonalisation", "global_scratch_eigenvectors",
+                              "tile_then_global_scratch", "one_slice", "generation2"])
+def test_ukf_teacher_forced_large_states(shim, oracle, knobs):
+    """Single steps from the oracle's state LATE in a run (40+ landmarks, n = 84 .. 104): the sizes where the step takes the packed
+    tridiagonalisation, the two- and three-per-SM classes of the eigenvector tile and the largest reflector / dense-product loops
+    -- none of which the short free-running tests reach.  The oracle walks the run in STRUCTURED mode (cross-checked against the
+    dense-faithful mode elsewhere) and the compared step itself is dense-faithful."""
+    p, lm, fwd, ang = H.config2(seed=7, steps=1300, filt="ukf_slam")
+    op = H.oracle_params(oracle, p)
+    stream, _ = H.oracle_meas_stream(oracle, op, lm, fwd, ang, seed=11, instance=2)
+    of = oracle.OracleFilter(oracle.UKF_SLAM, op, 50)
+    of.init(0, 0, 0)
+    fb = shim.FilterBatch(shim.UKF_SLAM, p.to_c(), 3, 50, 8)
+    for k, v in knobs:
+        fb.tune(k, v)
+    fb.init(0, 0, 0)
+    checked, worst, sizes = 0, 0.0, set()
+    for t in range(len(fwd)):
+        if of.M >= 40 and t % 61 == 0 and checked < 8:
+            for i in range(3):
+                fb.set_state(i, of.state(), of.cov(), of.landmark_ids(), of.timestep)
+            of.update(fwd[t], ang[t], stream[t], oracle.DENSE)
+            meas, n = fb.pack_meas([stream[t], [], stream[t]])
+            fb.step(fwd[t], ang[t], meas, n)
+            worst = max(worst, _compare(fb, 0, of), _compare(fb, 2, of))
+            sizes.add(4 + 2 * of.M)
+            checked += 1
+        else:
+            of.update(fwd[t], ang[t], stream[t], oracle.STRUCTURED)
+    assert checked >= 6 and min(sizes) <= 90 and max(sizes) == 104, (checked, sizes)
+    assert (fb.all_status() == 0).all()
+    print("ukf teacher-forced large states", knobs, sorted(sizes), "worst", worst)
+
+
 def test_ukf_edge_cases(shim, oracle):
     p = H.Params(filter="ukf_slam")
     op = H.oracle_params(oracle, p)
