@@ -110,7 +110,7 @@ def test_large_map_baseline_size_teacher_forced(shim, oracle):
             early.append(t)
         seen |= ids
     assert len(early) == 3, early
-    checks = early + [T - 3, T - 2, T - 1]
+    checks = early + [2638, 2639, T - 3, T - 2, T - 1]      # 2638 / 2639: 75 and 77 detections, past the 64 / 70 updates whose operands lm_front prefetches
     t_done, worst, report = 0, 0.0, []
     for t in checks:
         if t > t_done:
@@ -139,6 +139,7 @@ def test_large_map_baseline_size_teacher_forced(shim, oracle):
     assert all(k >= 10 and j >= 1 for _, _, k, j in report[: len(early)]), report    # updates and insertions in one step
     for t, n0, k, j in report[len(early):]:
         assert n0 >= 3503 and k >= 60, (t, n0, k)                          # BASELINE size: n >= 3500, k >= 60
+    assert max(k for _, _, k, _ in report) >= 74, report                   # the in-place operand loops of lm_front (m > 64, m > 70) ran
     print("large map full size: (t, n, updates, insertions) =", report, "worst normwise err", worst)
 
 
