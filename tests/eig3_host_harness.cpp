@@ -7,6 +7,8 @@
 #include <vector>
 #include <algorithm>
 #include <cmath>
+#include <cstring>
+#include <string>
 #ifdef TRACEJ
 #define EIG3_TRACE_ROOT(j) ((j) == TRACEJ)
 #endif
@@ -14,7 +16,8 @@
 
 using namespace slam::eig3;
 
-int main() {
+int main(int argc, char** argv) {
+    const bool variants = argc > 1 && std::string(argv[1]) == "variants";
     int n = 0, maxc = 16;
     if (scanf("%d %d", &n, &maxc) != 2) return 2;
     std::vector<double> d(n), e(n, 0.0), e2(n), lam(n), xs(n);
@@ -69,6 +72,31 @@ int main() {
         double x = lam[cfirst[t]];
         for (int q = cfirst[t] + 1; q <= t; ++q) { const double lq = lam[q], pert = 10.0 * EPS * std::fabs(lq); x = (lq - x < pert) ? x + pert : lq; }
         xs[t] = x;
+    }
+    if (variants) {
+        // the four formulations of the twisted-factorisation eigenvector (two work vectors with a second backward sweep; the same
+        // with batched read-backs and parked backward pivots; one work vector; one work vector + parked pivots) must agree BITWISE
+        std::vector<double> z0(n), w0(n), z1(n), w1(n), z2(n), z3(n), g3(n);
+        long bad_bits = 0;
+        for (int t = 0; t < n; ++t) {
+            const int a = b0[t], b = b1[t];
+            if (b - a == 1) continue;
+            double n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+            std::fill(z0.begin(), z0.end(), 0.0); std::fill(z1.begin(), z1.end(), 0.0); std::fill(z2.begin(), z2.end(), 0.0); std::fill(z3.begin(), z3.end(), 0.0);
+            std::fill(w0.begin(), w0.end(), 0.0); std::fill(w1.begin(), w1.end(), 0.0);
+            const int k0 = twisted_vector(d.data(), e.data(), e2.data(), a, b, xs[t], pivf, Slot{z0.data(), 1}, Slot{w0.data(), 1}, &n0);
+            const int k1 = twisted_vector_pf<8>(d.data(), e.data(), e2.data(), a, b, xs[t], pivf, Slot{z1.data(), 1}, Slot{w1.data(), 1}, &n1);
+            const int k2 = twisted_vector1(d.data(), e.data(), e2.data(), a, b, xs[t], pivf, Slot{z2.data(), 1}, &n2);
+            const int k3 = twisted_vector1g(d.data(), e.data(), e2.data(), a, b, xs[t], pivf, Slot{z3.data(), 1}, Slot{g3.data(), 1}, &n3);
+            if (k0 != k1 || k0 != k2 || k0 != k3) ++bad_bits;
+            if (memcmp(&n0, &n1, 8) || memcmp(&n0, &n2, 8) || memcmp(&n0, &n3, 8)) ++bad_bits;
+            for (int i = a; i < b; ++i) {
+                if (memcmp(&z0[i], &z1[i], 8) || memcmp(&z0[i], &z2[i], 8) || memcmp(&z0[i], &z3[i], 8)) ++bad_bits;
+                if (memcmp(&w0[i], &w1[i], 8)) ++bad_bits;
+            }
+        }
+        printf(bad_bits ? "variants differ %ld\n" : "variants ok\n", bad_bits);
+        return 0;
     }
     std::vector<double> V((size_t)n * n, 0.0), W((size_t)n * n, 0.0);
     bool bad = false;

@@ -113,3 +113,22 @@ def test_eig3_declines_large_clusters(harness):
     lam, V, st = run(harness, d, e, maxc=32)
     assert st == "ok" and quality(d, e, lam, V)[0] <= 1e-12
     assert run(harness, *tridiag_of(np.diag([1.0, 1.0 + 1e-9, 5.0]) + 1e-3), maxc=1)[2].startswith("declined")
+
+
+def test_eig3_eigenvector_formulations_agree_bitwise(harness):
+    """twisted_vector (two work vectors, second backward sweep), twisted_vector_pf (batched read-backs, parked backward pivots),
+    twisted_vector1 (one work vector: the shared-memory tile) and twisted_vector1g (tile + parked pivots) are re-schedulings of
+    the same arithmetic: same twist index, same norm, same components and kept factors, bit for bit."""
+    rng = np.random.default_rng(5)
+    mats = []
+    A = rng.normal(size=(104, 104)); mats.append(tridiag_of(A @ A.T / 104))
+    B = rng.normal(size=(37, 37)); mats.append(tridiag_of(B @ B.T - 2.0 * np.eye(37)))
+    m = 10
+    dw = np.abs(np.arange(-m, m + 1)).astype(float)
+    mats.append((np.concatenate([dw, dw]), np.concatenate([np.ones(2 * m), [1e-7], np.ones(2 * m), [0.0]])))
+    mats.append((1 + 1e-6 * np.arange(12), np.append(1e-6 * rng.uniform(0.5, 1, 11), 0.0)))
+    for d, e in mats:
+        n = len(d)
+        txt = f"{n} 16\n" + " ".join(repr(float(v)) for v in d) + "\n" + " ".join(repr(float(v)) for v in e[: n - 1]) + "\n"
+        out = subprocess.run([harness, "variants"], input=txt, capture_output=True, text=True, check=True).stdout
+        assert out.strip().endswith("variants ok"), out
