@@ -1578,15 +1578,19 @@ __host__ __device__ inline size_t eig3_carve(const int n_max, const int nt, unsi
 // capacity, so an instance with few landmarks runs at 4 CTAs per SM and only the largest ones at 2.  One launch per class; a CTA
 // whose instance belongs to another class exits at once.  caps[k] = largest n of class k (ascending), returns the class count;
 // 0 = the variant is not used (n_max beyond what fits twice per SM, or 128 threads).
-inline int eig3_classes(const BatchState& b, int caps[4], int* per = nullptr) {
+constexpr int EIG3_MAX_CLASSES = 6;
+inline int eig3_classes(const BatchState& b, int caps[EIG3_MAX_CLASSES], int* per = nullptr, int* nts = nullptr) {
     if (b.n_max > 128) return 0;
-    static const int per_sm[3] = {4, 3, 2};        // (<= 128 registers per thread: four CTAs of 128 threads at most)
+    // up to n = 64 a CTA of 64 threads (two warps, both live) at 8 / 6 / 5 CTAs per SM; beyond, 128 threads at 4 / 3 / 2
+    // (<= 128 registers per thread)
+    static const int per_sm[6] = {8, 6, 5, 4, 3, 2}, nt_of[6] = {64, 64, 64, 128, 128, 128};
     int nc = 0, prev = 0;
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < 6; ++k) {
         const size_t budget = (size_t)(227 * 1024) / per_sm[k] - 1024;
+        const int lim = (nt_of[k] == 64) ? (b.n_max < 64 ? b.n_max : 64) : b.n_max;
         int cap = prev;
-        while (cap < b.n_max && eig3_carve(cap + 1, 128, nullptr, nullptr, true) <= budget) ++cap;
-        if (cap > prev) { if (per) per[nc] = per_sm[k]; caps[nc++] = cap; prev = cap; }
+        while (cap < lim && eig3_carve(cap + 1, nt_of[k], nullptr, nullptr, true) <= budget) ++cap;
+        if (cap > prev) { if (per) per[nc] = per_sm[k]; if (nts) nts[nc] = nt_of[k]; caps[nc++] = cap; prev = cap; }
         if (cap >= b.n_max) return nc;
     }
     return 0;                                      // the largest instances would not fit twice per SM
@@ -1649,7 +1653,7 @@ __device__ __forceinline__ void eig3_gram_schmidt(const Eig3Smem& s, double* bas
 // refinement step (nearly parallel twisted vectors; the tile keeps no factors) is flagged nswp = -4 and re-done by the
 // TILE = false kernel, launched behind this one with only_flagged = 1.
 template <int NT, bool TILE>
-__global__ void __launch_bounds__(NT, TILE ? 4 : 512 / NT)       // 128 registers: room for the batches of pivots fetched ahead of the chains
+__global__ void __launch_bounds__(NT, TILE ? 512 / NT : 512 / NT)       // 128 registers: room for the batches of pivots fetched ahead of the chains
 ukf_eig3_kernel(BatchState b, UkfScratch u, const int i0, const int maxc, const int only_flagged, const int nlo, const int ncap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Eig3Smem s;
@@ -2872,8 +2876,11 @@ cudaError_t ukf_step_configure(const BatchState& b) {
     if (b.n_max <= 256) {
         if ((e = cudaFuncSetAttribute(ukf_eig3_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig3_carve(b.n_max, 128, nullptr, nullptr))) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(ukf_eig3_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig3_carve(b.n_max, 256, nullptr, nullptr))) != cudaSuccess) return e;
-        int caps[4];
-        if (eig3_classes(b, caps) > 0 && (e = cudaFuncSetAttribute(ukf_eig3_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig3_carve(b.n_max, 128, nullptr, nullptr, true))) != cudaSuccess) return e;
+        int caps[EIG3_MAX_CLASSES];
+        if (eig3_classes(b, caps) > 0) {
+            if ((e = cudaFuncSetAttribute(ukf_eig3_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig3_carve(b.n_max, 128, nullptr, nullptr, true))) != cudaSuccess) return e;
+            if ((e = cudaFuncSetAttribute(ukf_eig3_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig3_carve(b.n_max < 64 ? b.n_max : 64, 64, nullptr, nullptr, true))) != cudaSuccess) return e;
+        }
     }
     return cudaFuncSetAttribute(ukf_ql_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ql_smem_bytes(b));
 }
@@ -2963,11 +2970,14 @@ cudaError_t launch_ukf_step(const BatchState& b, const FilterConst& fc, const St
                 // parallel eigensolver + dense S-products; the instances it declines (nswp = -2) go on to the QL route below
                 // tile classes (eig3_tile = 1: all of them; 2: only those that fit at least three times per SM -- the sizes beyond go to the
                 // global-scratch kernel, whose chains prefetch their pivots and which keeps 4 CTAs per SM at any size)
-                int caps[4], per[4];
-                int ncls = u.eig3_tile ? eig3_classes(b, caps, per) : 0;
+                int caps[EIG3_MAX_CLASSES], per[EIG3_MAX_CLASSES], nts[EIG3_MAX_CLASSES];
+                int ncls = u.eig3_tile ? eig3_classes(b, caps, per, nts) : 0;
                 if (u.eig3_tile == 2) while (ncls > 0 && per[ncls - 1] < 3) --ncls;
-                for (int c = 0; c < ncls; ++c)
-                    ukf_eig3_kernel<128, true><<<i1 - i0, 128, eig3_carve(caps[c], 128, nullptr, nullptr, true), sk>>>(b, u, i0, u.maxc, 0, c ? caps[c - 1] : 0, caps[c]);
+                for (int c = 0; c < ncls; ++c) {
+                    const size_t sm = eig3_carve(caps[c], nts[c], nullptr, nullptr, true);
+                    if (nts[c] == 64) ukf_eig3_kernel<64, true><<<i1 - i0, 64, sm, sk>>>(b, u, i0, u.maxc, 0, c ? caps[c - 1] : 0, caps[c]);
+                    else ukf_eig3_kernel<128, true><<<i1 - i0, 128, sm, sk>>>(b, u, i0, u.maxc, 0, c ? caps[c - 1] : 0, caps[c]);
+                }
                 if (b.n_max <= 128) ukf_eig3_kernel<128, false><<<i1 - i0, 128, eig3_carve(b.n_max, 128, nullptr, nullptr), sk>>>(b, u, i0, u.maxc, ncls ? 1 : 0, ncls ? caps[ncls - 1] : 0, b.n_max);
                 else ukf_eig3_kernel<256, false><<<i1 - i0, 256, eig3_carve(b.n_max, 256, nullptr, nullptr), sk>>>(b, u, i0, u.maxc, 0, 0, b.n_max);
                 nback += ncls;
