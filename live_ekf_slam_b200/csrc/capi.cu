@@ -328,8 +328,8 @@ int slam_tune(slam_handle_t h, int key, int value) {
     if (key == 0) h->cap_force = value;
     else if (key == 1) h->cap_headroom = value;
     else if (key == 2) {
-        if (value != 0 && value != 32 && value != 64 && value != 128 && value != 256 && value != 512)
-            return fail(h, "slam_tune: CTA width must be 0 (automatic), 32, 64, 128, 256 or 512");
+        if (value != 0 && value != 32 && value != 64 && value != 96 && value != 128 && value != 256 && value != 512)
+            return fail(h, "slam_tune: CTA width must be 0 (automatic), 32, 64, 96 (sweep kernel only), 128, 256 or 512");
         h->force_threads = value;
     } else if (key == 3) h->sweep_off = value;
     else if (key == 5) { if (value < 1) return fail(h, "slam_tune: the sweep chunk must be >= 1 step"); h->sweep_chunk = value; }
@@ -1084,6 +1084,7 @@ int slam_get_profile(slam_handle_t h, double* total_ms, long long* launches) {
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
         tot += ms;
+        if (getenv("SLAM_DEBUG_SWEEP")) fprintf(stderr, "profiled launch %zu: %.4f ms\n", i / 2, ms);
     }
     if (total_ms) *total_ms = tot;
     if (launches) *launches = (long long)(h->ev_used / 2);

@@ -25,6 +25,8 @@
 #include "sim_device.cuh"
 
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 
 namespace slam {
 
@@ -102,17 +104,28 @@ template <int NT>
 struct CtaSync {            // the whole CTA runs the core (ekf_step_kernel)
     static __device__ __forceinline__ void sync() { if constexpr (NT == 32) __syncwarp(); else __syncthreads(); }
 };
+// Named barriers carry their id and thread count as IMMEDIATES: with a register operand ptxas cannot tell which of the 16
+// hardware barriers a CTA uses and reserves all of them, and the SM's barrier file then caps the residency at 4 CTAs per SM
+// whatever the tile size (ncu: launch__barrier_count 16, launch__occupancy_limit_barriers 4 -- what held the sweep kernel at
+// 4 instances per SM while the map was still small).
 template <int NT, int ID>
 struct NamedSync {          // a subset of the CTA's warps runs the core (ekf_sweep_kernel consumers)
     static __device__ __forceinline__ void sync() {
-        if constexpr (NT == 32) __syncwarp(); else asm volatile("bar.sync %0, %1;" ::"r"(ID), "r"(NT) : "memory");
+        if constexpr (NT == 32) __syncwarp(); else asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NT) : "memory");
     }
 };
-__device__ __forceinline__ void named_sync(const int id, const int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void named_arrive(const int id, const int count) {
+template <int ID, int COUNT>
+__device__ __forceinline__ void named_sync_i() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+template <int ID, int COUNT>
+__device__ __forceinline__ void named_arrive_i() {
     __threadfence_block();
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+    asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
 }
+// barrier ID0 + p, p in {0, 1} known at run time only
+template <int ID0, int COUNT>
+__device__ __forceinline__ void named_sync(const int p) { if (p) named_sync_i<ID0 + 1, COUNT>(); else named_sync_i<ID0, COUNT>(); }
+template <int ID0, int COUNT>
+__device__ __forceinline__ void named_arrive(const int p) { if (p) named_arrive_i<ID0 + 1, COUNT>(); else named_arrive_i<ID0, COUNT>(); }
 
 // ---- predict scalars (ekf.cpp:43-59), one thread: F_x(0,2), F_x(1,2), cos, sin and the new vehicle pose
 __device__ __forceinline__ void ekf_predict_scalars(const FilterConst& fc, const EkfSmem& s, const float d_d, const float d_th) {
@@ -156,6 +169,58 @@ __device__ __forceinline__ void ekf_assoc_prepass(const EkfSmem& s, const int la
     if (lane == 0) { s.iscr[IS_DEAD] = dead ? 1 : 0; s.iscr[IS_OVER] = (M_run > tile_lm) ? 1 : 0; }
 }
 
+// ---- P -= K (H P) (ekf.cpp:140) on the packed lower triangle.  A plane is a flat array of 16-byte words: block (a, bc),
+// bc <= a, of plane 0 / 1 (upper / lower row of the 2x2 block) is word a (a + 1) / 2 + bc.  Every block is updated by the one
+// expression below, whatever the walk: the results do not depend on the walk or on the CTA width.
+__device__ __forceinline__ void ekf_rank2_block(double2& p0, double2& p1, const double2 klo, const double2 khi, const double2 h0,
+                                                const double2 h1) {
+    p0.x = p0.x - (klo.x * h0.x + klo.y * h1.x);
+    p0.y = p0.y - (klo.x * h0.y + klo.y * h1.y);
+    p1.x = p1.x - (khi.x * h0.x + khi.y * h1.x);
+    p1.y = p1.y - (khi.x * h0.y + khi.y * h1.y);
+}
+// one row of K = (H P)^T S^-1: (h0 i00 + h1 i10, h0 i01 + h1 i11), the roundings fixed by explicit intrinsics
+__device__ __forceinline__ double2 ekf_gain_row(const double h0, const double h1, const double (&si)[4]) {
+    return make_double2(__fma_rn(h0, si[0], __dmul_rn(h1, si[2])), __fma_rn(h0, si[1], __dmul_rn(h1, si[3])));
+}
+// Flat walk: block rows are paired (A-1-q, q) into combined rows of constant length A+1 so that a flat index walks the
+// triangle with one division at entry; consecutive threads touch consecutive 16-byte words of each plane.  Every block
+// fetches K of its row and H P of its column: 128 bytes of shared-memory traffic for 12 FP64 instructions (ncu at the
+// 50-landmark tile: the shared-memory pipe is 74 % busy, 80 % of its wavefronts come from this loop).
+// Measured and rejected (B200, configs[1], same launches otherwise): 2 x 2 super-blocks per thread (half the
+// operand loads and index arithmetic, but 32-byte lane strides = two-way bank conflicts: -18 %), column strips with H P in
+// registers and one K broadcast per block row (-13 %), two blocks in flight per trip (-5 %).  All three also slowed the
+// launches whose rank-2 pass is negligible (8-landmark tiles): the kernel's hot path is ~65 KB of SASS walked by 4-10 CTAs per
+// SM in different phases, and what grows it pays in instruction fetch (stall_no_instruction 0.6 warps per issue).
+template <int NT>
+__device__ __forceinline__ void ekf_rank2_flat(const EkfSmem& s, const int ps2, const int A /* live block rows */) {
+    const int Lc = A + 1;                           // combined row length (blocks)
+    const int Q = (A + 1) >> 1;                     // combined rows
+    const int tid = threadIdx.x;
+    int q = tid / Lc, p = tid - q * Lc;
+    const int dq = NT / Lc, dp = NT - dq * Lc;
+    const double2* K2 = reinterpret_cast<const double2*>(s.K);
+    const double2* H02 = reinterpret_cast<const double2*>(s.H0);
+    const double2* H12 = reinterpret_cast<const double2*>(s.H1);
+    double2* P0 = reinterpret_cast<double2*>(s.P);
+    double2* P1 = reinterpret_cast<double2*>(s.P + ps2);
+    while (q < Q) {
+        const int split = A - q;
+        const bool first = p < split;
+        const int a = first ? (A - 1 - q) : q;
+        const int bc = first ? p : p - split;
+        if (first || (A - 1 - q != q)) {             // the self-paired middle block row is walked once
+            const int tb = ((a * (a + 1)) >> 1) + bc;
+            const double2 klo = K2[2 * a], khi = K2[2 * a + 1];
+            const double2 h0 = H02[bc], h1 = H12[bc];
+            double2 p0 = P0[tb], p1 = P1[tb];
+            ekf_rank2_block(p0, p1, klo, khi, h0, h1);
+            P0[tb] = p0; P1[tb] = p1;
+        }
+        p += dp; q += dq;
+        if (p >= Lc) { p -= Lc; ++q; }
+    }
+}
 // ---- one reference EKF::update on the shared-memory-resident filter, executed by NT threads (threadIdx.x < NT)
 // that synchronise through Sync.  On entry (all visible): s.P / s.x / s.xs (= s.x) / s.ids hold the committed filter
 // with M landmarks, s.meas the message, s.sc the predict scalars, and -- known-ID mode -- s.assoc / s.iscr[IS_DEAD]
@@ -312,11 +377,11 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
                 }
             }
             Sync::sync();
+            const double si[4] = {s.sc[SC_I00], s.sc[SC_I00 + 1], s.sc[SC_I00 + 2], s.sc[SC_I00 + 3]};     // S^-1
             // -- O(n) phase: H P (2 x n, kept for the sweep) and K = P H^T S^-1 = (H P)^T S^-1 (n x 2)
             {
                 const double q0 = s.sc[SC_Q0], q1 = s.sc[SC_Q0 + 1], q2 = s.sc[SC_Q0 + 2], q3 = s.sc[SC_Q0 + 3];
                 const double H[10] = {-q0, -q1, 0.0, q0, q1, q2, -q3, -1.0, -q2, q3};
-                const double i00 = s.sc[SC_I00], i01 = s.sc[SC_I00 + 1], i10 = s.sc[SC_I00 + 2], i11 = s.sc[SC_I00 + 3];
                 const int np = n + 1;
                 for (int j = tid; j < np; j += NT) {
                     double h0 = 0.0, h1 = 0.0;
@@ -327,8 +392,8 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
                         h1 = H[5] * p0; h1 += H[6] * p1; h1 += H[7] * p2; h1 += H[8] * p3; h1 += H[9] * p4;
                     }
                     s.H0[j] = h0; s.H1[j] = h1;
-                    s.K[2 * j] = h0 * i00 + h1 * i10;
-                    s.K[2 * j + 1] = h0 * i01 + h1 * i11;
+                    const double2 kj = ekf_gain_row(h0, h1, si);
+                    s.K[2 * j] = kj.x; s.K[2 * j + 1] = kj.y;
                 }
             }
             Sync::sync();
@@ -341,40 +406,8 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
                     s.x[q] = xv;
                 }
             }
-            // -- P -= K (H P), :140, on the lower triangle in 2x2 blocks.  Block rows are paired (A-1-q, q) into
-            //    combined rows of constant length A+1 so that a flat index walks the triangle with one division at
-            //    entry; consecutive threads touch consecutive 16-byte words of each plane.
-            {
-                const int A = 2 + M;                            // live block rows
-                const int Lc = A + 1;                           // combined row length (blocks)
-                const int Q = (A + 1) >> 1;                     // combined rows
-                int q = tid / Lc, p = tid - q * Lc;
-                const int dq = NT / Lc, dp = NT - dq * Lc;
-                const double2* K2 = reinterpret_cast<const double2*>(s.K);
-                const double2* H02 = reinterpret_cast<const double2*>(s.H0);
-                const double2* H12 = reinterpret_cast<const double2*>(s.H1);
-                double2* P0 = reinterpret_cast<double2*>(s.P);
-                double2* P1 = reinterpret_cast<double2*>(s.P + ps2);
-                while (q < Q) {
-                    const int split = A - q;
-                    const bool first = p < split;
-                    const int a = first ? (A - 1 - q) : q;
-                    const int bc = first ? p : p - split;
-                    if (first || (A - 1 - q != q)) {             // the self-paired middle block row is walked once
-                        const int tb = ((a * (a + 1)) >> 1) + bc;
-                        const double2 klo = K2[2 * a], khi = K2[2 * a + 1];
-                        const double2 h0 = H02[bc], h1 = H12[bc];
-                        double2 p0 = P0[tb], p1 = P1[tb];
-                        p0.x = p0.x - (klo.x * h0.x + klo.y * h1.x);
-                        p0.y = p0.y - (klo.x * h0.y + klo.y * h1.y);
-                        p1.x = p1.x - (khi.x * h0.x + khi.y * h1.x);
-                        p1.y = p1.y - (khi.x * h0.y + khi.y * h1.y);
-                        P0[tb] = p0; P1[tb] = p1;
-                    }
-                    p += dp; q += dq;
-                    if (p >= Lc) { p -= Lc; ++q; }
-                }
-            }
+            // -- P -= K (H P), :140, on the lower triangle
+            ekf_rank2_flat<NT>(s, ps2, 2 + M);
             Sync::sync();
         } else {
             // -------- landmark insertion, :141-173: one new block row (padded rows np, np+1)
@@ -543,7 +576,7 @@ __device__ __forceinline__ bool ekf_instance(const BatchState& b, const FilterCo
 
 // resident CTAs the register allocation must allow: about 768 threads per SM (<= 80 registers per thread)
 constexpr int step_min_blocks(int threads) { return threads >= 512 ? 1 : 768 / threads; }
-constexpr int sweep_min_blocks(int cw) { return cw == 1 ? 12 : cw == 2 ? 8 : cw == 4 ? 4 : 2; }   // (cw == 4 at 6 blocks / 64 registers measured slower: 113.8 -> 101 M updates/s)
+constexpr int sweep_min_blocks(int cw) { return cw == 1 ? 12 : cw == 2 ? 8 : cw == 3 ? 6 : cw == 4 ? 4 : 2; }   // (cw == 4 at 6 blocks / 64 registers measured slower: 113.8 -> 101 M updates/s)
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, step_min_blocks(THREADS))
@@ -660,11 +693,11 @@ ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, SweepA
                         if (lane == 0) w.nm[p] = nm_last;
                         trp[p][0] = tr[0]; trp[p][1] = tr[1]; trp[p][2] = tr[2];
                     }
-                    named_arrive(BAR_FULL0 + p, THREADS);
+                    named_arrive<BAR_FULL0, THREADS>(p);
                 }
                 if (t >= 1) {
                     const int q = (t - 1) & 1;
-                    named_sync(BAR_DONE0 + q, THREADS);          // step t-1 finished: snapshot[q] valid
+                    named_sync<BAR_DONE0, THREADS>(q);          // step t-1 finished: snapshot[q] valid
                     if (w.nm[2]) { aborted = true; break; }
                     const double* sn = w.snap + 12 * q;
                     if (REPLAY) {
@@ -707,7 +740,7 @@ ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, SweepA
             for (int t = 0; t < T; ++t) {
                 const int p = t & 1;
                 const bool frozen = (status & SLAM_STATUS_SAME_STEP_REMATCH) != 0;
-                named_sync(BAR_FULL0 + p, THREADS);              // message of step t is in w.meas[p]
+                named_sync<BAR_FULL0, THREADS>(p);              // message of step t is in w.meas[p]
                 nm = w.nm[p];
                 if (nm > b.max_meas) { nm = b.max_meas; status |= SLAM_STATUS_MEAS_OVERFLOW; }
                 if (!frozen) {
@@ -722,8 +755,8 @@ ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, SweepA
                         // the tile of this launch cannot take the insertions of this step: abort the chunk untouched
                         aborted = true;
                         if (tid == 0) w.nm[2] = 1;
-                        named_arrive(BAR_DONE0 + p, THREADS);
-                        if (t + 1 < T) named_sync(BAR_FULL0 + ((t + 1) & 1), THREADS);   // drain the message already under way
+                        named_arrive<BAR_DONE0, THREADS>(p);
+                        if (t + 1 < T) named_sync<BAR_FULL0, THREADS>((t + 1) & 1);   // drain the message already under way
                         break;
                     }
                     int n_upd = 0;
@@ -734,7 +767,7 @@ ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, SweepA
                 }
                 // pose snapshot for the per-step outputs (the producer consumes it while the next step runs)
                 if (tid < 12) w.snap[12 * p + tid] = (tid < 3) ? s.x[tid] : s.P[bpl_sym((tid - 3) / 3 + 1, (tid - 3) % 3 + 1, ps2)];
-                named_arrive(BAR_DONE0 + p, THREADS);
+                named_arrive<BAR_DONE0, THREADS>(p);
             }
             if (!aborted) {
                 // ---- commit the instance
@@ -878,12 +911,14 @@ cudaError_t ekf_step_configure(const BatchState& b) {
     const int sbytes = L.sweep_bytes;
     if ((e = set_smem_sweep<1>(sbytes)) != cudaSuccess) return e;
     if ((e = set_smem_sweep<2>(sbytes)) != cudaSuccess) return e;
+    if ((e = set_smem_sweep<3>(sbytes)) != cudaSuccess) return e;
     if ((e = set_smem_sweep<4>(sbytes)) != cudaSuccess) return e;
     return set_smem_sweep<8>(sbytes);
 }
 
 static cudaError_t launch_step_threads(int threads, int grid, size_t smem, cudaStream_t st, const BatchState& b,
                                        const FilterConst& fc, const StepInputs& in, int phases, const EkfLaunch& L) {
+    if (threads == 96) threads = 128;          // 96 (three filter warps) exists for the sweep kernel only
     switch (threads) {
         case 32: ekf_step_kernel<32><<<grid, 32, smem, st>>>(b, fc, in, phases, L); break;
         case 64: ekf_step_kernel<64><<<grid, 64, smem, st>>>(b, fc, in, phases, L); break;
@@ -938,19 +973,34 @@ static cudaError_t launch_sweep_t(const BatchState& b, const FilterConst& fc, co
     cudaError_t e = cudaMemsetAsync(a.work_counter, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     // filter warps per instance: the count that keeps the most instances resident per SM; among equals the widest
-    const int cws[4] = {1, 2, 4, 8};
-    const int occ[4] = {sweep_occupancy<1, REPLAY>(smem), sweep_occupancy<2, REPLAY>(smem), sweep_occupancy<4, REPLAY>(smem),
-                        sweep_occupancy<8, REPLAY>(smem)};
-    int best = 0;
-    for (int k = 1; k < 4; ++k) if (occ[k] >= occ[best]) best = k;
-    if (force_threads == 32) best = 0; else if (force_threads == 64) best = 1; else if (force_threads == 128) best = 2;
-    else if (force_threads >= 256) best = 3;
+    const int cws[5] = {1, 2, 3, 4, 8};
+    const int occ[5] = {sweep_occupancy<1, REPLAY>(smem), sweep_occupancy<2, REPLAY>(smem), sweep_occupancy<3, REPLAY>(smem),
+                        sweep_occupancy<4, REPLAY>(smem), sweep_occupancy<8, REPLAY>(smem)};
+    // Filter warps per instance by tile size.  Measured per chunk on B200 (4096 instances, profiles/r02p_sweep_chunks.txt): up
+    // to ~20 landmarks one warp with 10 instances per SM (the barrier file allows 64 / 6) wins, to ~38 two warps x 8 (7), to ~42
+    // three warps x 6, beyond it four warps x 4 (the rank-2 pass grows with n^2 and wants lanes; residency stops paying once the
+    // shared-memory pipe is ~3/4 busy).  A batch that fits the SMs at a wider CTA takes the wider CTA.
+    int best = L.cap_lm <= 20 ? 0 : L.cap_lm <= 38 ? 1 : L.cap_lm <= 42 ? 2 : 3;
+    const int sms_ = device_sm_count();
+    while (best < 3 && occ[best + 1] > 0 && b.batch <= sms_ * occ[best + 1]) ++best;
+    if (occ[best] <= 0) { best = 0; for (int k = 1; k < 5; ++k) if (occ[k] >= occ[best]) best = k; }
+    if (force_threads == 32) best = 0; else if (force_threads == 64) best = 1; else if (force_threads == 96) best = 2;
+    else if (force_threads == 128) best = 3; else if (force_threads >= 256) best = 4;
     const int per_sm = occ[best] > 0 ? occ[best] : 1;
     const int sms = device_sm_count();
-    const int grid = b.batch < sms * per_sm ? b.batch : sms * per_sm;
+    static const bool dbg = getenv("SLAM_DEBUG_SWEEP") != nullptr;
+    if (dbg) fprintf(stderr, "sweep launch: cap_lm %d smem %zu occ {%d,%d,%d,%d,%d} -> CW %d x %d per SM (t0 %d T %d)\n", L.cap_lm, smem,
+                     occ[0], occ[1], occ[2], occ[3], occ[4], cws[best], per_sm, a.t0, a.T);
+    // The persistent grid drains the batch in ceil(batch / resident CTAs) rounds; launching just the CTAs that many rounds
+    // need (4096 instances, 10 per SM: 1366 CTAs instead of 1480 for the same 3 rounds) leaves the tail round full and the
+    // others less crowded.
+    int grid = b.batch < sms * per_sm ? b.batch : sms * per_sm;
+    static const bool balance = getenv("SLAM_SWEEP_NO_BALANCE") == nullptr;
+    if (balance && grid < b.batch) { const int rounds = (b.batch + grid - 1) / grid; grid = (b.batch + rounds - 1) / rounds; }
     switch (cws[best]) {
         case 1: sweep_go<1, REPLAY>(grid, smem, st, b, fc, sim, sc, a, L); break;
         case 2: sweep_go<2, REPLAY>(grid, smem, st, b, fc, sim, sc, a, L); break;
+        case 3: sweep_go<3, REPLAY>(grid, smem, st, b, fc, sim, sc, a, L); break;
         case 4: sweep_go<4, REPLAY>(grid, smem, st, b, fc, sim, sc, a, L); break;
         default: sweep_go<8, REPLAY>(grid, smem, st, b, fc, sim, sc, a, L); break;
     }

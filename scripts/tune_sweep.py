@@ -1,4 +1,4 @@
-"""Scratch: sweep-kernel tuning grid (chunk length, tile headroom, CTA width) on configs[1]."""
+"""Scratch: sweep-kernel tuning grid (chunk length, tile headroom) on configs[1]; SLAM_SWEEP_NO_BALANCE=1 for the unbalanced grid."""
 import sys
 import time
 
@@ -12,7 +12,7 @@ fb = shim.FilterBatch(shim.EKF_SLAM, p.to_c(), B, 50, 8)
 sim = shim.Simulator(fb, lm, seed=1)
 
 
-def run(chunk, head, thr, reps=3):
+def run(chunk, head, thr=0, reps=4):
     fb.tune(5, chunk); fb.tune(6, head); fb.tune(2, thr)
     best = 1e9
     for _ in range(reps):
@@ -22,9 +22,10 @@ def run(chunk, head, thr, reps=3):
     print(f"chunk {chunk:4d} headroom {head:2d} threads {thr:3d}: {best*1e3:7.2f} ms  {B*T/best/1e6:7.2f} M updates/s", flush=True)
 
 
-for chunk in (8, 16, 32, 64, 128, 1000):
-    run(chunk, 8, 0)
-for head in (2, 4, 6, 12, 50):
-    run(32, head, 0)
-for thr in (32, 64, 128, 256):
-    run(32, 8, thr)
+run(32, 8)
+for chunk in (16, 24, 40, 48, 64):
+    run(chunk, 8)
+for head in (2, 4, 6, 10, 12):
+    run(32, head)
+for chunk, head in ((16, 4), (24, 4), (24, 6), (48, 10), (16, 6)):
+    run(chunk, head)
