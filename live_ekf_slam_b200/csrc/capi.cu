@@ -46,7 +46,7 @@ struct slam_filter {
     int cap_force = 0;                // > 0: force this capacity for the first pass (tests of the retry path)
     int force_threads = 0;            // > 0: CTA width of the EKF kernels (tuning)
     int sweep_off = 0;                // 1: slam_run* always uses per-step launches (tests compare both paths)
-    int sweep_chunk = 32;             // steps per launch of the persistent sweep kernel
+    int sweep_chunk = 48;             // steps per launch of the persistent sweep kernel (B200, configs[1]: 16 / 24 / 32 / 48 / 64 steps -> 123 / 128 / 130 / 133 / 129 M updates/s)
     int sweep_headroom = 8;           // landmarks of slack on top of the stale max(M) when sizing a chunk's tile
     int* d_work = nullptr;            // [2] work counters of the sweep kernel (tile-sized launch, full-capacity launch)
     int* d_progress = nullptr;        // [batch] run-relative steps completed (chunk gate of the sweep kernel)

@@ -226,7 +226,7 @@ __device__ __forceinline__ void ekf_rank2_flat(const EkfSmem& s, const int ps2, 
 // with M landmarks, s.meas the message, s.sc the predict scalars, and -- known-ID mode -- s.assoc / s.iscr[IS_DEAD]
 // the pre-pass.  Returns true when the step was applied; false when the instance died (same-step re-match): in
 // known-ID mode nothing has been modified then, in unknown-ID mode the shared-memory state must be discarded.
-template <int NT, class Sync>
+template <int NT, class Sync, bool KNOWN_ONLY = false>
 __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s, const int ps2, const int max_lm,
                                          const int phases, int& M, const int nm, int& status, int& n_upd) {
     constexpr int WARPS = NT / 32;
@@ -235,8 +235,10 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
     const bool nu_thread = (warp == NUW) && (lane == 0);
     const int M_start = M;
     n_upd = 0;
+    // (the sweep kernel runs known-ID batches only: KNOWN_ONLY compiles the box gate and its trigonometry out of its hot path)
+    const bool id_known = KNOWN_ONLY || fc.id_known;
 
-    if ((phases & STEP_UPDATE) && fc.id_known && s.iscr[IS_DEAD]) { status |= SLAM_STATUS_SAME_STEP_REMATCH; return false; }
+    if ((phases & STEP_UPDATE) && id_known && s.iscr[IS_DEAD]) { status |= SLAM_STATUS_SAME_STEP_REMATCH; return false; }
 
     // ---- PREDICT, ekf.cpp:43-61.  T = F_x P (rows 0,1 pick up row 2), P' = T F_x^T (cols 0,1 pick up col 2)
     //      + (F_v V) F_v^T on the vehicle block.  In the lower triangle only the column form exists for j >= 3:
@@ -288,7 +290,7 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
         const float r = s.meas[3 * l + 1], bb = s.meas[3 * l + 2];
         const int n = 3 + 2 * M;
         int slot, id;
-        if (fc.id_known) {
+        if (id_known) {
             slot = s.assoc[l];
             id = (int)s.meas[3 * l];
             if (slot == ASSOC_DROPPED) { status |= SLAM_STATUS_CAPACITY; continue; }
@@ -411,7 +413,7 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
             Sync::sync();
         } else {
             // -------- landmark insertion, :141-173: one new block row (padded rows np, np+1)
-            if (fc.id_known) {
+            if (id_known) {
                 if (nu_thread) {
                     double sb, cb; sincos(s.x[2] + (double)bb, &sb, &cb);
                     s.sc[SC_CB] = cb; s.sc[SC_SB] = sb;
@@ -760,7 +762,7 @@ ekf_sweep_kernel(BatchState b, FilterConst fc, SimState sim, SimConst sc, SweepA
                         break;
                     }
                     int n_upd = 0;
-                    if (ekf_core<NT, Sync>(fc, s, ps2, b.max_lm, STEP_PREDICT | STEP_UPDATE, M, nm, status, n_upd)) {
+                    if (ekf_core<NT, Sync, true>(fc, s, ps2, b.max_lm, STEP_PREDICT | STEP_UPDATE, M, nm, status, n_upd)) {
                         ++timestep;
                         if (tid == 0) ekf_work_terms(3 + 2 * M, nm, n_upd, wacc);
                     }
@@ -991,12 +993,9 @@ static cudaError_t launch_sweep_t(const BatchState& b, const FilterConst& fc, co
     static const bool dbg = getenv("SLAM_DEBUG_SWEEP") != nullptr;
     if (dbg) fprintf(stderr, "sweep launch: cap_lm %d smem %zu occ {%d,%d,%d,%d,%d} -> CW %d x %d per SM (t0 %d T %d)\n", L.cap_lm, smem,
                      occ[0], occ[1], occ[2], occ[3], occ[4], cws[best], per_sm, a.t0, a.T);
-    // The persistent grid drains the batch in ceil(batch / resident CTAs) rounds; launching just the CTAs that many rounds
-    // need (4096 instances, 10 per SM: 1366 CTAs instead of 1480 for the same 3 rounds) leaves the tail round full and the
-    // others less crowded.
-    int grid = b.batch < sms * per_sm ? b.batch : sms * per_sm;
-    static const bool balance = getenv("SLAM_SWEEP_NO_BALANCE") == nullptr;
-    if (balance && grid < b.batch) { const int rounds = (b.batch + grid - 1) / grid; grid = (b.batch + rounds - 1) / rounds; }
+    // (launching only the CTAs that ceil(batch / resident CTAs) rounds need -- 1366 instead of 1480 at 10 per SM -- measured
+    // slower, 130.1 -> 126.9 M updates/s: the work counter already evens the rounds out)
+    const int grid = b.batch < sms * per_sm ? b.batch : sms * per_sm;
     switch (cws[best]) {
         case 1: sweep_go<1, REPLAY>(grid, smem, st, b, fc, sim, sc, a, L); break;
         case 2: sweep_go<2, REPLAY>(grid, smem, st, b, fc, sim, sc, a, L); break;

@@ -1,7 +1,7 @@
 """gpurun_out/traffic/{which}.csv (ncu) + {which}_probe.json -> profiles/ncu_traffic.json (read by bench.py's roofline.traffic)"""
 import csv, json, os, sys
 names = {"step": ["ekf_step_kernel"], "sweep": ["ekf_sweep_kernel"], "gemm": ["lm_gemm"], "ukf": ["ukf_front2_kernel", "ukf_eig3_kernel", "ukf_back3_kernel"]}
-out = {}
+out = json.load(open("profiles/ncu_traffic.json")) if os.path.exists("profiles/ncu_traffic.json") else {}     # entries without a new capture are kept
 for which, kernels in names.items():
     c, pj = f"gpurun_out/traffic/{which}.csv", f"gpurun_out/traffic/{which}_probe.json"
     if not (os.path.exists(c) and os.path.exists(pj)):

@@ -22,8 +22,8 @@ if which in ("step", "sweep", "ukf"):
     lm = wl.grid_map_5x10()
     fwd, ang = wl.tsp_trajectory(lm, p, rng, 1000)
     if which == "sweep":
-        S = 28 * 32                   # chunk 28 of 32 steps
-        sel = ("ekf_sweep_kernel", 2 * 28, "chunk 28 (filter steps 896..927) of the 4096-instance sweep; first (tile-sized) launch of the chunk")
+        S = 18 * 48                   # chunk 18 of 48 steps (the library's default chunk length)
+        sel = ("ekf_sweep_kernel", None, "chunk 18 (filter steps 864..911) of the 4096-instance sweep (full-capacity tile: one launch)")
     elif which == "step":
         sel = ("ekf_step_kernel", 2 * S, "filter step 900 of the 4096-instance sweep, per-step path (first-pass launch)")
     else:
@@ -40,7 +40,7 @@ if which in ("step", "sweep", "ukf"):
     sim.run(fwd[:S], ang[:S], first_step=0)
     s0 = fb.stats()
     l0 = fb.kernel_launches
-    nstep = 32 if which == "sweep" else 1
+    nstep = 48 if which == "sweep" else 1
     sim.run(fwd[S:S + nstep], ang[S:S + nstep], first_step=S)
     fb.synchronize()
     l1 = fb.kernel_launches
