@@ -117,6 +117,9 @@ __device__ __forceinline__ float sin_f(float x) { return (float)sin((double)x); 
 // common case on the filter path.  Otherwise n' = rint(a / 2pi) and r = fma(-n', 2pi, a): whenever |r| is clearly
 // below pi, n' is the integer nearest to a / 2pi, so a - n' 2pi IS the IEEE remainder, which is representable, and the
 // fma (exact product, one rounding) returns it exactly.  Anything near the +-pi boundary goes to the library routine.
+// (the library routine stays out of line: its loop inlined at every call site grows the kernels' hot paths, which the
+// persistent EKF kernel pays for in instruction fetch)
+static __device__ __noinline__ double wrap_2pi_library(double a) { return remainder(a, TWO_PI_REF); }
 __device__ __forceinline__ double wrap_2pi(double a) {
     if (fabs(a) <= PI_REF) return a;
     if (fabs(a) < 1.0e6) {
@@ -124,7 +127,7 @@ __device__ __forceinline__ double wrap_2pi(double a) {
         const double r = fma(-n, TWO_PI_REF, a);
         if (fabs(r) < 3.1415) return r;
     }
-    return remainder(a, TWO_PI_REF);
+    return wrap_2pi_library(a);
 }
 
 // ---------------------------------------------------------------------------------------------

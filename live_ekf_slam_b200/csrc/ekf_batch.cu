@@ -150,15 +150,24 @@ __device__ __forceinline__ void ekf_assoc_prepass(const EkfSmem& s, const int la
                                                   const int tile_lm) {
     int M_run = M;
     bool dead = false;
+#ifdef EKF_X1
+#pragma unroll 1
+#endif
     for (int l = 0; l < nm; ++l) {
         const int id = (int)s.meas[3 * l];                                 // :101
         int cand = INT_MAX;
+#ifdef EKF_X1
+#pragma unroll 1
+#endif
         for (int j = lane; j < M; j += 32)
             if (s.ids[j] == id) { cand = j; break; }
         cand = __reduce_min_sync(0xffffffffu, cand);                       // first match in ascending slot order
         int code = cand;
         if (cand == INT_MAX) {
             bool dup = false;
+#ifdef EKF_X1
+#pragma unroll 1
+#endif
             for (int q = lane; q < l; q += 32) dup |= (s.assoc[q] == ASSOC_NEW) && ((int)s.meas[3 * q] == id);
             if (__any_sync(0xffffffffu, dup)) { dead = true; break; }
             if (M_run < max_lm) { code = ASSOC_NEW; ++M_run; } else code = ASSOC_DROPPED;
