@@ -330,9 +330,12 @@ def measure_batch(cx: Ctx, filt: str, B: int, T: int, K: int, W: int, warm_T: in
         roofline = {"bound": "hbm", "kernel": "ekf_sweep_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "peak_source": peak_src,
                     "real_limiter": "NOT HBM: P is resident in shared memory for the steps of a launch (DRAM busy ~2 % in the ncu "
-                                    "capture); the kernel is bound by barrier / dependent-FP64 latency and shared-memory issue. "
-                                    "`frac` is the contract's streaming-equivalent figure (what a per-step streaming design would "
-                                    "have had to move), it can exceed 1 and is not an HBM utilisation",
+                                    "capture). One instance-step is a ~6.5 us chain of dependent scalar FP64 work (sincos, sqrt, "
+                                    "divisions, atan2), so throughput = resident instances per SM / that latency (10 one-warp CTAs per "
+                                    "SM on small tiles .. 4 four-warp CTAs at the full map) until the shared-memory pipe saturates "
+                                    "(ncu at the 50-landmark tile: l1tex shared-memory wavefronts 74 % of peak, issue slots 46 %, FP64 "
+                                    "pipe 18 %). `frac` is the contract's streaming-equivalent figure (what a per-step streaming design "
+                                    "would have had to move), it can exceed 1 and is not an HBM utilisation",
                     "moved_model_gbs": loc2[12] / (s_ms * 1e-3) / 1e9 if s_ms > 0 else 0.0,
                     "hbm_utilisation_model": loc2[12] / (s_ms * 1e-3) / 1e9 / peak if s_ms > 0 else 0.0,
                     "fp64_frac": {"executed_model_tflops": loc2[13] / (s_ms * 1e-3) / 1e12, "algorithmic_tflops": loc2[9] / (s_ms * 1e-3) / 1e12,

@@ -150,24 +150,18 @@ __device__ __forceinline__ void ekf_assoc_prepass(const EkfSmem& s, const int la
                                                   const int tile_lm) {
     int M_run = M;
     bool dead = false;
-#ifdef EKF_X1
 #pragma unroll 1
-#endif
     for (int l = 0; l < nm; ++l) {
         const int id = (int)s.meas[3 * l];                                 // :101
         int cand = INT_MAX;
-#ifdef EKF_X1
 #pragma unroll 1
-#endif
         for (int j = lane; j < M; j += 32)
             if (s.ids[j] == id) { cand = j; break; }
         cand = __reduce_min_sync(0xffffffffu, cand);                       // first match in ascending slot order
         int code = cand;
         if (cand == INT_MAX) {
             bool dup = false;
-#ifdef EKF_X1
 #pragma unroll 1
-#endif
             for (int q = lane; q < l; q += 32) dup |= (s.assoc[q] == ASSOC_NEW) && ((int)s.meas[3 * q] == id);
             if (__any_sync(0xffffffffu, dup)) { dead = true; break; }
             if (M_run < max_lm) { code = ASSOC_NEW; ++M_run; } else code = ASSOC_DROPPED;
@@ -634,7 +628,9 @@ ekf_step_kernel(BatchState b, FilterConst fc, StepInputs in, int phases, EkfLaun
 // Known-ID mode only (the host falls back to per-step launches otherwise): the pre-pass association detects a
 // same-step re-match before the step touches anything, so a dead instance stays at its committed state.
 // ------------------------------------------------------------------------------------------------------------
-enum { BAR_CONS = 1, BAR_FULL0 = 2, BAR_FULL1 = 3, BAR_DONE0 = 4, BAR_DONE1 = 5 };
+// (BAR_CONS is the highest id: the one-warp variant synchronises its filter threads with __syncwarp and never names it, so it
+// holds 5 hardware barriers instead of 6 and 12 instead of 10 of its CTAs fit the SM's barrier file)
+enum { BAR_FULL0 = 1, BAR_FULL1 = 2, BAR_DONE0 = 3, BAR_DONE1 = 4, BAR_CONS = 5 };
 
 struct SweepSmem {
     float* meas[2];     // [max_meas][3] message of step parity p

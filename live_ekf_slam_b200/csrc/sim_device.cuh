@@ -26,9 +26,6 @@ __device__ __forceinline__ int sim_get_cmd_warp(const int lane, const SimConst& 
     const double tx = tr[0] + d * cy, ty = tr[1] + d * sy, tyaw = tr[2] + hdg;   // :222 (yaw never wrapped)
     tr[0] = tx; tr[1] = ty; tr[2] = tyaw;
     int count = 0;
-#ifdef EKF_X2
-#pragma unroll 1
-#endif
     for (int base = 0; base < n_lm; base += 32) {
         const int id = base + lane;
         bool vis = false;

@@ -1,0 +1,6 @@
+#!/bin/bash
+set -u
+O=gpurun_out/r02x
+mkdir -p $O
+SLAM_DEBUG_SWEEP=1 timeout 600 python scripts/sweep_chunks.py 0 32 64 > $O/chunks.txt 2> $O/chunks.err
+cut -c1-60 $O/chunks.txt
