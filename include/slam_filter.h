@@ -223,8 +223,9 @@ int  slam_build_info(char* buf, int cap);             /* arch, compile flags */
 int  slam_get_ukf_routes(slam_handle_t h, long long* out /* 3 */);
 /* tuning / test knobs.  key 0: force the shared-memory landmark capacity of the first pass (0 = automatic;
  * instances that do not fit are drained by the full-capacity retry pass); key 1: headroom (landmarks) added to
- * the stale max(M) hint of the per-step launches; key 2: CTA width of the EKF kernels (0 = automatic); key 3: 1 =
- * slam_run* uses per-step launches instead of the persistent sweep kernel; key 5: steps per sweep-kernel launch;
+ * the stale max(M) hint of the per-step launches; key 2: CTA width of the EKF kernels (0 = automatic: by tile size; 32 / 64 / 128 / 256 / 512, and 96 =
+ * three filter warps, sweep kernel only); key 3: 1 = slam_run* uses per-step launches instead of the persistent sweep kernel;
+ * key 5: steps per sweep-kernel launch (default 48);
  * key 6: headroom of the sweep kernel's tile; key 7: UKF step generation (3 = parallel tridiagonal eigensolver + dense products
  * with its eigenvectors, default; 2 = QL rotation log replayed on the vectors, warp per instance; 1 = explicit eigenvector matrix,
  * CTA per instance); key 12: largest cluster of close eigenvalues the generation-3 eigensolver re-orthogonalises itself (larger

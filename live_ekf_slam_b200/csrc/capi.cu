@@ -454,7 +454,7 @@ static int do_step(slam_filter* h, const float* d_fwd, const float* d_ang, int c
         CK(cudaEventRecord(h->hint_ev[slot], h->stream));
         h->step_seq += 1;
     }
-    if (h->kind == SLAM_EKF_SLAM) h->launches += (cap < h->b.max_lm || posted_hint) ? 2 : 1;
+    if (h->kind == SLAM_EKF_SLAM) h->launches += (cap > 0 && cap < h->b.max_lm) ? 2 : 1;      // (a capacity-limited launch is followed by its retry pass)
     return 0;
 }
 

@@ -945,7 +945,10 @@ cudaError_t launch_ekf_step(const BatchState& b, const FilterConst& fc, const St
     const size_t smem = (size_t)L.smem_bytes;
     // (the deferred-instance counter is re-armed by the retry pass itself: no memset on the stream)
     cudaError_t e = launch_step_threads(force_threads ? force_threads : pick_threads(smem, nullptr), b.batch, smem, st, b, fc, in, phases, L);
-    if (e != cudaSuccess || (!limited && !b.hint_host)) return e;      // (the retry pass also posts the capacity hint)
+    // A full-capacity launch defers nothing, and the hint the retry pass would post is not needed any more either: max(M) only
+    // grows between resets, so once hint + headroom reaches max_lm every later launch is a full-capacity one (the posted word keeps
+    // its last value; slam_reset zeroes it).  Skipping the empty pass takes ~4 us off every such tick.
+    if (e != cudaSuccess || !limited) return e;
     const EkfLaunch R = make_launch(b, b.max_lm, 1);
     const size_t rsmem = (size_t)R.smem_bytes;
     int per_sm = 1;
