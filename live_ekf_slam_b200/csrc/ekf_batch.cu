@@ -192,7 +192,8 @@ __device__ __forceinline__ double2 ekf_gain_row(const double h0, const double h1
 // 50-landmark tile: the shared-memory pipe is 74 % busy, 80 % of its wavefronts come from this loop).
 // Measured and rejected (B200, configs[1], same launches otherwise): 2 x 2 super-blocks per thread (half the
 // operand loads and index arithmetic, but 32-byte lane strides = two-way bank conflicts: -18 %), column strips with H P in
-// registers and one K broadcast per block row (-13 %), two blocks in flight per trip (-5 %).  All three also slowed the
+// registers and one K broadcast per block row (-13 %; with the next row's loads issued ahead of the stores -30 %: a warp
+// per block row serialises A / warps row trips), two blocks in flight per trip (-5 %).  All three also slowed the
 // launches whose rank-2 pass is negligible (8-landmark tiles): the kernel's hot path is ~65 KB of SASS walked by 4-10 CTAs per
 // SM in different phases, and what grows it pays in instruction fetch (stall_no_instruction 0.6 warps per issue).
 template <int NT>
