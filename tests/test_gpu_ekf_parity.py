@@ -305,11 +305,12 @@ def test_cta_widths_agree_with_oracle(shim, oracle, threads):
     assert max(o.M for o in ofs) >= 5
 
 
-@pytest.mark.parametrize("threads,chunk,cap", [(0, 32, 0), (512, 1000, 0), (32, 7, 0), (64, 50, 3), (128, 16, 12)])
+@pytest.mark.parametrize("threads,chunk,cap", [(0, 32, 0), (512, 1000, 0), (32, 7, 0), (64, 50, 3), (128, 16, 12), (96, 48, 0), (96, 20, 5)])
 def test_sweep_kernel_matches_per_step_launches(shim, oracle, threads, chunk, cap):
     """slam_run on a known-ID EKF batch runs on the persistent ekf_sweep_kernel (simulator + filter + error terms, P
     resident in shared memory for a chunk of steps per launch, tile sized from the landmarks held so far).  Whatever
-    the chunk length, the CTA width and the tile capacity (cap > 0 forces small tiles: instances that outgrow them
+    the chunk length, the CTA width (32 .. 512 threads = 1, 2, 4, 8 filter warps; 96 = the three-warp variant that exists for
+    the sweep kernel only; 0 = by tile size) and the tile capacity (cap > 0 forces small tiles: instances that outgrow them
     abort the chunk untouched and are redone by the full-capacity launch), it must reproduce the per-step launch
     sequence: same association log, landmark ids, messages, truth, statistics; state and covariance to rounding."""
     p, lm, fwd, ang = H.config2(seed=4, steps=260)
