@@ -16,7 +16,7 @@ tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
 cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 dis = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
-own = os.path.basename(obj).replace(".o", ".cu")
+own = os.environ.get("OWN") or os.path.basename(obj).replace(".o", ".cu")
 sections, name, frames = collections.OrderedDict(), None, []
 for ln in dis:
     m = re.match(r"\s*\.text\.(\S+):", ln)
