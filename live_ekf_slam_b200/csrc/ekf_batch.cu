@@ -186,50 +186,41 @@ __device__ __forceinline__ void ekf_rank2_block(double2& p0, double2& p1, const 
 __device__ __forceinline__ double2 ekf_gain_row(const double h0, const double h1, const double (&si)[4]) {
     return make_double2(__fma_rn(h0, si[0], __dmul_rn(h1, si[2])), __fma_rn(h0, si[1], __dmul_rn(h1, si[3])));
 }
-// Flat walk: block rows are paired (A-1-q, q) into combined rows of constant length A+1 so that a flat index walks the
-// triangle with one division at entry; consecutive threads touch consecutive 16-byte words of each plane.  Every block
-// fetches K of its row and H P of its column: 128 bytes of shared-memory traffic for 12 FP64 instructions (ncu at the
-// 50-landmark tile: the shared-memory pipe is 74 % busy, 80 % of its wavefronts come from this loop).
+// Flat walk: thread t takes the words t, t + NT, ... of the triangle in STORAGE order, so the lanes of a warp always touch 32
+// consecutive 16-byte words of each plane (no bank conflicts, also where a warp straddles block rows -- the earlier walk over
+// paired block rows (A-1-q, q) split a warp into runs at unrelated addresses: 17 % excess shared-memory wavefronts at the
+// 50-landmark tile, where that pipe is 74 % busy).  The block row of word t is a = floor((sqrt(8 t + 1) - 1) / 2); with 1.5 in
+// place of 1 under an APPROXIMATE square root (MUFU.SQRT, relative error ~2^-22) the truncation is exact for every t the
+// batched tiles can hold: a row's first word has sqrt(8 t + 1) = 2 a + 1 exactly and the half pushes it ~1e-3 above the
+// integer, a row's last word stays ~0.017 below the next one (checked exhaustively on the host for A <= 120).  Every block
+// fetches K of its row (a broadcast within the row) and H P of its column: 128 bytes of shared-memory traffic for 12 FP64
+// instructions (80 % of the kernel's shared-memory wavefronts at the full map).
 // Measured and rejected (B200, configs[1], same launches otherwise): 2 x 2 super-blocks per thread (half the
 // operand loads and index arithmetic, but 32-byte lane strides = two-way bank conflicts: -18 %), column strips with H P in
 // registers and one K broadcast per block row (-13 %; with the next row's loads issued ahead of the stores -30 %: a warp
 // per block row serialises A / warps row trips), two blocks in flight per trip (-5 %).  All three also slowed the
-// launches whose rank-2 pass is negligible (8-landmark tiles): the kernel's hot path is ~65 KB of SASS walked by 4-10 CTAs per
+// launches whose rank-2 pass is negligible (8-landmark tiles): the kernel's hot path is ~60 KB of SASS walked by 4-12 CTAs per
 // SM in different phases, and what grows it pays in instruction fetch (stall_no_instruction 0.6 warps per issue).
+__device__ __forceinline__ float sqrt_approx(const float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 template <int NT>
 __device__ __forceinline__ void ekf_rank2_flat(const EkfSmem& s, const int ps2, const int A /* live block rows */) {
-    const int Lc = A + 1;                           // combined row length (blocks)
-    const int Q = (A + 1) >> 1;                     // combined rows
-    const int tid = threadIdx.x;
-    // tid / Lc and NT / Lc by one reciprocal: inv = floor(65536 / Lc) + 1 gives floor(v / Lc) = (v inv) >> 16 exactly while
-    // v Lc < 65536 (v <= 512 threads, Lc <= 120); the float quotient truncates to the exact floor (65536 / Lc is either an
-    // integer or at least 1 / Lc away from one).  Two integer divisions per thread and update were 3.5 % of the kernel's
-    // instructions on mid-size tiles.
-    const int inv = __float2int_rz(65536.0f / (float)Lc) + 1;
-    int q = (tid * inv) >> 16, p = tid - q * Lc;
-    const int dq = (NT * inv) >> 16, dp = NT - dq * Lc;
+    const int words = (A * (A + 1)) >> 1;           // 16-byte words per plane
     const double2* K2 = reinterpret_cast<const double2*>(s.K);
     const double2* H02 = reinterpret_cast<const double2*>(s.H0);
     const double2* H12 = reinterpret_cast<const double2*>(s.H1);
     double2* P0 = reinterpret_cast<double2*>(s.P);
     double2* P1 = reinterpret_cast<double2*>(s.P + ps2);
-    while (q < Q) {
-        const int split = A - q;
-        const bool first = p < split;
-        const int a = first ? (A - 1 - q) : q;
-        const int bc = first ? p : p - split;
-        if (first || (A - 1 - q != q)) {             // the self-paired middle block row is walked once
-            const int tb = ((a * (a + 1)) >> 1) + bc;
-            const double2 klo = K2[2 * a], khi = K2[2 * a + 1];
-            const double2 h0 = H02[bc], h1 = H12[bc];
-            double2 p0 = P0[tb], p1 = P1[tb];
-            ekf_rank2_block(p0, p1, klo, khi, h0, h1);
-            P0[tb] = p0; P1[tb] = p1;
-        }
-        p += dp; q += dq;
-        if (p >= Lc) { p -= Lc; ++q; }
+    for (int t = threadIdx.x; t < words; t += NT) {
+        const int a = __float2int_rz((sqrt_approx((float)(8 * t) + 1.5f) - 1.0f) * 0.5f);
+        const int bc = t - ((a * (a + 1)) >> 1);
+        const double2 klo = K2[2 * a], khi = K2[2 * a + 1];
+        const double2 h0 = H02[bc], h1 = H12[bc];
+        double2 p0 = P0[t], p1 = P1[t];
+        ekf_rank2_block(p0, p1, klo, khi, h0, h1);
+        P0[t] = p0; P1[t] = p1;
     }
 }
+
 // ---- one reference EKF::update on the shared-memory-resident filter, executed by NT threads (threadIdx.x < NT)
 // that synchronise through Sync.  On entry (all visible): s.P / s.x / s.xs (= s.x) / s.ids hold the committed filter
 // with M landmarks, s.meas the message, s.sc the predict scalars, and -- known-ID mode -- s.assoc / s.iscr[IS_DEAD]
