@@ -984,10 +984,10 @@ static cudaError_t launch_sweep_t(const BatchState& b, const FilterConst& fc, co
     const int occ[5] = {sweep_occupancy<1, REPLAY>(smem), sweep_occupancy<2, REPLAY>(smem), sweep_occupancy<3, REPLAY>(smem),
                         sweep_occupancy<4, REPLAY>(smem), sweep_occupancy<8, REPLAY>(smem)};
     // Filter warps per instance by tile size.  Measured per chunk on B200 (4096 instances, profiles/r02p_sweep_chunks.txt): up
-    // to ~20 landmarks one warp with 10 instances per SM (the barrier file allows 64 / 6) wins, to ~38 two warps x 8 (7), to ~42
-    // three warps x 6, beyond it four warps x 4 (the rank-2 pass grows with n^2 and wants lanes; residency stops paying once the
+    // to ~20 landmarks one warp with 10 instances per SM (the barrier file allows 64 / 6) wins, to ~38 two warps x 8 (7), to ~46
+    // three warps x 6 (5), beyond it four warps x 4 (the rank-2 pass grows with n^2 and wants lanes; residency stops paying once the
     // shared-memory pipe is ~3/4 busy).  A batch that fits the SMs at a wider CTA takes the wider CTA.
-    int best = L.cap_lm <= 20 ? 0 : L.cap_lm <= 38 ? 1 : L.cap_lm <= 42 ? 2 : 3;
+    int best = L.cap_lm <= 20 ? 0 : L.cap_lm <= 38 ? 1 : occ[2] >= 5 ? 2 : 3;       // (three warps while five such CTAs fit, ~46 landmarks)
     const int sms_ = device_sm_count();
     while (best < 3 && occ[best + 1] > 0 && b.batch <= sms_ * occ[best + 1]) ++best;
     if (occ[best] <= 0) { best = 0; for (int k = 1; k < 5; ++k) if (occ[k] >= occ[best]) best = k; }
