@@ -198,7 +198,8 @@ __device__ __forceinline__ double2 ekf_gain_row(const double h0, const double h1
 // Measured and rejected (B200, configs[1], same launches otherwise): 2 x 2 super-blocks per thread (half the
 // operand loads and index arithmetic, but 32-byte lane strides = two-way bank conflicts: -18 %), column strips with H P in
 // registers and one K broadcast per block row (-13 %; with the next row's loads issued ahead of the stores -30 %: a warp
-// per block row serialises A / warps row trips), two blocks in flight per trip (-5 %).  All three also slowed the
+// per block row serialises A / warps row trips), two blocks in flight per trip (-5 %; as vertical pairs (a, bc), (a + 1, bc) that
+// share the H P operand on top of the storage-order walk: -3 %).  All three also slowed the
 // launches whose rank-2 pass is negligible (8-landmark tiles): the kernel's hot path is ~60 KB of SASS walked by 4-12 CTAs per
 // SM in different phases, and what grows it pays in instruction fetch (stall_no_instruction 0.6 warps per issue).
 __device__ __forceinline__ float sqrt_approx(const float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -221,36 +222,6 @@ __device__ __forceinline__ void ekf_rank2_flat(const EkfSmem& s, const int ps2, 
     }
 }
 
-#ifdef EKF_VPAIR
-// A/B variant (scripts/build_variant.sh -DEKF_VPAIR): a thread takes the blocks (a, bc) and (a + 1, bc) of a DOUBLE block row
-// (a = 2 d) together: H P of the column is fetched once for both, the two K rows are broadcasts, the lanes of a warp still walk
-// consecutive words of both rows.  Item u of double row d is column bc = u - d (d + 1), d = floor((sqrt(4 u + 1.5) - 1) / 2)
-// (approximate square root, exact truncation: same argument as above); column 2 d + 1 exists in the lower row only.
-template <int NT>
-__device__ __forceinline__ void ekf_rank2_vpair(const EkfSmem& s, const int ps2, const int A) {
-    const int D = (A + 1) >> 1, items = D * (D + 1);
-    const double2* K2 = reinterpret_cast<const double2*>(s.K);
-    const double2* H02 = reinterpret_cast<const double2*>(s.H0);
-    const double2* H12 = reinterpret_cast<const double2*>(s.H1);
-    double2* P0 = reinterpret_cast<double2*>(s.P);
-    double2* P1 = reinterpret_cast<double2*>(s.P + ps2);
-    for (int u = threadIdx.x; u < items; u += NT) {
-        const int d = __float2int_rz((sqrt_approx((float)(4 * u) + 1.5f) - 1.0f) * 0.5f);
-        const int bc = u - d * (d + 1);
-        const int a = 2 * d;
-        const bool up = bc <= a, lo = a + 1 < A;
-        const int t0 = d * (2 * d + 1) + (up ? bc : 0);
-        const int t1 = lo ? d * (2 * d + 1) + a + 1 + bc : t0;
-        const double2 h0 = H02[bc], h1 = H12[bc];
-        const double2 ka0 = K2[2 * a], ka1 = K2[2 * a + 1], kb0 = K2[2 * a + 2], kb1 = K2[2 * a + 3];
-        double2 p0 = P0[t0], p1 = P1[t0], q0 = P0[t1], q1 = P1[t1];
-        ekf_rank2_block(p0, p1, ka0, ka1, h0, h1);
-        ekf_rank2_block(q0, q1, kb0, kb1, h0, h1);
-        if (up) { P0[t0] = p0; P1[t0] = p1; }
-        if (lo) { P0[t1] = q0; P1[t1] = q1; }
-    }
-}
-#endif
 // ---- one reference EKF::update on the shared-memory-resident filter, executed by NT threads (threadIdx.x < NT)
 // that synchronise through Sync.  On entry (all visible): s.P / s.x / s.xs (= s.x) / s.ids hold the committed filter
 // with M landmarks, s.meas the message, s.sc the predict scalars, and -- known-ID mode -- s.assoc / s.iscr[IS_DEAD]
@@ -439,11 +410,7 @@ __device__ __forceinline__ bool ekf_core(const FilterConst& fc, const EkfSmem& s
                 }
             }
             // -- P -= K (H P), :140, on the lower triangle
-#ifdef EKF_VPAIR
-            ekf_rank2_vpair<NT>(s, ps2, 2 + M);
-#else
             ekf_rank2_flat<NT>(s, ps2, 2 + M);
-#endif
             Sync::sync();
         } else {
             // -------- landmark insertion, :141-173: one new block row (padded rows np, np+1)
