@@ -9,7 +9,7 @@ for round in 1 2; do
 for v in intree _ab/*.so; do
   n=$(basename $v .so)
   if [ "$v" != intree ]; then cp $v $L; else cp $O/orig.so $L; fi
-  echo "$n: $(timeout 300 python scripts/sweep_chunks.py 0 2>/dev/null | head -1 | cut -c1-60)" | tee -a $O/ab.txt
+  echo "$n: $(timeout 300 python scripts/sweep_chunks.py 0 2>/dev/null | head -1 | cut -c1-175)" | tee -a $O/ab.txt
 done
 done
 cp $O/orig.so $L; rm -f $O/orig.so
